@@ -1,0 +1,418 @@
+// cct_deflate.cu — bit-exact zlib-1.3 level-9 `compress2` on the GPU, one zlib stream per image payload.
+//
+// Replaces `zlib.compress(data, level = 9)` (reference src/codec/core.py:340).  Stages (see
+// deflate_core.cuh for the decomposition and SURVEY.md Appendix B for the algorithm being matched):
+//   k_chains       hash-chain links for every position (warp per stream, head table in shared memory)
+//   k_probe        cold-start longest_match over the first kProbeK chain entries, one thread per position
+//   k_parse        deflate_slow's lazy state machine as a walk over the probe table (per stream)
+//   k_adler        Adler-32 of the payload (CTA per stream)
+//   k_block_build  per 16383-symbol block: histograms, build_tree x3, block-type choice, header bits
+//   k_layout       bit offsets of the blocks of each stream, stream length, zlib header/trailer
+//   k_pack         Huffman/extra bits of every symbol, placed by a prefix sum of code lengths
+//   k_offsets / k_copy   .cct header + stream -> caller's arena at scanned offsets
+#include <cuda_runtime.h>
+
+#include "cct_kernels.h"
+#include "deflate_core.cuh"
+
+namespace cct {
+
+constexpr int kProbeK = 32;
+
+static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+size_t deflate_ws_bytes(int B, int64_t max_len) {
+    DeflateWs ws;
+    return deflate_ws_carve(&ws, nullptr, B, max_len);
+}
+
+size_t deflate_ws_carve(DeflateWs *ws, void *mem, int B, int64_t max_len) {
+    char *p = (char *)mem;
+    size_t used = 0;
+    auto take = [&](size_t bytes) { void *r = p ? p + used : nullptr; used += (size_t)align_up((int64_t)bytes, 256); return r; };
+    ws->stride = align_up(max_len + 16, 16);
+    ws->max_blocks = (int)(max_len / kSymEnd + 2);
+    ws->dist16 = (uint16_t *)take((size_t)B * ws->stride * sizeof(uint16_t));
+    ws->mtab = (uint32_t *)take((size_t)B * ws->stride * sizeof(uint32_t));
+    ws->syms = (uint32_t *)take((size_t)B * ws->stride * sizeof(uint32_t));
+    ws->blk_end = (int32_t *)take((size_t)B * ws->max_blocks * sizeof(int32_t));
+    ws->nsym = (int32_t *)take((size_t)B * sizeof(int32_t));
+    ws->nflush = (int32_t *)take((size_t)B * sizeof(int32_t));
+    ws->adler = (uint32_t *)take((size_t)B * sizeof(uint32_t));
+    ws->desc = (BlockDesc *)take((size_t)B * ws->max_blocks * sizeof(BlockDesc));
+    return used;
+}
+
+// ------------------------------------------------------------------ k_chains
+// head[h] holds the low 16 bits of the latest position with hash h.  Entries are kept unambiguous by a
+// sweep every 8192 positions that re-parks everything older than 32767 at "49152 behind".
+constexpr int kHeadEntries = 32768;
+__global__ void __launch_bounds__(32) k_chains(const uint8_t *__restrict__ in, int64_t in_stride,
+                                               const int32_t *__restrict__ in_len, uint16_t *__restrict__ dist16,
+                                               int64_t stride) {
+    extern __shared__ uint16_t head[];
+    const int stream = blockIdx.x, lane = threadIdx.x;
+    const int n = in_len[stream];
+    const uint8_t *w = in + (int64_t)stream * in_stride;
+    uint16_t *d16 = dist16 + (int64_t)stream * stride;
+    uint32_t *head32 = reinterpret_cast<uint32_t *>(head);
+    for (int i = lane; i < kHeadEntries / 2; i += 32) head32[i] = 0x40004000u;  // (0 - 49152) & 0xFFFF
+    __syncwarp();
+    for (int base = 0; base < n; base += 32) {
+        if (base && (base & 8191) == 0) {
+            const uint32_t far = (uint32_t)(base - 49152) & 0xFFFFu;
+            for (int i = lane; i < kHeadEntries / 2; i += 32) {
+                uint32_t v = head32[i];
+                uint32_t lo = v & 0xFFFFu, hi = v >> 16;
+                if (((uint32_t)(base - lo) & 0xFFFFu) >= 32768u) lo = far;
+                if (((uint32_t)(base - hi) & 0xFFFFu) >= 32768u) hi = far;
+                head32[i] = lo | (hi << 16);
+            }
+            __syncwarp();
+        }
+        const int s = base + lane;
+        const bool valid = s >= 1 && s + 2 < n;  // position 0 doubles as NIL in zlib: never a match source
+        uint32_t h = 0x8000u | (uint32_t)lane;   // unique key for lanes that do not insert
+        if (valid) h = hash3(w + s);
+        if (base + 640 < n) asm volatile("prefetch.global.L1 [%0];" ::"l"(w + base + 512 + 4 * lane));
+        const unsigned peers = __match_any_sync(0xffffffffu, h);
+        const unsigned lower = peers & ((1u << lane) - 1u);
+        int dist = 0;
+        if (valid) {
+            if (lower) dist = lane - (31 - __clz((int)lower));
+            else {
+                uint32_t d = (uint32_t)(s - head[h]) & 0xFFFFu;
+                dist = (d >= 1u && d < 32768u) ? (int)d : 0;
+            }
+        }
+        __syncwarp();
+        if (valid && (peers >> lane) == 1u) head[h] = (uint16_t)s;
+        if (s < n) d16[s] = (uint16_t)dist;
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------ k_probe
+__global__ void __launch_bounds__(256) k_probe(const uint8_t *__restrict__ in, int64_t in_stride,
+                                               const int32_t *__restrict__ in_len, const uint16_t *__restrict__ dist16,
+                                               uint32_t *__restrict__ mtab, int64_t stride) {
+    const int stream = blockIdx.y;
+    const int n = in_len[stream];
+    const int s = blockIdx.x * 256 + threadIdx.x;
+    if (s >= n) return;
+    LzView v{in + (int64_t)stream * in_stride, dist16 + (int64_t)stream * stride, n};
+    mtab[(int64_t)stream * stride + s] = match_probe(v, s, kProbeK);
+}
+
+// ------------------------------------------------------------------ k_parse
+__global__ void __launch_bounds__(32) k_parse(const uint8_t *__restrict__ in, int64_t in_stride,
+                                              const int32_t *__restrict__ in_len, const uint16_t *__restrict__ dist16,
+                                              const uint32_t *__restrict__ mtab, uint32_t *__restrict__ syms, int64_t stride,
+                                              int32_t *__restrict__ blk_end, int max_blocks, int32_t *__restrict__ nsym,
+                                              int32_t *__restrict__ nflush) {
+    const int stream = blockIdx.x;
+    if (threadIdx.x != 0) return;
+    LzView v{in + (int64_t)stream * in_stride, dist16 + (int64_t)stream * stride, in_len[stream]};
+    int nf = 0;
+    int ns = parse_stream(v, mtab + (int64_t)stream * stride, syms + (int64_t)stream * stride,
+                          blk_end + (int64_t)stream * max_blocks, &nf);
+    nsym[stream] = ns;
+    nflush[stream] = nf;
+}
+
+// ------------------------------------------------------------------ k_adler
+__global__ void __launch_bounds__(256) k_adler(const uint8_t *__restrict__ in, int64_t in_stride,
+                                               const int32_t *__restrict__ in_len, uint32_t *__restrict__ adler) {
+    const int stream = blockIdx.x, tid = threadIdx.x;
+    const int n = in_len[stream];
+    const uint8_t *w = in + (int64_t)stream * in_stride;
+    // A = 1 + sum d_i ; B = n + sum d_i * (n - i)   (mod 65521)
+    unsigned long long sa = 0, sb = 0;
+    for (int i = tid; i < n; i += 256) {
+        unsigned long long d = w[i];
+        sa += d; sb += d * (unsigned long long)(n - i);
+    }
+    __shared__ unsigned long long ra[8], rb[8];
+    for (int o = 16; o; o >>= 1) { sa += __shfl_xor_sync(0xffffffffu, sa, o); sb += __shfl_xor_sync(0xffffffffu, sb, o); }
+    if ((tid & 31) == 0) { ra[tid >> 5] = sa; rb[tid >> 5] = sb % 65521ull; }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long A = 1, Bv = (unsigned long long)n;
+        for (int k = 0; k < 8; k++) { A += ra[k]; Bv += rb[k]; }
+        adler[stream] = (uint32_t)(((Bv % 65521ull) << 16) | (A % 65521ull));
+    }
+}
+
+// ------------------------------------------------------------------ k_block_build
+struct BlockBuildSmem {
+    BlockWork wk;
+    BlockDesc desc;
+    uint32_t lh[kLCodes + 2];
+    uint32_t dh[kDCodes + 2];
+};
+
+__global__ void __launch_bounds__(32) k_block_build(const uint32_t *__restrict__ syms, int64_t stride,
+                                                    const int32_t *__restrict__ blk_end, int max_blocks,
+                                                    const int32_t *__restrict__ nsym, const int32_t *__restrict__ nflush,
+                                                    const int32_t *__restrict__ in_len, BlockDesc *__restrict__ desc) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BlockBuildSmem &sm = *reinterpret_cast<BlockBuildSmem *>(smem_raw);
+    const int stream = blockIdx.y, blk = blockIdx.x, lane = threadIdx.x;
+    const int nf = nflush[stream];
+    if (blk > nf) return;
+    uint32_t *z = reinterpret_cast<uint32_t *>(&sm);
+    for (int i = lane; i < (int)(sizeof(BlockBuildSmem) / 4); i += 32) z[i] = 0;
+    __syncwarp();
+    const int32_t *be = blk_end + (int64_t)stream * max_blocks;
+    const uint32_t sym_begin = (uint32_t)blk * kSymEnd;
+    const uint32_t ns = blk < nf ? (uint32_t)kSymEnd : (uint32_t)(nsym[stream] - nf * kSymEnd);
+    const uint32_t pos_begin = blk == 0 ? 0u : (uint32_t)be[blk - 1];
+    const uint32_t pos_end = blk < nf ? (uint32_t)be[blk] : (uint32_t)in_len[stream];
+    const uint32_t *sy = syms + (int64_t)stream * stride + sym_begin;
+    for (uint32_t i = lane; i < ns; i += 32) {
+        uint32_t s = sy[i];
+        if (sym_dist(s) == 0) atomicAdd(&sm.lh[sym_lc(s)], 1u);
+        else { atomicAdd(&sm.lh[257 + len_code(sym_lc(s))], 1u); atomicAdd(&sm.dh[dist_code(sym_dist(s) - 1)], 1u); }
+    }
+    __syncwarp();
+    for (int i = lane; i < kLCodes; i += 32) sm.wk.lt.freq[i] = (uint16_t)sm.lh[i];
+    if (lane < kDCodes) sm.wk.dt.freq[lane] = (uint16_t)sm.dh[lane];
+    __syncwarp();
+    if (lane == 0) {
+        sm.wk.lt.freq[256] = 1;
+        sm.desc.sym_begin = sym_begin; sm.desc.nsym = ns;
+        sm.desc.pos_begin = pos_begin; sm.desc.stored_len = pos_end - pos_begin;
+        sm.desc.last = blk == nf;
+        build_block(sm.wk, &sm.desc);
+    }
+    __syncwarp();
+    uint32_t *dst = reinterpret_cast<uint32_t *>(desc + (int64_t)stream * max_blocks + blk);
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(&sm.desc);
+    for (int i = lane; i < (int)(sizeof(BlockDesc) / 4); i += 32) dst[i] = src[i];
+}
+
+// ------------------------------------------------------------------ k_layout
+__global__ void k_layout(BlockDesc *__restrict__ desc, int max_blocks, const int32_t *__restrict__ nflush,
+                         const uint32_t *__restrict__ adler, uint8_t *__restrict__ out, int64_t out_stride,
+                         int32_t *__restrict__ out_len, int B) {
+    int stream = blockIdx.x * blockDim.x + threadIdx.x;
+    if (stream >= B) return;
+    BlockDesc *d = desc + (int64_t)stream * max_blocks;
+    uint64_t bit = 16;
+    int nblk = nflush[stream] + 1;
+    for (int b = 0; b < nblk; b++) {
+        d[b].bit_start = bit;
+        if (d[b].type == 0) {
+            bit += 3;
+            bit = (bit + 7) & ~7ull;
+            bit += 32 + 8ull * d[b].stored_len;
+        } else {
+            bit += d[b].hdr_bits + d[b].body_bits;
+        }
+    }
+    bit = (bit + 7) & ~7ull;
+    uint8_t *o = out + (int64_t)stream * out_stride;
+    int64_t len = (int64_t)(bit >> 3);
+    o[0] = 0x78; o[1] = 0xDA;  // CMF/FLG for wbits 15, level 9
+    uint32_t ad = adler[stream];
+    o[len] = (uint8_t)(ad >> 24); o[len + 1] = (uint8_t)(ad >> 16); o[len + 2] = (uint8_t)(ad >> 8); o[len + 3] = (uint8_t)ad;
+    out_len[stream] = (int32_t)(len + 4);
+}
+
+// ------------------------------------------------------------------ k_pack
+__device__ __forceinline__ void or_bits(uint32_t *out32, uint64_t bitpos, uint32_t value, int nb) {
+    uint64_t word = bitpos >> 5;
+    int off = (int)(bitpos & 31);
+    atomicOr(out32 + word, value << off);
+    if (off + nb > 32) atomicOr(out32 + word + 1, value >> (32 - off));
+}
+
+struct BitSink {  // per-thread streaming writer: first and last word are OR-ed, interior words stored
+    uint32_t *wp; unsigned long long acc; int fill; bool first;
+    __device__ __forceinline__ void put(uint32_t v, int nb) {
+        acc |= (unsigned long long)v << fill;
+        fill += nb;
+        if (fill >= 32) {
+            uint32_t word = (uint32_t)acc;
+            if (first) { atomicOr(wp, word); first = false; } else *wp = word;
+            wp++; acc >>= 32; fill -= 32;
+        }
+    }
+    __device__ __forceinline__ void finish() { if (fill > 0) atomicOr(wp, (uint32_t)acc); }
+};
+
+constexpr int kPackThreads = 256;
+__global__ void __launch_bounds__(kPackThreads) k_pack(const uint8_t *__restrict__ in, int64_t in_stride,
+                                                       const BlockDesc *__restrict__ desc, int max_blocks,
+                                                       const int32_t *__restrict__ nflush, const uint32_t *__restrict__ syms,
+                                                       int64_t stride, uint8_t *__restrict__ out, int64_t out_stride) {
+    const int stream = blockIdx.y, blk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (blk > nflush[stream]) return;
+    const BlockDesc &d = desc[(int64_t)stream * max_blocks + blk];
+    uint32_t *out32 = reinterpret_cast<uint32_t *>(out + (int64_t)stream * out_stride);
+    const uint64_t bit_start = d.bit_start;
+    const int hdr_bits = (int)d.hdr_bits;
+    if (wid == 0) {
+        for (int i = lane; i * 32 < hdr_bits; i += 32) {
+            int nb = hdr_bits - i * 32; if (nb > 32) nb = 32;
+            or_bits(out32, bit_start + 32ull * i, d.hdr[i], nb);
+        }
+    }
+    if (d.type == 0) {  // stored block: LEN, ~LEN, raw bytes at the next byte boundary
+        uint8_t *o = out + (int64_t)stream * out_stride + (((bit_start + 3) + 7) >> 3);
+        const uint32_t len = d.stored_len;
+        if (tid == 0) { o[0] = (uint8_t)len; o[1] = (uint8_t)(len >> 8); o[2] = (uint8_t)~len; o[3] = (uint8_t)(~len >> 8); }
+        const uint8_t *src = in + (int64_t)stream * in_stride + d.pos_begin;
+        for (uint32_t i = tid; i < len; i += kPackThreads) o[4 + i] = src[i];
+        return;
+    }
+    __shared__ uint16_t lcode[kLCodes + 2], dcode[kDCodes + 2];
+    __shared__ uint8_t llen[kLCodes + 2], dlen[kDCodes + 2];
+    __shared__ uint32_t warp_sum[kPackThreads / 32];
+    for (int i = tid; i < kLCodes + 2; i += kPackThreads) { lcode[i] = d.lcode[i]; llen[i] = d.llen[i]; }
+    if (tid < kDCodes + 2) { dcode[tid] = d.dcode[tid]; dlen[tid] = d.dlen[tid]; }
+    __syncthreads();
+    const int ns = (int)d.nsym;
+    const int per = (ns + kPackThreads - 1) / kPackThreads;
+    const int i0 = min(ns, tid * per), i1 = min(ns, i0 + per);
+    const uint32_t *sy = syms + (int64_t)stream * stride + d.sym_begin;
+    uint32_t bits = 0;
+    for (int i = i0; i < i1; i++) bits += (uint32_t)sym_nbits(sy[i], llen, dlen);
+    uint32_t incl = bits;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sum[wid] = incl;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (int w = 0; w < wid; w++) woff += warp_sum[w];
+    const uint64_t start = bit_start + (uint64_t)hdr_bits + woff + incl - bits;
+    if (i1 > i0) {
+        BitSink sink{out32 + (start >> 5), 0ull, (int)(start & 31), true};
+        for (int i = i0; i < i1; i++) {
+            int nb;
+            unsigned long long b = sym_bits(sy[i], lcode, llen, dcode, dlen, &nb);
+            if (nb > 32) { sink.put((uint32_t)b, 32); sink.put((uint32_t)(b >> 32), nb - 32); }
+            else sink.put((uint32_t)b, nb);
+        }
+        sink.finish();
+    }
+    if (tid == 0)  // END_BLOCK closes the block
+        or_bits(out32, bit_start + (uint64_t)hdr_bits + d.body_bits - llen[256], lcode[256], llen[256]);
+}
+
+void launch_deflate(const uint8_t *in, int64_t in_stride, const int32_t *in_len, int B, int64_t max_len, uint8_t *out,
+                    int64_t out_stride, int32_t *out_len, const DeflateWs &ws, cudaStream_t st) {
+    if (B == 0) return;
+    static bool attr_done = false;
+    const int chain_smem = kHeadEntries * (int)sizeof(uint16_t);
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_chains, cudaFuncAttributeMaxDynamicSharedMemorySize, chain_smem);
+        cudaFuncSetAttribute(k_block_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlockBuildSmem));
+        attr_done = true;
+    }
+    { CCT_KERNEL(k_chains, st);
+    k_chains<<<B, 32, chain_smem, st>>>(in, in_stride, in_len, ws.dist16, ws.stride);
+    }
+    dim3 gp((unsigned)((max_len + 255) / 256), (unsigned)B);
+    { CCT_KERNEL(k_probe, st);
+    k_probe<<<gp, 256, 0, st>>>(in, in_stride, in_len, ws.dist16, ws.mtab, ws.stride);
+    }
+    { CCT_KERNEL(k_parse, st);
+    k_parse<<<B, 32, 0, st>>>(in, in_stride, in_len, ws.dist16, ws.mtab, ws.syms, ws.stride, ws.blk_end, ws.max_blocks,
+                              ws.nsym, ws.nflush);
+    }
+    { CCT_KERNEL(k_adler, st);
+    k_adler<<<B, 256, 0, st>>>(in, in_stride, in_len, ws.adler);
+    }
+    dim3 gb((unsigned)ws.max_blocks, (unsigned)B);
+    { CCT_KERNEL(k_block_build, st);
+    k_block_build<<<gb, 32, sizeof(BlockBuildSmem), st>>>(ws.syms, ws.stride, ws.blk_end, ws.max_blocks, ws.nsym, ws.nflush,
+                                                          in_len, ws.desc);
+    }
+    { CCT_KERNEL(k_layout, st);
+    k_layout<<<(B + 127) / 128, 128, 0, st>>>(ws.desc, ws.max_blocks, ws.nflush, ws.adler, out, out_stride, out_len, B);
+    }
+    { CCT_KERNEL(k_pack, st);
+    k_pack<<<gb, kPackThreads, 0, st>>>(in, in_stride, ws.desc, ws.max_blocks, ws.nflush, ws.syms, ws.stride, out, out_stride);
+    }
+}
+
+// ------------------------------------------------------------------ assembly into the caller's arena
+__global__ void __launch_bounds__(1024) k_offsets(const int32_t *__restrict__ body_len, int B, int64_t *__restrict__ offsets,
+                                                  int first) {
+    __shared__ long long warp_sum[32];
+    __shared__ long long carry;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry = offsets[first];
+    __syncthreads();
+    for (int base = 0; base < B; base += 1024) {
+        int i = base + tid;
+        long long v = i < B ? (long long)kHeaderBytes + body_len[i] : 0;
+        long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_sum[wid] = incl;
+        __syncthreads();
+        long long woff = 0, total = 0;
+        for (int w = 0; w < 32; w++) { if (w < wid) woff += warp_sum[w]; total += warp_sum[w]; }
+        if (i < B) offsets[first + 1 + i] = carry + woff + incl;
+        __syncthreads();
+        if (tid == 0) carry += total;
+        __syncthreads();
+    }
+}
+
+constexpr int kCopyBytes = 4096;  // bytes per CTA
+__global__ void __launch_bounds__(256) k_copy(const uint8_t *__restrict__ body, int64_t body_stride,
+                                              const int32_t *__restrict__ body_len, int rows, int cols, uint32_t flags,
+                                              uint8_t *__restrict__ arena, int64_t arena_cap,
+                                              const int64_t *__restrict__ offsets, int first, uint32_t *__restrict__ status) {
+    const int img = blockIdx.y;
+    const int len = body_len[img];
+    const int64_t lo = offsets[first + img], hi = offsets[first + img + 1];
+    if (hi > arena_cap) {
+        if (blockIdx.x == 0 && threadIdx.x == 0 && status) status[img] |= 2u;  // CCT_ST_CAPACITY
+        return;
+    }
+    const int64_t start = (int64_t)blockIdx.x * kCopyBytes;
+    if (start >= len) return;
+    uint8_t *dst = arena + lo;
+    if (blockIdx.x == 0 && threadIdx.x < kHeaderBytes) {  // core.py:193-210
+        const int t = threadIdx.x;
+        uint8_t hb;
+        switch (t) {
+            case 0: hb = 'p'; break; case 1: hb = 'a'; break; case 2: hb = 'c'; break; case 3: hb = 't'; break;
+            case 4: hb = (uint8_t)(rows >> 8); break; case 5: hb = (uint8_t)rows; break;
+            case 6: hb = (uint8_t)(cols >> 8); break; case 7: hb = (uint8_t)cols; break;
+            case 8: hb = 1; break; case 9: hb = 2; break;
+            case 10: hb = (flags & 1u) != 0; break; case 11: hb = (flags & 2u) != 0; break;
+            default: hb = (flags & 4u) != 0; break;
+        }
+        dst[t] = hb;
+    }
+    const uint8_t *src = body + (int64_t)img * body_stride;
+    const int64_t end = min((int64_t)len, start + kCopyBytes);
+    for (int64_t i = start + threadIdx.x; i < end; i += 256) dst[kHeaderBytes + i] = src[i];
+}
+
+void launch_assemble(const uint8_t *body, int64_t body_stride, const int32_t *body_len, int B, int rows, int cols,
+                     uint32_t flags, uint8_t *arena, int64_t arena_cap, int64_t *offsets, int first, uint32_t *status,
+                     cudaStream_t st) {
+    if (B == 0) return;
+    { CCT_KERNEL(k_offsets, st);
+    k_offsets<<<1, 1024, 0, st>>>(body_len, B, offsets, first);
+    }
+    dim3 g((unsigned)((body_stride + kCopyBytes - 1) / kCopyBytes), (unsigned)B);
+    { CCT_KERNEL(k_copy, st);
+    k_copy<<<g, 256, 0, st>>>(body, body_stride, body_len, rows, cols, flags, arena, arena_cap, offsets, first,
+                              status ? status + first : nullptr);
+    }
+}
+
+}  // namespace cct

@@ -1,0 +1,77 @@
+// cct_kernels.h — launcher prototypes shared by the .cu files and the C-ABI layer (cct_api.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "cct_common.cuh"
+
+namespace cct {
+
+struct BlockDesc;
+
+// ---- launch accounting (cct_api.cu): every kernel launch is counted; with profiling on it is also bracketed
+// by CUDA events on its own stream so bench.py can report per-kernel device time from the timed region.
+void prof_before(const char *name, cudaStream_t st);
+void prof_after(cudaStream_t st);
+struct ProfScope {
+    cudaStream_t st;
+    ProfScope(const char *name, cudaStream_t s) : st(s) { prof_before(name, s); }
+    ~ProfScope() { prof_after(st); }
+};
+#define CCT_KERNEL(name, st) ::cct::ProfScope prof_scope_##name(#name, st)
+
+// ---- cct_encode.cu
+void launch_curve_pow2(int32_t *d_order, int n, cudaStream_t st);
+void launch_iota(int32_t *d_order, int64_t n, cudaStream_t st);
+void launch_gather_stats(const uint16_t *px, const int32_t *order, uint16_t *hv, uint8_t *info, int B, int64_t n_px,
+                         cudaStream_t st);
+void launch_mesh(const uint16_t *hv, const uint8_t *info, uint8_t *jump, uint8_t *taken, int32_t *stats, int B,
+                 int64_t n_px, cudaStream_t st);
+void launch_emit(const uint16_t *hv, const uint8_t *jump, const uint8_t *taken, uint8_t *payload, int64_t pstride,
+                 int32_t *plen, uint32_t *status, int32_t *stats, int B, int64_t n_px, cudaStream_t st);
+
+// ---- cct_deflate.cu
+struct DeflateWs {  // device scratch for one pass over B streams of capacity max_len
+    uint16_t *dist16;    // [B][stride]
+    uint32_t *mtab;      // [B][stride]
+    uint32_t *syms;      // [B][stride]
+    int32_t *blk_end;    // [B][max_blocks]
+    int32_t *nsym;       // [B]
+    int32_t *nflush;     // [B]
+    uint32_t *adler;     // [B]
+    BlockDesc *desc;     // [B][max_blocks]
+    int64_t stride;      // elements per stream in dist16/mtab/syms (>= max_len, multiple of 16)
+    int max_blocks;
+};
+size_t deflate_ws_bytes(int B, int64_t max_len);
+// carve `ws` out of raw memory; returns bytes used
+size_t deflate_ws_carve(DeflateWs *ws, void *mem, int B, int64_t max_len);
+// zlib streams of in[i*in_stride .. +in_len[i]) -> out[i*out_stride ..], lengths -> out_len[i].
+// `out` must be zero-filled by the caller for out_stride*B bytes (the bit packer ORs into it).
+void launch_deflate(const uint8_t *in, int64_t in_stride, const int32_t *in_len, int B, int64_t max_len, uint8_t *out,
+                    int64_t out_stride, int32_t *out_len, const DeflateWs &ws, cudaStream_t st);
+
+// ---- cct_decode.cu
+int launch_inflate(const uint8_t *in, const int64_t *in_off, int64_t in_stride, const int32_t *in_len, int hdr_skip,
+                   int B, uint8_t *out, int64_t out_stride, int32_t *out_len, uint32_t *status, cudaStream_t st);
+struct DecodeWs {
+    uint8_t *payload;  // [B][pstride]
+    int32_t *plen;     // [B]
+    uint16_t *vals;    // [B][n_px]
+    uint8_t *jflag;    // [B][nb]
+    int32_t *slotA, *slotB;  // [B][nb]
+    uint8_t *fl;       // [B] transform flags from each header
+    int64_t pstride;
+};
+size_t decode_ws_bytes(int B, int64_t n_px);
+size_t decode_ws_carve(DecodeWs *ws, void *mem, int B, int64_t n_px);
+void launch_decode(const uint8_t *files, const int64_t *offsets, int B, int rows, int cols, const int32_t *order_fractal,
+                   uint16_t *px, uint32_t *status, const DecodeWs &ws, cudaStream_t st);
+
+// ---- assembly (cct_deflate.cu)
+// file lengths -> offsets[first+1 .. first+B] (running from offsets[first]) and copy header + body into the arena
+void launch_assemble(const uint8_t *body, int64_t body_stride, const int32_t *body_len, int B, int rows, int cols,
+                     uint32_t flags, uint8_t *arena, int64_t arena_cap, int64_t *offsets, int first, uint32_t *status,
+                     cudaStream_t st);
+
+}  // namespace cct

@@ -1,0 +1,444 @@
+// deflate_core.cuh — the scalar building blocks of the bit-exact zlib-1.3 level-9 encoder, written as
+// host/device functions so the CUDA kernels (cct_deflate.cu) and the CPU test harness
+// (tests/hostsim) run the very same code.
+//
+// What is restated: the reference's entropy stage is `zlib.compress(data, level = 9)`
+// (reference src/codec/core.py:340) = system libz 1.3 `deflate_slow` + `trees.c` (third-party, not in the
+// reference tree; algorithm recorded in SURVEY.md Appendix B).  The decomposition used here:
+//   1. hash chains are parse-independent (every position is inserted exactly once, in order), so
+//      `dist16[s]` = distance to the previous position with the same 3-byte hash is a pure function
+//      of the data (kernel k_chains);
+//   2. `match_probe` runs longest_match from a cold start (best = 2) over the first K chain entries
+//      for EVERY position in parallel and records (len, dist, complete?) in a table;
+//   3. `parse_stream` walks the table sequentially with zlib's lazy-evaluation state machine; where
+//      the probe was incomplete it falls back to `match_full`, the exact longest_match loop;
+//   4. `build_block` restates _tr_flush_block's tree construction and block-type choice;
+//   5. the symbol bits are then packed in parallel from the code tables.
+#pragma once
+#include "cct_common.cuh"
+
+namespace cct {
+
+// ------------------------------------------------------------------------------------------------
+// symbol / table encodings
+// ------------------------------------------------------------------------------------------------
+// mtab entry: bits 0..8 best length (0 = no match), bits 9..23 distance, bit 31 = probe incomplete
+constexpr uint32_t kProbeIncomplete = 0x80000000u;
+CCT_HD uint32_t mtab_pack(int len, int dist) { return (uint32_t)len | ((uint32_t)dist << 9); }
+CCT_HD int mtab_len(uint32_t e) { return (int)(e & 511u); }
+CCT_HD int mtab_dist(uint32_t e) { return (int)((e >> 9) & 32767u); }
+
+// LZ77 symbol: bits 0..7 literal byte or (len-3), bits 8..23 distance (0 = literal)
+CCT_HD uint32_t sym_pack(int lc, int dist) { return (uint32_t)lc | ((uint32_t)dist << 8); }
+CCT_HD int sym_lc(uint32_t s) { return (int)(s & 255u); }
+CCT_HD int sym_dist(uint32_t s) { return (int)(s >> 8); }
+
+CCT_HD uint32_t hash3(const uint8_t *p) {  // UPDATE_HASH x3 with hash_shift 5, 15-bit mask
+    return (((uint32_t)p[0] << 10) ^ ((uint32_t)p[1] << 5) ^ (uint32_t)p[2]) & 0x7FFFu;
+}
+
+// length code / extra bits of lc = len-3 (trees.c _length_code, base_length, extra_lbits)
+CCT_HD int len_code(int lc) {
+    if (lc < 8) return lc;
+    if (lc == 255) return 28;
+    int m = ilog2((uint32_t)lc);
+    return 4 * (m - 2) + 4 + ((lc >> (m - 2)) & 3);
+}
+CCT_HD int len_extra_bits(int code) { return (code < 8 || code == 28) ? 0 : (code >> 2) - 1; }
+// distance code / extra bits of d = dist-1 (trees.c _dist_code, base_dist, extra_dbits)
+CCT_HD int dist_code(int d) {
+    if (d < 4) return d;
+    int m = ilog2((uint32_t)d);
+    return 2 * m + ((d >> (m - 1)) & 1);
+}
+CCT_HD int dist_extra_bits(int code) { return code < 4 ? 0 : (code >> 1) - 1; }
+CCT_HD int bl_extra_bits(int code) { return code < 16 ? 0 : (code == 16 ? 2 : (code == 17 ? 3 : 7)); }
+
+CCT_HD uint32_t bit_reverse(uint32_t code, int len) {
+    uint32_t res = 0;
+    for (int i = 0; i < len; i++) { res = (res << 1) | (code & 1u); code >>= 1; }
+    return res;
+}
+// static trees (trees.c tr_static_init): literal/length lengths and bit-reversed codes
+CCT_HD int static_llen(int n) { return n <= 143 ? 8 : (n <= 255 ? 9 : (n <= 279 ? 7 : 8)); }
+CCT_HD uint32_t static_lcode(int n) {
+    uint32_t c = n <= 143 ? 0x30u + (uint32_t)n
+                          : (n <= 255 ? 0x190u + (uint32_t)(n - 144) : (n <= 279 ? (uint32_t)(n - 256) : 0xC0u + (uint32_t)(n - 280)));
+    return bit_reverse(c, static_llen(n));
+}
+
+// ------------------------------------------------------------------------------------------------
+// longest_match
+// ------------------------------------------------------------------------------------------------
+struct LzView {
+    const uint8_t *w;        // payload bytes
+    const uint16_t *dist16;  // chain links: distance to previous same-hash position, 0 = none / >= 32768
+    int n;                   // payload length
+};
+
+CCT_HD int match_extend(const uint8_t *a, const uint8_t *b, int from, int cap) {
+    int len = from;
+    while (len < cap && a[len] == b[len]) len++;
+    return len;
+}
+
+// Cold-start probe over at most K chain entries (deflate.c longest_match with best_len = 2).
+// The answer for any prev_length follows from it when the probe is complete: the search result is the
+// first-visited candidate attaining the maximum length.
+CCT_HD uint32_t match_probe(const LzView &v, int s, int K) {
+    int look = v.n - s;
+    if (look < kMinMatch) return 0;
+    int d0 = v.dist16[s];
+    if (d0 == 0 || d0 > kMaxDist) return 0;
+    int cap = look < kMaxMatch ? look : kMaxMatch;
+    const uint8_t *b = v.w + s;
+    int best = 2, bdist = 0, cur = s - d0;
+    for (int cnt = 1;; cnt++) {
+        const uint8_t *a = v.w + cur;
+        if (a[best] == b[best] && a[best - 1] == b[best - 1] && a[0] == b[0] && a[1] == b[1]) {
+            int len = match_extend(a, b, 2, cap);
+            if (len > best) {
+                best = len; bdist = s - cur;
+                if (len >= cap) break;
+            }
+        }
+        int dl = v.dist16[cur];
+        if (dl == 0) break;
+        cur -= dl;
+        if (s - cur >= kMaxDist) break;  // cur <= limit
+        if (cnt == K) return kProbeIncomplete;
+    }
+    return best >= kMinMatch ? mtab_pack(best, bdist) : 0;
+}
+
+// Exact longest_match for position s with the parser's prev_length (chain budget 4096, or 1024 once
+// prev_length >= good_length 32).  Requires: valid head, prev_len < 258, prev_len < look.
+// Returns the improved length (> prev_len) and its distance, or 0.
+CCT_HD int match_full(const LzView &v, int s, int prev_len, int *out_dist) {
+    int look = v.n - s;
+    int cap = look < kMaxMatch ? look : kMaxMatch;
+    const uint8_t *b = v.w + s;
+    int best = prev_len, bdist = 0, cur = s - v.dist16[s];
+    int chain = prev_len >= kGoodLen ? kChainGood : kChainFull;
+    do {
+        const uint8_t *a = v.w + cur;
+        if (a[best] == b[best] && a[best - 1] == b[best - 1] && a[0] == b[0] && a[1] == b[1]) {
+            int len = match_extend(a, b, 2, cap);
+            if (len > best) {
+                best = len; bdist = s - cur;
+                if (len >= cap) break;
+            }
+        }
+        int dl = v.dist16[cur];
+        if (dl == 0) break;
+        cur -= dl;
+        if (s - cur >= kMaxDist) break;
+    } while (--chain != 0);
+    *out_dist = bdist;
+    return best > prev_len ? best : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// deflate_slow as a walk over the probe table
+// ------------------------------------------------------------------------------------------------
+// Writes LZ77 symbols to syms[] and, for every in-loop flush (16383 symbols tallied), the payload
+// position at which the block ended to blk_end[].  Returns the number of symbols; *n_flush = number of
+// in-loop flushes.  The final block (last = 1) holds symbols [16383 * n_flush, nsym) and ends at n
+// (it may be empty, and the trailing literal never triggers a flush).
+CCT_HD int parse_stream(const LzView &v, const uint32_t *mtab, uint32_t *syms, int32_t *blk_end, int *n_flush) {
+    const int n = v.n;
+    int s = 0, match_len = 2, match_dist = 0, nsym = 0, nfl = 0, in_block = 0;
+    bool avail = false;
+    while (s < n) {
+        int look = n - s;
+        int prev_len = match_len, prev_dist = match_dist;
+        match_len = 2;
+        uint32_t e = look >= kMinMatch ? mtab[s] : 0u;
+        if (e != 0 && prev_len < kMaxMatch && prev_len < look) {
+            int ml = 0, md = 0;
+            if (e & kProbeIncomplete) ml = match_full(v, s, prev_len, &md);
+            else if (mtab_len(e) > prev_len) { ml = mtab_len(e); md = mtab_dist(e); }
+            if (ml == kMinMatch && md > kTooFar) ml = 0;
+            if (ml) { match_len = ml; match_dist = md; }
+        }
+        if (prev_len >= kMinMatch && match_len <= prev_len) {
+            syms[nsym++] = sym_pack(prev_len - kMinMatch, prev_dist);
+            s += prev_len - 1;
+            avail = false; match_len = 2;
+            if (++in_block == kSymEnd) { blk_end[nfl++] = s; in_block = 0; }
+        } else if (avail) {
+            syms[nsym++] = sym_pack(v.w[s - 1], 0);
+            if (++in_block == kSymEnd) { blk_end[nfl++] = s; in_block = 0; }
+            s++;
+        } else {
+            avail = true; s++;
+        }
+    }
+    if (avail) syms[nsym++] = sym_pack(v.w[n - 1], 0);
+    *n_flush = nfl;
+    return nsym;
+}
+
+// ------------------------------------------------------------------------------------------------
+// trees.c: build_tree / gen_bitlen / gen_codes / scan_tree / send_tree / block-type choice
+// ------------------------------------------------------------------------------------------------
+constexpr int kLCodes = 286, kDCodes = 30, kBLCodes = 19, kHeapSize = 2 * kLCodes + 1, kMaxBits = 15;
+constexpr int kHdrWords = 160;  // dynamic-block header bit string capacity (worst case 4498 bits)
+
+struct Tree {  // one Huffman tree under construction (ct_data with Freq/Dad/Len/Code split out)
+    uint16_t freq[kHeapSize];
+    uint16_t dad[kHeapSize];
+    uint16_t len[kHeapSize];
+    uint16_t code[kHeapSize];
+    int max_code;
+};
+
+struct SmallTree {  // distance (30 symbols) and bit-length (19 symbols) trees
+    uint16_t freq[2 * kDCodes + 1];
+    uint16_t dad[2 * kDCodes + 1];
+    uint16_t len[2 * kDCodes + 1];
+    uint16_t code[2 * kDCodes + 1];
+    int max_code;
+};
+
+struct TreeScratch {
+    int16_t heap[kHeapSize];
+    uint8_t depth[kHeapSize];
+    uint16_t bl_count[kMaxBits + 1];
+    int heap_len, heap_max;
+    int64_t opt_len, static_len;
+};
+
+template <class T>
+CCT_HD bool tree_smaller(const T &t, const uint8_t *depth, int n, int m) {
+    return t.freq[n] < t.freq[m] || (t.freq[n] == t.freq[m] && depth[n] <= depth[m]);
+}
+
+template <class T>
+CCT_HDN inline void pq_down(TreeScratch &s, const T &t, int k) {
+    int v = s.heap[k], j = k << 1;
+    while (j <= s.heap_len) {
+        if (j < s.heap_len && tree_smaller(t, s.depth, s.heap[j + 1], s.heap[j])) j++;
+        if (tree_smaller(t, s.depth, v, s.heap[j])) break;
+        s.heap[k] = s.heap[j]; k = j; j <<= 1;
+    }
+    s.heap[k] = (int16_t)v;
+}
+
+// kind: 0 literal/length tree, 1 distance tree, 2 bit-length tree
+template <class T>
+CCT_HDN inline void build_tree(TreeScratch &s, T &t, int kind) {
+    const int elems = kind == 0 ? kLCodes : (kind == 1 ? kDCodes : kBLCodes);
+    const int base = kind == 0 ? 257 : 0;
+    const int max_length = kind == 2 ? 7 : kMaxBits;
+    const int heap_size = 2 * elems + 1;  // zlib uses one HEAP_SIZE array; only relative order matters
+    int n, m, max_code = -1, node;
+    s.heap_len = 0; s.heap_max = heap_size;
+    for (n = 0; n < elems; n++) {
+        if (t.freq[n] != 0) { s.heap[++s.heap_len] = (int16_t)(max_code = n); s.depth[n] = 0; }
+        else t.len[n] = 0;
+    }
+    while (s.heap_len < 2) {  // force at least two codes
+        node = s.heap[++s.heap_len] = (int16_t)(max_code < 2 ? ++max_code : 0);
+        t.freq[node] = 1; s.depth[node] = 0;
+        s.opt_len--;
+        if (kind == 0) s.static_len -= static_llen(node);
+        else if (kind == 1) s.static_len -= 5;
+    }
+    t.max_code = max_code;
+    for (n = s.heap_len / 2; n >= 1; n--) pq_down(s, t, n);
+    node = elems;
+    do {
+        n = s.heap[1]; s.heap[1] = s.heap[s.heap_len--]; pq_down(s, t, 1);
+        m = s.heap[1];
+        s.heap[--s.heap_max] = (int16_t)n; s.heap[--s.heap_max] = (int16_t)m;
+        t.freq[node] = (uint16_t)(t.freq[n] + t.freq[m]);
+        s.depth[node] = (uint8_t)((s.depth[n] >= s.depth[m] ? s.depth[n] : s.depth[m]) + 1);
+        t.dad[n] = t.dad[m] = (uint16_t)node;
+        s.heap[1] = (int16_t)node++;
+        pq_down(s, t, 1);
+    } while (s.heap_len >= 2);
+    s.heap[--s.heap_max] = s.heap[1];
+
+    // gen_bitlen
+    int h, bits, overflow = 0;
+    for (bits = 0; bits <= kMaxBits; bits++) s.bl_count[bits] = 0;
+    t.len[s.heap[s.heap_max]] = 0;
+    for (h = s.heap_max + 1; h < heap_size; h++) {
+        n = s.heap[h];
+        bits = t.len[t.dad[n]] + 1;
+        if (bits > max_length) { bits = max_length; overflow++; }
+        t.len[n] = (uint16_t)bits;
+        if (n > max_code) continue;  // internal node
+        s.bl_count[bits]++;
+        int xbits = 0;
+        if (n >= base) xbits = kind == 0 ? len_extra_bits(n - base) : (kind == 1 ? dist_extra_bits(n) : bl_extra_bits(n));
+        s.opt_len += (int64_t)t.freq[n] * (bits + xbits);
+        if (kind == 0) s.static_len += (int64_t)t.freq[n] * (static_llen(n) + xbits);
+        else if (kind == 1) s.static_len += (int64_t)t.freq[n] * (5 + xbits);
+    }
+    if (overflow) {
+        do {
+            bits = max_length - 1;
+            while (s.bl_count[bits] == 0) bits--;
+            s.bl_count[bits]--; s.bl_count[bits + 1] += 2; s.bl_count[max_length]--;
+            overflow -= 2;
+        } while (overflow > 0);
+        for (bits = max_length; bits != 0; bits--) {
+            n = s.bl_count[bits];
+            while (n != 0) {
+                m = s.heap[--h];
+                if (m > max_code) continue;
+                if (t.len[m] != (unsigned)bits) {
+                    s.opt_len += ((int64_t)bits - t.len[m]) * t.freq[m];
+                    t.len[m] = (uint16_t)bits;
+                }
+                n--;
+            }
+        }
+    }
+    // gen_codes
+    uint32_t next_code[kMaxBits + 1], code = 0;
+    next_code[0] = 0;
+    for (bits = 1; bits <= kMaxBits; bits++) { code = (code + s.bl_count[bits - 1]) << 1; next_code[bits] = code & 0xFFFFu; }
+    for (n = 0; n <= max_code; n++) {
+        int len = t.len[n];
+        if (len == 0) continue;
+        t.code[n] = (uint16_t)bit_reverse(next_code[len]++, len);
+    }
+}
+
+// tiny LSB-first bit writer into a uint32 word array (dynamic-block header string)
+struct HdrBits {
+    uint32_t *w; int nbits;
+    CCT_HD void put(uint32_t value, int length) {
+        int word = nbits >> 5, off = nbits & 31;
+        w[word] |= value << off;
+        if (off + length > 32) w[word + 1] |= value >> (32 - off);
+        nbits += length;
+    }
+};
+
+// scan_tree (count into blfreq) when bl == nullptr, send_tree (emit) otherwise — one control flow
+template <class T>
+CCT_HDN inline void tree_rle(const T &t, int max_code, uint16_t *blfreq, const SmallTree *bl, HdrBits *out) {
+    int prevlen = -1, curlen, nextlen = t.len[0], count = 0, max_count = 7, min_count = 4;
+    if (nextlen == 0) { max_count = 138; min_count = 3; }
+    for (int n = 0; n <= max_code; n++) {
+        curlen = nextlen;
+        nextlen = (n + 1 <= max_code) ? t.len[n + 1] : 0xFFFF;
+        if (++count < max_count && curlen == nextlen) continue;
+        else if (count < min_count) {
+            if (blfreq) blfreq[curlen] += (uint16_t)count;
+            else do { out->put(bl->code[curlen], bl->len[curlen]); } while (--count != 0);
+        } else if (curlen != 0) {
+            if (curlen != prevlen) {
+                if (blfreq) blfreq[curlen]++;
+                else { out->put(bl->code[curlen], bl->len[curlen]); count--; }
+            }
+            if (blfreq) blfreq[16]++;
+            else { out->put(bl->code[16], bl->len[16]); out->put((uint32_t)(count - 3), 2); }
+        } else if (count <= 10) {
+            if (blfreq) blfreq[17]++;
+            else { out->put(bl->code[17], bl->len[17]); out->put((uint32_t)(count - 3), 3); }
+        } else {
+            if (blfreq) blfreq[18]++;
+            else { out->put(bl->code[18], bl->len[18]); out->put((uint32_t)(count - 11), 7); }
+        }
+        count = 0; prevlen = curlen;
+        if (nextlen == 0) { max_count = 138; min_count = 3; }
+        else if (curlen == nextlen) { max_count = 6; min_count = 3; }
+        else { max_count = 7; min_count = 4; }
+    }
+}
+
+// Result of _tr_flush_block's decisions for one block; consumed by the bit-packing kernel.
+struct BlockDesc {
+    uint32_t sym_begin, nsym;        // symbol range inside the stream's symbol array
+    uint32_t pos_begin, stored_len;  // payload bytes covered (for stored blocks)
+    uint32_t type, last;             // 0 stored, 1 static, 2 dynamic
+    uint32_t hdr_bits;               // header bit count incl. the 3 block-header bits (dynamic: + trees)
+    uint32_t body_bits;              // symbol bits + EOB (0 for stored)
+    uint64_t bit_start;              // absolute bit offset in the zlib stream (filled by the layout pass)
+    uint16_t lcode[kLCodes + 2]; uint8_t llen[kLCodes + 2];
+    uint16_t dcode[kDCodes + 2]; uint8_t dlen[kDCodes + 2];
+    uint32_t hdr[kHdrWords];
+};
+
+struct BlockWork {  // scratch for build_block (shared or local memory)
+    Tree lt; SmallTree dt, bt; TreeScratch sc;
+};
+
+// lt.freq / dt.freq must hold the block's symbol frequencies (incl. freq[256] = 1) on entry, every
+// other field zero.  Fills desc->type/hdr/hdr_bits/body_bits and the code tables.
+CCT_HDN inline void build_block(BlockWork &wk, BlockDesc *desc) {
+    const uint8_t bl_order[kBLCodes] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+    wk.sc.opt_len = 0; wk.sc.static_len = 0;
+    build_tree(wk.sc, wk.lt, 0);
+    build_tree(wk.sc, wk.dt, 1);
+    tree_rle(wk.lt, wk.lt.max_code, wk.bt.freq, (const SmallTree *)nullptr, (HdrBits *)nullptr);
+    tree_rle(wk.dt, wk.dt.max_code, wk.bt.freq, (const SmallTree *)nullptr, (HdrBits *)nullptr);
+    build_tree(wk.sc, wk.bt, 2);
+    int max_blindex;
+    for (max_blindex = kBLCodes - 1; max_blindex >= 3; max_blindex--)
+        if (wk.bt.len[bl_order[max_blindex]] != 0) break;
+    wk.sc.opt_len += 3 * ((int64_t)max_blindex + 1) + 5 + 5 + 4;
+    int64_t opt_lenb = (wk.sc.opt_len + 3 + 7) >> 3, static_lenb = (wk.sc.static_len + 3 + 7) >> 3;
+    if (static_lenb <= opt_lenb) opt_lenb = static_lenb;
+    for (int i = 0; i < kHdrWords; i++) desc->hdr[i] = 0;
+    HdrBits hb{desc->hdr, 0};
+    if ((int64_t)desc->stored_len + 4 <= opt_lenb) {
+        desc->type = 0;
+        hb.put((0u << 1) + desc->last, 3);
+        desc->body_bits = 0;
+    } else if (static_lenb == opt_lenb) {
+        desc->type = 1;
+        hb.put((1u << 1) + desc->last, 3);
+        desc->body_bits = (uint32_t)wk.sc.static_len;
+        for (int n = 0; n < kLCodes + 2; n++) { desc->lcode[n] = (uint16_t)static_lcode(n); desc->llen[n] = (uint8_t)static_llen(n); }
+        for (int n = 0; n < kDCodes; n++) { desc->dcode[n] = (uint16_t)bit_reverse((uint32_t)n, 5); desc->dlen[n] = 5; }
+    } else {
+        desc->type = 2;
+        hb.put((2u << 1) + desc->last, 3);
+        hb.put((uint32_t)(wk.lt.max_code + 1 - 257), 5);
+        hb.put((uint32_t)(wk.dt.max_code + 1 - 1), 5);
+        hb.put((uint32_t)(max_blindex + 1 - 4), 4);
+        for (int r = 0; r <= max_blindex; r++) hb.put(wk.bt.len[bl_order[r]], 3);
+        tree_rle(wk.lt, wk.lt.max_code, (uint16_t *)nullptr, &wk.bt, &hb);
+        tree_rle(wk.dt, wk.dt.max_code, (uint16_t *)nullptr, &wk.bt, &hb);
+        desc->body_bits = (uint32_t)(wk.sc.opt_len - (hb.nbits - 3));
+        for (int n = 0; n < kLCodes; n++) { desc->lcode[n] = wk.lt.code[n]; desc->llen[n] = (uint8_t)(n <= wk.lt.max_code ? wk.lt.len[n] : 0); }
+        for (int n = 0; n < kDCodes; n++) { desc->dcode[n] = wk.dt.code[n]; desc->dlen[n] = (uint8_t)(n <= wk.dt.max_code ? wk.dt.len[n] : 0); }
+    }
+    desc->hdr_bits = (uint32_t)hb.nbits;
+}
+
+// bits of one LZ77 symbol under a block's code tables: returns the bit string (LSB-first, <= 48 bits)
+CCT_HD uint64_t sym_bits(uint32_t sym, const uint16_t *lcode, const uint8_t *llen, const uint16_t *dcode,
+                         const uint8_t *dlen, int *nbits) {
+    int dist = sym_dist(sym), lc = sym_lc(sym);
+    if (dist == 0) { *nbits = llen[lc]; return lcode[lc]; }
+    int code = len_code(lc);
+    uint64_t bits = lcode[code + 257];
+    int nb = llen[code + 257];
+    int extra = len_extra_bits(code);
+    if (extra) { bits |= (uint64_t)(lc & ((1 << extra) - 1)) << nb; nb += extra; }
+    int d = dist - 1;
+    code = dist_code(d);
+    bits |= (uint64_t)dcode[code] << nb; nb += dlen[code];
+    extra = dist_extra_bits(code);
+    if (extra) { bits |= (uint64_t)(d & ((1 << extra) - 1)) << nb; nb += extra; }
+    *nbits = nb;
+    return bits;
+}
+
+CCT_HD int sym_nbits(uint32_t sym, const uint8_t *llen, const uint8_t *dlen) {
+    int dist = sym_dist(sym), lc = sym_lc(sym);
+    if (dist == 0) return llen[lc];
+    int code = len_code(lc);
+    int nb = llen[code + 257] + len_extra_bits(code);
+    code = dist_code(dist - 1);
+    return nb + dlen[code] + dist_extra_bits(code);
+}
+
+}  // namespace cct

@@ -1,0 +1,271 @@
+// inflate_core.cuh — RFC 1950/1951 decoder and the CompaCT op-stream decoder as host/device functions
+// (the kernels in cct_decode.cu and the CPU harness in tests/hostsim run the same code).
+//
+// Restates: `zlib.decompress(file_bytes[13:])` (reference src/codec/core.py:420-421; any conformant
+// inflate reproduces it) and the decode loop (core.py:453-520) in the parallel-friendly
+// formulation of SURVEY Appendix A.5: ops -> deltas -> running sum; JUMPs -> unit table -> scatter.
+#pragma once
+#include "cct_common.cuh"
+
+namespace cct {
+
+constexpr int kLitBits = 10;  // primary lookup width, literal/length codes
+constexpr int kDstBits = 9;   // primary lookup width, distance codes
+
+struct InflateTables {  // per-stream decode tables (shared memory on the device)
+    uint16_t lit[1 << kLitBits];  // len << 12 | symbol ; 0 = code longer than kLitBits (slow path)
+    uint16_t dst[1 << kDstBits];
+    uint16_t lcount[16], dcount[16];   // canonical: number of codes of each length
+    uint16_t lsym[288], dsym[32];      // symbols ordered by (length, symbol)
+};
+
+// RFC 1951 §3.2.5 length / distance bases as closed forms
+CCT_HD int len_extra_bits_inf(int idx) { return (idx < 8 || idx == 28) ? 0 : (idx >> 2) - 1; }
+CCT_HD int len_base_inf(int idx) {
+    if (idx < 8) return 3 + idx;
+    if (idx == 28) return 258;
+    return 3 + ((4 + (idx & 3)) << ((idx >> 2) - 1));
+}
+CCT_HD int dist_base_inf(int ds) { return ds < 4 ? 1 + ds : 1 + ((2 + (ds & 1)) << ((ds >> 1) - 1)); }
+
+struct BitReader {
+    const uint8_t *in; int len, pos; uint64_t buf; int nbits; bool bad;
+    CCT_HD void refill() {
+        while (nbits <= 56 && pos < len) { buf |= (uint64_t)in[pos++] << nbits; nbits += 8; }
+    }
+    CCT_HD uint32_t peek(int n) const { return (uint32_t)(buf & ((1ull << n) - 1)); }
+    CCT_HD void drop(int n) { if (n > nbits) { bad = true; n = nbits; } buf >>= n; nbits -= n; }
+    CCT_HD uint32_t take(int n) { uint32_t v = peek(n); drop(n); return v; }
+};
+
+// Build primary table + canonical arrays from code lengths.  Returns false for an over-subscribed set.
+CCT_HDN inline bool build_decode_table(const uint8_t *lens, int nsym, int prim_bits, uint16_t *prim, uint16_t *count,
+                                       uint16_t *symbols) {
+    uint16_t offs[16];
+    for (int i = 0; i < 16; i++) count[i] = 0;
+    for (int i = 0; i < nsym; i++) count[lens[i]]++;
+    count[0] = 0;
+    int left = 1;
+    for (int l = 1; l <= 15; l++) { left <<= 1; left -= count[l]; if (left < 0) return false; }
+    offs[1] = 0;
+    for (int l = 1; l < 15; l++) offs[l + 1] = (uint16_t)(offs[l] + count[l]);
+    for (int i = 0; i < nsym; i++) if (lens[i]) symbols[offs[lens[i]]++] = (uint16_t)i;
+    for (int i = 0; i < (1 << prim_bits); i++) prim[i] = 0;
+    // canonical codes, shortest first
+    uint32_t code = 0; int idx = 0;
+    for (int l = 1; l <= prim_bits; l++) {
+        for (int c = 0; c < count[l]; c++, idx++, code++) {
+            uint32_t rev = 0;
+            for (int b = 0; b < l; b++) rev |= ((code >> b) & 1u) << (l - 1 - b);
+            uint16_t e = (uint16_t)((l << 12) | symbols[idx]);
+            for (uint32_t k = rev; k < (1u << prim_bits); k += (1u << l)) prim[k] = e;
+        }
+        code <<= 1;
+    }
+    return true;
+}
+
+// Decode one symbol; drops its bits.  Returns -1 on an invalid code.
+CCT_HD int decode_symbol(BitReader &br, const uint16_t *prim, int prim_bits, const uint16_t *count, const uint16_t *symbols) {
+    uint16_t e = prim[br.peek(prim_bits)];
+    if (e) { br.drop(e >> 12); return e & 0xFFF; }
+    // slow path: canonical bit-by-bit (codes longer than prim_bits)
+    int code = 0, first = 0, index = 0;
+    uint64_t b = br.buf;
+    for (int l = 1; l <= 15; l++) {
+        code |= (int)(b & 1); b >>= 1;
+        int c = count[l];
+        if (code - c < first) { br.drop(l); return symbols[index + (code - first)]; }
+        index += c; first += c; first <<= 1; code <<= 1;
+    }
+    return -1;
+}
+
+// zlib stream -> bytes.  Returns output length, or -1 on any error (bad header, invalid code, distance
+// too far, output overflow, truncated input, Adler-32 mismatch).
+CCT_HDN inline int inflate_stream(const uint8_t *in, int in_len, uint8_t *out, int out_cap, InflateTables &tb) {
+    if (in_len < 6) return -1;
+    if ((in[0] & 0x0F) != 8 || (((uint32_t)in[0] << 8) | in[1]) % 31 != 0 || (in[1] & 0x20)) return -1;
+    BitReader br{in, in_len - 4, 2, 0, 0, false};
+    int op = 0;
+    uint32_t a1 = 1, a2 = 0;
+    int since_mod = 0;
+    bool last = false;
+    uint8_t lens[320];
+    while (!last) {
+        br.refill();
+        last = br.take(1);
+        int type = (int)br.take(2);
+        if (type == 0) {
+            br.drop(br.nbits & 7);
+            br.refill();
+            uint32_t len = br.take(16), nlen = br.take(16);
+            if (br.bad || (len ^ 0xFFFFu) != nlen) return -1;
+            // bytes still in the bit buffer first, then straight from the input
+            if (op + (int)len > out_cap) return -1;
+            for (uint32_t i = 0; i < len; i++) {
+                uint8_t c;
+                if (br.nbits >= 8) { c = (uint8_t)br.take(8); }
+                else { if (br.pos >= br.len) return -1; c = br.in[br.pos++]; }
+                out[op++] = c;
+                a1 += c; a2 += a1;
+                if (++since_mod == 5552) { a1 %= 65521u; a2 %= 65521u; since_mod = 0; }
+            }
+            continue;
+        }
+        if (type == 3) return -1;
+        if (type == 1) {
+            for (int i = 0; i < 144; i++) lens[i] = 8;
+            for (int i = 144; i < 256; i++) lens[i] = 9;
+            for (int i = 256; i < 280; i++) lens[i] = 7;
+            for (int i = 280; i < 288; i++) lens[i] = 8;
+            build_decode_table(lens, 288, kLitBits, tb.lit, tb.lcount, tb.lsym);
+            for (int i = 0; i < 30; i++) lens[i] = 5;
+            build_decode_table(lens, 30, kDstBits, tb.dst, tb.dcount, tb.dsym);
+        } else {
+            const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+            int nlen = (int)br.take(5) + 257, ndist = (int)br.take(5) + 1, ncode = (int)br.take(4) + 4;
+            if (nlen > 286 || ndist > 30) return -1;
+            uint8_t cl[19];
+            for (int i = 0; i < 19; i++) cl[i] = 0;
+            for (int i = 0; i < ncode; i++) { br.refill(); cl[order[i]] = (uint8_t)br.take(3); }
+            // the code-length code is tiny: reuse the distance table storage for it
+            if (!build_decode_table(cl, 19, 7, tb.dst, tb.dcount, tb.dsym)) return -1;
+            int idx = 0;
+            while (idx < nlen + ndist) {
+                br.refill();
+                int sym = decode_symbol(br, tb.dst, 7, tb.dcount, tb.dsym);
+                if (sym < 0 || br.bad) return -1;
+                if (sym < 16) lens[idx++] = (uint8_t)sym;
+                else {
+                    int rep, val = 0;
+                    if (sym == 16) { if (idx == 0) return -1; val = lens[idx - 1]; rep = 3 + (int)br.take(2); }
+                    else if (sym == 17) rep = 3 + (int)br.take(3);
+                    else rep = 11 + (int)br.take(7);
+                    if (idx + rep > nlen + ndist) return -1;
+                    while (rep--) lens[idx++] = (uint8_t)val;
+                }
+            }
+            if (lens[256] == 0) return -1;
+            uint8_t dl[32];
+            for (int i = 0; i < ndist; i++) dl[i] = lens[nlen + i];
+            if (!build_decode_table(lens, nlen, kLitBits, tb.lit, tb.lcount, tb.lsym)) return -1;
+            if (!build_decode_table(dl, ndist, kDstBits, tb.dst, tb.dcount, tb.dsym)) return -1;
+        }
+        for (;;) {
+            br.refill();
+            int sym = decode_symbol(br, tb.lit, kLitBits, tb.lcount, tb.lsym);
+            if (sym < 0 || br.bad) return -1;
+            if (sym < 256) {
+                if (op >= out_cap) return -1;
+                out[op++] = (uint8_t)sym;
+                a1 += (uint32_t)sym; a2 += a1;
+                if (++since_mod == 5552) { a1 %= 65521u; a2 %= 65521u; since_mod = 0; }
+                continue;
+            }
+            if (sym == 256) break;
+            sym -= 257;
+            if (sym >= 29) return -1;
+            int lx = len_extra_bits_inf(sym);
+            int len = len_base_inf(sym) + (int)br.take(lx);
+            int ds = decode_symbol(br, tb.dst, kDstBits, tb.dcount, tb.dsym);
+            if (ds < 0 || ds >= 30) return -1;
+            br.refill();
+            int dx = ds < 4 ? 0 : (ds >> 1) - 1;
+            int dist = dist_base_inf(ds) + (int)br.take(dx);
+            if (br.bad || dist > op || op + len > out_cap) return -1;
+            for (int i = 0; i < len; i++) {
+                uint8_t c = out[op - dist];
+                out[op++] = c;
+                a1 += c; a2 += a1;
+                if (++since_mod == 5552) { a1 %= 65521u; a2 %= 65521u; since_mod = 0; }
+            }
+        }
+    }
+    a1 %= 65521u; a2 %= 65521u;
+    const uint8_t *t = in + in_len - 4;
+    // the trailer must start right after the last block (byte aligned)
+    br.drop(br.nbits & 7);
+    int consumed = br.pos - (br.nbits >> 3);
+    if (consumed != in_len - 4) return -1;
+    uint32_t want = ((uint32_t)t[0] << 24) | ((uint32_t)t[1] << 16) | ((uint32_t)t[2] << 8) | t[3];
+    if (want != ((a2 << 16) | a1)) return -1;
+    return op;
+}
+
+// ------------------------------------------------------------------------------------------------
+// CompaCT op stream (core.py:453-520 restated per SURVEY A.5)
+// ------------------------------------------------------------------------------------------------
+constexpr int32_t kSlotSecond = 0x40000000;  // slotB flag: second half of a meshed unit
+
+// payload -> value of every pixel op in final order (vals[k]) and the JUMP distance at each unit start
+// (jflag[k/16], 0 = none).  Returns CCT_ST_* bits (0 = fine).  plen includes the EOF byte, which the
+// reference's reader never consumes (core.py:137,142).
+CCT_HDN inline uint32_t ops_to_values(const uint8_t *payload, int plen, int n_px, uint16_t *vals, uint8_t *jflag) {
+    const int end = plen - 1;
+    int pos = 0, value = 0;
+    uint32_t st = 0;
+    for (int k = 0; k < n_px; k++) {
+        if (pos >= end) return st | 64u;
+        int b = payload[pos];
+        if ((b & 0xC0) == 0x80) {  // JUMP (core.py:484-494)
+            if ((k & 15) == 0) jflag[k >> 4] = (uint8_t)(b & 0x3F);
+            else st |= 64u;  // never produced by the encoder
+            if (++pos >= end) return st | 64u;
+            b = payload[pos];
+        }
+        int delta = 0;
+        if ((b & 0xF0) == 0xE0) {  // FULL (core.py:500-506)
+            if (pos + 1 >= end) return st | 64u;
+            int full = ((b << 8) | payload[pos + 1]) & 0xFFF;
+            delta = full > 2048 ? full - 4096 : full;
+            pos += 2;
+        } else {
+            if ((b & 0x80) == 0) {  // DELTA (core.py:513-516)
+                int x = b & 0x7F;
+                delta = x > 64 ? x - 128 : x;
+            }  // any other tag: the reference leaves the pixel unchanged
+            pos += 1;
+        }
+        value += delta;
+        if (value < 0 || value > 65535) st |= 32u;  // reference: OverflowError (core.py:506,516)
+        vals[k] = (uint16_t)value;
+    }
+    return st;
+}
+
+// JUMP flags -> unit table.  Slot q covers pixel ops [16q, 16q+16).  slotA[q] = block A of the unit,
+// slotB[q] = -1 (plain unit) or partner block B (| kSlotSecond in the unit's second slot).
+CCT_HDN inline uint32_t resolve_units(const uint8_t *jflag, int nb, int32_t *slotA, int32_t *slotB) {
+    uint64_t win = 0;  // bit i: block cur+i already consumed as a partner
+    int cur = 0, q = 0;
+    while (q < nb) {
+        while (win & 1ull) { win >>= 1; cur++; }
+        int A = cur, j = jflag[q];
+        if (j) {
+            int B = A + j;
+            if (B >= nb || q + 1 >= nb || ((win >> j) & 1ull)) return 64u;
+            slotA[q] = A; slotB[q] = B;
+            slotA[q + 1] = A; slotB[q + 1] = B | kSlotSecond;
+            win |= 1ull << j;
+            q += 2;
+        } else {
+            slotA[q] = A; slotB[q] = -1;
+            q += 1;
+        }
+        win >>= 1; cur++;
+    }
+    return 0;
+}
+
+// raster index of pixel op k given the unit table and the traversal order
+CCT_HD int32_t op_raster(int k, const int32_t *slotA, const int32_t *slotB, const int32_t *order) {
+    int q = k >> 4, i = k & 15;
+    int32_t A = slotA[q], Bf = slotB[q];
+    if (Bf < 0) return order[A * kBlock + i];
+    int m = i + ((Bf & kSlotSecond) ? 16 : 0);
+    int32_t blk = (m & 1) ? (Bf & ~kSlotSecond) : A;
+    return order[blk * kBlock + (m >> 1)];
+}
+
+}  // namespace cct

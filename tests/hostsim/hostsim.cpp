@@ -1,0 +1,135 @@
+// tests/hostsim/hostsim.cpp — runs the product's host/device scalar cores (csrc/*_core.cuh) on the CPU,
+// stage by stage in the same order as the CUDA kernels, so the staged zlib-9 formulation (chains ->
+// probe table -> table walk -> trees -> bit packing) can be checked against libz without a GPU.
+// TEST INFRASTRUCTURE: built and loaded by tests/ only; the product library never contains this file.
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "deflate_core.cuh"
+#include "inflate_core.cuh"
+
+using namespace cct;
+
+static void chains_reference(const uint8_t *w, int n, std::vector<uint16_t> &dist16) {
+    // dist16[s] = s - (latest p < s, p >= 1, with hash3(p) == hash3(s)), 0 if none or >= 32768
+    std::vector<int32_t> head(32768, 0);
+    dist16.assign((size_t)n + 1, 0);
+    for (int s = 0; s + 2 < n; s++) {
+        uint32_t h = hash3(w + s);
+        int p = head[h];
+        if (p != 0 && s - p < 32768) dist16[s] = (uint16_t)(s - p);
+        head[h] = s;  // position 0 is stored as 0 == NIL, exactly like zlib
+    }
+}
+
+static uint32_t adler32_(const uint8_t *p, int64_t n) {
+    uint32_t a = 1, b = 0;
+    while (n > 0) {
+        int64_t k = n < 5552 ? n : 5552;
+        n -= k;
+        while (k--) { a += *p++; b += a; }
+        a %= 65521; b %= 65521;
+    }
+    return (b << 16) | a;
+}
+
+extern "C" {
+
+// Staged zlib-9 of src[0..n).  probe_k = chain entries examined by the parallel probe.
+// stats[0] = symbols, [1] = blocks, [2] = incomplete probes hit by the walk (filled if non-null).
+int64_t hs_deflate(const uint8_t *src, int n, uint8_t *dst, int64_t cap, int probe_k, int64_t *stats) {
+    std::vector<uint16_t> dist16;
+    chains_reference(src, n, dist16);
+    LzView v{src, dist16.data(), n};
+    std::vector<uint32_t> mtab((size_t)n + 1, 0);
+    int64_t n_incomplete = 0;
+    for (int s = 0; s < n; s++) { mtab[s] = match_probe(v, s, probe_k); n_incomplete += (mtab[s] & kProbeIncomplete) != 0; }
+    std::vector<uint32_t> syms((size_t)n + 1);
+    std::vector<int32_t> blk_end((size_t)n / kSymEnd + 2);
+    int n_flush = 0;
+    int nsym = parse_stream(v, mtab.data(), syms.data(), blk_end.data(), &n_flush);
+    int nblk = n_flush + 1;
+    std::vector<BlockDesc> desc((size_t)nblk);
+    BlockWork *wk = new BlockWork;
+    for (int b = 0; b < nblk; b++) {
+        BlockDesc &d = desc[b];
+        d.sym_begin = (uint32_t)b * kSymEnd;
+        d.nsym = b < n_flush ? (uint32_t)kSymEnd : (uint32_t)(nsym - n_flush * kSymEnd);
+        d.pos_begin = b == 0 ? 0u : (uint32_t)blk_end[b - 1];
+        d.stored_len = (b < n_flush ? (uint32_t)blk_end[b] : (uint32_t)n) - d.pos_begin;
+        d.last = b == nblk - 1;
+        memset(wk, 0, sizeof(BlockWork));
+        wk->lt.freq[256] = 1;
+        for (uint32_t i = 0; i < d.nsym; i++) {
+            uint32_t sy = syms[d.sym_begin + i];
+            if (sym_dist(sy) == 0) wk->lt.freq[sym_lc(sy)]++;
+            else { wk->lt.freq[257 + len_code(sym_lc(sy))]++; wk->dt.freq[dist_code(sym_dist(sy) - 1)]++; }
+        }
+        build_block(*wk, &d);
+    }
+    delete wk;
+    // layout + packing
+    std::vector<uint8_t> out((size_t)deflate_bound(n) + 64, 0);
+    out[0] = 0x78; out[1] = 0xDA;
+    uint64_t bit = 16;
+    auto put = [&](uint64_t bits, int nb) {
+        for (int i = 0; i < nb; i++, bit++) if ((bits >> i) & 1) out[bit >> 3] |= (uint8_t)(1u << (bit & 7));
+    };
+    for (int b = 0; b < nblk; b++) {
+        BlockDesc &d = desc[b];
+        d.bit_start = bit;
+        for (uint32_t i = 0; i < d.hdr_bits; i++) put((d.hdr[i >> 5] >> (i & 31)) & 1u, 1);
+        if (d.type == 0) {
+            bit = (bit + 7) & ~7ull;
+            put(d.stored_len & 0xFFFF, 16); put(~d.stored_len & 0xFFFF, 16);
+            memcpy(&out[bit >> 3], src + d.pos_begin, d.stored_len);
+            bit += 8ull * d.stored_len;
+        } else {
+            uint64_t before = bit;
+            for (uint32_t i = 0; i < d.nsym; i++) {
+                int nb; uint64_t bits = sym_bits(syms[d.sym_begin + i], d.lcode, d.llen, d.dcode, d.dlen, &nb);
+                if (nb != sym_nbits(syms[d.sym_begin + i], d.llen, d.dlen)) return -3;
+                put(bits, nb);
+            }
+            put(d.lcode[256], d.llen[256]);
+            if (bit - before != d.body_bits) return -2;  // opt_len / static_len accounting must be exact
+        }
+    }
+    bit = (bit + 7) & ~7ull;
+    uint32_t ad = adler32_(src, n);
+    int64_t len = (int64_t)(bit >> 3);
+    out[len++] = (uint8_t)(ad >> 24); out[len++] = (uint8_t)(ad >> 16); out[len++] = (uint8_t)(ad >> 8); out[len++] = (uint8_t)ad;
+    if (stats) { stats[0] = nsym; stats[1] = nblk; stats[2] = n_incomplete; }
+    if (len > cap) return -1;
+    memcpy(dst, out.data(), (size_t)len);
+    return len;
+}
+
+int hs_inflate(const uint8_t *in, int in_len, uint8_t *out, int out_cap) {
+    InflateTables *tb = new InflateTables;
+    int r = inflate_stream(in, in_len, out, out_cap, *tb);
+    delete tb;
+    return r;
+}
+
+// payload (ops + EOF) -> raster pixels, via the same three steps as the decode kernels
+uint32_t hs_decode_payload(const uint8_t *payload, int plen, int n_px, const int32_t *order, uint16_t *out) {
+    int nb = n_px / kBlock;
+    std::vector<uint16_t> vals((size_t)n_px);
+    std::vector<uint8_t> jflag((size_t)nb, 0);
+    std::vector<int32_t> slotA((size_t)nb), slotB((size_t)nb);
+    uint32_t st = ops_to_values(payload, plen, n_px, vals.data(), jflag.data());
+    if (st & 64u) return st;
+    st |= resolve_units(jflag.data(), nb, slotA.data(), slotB.data());
+    if (st & 64u) return st;
+    for (int k = 0; k < n_px; k++) out[op_raster(k, slotA.data(), slotB.data(), order)] = vals[k];
+    return st;
+}
+
+uint32_t hs_hilbert(uint32_t n, uint32_t d) { return hilbert_d2raster(n, d); }
+int hs_len_code(int lc) { return len_code(lc); }
+int hs_dist_code(int d) { return dist_code(d); }
+
+}  // extern "C"

@@ -1,0 +1,329 @@
+"""GPU parity tests: the CUDA path (through the C ABI / its Python mirror) against the oracle and the
+golden fixtures.  Bit-exact everywhere (integer/byte work).  Run on the B200 box: pytest -m gpu."""
+import ctypes as C
+import hashlib
+import zlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+@pytest.fixture(scope="module")
+def native(pkg):
+    L = pkg._native.lib()
+    assert L.cct_device_count() >= 1
+    return pkg._native
+
+
+def _dev(torch, a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _stages(torch, native, img, flags=7):
+    """cct_debug_encode_stages for one image -> (order, jump, payload bytes)."""
+    L = native.lib()
+    rows, cols = img.shape
+    n = rows * cols
+    d_px = _dev(torch, img.view(np.int16))
+    ws = torch.empty(int(L.cct_encode_workspace_bytes(1, rows, cols, flags)), dtype=torch.uint8, device="cuda")
+    d_order = torch.empty(n, dtype=torch.int32, device="cuda")
+    d_jump = torch.empty(n // 16, dtype=torch.uint8, device="cuda")
+    d_payload = torch.empty(int(L.cct_payload_bound(rows, cols)), dtype=torch.uint8, device="cuda")
+    d_plen = torch.zeros(1, dtype=torch.int32, device="cuda")
+    native.check(L.cct_debug_encode_stages(d_px.data_ptr(), rows, cols, flags, d_order.data_ptr(), d_jump.data_ptr(),
+                                           d_payload.data_ptr(), d_plen.data_ptr(), ws.data_ptr(), ws.numel(),
+                                           torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    plen = int(d_plen.item())
+    return d_order.cpu().numpy(), d_jump.cpu().numpy(), d_payload[:plen].cpu().numpy().tobytes()
+
+
+def _gpu_deflate(torch, native, blobs):
+    L = native.lib()
+    B = len(blobs)
+    max_len = max(max(len(b) for b in blobs), 1)
+    in_stride = (max_len + 15) // 16 * 16
+    out_stride = int(L.cct_deflate_bound(max_len))
+    h_in = np.zeros((B, in_stride), dtype=np.uint8)
+    for i, b in enumerate(blobs):
+        h_in[i, :len(b)] = np.frombuffer(b, dtype=np.uint8)
+    d_in = _dev(torch, h_in)
+    d_len = _dev(torch, np.array([len(b) for b in blobs], dtype=np.int32))
+    d_out = torch.empty((B, out_stride), dtype=torch.uint8, device="cuda")
+    d_olen = torch.zeros(B, dtype=torch.int32, device="cuda")
+    ws = torch.empty(int(L.cct_deflate_workspace_bytes(B, max_len)), dtype=torch.uint8, device="cuda")
+    native.check(L.cct_deflate_batch(d_in.data_ptr(), in_stride, d_len.data_ptr(), B, max_len, d_out.data_ptr(),
+                                     out_stride, d_olen.data_ptr(), ws.data_ptr(), ws.numel(),
+                                     torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    out, olen = d_out.cpu().numpy(), d_olen.cpu().numpy()
+    return [out[i, :olen[i]].tobytes() for i in range(B)]
+
+
+def _gpu_inflate(torch, native, streams, cap):
+    L = native.lib()
+    B = len(streams)
+    in_stride = max(len(s) for s in streams) + 16
+    h_in = np.zeros((B, in_stride), dtype=np.uint8)
+    for i, s in enumerate(streams):
+        h_in[i, :len(s)] = np.frombuffer(s, dtype=np.uint8)
+    d_in = _dev(torch, h_in)
+    d_len = _dev(torch, np.array([len(s) for s in streams], dtype=np.int32))
+    d_out = torch.zeros((B, cap), dtype=torch.uint8, device="cuda")
+    d_olen = torch.zeros(B, dtype=torch.int32, device="cuda")
+    d_st = torch.zeros(B, dtype=torch.int32, device="cuda")
+    native.check(L.cct_inflate_batch(d_in.data_ptr(), in_stride, d_len.data_ptr(), B, d_out.data_ptr(), cap,
+                                     d_olen.data_ptr(), d_st.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    out, olen, st = d_out.cpu().numpy(), d_olen.cpu().numpy(), d_st.cpu().numpy()
+    return [out[i, :olen[i]].tobytes() for i in range(B)], st
+
+
+# ------------------------------------------------------------------------------------------ stage parity
+
+@pytest.mark.parametrize("shape", [(512, 512), (64, 64), (32, 64), (64, 32), (48, 80), (20, 20), (12, 12), (4, 4), (1, 16), (36, 44)])
+def test_traversal_table(torch_cuda, native, oracle, synth, shape):
+    img = synth.random_walk_image(1, *shape)
+    order, _, _ = _stages(torch_cuda, native, img)
+    assert (order == oracle.curve(*shape)).all()
+
+
+def test_stage_payload_and_jumps(torch_cuda, native, oracle, synth, golden_cct):
+    imgs = [synth.synth_ct(s) for s in (0, 1, 2)] + [oracle.decode(golden_cct)]
+    imgs += [synth.random_walk_image(50 + k, h, w) for k, (h, w) in enumerate([(64, 64), (32, 64), (48, 80), (128, 128), (16, 16)])]
+    b0 = synth.random_walk_image(7, 32, 32)
+    b0[:4, :4] = (np.arange(16).reshape(4, 4) % 2) * 900  # difficult block 0: uint32-wrap quirk
+    imgs.append(b0)
+    for img in imgs:
+        for flags in (7, 5, 6, 4):  # with / without fractal and segmentation
+            _, det = oracle.encode(img, fractal=bool(flags & 1), seg=bool(flags & 2), detail=True)
+            _, jump, payload = _stages(torch_cuda, native, img, flags)
+            want_jump = np.where(det["jumps"] >= 0, det["jumps"] - np.arange(len(det["jumps"])), 0).astype(np.uint8)
+            assert (jump == want_jump).all(), (img.shape, flags)
+            assert payload == det["payload"], (img.shape, flags)
+
+
+def _corpus():
+    from test_oracle import _deflate_corpus
+    return _deflate_corpus()
+
+
+def test_deflate_matches_libz(torch_cuda, native, oracle, synth):
+    blobs = [b for b in _corpus() if len(b) > 0]
+    for s in (0, 1):
+        blobs.append(oracle.encode(synth.synth_ct(s), detail=True)[1]["payload"])
+    got = _gpu_deflate(torch_cuda, native, blobs)
+    for b, g in zip(blobs, got):
+        assert g == zlib.compress(b, 9), len(b)
+
+
+def test_deflate_block_boundaries(torch_cuda, native):
+    rng = np.random.default_rng(11)
+    lits = rng.permutation(np.arange(256, dtype=np.uint8).repeat(200))
+    blobs = []
+    for n in (16382, 16383, 16384, 16385, 32765, 32766, 32767, 32768):
+        data = lits[:n].tobytes()
+        blobs += [data, data + data[-40:]]
+    got = _gpu_deflate(torch_cuda, native, blobs)
+    for b, g in zip(blobs, got):
+        assert g == zlib.compress(b, 9), len(b)
+
+
+def test_deflate_empty_and_tiny(torch_cuda, native):
+    blobs = [b"a", b"ab", b"abc", b"aaaa", bytes(5), bytes(300)]
+    got = _gpu_deflate(torch_cuda, native, blobs)
+    for b, g in zip(blobs, got):
+        assert g == zlib.compress(b, 9), b[:8]
+
+
+def test_inflate_any_conformant_stream(torch_cuda, native):
+    blobs = [b for b in _corpus() if len(b) > 0]
+    cap = max(len(b) for b in blobs)
+    for level in (0, 1, 6, 9):
+        streams = [zlib.compress(b, level) for b in blobs]
+        got, st = _gpu_inflate(torch_cuda, native, streams, cap)
+        assert not st.any()
+        for b, g in zip(blobs, got):
+            assert g == b, (level, len(b))
+    # corrupt streams are flagged, not crashed on
+    bad = bytearray(zlib.compress(blobs[-1], 9))
+    bad[len(bad) // 2] ^= 0x55
+    trunc = zlib.compress(blobs[-1], 9)[:-7]
+    _, st = _gpu_inflate(torch_cuda, native, [bytes(bad), trunc, b"\x00\x01\x02\x03\x04\x05\x06"], cap)
+    assert (st != 0).all()
+
+
+# ------------------------------------------------------------------------------------------ end to end
+
+def test_reference_golden_vector(torch_cuda, pkg, golden_cct, golden_digests):
+    cfg = pkg.default_config()
+    raw = pkg.Decoder(cfg, golden_cct).decode()
+    assert hashlib.sha1(raw).hexdigest() == golden_digests["reference_testing"]["decoded_sha1"]
+    img = np.frombuffer(raw, dtype=np.uint16).reshape(512, 512)
+    enc = pkg.Encoder(cfg, img)
+    out = enc.encode()
+    assert out == golden_cct
+    assert (enc.info["delta"], enc.info["full"], enc.n_jumps, enc.n_difficult) == (248215, 13929, 96, 554)
+
+
+def test_small_goldens(torch_cuda, pkg, golden_small):
+    cfg = pkg.default_config()
+    names = sorted(k[:-4] for k in golden_small if k.endswith("__in"))
+    for name in names:
+        img = golden_small[name + "__in"]
+        ref = golden_small[name + "__out"].tobytes()
+        assert pkg.Encoder(cfg, img).encode() == ref, name
+        if bool(golden_small[name + "__domain"]):
+            out = np.frombuffer(pkg.Decoder(cfg, ref).decode(), dtype=np.uint16).reshape(img.shape)
+            assert (out == img).all(), name
+
+
+def test_flag_variants(torch_cuda, pkg, golden_small):
+    for name in ("walk_32x64", "synth_ct_64"):
+        img = golden_small[name + "__in"]
+        for fr in (0, 1):
+            for sg in (0, 1):
+                for df in (0, 1):
+                    cfg = pkg.default_config()
+                    cfg["encoder"]["transforms"]["fractal"] = bool(fr)
+                    cfg["encoder"]["transforms"]["segmentation"] = bool(sg)
+                    cfg["encoder"]["deflate_compression"] = bool(df)
+                    ref = golden_small[f"{name}__flags{fr}{sg}{df}"].tobytes()
+                    assert pkg.Encoder(cfg, img).encode() == ref, (name, fr, sg, df)
+                    out = np.frombuffer(pkg.Decoder(cfg, ref).decode(), dtype=np.uint16).reshape(img.shape)
+                    assert (out == img).all(), (name, fr, sg, df)
+
+
+def test_full_size_digests(torch_cuda, pkg, synth, golden_digests):
+    cfg = pkg.default_config()
+    for seed, d in golden_digests["synth_ct_512"].items():
+        img = synth.synth_ct(int(seed))
+        out = pkg.Encoder(cfg, img).encode()
+        assert len(out) == d["len"] and hashlib.sha256(out).hexdigest() == d["sha256"], seed
+        assert pkg.Decoder(cfg, out).decode() == img.tobytes()
+
+
+def test_radiograph_2048(torch_cuda, pkg, synth, oracle, golden_digests):
+    d = golden_digests["synth_radiograph_2048_seed0"]
+    img = synth.synth_radiograph(0, 2048)
+    out = pkg.Encoder(pkg.default_config(), img).encode()
+    assert len(out) == d["len"] and hashlib.sha256(out).hexdigest() == d["sha256"]
+    assert pkg.Decoder(pkg.default_config(), out).decode() == img.tobytes()
+    # a batch of two more, device-resident, against the oracle
+    imgs = np.stack([synth.synth_radiograph(s, 2048) for s in (1, 2)])
+    arena, offsets, status = pkg.encode_batch(torch_cuda.from_numpy(imgs.view(np.int16)).cuda())
+    arena, offsets = arena.cpu().numpy(), offsets.cpu().numpy()
+    for i in range(2):
+        assert arena[offsets[i]:offsets[i + 1]].tobytes() == oracle.encode(imgs[i])
+
+
+def test_batch_device_resident(torch_cuda, pkg, synth, oracle):
+    B = 48
+    imgs = synth.synth_ct_batch(range(100, 100 + B), workers=8)
+    d_imgs = torch_cuda.from_numpy(imgs.view(np.int16)).cuda()
+    arena, offsets, status, stats = pkg.encode_batch(d_imgs, return_stats=True)
+    assert not status.cpu().numpy().any()
+    h_arena, h_off = arena.cpu().numpy(), offsets.cpu().numpy()
+    want_arena, want_off = oracle.encode_batch(imgs, nthreads=8)
+    assert (h_off == want_off).all()
+    assert h_arena[:h_off[-1]].tobytes() == want_arena.tobytes()
+    px, dst = pkg.decode_batch(arena, offsets, (512, 512))
+    assert not dst.cpu().numpy().any()
+    assert torch_cuda.equal(px.view(torch_cuda.int16), d_imgs)
+    # decode of oracle-written files, host buffers in and out
+    px2, st2 = pkg.decode_batch(want_arena, want_off, (512, 512))
+    assert not st2.any() and (px2 == imgs).all()
+
+
+def test_multi_pass_small_workspace(torch_cuda, native, pkg, synth, oracle):
+    """A workspace that holds only 3 images forces several passes over the same stream."""
+    L = native.lib()
+    B, n = 10, 128
+    imgs = np.stack([synth.synth_ct(s, n) for s in range(B)])
+    d_px = torch_cuda.from_numpy(imgs.view(np.int16)).cuda()
+    ws = torch_cuda.empty(int(L.cct_encode_workspace_bytes(3, n, n, 7)), dtype=torch_cuda.uint8, device="cuda")
+    cap = B * int(L.cct_file_bound(n, n))
+    arena = torch_cuda.empty(cap, dtype=torch_cuda.uint8, device="cuda")
+    off = torch_cuda.empty(B + 1, dtype=torch_cuda.int64, device="cuda")
+    st = torch_cuda.empty(B, dtype=torch_cuda.int32, device="cuda")
+    native.check(L.cct_encode_batch(d_px.data_ptr(), B, n, n, 7, arena.data_ptr(), cap, off.data_ptr(), st.data_ptr(),
+                                    None, ws.data_ptr(), ws.numel(), torch_cuda.cuda.current_stream().cuda_stream))
+    torch_cuda.cuda.synchronize()
+    h_arena, h_off = arena.cpu().numpy(), off.cpu().numpy()
+    for i in range(B):
+        assert h_arena[h_off[i]:h_off[i + 1]].tobytes() == oracle.encode(imgs[i]), i
+    dws = torch_cuda.empty(int(L.cct_decode_workspace_bytes(4, n, n)), dtype=torch_cuda.uint8, device="cuda")
+    px = torch_cuda.empty((B, n, n), dtype=torch_cuda.int16, device="cuda")
+    native.check(L.cct_decode_batch(arena.data_ptr(), off.data_ptr(), B, n, n, px.data_ptr(), st.data_ptr(),
+                                    dws.data_ptr(), dws.numel(), torch_cuda.cuda.current_stream().cuda_stream))
+    torch_cuda.cuda.synchronize()
+    assert not st.cpu().numpy().any() and torch_cuda.equal(px, d_px)
+    # too small for even one image -> error code, not a crash
+    rc = L.cct_encode_batch(d_px.data_ptr(), B, n, n, 7, arena.data_ptr(), cap, off.data_ptr(), st.data_ptr(), None,
+                            ws.data_ptr(), 1024, None)
+    assert rc == native.E_WORKSPACE
+
+
+def test_errors_and_domain(torch_cuda, pkg, oracle, native):
+    cfg = pkg.default_config()
+    with pytest.raises(ValueError):
+        pkg.Encoder(cfg, np.zeros((6, 6), dtype=np.uint16)).encode()  # N % 16 (core.py:245)
+    with pytest.raises(ValueError):
+        pkg.Decoder(cfg, b"lite" + bytes(40)).decode()  # bad magic (core.py:388-389)
+    bad = dict(cfg, encoder=dict(cfg["encoder"], transforms=dict(cfg["encoder"]["transforms"], delta=False)))
+    with pytest.raises(NotImplementedError):
+        pkg.Encoder(bad, np.zeros((16, 16), dtype=np.uint16)).encode()
+    zip_ = dict(cfg, encoder=dict(cfg["encoder"], transforms=dict(cfg["encoder"]["transforms"], zipper=True)))
+    with pytest.raises(NotImplementedError):
+        pkg.Encoder(zip_, np.zeros((16, 16), dtype=np.uint16)).encode()
+    # out of the lossless domain: encoder bytes still exact, status flags it, decoder raises like the reference
+    img = np.full((32, 32), 3000, dtype=np.uint16)
+    enc = pkg.Encoder(cfg, img)
+    out = enc.encode()
+    assert out == oracle.encode(img) and not enc.domain_ok
+    with pytest.raises(OverflowError):
+        oracle.decode(out)
+    with pytest.raises(OverflowError):
+        pkg.Decoder(cfg, out).decode()
+    # corrupt zlib stream -> zlib.error like the reference
+    good = bytearray(pkg.Encoder(cfg, np.zeros((32, 32), dtype=np.uint16)).encode())
+    good[-2] ^= 0xFF
+    with pytest.raises(zlib.error):
+        pkg.Decoder(cfg, bytes(good)).decode()
+    # arena too small -> error, not an overrun
+    L = native.lib()
+    arena = np.zeros(64, dtype=np.uint8); off = np.zeros(2, dtype=np.int64); st = np.zeros(1, dtype=np.uint32)
+    rc = L.cct_encode_host(img.ctypes.data, 1, 32, 32, 7, arena.ctypes.data, 64, off.ctypes.data, st.ctypes.data, None, -1)
+    assert rc == native.E_CAPACITY and (st[0] & native.ST_CAPACITY)
+
+
+def test_config_batch_roundtrip_4096(torch_cuda, pkg, synth, oracle):
+    """BASELINE.json configs[1] at full size through size-independent properties: every bytestream length and a
+    checksum of checksums equal the oracle's, and decode(encode(x)) == x for all 4096 slices."""
+    import os
+    B = 4096
+    base = synth.synth_ct_batch(range(256), workers=min(32, os.cpu_count() or 8))
+    imgs = np.concatenate([base] * (B // 256))  # seeds repeat mod 256: bounded CPU time, full-size batch
+    d_imgs = torch_cuda.from_numpy(imgs.view(np.int16)).cuda()
+    arena, offsets, status = pkg.encode_batch(d_imgs)
+    assert not status.cpu().numpy().any()
+    h_off = offsets.cpu().numpy()
+    want_arena, want_off = oracle.encode_batch(base, nthreads=min(32, os.cpu_count() or 8))
+    lens = np.diff(h_off)
+    assert (lens.reshape(B // 256, 256) == np.diff(want_off)[None, :]).all()
+    h_arena = arena[:h_off[-1]].cpu().numpy()
+    assert h_arena[:want_off[-1]].tobytes() == want_arena.tobytes()
+    rep = h_arena.reshape(B // 256, -1)
+    assert (rep == rep[0]).all()  # identical inputs -> identical bytes in every replica
+    px, dst = pkg.decode_batch(arena, offsets, (512, 512))
+    assert not dst.cpu().numpy().any()
+    assert torch_cuda.equal(px.view(torch_cuda.int16), d_imgs)
