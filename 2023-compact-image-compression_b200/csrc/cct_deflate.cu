@@ -17,7 +17,7 @@
 
 namespace cct {
 
-constexpr int kProbeK = 32;
+constexpr int kProbeK = 64;  // loop steps of the parallel probe (run groups count as one step)
 
 static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
@@ -33,6 +33,8 @@ size_t deflate_ws_carve(DeflateWs *ws, void *mem, int B, int64_t max_len) {
     ws->stride = align_up(max_len + 16, 16);
     ws->max_blocks = (int)(max_len / kSymEnd + 2);
     ws->dist16 = (uint16_t *)take((size_t)B * ws->stride * sizeof(uint16_t));
+    ws->rb16 = (uint16_t *)take((size_t)B * ws->stride * sizeof(uint16_t));
+    ws->rl16 = (uint16_t *)take((size_t)B * ws->stride * sizeof(uint16_t));
     ws->mtab = (uint32_t *)take((size_t)B * ws->stride * sizeof(uint32_t));
     ws->syms = (uint32_t *)take((size_t)B * ws->stride * sizeof(uint32_t));
     ws->blk_end = (int32_t *)take((size_t)B * ws->max_blocks * sizeof(int32_t));
@@ -46,18 +48,23 @@ size_t deflate_ws_carve(DeflateWs *ws, void *mem, int B, int64_t max_len) {
 // ------------------------------------------------------------------ k_chains
 // head[h] holds the low 16 bits of the latest position with hash h.  Entries are kept unambiguous by a
 // sweep every 8192 positions that re-parks everything older than 32767 at "49152 behind".
+// The same warp also records, for every position, how many equal bytes precede it (rb16, forward pass) and
+// follow it (rl16, reverse pass): chain_walk uses them to consume whole runs in one step.
 constexpr int kHeadEntries = 32768;
 __global__ void __launch_bounds__(32) k_chains(const uint8_t *__restrict__ in, int64_t in_stride,
                                                const int32_t *__restrict__ in_len, uint16_t *__restrict__ dist16,
-                                               int64_t stride) {
+                                               uint16_t *__restrict__ rb16, uint16_t *__restrict__ rl16, int64_t stride) {
     extern __shared__ uint16_t head[];
     const int stream = blockIdx.x, lane = threadIdx.x;
     const int n = in_len[stream];
     const uint8_t *w = in + (int64_t)stream * in_stride;
     uint16_t *d16 = dist16 + (int64_t)stream * stride;
+    uint16_t *rb = rb16 + (int64_t)stream * stride;
+    uint16_t *rl = rl16 + (int64_t)stream * stride;
     uint32_t *head32 = reinterpret_cast<uint32_t *>(head);
     for (int i = lane; i < kHeadEntries / 2; i += 32) head32[i] = 0x40004000u;  // (0 - 49152) & 0xFFFF
     __syncwarp();
+    int carry = 0;  // rb of position base-1
     for (int base = 0; base < n; base += 32) {
         if (base && (base & 8191) == 0) {
             const uint32_t far = (uint32_t)(base - 49152) & 0xFFFFu;
@@ -85,39 +92,115 @@ __global__ void __launch_bounds__(32) k_chains(const uint8_t *__restrict__ in, i
                 dist = (d >= 1u && d < 32768u) ? (int)d : 0;
             }
         }
+        // equal-to-previous flags -> count of equal bytes before s
+        const bool eq = s >= 1 && s < n && w[s] == w[s - 1];
+        const unsigned em = __ballot_sync(0xffffffffu, eq);
+        const unsigned zeros_below = ~em & ((2u << lane) - 1u);  // positions <= lane whose flag is 0
+        int back = zeros_below ? lane - (31 - __clz((int)zeros_below)) : lane + 1 + carry;
+        if (back > 65535) back = 65535;
+        carry = __shfl_sync(0xffffffffu, back, 31);
         __syncwarp();
         if (valid && (peers >> lane) == 1u) head[h] = (uint16_t)s;
-        if (s < n) d16[s] = (uint16_t)dist;
+        if (s < n) { d16[s] = (uint16_t)dist; rb[s] = (uint16_t)back; }
         __syncwarp();
+    }
+    // reverse pass: count of equal bytes after s
+    carry = 0;  // rl of position base+32
+    for (int base = ((n - 1) / 32) * 32; base >= 0; base -= 32) {
+        const int s = base + lane;
+        const bool eq = s + 1 < n && w[s] == w[s + 1];
+        const unsigned em = __ballot_sync(0xffffffffu, eq);
+        const unsigned zeros_above = ~em & ~((1u << lane) - 1u);  // positions >= lane whose flag is 0
+        int fwd = zeros_above ? (__ffs((int)zeros_above) - 1) - lane : (32 - lane) + carry;
+        if (fwd > 65535) fwd = 65535;
+        carry = __shfl_sync(0xffffffffu, fwd, 0);
+        if (s < n) rl[s] = (uint16_t)fwd;
     }
 }
 
 // ------------------------------------------------------------------ k_probe
 __global__ void __launch_bounds__(256) k_probe(const uint8_t *__restrict__ in, int64_t in_stride,
                                                const int32_t *__restrict__ in_len, const uint16_t *__restrict__ dist16,
+                                               const uint16_t *__restrict__ rb16, const uint16_t *__restrict__ rl16,
                                                uint32_t *__restrict__ mtab, int64_t stride) {
     const int stream = blockIdx.y;
     const int n = in_len[stream];
     const int s = blockIdx.x * 256 + threadIdx.x;
     if (s >= n) return;
-    LzView v{in + (int64_t)stream * in_stride, dist16 + (int64_t)stream * stride, n};
-    mtab[(int64_t)stream * stride + s] = match_probe(v, s, kProbeK);
+    const int64_t o = (int64_t)stream * stride;
+    LzView v{in + (int64_t)stream * in_stride, dist16 + o, rb16 + o, rl16 + o, n};
+    mtab[o + s] = match_probe(v, s, kProbeK);
 }
 
 // ------------------------------------------------------------------ k_parse
+// One warp per stream.  Lane 0 runs deflate_slow's state machine (parse_span) over a window of the probe table
+// staged in shared memory while lanes 1..31 fetch the next window; symbols are collected in shared memory and
+// written out by the whole warp.
+constexpr int kParseWin = 512;   // positions per staged window
+constexpr int kParseSyms = 512;  // symbol buffer entries
+struct ParseSmem {
+    uint32_t tab[2][kParseWin];
+    uint8_t wprev[2][kParseWin + 4];
+    uint32_t sym[kParseSyms];
+    ParseState st;
+    int produced;
+};
+
+__device__ __forceinline__ void parse_stage(ParseSmem &sm, int buf, const uint32_t *mt, const uint8_t *w, int wbase, int n,
+                                            int lane, int nlanes) {
+    // tab[i] = mtab[wbase + i], wprev[i] = w[wbase + i - 1]
+    const int cnt = min(kParseWin, n - wbase);
+    for (int i = lane; i < cnt; i += nlanes) {
+        sm.tab[buf][i] = mt[wbase + i];
+        sm.wprev[buf][i] = wbase + i >= 1 ? w[wbase + i - 1] : 0;
+    }
+}
+
 __global__ void __launch_bounds__(32) k_parse(const uint8_t *__restrict__ in, int64_t in_stride,
                                               const int32_t *__restrict__ in_len, const uint16_t *__restrict__ dist16,
+                                              const uint16_t *__restrict__ rb16, const uint16_t *__restrict__ rl16,
                                               const uint32_t *__restrict__ mtab, uint32_t *__restrict__ syms, int64_t stride,
                                               int32_t *__restrict__ blk_end, int max_blocks, int32_t *__restrict__ nsym,
                                               int32_t *__restrict__ nflush) {
-    const int stream = blockIdx.x;
-    if (threadIdx.x != 0) return;
-    LzView v{in + (int64_t)stream * in_stride, dist16 + (int64_t)stream * stride, in_len[stream]};
-    int nf = 0;
-    int ns = parse_stream(v, mtab + (int64_t)stream * stride, syms + (int64_t)stream * stride,
-                          blk_end + (int64_t)stream * max_blocks, &nf);
-    nsym[stream] = ns;
-    nflush[stream] = nf;
+    __shared__ ParseSmem sm;
+    const int stream = blockIdx.x, lane = threadIdx.x;
+    const int64_t o = (int64_t)stream * stride;
+    const int n = in_len[stream];
+    const uint8_t *w = in + (int64_t)stream * in_stride;
+    LzView v{w, dist16 + o, rb16 + o, rl16 + o, n};
+    const uint32_t *mt = mtab + o;
+    uint32_t *out = syms + o;
+    int32_t *be = blk_end + (int64_t)stream * max_blocks;
+    if (lane == 0) parse_init(sm.st);
+    if (n > 0) parse_stage(sm, 0, mt, w, 0, n, lane, 32);
+    __syncwarp();
+    int written = 0;  // symbols already flushed to global (warp-uniform)
+    int buf = 0;
+    for (int wbase = 0; wbase < n; wbase += kParseWin, buf ^= 1) {
+        const int wend = min(wbase + kParseWin, n);
+        bool staged_next = false;
+        for (;;) {  // lane 0 may need several rounds if the symbol buffer fills up
+            if (lane == 0) {
+                sm.produced = sm.st.s < wend
+                    ? parse_span(v, sm.st, wend, sm.tab[buf], wbase, sm.wprev[buf], wbase, sm.sym, kParseSyms, be) : 0;
+            } else if (!staged_next && wend < n) {
+                parse_stage(sm, buf ^ 1, mt, w, wend, n, lane - 1, 31);
+            }
+            staged_next = true;
+            __syncwarp();
+            const int k = sm.produced;
+            for (int i = lane; i < k; i += 32) out[written + i] = sm.sym[i];
+            written += k;
+            const bool more = sm.st.s < wend;
+            __syncwarp();
+            if (!more) break;
+        }
+    }
+    if (lane == 0) {
+        written += parse_finish(v, sm.st, out + written);
+        nsym[stream] = written;
+        nflush[stream] = sm.st.nfl;
+    }
 }
 
 // ------------------------------------------------------------------ k_adler
@@ -314,14 +397,14 @@ void launch_deflate(const uint8_t *in, int64_t in_stride, const int32_t *in_len,
         attr_done = true;
     }
     { CCT_KERNEL(k_chains, st);
-    k_chains<<<B, 32, chain_smem, st>>>(in, in_stride, in_len, ws.dist16, ws.stride);
+    k_chains<<<B, 32, chain_smem, st>>>(in, in_stride, in_len, ws.dist16, ws.rb16, ws.rl16, ws.stride);
     }
     dim3 gp((unsigned)((max_len + 255) / 256), (unsigned)B);
     { CCT_KERNEL(k_probe, st);
-    k_probe<<<gp, 256, 0, st>>>(in, in_stride, in_len, ws.dist16, ws.mtab, ws.stride);
+    k_probe<<<gp, 256, 0, st>>>(in, in_stride, in_len, ws.dist16, ws.rb16, ws.rl16, ws.mtab, ws.stride);
     }
     { CCT_KERNEL(k_parse, st);
-    k_parse<<<B, 32, 0, st>>>(in, in_stride, in_len, ws.dist16, ws.mtab, ws.syms, ws.stride, ws.blk_end, ws.max_blocks,
+    k_parse<<<B, 32, 0, st>>>(in, in_stride, in_len, ws.dist16, ws.rb16, ws.rl16, ws.mtab, ws.syms, ws.stride, ws.blk_end, ws.max_blocks,
                               ws.nsym, ws.nflush);
     }
     { CCT_KERNEL(k_adler, st);

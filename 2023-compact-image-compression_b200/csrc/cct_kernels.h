@@ -32,7 +32,8 @@ void launch_emit(const uint16_t *hv, const uint8_t *jump, const uint8_t *taken, 
 
 // ---- cct_deflate.cu
 struct DeflateWs {  // device scratch for one pass over B streams of capacity max_len
-    uint16_t *dist16;    // [B][stride]
+    uint16_t *dist16;    // [B][stride] chain links
+    uint16_t *rb16, *rl16;  // [B][stride] equal bytes before / after each position
     uint32_t *mtab;      // [B][stride]
     uint32_t *syms;      // [B][stride]
     int32_t *blk_end;    // [B][max_blocks]

@@ -17,6 +17,14 @@
 #pragma once
 #include "cct_common.cuh"
 
+// Work counters for the CPU harness (tests/hostsim defines CCT_STATS); compiled out of the kernels.
+#if defined(CCT_STATS) && !defined(__CUDA_ARCH__)
+extern long long cct_stat[8];
+#define CCT_COUNT(i) (cct_stat[i]++)
+#else
+#define CCT_COUNT(i) ((void)0)
+#endif
+
 namespace cct {
 
 // ------------------------------------------------------------------------------------------------
@@ -73,6 +81,8 @@ CCT_HD uint32_t static_lcode(int n) {
 struct LzView {
     const uint8_t *w;        // payload bytes
     const uint16_t *dist16;  // chain links: distance to previous same-hash position, 0 = none / >= 32768
+    const uint16_t *rb16;    // number of bytes equal to w[p] immediately before p (capped at 65535)
+    const uint16_t *rl16;    // number of bytes equal to w[p] immediately after p  (capped at 65535)
     int n;                   // payload length
 };
 
@@ -82,32 +92,79 @@ CCT_HD int match_extend(const uint8_t *a, const uint8_t *b, int from, int cap) {
     return len;
 }
 
-// Cold-start probe over at most K chain entries (deflate.c longest_match with best_len = 2).
-// The answer for any prev_length follows from it when the probe is complete: the search result is the
-// first-visited candidate attaining the maximum length.
-CCT_HD uint32_t match_probe(const LzView &v, int s, int K) {
-    int look = v.n - s;
-    if (look < kMinMatch) return 0;
-    int d0 = v.dist16[s];
-    if (d0 == 0 || d0 > kMaxDist) return 0;
-    int cap = look < kMaxMatch ? look : kMaxMatch;
+// How a chain walk ended.
+constexpr int kWalkDone = 0;    // chain end, distance limit or a match of the maximum useful length
+constexpr int kWalkBudget = 1;  // chain budget exhausted
+constexpr int kWalkSteps = 2;   // step cap of the probe reached
+
+// longest_match's candidate loop (deflate.c), walking the chain of position s from its head.
+//   best / bdist   in: best_len to beat (prev_length, or 2 for a cold start); out: result
+//   chain          number of candidates that may still be visited (max_chain_length, quartered by the caller)
+//   max_steps      cap on LOOP STEPS (not candidates) for the parallel probe
+// One loop step handles either a single candidate or a whole RUN GROUP.  When the target starts with R >= 3
+// copies of a byte c and the candidate `cur` also starts with (c,c,c), the chain entries below cur inside that
+// run are exactly the consecutive positions cur-1, cur-2, ... down to the run start (all have the hash of
+// (c,c,c)), and the match length of the i-th of them is known in closed form from its count of leading c's,
+// m + i: m+i if m+i < R, "R + whatever follows" if m+i == R, exactly R if m+i > R (R < cap), cap if R == cap.
+// Since only the first-visited candidate attaining the maximum matters, the group is consumed in
+// one step; the chain budget and the distance limit are charged as if every member had been visited.
+CCT_HD int chain_walk(const LzView &v, int s, int cap, int &best, int &bdist, int chain, int max_steps) {
     const uint8_t *b = v.w + s;
-    int best = 2, bdist = 0, cur = s - d0;
-    for (int cnt = 1;; cnt++) {
+    int R = 0;  // leading run of the target, if it is at least one hash triple long
+    if (b[1] == b[0] && b[2] == b[0]) { R = (int)v.rl16[s] + 1; if (R > cap) R = cap; }
+    int cur = s - v.dist16[s];
+    for (int step = 1;; step++) {
+        CCT_COUNT(0);
         const uint8_t *a = v.w + cur;
-        if (a[best] == b[best] && a[best - 1] == b[best - 1] && a[0] == b[0] && a[1] == b[1]) {
-            int len = match_extend(a, b, 2, cap);
+        if (R && a[0] == b[0] && v.rl16[cur] >= 2) {
+            const int m = (int)v.rl16[cur] + 1;  // leading c's of the top candidate
+            int t = v.rb16[cur];                 // further candidates of this run below cur
+            if (cur - t < 1) t = cur - 1;        // position 0 is never in a chain
+            const int count_dist = kMaxDist - (s - cur);
+            int nvis = t + 1;
+            if (chain < nvis) nvis = chain;
+            if (count_dist < nvis) nvis = count_dist;
+            const int i_key = m >= R ? 0 : R - m;  // first member with at least R leading c's
+            if (R < cap && m > R) {
+                if (R > best) { best = R; bdist = s - cur; }
+            } else if (i_key < nvis) {
+                const int c_al = cur - i_key;
+                const int L = R < cap ? match_extend(v.w + c_al, b, R, cap) : cap;
+                if (L > best) { best = L; bdist = s - c_al; if (L >= cap) return kWalkDone; }
+            } else {
+                const int L = m + nvis - 1;  // only members with fewer than R leading c's were reached
+                if (L > best) { best = L; bdist = s - (cur - (nvis - 1)); }
+            }
+            if (nvis < t + 1) return nvis == count_dist ? kWalkDone : kWalkBudget;
+            chain -= t;
+            cur -= t;
+        } else if (a[best] == b[best] && a[best - 1] == b[best - 1] && a[0] == b[0] && a[1] == b[1]) {
+            const int len = match_extend(a, b, 2, cap);
             if (len > best) {
                 best = len; bdist = s - cur;
-                if (len >= cap) break;
+                if (len >= cap) return kWalkDone;
             }
         }
-        int dl = v.dist16[cur];
-        if (dl == 0) break;
+        const int dl = v.dist16[cur];
+        if (dl == 0) return kWalkDone;
         cur -= dl;
-        if (s - cur >= kMaxDist) break;  // cur <= limit
-        if (cnt == K) return kProbeIncomplete;
+        if (s - cur >= kMaxDist) return kWalkDone;  // cur <= limit
+        if (--chain == 0) return kWalkBudget;
+        if (step == max_steps) return kWalkSteps;
     }
+}
+
+// Cold-start probe (best_len = 2) over at most K loop steps.  Complete probes are valid for every parser
+// state: the answer for any prev_length is "the recorded match if it is longer" (SURVEY B.4), provided the walk
+// ended inside the smallest chain budget the parser ever applies (1024, deflate.c good_length rule).
+CCT_HD uint32_t match_probe(const LzView &v, int s, int K) {
+    const int look = v.n - s;
+    if (look < kMinMatch) return 0;
+    const int d0 = v.dist16[s];
+    if (d0 == 0 || d0 > kMaxDist) return 0;
+    const int cap = look < kMaxMatch ? look : kMaxMatch;
+    int best = 2, bdist = 0;
+    if (chain_walk(v, s, cap, best, bdist, kChainGood, K) != kWalkDone) return kProbeIncomplete;
     return best >= kMinMatch ? mtab_pack(best, bdist) : 0;
 }
 
@@ -115,25 +172,11 @@ CCT_HD uint32_t match_probe(const LzView &v, int s, int K) {
 // prev_length >= good_length 32).  Requires: valid head, prev_len < 258, prev_len < look.
 // Returns the improved length (> prev_len) and its distance, or 0.
 CCT_HD int match_full(const LzView &v, int s, int prev_len, int *out_dist) {
-    int look = v.n - s;
-    int cap = look < kMaxMatch ? look : kMaxMatch;
-    const uint8_t *b = v.w + s;
-    int best = prev_len, bdist = 0, cur = s - v.dist16[s];
-    int chain = prev_len >= kGoodLen ? kChainGood : kChainFull;
-    do {
-        const uint8_t *a = v.w + cur;
-        if (a[best] == b[best] && a[best - 1] == b[best - 1] && a[0] == b[0] && a[1] == b[1]) {
-            int len = match_extend(a, b, 2, cap);
-            if (len > best) {
-                best = len; bdist = s - cur;
-                if (len >= cap) break;
-            }
-        }
-        int dl = v.dist16[cur];
-        if (dl == 0) break;
-        cur -= dl;
-        if (s - cur >= kMaxDist) break;
-    } while (--chain != 0);
+    const int look = v.n - s;
+    const int cap = look < kMaxMatch ? look : kMaxMatch;
+    int best = prev_len, bdist = 0;
+    CCT_COUNT(1);
+    chain_walk(v, s, cap, best, bdist, prev_len >= kGoodLen ? kChainGood : kChainFull, 0x7FFFFFFF);
     *out_dist = bdist;
     return best > prev_len ? best : 0;
 }
@@ -141,19 +184,31 @@ CCT_HD int match_full(const LzView &v, int s, int prev_len, int *out_dist) {
 // ------------------------------------------------------------------------------------------------
 // deflate_slow as a walk over the probe table
 // ------------------------------------------------------------------------------------------------
-// Writes LZ77 symbols to syms[] and, for every in-loop flush (16383 symbols tallied), the payload
-// position at which the block ended to blk_end[].  Returns the number of symbols; *n_flush = number of
-// in-loop flushes.  The final block (last = 1) holds symbols [16383 * n_flush, nsym) and ends at n
-// (it may be empty, and the trailing literal never triggers a flush).
-CCT_HD int parse_stream(const LzView &v, const uint32_t *mtab, uint32_t *syms, int32_t *blk_end, int *n_flush) {
+// The state machine is resumable so the kernel can run it over staged windows: `parse_span` walks positions
+// while st.s < s_end, reading the probe table as tab[s - tab_base] and the byte BEFORE position s as
+// wprev[s - wprev_base], and appends LZ77 symbols to out[] (at most out_cap; it stops early when full and
+// can simply be called again).  Every in-loop flush (16383 symbols tallied) records the payload position at
+// which the block ended in blk_end[].  `parse_finish` emits the trailing literal (it never
+// triggers a flush; the final block holds symbols [16383 * nfl, nsym) and may be empty).
+struct ParseState {
+    int s, match_len, match_dist, nsym, in_block, nfl;
+    bool avail;
+};
+CCT_HD void parse_init(ParseState &st) {
+    st.s = 0; st.match_len = 2; st.match_dist = 0; st.nsym = 0; st.in_block = 0; st.nfl = 0; st.avail = false;
+}
+
+CCT_HD int parse_span(const LzView &v, ParseState &st, int s_end, const uint32_t *tab, int tab_base,
+                      const uint8_t *wprev, int wprev_base, uint32_t *out, int out_cap, int32_t *blk_end) {
     const int n = v.n;
-    int s = 0, match_len = 2, match_dist = 0, nsym = 0, nfl = 0, in_block = 0;
-    bool avail = false;
-    while (s < n) {
-        int look = n - s;
-        int prev_len = match_len, prev_dist = match_dist;
+    int k = 0;
+    int s = st.s, match_len = st.match_len, match_dist = st.match_dist, in_block = st.in_block;
+    bool avail = st.avail;
+    while (s < s_end && k < out_cap) {
+        const int look = n - s;
+        const int prev_len = match_len, prev_dist = match_dist;
         match_len = 2;
-        uint32_t e = look >= kMinMatch ? mtab[s] : 0u;
+        const uint32_t e = look >= kMinMatch ? tab[s - tab_base] : 0u;
         if (e != 0 && prev_len < kMaxMatch && prev_len < look) {
             int ml = 0, md = 0;
             if (e & kProbeIncomplete) ml = match_full(v, s, prev_len, &md);
@@ -162,21 +217,41 @@ CCT_HD int parse_stream(const LzView &v, const uint32_t *mtab, uint32_t *syms, i
             if (ml) { match_len = ml; match_dist = md; }
         }
         if (prev_len >= kMinMatch && match_len <= prev_len) {
-            syms[nsym++] = sym_pack(prev_len - kMinMatch, prev_dist);
+            out[k++] = sym_pack(prev_len - kMinMatch, prev_dist);
             s += prev_len - 1;
             avail = false; match_len = 2;
-            if (++in_block == kSymEnd) { blk_end[nfl++] = s; in_block = 0; }
+            if (++in_block == kSymEnd) { blk_end[st.nfl++] = s; in_block = 0; }
         } else if (avail) {
-            syms[nsym++] = sym_pack(v.w[s - 1], 0);
-            if (++in_block == kSymEnd) { blk_end[nfl++] = s; in_block = 0; }
+            out[k++] = sym_pack(wprev[s - wprev_base], 0);
+            if (++in_block == kSymEnd) { blk_end[st.nfl++] = s; in_block = 0; }
             s++;
         } else {
             avail = true; s++;
         }
     }
-    if (avail) syms[nsym++] = sym_pack(v.w[n - 1], 0);
-    *n_flush = nfl;
-    return nsym;
+    st.s = s; st.match_len = match_len; st.match_dist = match_dist; st.in_block = in_block; st.avail = avail;
+    st.nsym += k;
+    return k;
+}
+
+// Trailing literal after the loop (deflate.c: `if (s->match_available) _tr_tally_lit(...)`).  Returns 0 or 1.
+CCT_HD int parse_finish(const LzView &v, ParseState &st, uint32_t *out) {
+    if (!st.avail) return 0;
+    out[0] = sym_pack(v.w[v.n - 1], 0);
+    st.avail = false;
+    st.nsym += 1;
+    return 1;
+}
+
+// Whole-stream convenience wrapper (CPU harness).
+CCT_HD int parse_stream(const LzView &v, const uint32_t *mtab, uint32_t *syms, int32_t *blk_end, int *n_flush) {
+    ParseState st;
+    parse_init(st);
+    int total = 0;
+    while (st.s < v.n) total += parse_span(v, st, v.n, mtab, 0, v.w, 1, syms + total, 0x7FFFFFFF, blk_end);
+    total += parse_finish(v, st, syms + total);
+    *n_flush = st.nfl;
+    return total;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -7,10 +7,13 @@
 #include <cstring>
 #include <vector>
 
+#define CCT_STATS 1
 #include "deflate_core.cuh"
 #include "inflate_core.cuh"
 
 using namespace cct;
+
+long long cct_stat[8];
 
 static void chains_reference(const uint8_t *w, int n, std::vector<uint16_t> &dist16) {
     // dist16[s] = s - (latest p < s, p >= 1, with hash3(p) == hash3(s)), 0 if none or >= 32768
@@ -22,6 +25,13 @@ static void chains_reference(const uint8_t *w, int n, std::vector<uint16_t> &dis
         if (p != 0 && s - p < 32768) dist16[s] = (uint16_t)(s - p);
         head[h] = s;  // position 0 is stored as 0 == NIL, exactly like zlib
     }
+}
+
+static void runs_reference(const uint8_t *w, int n, std::vector<uint16_t> &rb16, std::vector<uint16_t> &rl16) {
+    rb16.assign((size_t)n + 1, 0);
+    rl16.assign((size_t)n + 1, 0);
+    for (int p = 1; p < n; p++) rb16[p] = w[p] == w[p - 1] ? (uint16_t)(rb16[p - 1] == 65535 ? 65535 : rb16[p - 1] + 1) : 0;
+    for (int p = n - 2; p >= 0; p--) rl16[p] = w[p] == w[p + 1] ? (uint16_t)(rl16[p + 1] == 65535 ? 65535 : rl16[p + 1] + 1) : 0;
 }
 
 static uint32_t adler32_(const uint8_t *p, int64_t n) {
@@ -38,18 +48,24 @@ static uint32_t adler32_(const uint8_t *p, int64_t n) {
 extern "C" {
 
 // Staged zlib-9 of src[0..n).  probe_k = chain entries examined by the parallel probe.
-// stats[0] = symbols, [1] = blocks, [2] = incomplete probes hit by the walk (filled if non-null).
+// stats[0] = symbols, [1] = blocks, [2] = incomplete probe entries, [3] = probe loop steps, [4] = loop steps of the
+// on-demand searches made by the walk (stats must hold 5 values if non-null).
 int64_t hs_deflate(const uint8_t *src, int n, uint8_t *dst, int64_t cap, int probe_k, int64_t *stats) {
+    long long c0 = cct_stat[0];
     std::vector<uint16_t> dist16;
     chains_reference(src, n, dist16);
-    LzView v{src, dist16.data(), n};
+    std::vector<uint16_t> rb16, rl16;
+    runs_reference(src, n, rb16, rl16);
+    LzView v{src, dist16.data(), rb16.data(), rl16.data(), n};
     std::vector<uint32_t> mtab((size_t)n + 1, 0);
     int64_t n_incomplete = 0;
     for (int s = 0; s < n; s++) { mtab[s] = match_probe(v, s, probe_k); n_incomplete += (mtab[s] & kProbeIncomplete) != 0; }
+    long long c1 = cct_stat[0];
     std::vector<uint32_t> syms((size_t)n + 1);
     std::vector<int32_t> blk_end((size_t)n / kSymEnd + 2);
     int n_flush = 0;
     int nsym = parse_stream(v, mtab.data(), syms.data(), blk_end.data(), &n_flush);
+    long long c2 = cct_stat[0];
     int nblk = n_flush + 1;
     std::vector<BlockDesc> desc((size_t)nblk);
     BlockWork *wk = new BlockWork;
@@ -101,11 +117,13 @@ int64_t hs_deflate(const uint8_t *src, int n, uint8_t *dst, int64_t cap, int pro
     uint32_t ad = adler32_(src, n);
     int64_t len = (int64_t)(bit >> 3);
     out[len++] = (uint8_t)(ad >> 24); out[len++] = (uint8_t)(ad >> 16); out[len++] = (uint8_t)(ad >> 8); out[len++] = (uint8_t)ad;
-    if (stats) { stats[0] = nsym; stats[1] = nblk; stats[2] = n_incomplete; }
+    if (stats) { stats[0] = nsym; stats[1] = nblk; stats[2] = n_incomplete; stats[3] = c1 - c0; stats[4] = c2 - c1; }
     if (len > cap) return -1;
     memcpy(dst, out.data(), (size_t)len);
     return len;
 }
+
+void hs_stats(long long *out, int reset) { for (int i = 0; i < 8; i++) { out[i] = cct_stat[i]; if (reset) cct_stat[i] = 0; } }
 
 int hs_inflate(const uint8_t *in, int in_len, uint8_t *out, int out_cap) {
     InflateTables *tb = new InflateTables;

@@ -302,7 +302,7 @@ def test_errors_and_domain(torch_cuda, pkg, oracle, native):
     # arena too small -> error, not an overrun
     L = native.lib()
     arena = np.zeros(64, dtype=np.uint8); off = np.zeros(2, dtype=np.int64); st = np.zeros(1, dtype=np.uint32)
-    rc = L.cct_encode_host(img.ctypes.data, 1, 32, 32, 7, arena.ctypes.data, 64, off.ctypes.data, st.ctypes.data, None, -1)
+    rc = L.cct_encode_host(img.ctypes.data, 1, 32, 32, 7, arena.ctypes.data, 20, off.ctypes.data, st.ctypes.data, None, -1)
     assert rc == native.E_CAPACITY and (st[0] & native.ST_CAPACITY)
 
 

@@ -39,7 +39,7 @@ def _hs_deflate(L, data, k):
     src = np.frombuffer(data, dtype=np.uint8) if data else np.zeros(1, np.uint8)
     cap = len(data) + len(data) // 1000 * 6 + 1024
     out = np.empty(cap, np.uint8)
-    st = (C.c_int64 * 3)()
+    st = (C.c_int64 * 5)()
     r = L.hs_deflate(_p(src, C.c_uint8), len(data), _p(out, C.c_uint8), cap, k, st)
     assert r >= 0, r
     return out[:r].tobytes()
