@@ -32,6 +32,8 @@ size_t decode_ws_carve(DecodeWs *ws, void *mem, int B, int64_t n_px) {
     ws->slotA = (int32_t *)take((size_t)B * nb * sizeof(int32_t));
     ws->slotB = (int32_t *)take((size_t)B * nb * sizeof(int32_t));
     ws->fl = (uint8_t *)take((size_t)B);
+    ws->max_chunks = (int)(ws->pstride / kOpsChunk + 1);
+    ws->chunks = (OpsChunkSum *)take((size_t)B * ws->max_chunks * sizeof(OpsChunkSum));
     return used;
 }
 
@@ -100,16 +102,51 @@ __global__ void __launch_bounds__(32) k_dec_inflate(const uint8_t *__restrict__ 
     }
 }
 
-__global__ void __launch_bounds__(32) k_dec_ops(const uint8_t *__restrict__ payload, int64_t pstride,
-                                                const int32_t *__restrict__ plen, int n_px, uint16_t *__restrict__ vals,
-                                                uint8_t *__restrict__ jflag, int32_t *__restrict__ slotA,
-                                                int32_t *__restrict__ slotB, uint32_t *__restrict__ status) {
-    const int i = blockIdx.x;
-    if (threadIdx.x != 0 || status[i]) return;
+// Op stream -> values, in three parallel passes over fixed chunks (see inflate_core.cuh).
+__global__ void __launch_bounds__(128) k_dec_ops_scan(const uint8_t *__restrict__ payload, int64_t pstride,
+                                                      const int32_t *__restrict__ plen, OpsChunkSum *__restrict__ cs,
+                                                      int max_chunks, const uint32_t *__restrict__ status) {
+    const int i = blockIdx.y;
+    const int t = blockIdx.x * 128 + threadIdx.x;  // chunk * 2 + entry state
+    const int c = t >> 1, e = t & 1;
+    const int n = plen[i];
+    if (status[i] || c * kOpsChunk >= n) return;
+    int nops, dsum, ex;
+    ops_scan_chunk(payload + (int64_t)i * pstride, c * kOpsChunk, (c + 1) * kOpsChunk, n - 1, e, &nops, &dsum, &ex);
+    OpsChunkSum &o = cs[(int64_t)i * max_chunks + c];
+    o.nops[e] = nops; o.dsum[e] = dsum; o.exit_state[e] = (uint8_t)ex;
+}
+
+__global__ void __launch_bounds__(128) k_dec_ops_link(const int32_t *__restrict__ plen, OpsChunkSum *__restrict__ cs,
+                                                      int max_chunks, int n_px, uint32_t *__restrict__ status, int B) {
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= B || status[i]) return;
+    const int n_chunks = (plen[i] + kOpsChunk - 1) / kOpsChunk;
+    status[i] |= ops_link_chunks(cs + (int64_t)i * max_chunks, n_chunks, n_px);
+}
+
+__global__ void __launch_bounds__(128) k_dec_ops_emit(const uint8_t *__restrict__ payload, int64_t pstride,
+                                                      const int32_t *__restrict__ plen, const OpsChunkSum *__restrict__ cs,
+                                                      int max_chunks, int n_px, uint16_t *__restrict__ vals,
+                                                      uint8_t *__restrict__ jflag, uint32_t *__restrict__ status) {
+    const int i = blockIdx.y;
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    const int n = plen[i];
+    if ((status[i] & ~32u) || c * kOpsChunk >= n) return;
+    const uint32_t st = ops_emit_chunk(payload + (int64_t)i * pstride, c * kOpsChunk, (c + 1) * kOpsChunk, n - 1,
+                                       cs[(int64_t)i * max_chunks + c], n_px, vals + (int64_t)i * n_px,
+                                       jflag + (int64_t)i * (n_px / kBlock));
+    if (st) atomicOr(status + i, st);
+}
+
+// JUMP flags -> unit table, one thread per image (sequential first-unconsumed-block walk, core.py:459-464)
+__global__ void __launch_bounds__(32) k_dec_units(const uint8_t *__restrict__ jflag, int n_px, int32_t *__restrict__ slotA,
+                                                  int32_t *__restrict__ slotB, uint32_t *__restrict__ status, int B) {
+    const int i = blockIdx.x * 32 + threadIdx.x;
+    if (i >= B || (status[i] & ~32u)) return;
     const int nb = n_px / kBlock;
-    uint32_t st = ops_to_values(payload + (int64_t)i * pstride, plen[i], n_px, vals + (int64_t)i * n_px, jflag + (int64_t)i * nb);
-    if (!(st & 64u)) st |= resolve_units(jflag + (int64_t)i * nb, nb, slotA + (int64_t)i * nb, slotB + (int64_t)i * nb);
-    status[i] |= st;
+    const uint32_t st = resolve_units(jflag + (int64_t)i * nb, nb, slotA + (int64_t)i * nb, slotB + (int64_t)i * nb);
+    if (st) status[i] |= st;
 }
 
 __global__ void __launch_bounds__(256) k_dec_scatter(const uint16_t *__restrict__ vals, const int32_t *__restrict__ slotA,
@@ -145,8 +182,18 @@ void launch_decode(const uint8_t *files, const int64_t *offsets, int B, int rows
     { CCT_KERNEL(k_dec_inflate, st);
     k_dec_inflate<<<B, 32, 0, st>>>(files, offsets, ws.fl, ws.payload, ws.pstride, ws.plen, status);
     }
-    { CCT_KERNEL(k_dec_ops, st);
-    k_dec_ops<<<B, 32, 0, st>>>(ws.payload, ws.pstride, ws.plen, n_px, ws.vals, ws.jflag, ws.slotA, ws.slotB, status);
+    dim3 gs((unsigned)((2 * ws.max_chunks + 127) / 128), (unsigned)B), ge((unsigned)((ws.max_chunks + 127) / 128), (unsigned)B);
+    { CCT_KERNEL(k_dec_ops_scan, st);
+    k_dec_ops_scan<<<gs, 128, 0, st>>>(ws.payload, ws.pstride, ws.plen, ws.chunks, ws.max_chunks, status);
+    }
+    { CCT_KERNEL(k_dec_ops_link, st);
+    k_dec_ops_link<<<(B + 127) / 128, 128, 0, st>>>(ws.plen, ws.chunks, ws.max_chunks, n_px, status, B);
+    }
+    { CCT_KERNEL(k_dec_ops_emit, st);
+    k_dec_ops_emit<<<ge, 128, 0, st>>>(ws.payload, ws.pstride, ws.plen, ws.chunks, ws.max_chunks, n_px, ws.vals, ws.jflag, status);
+    }
+    { CCT_KERNEL(k_dec_units, st);
+    k_dec_units<<<(B + 31) / 32, 32, 0, st>>>(ws.jflag, n_px, ws.slotA, ws.slotB, status, B);
     }
     dim3 g((unsigned)((n_px + 255) / 256), (unsigned)B);
     { CCT_KERNEL(k_dec_scatter, st);

@@ -4,7 +4,7 @@
 // deflate_core.cuh for the decomposition and SURVEY.md Appendix B for the algorithm being matched):
 //   k_chains       hash-chain links for every position (warp per stream, head table in shared memory)
 //   k_probe        cold-start longest_match over the first kProbeK chain entries, one thread per position
-//   k_parse        deflate_slow's lazy state machine as a walk over the probe table (per stream)
+//   k_walk_spec / k_walk_stitch / k_symscan   deflate_slow's lazy state machine as a windowed speculative walk
 //   k_adler        Adler-32 of the payload (CTA per stream)
 //   k_block_build  per 16383-symbol block: histograms, build_tree x3, block-type choice, header bits
 //   k_layout       bit offsets of the blocks of each stream, stream length, zlib header/trailer
@@ -17,6 +17,7 @@
 
 namespace cct {
 
+constexpr int kWalkWin = 1024;  // positions per speculative parse window
 constexpr int kProbeK = 64;  // loop steps of the parallel probe (run groups count as one step)
 
 static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
@@ -37,6 +38,10 @@ size_t deflate_ws_carve(DeflateWs *ws, void *mem, int B, int64_t max_len) {
     ws->rl16 = (uint16_t *)take((size_t)B * ws->stride * sizeof(uint16_t));
     ws->mtab = (uint32_t *)take((size_t)B * ws->stride * sizeof(uint32_t));
     ws->syms = (uint32_t *)take((size_t)B * ws->stride * sizeof(uint32_t));
+    ws->rec = (uint32_t *)take((size_t)B * ws->stride * sizeof(uint32_t));
+    ws->flag = (uint8_t *)take((size_t)B * ws->stride);
+    ws->max_win = (int)(max_len / kWalkWin + 1);
+    ws->exits = (Walk *)take((size_t)B * ws->max_win * sizeof(Walk));
     ws->blk_end = (int32_t *)take((size_t)B * ws->max_blocks * sizeof(int32_t));
     ws->nsym = (int32_t *)take((size_t)B * sizeof(int32_t));
     ws->nflush = (int32_t *)take((size_t)B * sizeof(int32_t));
@@ -64,45 +69,66 @@ __global__ void __launch_bounds__(32) k_chains(const uint8_t *__restrict__ in, i
     uint32_t *head32 = reinterpret_cast<uint32_t *>(head);
     for (int i = lane; i < kHeadEntries / 2; i += 32) head32[i] = 0x40004000u;  // (0 - 49152) & 0xFFFF
     __syncwarp();
+    // The payload is staged 128 positions at a time: stage[i] = w[cbase - 4 + i], i in [0, 136), fetched two
+    // chunks ahead into registers so the dependent part of the loop only touches shared memory.
+    __shared__ __align__(16) uint8_t stage[136];
+    uint32_t *stage32 = reinterpret_cast<uint32_t *>(stage);
+    const uint32_t *w32 = reinterpret_cast<const uint32_t *>(w);  // stream base is 16-byte aligned
+    const int n_words = (n + 3) >> 2;
+    auto fetch = [&](int cbase, int j) -> uint32_t {  // word j of the chunk starting at cbase
+        const int wi = (cbase >> 2) - 1 + j;
+        return (wi >= 0 && wi < n_words) ? __ldg(w32 + wi) : 0u;
+    };
+    uint32_t p0 = fetch(0, lane), p0x = lane < 2 ? fetch(0, 32 + lane) : 0u;
+    uint32_t p1 = fetch(128, lane), p1x = lane < 2 ? fetch(128, 32 + lane) : 0u;
     int carry = 0;  // rb of position base-1
-    for (int base = 0; base < n; base += 32) {
-        if (base && (base & 8191) == 0) {
-            const uint32_t far = (uint32_t)(base - 49152) & 0xFFFFu;
-            for (int i = lane; i < kHeadEntries / 2; i += 32) {
-                uint32_t v = head32[i];
-                uint32_t lo = v & 0xFFFFu, hi = v >> 16;
-                if (((uint32_t)(base - lo) & 0xFFFFu) >= 32768u) lo = far;
-                if (((uint32_t)(base - hi) & 0xFFFFu) >= 32768u) hi = far;
-                head32[i] = lo | (hi << 16);
+    for (int cbase = 0; cbase < n; cbase += 128) {
+        stage32[lane] = p0;
+        if (lane < 2) stage32[32 + lane] = p0x;
+        p0 = p1; p0x = p1x;
+        p1 = fetch(cbase + 256, lane);
+        p1x = lane < 2 ? fetch(cbase + 256, 32 + lane) : 0u;
+        __syncwarp();
+#pragma unroll 1
+        for (int base = cbase; base < cbase + 128 && base < n; base += 32) {
+            if (base && (base & 8191) == 0) {
+                const uint32_t far = (uint32_t)(base - 49152) & 0xFFFFu;
+                for (int i = lane; i < kHeadEntries / 2; i += 32) {
+                    uint32_t v = head32[i];
+                    uint32_t lo = v & 0xFFFFu, hi = v >> 16;
+                    if (((uint32_t)(base - lo) & 0xFFFFu) >= 32768u) lo = far;
+                    if (((uint32_t)(base - hi) & 0xFFFFu) >= 32768u) hi = far;
+                    head32[i] = lo | (hi << 16);
+                }
+                __syncwarp();
             }
+            const int s = base + lane;
+            const uint8_t *sb = stage + 4 + (base - cbase) + lane;  // sb[k] = w[s + k], k in [-1, 2]
+            const bool valid = s >= 1 && s + 2 < n;  // position 0 doubles as NIL in zlib: never a match source
+            uint32_t h = 0x8000u | (uint32_t)lane;   // unique key for lanes that do not insert
+            if (valid) h = hash3(sb);
+            const unsigned peers = __match_any_sync(0xffffffffu, h);
+            const unsigned lower = peers & ((1u << lane) - 1u);
+            int dist = 0;
+            if (valid) {
+                if (lower) dist = lane - (31 - __clz((int)lower));
+                else {
+                    uint32_t d = (uint32_t)(s - head[h]) & 0xFFFFu;
+                    dist = (d >= 1u && d < 32768u) ? (int)d : 0;
+                }
+            }
+            // equal-to-previous flags -> count of equal bytes before s
+            const bool eq = s >= 1 && s < n && sb[0] == sb[-1];
+            const unsigned em = __ballot_sync(0xffffffffu, eq);
+            const unsigned zeros_below = ~em & ((2u << lane) - 1u);  // positions <= lane whose flag is 0
+            int back = zeros_below ? lane - (31 - __clz((int)zeros_below)) : lane + 1 + carry;
+            if (back > 65535) back = 65535;
+            carry = __shfl_sync(0xffffffffu, back, 31);
+            __syncwarp();
+            if (valid && (peers >> lane) == 1u) head[h] = (uint16_t)s;
+            if (s < n) { d16[s] = (uint16_t)dist; rb[s] = (uint16_t)back; }
             __syncwarp();
         }
-        const int s = base + lane;
-        const bool valid = s >= 1 && s + 2 < n;  // position 0 doubles as NIL in zlib: never a match source
-        uint32_t h = 0x8000u | (uint32_t)lane;   // unique key for lanes that do not insert
-        if (valid) h = hash3(w + s);
-        if (base + 640 < n) asm volatile("prefetch.global.L1 [%0];" ::"l"(w + base + 512 + 4 * lane));
-        const unsigned peers = __match_any_sync(0xffffffffu, h);
-        const unsigned lower = peers & ((1u << lane) - 1u);
-        int dist = 0;
-        if (valid) {
-            if (lower) dist = lane - (31 - __clz((int)lower));
-            else {
-                uint32_t d = (uint32_t)(s - head[h]) & 0xFFFFu;
-                dist = (d >= 1u && d < 32768u) ? (int)d : 0;
-            }
-        }
-        // equal-to-previous flags -> count of equal bytes before s
-        const bool eq = s >= 1 && s < n && w[s] == w[s - 1];
-        const unsigned em = __ballot_sync(0xffffffffu, eq);
-        const unsigned zeros_below = ~em & ((2u << lane) - 1u);  // positions <= lane whose flag is 0
-        int back = zeros_below ? lane - (31 - __clz((int)zeros_below)) : lane + 1 + carry;
-        if (back > 65535) back = 65535;
-        carry = __shfl_sync(0xffffffffu, back, 31);
-        __syncwarp();
-        if (valid && (peers >> lane) == 1u) head[h] = (uint16_t)s;
-        if (s < n) { d16[s] = (uint16_t)dist; rb[s] = (uint16_t)back; }
-        __syncwarp();
     }
     // reverse pass: count of equal bytes after s
     carry = 0;  // rl of position base+32
@@ -132,74 +158,96 @@ __global__ void __launch_bounds__(256) k_probe(const uint8_t *__restrict__ in, i
     mtab[o + s] = match_probe(v, s, kProbeK);
 }
 
-// ------------------------------------------------------------------ k_parse
-// One warp per stream.  Lane 0 runs deflate_slow's state machine (parse_span) over a window of the probe table
-// staged in shared memory while lanes 1..31 fetch the next window; symbols are collected in shared memory and
-// written out by the whole warp.
-constexpr int kParseWin = 512;   // positions per staged window
-constexpr int kParseSyms = 512;  // symbol buffer entries
-struct ParseSmem {
-    uint32_t tab[2][kParseWin];
-    uint8_t wprev[2][kParseWin + 4];
-    uint32_t sym[kParseSyms];
-    ParseState st;
-    int produced;
-};
-
-__device__ __forceinline__ void parse_stage(ParseSmem &sm, int buf, const uint32_t *mt, const uint8_t *w, int wbase, int n,
-                                            int lane, int nlanes) {
-    // tab[i] = mtab[wbase + i], wprev[i] = w[wbase + i - 1]
-    const int cnt = min(kParseWin, n - wbase);
-    for (int i = lane; i < cnt; i += nlanes) {
-        sm.tab[buf][i] = mt[wbase + i];
-        sm.wprev[buf][i] = wbase + i >= 1 ? w[wbase + i - 1] : 0;
-    }
+// ------------------------------------------------------------------ parse: k_walk_spec / k_walk_stitch / k_symscan
+// deflate_slow's lazy state machine, re-indexed by symbol start (deflate_core.cuh):
+//   k_walk_spec    one thread per kWalkWin-position window walks it speculatively from a cold start
+//   k_walk_stitch  one thread per stream joins the windows: it re-walks only until the true path meets the
+//                  speculative one (typically a few symbols), then adopts the window's recorded exit state
+//   k_symscan      CTA per stream: prefix sum of the symbol-start flags -> dense symbol array, block boundaries
+__global__ void __launch_bounds__(128) k_walk_spec(const uint8_t *__restrict__ in, int64_t in_stride,
+                                                   const int32_t *__restrict__ in_len, const uint16_t *__restrict__ dist16,
+                                                   const uint16_t *__restrict__ rb16, const uint16_t *__restrict__ rl16,
+                                                   const uint32_t *__restrict__ mtab, uint8_t *__restrict__ flag,
+                                                   uint32_t *__restrict__ rec, Walk *__restrict__ exits, int64_t stride,
+                                                   int max_win) {
+    const int stream = blockIdx.y;
+    const int k = blockIdx.x * 128 + threadIdx.x;
+    const int n = in_len[stream];
+    const int ws = k * kWalkWin;
+    if (ws >= n) return;
+    const int64_t o = (int64_t)stream * stride;
+    LzView v{in + (int64_t)stream * in_stride, dist16 + o, rb16 + o, rl16 + o, n};
+    exits[(int64_t)stream * max_win + k] = walk_window(v, mtab + o, ws, min(ws + kWalkWin, n), flag + o, rec + o);
 }
 
-__global__ void __launch_bounds__(32) k_parse(const uint8_t *__restrict__ in, int64_t in_stride,
-                                              const int32_t *__restrict__ in_len, const uint16_t *__restrict__ dist16,
-                                              const uint16_t *__restrict__ rb16, const uint16_t *__restrict__ rl16,
-                                              const uint32_t *__restrict__ mtab, uint32_t *__restrict__ syms, int64_t stride,
-                                              int32_t *__restrict__ blk_end, int max_blocks, int32_t *__restrict__ nsym,
-                                              int32_t *__restrict__ nflush) {
-    __shared__ ParseSmem sm;
-    const int stream = blockIdx.x, lane = threadIdx.x;
+__global__ void __launch_bounds__(128) k_walk_stitch(const uint8_t *__restrict__ in, int64_t in_stride,
+                                                    const int32_t *__restrict__ in_len, const uint16_t *__restrict__ dist16,
+                                                    const uint16_t *__restrict__ rb16, const uint16_t *__restrict__ rl16,
+                                                    const uint32_t *__restrict__ mtab, uint8_t *__restrict__ flag,
+                                                    uint32_t *__restrict__ rec, const Walk *__restrict__ exits, int64_t stride,
+                                                    int max_win, int B) {
+    // one warp per stream, lane 0 walks: streams diverge completely, so sharing a warp would serialise them
+    const int stream = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (stream >= B || (threadIdx.x & 31)) return;
     const int64_t o = (int64_t)stream * stride;
+    LzView v{in + (int64_t)stream * in_stride, dist16 + o, rb16 + o, rl16 + o, in_len[stream]};
+    walk_stitch(v, mtab + o, kWalkWin, flag + o, rec + o, exits + (int64_t)stream * max_win);
+}
+
+constexpr int kScanThreads = 256;
+constexpr int kScanPer = 16;  // positions per thread per tile
+__global__ void __launch_bounds__(kScanThreads) k_symscan(const int32_t *__restrict__ in_len, const uint8_t *__restrict__ flag,
+                                                          const uint32_t *__restrict__ rec, uint32_t *__restrict__ syms,
+                                                          int64_t stride, int32_t *__restrict__ blk_end, int max_blocks,
+                                                          int32_t *__restrict__ nsym, int32_t *__restrict__ nflush) {
+    const int stream = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n = in_len[stream];
-    const uint8_t *w = in + (int64_t)stream * in_stride;
-    LzView v{w, dist16 + o, rb16 + o, rl16 + o, n};
-    const uint32_t *mt = mtab + o;
+    const int64_t o = (int64_t)stream * stride;
+    const uint8_t *fl = flag + o;
+    const uint32_t *rc = rec + o;
     uint32_t *out = syms + o;
     int32_t *be = blk_end + (int64_t)stream * max_blocks;
-    if (lane == 0) parse_init(sm.st);
-    if (n > 0) parse_stage(sm, 0, mt, w, 0, n, lane, 32);
-    __syncwarp();
-    int written = 0;  // symbols already flushed to global (warp-uniform)
-    int buf = 0;
-    for (int wbase = 0; wbase < n; wbase += kParseWin, buf ^= 1) {
-        const int wend = min(wbase + kParseWin, n);
-        bool staged_next = false;
-        for (;;) {  // lane 0 may need several rounds if the symbol buffer fills up
-            if (lane == 0) {
-                sm.produced = sm.st.s < wend
-                    ? parse_span(v, sm.st, wend, sm.tab[buf], wbase, sm.wprev[buf], wbase, sm.sym, kParseSyms, be) : 0;
-            } else if (!staged_next && wend < n) {
-                parse_stage(sm, buf ^ 1, mt, w, wend, n, lane - 1, 31);
-            }
-            staged_next = true;
-            __syncwarp();
-            const int k = sm.produced;
-            for (int i = lane; i < k; i += 32) out[written + i] = sm.sym[i];
-            written += k;
-            const bool more = sm.st.s < wend;
-            __syncwarp();
-            if (!more) break;
+    __shared__ int warp_sum[kScanThreads / 32];
+    __shared__ int carry_s;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += kScanThreads * kScanPer) {
+        const int p0 = base + tid * kScanPer;
+        uint4 f4 = make_uint4(0, 0, 0, 0);
+        if (p0 < n) f4 = *reinterpret_cast<const uint4 *>(fl + p0);  // stride is a multiple of 16; tail bytes are zero
+        const uint32_t fw[4] = {f4.x, f4.y, f4.z, f4.w};
+        int cnt = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) cnt += __popc(fw[j] & 0x01010101u);
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
         }
+        if (lane == 31) warp_sum[wid] = incl;
+        __syncthreads();
+        int woff = 0, total = 0;
+        for (int w = 0; w < kScanThreads / 32; w++) { if (w < wid) woff += warp_sum[w]; total += warp_sum[w]; }
+        int idx = carry_s + woff + incl - cnt;
+        __syncthreads();
+        if (tid == 0) carry_s += total;
+        if (cnt) {
+#pragma unroll
+            for (int j = 0; j < kScanPer; j++) {
+                if ((fw[j >> 2] >> (8 * (j & 3))) & 1u) {
+                    const int p = p0 + j;
+                    if (idx > 0 && idx % kSymEnd == 0) be[idx / kSymEnd - 1] = p;
+                    out[idx++] = rc[p];
+                }
+            }
+        }
+        __syncthreads();
     }
-    if (lane == 0) {
-        written += parse_finish(v, sm.st, out + written);
-        nsym[stream] = written;
-        nflush[stream] = sm.st.nfl;
+    if (tid == 0) {
+        const int total = carry_s;
+        nsym[stream] = total;
+        nflush[stream] = finish_blocks(total, total ? out[total - 1] : 0u, n, be);
     }
 }
 
@@ -403,9 +451,18 @@ void launch_deflate(const uint8_t *in, int64_t in_stride, const int32_t *in_len,
     { CCT_KERNEL(k_probe, st);
     k_probe<<<gp, 256, 0, st>>>(in, in_stride, in_len, ws.dist16, ws.rb16, ws.rl16, ws.mtab, ws.stride);
     }
-    { CCT_KERNEL(k_parse, st);
-    k_parse<<<B, 32, 0, st>>>(in, in_stride, in_len, ws.dist16, ws.rb16, ws.rl16, ws.mtab, ws.syms, ws.stride, ws.blk_end, ws.max_blocks,
-                              ws.nsym, ws.nflush);
+    cudaMemsetAsync(ws.flag, 0, (size_t)B * ws.stride, st);
+    dim3 gw((unsigned)((ws.max_win + 127) / 128), (unsigned)B);
+    { CCT_KERNEL(k_walk_spec, st);
+    k_walk_spec<<<gw, 128, 0, st>>>(in, in_stride, in_len, ws.dist16, ws.rb16, ws.rl16, ws.mtab, ws.flag, ws.rec, ws.exits, ws.stride,
+                                    ws.max_win);
+    }
+    { CCT_KERNEL(k_walk_stitch, st);
+    k_walk_stitch<<<(B + 3) / 4, 128, 0, st>>>(in, in_stride, in_len, ws.dist16, ws.rb16, ws.rl16, ws.mtab, ws.flag, ws.rec, ws.exits,
+                                                ws.stride, ws.max_win, B);
+    }
+    { CCT_KERNEL(k_symscan, st);
+    k_symscan<<<B, kScanThreads, 0, st>>>(in_len, ws.flag, ws.rec, ws.syms, ws.stride, ws.blk_end, ws.max_blocks, ws.nsym, ws.nflush);
     }
     { CCT_KERNEL(k_adler, st);
     k_adler<<<B, 256, 0, st>>>(in, in_stride, in_len, ws.adler);

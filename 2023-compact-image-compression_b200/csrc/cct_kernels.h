@@ -8,6 +8,8 @@
 namespace cct {
 
 struct BlockDesc;
+struct Walk;
+struct OpsChunkSum;
 
 // ---- launch accounting (cct_api.cu): every kernel launch is counted; with profiling on it is also bracketed
 // by CUDA events on its own stream so bench.py can report per-kernel device time from the timed region.
@@ -35,7 +37,11 @@ struct DeflateWs {  // device scratch for one pass over B streams of capacity ma
     uint16_t *dist16;    // [B][stride] chain links
     uint16_t *rb16, *rl16;  // [B][stride] equal bytes before / after each position
     uint32_t *mtab;      // [B][stride]
-    uint32_t *syms;      // [B][stride]
+    uint32_t *syms;      // [B][stride] dense LZ77 symbols
+    uint32_t *rec;       // [B][stride] symbol decided at each symbol start
+    uint8_t *flag;       // [B][stride] 1 = a symbol starts here
+    Walk *exits;         // [B][max_win] state each speculative window was left with
+    int max_win;
     int32_t *blk_end;    // [B][max_blocks]
     int32_t *nsym;       // [B]
     int32_t *nflush;     // [B]
@@ -62,6 +68,8 @@ struct DecodeWs {
     uint8_t *jflag;    // [B][nb]
     int32_t *slotA, *slotB;  // [B][nb]
     uint8_t *fl;       // [B] transform flags from each header
+    OpsChunkSum *chunks;  // [B][max_chunks] op-stream chunk summaries
+    int max_chunks;
     int64_t pstride;
 };
 size_t decode_ws_bytes(int B, int64_t n_px);

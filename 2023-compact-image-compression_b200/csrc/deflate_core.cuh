@@ -10,8 +10,9 @@
 //      of the data (kernel k_chains);
 //   2. `match_probe` runs longest_match from a cold start (best = 2) over the first K chain entries
 //      for EVERY position in parallel and records (len, dist, complete?) in a table;
-//   3. `parse_stream` walks the table sequentially with zlib's lazy-evaluation state machine; where
-//      the probe was incomplete it falls back to `match_full`, the exact longest_match loop;
+//   3. zlib's lazy-evaluation state machine is walked over symbol starts: speculatively per window in
+//      parallel (`walk_window`), then stitched per stream (`walk_stitch`); where the probe was incomplete
+//      it falls back to `match_full`, the exact longest_match loop;
 //   4. `build_block` restates _tr_flush_block's tree construction and block-type choice;
 //   5. the symbol bits are then packed in parallel from the code tables.
 #pragma once
@@ -182,76 +183,109 @@ CCT_HD int match_full(const LzView &v, int s, int prev_len, int *out_dist) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// deflate_slow as a walk over the probe table
+// deflate_slow as a walk over symbol starts
 // ------------------------------------------------------------------------------------------------
-// The state machine is resumable so the kernel can run it over staged windows: `parse_span` walks positions
-// while st.s < s_end, reading the probe table as tab[s - tab_base] and the byte BEFORE position s as
-// wprev[s - wprev_base], and appends LZ77 symbols to out[] (at most out_cap; it stops early when full and
-// can simply be called again).  Every in-loop flush (16383 symbols tallied) records the payload position at
-// which the block ended in blk_end[].  `parse_finish` emits the trailing literal (it never
-// triggers a flush; the final block holds symbols [16383 * nfl, nsym) and may be empty).
-struct ParseState {
-    int s, match_len, match_dist, nsym, in_block, nfl;
-    bool avail;
+// deflate_slow (deflate.c) emits the literal for byte s-1 while standing at s; re-indexed by the position a
+// symbol STARTS at, its lazy state machine reads:
+//     at symbol start p, with either no pending match ("cold") or the match (pl, pd) found at p by the
+//     previous step's look-ahead:
+//         cur = pending, or the cold search at p (prev_length 2, TOO_FAR rule)
+//         no cur                      -> LITERAL(w[p]);  next start p+1, cold
+//         search at p+1 beats cur     -> LITERAL(w[p]);  next start p+1, pending = that longer match
+//         otherwise                   -> MATCH(cur);     next start p+len, cold
+// A search result comes from the probe table when the probe was complete (then it does not depend on
+// prev_length beyond "must be longer", so a pending match at p is simply the table entry of p and the walk
+// state is a function of p alone) and from match_full otherwise.  Because the state is (almost always) a
+// function of p, walks started at different positions coincide from the first symbol start they share: the
+// parse is done speculatively per window in parallel (walk_window), then stitched by one sequential pass per
+// stream that only re-walks up to the point where the true path joins the speculative one (walk_stitch).
+struct Walk {
+    int p, pl, pd;  // symbol start, pending match length (0 = cold) and distance
 };
-CCT_HD void parse_init(ParseState &st) {
-    st.s = 0; st.match_len = 2; st.match_dist = 0; st.nsym = 0; st.in_block = 0; st.nfl = 0; st.avail = false;
+
+CCT_HD bool lookup_match(const LzView &v, const uint32_t *mtab, int p, int prev_len, int *len, int *dist) {
+    const int look = v.n - p;
+    if (look < kMinMatch) return false;
+    const uint32_t e = mtab[p];
+    if (e == 0 || prev_len >= kMaxMatch || prev_len >= look) return false;
+    int ml = 0, md = 0;
+    if (e & kProbeIncomplete) ml = match_full(v, p, prev_len, &md);
+    else if (mtab_len(e) > prev_len) { ml = mtab_len(e); md = mtab_dist(e); }
+    if (ml == kMinMatch && md > kTooFar) ml = 0;
+    *len = ml; *dist = md;
+    return ml != 0;
 }
 
-CCT_HD int parse_span(const LzView &v, ParseState &st, int s_end, const uint32_t *tab, int tab_base,
-                      const uint8_t *wprev, int wprev_base, uint32_t *out, int out_cap, int32_t *blk_end) {
+// One symbol: returns it and advances the walk.
+CCT_HD uint32_t walk_step(const LzView &v, const uint32_t *mtab, Walk &w) {
+    const int p = w.p;
+    int l0 = w.pl, d0 = w.pd;
+    if (!l0 && !lookup_match(v, mtab, p, 2, &l0, &d0)) { w.p = p + 1; return sym_pack(v.w[p], 0); }
+    int l1, d1;
+    if (lookup_match(v, mtab, p + 1, l0, &l1, &d1)) { w.p = p + 1; w.pl = l1; w.pd = d1; return sym_pack(v.w[p], 0); }
+    w.p = p + l0; w.pl = 0; w.pd = 0;
+    return sym_pack(l0 - kMinMatch, d0);
+}
+
+// Do two walks standing on the same symbol start continue identically?
+CCT_HD bool walk_same_state(const uint32_t *mtab, const Walk &a, const Walk &b) {
+    if (a.pl == b.pl && a.pd == b.pd) return true;
+    return !(mtab[a.p] & kProbeIncomplete);  // complete probe: the state is a function of the position
+}
+
+// Speculative walk of window [ws, we): assumes a cold symbol start at ws.  Marks flag[p] = 1 and records
+// rec[p] = symbol for every symbol start it visits; returns the state it leaves the window with.
+CCT_HD Walk walk_window(const LzView &v, const uint32_t *mtab, int ws, int we, uint8_t *flag, uint32_t *rec) {
+    Walk w{ws, 0, 0};
+    while (w.p < we) {
+        const int q = w.p;
+        rec[q] = walk_step(v, mtab, w);
+        flag[q] = 1;
+    }
+    return w;
+}
+
+// Sequential stitch of one stream: window after window, advance the true walk T and (re-running it) the
+// speculative walk S of the window in position order; S's marks that T does not confirm are cleared, T's
+// symbols are recorded, and as soon as both stand on the same symbol start in the same state the rest of the
+// window's speculation is accepted wholesale (T jumps to the recorded exit state).
+CCT_HDN inline void walk_stitch(const LzView &v, const uint32_t *mtab, int win, uint8_t *flag, uint32_t *rec,
+                                const Walk *exits) {
+    Walk T{0, 0, 0};
     const int n = v.n;
-    int k = 0;
-    int s = st.s, match_len = st.match_len, match_dist = st.match_dist, in_block = st.in_block;
-    bool avail = st.avail;
-    while (s < s_end && k < out_cap) {
-        const int look = n - s;
-        const int prev_len = match_len, prev_dist = match_dist;
-        match_len = 2;
-        const uint32_t e = look >= kMinMatch ? tab[s - tab_base] : 0u;
-        if (e != 0 && prev_len < kMaxMatch && prev_len < look) {
-            int ml = 0, md = 0;
-            if (e & kProbeIncomplete) ml = match_full(v, s, prev_len, &md);
-            else if (mtab_len(e) > prev_len) { ml = mtab_len(e); md = mtab_dist(e); }
-            if (ml == kMinMatch && md > kTooFar) ml = 0;
-            if (ml) { match_len = ml; match_dist = md; }
-        }
-        if (prev_len >= kMinMatch && match_len <= prev_len) {
-            out[k++] = sym_pack(prev_len - kMinMatch, prev_dist);
-            s += prev_len - 1;
-            avail = false; match_len = 2;
-            if (++in_block == kSymEnd) { blk_end[st.nfl++] = s; in_block = 0; }
-        } else if (avail) {
-            out[k++] = sym_pack(wprev[s - wprev_base], 0);
-            if (++in_block == kSymEnd) { blk_end[st.nfl++] = s; in_block = 0; }
-            s++;
-        } else {
-            avail = true; s++;
+    for (int k = 0, ws = 0; ws < n; k++, ws += win) {
+        const int we = ws + win < n ? ws + win : n;
+        if (T.p == ws && T.pl == 0) { T = exits[k]; continue; }  // speculation started from the true state
+        Walk S{ws, 0, 0};
+        for (;;) {
+            const bool t_in = T.p < we, s_in = S.p < we;
+            if (!t_in && !s_in) break;
+            if (t_in && s_in && T.p == S.p) {
+                if (walk_same_state(mtab, T, S)) { T = exits[k]; break; }
+                const int q = T.p;  // same start, different pending match over an incomplete probe: both move on
+                rec[q] = walk_step(v, mtab, T);
+                walk_step(v, mtab, S);
+            } else if (s_in && (!t_in || S.p < T.p)) {
+                flag[S.p] = 0;  // not on the true path
+                walk_step(v, mtab, S);
+            } else {
+                const int q = T.p;
+                rec[q] = walk_step(v, mtab, T);
+                flag[q] = 1;
+            }
         }
     }
-    st.s = s; st.match_len = match_len; st.match_dist = match_dist; st.in_block = in_block; st.avail = avail;
-    st.nsym += k;
-    return k;
 }
 
-// Trailing literal after the loop (deflate.c: `if (s->match_available) _tr_tally_lit(...)`).  Returns 0 or 1.
-CCT_HD int parse_finish(const LzView &v, ParseState &st, uint32_t *out) {
-    if (!st.avail) return 0;
-    out[0] = sym_pack(v.w[v.n - 1], 0);
-    st.avail = false;
-    st.nsym += 1;
-    return 1;
-}
-
-// Whole-stream convenience wrapper (CPU harness).
-CCT_HD int parse_stream(const LzView &v, const uint32_t *mtab, uint32_t *syms, int32_t *blk_end, int *n_flush) {
-    ParseState st;
-    parse_init(st);
-    int total = 0;
-    while (st.s < v.n) total += parse_span(v, st, v.n, mtab, 0, v.w, 1, syms + total, 0x7FFFFFFF, blk_end);
-    total += parse_finish(v, st, syms + total);
-    *n_flush = st.nfl;
-    return total;
+// Block boundaries.  zlib flushes a block as soon as 16383 symbols have been tallied inside its
+// loop; the literal for the last byte is tallied after the loop and never triggers a flush.  With symbols
+// numbered in stream order, block j < nflush ends where symbol 16383 (j+1) starts (recorded by the compaction
+// pass), or at n when the input ends exactly there (then zlib appends an empty last block).
+CCT_HD int finish_blocks(int nsym, uint32_t last_sym, int n, int32_t *blk_end) {
+    const int lastlit = (nsym > 0 && sym_dist(last_sym) == 0) ? 1 : 0;
+    const int nf = (nsym - lastlit) / kSymEnd;
+    if (nf > 0 && nf * kSymEnd == nsym) blk_end[nf - 1] = n;
+    return nf;
 }
 
 // ------------------------------------------------------------------------------------------------

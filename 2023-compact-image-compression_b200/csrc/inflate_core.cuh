@@ -198,39 +198,94 @@ CCT_HDN inline int inflate_stream(const uint8_t *in, int in_len, uint8_t *out, i
 // ------------------------------------------------------------------------------------------------
 constexpr int32_t kSlotSecond = 0x40000000;  // slotB flag: second half of a meshed unit
 
-// payload -> value of every pixel op in final order (vals[k]) and the JUMP distance at each unit start
-// (jflag[k/16], 0 = none).  Returns CCT_ST_* bits (0 = fine).  plen includes the EOF byte, which the
-// reference's reader never consumes (core.py:137,142).
-CCT_HDN inline uint32_t ops_to_values(const uint8_t *payload, int plen, int n_px, uint16_t *vals, uint8_t *jflag) {
-    const int end = plen - 1;
-    int pos = 0, value = 0;
+// One op of the stream at payload[pos]: returns its byte length (1 or 2), sets *delta and *kind
+// (0 pixel op, 1 JUMP with *delta = distance).  `end` = plen - 1: the reference's reader never consumes the
+// EOF byte (core.py:137,142).  A FULL op whose low byte would be at/after `end` is reported as length 0.
+CCT_HD int op_decode(const uint8_t *payload, int pos, int end, int *delta, int *kind) {
+    const int b = payload[pos];
+    *kind = 0;
+    if ((b & 0xC0) == 0x80) { *kind = 1; *delta = b & 0x3F; return 1; }  // JUMP (core.py:484-494)
+    if ((b & 0xF0) == 0xE0) {                                           // FULL (core.py:500-506)
+        if (pos + 1 >= end) return 0;
+        const int full = ((b << 8) | payload[pos + 1]) & 0xFFF;
+        *delta = full > 2048 ? full - 4096 : full;                      // signed(x, 12): x > 2048 -> x - 4096
+        return 2;
+    }
+    if ((b & 0x80) == 0) {                                              // DELTA (core.py:513-516)
+        const int x = b & 0x7F;
+        *delta = x > 64 ? x - 128 : x;
+    } else *delta = 0;  // any other tag: the reference leaves the pixel unchanged
+    return 1;
+}
+
+// The op stream is cut into fixed chunks so it can be decoded in parallel (op starts follow a
+// 2-state automaton -- "this byte is the low byte of a FULL op that started in the previous chunk").
+// Pass 1 summarises a chunk for one entry state; pass 2 (ops_link_chunks) chains the summaries of a stream;
+// pass 3 (ops_emit_chunk) decodes the chunk again with its now-known entry state, op index and running value.
+constexpr int kOpsChunk = 1024;
+struct OpsChunkSum { int32_t nops[2]; int32_t dsum[2]; uint8_t exit_state[2]; uint8_t entry; uint8_t pad; int32_t op_base; int32_t val_base; };
+
+CCT_HD void ops_scan_chunk(const uint8_t *payload, int lo, int hi, int end, int entry, int *nops, int *dsum, int *exit_state) {
+    int pos = lo + entry, n = 0, sum = 0;
+    const int stop = hi < end ? hi : end;
+    while (pos < stop) {
+        int delta, kind;
+        const int len = op_decode(payload, pos, end, &delta, &kind);
+        if (len == 0) { pos = stop; break; }
+        pos += len;
+        if (!kind) { n++; sum += delta; }
+    }
+    *nops = n; *dsum = sum; *exit_state = pos > hi ? 1 : 0;
+}
+
+// Sequential link over the chunk summaries of one stream.  Returns CCT_ST_* bits (truncated if fewer than n_px ops).
+CCT_HDN inline uint32_t ops_link_chunks(OpsChunkSum *cs, int n_chunks, int n_px) {
+    int state = 0, ops = 0, val = 0;
+    for (int c = 0; c < n_chunks; c++) {
+        cs[c].entry = (uint8_t)state; cs[c].op_base = ops; cs[c].val_base = val;
+        ops += cs[c].nops[state]; val += cs[c].dsum[state];
+        state = cs[c].exit_state[state];
+    }
+    return ops < n_px ? 64u : 0u;
+}
+
+// Pass 3: values of the chunk's pixel ops -> vals[k]; JUMP distances -> jflag[k / 16].  Returns status bits.
+CCT_HD uint32_t ops_emit_chunk(const uint8_t *payload, int lo, int hi, int end, const OpsChunkSum &cs, int n_px,
+                               uint16_t *vals, uint8_t *jflag) {
+    int pos = lo + cs.entry, k = cs.op_base, value = cs.val_base;
+    const int stop = hi < end ? hi : end;
     uint32_t st = 0;
-    for (int k = 0; k < n_px; k++) {
-        if (pos >= end) return st | 64u;
-        int b = payload[pos];
-        if ((b & 0xC0) == 0x80) {  // JUMP (core.py:484-494)
-            if ((k & 15) == 0) jflag[k >> 4] = (uint8_t)(b & 0x3F);
-            else st |= 64u;  // never produced by the encoder
-            if (++pos >= end) return st | 64u;
-            b = payload[pos];
-        }
-        int delta = 0;
-        if ((b & 0xF0) == 0xE0) {  // FULL (core.py:500-506)
-            if (pos + 1 >= end) return st | 64u;
-            int full = ((b << 8) | payload[pos + 1]) & 0xFFF;
-            delta = full > 2048 ? full - 4096 : full;
-            pos += 2;
-        } else {
-            if ((b & 0x80) == 0) {  // DELTA (core.py:513-516)
-                int x = b & 0x7F;
-                delta = x > 64 ? x - 128 : x;
-            }  // any other tag: the reference leaves the pixel unchanged
-            pos += 1;
+    while (pos < stop && k < n_px) {
+        int delta, kind;
+        const int len = op_decode(payload, pos, end, &delta, &kind);
+        if (len == 0) break;
+        pos += len;
+        if (kind) {
+            if ((k & 15) == 0) jflag[k >> 4] = (uint8_t)delta;
+            else st |= 64u;  // a JUMP inside a unit is never produced by the encoder
+            continue;
         }
         value += delta;
         if (value < 0 || value > 65535) st |= 32u;  // reference: OverflowError (core.py:506,516)
-        vals[k] = (uint16_t)value;
+        vals[k++] = (uint16_t)value;
     }
+    return st;
+}
+
+// Whole-stream convenience wrapper (CPU harness): same three passes, sequentially.
+CCT_HDN inline uint32_t ops_to_values(const uint8_t *payload, int plen, int n_px, uint16_t *vals, uint8_t *jflag,
+                                      OpsChunkSum *cs) {
+    const int end = plen - 1;
+    const int n_chunks = (plen + kOpsChunk - 1) / kOpsChunk;
+    for (int c = 0; c < n_chunks; c++)
+        for (int e = 0; e < 2; e++) {
+            int nops, dsum, ex;
+            ops_scan_chunk(payload, c * kOpsChunk, (c + 1) * kOpsChunk, end, e, &nops, &dsum, &ex);
+            cs[c].nops[e] = nops; cs[c].dsum[e] = dsum; cs[c].exit_state[e] = (uint8_t)ex;
+        }
+    uint32_t st = ops_link_chunks(cs, n_chunks, n_px);
+    for (int c = 0; c < n_chunks; c++)
+        st |= ops_emit_chunk(payload, c * kOpsChunk, (c + 1) * kOpsChunk, end, cs[c], n_px, vals, jflag);
     return st;
 }
 

@@ -97,7 +97,7 @@ def stage_of(kernel):
         return "front"        # reads 2N, writes P
     if kernel in ("k_dec_inflate",):
         return "inflate"      # reads F, writes P (K6)
-    if kernel in ("k_dec_ops", "k_dec_scatter", "k_dec_header"):
+    if kernel.startswith("k_dec_"):
         return "back"         # reads P, writes 2N (K7-K8)
     return "deflate"          # reads P, writes F (K5)
 

@@ -4,6 +4,7 @@
 // TEST INFRASTRUCTURE: built and loaded by tests/ only; the product library never contains this file.
 #include <cstdint>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -50,7 +51,7 @@ extern "C" {
 // Staged zlib-9 of src[0..n).  probe_k = chain entries examined by the parallel probe.
 // stats[0] = symbols, [1] = blocks, [2] = incomplete probe entries, [3] = probe loop steps, [4] = loop steps of the
 // on-demand searches made by the walk (stats must hold 5 values if non-null).
-int64_t hs_deflate(const uint8_t *src, int n, uint8_t *dst, int64_t cap, int probe_k, int64_t *stats) {
+int64_t hs_deflate2(const uint8_t *src, int n, uint8_t *dst, int64_t cap, int probe_k, int parse_win, int64_t *stats) {
     long long c0 = cct_stat[0];
     std::vector<uint16_t> dist16;
     chains_reference(src, n, dist16);
@@ -61,10 +62,21 @@ int64_t hs_deflate(const uint8_t *src, int n, uint8_t *dst, int64_t cap, int pro
     int64_t n_incomplete = 0;
     for (int s = 0; s < n; s++) { mtab[s] = match_probe(v, s, probe_k); n_incomplete += (mtab[s] & kProbeIncomplete) != 0; }
     long long c1 = cct_stat[0];
+    // speculative windows -> stitch -> compaction (the three parse kernels, sequentially)
+    const int win = parse_win > 0 ? parse_win : 1024;
+    std::vector<uint8_t> flag((size_t)n + 1, 0);
+    std::vector<uint32_t> rec((size_t)n + 1, 0);
+    std::vector<Walk> exits((size_t)n / win + 2);
+    for (int k = 0, ws = 0; ws < n; k++, ws += win) exits[k] = walk_window(v, mtab.data(), ws, std::min(ws + win, n), flag.data(), rec.data());
+    walk_stitch(v, mtab.data(), win, flag.data(), rec.data(), exits.data());
     std::vector<uint32_t> syms((size_t)n + 1);
     std::vector<int32_t> blk_end((size_t)n / kSymEnd + 2);
-    int n_flush = 0;
-    int nsym = parse_stream(v, mtab.data(), syms.data(), blk_end.data(), &n_flush);
+    int nsym = 0;
+    for (int p = 0; p < n; p++) if (flag[p]) {
+        if (nsym > 0 && nsym % kSymEnd == 0) blk_end[nsym / kSymEnd - 1] = p;
+        syms[nsym++] = rec[p];
+    }
+    int n_flush = finish_blocks(nsym, nsym ? syms[nsym - 1] : 0u, n, blk_end.data());
     long long c2 = cct_stat[0];
     int nblk = n_flush + 1;
     std::vector<BlockDesc> desc((size_t)nblk);
@@ -125,6 +137,10 @@ int64_t hs_deflate(const uint8_t *src, int n, uint8_t *dst, int64_t cap, int pro
 
 void hs_stats(long long *out, int reset) { for (int i = 0; i < 8; i++) { out[i] = cct_stat[i]; if (reset) cct_stat[i] = 0; } }
 
+int64_t hs_deflate(const uint8_t *src, int n, uint8_t *dst, int64_t cap, int probe_k, int64_t *stats) {
+    return hs_deflate2(src, n, dst, cap, probe_k, 1024, stats);
+}
+
 int hs_inflate(const uint8_t *in, int in_len, uint8_t *out, int out_cap) {
     InflateTables *tb = new InflateTables;
     int r = inflate_stream(in, in_len, out, out_cap, *tb);
@@ -138,7 +154,8 @@ uint32_t hs_decode_payload(const uint8_t *payload, int plen, int n_px, const int
     std::vector<uint16_t> vals((size_t)n_px);
     std::vector<uint8_t> jflag((size_t)nb, 0);
     std::vector<int32_t> slotA((size_t)nb), slotB((size_t)nb);
-    uint32_t st = ops_to_values(payload, plen, n_px, vals.data(), jflag.data());
+    std::vector<OpsChunkSum> cs((size_t)plen / kOpsChunk + 2);
+    uint32_t st = ops_to_values(payload, plen, n_px, vals.data(), jflag.data(), cs.data());
     if (st & 64u) return st;
     st |= resolve_units(jflag.data(), nb, slotA.data(), slotB.data());
     if (st & 64u) return st;
