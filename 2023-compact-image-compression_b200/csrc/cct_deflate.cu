@@ -37,6 +37,7 @@ size_t deflate_ws_carve(DeflateWs *ws, void *mem, int B, int64_t max_len) {
     ws->rb16 = (uint16_t *)take((size_t)B * ws->stride * sizeof(uint16_t));
     ws->rl16 = (uint16_t *)take((size_t)B * ws->stride * sizeof(uint16_t));
     ws->mtab = (uint32_t *)take((size_t)B * ws->stride * sizeof(uint32_t));
+    ws->mhi = (uint32_t *)take((size_t)B * ws->stride * sizeof(uint32_t));
     ws->syms = (uint32_t *)take((size_t)B * ws->stride * sizeof(uint32_t));
     ws->rec = (uint32_t *)take((size_t)B * ws->stride * sizeof(uint32_t));
     ws->flag = (uint8_t *)take((size_t)B * ws->stride);
@@ -107,14 +108,40 @@ __global__ void __launch_bounds__(32) k_chains(const uint8_t *__restrict__ in, i
             const bool valid = s >= 1 && s + 2 < n;  // position 0 doubles as NIL in zlib: never a match source
             uint32_t h = 0x8000u | (uint32_t)lane;   // unique key for lanes that do not insert
             if (valid) h = hash3(sb);
-            const unsigned peers = __match_any_sync(0xffffffffu, h);
-            const unsigned lower = peers & ((1u << lane) - 1u);
+            // previous position with the same hash: the nearest lower lane holding it, else the head table.
+            // Same-hash lanes inside one group are found without a full match: either every inserting lane has
+            // one hash (a run), or all hashes are distinct -- detected by letting every lane store its position
+            // and read the slot back -- or, rarely, the general case (__match_any_sync is a software loop here).
+            const unsigned vmask = __ballot_sync(0xffffffffu, valid);
             int dist = 0;
-            if (valid) {
-                if (lower) dist = lane - (31 - __clz((int)lower));
-                else {
-                    uint32_t d = (uint32_t)(s - head[h]) & 0xFFFFu;
-                    dist = (d >= 1u && d < 32768u) ? (int)d : 0;
+            uint32_t old = 0;
+            if (valid) old = head[h];
+            const int first = __ffs((int)vmask) - 1;
+            const uint32_t h0 = __shfl_sync(0xffffffffu, h, first < 0 ? 0 : first);
+            const bool uniform = vmask && __ballot_sync(0xffffffffu, valid && h == h0) == vmask;
+            __syncwarp();
+            if (uniform) {
+                if (valid) {
+                    const unsigned lower = vmask & ((1u << lane) - 1u);
+                    if (lower) dist = lane - (31 - __clz((int)lower));
+                    else { uint32_t d = (uint32_t)(s - old) & 0xFFFFu; dist = (d >= 1u && d < 32768u) ? (int)d : 0; }
+                    if ((vmask >> lane) == 1u) head[h] = (uint16_t)s;
+                }
+            } else {
+                if (valid) head[h] = (uint16_t)s;
+                __syncwarp();
+                const bool lost = valid && head[h] != (uint16_t)s;
+                if (__ballot_sync(0xffffffffu, lost) == 0u) {  // all distinct: every lane owns its slot
+                    if (valid) { uint32_t d = (uint32_t)(s - old) & 0xFFFFu; dist = (d >= 1u && d < 32768u) ? (int)d : 0; }
+                } else {
+                    const unsigned peers = __match_any_sync(0xffffffffu, h);
+                    const unsigned lower = peers & ((1u << lane) - 1u);
+                    if (valid) {
+                        if (lower) dist = lane - (31 - __clz((int)lower));
+                        else { uint32_t d = (uint32_t)(s - old) & 0xFFFFu; dist = (d >= 1u && d < 32768u) ? (int)d : 0; }
+                    }
+                    __syncwarp();
+                    if (valid && (peers >> lane) == 1u) head[h] = (uint16_t)s;  // the latest position wins
                 }
             }
             // equal-to-previous flags -> count of equal bytes before s
@@ -124,8 +151,6 @@ __global__ void __launch_bounds__(32) k_chains(const uint8_t *__restrict__ in, i
             int back = zeros_below ? lane - (31 - __clz((int)zeros_below)) : lane + 1 + carry;
             if (back > 65535) back = 65535;
             carry = __shfl_sync(0xffffffffu, back, 31);
-            __syncwarp();
-            if (valid && (peers >> lane) == 1u) head[h] = (uint16_t)s;
             if (s < n) { d16[s] = (uint16_t)dist; rb[s] = (uint16_t)back; }
             __syncwarp();
         }
@@ -148,14 +173,17 @@ __global__ void __launch_bounds__(32) k_chains(const uint8_t *__restrict__ in, i
 __global__ void __launch_bounds__(256) k_probe(const uint8_t *__restrict__ in, int64_t in_stride,
                                                const int32_t *__restrict__ in_len, const uint16_t *__restrict__ dist16,
                                                const uint16_t *__restrict__ rb16, const uint16_t *__restrict__ rl16,
-                                               uint32_t *__restrict__ mtab, int64_t stride) {
+                                               uint32_t *__restrict__ mlo, uint32_t *__restrict__ mhi, int64_t stride) {
     const int stream = blockIdx.y;
     const int n = in_len[stream];
     const int s = blockIdx.x * 256 + threadIdx.x;
     if (s >= n) return;
     const int64_t o = (int64_t)stream * stride;
     LzView v{in + (int64_t)stream * in_stride, dist16 + o, rb16 + o, rl16 + o, n};
-    mtab[o + s] = match_probe(v, s, kProbeK);
+    uint32_t lo, hi;
+    match_probe(v, s, kProbeK, &lo, &hi);
+    mlo[o + s] = lo;
+    mhi[o + s] = hi;
 }
 
 // ------------------------------------------------------------------ parse: k_walk_spec / k_walk_stitch / k_symscan
@@ -167,7 +195,7 @@ __global__ void __launch_bounds__(256) k_probe(const uint8_t *__restrict__ in, i
 __global__ void __launch_bounds__(128) k_walk_spec(const uint8_t *__restrict__ in, int64_t in_stride,
                                                    const int32_t *__restrict__ in_len, const uint16_t *__restrict__ dist16,
                                                    const uint16_t *__restrict__ rb16, const uint16_t *__restrict__ rl16,
-                                                   const uint32_t *__restrict__ mtab, uint8_t *__restrict__ flag,
+                                                   const uint32_t *__restrict__ mlo, const uint32_t *__restrict__ mhi, uint8_t *__restrict__ flag,
                                                    uint32_t *__restrict__ rec, Walk *__restrict__ exits, int64_t stride,
                                                    int max_win) {
     const int stream = blockIdx.y;
@@ -177,13 +205,13 @@ __global__ void __launch_bounds__(128) k_walk_spec(const uint8_t *__restrict__ i
     if (ws >= n) return;
     const int64_t o = (int64_t)stream * stride;
     LzView v{in + (int64_t)stream * in_stride, dist16 + o, rb16 + o, rl16 + o, n};
-    exits[(int64_t)stream * max_win + k] = walk_window(v, mtab + o, ws, min(ws + kWalkWin, n), flag + o, rec + o);
+    exits[(int64_t)stream * max_win + k] = walk_window(v, ProbeTab{mlo + o, mhi + o}, ws, min(ws + kWalkWin, n), flag + o, rec + o);
 }
 
 __global__ void __launch_bounds__(128) k_walk_stitch(const uint8_t *__restrict__ in, int64_t in_stride,
                                                     const int32_t *__restrict__ in_len, const uint16_t *__restrict__ dist16,
                                                     const uint16_t *__restrict__ rb16, const uint16_t *__restrict__ rl16,
-                                                    const uint32_t *__restrict__ mtab, uint8_t *__restrict__ flag,
+                                                    const uint32_t *__restrict__ mlo, const uint32_t *__restrict__ mhi, uint8_t *__restrict__ flag,
                                                     uint32_t *__restrict__ rec, const Walk *__restrict__ exits, int64_t stride,
                                                     int max_win, int B) {
     // one warp per stream, lane 0 walks: streams diverge completely, so sharing a warp would serialise them
@@ -191,7 +219,7 @@ __global__ void __launch_bounds__(128) k_walk_stitch(const uint8_t *__restrict__
     if (stream >= B || (threadIdx.x & 31)) return;
     const int64_t o = (int64_t)stream * stride;
     LzView v{in + (int64_t)stream * in_stride, dist16 + o, rb16 + o, rl16 + o, in_len[stream]};
-    walk_stitch(v, mtab + o, kWalkWin, flag + o, rec + o, exits + (int64_t)stream * max_win);
+    walk_stitch(v, ProbeTab{mlo + o, mhi + o}, kWalkWin, flag + o, rec + o, exits + (int64_t)stream * max_win);
 }
 
 constexpr int kScanThreads = 256;
@@ -449,16 +477,16 @@ void launch_deflate(const uint8_t *in, int64_t in_stride, const int32_t *in_len,
     }
     dim3 gp((unsigned)((max_len + 255) / 256), (unsigned)B);
     { CCT_KERNEL(k_probe, st);
-    k_probe<<<gp, 256, 0, st>>>(in, in_stride, in_len, ws.dist16, ws.rb16, ws.rl16, ws.mtab, ws.stride);
+    k_probe<<<gp, 256, 0, st>>>(in, in_stride, in_len, ws.dist16, ws.rb16, ws.rl16, ws.mtab, ws.mhi, ws.stride);
     }
     cudaMemsetAsync(ws.flag, 0, (size_t)B * ws.stride, st);
     dim3 gw((unsigned)((ws.max_win + 127) / 128), (unsigned)B);
     { CCT_KERNEL(k_walk_spec, st);
-    k_walk_spec<<<gw, 128, 0, st>>>(in, in_stride, in_len, ws.dist16, ws.rb16, ws.rl16, ws.mtab, ws.flag, ws.rec, ws.exits, ws.stride,
+    k_walk_spec<<<gw, 128, 0, st>>>(in, in_stride, in_len, ws.dist16, ws.rb16, ws.rl16, ws.mtab, ws.mhi, ws.flag, ws.rec, ws.exits, ws.stride,
                                     ws.max_win);
     }
     { CCT_KERNEL(k_walk_stitch, st);
-    k_walk_stitch<<<(B + 3) / 4, 128, 0, st>>>(in, in_stride, in_len, ws.dist16, ws.rb16, ws.rl16, ws.mtab, ws.flag, ws.rec, ws.exits,
+    k_walk_stitch<<<(B + 3) / 4, 128, 0, st>>>(in, in_stride, in_len, ws.dist16, ws.rb16, ws.rl16, ws.mtab, ws.mhi, ws.flag, ws.rec, ws.exits,
                                                 ws.stride, ws.max_win, B);
     }
     { CCT_KERNEL(k_symscan, st);

@@ -102,11 +102,12 @@ constexpr int kWalkSteps = 2;   // step cap of the probe reached
 //   best / bdist   in: best_len to beat (prev_length, or 2 for a cold start); out: result
 //   chain          number of candidates that may still be visited (max_chain_length, quartered by the caller)
 //   max_steps      cap on LOOP STEPS (not candidates) for the parallel probe
-// One loop step handles either a single candidate or a whole RUN GROUP.  When the target starts with R >= 3
-// copies of a byte c and the candidate `cur` also starts with (c,c,c), the chain entries below cur inside that
-// run are exactly the consecutive positions cur-1, cur-2, ... down to the run start (all have the hash of
-// (c,c,c)), and the match length of the i-th of them is known in closed form from its count of leading c's,
-// m + i: m+i if m+i < R, "R + whatever follows" if m+i == R, exactly R if m+i > R (R < cap), cap if R == cap.
+// One loop step handles either a single candidate or a whole RUN GROUP.  When the candidate `cur` starts with
+// a triple (c,c,c), the chain entries below cur inside that run are exactly the consecutive positions cur-1,
+// cur-2, ... down to the run start (all have the hash of (c,c,c)).  If the target does not itself start with
+// (c,c,c) -- the chain only shares the hash -- none of them matches 3 bytes.  If it starts with R >= 3 copies
+// of c, the match length of the i-th member is known in closed form from its count of leading c's, m + i:
+// m+i if m+i < R, "R + whatever follows" if m+i == R, exactly R if m+i > R (R < cap), cap if R == cap.
 // Since only the first-visited candidate attaining the maximum matters, the group is consumed in
 // one step; the chain budget and the distance limit are charged as if every member had been visited.
 CCT_HD int chain_walk(const LzView &v, int s, int cap, int &best, int &bdist, int chain, int max_steps) {
@@ -117,7 +118,8 @@ CCT_HD int chain_walk(const LzView &v, int s, int cap, int &best, int &bdist, in
     for (int step = 1;; step++) {
         CCT_COUNT(0);
         const uint8_t *a = v.w + cur;
-        if (R && a[0] == b[0] && v.rl16[cur] >= 2) {
+        if (v.rl16[cur] >= 2) {
+            // cur starts a triple (c,c,c): the chain entries below it inside the run form one group
             const int m = (int)v.rl16[cur] + 1;  // leading c's of the top candidate
             int t = v.rb16[cur];                 // further candidates of this run below cur
             if (cur - t < 1) t = cur - 1;        // position 0 is never in a chain
@@ -125,17 +127,19 @@ CCT_HD int chain_walk(const LzView &v, int s, int cap, int &best, int &bdist, in
             int nvis = t + 1;
             if (chain < nvis) nvis = chain;
             if (count_dist < nvis) nvis = count_dist;
-            const int i_key = m >= R ? 0 : R - m;  // first member with at least R leading c's
-            if (R < cap && m > R) {
-                if (R > best) { best = R; bdist = s - cur; }
-            } else if (i_key < nvis) {
-                const int c_al = cur - i_key;
-                const int L = R < cap ? match_extend(v.w + c_al, b, R, cap) : cap;
-                if (L > best) { best = L; bdist = s - c_al; if (L >= cap) return kWalkDone; }
-            } else {
-                const int L = m + nvis - 1;  // only members with fewer than R leading c's were reached
-                if (L > best) { best = L; bdist = s - (cur - (nvis - 1)); }
-            }
+            if (R && a[0] == b[0]) {
+                const int i_key = m >= R ? 0 : R - m;  // first member with at least R leading c's
+                if (R < cap && m > R) {
+                    if (R > best) { best = R; bdist = s - cur; }
+                } else if (i_key < nvis) {
+                    const int c_al = cur - i_key;
+                    const int L = R < cap ? match_extend(v.w + c_al, b, R, cap) : cap;
+                    if (L > best) { best = L; bdist = s - c_al; if (L >= cap) return kWalkDone; }
+                } else {
+                    const int L = m + nvis - 1;  // only members with fewer than R leading c's were reached
+                    if (L > best) { best = L; bdist = s - (cur - (nvis - 1)); }
+                }
+            }  // else: the target does not start with (c,c,c) (a hash collision): no member matches 3 bytes
             if (nvis < t + 1) return nvis == count_dist ? kWalkDone : kWalkBudget;
             chain -= t;
             cur -= t;
@@ -155,18 +159,26 @@ CCT_HD int chain_walk(const LzView &v, int s, int cap, int &best, int &bdist, in
     }
 }
 
-// Cold-start probe (best_len = 2) over at most K loop steps.  Complete probes are valid for every parser
-// state: the answer for any prev_length is "the recorded match if it is longer" (SURVEY B.4), provided the walk
-// ended inside the smallest chain budget the parser ever applies (1024, deflate.c good_length rule).
-CCT_HD uint32_t match_probe(const LzView &v, int s, int K) {
+// Cold-start probe (best_len = 2) over at most K loop steps.  longest_match's answer for any prev_length is
+// "the first-visited candidate attaining the maximum length, if that is longer" (SURVEY B.4); prev_length only
+// changes the chain budget (4096, quartered to 1024 once prev_length >= good_length 32), so the probe records
+// one entry per budget: *lo for prev_length < 32, *hi for prev_length >= 32.  They differ only when the chain
+// holds more than 1024 candidates.  An entry is kProbeIncomplete when the step cap ended the walk first.
+CCT_HD void match_probe(const LzView &v, int s, int K, uint32_t *lo, uint32_t *hi) {
+    *lo = *hi = 0;
     const int look = v.n - s;
-    if (look < kMinMatch) return 0;
+    if (look < kMinMatch) return;
     const int d0 = v.dist16[s];
-    if (d0 == 0 || d0 > kMaxDist) return 0;
+    if (d0 == 0 || d0 > kMaxDist) return;
     const int cap = look < kMaxMatch ? look : kMaxMatch;
     int best = 2, bdist = 0;
-    if (chain_walk(v, s, cap, best, bdist, kChainGood, K) != kWalkDone) return kProbeIncomplete;
-    return best >= kMinMatch ? mtab_pack(best, bdist) : 0;
+    int r = chain_walk(v, s, cap, best, bdist, kChainGood, K);
+    const uint32_t e = r == kWalkSteps ? kProbeIncomplete : (best >= kMinMatch ? mtab_pack(best, bdist) : 0u);
+    *lo = *hi = e;
+    if (r != kWalkBudget) return;
+    best = 2; bdist = 0;
+    r = chain_walk(v, s, cap, best, bdist, kChainFull, K);
+    *lo = r == kWalkSteps ? kProbeIncomplete : (best >= kMinMatch ? mtab_pack(best, bdist) : 0u);
 }
 
 // Exact longest_match for position s with the parser's prev_length (chain budget 4096, or 1024 once
@@ -203,10 +215,14 @@ struct Walk {
     int p, pl, pd;  // symbol start, pending match length (0 = cold) and distance
 };
 
-CCT_HD bool lookup_match(const LzView &v, const uint32_t *mtab, int p, int prev_len, int *len, int *dist) {
+struct ProbeTab {
+    const uint32_t *lo, *hi;  // entries for chain budget 4096 (prev_length < 32) and 1024 (prev_length >= 32)
+};
+
+CCT_HD bool lookup_match(const LzView &v, const ProbeTab &mt, int p, int prev_len, int *len, int *dist) {
     const int look = v.n - p;
     if (look < kMinMatch) return false;
-    const uint32_t e = mtab[p];
+    const uint32_t e = prev_len >= kGoodLen ? mt.hi[p] : mt.lo[p];
     if (e == 0 || prev_len >= kMaxMatch || prev_len >= look) return false;
     int ml = 0, md = 0;
     if (e & kProbeIncomplete) ml = match_full(v, p, prev_len, &md);
@@ -217,7 +233,7 @@ CCT_HD bool lookup_match(const LzView &v, const uint32_t *mtab, int p, int prev_
 }
 
 // One symbol: returns it and advances the walk.
-CCT_HD uint32_t walk_step(const LzView &v, const uint32_t *mtab, Walk &w) {
+CCT_HD uint32_t walk_step(const LzView &v, const ProbeTab &mtab, Walk &w) {
     const int p = w.p;
     int l0 = w.pl, d0 = w.pd;
     if (!l0 && !lookup_match(v, mtab, p, 2, &l0, &d0)) { w.p = p + 1; return sym_pack(v.w[p], 0); }
@@ -228,14 +244,15 @@ CCT_HD uint32_t walk_step(const LzView &v, const uint32_t *mtab, Walk &w) {
 }
 
 // Do two walks standing on the same symbol start continue identically?
-CCT_HD bool walk_same_state(const uint32_t *mtab, const Walk &a, const Walk &b) {
+CCT_HD bool walk_same_state(const ProbeTab &mt, const Walk &a, const Walk &b) {
     if (a.pl == b.pl && a.pd == b.pd) return true;
-    return !(mtab[a.p] & kProbeIncomplete);  // complete probe: the state is a function of the position
+    const uint32_t e = mt.lo[a.p];  // one complete entry for both budgets: the state is a function of the position
+    return e == mt.hi[a.p] && !(e & kProbeIncomplete);
 }
 
 // Speculative walk of window [ws, we): assumes a cold symbol start at ws.  Marks flag[p] = 1 and records
 // rec[p] = symbol for every symbol start it visits; returns the state it leaves the window with.
-CCT_HD Walk walk_window(const LzView &v, const uint32_t *mtab, int ws, int we, uint8_t *flag, uint32_t *rec) {
+CCT_HD Walk walk_window(const LzView &v, const ProbeTab &mtab, int ws, int we, uint8_t *flag, uint32_t *rec) {
     Walk w{ws, 0, 0};
     while (w.p < we) {
         const int q = w.p;
@@ -249,7 +266,7 @@ CCT_HD Walk walk_window(const LzView &v, const uint32_t *mtab, int ws, int we, u
 // speculative walk S of the window in position order; S's marks that T does not confirm are cleared, T's
 // symbols are recorded, and as soon as both stand on the same symbol start in the same state the rest of the
 // window's speculation is accepted wholesale (T jumps to the recorded exit state).
-CCT_HDN inline void walk_stitch(const LzView &v, const uint32_t *mtab, int win, uint8_t *flag, uint32_t *rec,
+CCT_HDN inline void walk_stitch(const LzView &v, const ProbeTab &mtab, int win, uint8_t *flag, uint32_t *rec,
                                 const Walk *exits) {
     Walk T{0, 0, 0};
     const int n = v.n;

@@ -58,17 +58,21 @@ int64_t hs_deflate2(const uint8_t *src, int n, uint8_t *dst, int64_t cap, int pr
     std::vector<uint16_t> rb16, rl16;
     runs_reference(src, n, rb16, rl16);
     LzView v{src, dist16.data(), rb16.data(), rl16.data(), n};
-    std::vector<uint32_t> mtab((size_t)n + 1, 0);
+    std::vector<uint32_t> mlo((size_t)n + 1, 0), mhi((size_t)n + 1, 0);
     int64_t n_incomplete = 0;
-    for (int s = 0; s < n; s++) { mtab[s] = match_probe(v, s, probe_k); n_incomplete += (mtab[s] & kProbeIncomplete) != 0; }
+    for (int s = 0; s < n; s++) {
+        match_probe(v, s, probe_k, &mlo[s], &mhi[s]);
+        n_incomplete += ((mlo[s] | mhi[s]) & kProbeIncomplete) != 0;
+    }
+    ProbeTab mtab{mlo.data(), mhi.data()};
     long long c1 = cct_stat[0];
     // speculative windows -> stitch -> compaction (the three parse kernels, sequentially)
     const int win = parse_win > 0 ? parse_win : 1024;
     std::vector<uint8_t> flag((size_t)n + 1, 0);
     std::vector<uint32_t> rec((size_t)n + 1, 0);
     std::vector<Walk> exits((size_t)n / win + 2);
-    for (int k = 0, ws = 0; ws < n; k++, ws += win) exits[k] = walk_window(v, mtab.data(), ws, std::min(ws + win, n), flag.data(), rec.data());
-    walk_stitch(v, mtab.data(), win, flag.data(), rec.data(), exits.data());
+    for (int k = 0, ws = 0; ws < n; k++, ws += win) exits[k] = walk_window(v, mtab, ws, std::min(ws + win, n), flag.data(), rec.data());
+    walk_stitch(v, mtab, win, flag.data(), rec.data(), exits.data());
     std::vector<uint32_t> syms((size_t)n + 1);
     std::vector<int32_t> blk_end((size_t)n / kSymEnd + 2);
     int nsym = 0;
