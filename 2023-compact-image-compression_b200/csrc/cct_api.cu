@@ -363,7 +363,7 @@ size_t cct_deflate_workspace_bytes(int B, size_t max_len) { return deflate_ws_by
 int cct_deflate_batch(const uint8_t *d_in, size_t in_stride, const int32_t *d_in_len, int B, size_t max_len,
                       uint8_t *d_out, size_t out_stride, int32_t *d_out_len, void *d_ws, size_t ws_bytes, void *stream) {
     if (B < 0 || (B > 0 && (!d_in || !d_in_len || !d_out || !d_out_len || !d_ws))) return CCT_E_ARG;
-    if (out_stride % 4 || out_stride < cct_deflate_bound(max_len) || max_len > (1u << 27)) return CCT_E_ARG;
+    if (out_stride % 4 || in_stride % 16 || out_stride < cct_deflate_bound(max_len) || max_len > (1u << 27)) return CCT_E_ARG;
     if (cct_device_count() == 0) return CCT_E_NO_DEVICE;
     if (deflate_ws_bytes(std::max(B, 1), (int64_t)max_len) > ws_bytes) return CCT_E_WORKSPACE;
     if (B == 0) return CCT_OK;
@@ -376,13 +376,22 @@ int cct_deflate_batch(const uint8_t *d_in, size_t in_stride, const int32_t *d_in
     return CCT_OK;
 }
 
+size_t cct_inflate_workspace_bytes(int B, size_t out_stride) {
+    InflateWs iw;
+    return inflate_ws_carve(&iw, nullptr, std::max(B, 1), (int64_t)out_stride);
+}
+
 int cct_inflate_batch(const uint8_t *d_in, size_t in_stride, const int32_t *d_in_len, int B, uint8_t *d_out,
-                      size_t out_stride, int32_t *d_out_len, uint32_t *d_status, void *stream) {
-    if (B < 0 || (B > 0 && (!d_in || !d_in_len || !d_out || !d_out_len))) return CCT_E_ARG;
+                      size_t out_stride, int32_t *d_out_len, uint32_t *d_status, void *d_ws, size_t ws_bytes, void *stream) {
+    if (B < 0 || (B > 0 && (!d_in || !d_in_len || !d_out || !d_out_len || !d_status || !d_ws))) return CCT_E_ARG;
     if (cct_device_count() == 0) return CCT_E_NO_DEVICE;
+    if (cct_inflate_workspace_bytes(B, out_stride) > ws_bytes) return CCT_E_WORKSPACE;
+    if (B == 0) return CCT_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    if (d_status && B) CK(cudaMemsetAsync(d_status, 0, (size_t)B * 4, st));
-    launch_inflate(d_in, nullptr, (int64_t)in_stride, d_in_len, 0, B, d_out, (int64_t)out_stride, d_out_len, d_status, st);
+    CK(cudaMemsetAsync(d_status, 0, (size_t)B * 4, st));
+    InflateWs iw;
+    inflate_ws_carve(&iw, d_ws, B, (int64_t)out_stride);
+    launch_inflate(d_in, (int64_t)in_stride, d_in_len, B, d_out, (int64_t)out_stride, d_out_len, d_status, iw, st);
     CK(cudaGetLastError());
     return CCT_OK;
 }

@@ -2,8 +2,10 @@
 //
 // Reference path restated (reference src/codec/core.py):
 //   core.py:385-402   read_header (magic, dims, flags)              -> k_dec_header
-//   core.py:420-421   zlib.decompress(file_bytes[13:])              -> k_dec_inflate (one stream per warp slot)
-//   core.py:453-520   padded-order walk with JUMP splicing          -> k_dec_ops (ops -> running values, unit table)
+//   core.py:420-421   zlib.decompress(file_bytes[13:])              -> k_inflate_sym (thread per stream) + k_lz_expand
+//                                                                      (warp per stream) + k_adler_check
+//   core.py:453-520   padded-order walk with JUMP splicing          -> k_dec_ops_scan/link/emit (chunk-parallel ops ->
+//                                                                      running values), k_dec_units (JUMP unit table)
 //                                                                      k_dec_scatter (value k -> raster index)
 #include <cuda_runtime.h>
 
@@ -32,32 +34,144 @@ size_t decode_ws_carve(DecodeWs *ws, void *mem, int B, int64_t n_px) {
     ws->slotA = (int32_t *)take((size_t)B * nb * sizeof(int32_t));
     ws->slotB = (int32_t *)take((size_t)B * nb * sizeof(int32_t));
     ws->fl = (uint8_t *)take((size_t)B);
+    used += inflate_ws_carve(&ws->iw, p ? p + used : nullptr, B, ws->pstride);
     ws->max_chunks = (int)(ws->pstride / kOpsChunk + 1);
     ws->chunks = (OpsChunkSum *)take((size_t)B * ws->max_chunks * sizeof(OpsChunkSum));
     return used;
 }
 
-// ------------------------------------------------------------------ generic batched inflate
-__global__ void __launch_bounds__(32) k_inflate(const uint8_t *__restrict__ in, const int64_t *__restrict__ in_off,
-                                                int64_t in_stride, const int32_t *__restrict__ in_len, int hdr_skip,
-                                                uint8_t *__restrict__ out, int64_t out_stride, int32_t *__restrict__ out_len,
-                                                uint32_t *__restrict__ status) {
-    __shared__ InflateTables tb;
-    const int i = blockIdx.x;
-    if (threadIdx.x != 0) return;
-    const uint8_t *src = in + (in_off ? in_off[i] : (int64_t)i * in_stride) + hdr_skip;
-    int len = (in_off ? (int)(in_off[i + 1] - in_off[i]) : in_len[i]) - hdr_skip;
-    int r = len > 0 ? inflate_stream(src, len, out + (int64_t)i * out_stride, (int)out_stride, tb) : -1;
-    if (r < 0) { if (status) status[i] |= 16u; r = 0; }  // CCT_ST_INFLATE
-    out_len[i] = r;
+// ------------------------------------------------------------------ inflate (two passes)
+// k_inflate_sym   Huffman decode, ONE THREAD PER STREAM (32 streams per warp, each with its own code tables in
+//                 shared memory): the bit-serial part of inflate touches only the bit reader and the tables and
+//                 appends LZ77 symbols to a per-stream list;
+// k_lz_expand     LZ77 expansion, one warp per stream: 32 symbols at a time, output offsets by a warp scan,
+//                 literals stored in parallel, matches copied by the whole warp in symbol order;
+// k_adler_check   Adler-32 of the expanded bytes against the stream trailer (CTA per stream).
+struct StreamSrc {  // where stream i lives: arena + offsets (with a header to skip) or fixed stride + lengths
+    const uint8_t *base; const int64_t *off; int64_t stride; const int32_t *len; int skip;
+    __device__ const uint8_t *ptr(int i) const { return base + (off ? off[i] : (int64_t)i * stride) + skip; }
+    __device__ int size(int i) const { return (off ? (int)(off[i + 1] - off[i]) : len[i]) - skip; }
+};
+
+constexpr int kInfStreams = 32;  // streams per CTA (one warp)
+__global__ void __launch_bounds__(kInfStreams) k_inflate_sym(StreamSrc src, const uint8_t *__restrict__ fl, int B,
+                                                             uint32_t *__restrict__ syms, int64_t sym_stride, int out_cap,
+                                                             int32_t *__restrict__ nsym, int32_t *__restrict__ out_len,
+                                                             uint32_t *__restrict__ adler_want, uint32_t *__restrict__ status) {
+    extern __shared__ __align__(16) unsigned char tb_raw[];
+    InflateTables *tbs = reinterpret_cast<InflateTables *>(tb_raw);
+    const int i = blockIdx.x * kInfStreams + threadIdx.x;
+    if (i >= B) return;
+    nsym[i] = 0; out_len[i] = 0; adler_want[i] = 1;
+    if (status[i] || (fl && !(fl[i] & 4u))) return;
+    int olen = 0;
+    uint32_t want = 0;
+    const int len = src.size(i);
+    const int ns = len > 0 ? inflate_symbols(src.ptr(i), len, syms + (int64_t)i * sym_stride, (int)sym_stride, out_cap,
+                                             tbs[threadIdx.x], &olen, &want) : -1;
+    if (ns < 0) { status[i] |= 16u; return; }  // CCT_ST_INFLATE
+    nsym[i] = ns; out_len[i] = olen; adler_want[i] = want;
 }
 
-int launch_inflate(const uint8_t *in, const int64_t *in_off, int64_t in_stride, const int32_t *in_len, int hdr_skip,
-                   int B, uint8_t *out, int64_t out_stride, int32_t *out_len, uint32_t *status, cudaStream_t st) {
-    if (B == 0) return 0;
-    { CCT_KERNEL(k_inflate, st);
-    k_inflate<<<B, 32, 0, st>>>(in, in_off, in_stride, in_len, hdr_skip, out, out_stride, out_len, status);
+constexpr int kLzWarps = 4;
+__global__ void __launch_bounds__(32 * kLzWarps) k_lz_expand(const uint32_t *__restrict__ syms, int64_t sym_stride,
+                                                             const int32_t *__restrict__ nsym, uint8_t *__restrict__ out,
+                                                             int64_t out_stride, int B) {
+    const int i = blockIdx.x * kLzWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= B) return;
+    const int ns = nsym[i];
+    const uint32_t *sy = syms + (int64_t)i * sym_stride;
+    uint8_t *o = out + (int64_t)i * out_stride;
+    int base = 0;
+    for (int g = 0; g < ns; g += 32) {
+        const int k = g + lane;
+        const uint32_t s = k < ns ? sy[k] : 0u;
+        const int dist = (int)(s >> 8);
+        const int len = k < ns ? (dist ? (int)(s & 255u) + 3 : 1) : 0;
+        int incl = len;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const int pos = base + incl - len;
+        if (len && !dist) o[pos] = (uint8_t)s;
+        unsigned mm = __ballot_sync(0xffffffffu, dist != 0);
+        __syncwarp();
+        while (mm) {
+            const int l = __ffs((int)mm) - 1;
+            mm &= mm - 1;
+            const int mpos = __shfl_sync(0xffffffffu, pos, l), mlen = __shfl_sync(0xffffffffu, len, l);
+            const int mdist = __shfl_sync(0xffffffffu, dist, l);
+            const uint8_t *from = o + mpos - mdist;
+            if (mdist >= mlen) {
+                for (int j = lane; j < mlen; j += 32) o[mpos + j] = from[j];
+            } else {  // overlapping copy: the source repeats with period mdist
+                for (int j = lane; j < mlen; j += 32) o[mpos + j] = from[j % mdist];
+            }
+            __syncwarp();
+        }
+        base += __shfl_sync(0xffffffffu, incl, 31);
     }
+}
+
+__global__ void __launch_bounds__(256) k_adler_check(const uint8_t *__restrict__ data, int64_t stride,
+                                                     const int32_t *__restrict__ len, const uint32_t *__restrict__ want,
+                                                     const uint8_t *__restrict__ fl, uint32_t *__restrict__ status) {
+    const int i = blockIdx.x, tid = threadIdx.x;
+    if (status[i] || (fl && !(fl[i] & 4u))) return;
+    const int n = len[i];
+    const uint8_t *w = data + (int64_t)i * stride;
+    unsigned long long sa = 0, sb = 0;  // A = 1 + sum d ; B = n + sum d * (n - idx)   (mod 65521)
+    for (int k = tid; k < n; k += 256) {
+        unsigned long long d = w[k];
+        sa += d; sb += d * (unsigned long long)(n - k);
+    }
+    __shared__ unsigned long long ra[8], rb[8];
+    for (int o = 16; o; o >>= 1) { sa += __shfl_xor_sync(0xffffffffu, sa, o); sb += __shfl_xor_sync(0xffffffffu, sb, o); }
+    if ((tid & 31) == 0) { ra[tid >> 5] = sa; rb[tid >> 5] = sb % 65521ull; }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long A = 1, Bv = (unsigned long long)n;
+        for (int k = 0; k < 8; k++) { A += ra[k]; Bv += rb[k]; }
+        const uint32_t got = (uint32_t)(((Bv % 65521ull) << 16) | (A % 65521ull));
+        if (got != want[i]) status[i] |= 16u;
+    }
+}
+
+static void launch_inflate_passes(StreamSrc src, const uint8_t *fl, int B, const InflateWs &iw, uint8_t *out,
+                                  int64_t out_stride, int32_t *out_len, uint32_t *status, cudaStream_t st) {
+    static bool attr_done = false;
+    const int smem = kInfStreams * (int)sizeof(InflateTables);
+    if (!attr_done) { cudaFuncSetAttribute(k_inflate_sym, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_done = true; }
+    { CCT_KERNEL(k_inflate_sym, st);
+    k_inflate_sym<<<(B + kInfStreams - 1) / kInfStreams, kInfStreams, smem, st>>>(src, fl, B, iw.syms, iw.sym_stride, (int)out_stride,
+                                                                                 iw.nsym, out_len, iw.adler, status);
+    }
+    { CCT_KERNEL(k_lz_expand, st);
+    k_lz_expand<<<(B + kLzWarps - 1) / kLzWarps, 32 * kLzWarps, 0, st>>>(iw.syms, iw.sym_stride, iw.nsym, out, out_stride, B);
+    }
+    { CCT_KERNEL(k_adler_check, st);
+    k_adler_check<<<B, 256, 0, st>>>(out, out_stride, out_len, iw.adler, fl, status);
+    }
+}
+
+size_t inflate_ws_carve(InflateWs *iw, void *mem, int B, int64_t out_stride) {
+    char *p = (char *)mem;
+    size_t used = 0;
+    auto take = [&](size_t bytes) { void *r = p ? p + used : nullptr; used += (size_t)align_up((int64_t)bytes, 256); return r; };
+    iw->sym_stride = align_up(out_stride, 4);
+    iw->syms = (uint32_t *)take((size_t)B * iw->sym_stride * sizeof(uint32_t));
+    iw->nsym = (int32_t *)take((size_t)B * 4);
+    iw->adler = (uint32_t *)take((size_t)B * 4);
+    return used;
+}
+
+int launch_inflate(const uint8_t *in, int64_t in_stride, const int32_t *in_len, int B, uint8_t *out, int64_t out_stride,
+                   int32_t *out_len, uint32_t *status, const InflateWs &iw, cudaStream_t st) {
+    if (B == 0) return 0;
+    StreamSrc src{in, nullptr, in_stride, in_len, 0};
+    launch_inflate_passes(src, nullptr, B, iw, out, out_stride, out_len, status, st);
     return 0;
 }
 
@@ -81,25 +195,18 @@ __global__ void k_dec_header(const uint8_t *__restrict__ files, const int64_t *_
     fl[i] = flags;
 }
 
-__global__ void __launch_bounds__(32) k_dec_inflate(const uint8_t *__restrict__ files, const int64_t *__restrict__ offsets,
-                                                    const uint8_t *__restrict__ fl, uint8_t *__restrict__ payload,
-                                                    int64_t pstride, int32_t *__restrict__ plen, uint32_t *__restrict__ status) {
-    __shared__ InflateTables tb;
-    const int i = blockIdx.x, lane = threadIdx.x;
-    if (status[i]) { if (lane == 0) plen[i] = 0; return; }
+// deflate flag off: the payload follows the header as is (core.py:420)
+__global__ void __launch_bounds__(128) k_dec_rawcopy(const uint8_t *__restrict__ files, const int64_t *__restrict__ offsets,
+                                                     const uint8_t *__restrict__ fl, uint8_t *__restrict__ payload,
+                                                     int64_t pstride, int32_t *__restrict__ plen, uint32_t *__restrict__ status) {
+    const int i = blockIdx.x;
+    if (status[i] || (fl[i] & 4u)) return;
     const uint8_t *src = files + offsets[i] + kHeaderBytes;
     const int len = (int)(offsets[i + 1] - offsets[i]) - kHeaderBytes;
+    const int n = len < (int)pstride ? len : (int)pstride;
     uint8_t *dst = payload + (int64_t)i * pstride;
-    if (fl[i] & 4u) {
-        if (lane != 0) return;
-        int r = len > 0 ? inflate_stream(src, len, dst, (int)pstride, tb) : -1;
-        if (r < 0) { status[i] |= 16u; r = 0; }
-        plen[i] = r;
-    } else {  // deflate flag off: the payload follows the header as is (core.py:420)
-        int n = len < (int)pstride ? len : (int)pstride;
-        for (int k = lane; k < n; k += 32) dst[k] = src[k];
-        if (lane == 0) { plen[i] = n; if (n < len) status[i] |= 64u; }
-    }
+    for (int k = threadIdx.x; k < n; k += 128) dst[k] = src[k];
+    if (threadIdx.x == 0) { plen[i] = n; if (n < len) status[i] |= 64u; }
 }
 
 // Op stream -> values, in three parallel passes over fixed chunks (see inflate_core.cuh).
@@ -179,8 +286,10 @@ void launch_decode(const uint8_t *files, const int64_t *offsets, int B, int rows
     { CCT_KERNEL(k_dec_header, st);
     k_dec_header<<<(B + 127) / 128, 128, 0, st>>>(files, offsets, B, rows, cols, status, ws.fl);
     }
-    { CCT_KERNEL(k_dec_inflate, st);
-    k_dec_inflate<<<B, 32, 0, st>>>(files, offsets, ws.fl, ws.payload, ws.pstride, ws.plen, status);
+    StreamSrc src{files, offsets, 0, nullptr, kHeaderBytes};
+    launch_inflate_passes(src, ws.fl, B, ws.iw, ws.payload, ws.pstride, ws.plen, status, st);
+    { CCT_KERNEL(k_dec_rawcopy, st);
+    k_dec_rawcopy<<<B, 128, 0, st>>>(files, offsets, ws.fl, ws.payload, ws.pstride, ws.plen, status);
     }
     dim3 gs((unsigned)((2 * ws.max_chunks + 127) / 128), (unsigned)B), ge((unsigned)((ws.max_chunks + 127) / 128), (unsigned)B);
     { CCT_KERNEL(k_dec_ops_scan, st);

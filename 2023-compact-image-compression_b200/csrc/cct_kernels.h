@@ -59,8 +59,15 @@ void launch_deflate(const uint8_t *in, int64_t in_stride, const int32_t *in_len,
                     int64_t out_stride, int32_t *out_len, const DeflateWs &ws, cudaStream_t st);
 
 // ---- cct_decode.cu
-int launch_inflate(const uint8_t *in, const int64_t *in_off, int64_t in_stride, const int32_t *in_len, int hdr_skip,
-                   int B, uint8_t *out, int64_t out_stride, int32_t *out_len, uint32_t *status, cudaStream_t st);
+struct InflateWs {
+    uint32_t *syms;      // [B][sym_stride] LZ77 symbols of each stream
+    int32_t *nsym;       // [B]
+    uint32_t *adler;     // [B] Adler-32 read from each trailer
+    int64_t sym_stride;
+};
+size_t inflate_ws_carve(InflateWs *iw, void *mem, int B, int64_t out_stride);
+int launch_inflate(const uint8_t *in, int64_t in_stride, const int32_t *in_len, int B, uint8_t *out, int64_t out_stride,
+                   int32_t *out_len, uint32_t *status, const InflateWs &iw, cudaStream_t st);
 struct DecodeWs {
     uint8_t *payload;  // [B][pstride]
     int32_t *plen;     // [B]
@@ -68,6 +75,7 @@ struct DecodeWs {
     uint8_t *jflag;    // [B][nb]
     int32_t *slotA, *slotB;  // [B][nb]
     uint8_t *fl;       // [B] transform flags from each header
+    InflateWs iw;
     OpsChunkSum *chunks;  // [B][max_chunks] op-stream chunk summaries
     int max_chunks;
     int64_t pstride;

@@ -17,6 +17,7 @@ struct InflateTables {  // per-stream decode tables (shared memory on the device
     uint16_t dst[1 << kDstBits];
     uint16_t lcount[16], dcount[16];   // canonical: number of codes of each length
     uint16_t lsym[288], dsym[32];      // symbols ordered by (length, symbol)
+    uint32_t pad;                      // size = 945 words: consecutive tables start in different smem banks
 };
 
 // RFC 1951 §3.2.5 length / distance bases as closed forms
@@ -31,6 +32,11 @@ CCT_HD int dist_base_inf(int ds) { return ds < 4 ? 1 + ds : 1 + ((2 + (ds & 1)) 
 struct BitReader {
     const uint8_t *in; int len, pos; uint64_t buf; int nbits; bool bad;
     CCT_HD void refill() {
+        if (nbits <= 32 && pos + 4 <= len && ((uintptr_t)(in + pos) & 3u) == 0) {  // aligned 32-bit fast path
+            buf |= (uint64_t)(*reinterpret_cast<const uint32_t *>(in + pos)) << nbits;
+            pos += 4; nbits += 32;
+            return;
+        }
         while (nbits <= 56 && pos < len) { buf |= (uint64_t)in[pos++] << nbits; nbits += 8; }
     }
     CCT_HD uint32_t peek(int n) const { return (uint32_t)(buf & ((1ull << n) - 1)); }
@@ -81,36 +87,36 @@ CCT_HD int decode_symbol(BitReader &br, const uint16_t *prim, int prim_bits, con
     return -1;
 }
 
-// zlib stream -> bytes.  Returns output length, or -1 on any error (bad header, invalid code, distance
-// too far, output overflow, truncated input, Adler-32 mismatch).
-CCT_HDN inline int inflate_stream(const uint8_t *in, int in_len, uint8_t *out, int out_cap, InflateTables &tb) {
+// Pass 1 of inflate: zlib stream -> LZ77 symbols (same packing as the encoder: bits 0..7 literal byte or len-3,
+// bits 8..23 distance, 0 = literal).  Nothing but the bit reader and the code tables is touched, so one
+// thread per stream can run it with its tables in shared memory.  Returns the number of symbols, or -1 on any
+// error (bad header, invalid code, too many symbols, truncated input).  *out_len = bytes the symbols expand
+// to; *adler_want = the trailer value (checked after pass 2).
+CCT_HDN inline int inflate_symbols(const uint8_t *in, int in_len, uint32_t *syms, int sym_cap, int out_cap,
+                                   InflateTables &tb, int *out_len, uint32_t *adler_want) {
     if (in_len < 6) return -1;
     if ((in[0] & 0x0F) != 8 || (((uint32_t)in[0] << 8) | in[1]) % 31 != 0 || (in[1] & 0x20)) return -1;
     BitReader br{in, in_len - 4, 2, 0, 0, false};
-    int op = 0;
-    uint32_t a1 = 1, a2 = 0;
-    int since_mod = 0;
+    int ns = 0, op = 0;
     bool last = false;
     uint8_t lens[320];
     while (!last) {
         br.refill();
         last = br.take(1);
-        int type = (int)br.take(2);
-        if (type == 0) {
+        const int type = (int)br.take(2);
+        if (type == 0) {  // stored: every byte becomes a literal symbol
             br.drop(br.nbits & 7);
             br.refill();
-            uint32_t len = br.take(16), nlen = br.take(16);
+            const uint32_t len = br.take(16), nlen = br.take(16);
             if (br.bad || (len ^ 0xFFFFu) != nlen) return -1;
-            // bytes still in the bit buffer first, then straight from the input
-            if (op + (int)len > out_cap) return -1;
+            if (ns + (int)len > sym_cap || op + (int)len > out_cap) return -1;
             for (uint32_t i = 0; i < len; i++) {
                 uint8_t c;
-                if (br.nbits >= 8) { c = (uint8_t)br.take(8); }
+                if (br.nbits >= 8) c = (uint8_t)br.take(8);
                 else { if (br.pos >= br.len) return -1; c = br.in[br.pos++]; }
-                out[op++] = c;
-                a1 += c; a2 += a1;
-                if (++since_mod == 5552) { a1 %= 65521u; a2 %= 65521u; since_mod = 0; }
+                syms[ns++] = c;
             }
+            op += (int)len;
             continue;
         }
         if (type == 3) return -1;
@@ -124,17 +130,16 @@ CCT_HDN inline int inflate_stream(const uint8_t *in, int in_len, uint8_t *out, i
             build_decode_table(lens, 30, kDstBits, tb.dst, tb.dcount, tb.dsym);
         } else {
             const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
-            int nlen = (int)br.take(5) + 257, ndist = (int)br.take(5) + 1, ncode = (int)br.take(4) + 4;
+            const int nlen = (int)br.take(5) + 257, ndist = (int)br.take(5) + 1, ncode = (int)br.take(4) + 4;
             if (nlen > 286 || ndist > 30) return -1;
             uint8_t cl[19];
             for (int i = 0; i < 19; i++) cl[i] = 0;
             for (int i = 0; i < ncode; i++) { br.refill(); cl[order[i]] = (uint8_t)br.take(3); }
-            // the code-length code is tiny: reuse the distance table storage for it
-            if (!build_decode_table(cl, 19, 7, tb.dst, tb.dcount, tb.dsym)) return -1;
+            if (!build_decode_table(cl, 19, 7, tb.dst, tb.dcount, tb.dsym)) return -1;  // borrows the distance table
             int idx = 0;
             while (idx < nlen + ndist) {
                 br.refill();
-                int sym = decode_symbol(br, tb.dst, 7, tb.dcount, tb.dsym);
+                const int sym = decode_symbol(br, tb.dst, 7, tb.dcount, tb.dsym);
                 if (sym < 0 || br.bad) return -1;
                 if (sym < 16) lens[idx++] = (uint8_t)sym;
                 else {
@@ -155,42 +160,51 @@ CCT_HDN inline int inflate_stream(const uint8_t *in, int in_len, uint8_t *out, i
         for (;;) {
             br.refill();
             int sym = decode_symbol(br, tb.lit, kLitBits, tb.lcount, tb.lsym);
-            if (sym < 0 || br.bad) return -1;
-            if (sym < 256) {
-                if (op >= out_cap) return -1;
-                out[op++] = (uint8_t)sym;
-                a1 += (uint32_t)sym; a2 += a1;
-                if (++since_mod == 5552) { a1 %= 65521u; a2 %= 65521u; since_mod = 0; }
-                continue;
-            }
+            if (sym < 0 || br.bad || ns >= sym_cap) return -1;
+            if (sym < 256) { syms[ns++] = (uint32_t)sym; op++; continue; }
             if (sym == 256) break;
             sym -= 257;
             if (sym >= 29) return -1;
-            int lx = len_extra_bits_inf(sym);
-            int len = len_base_inf(sym) + (int)br.take(lx);
-            int ds = decode_symbol(br, tb.dst, kDstBits, tb.dcount, tb.dsym);
+            const int len = len_base_inf(sym) + (int)br.take(len_extra_bits_inf(sym));
+            const int ds = decode_symbol(br, tb.dst, kDstBits, tb.dcount, tb.dsym);
             if (ds < 0 || ds >= 30) return -1;
             br.refill();
-            int dx = ds < 4 ? 0 : (ds >> 1) - 1;
-            int dist = dist_base_inf(ds) + (int)br.take(dx);
-            if (br.bad || dist > op || op + len > out_cap) return -1;
-            for (int i = 0; i < len; i++) {
-                uint8_t c = out[op - dist];
-                out[op++] = c;
-                a1 += c; a2 += a1;
-                if (++since_mod == 5552) { a1 %= 65521u; a2 %= 65521u; since_mod = 0; }
-            }
+            const int dist = dist_base_inf(ds) + (int)br.take(ds < 4 ? 0 : (ds >> 1) - 1);
+            if (br.bad || dist > op) return -1;
+            syms[ns++] = (uint32_t)(len - 3) | ((uint32_t)dist << 8);
+            op += len;
         }
+        if (op > out_cap) return -1;
     }
-    a1 %= 65521u; a2 %= 65521u;
+    br.drop(br.nbits & 7);  // the Adler-32 trailer follows the last block at the next byte boundary
+    if (br.pos - (br.nbits >> 3) != in_len - 4) return -1;
     const uint8_t *t = in + in_len - 4;
-    // the trailer must start right after the last block (byte aligned)
-    br.drop(br.nbits & 7);
-    int consumed = br.pos - (br.nbits >> 3);
-    if (consumed != in_len - 4) return -1;
-    uint32_t want = ((uint32_t)t[0] << 24) | ((uint32_t)t[1] << 16) | ((uint32_t)t[2] << 8) | t[3];
-    if (want != ((a2 << 16) | a1)) return -1;
-    return op;
+    *adler_want = ((uint32_t)t[0] << 24) | ((uint32_t)t[1] << 16) | ((uint32_t)t[2] << 8) | t[3];
+    *out_len = op;
+    return ns;
+}
+
+// Pass 2 of inflate, sequential form (CPU harness): symbols -> bytes.
+CCT_HDN inline void lz_expand(const uint32_t *syms, int ns, uint8_t *out) {
+    int op = 0;
+    for (int i = 0; i < ns; i++) {
+        const uint32_t sy = syms[i];
+        const int dist = (int)(sy >> 8);
+        if (!dist) { out[op++] = (uint8_t)sy; continue; }
+        const int len = (int)(sy & 255u) + 3;
+        for (int k = 0; k < len; k++, op++) out[op] = out[op - dist];
+    }
+}
+
+CCT_HD uint32_t adler32_bytes(const uint8_t *p, int n) {
+    uint32_t a = 1, b = 0;
+    while (n > 0) {
+        int k = n < 5552 ? n : 5552;
+        n -= k;
+        while (k--) { a += *p++; b += a; }
+        a %= 65521u; b %= 65521u;
+    }
+    return (b << 16) | a;
 }
 
 // ------------------------------------------------------------------------------------------------

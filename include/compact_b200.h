@@ -128,14 +128,18 @@ int cct_debug_encode_stages(const uint16_t *d_px, int rows, int cols, uint32_t f
                             uint8_t *d_jump, uint8_t *d_payload, int32_t *d_payload_len, void *d_ws, size_t ws_bytes,
                             void *stream);
 /* zlib-level-9 stream (bit-exact with libz 1.3 compress2(...,9)) of B byte strings of equal capacity:
- * string i = d_in[i*in_stride .. +d_in_len[i]); stream i is written at d_out[i*out_stride ..], length d_out_len[i]. */
+ * string i = d_in[i*in_stride .. +d_in_len[i]); stream i is written at d_out[i*out_stride ..], length d_out_len[i].
+ * d_in must be 16-byte aligned and in_stride a multiple of 16. */
 size_t cct_deflate_workspace_bytes(int B, size_t max_len);
 size_t cct_deflate_bound(size_t len);
 int cct_deflate_batch(const uint8_t *d_in, size_t in_stride, const int32_t *d_in_len, int B, size_t max_len,
                       uint8_t *d_out, size_t out_stride, int32_t *d_out_len, void *d_ws, size_t ws_bytes, void *stream);
-/* RFC 1950 inflate of B streams (any conformant zlib stream). d_status[i] gets CCT_ST_INFLATE on error. */
+/* RFC 1950 inflate of B streams (any conformant zlib stream). d_status[i] gets CCT_ST_INFLATE on error
+ * (invalid code, output longer than out_stride, truncated input, Adler-32 mismatch). */
+size_t cct_inflate_workspace_bytes(int B, size_t out_stride);
 int cct_inflate_batch(const uint8_t *d_in, size_t in_stride, const int32_t *d_in_len, int B, uint8_t *d_out,
-                      size_t out_stride, int32_t *d_out_len, uint32_t *d_status, void *stream);
+                      size_t out_stride, int32_t *d_out_len, uint32_t *d_status, void *d_ws, size_t ws_bytes,
+                      void *stream);
 
 /* Launch accounting for bench.py: number of kernels launched by this library since the last reset, and
  * optional per-kernel device timing (CUDA events recorded on the launching stream around every kernel).

@@ -81,8 +81,10 @@ def _gpu_inflate(torch, native, streams, cap):
     d_out = torch.zeros((B, cap), dtype=torch.uint8, device="cuda")
     d_olen = torch.zeros(B, dtype=torch.int32, device="cuda")
     d_st = torch.zeros(B, dtype=torch.int32, device="cuda")
+    ws = torch.empty(int(L.cct_inflate_workspace_bytes(B, cap)), dtype=torch.uint8, device="cuda")
     native.check(L.cct_inflate_batch(d_in.data_ptr(), in_stride, d_len.data_ptr(), B, d_out.data_ptr(), cap,
-                                     d_olen.data_ptr(), d_st.data_ptr(), torch.cuda.current_stream().cuda_stream))
+                                     d_olen.data_ptr(), d_st.data_ptr(), ws.data_ptr(), ws.numel(),
+                                     torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     out, olen, st = d_out.cpu().numpy(), d_olen.cpu().numpy(), d_st.cpu().numpy()
     return [out[i, :olen[i]].tobytes() for i in range(B)], st
