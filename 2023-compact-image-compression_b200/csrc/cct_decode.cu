@@ -61,16 +61,25 @@ __global__ void __launch_bounds__(kInfStreams) k_inflate_sym(StreamSrc src, cons
     extern __shared__ __align__(16) unsigned char tb_raw[];
     InflateTables *tbs = reinterpret_cast<InflateTables *>(tb_raw);
     const int i = blockIdx.x * kInfStreams + threadIdx.x;
+    const bool mine = i < B && !status[i] && !(fl && !(fl[i] & 4u));
+    InflateState st;
+    st.phase = kInfDone;
+    st.ns = 0; st.op = 0; st.adler_want = 1;
+    if (mine) {
+        const int len = src.size(i);
+        if (len > 0) inflate_begin(st, src.ptr(i), len); else st.phase = kInfError;
+    }
+    uint32_t *out = syms + (int64_t)(i < B ? i : 0) * sym_stride;
+    // flat state machine: all 32 streams take one step, then reconverge at the vote
+    for (;;) {
+        const bool run = st.phase < kInfDone;
+        if (!__any_sync(0xffffffffu, run)) break;
+        if (run) inflate_step(st, tbs[threadIdx.x], out, (int)sym_stride, out_cap);
+    }
     if (i >= B) return;
-    nsym[i] = 0; out_len[i] = 0; adler_want[i] = 1;
-    if (status[i] || (fl && !(fl[i] & 4u))) return;
-    int olen = 0;
-    uint32_t want = 0;
-    const int len = src.size(i);
-    const int ns = len > 0 ? inflate_symbols(src.ptr(i), len, syms + (int64_t)i * sym_stride, (int)sym_stride, out_cap,
-                                             tbs[threadIdx.x], &olen, &want) : -1;
-    if (ns < 0) { status[i] |= 16u; return; }  // CCT_ST_INFLATE
-    nsym[i] = ns; out_len[i] = olen; adler_want[i] = want;
+    if (!mine) { nsym[i] = 0; out_len[i] = 0; adler_want[i] = 1; return; }
+    if (st.phase != kInfDone) { status[i] |= 16u; nsym[i] = 0; out_len[i] = 0; adler_want[i] = 1; return; }  // CCT_ST_INFLATE
+    nsym[i] = st.ns; out_len[i] = st.op; adler_want[i] = st.adler_want;
 }
 
 constexpr int kLzWarps = 4;

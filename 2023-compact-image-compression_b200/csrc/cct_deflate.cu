@@ -35,10 +35,10 @@ size_t deflate_ws_carve(DeflateWs *ws, void *mem, int B, int64_t max_len) {
     ws->max_blocks = (int)(max_len / kSymEnd + 2);
     ws->dist16 = (uint16_t *)take((size_t)B * ws->stride * sizeof(uint16_t));
     ws->rb16 = (uint16_t *)take((size_t)B * ws->stride * sizeof(uint16_t));
-    ws->rl16 = (uint16_t *)take((size_t)B * ws->stride * sizeof(uint16_t));
+    ws->recs = (ChainRec *)take((size_t)B * ws->stride * sizeof(ChainRec));
     ws->mtab = (uint32_t *)take((size_t)B * ws->stride * sizeof(uint32_t));
     ws->mhi = (uint32_t *)take((size_t)B * ws->stride * sizeof(uint32_t));
-    ws->syms = (uint32_t *)take((size_t)B * ws->stride * sizeof(uint32_t));
+    ws->syms = ws->mtab;  // the dense symbol array reuses the probe table once the walk is over
     ws->rec = (uint32_t *)take((size_t)B * ws->stride * sizeof(uint32_t));
     ws->flag = (uint8_t *)take((size_t)B * ws->stride);
     ws->max_win = (int)(max_len / kWalkWin + 1);
@@ -59,14 +59,14 @@ size_t deflate_ws_carve(DeflateWs *ws, void *mem, int B, int64_t max_len) {
 constexpr int kHeadEntries = 32768;
 __global__ void __launch_bounds__(32) k_chains(const uint8_t *__restrict__ in, int64_t in_stride,
                                                const int32_t *__restrict__ in_len, uint16_t *__restrict__ dist16,
-                                               uint16_t *__restrict__ rb16, uint16_t *__restrict__ rl16, int64_t stride) {
+                                               uint16_t *__restrict__ rb16, ChainRec *__restrict__ recs_all, int64_t stride) {
     extern __shared__ uint16_t head[];
     const int stream = blockIdx.x, lane = threadIdx.x;
     const int n = in_len[stream];
     const uint8_t *w = in + (int64_t)stream * in_stride;
     uint16_t *d16 = dist16 + (int64_t)stream * stride;
     uint16_t *rb = rb16 + (int64_t)stream * stride;
-    uint16_t *rl = rl16 + (int64_t)stream * stride;
+    ChainRec *recs = recs_all + (int64_t)stream * stride;
     uint32_t *head32 = reinterpret_cast<uint32_t *>(head);
     for (int i = lane; i < kHeadEntries / 2; i += 32) head32[i] = 0x40004000u;  // (0 - 49152) & 0xFFFF
     __syncwarp();
@@ -90,29 +90,42 @@ __global__ void __launch_bounds__(32) k_chains(const uint8_t *__restrict__ in, i
         p1 = fetch(cbase + 256, lane);
         p1x = lane < 2 ? fetch(cbase + 256, 32 + lane) : 0u;
         __syncwarp();
-#pragma unroll 1
-        for (int base = cbase; base < cbase + 128 && base < n; base += 32) {
-            if (base && (base & 8191) == 0) {
-                const uint32_t far = (uint32_t)(base - 49152) & 0xFFFFu;
-                for (int i = lane; i < kHeadEntries / 2; i += 32) {
-                    uint32_t v = head32[i];
-                    uint32_t lo = v & 0xFFFFu, hi = v >> 16;
-                    if (((uint32_t)(base - lo) & 0xFFFFu) >= 32768u) lo = far;
-                    if (((uint32_t)(base - hi) & 0xFFFFu) >= 32768u) hi = far;
-                    head32[i] = lo | (hi << 16);
-                }
-                __syncwarp();
+        if (cbase && (cbase & 8191) == 0) {  // sweep: re-park entries older than 32767 (128 divides 8192)
+            const uint32_t far = (uint32_t)(cbase - 49152) & 0xFFFFu;
+            for (int i = lane; i < kHeadEntries / 2; i += 32) {
+                uint32_t v = head32[i];
+                uint32_t lo = v & 0xFFFFu, hi = v >> 16;
+                if (((uint32_t)(cbase - lo) & 0xFFFFu) >= 32768u) lo = far;
+                if (((uint32_t)(cbase - hi) & 0xFFFFu) >= 32768u) hi = far;
+                head32[i] = lo | (hi << 16);
             }
-            const int s = base + lane;
-            const uint8_t *sb = stage + 4 + (base - cbase) + lane;  // sb[k] = w[s + k], k in [-1, 2]
-            const bool valid = s >= 1 && s + 2 < n;  // position 0 doubles as NIL in zlib: never a match source
-            uint32_t h = 0x8000u | (uint32_t)lane;   // unique key for lanes that do not insert
-            if (valid) h = hash3(sb);
+            __syncwarp();
+        }
+        // phase A (independent of the head table, so the four groups of the chunk overlap): hashes, validity,
+        // equal-to-previous flags
+        uint32_t hh[4];
+        unsigned vm[4], em[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int s = cbase + 32 * j + lane;
+            const uint8_t *sb = stage + 4 + 32 * j + lane;  // sb[k] = w[s + k], k in [-1, 2]
+            const bool valid = s >= 1 && s + 2 < n;         // position 0 doubles as NIL in zlib: never a match source
+            hh[j] = valid ? hash3(sb) : (0x8000u | (uint32_t)lane);
+            vm[j] = __ballot_sync(0xffffffffu, valid);
+            em[j] = __ballot_sync(0xffffffffu, s >= 1 && s < n && sb[0] == sb[-1]);
+        }
+        // phase B: table lookups / insertions, group after group
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int s = cbase + 32 * j + lane;
+            if (cbase + 32 * j >= n) break;
+            const uint32_t h = hh[j];
+            const unsigned vmask = vm[j];
+            const bool valid = (vmask >> lane) & 1u;
             // previous position with the same hash: the nearest lower lane holding it, else the head table.
             // Same-hash lanes inside one group are found without a full match: either every inserting lane has
             // one hash (a run), or all hashes are distinct -- detected by letting every lane store its position
             // and read the slot back -- or, rarely, the general case (__match_any_sync is a software loop here).
-            const unsigned vmask = __ballot_sync(0xffffffffu, valid);
             int dist = 0;
             uint32_t old = 0;
             if (valid) old = head[h];
@@ -144,10 +157,8 @@ __global__ void __launch_bounds__(32) k_chains(const uint8_t *__restrict__ in, i
                     if (valid && (peers >> lane) == 1u) head[h] = (uint16_t)s;  // the latest position wins
                 }
             }
-            // equal-to-previous flags -> count of equal bytes before s
-            const bool eq = s >= 1 && s < n && sb[0] == sb[-1];
-            const unsigned em = __ballot_sync(0xffffffffu, eq);
-            const unsigned zeros_below = ~em & ((2u << lane) - 1u);  // positions <= lane whose flag is 0
+            // count of equal bytes before s from the flags
+            const unsigned zeros_below = ~em[j] & ((2u << lane) - 1u);  // positions <= lane whose flag is 0
             int back = zeros_below ? lane - (31 - __clz((int)zeros_below)) : lane + 1 + carry;
             if (back > 65535) back = 65535;
             carry = __shfl_sync(0xffffffffu, back, 31);
@@ -155,31 +166,32 @@ __global__ void __launch_bounds__(32) k_chains(const uint8_t *__restrict__ in, i
             __syncwarp();
         }
     }
-    // reverse pass: count of equal bytes after s
+    // reverse pass: count of equal bytes after s; assembles the per-position record the chain walks load
+    __syncwarp();
     carry = 0;  // rl of position base+32
     for (int base = ((n - 1) / 32) * 32; base >= 0; base -= 32) {
         const int s = base + lane;
-        const bool eq = s + 1 < n && w[s] == w[s + 1];
+        const uint8_t c0 = s < n ? w[s] : 0, c1 = s + 1 < n ? w[s + 1] : 0;
+        const bool eq = s + 1 < n && c0 == c1;
         const unsigned em = __ballot_sync(0xffffffffu, eq);
         const unsigned zeros_above = ~em & ~((1u << lane) - 1u);  // positions >= lane whose flag is 0
         int fwd = zeros_above ? (__ffs((int)zeros_above) - 1) - lane : (32 - lane) + carry;
         if (fwd > 65535) fwd = 65535;
         carry = __shfl_sync(0xffffffffu, fwd, 0);
-        if (s < n) rl[s] = (uint16_t)fwd;
+        if (s < n) recs[s] = ChainRec{d16[s], (uint16_t)fwd, rb[s], c0, c1};
     }
 }
 
 // ------------------------------------------------------------------ k_probe
 __global__ void __launch_bounds__(256) k_probe(const uint8_t *__restrict__ in, int64_t in_stride,
-                                               const int32_t *__restrict__ in_len, const uint16_t *__restrict__ dist16,
-                                               const uint16_t *__restrict__ rb16, const uint16_t *__restrict__ rl16,
+                                               const int32_t *__restrict__ in_len, const ChainRec *__restrict__ recs,
                                                uint32_t *__restrict__ mlo, uint32_t *__restrict__ mhi, int64_t stride) {
     const int stream = blockIdx.y;
     const int n = in_len[stream];
     const int s = blockIdx.x * 256 + threadIdx.x;
     if (s >= n) return;
     const int64_t o = (int64_t)stream * stride;
-    LzView v{in + (int64_t)stream * in_stride, dist16 + o, rb16 + o, rl16 + o, n};
+    LzView v{in + (int64_t)stream * in_stride, recs + o, n};
     uint32_t lo, hi;
     match_probe(v, s, kProbeK, &lo, &hi);
     mlo[o + s] = lo;
@@ -193,8 +205,7 @@ __global__ void __launch_bounds__(256) k_probe(const uint8_t *__restrict__ in, i
 //                  speculative one (typically a few symbols), then adopts the window's recorded exit state
 //   k_symscan      CTA per stream: prefix sum of the symbol-start flags -> dense symbol array, block boundaries
 __global__ void __launch_bounds__(128) k_walk_spec(const uint8_t *__restrict__ in, int64_t in_stride,
-                                                   const int32_t *__restrict__ in_len, const uint16_t *__restrict__ dist16,
-                                                   const uint16_t *__restrict__ rb16, const uint16_t *__restrict__ rl16,
+                                                   const int32_t *__restrict__ in_len, const ChainRec *__restrict__ recs,
                                                    const uint32_t *__restrict__ mlo, const uint32_t *__restrict__ mhi, uint8_t *__restrict__ flag,
                                                    uint32_t *__restrict__ rec, Walk *__restrict__ exits, int64_t stride,
                                                    int max_win) {
@@ -204,13 +215,12 @@ __global__ void __launch_bounds__(128) k_walk_spec(const uint8_t *__restrict__ i
     const int ws = k * kWalkWin;
     if (ws >= n) return;
     const int64_t o = (int64_t)stream * stride;
-    LzView v{in + (int64_t)stream * in_stride, dist16 + o, rb16 + o, rl16 + o, n};
+    LzView v{in + (int64_t)stream * in_stride, recs + o, n};
     exits[(int64_t)stream * max_win + k] = walk_window(v, ProbeTab{mlo + o, mhi + o}, ws, min(ws + kWalkWin, n), flag + o, rec + o);
 }
 
 __global__ void __launch_bounds__(128) k_walk_stitch(const uint8_t *__restrict__ in, int64_t in_stride,
-                                                    const int32_t *__restrict__ in_len, const uint16_t *__restrict__ dist16,
-                                                    const uint16_t *__restrict__ rb16, const uint16_t *__restrict__ rl16,
+                                                    const int32_t *__restrict__ in_len, const ChainRec *__restrict__ recs,
                                                     const uint32_t *__restrict__ mlo, const uint32_t *__restrict__ mhi, uint8_t *__restrict__ flag,
                                                     uint32_t *__restrict__ rec, const Walk *__restrict__ exits, int64_t stride,
                                                     int max_win, int B) {
@@ -218,7 +228,7 @@ __global__ void __launch_bounds__(128) k_walk_stitch(const uint8_t *__restrict__
     const int stream = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (stream >= B || (threadIdx.x & 31)) return;
     const int64_t o = (int64_t)stream * stride;
-    LzView v{in + (int64_t)stream * in_stride, dist16 + o, rb16 + o, rl16 + o, in_len[stream]};
+    LzView v{in + (int64_t)stream * in_stride, recs + o, in_len[stream]};
     walk_stitch(v, ProbeTab{mlo + o, mhi + o}, kWalkWin, flag + o, rec + o, exits + (int64_t)stream * max_win);
 }
 
@@ -473,20 +483,20 @@ void launch_deflate(const uint8_t *in, int64_t in_stride, const int32_t *in_len,
         attr_done = true;
     }
     { CCT_KERNEL(k_chains, st);
-    k_chains<<<B, 32, chain_smem, st>>>(in, in_stride, in_len, ws.dist16, ws.rb16, ws.rl16, ws.stride);
+    k_chains<<<B, 32, chain_smem, st>>>(in, in_stride, in_len, ws.dist16, ws.rb16, ws.recs, ws.stride);
     }
     dim3 gp((unsigned)((max_len + 255) / 256), (unsigned)B);
     { CCT_KERNEL(k_probe, st);
-    k_probe<<<gp, 256, 0, st>>>(in, in_stride, in_len, ws.dist16, ws.rb16, ws.rl16, ws.mtab, ws.mhi, ws.stride);
+    k_probe<<<gp, 256, 0, st>>>(in, in_stride, in_len, ws.recs, ws.mtab, ws.mhi, ws.stride);
     }
     cudaMemsetAsync(ws.flag, 0, (size_t)B * ws.stride, st);
     dim3 gw((unsigned)((ws.max_win + 127) / 128), (unsigned)B);
     { CCT_KERNEL(k_walk_spec, st);
-    k_walk_spec<<<gw, 128, 0, st>>>(in, in_stride, in_len, ws.dist16, ws.rb16, ws.rl16, ws.mtab, ws.mhi, ws.flag, ws.rec, ws.exits, ws.stride,
+    k_walk_spec<<<gw, 128, 0, st>>>(in, in_stride, in_len, ws.recs, ws.mtab, ws.mhi, ws.flag, ws.rec, ws.exits, ws.stride,
                                     ws.max_win);
     }
     { CCT_KERNEL(k_walk_stitch, st);
-    k_walk_stitch<<<(B + 3) / 4, 128, 0, st>>>(in, in_stride, in_len, ws.dist16, ws.rb16, ws.rl16, ws.mtab, ws.mhi, ws.flag, ws.rec, ws.exits,
+    k_walk_stitch<<<(B + 3) / 4, 128, 0, st>>>(in, in_stride, in_len, ws.recs, ws.mtab, ws.mhi, ws.flag, ws.rec, ws.exits,
                                                 ws.stride, ws.max_win, B);
     }
     { CCT_KERNEL(k_symscan, st);

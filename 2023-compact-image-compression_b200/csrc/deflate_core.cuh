@@ -79,12 +79,18 @@ CCT_HD uint32_t static_lcode(int n) {
 // ------------------------------------------------------------------------------------------------
 // longest_match
 // ------------------------------------------------------------------------------------------------
+// Everything the chain walk needs to know about a position, in one aligned 8-byte load.
+struct alignas(8) ChainRec {
+    uint16_t dist;  // chain link: distance to the previous position with the same hash, 0 = none / >= 32768
+    uint16_t rl;    // number of bytes equal to w[p] immediately after p  (capped at 65535)
+    uint16_t rb;    // number of bytes equal to w[p] immediately before p (capped at 65535)
+    uint8_t b0, b1; // w[p], w[p+1]
+};
+
 struct LzView {
-    const uint8_t *w;        // payload bytes
-    const uint16_t *dist16;  // chain links: distance to previous same-hash position, 0 = none / >= 32768
-    const uint16_t *rb16;    // number of bytes equal to w[p] immediately before p (capped at 65535)
-    const uint16_t *rl16;    // number of bytes equal to w[p] immediately after p  (capped at 65535)
-    int n;                   // payload length
+    const uint8_t *w;       // payload bytes
+    const ChainRec *recs;   // per-position record (k_chains)
+    int n;                  // payload length
 };
 
 CCT_HD int match_extend(const uint8_t *a, const uint8_t *b, int from, int cap) {
@@ -112,22 +118,26 @@ constexpr int kWalkSteps = 2;   // step cap of the probe reached
 // one step; the chain budget and the distance limit are charged as if every member had been visited.
 CCT_HD int chain_walk(const LzView &v, int s, int cap, int &best, int &bdist, int chain, int max_steps) {
     const uint8_t *b = v.w + s;
+    const ChainRec rs = v.recs[s];
+    const uint8_t b0 = rs.b0, b1 = rs.b1;
     int R = 0;  // leading run of the target, if it is at least one hash triple long
-    if (b[1] == b[0] && b[2] == b[0]) { R = (int)v.rl16[s] + 1; if (R > cap) R = cap; }
-    int cur = s - v.dist16[s];
+    if (rs.rl >= 2) { R = (int)rs.rl + 1; if (R > cap) R = cap; }
+    int cur = s - rs.dist;
     for (int step = 1;; step++) {
         CCT_COUNT(0);
+        const ChainRec rc = v.recs[cur];  // one load: link, run lengths and the first two bytes of the candidate
         const uint8_t *a = v.w + cur;
-        if (v.rl16[cur] >= 2) {
+        const uint8_t a_best = a[best], a_best1 = a[best - 1];
+        if (rc.rl >= 2) {
             // cur starts a triple (c,c,c): the chain entries below it inside the run form one group
-            const int m = (int)v.rl16[cur] + 1;  // leading c's of the top candidate
-            int t = v.rb16[cur];                 // further candidates of this run below cur
-            if (cur - t < 1) t = cur - 1;        // position 0 is never in a chain
+            const int m = (int)rc.rl + 1;  // leading c's of the top candidate
+            int t = rc.rb;                 // further candidates of this run below cur
+            if (cur - t < 1) t = cur - 1;  // position 0 is never in a chain
             const int count_dist = kMaxDist - (s - cur);
             int nvis = t + 1;
             if (chain < nvis) nvis = chain;
             if (count_dist < nvis) nvis = count_dist;
-            if (R && a[0] == b[0]) {
+            if (R && rc.b0 == b0) {
                 const int i_key = m >= R ? 0 : R - m;  // first member with at least R leading c's
                 if (R < cap && m > R) {
                     if (R > best) { best = R; bdist = s - cur; }
@@ -143,14 +153,23 @@ CCT_HD int chain_walk(const LzView &v, int s, int cap, int &best, int &bdist, in
             if (nvis < t + 1) return nvis == count_dist ? kWalkDone : kWalkBudget;
             chain -= t;
             cur -= t;
-        } else if (a[best] == b[best] && a[best - 1] == b[best - 1] && a[0] == b[0] && a[1] == b[1]) {
+            if (t) {  // moved to the bottom of the run: its link is the group's way out
+                const int dl = v.recs[cur].dist;
+                if (dl == 0) return kWalkDone;
+                cur -= dl;
+                if (s - cur >= kMaxDist) return kWalkDone;
+                if (--chain == 0) return kWalkBudget;
+                if (step == max_steps) return kWalkSteps;
+                continue;
+            }
+        } else if (a_best == b[best] && a_best1 == b[best - 1] && rc.b0 == b0 && rc.b1 == b1) {
             const int len = match_extend(a, b, 2, cap);
             if (len > best) {
                 best = len; bdist = s - cur;
                 if (len >= cap) return kWalkDone;
             }
         }
-        const int dl = v.dist16[cur];
+        const int dl = rc.dist;
         if (dl == 0) return kWalkDone;
         cur -= dl;
         if (s - cur >= kMaxDist) return kWalkDone;  // cur <= limit
@@ -168,7 +187,7 @@ CCT_HD void match_probe(const LzView &v, int s, int K, uint32_t *lo, uint32_t *h
     *lo = *hi = 0;
     const int look = v.n - s;
     if (look < kMinMatch) return;
-    const int d0 = v.dist16[s];
+    const int d0 = v.recs[s].dist;
     if (d0 == 0 || d0 > kMaxDist) return;
     const int cap = look < kMaxMatch ? look : kMaxMatch;
     int best = 2, bdist = 0;

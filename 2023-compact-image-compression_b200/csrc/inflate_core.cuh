@@ -89,99 +89,129 @@ CCT_HD int decode_symbol(BitReader &br, const uint16_t *prim, int prim_bits, con
 
 // Pass 1 of inflate: zlib stream -> LZ77 symbols (same packing as the encoder: bits 0..7 literal byte or len-3,
 // bits 8..23 distance, 0 = literal).  Nothing but the bit reader and the code tables is touched, so one
-// thread per stream can run it with its tables in shared memory.  Returns the number of symbols, or -1 on any
-// error (bad header, invalid code, too many symbols, truncated input).  *out_len = bytes the symbols expand
-// to; *adler_want = the trailer value (checked after pass 2).
+// thread per stream can run it with its tables in shared memory.  It is written as a flat state machine
+// (`inflate_step` = one block header, one symbol, or a few stored bytes) so that the 32 streams sharing a warp
+// reconverge after every step instead of drifting apart inside nested loops.
+enum { kInfHeader = 0, kInfSymbol = 1, kInfStored = 2, kInfTrailer = 3, kInfDone = 4, kInfError = 5 };
+struct InflateState {
+    BitReader br;
+    int phase, ns, op, stored_left;
+    bool last;
+    uint32_t adler_want;
+};
+
+CCT_HD void inflate_begin(InflateState &st, const uint8_t *in, int in_len) {
+    st.br = BitReader{in, in_len - 4, 2, 0, 0, false};
+    st.ns = 0; st.op = 0; st.stored_left = 0; st.last = false; st.adler_want = 1;
+    st.phase = kInfHeader;
+    if (in_len < 6 || (in[0] & 0x0F) != 8 || (((uint32_t)in[0] << 8) | in[1]) % 31 != 0 || (in[1] & 0x20)) st.phase = kInfError;
+}
+
+// Block header + code tables (RFC 1951 3.2.3 - 3.2.7).  Returns the next phase.
+CCT_HDN inline int inflate_header(InflateState &st, InflateTables &tb) {
+    BitReader &br = st.br;
+    uint8_t lens[320];
+    br.refill();
+    st.last = br.take(1);
+    const int type = (int)br.take(2);
+    if (type == 0) {
+        br.drop(br.nbits & 7);
+        br.refill();
+        const uint32_t len = br.take(16), nlen = br.take(16);
+        if (br.bad || (len ^ 0xFFFFu) != nlen) return kInfError;
+        st.stored_left = (int)len;
+        return kInfStored;
+    }
+    if (type == 3) return kInfError;
+    if (type == 1) {
+        for (int i = 0; i < 144; i++) lens[i] = 8;
+        for (int i = 144; i < 256; i++) lens[i] = 9;
+        for (int i = 256; i < 280; i++) lens[i] = 7;
+        for (int i = 280; i < 288; i++) lens[i] = 8;
+        build_decode_table(lens, 288, kLitBits, tb.lit, tb.lcount, tb.lsym);
+        for (int i = 0; i < 30; i++) lens[i] = 5;
+        build_decode_table(lens, 30, kDstBits, tb.dst, tb.dcount, tb.dsym);
+        return kInfSymbol;
+    }
+    const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+    const int nlen = (int)br.take(5) + 257, ndist = (int)br.take(5) + 1, ncode = (int)br.take(4) + 4;
+    if (nlen > 286 || ndist > 30) return kInfError;
+    uint8_t cl[19];
+    for (int i = 0; i < 19; i++) cl[i] = 0;
+    for (int i = 0; i < ncode; i++) { br.refill(); cl[order[i]] = (uint8_t)br.take(3); }
+    if (!build_decode_table(cl, 19, 7, tb.dst, tb.dcount, tb.dsym)) return kInfError;  // borrows the distance table
+    int idx = 0;
+    while (idx < nlen + ndist) {
+        br.refill();
+        const int sym = decode_symbol(br, tb.dst, 7, tb.dcount, tb.dsym);
+        if (sym < 0 || br.bad) return kInfError;
+        if (sym < 16) lens[idx++] = (uint8_t)sym;
+        else {
+            int rep, val = 0;
+            if (sym == 16) { if (idx == 0) return kInfError; val = lens[idx - 1]; rep = 3 + (int)br.take(2); }
+            else if (sym == 17) rep = 3 + (int)br.take(3);
+            else rep = 11 + (int)br.take(7);
+            if (idx + rep > nlen + ndist) return kInfError;
+            while (rep--) lens[idx++] = (uint8_t)val;
+        }
+    }
+    if (lens[256] == 0) return kInfError;
+    uint8_t dl[32];
+    for (int i = 0; i < ndist; i++) dl[i] = lens[nlen + i];
+    if (!build_decode_table(lens, nlen, kLitBits, tb.lit, tb.lcount, tb.lsym)) return kInfError;
+    if (!build_decode_table(dl, ndist, kDstBits, tb.dst, tb.dcount, tb.dsym)) return kInfError;
+    return kInfSymbol;
+}
+
+CCT_HD void inflate_step(InflateState &st, InflateTables &tb, uint32_t *syms, int sym_cap, int out_cap) {
+    BitReader &br = st.br;
+    if (st.phase == kInfSymbol) {
+        br.refill();
+        int sym = decode_symbol(br, tb.lit, kLitBits, tb.lcount, tb.lsym);
+        if (sym < 0 || br.bad || st.ns >= sym_cap) { st.phase = kInfError; return; }
+        if (sym < 256) { syms[st.ns++] = (uint32_t)sym; st.op++; return; }
+        if (sym == 256) { st.phase = st.op > out_cap ? kInfError : (st.last ? kInfTrailer : kInfHeader); return; }
+        sym -= 257;
+        if (sym >= 29) { st.phase = kInfError; return; }
+        const int len = len_base_inf(sym) + (int)br.take(len_extra_bits_inf(sym));
+        const int ds = decode_symbol(br, tb.dst, kDstBits, tb.dcount, tb.dsym);
+        if (ds < 0 || ds >= 30) { st.phase = kInfError; return; }
+        br.refill();
+        const int dist = dist_base_inf(ds) + (int)br.take(ds < 4 ? 0 : (ds >> 1) - 1);
+        if (br.bad || dist > st.op) { st.phase = kInfError; return; }
+        syms[st.ns++] = (uint32_t)(len - 3) | ((uint32_t)dist << 8);
+        st.op += len;
+    } else if (st.phase == kInfHeader) {
+        st.phase = inflate_header(st, tb);
+    } else if (st.phase == kInfStored) {  // stored bytes become literal symbols, a few per step
+        int k = st.stored_left < 8 ? st.stored_left : 8;
+        if (st.ns + k > sym_cap || st.op + k > out_cap) { st.phase = kInfError; return; }
+        st.stored_left -= k; st.op += k;
+        for (; k > 0; k--) {
+            uint8_t c;
+            if (br.nbits >= 8) c = (uint8_t)br.take(8);
+            else { if (br.pos >= br.len) { st.phase = kInfError; return; } c = br.in[br.pos++]; }
+            syms[st.ns++] = c;
+        }
+        if (st.stored_left == 0) st.phase = st.last ? kInfTrailer : kInfHeader;
+    } else if (st.phase == kInfTrailer) {  // the Adler-32 trailer follows the last block at the next byte boundary
+        br.drop(br.nbits & 7);
+        if (br.pos - (br.nbits >> 3) != br.len) { st.phase = kInfError; return; }
+        const uint8_t *t = br.in + br.len;
+        st.adler_want = ((uint32_t)t[0] << 24) | ((uint32_t)t[1] << 16) | ((uint32_t)t[2] << 8) | t[3];
+        st.phase = kInfDone;
+    }
+}
+
+// Whole-stream wrapper (CPU harness).  Returns the number of symbols or -1.
 CCT_HDN inline int inflate_symbols(const uint8_t *in, int in_len, uint32_t *syms, int sym_cap, int out_cap,
                                    InflateTables &tb, int *out_len, uint32_t *adler_want) {
-    if (in_len < 6) return -1;
-    if ((in[0] & 0x0F) != 8 || (((uint32_t)in[0] << 8) | in[1]) % 31 != 0 || (in[1] & 0x20)) return -1;
-    BitReader br{in, in_len - 4, 2, 0, 0, false};
-    int ns = 0, op = 0;
-    bool last = false;
-    uint8_t lens[320];
-    while (!last) {
-        br.refill();
-        last = br.take(1);
-        const int type = (int)br.take(2);
-        if (type == 0) {  // stored: every byte becomes a literal symbol
-            br.drop(br.nbits & 7);
-            br.refill();
-            const uint32_t len = br.take(16), nlen = br.take(16);
-            if (br.bad || (len ^ 0xFFFFu) != nlen) return -1;
-            if (ns + (int)len > sym_cap || op + (int)len > out_cap) return -1;
-            for (uint32_t i = 0; i < len; i++) {
-                uint8_t c;
-                if (br.nbits >= 8) c = (uint8_t)br.take(8);
-                else { if (br.pos >= br.len) return -1; c = br.in[br.pos++]; }
-                syms[ns++] = c;
-            }
-            op += (int)len;
-            continue;
-        }
-        if (type == 3) return -1;
-        if (type == 1) {
-            for (int i = 0; i < 144; i++) lens[i] = 8;
-            for (int i = 144; i < 256; i++) lens[i] = 9;
-            for (int i = 256; i < 280; i++) lens[i] = 7;
-            for (int i = 280; i < 288; i++) lens[i] = 8;
-            build_decode_table(lens, 288, kLitBits, tb.lit, tb.lcount, tb.lsym);
-            for (int i = 0; i < 30; i++) lens[i] = 5;
-            build_decode_table(lens, 30, kDstBits, tb.dst, tb.dcount, tb.dsym);
-        } else {
-            const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
-            const int nlen = (int)br.take(5) + 257, ndist = (int)br.take(5) + 1, ncode = (int)br.take(4) + 4;
-            if (nlen > 286 || ndist > 30) return -1;
-            uint8_t cl[19];
-            for (int i = 0; i < 19; i++) cl[i] = 0;
-            for (int i = 0; i < ncode; i++) { br.refill(); cl[order[i]] = (uint8_t)br.take(3); }
-            if (!build_decode_table(cl, 19, 7, tb.dst, tb.dcount, tb.dsym)) return -1;  // borrows the distance table
-            int idx = 0;
-            while (idx < nlen + ndist) {
-                br.refill();
-                const int sym = decode_symbol(br, tb.dst, 7, tb.dcount, tb.dsym);
-                if (sym < 0 || br.bad) return -1;
-                if (sym < 16) lens[idx++] = (uint8_t)sym;
-                else {
-                    int rep, val = 0;
-                    if (sym == 16) { if (idx == 0) return -1; val = lens[idx - 1]; rep = 3 + (int)br.take(2); }
-                    else if (sym == 17) rep = 3 + (int)br.take(3);
-                    else rep = 11 + (int)br.take(7);
-                    if (idx + rep > nlen + ndist) return -1;
-                    while (rep--) lens[idx++] = (uint8_t)val;
-                }
-            }
-            if (lens[256] == 0) return -1;
-            uint8_t dl[32];
-            for (int i = 0; i < ndist; i++) dl[i] = lens[nlen + i];
-            if (!build_decode_table(lens, nlen, kLitBits, tb.lit, tb.lcount, tb.lsym)) return -1;
-            if (!build_decode_table(dl, ndist, kDstBits, tb.dst, tb.dcount, tb.dsym)) return -1;
-        }
-        for (;;) {
-            br.refill();
-            int sym = decode_symbol(br, tb.lit, kLitBits, tb.lcount, tb.lsym);
-            if (sym < 0 || br.bad || ns >= sym_cap) return -1;
-            if (sym < 256) { syms[ns++] = (uint32_t)sym; op++; continue; }
-            if (sym == 256) break;
-            sym -= 257;
-            if (sym >= 29) return -1;
-            const int len = len_base_inf(sym) + (int)br.take(len_extra_bits_inf(sym));
-            const int ds = decode_symbol(br, tb.dst, kDstBits, tb.dcount, tb.dsym);
-            if (ds < 0 || ds >= 30) return -1;
-            br.refill();
-            const int dist = dist_base_inf(ds) + (int)br.take(ds < 4 ? 0 : (ds >> 1) - 1);
-            if (br.bad || dist > op) return -1;
-            syms[ns++] = (uint32_t)(len - 3) | ((uint32_t)dist << 8);
-            op += len;
-        }
-        if (op > out_cap) return -1;
-    }
-    br.drop(br.nbits & 7);  // the Adler-32 trailer follows the last block at the next byte boundary
-    if (br.pos - (br.nbits >> 3) != in_len - 4) return -1;
-    const uint8_t *t = in + in_len - 4;
-    *adler_want = ((uint32_t)t[0] << 24) | ((uint32_t)t[1] << 16) | ((uint32_t)t[2] << 8) | t[3];
-    *out_len = op;
-    return ns;
+    InflateState st;
+    inflate_begin(st, in, in_len);
+    while (st.phase < kInfDone) inflate_step(st, tb, syms, sym_cap, out_cap);
+    if (st.phase != kInfDone) return -1;
+    *out_len = st.op; *adler_want = st.adler_want;
+    return st.ns;
 }
 
 // Pass 2 of inflate, sequential form (CPU harness): symbols -> bytes.
