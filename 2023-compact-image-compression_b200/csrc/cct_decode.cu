@@ -9,6 +9,8 @@
 //                                                                      k_dec_scatter (value k -> raster index)
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "cct_kernels.h"
 #include "inflate_core.cuh"
 
@@ -53,14 +55,21 @@ struct StreamSrc {  // where stream i lives: arena + offsets (with a header to s
     __device__ int size(int i) const { return (off ? (int)(off[i + 1] - off[i]) : len[i]) - skip; }
 };
 
-constexpr int kInfStreams = 32;  // streams per CTA (one warp)
-__global__ void __launch_bounds__(kInfStreams) k_inflate_sym(StreamSrc src, const uint8_t *__restrict__ fl, int B,
-                                                             uint32_t *__restrict__ syms, int64_t sym_stride, int out_cap,
-                                                             int32_t *__restrict__ nsym, int32_t *__restrict__ out_len,
-                                                             uint32_t *__restrict__ adler_want, uint32_t *__restrict__ status) {
+// LANES streams per warp (lanes 0..LANES-1 each decode one stream), kInfWarps warps per CTA.  Few lanes per
+// warp keep the per-step divergence (literal vs match vs table build) cheap; many warps per SM hide the
+// latency of the bit-serial dependency chain.
+constexpr int kInfWarps = 4;
+template <int LANES>
+__global__ void __launch_bounds__(32 * kInfWarps) k_inflate_sym(StreamSrc src, const uint8_t *__restrict__ fl, int B,
+                                                                uint32_t *__restrict__ syms, int64_t sym_stride, int out_cap,
+                                                                int32_t *__restrict__ nsym, int32_t *__restrict__ out_len,
+                                                                uint32_t *__restrict__ adler_want, uint32_t *__restrict__ status) {
     extern __shared__ __align__(16) unsigned char tb_raw[];
     InflateTables *tbs = reinterpret_cast<InflateTables *>(tb_raw);
-    const int i = blockIdx.x * kInfStreams + threadIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane >= LANES) return;
+    const int slot = warp * LANES + lane;
+    const int i = (blockIdx.x * kInfWarps + warp) * LANES + lane;
     const bool mine = i < B && !status[i] && !(fl && !(fl[i] & 4u));
     InflateState st;
     st.phase = kInfDone;
@@ -70,16 +79,27 @@ __global__ void __launch_bounds__(kInfStreams) k_inflate_sym(StreamSrc src, cons
         if (len > 0) inflate_begin(st, src.ptr(i), len); else st.phase = kInfError;
     }
     uint32_t *out = syms + (int64_t)(i < B ? i : 0) * sym_stride;
-    // flat state machine: all 32 streams take one step, then reconverge at the vote
+    constexpr unsigned kMask = LANES == 32 ? 0xffffffffu : ((1u << LANES) - 1u);
+    // flat state machine: the streams sharing the warp take one step each, then reconverge at the vote
     for (;;) {
         const bool run = st.phase < kInfDone;
-        if (!__any_sync(0xffffffffu, run)) break;
-        if (run) inflate_step(st, tbs[threadIdx.x], out, (int)sym_stride, out_cap);
+        if (!__any_sync(kMask, run)) break;
+        if (run) inflate_step(st, tbs[slot], out, (int)sym_stride, out_cap);
     }
     if (i >= B) return;
     if (!mine) { nsym[i] = 0; out_len[i] = 0; adler_want[i] = 1; return; }
     if (st.phase != kInfDone) { status[i] |= 16u; nsym[i] = 0; out_len[i] = 0; adler_want[i] = 1; return; }  // CCT_ST_INFLATE
     nsym[i] = st.ns; out_len[i] = st.op; adler_want[i] = st.adler_want;
+}
+
+template <int LANES>
+static void launch_inflate_sym(StreamSrc src, const uint8_t *fl, int B, const InflateWs &iw, int out_cap, int32_t *out_len,
+                               uint32_t *status, cudaStream_t st) {
+    const int smem = kInfWarps * LANES * (int)sizeof(InflateTables);
+    cudaFuncSetAttribute(k_inflate_sym<LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const int per_cta = kInfWarps * LANES;
+    k_inflate_sym<LANES><<<(B + per_cta - 1) / per_cta, 32 * kInfWarps, smem, st>>>(src, fl, B, iw.syms, iw.sym_stride, out_cap,
+                                                                                    iw.nsym, out_len, iw.adler, status);
 }
 
 constexpr int kLzWarps = 4;
@@ -150,12 +170,15 @@ __global__ void __launch_bounds__(256) k_adler_check(const uint8_t *__restrict__
 
 static void launch_inflate_passes(StreamSrc src, const uint8_t *fl, int B, const InflateWs &iw, uint8_t *out,
                                   int64_t out_stride, int32_t *out_len, uint32_t *status, cudaStream_t st) {
-    static bool attr_done = false;
-    const int smem = kInfStreams * (int)sizeof(InflateTables);
-    if (!attr_done) { cudaFuncSetAttribute(k_inflate_sym, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_done = true; }
+    static int lanes = 0;
+    if (!lanes) { const char *e = getenv("CCT_INF_LANES"); lanes = e ? atoi(e) : 1; }  // tuning knob, default 1
     { CCT_KERNEL(k_inflate_sym, st);
-    k_inflate_sym<<<(B + kInfStreams - 1) / kInfStreams, kInfStreams, smem, st>>>(src, fl, B, iw.syms, iw.sym_stride, (int)out_stride,
-                                                                                 iw.nsym, out_len, iw.adler, status);
+    switch (lanes) {
+        case 2: launch_inflate_sym<2>(src, fl, B, iw, (int)out_stride, out_len, status, st); break;
+        case 4: launch_inflate_sym<4>(src, fl, B, iw, (int)out_stride, out_len, status, st); break;
+        case 8: launch_inflate_sym<8>(src, fl, B, iw, (int)out_stride, out_len, status, st); break;
+        default: launch_inflate_sym<1>(src, fl, B, iw, (int)out_stride, out_len, status, st); break;
+    }
     }
     { CCT_KERNEL(k_lz_expand, st);
     k_lz_expand<<<(B + kLzWarps - 1) / kLzWarps, 32 * kLzWarps, 0, st>>>(iw.syms, iw.sym_stride, iw.nsym, out, out_stride, B);

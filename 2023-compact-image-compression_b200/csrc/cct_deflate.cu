@@ -2,7 +2,8 @@
 //
 // Replaces `zlib.compress(data, level = 9)` (reference src/codec/core.py:340).  Stages (see
 // deflate_core.cuh for the decomposition and SURVEY.md Appendix B for the algorithm being matched):
-//   k_chains       hash-chain links for every position (warp per stream, head table in shared memory)
+//   k_chains       hash-chain links for every position (warp per stream, head table in L2-resident global memory)
+//   k_runs         equal-byte run lengths around every position; packs the per-position ChainRec
 //   k_probe        cold-start longest_match over the first kProbeK chain entries, one thread per position
 //   k_walk_spec / k_walk_stitch / k_symscan   deflate_slow's lazy state machine as a windowed speculative walk
 //   k_adler        Adler-32 of the payload (CTA per stream)
@@ -35,6 +36,7 @@ size_t deflate_ws_carve(DeflateWs *ws, void *mem, int B, int64_t max_len) {
     ws->max_blocks = (int)(max_len / kSymEnd + 2);
     ws->dist16 = (uint16_t *)take((size_t)B * ws->stride * sizeof(uint16_t));
     ws->rb16 = (uint16_t *)take((size_t)B * ws->stride * sizeof(uint16_t));
+    ws->heads = (uint16_t *)take((size_t)B * 32768 * sizeof(uint16_t));
     ws->recs = (ChainRec *)take((size_t)B * ws->stride * sizeof(ChainRec));
     ws->mtab = (uint32_t *)take((size_t)B * ws->stride * sizeof(uint32_t));
     ws->mhi = (uint32_t *)take((size_t)B * ws->stride * sizeof(uint32_t));
@@ -51,124 +53,120 @@ size_t deflate_ws_carve(DeflateWs *ws, void *mem, int B, int64_t max_len) {
     return used;
 }
 
-// ------------------------------------------------------------------ k_chains
-// head[h] holds the low 16 bits of the latest position with hash h.  Entries are kept unambiguous by a
-// sweep every 8192 positions that re-parks everything older than 32767 at "49152 behind".
-// The same warp also records, for every position, how many equal bytes precede it (rb16, forward pass) and
-// follow it (rl16, reverse pass): chain_walk uses them to consume whole runs in one step.
+// ------------------------------------------------------------------ k_chains / k_runs
+// k_chains: distance from every position to the previous position with the same 3-byte hash (zlib's prev[]),
+// one warp per stream, 32 positions per step.  The 32768-entry head table (low 16 bits of the latest position
+// per hash) lives in global memory so that every stream of the pass is resident at once and the L2 round trips
+// of one stream hide behind the other warps.  Entries are kept unambiguous by a sweep every 8192 positions that
+// re-parks everything older than 32767 at "49152 behind".
+// k_runs: per position, the count of equal bytes before and after it (forward and reverse sweep with a carry),
+// assembled with the link and the first two bytes into the 8-byte ChainRec the chain walks load.
 constexpr int kHeadEntries = 32768;
-__global__ void __launch_bounds__(32) k_chains(const uint8_t *__restrict__ in, int64_t in_stride,
-                                               const int32_t *__restrict__ in_len, uint16_t *__restrict__ dist16,
-                                               uint16_t *__restrict__ rb16, ChainRec *__restrict__ recs_all, int64_t stride) {
-    extern __shared__ uint16_t head[];
-    const int stream = blockIdx.x, lane = threadIdx.x;
+constexpr int kChainWarps = 4;
+
+__device__ __forceinline__ int head_dist(int s, uint32_t old) {
+    const uint32_t d = (uint32_t)(s - old) & 0xFFFFu;
+    return (d >= 1u && d < 32768u) ? (int)d : 0;
+}
+
+__global__ void __launch_bounds__(32 * kChainWarps) k_chains(const uint8_t *__restrict__ in, int64_t in_stride,
+                                                             const int32_t *__restrict__ in_len, uint16_t *__restrict__ dist16,
+                                                             int64_t stride, uint16_t *__restrict__ heads, int B) {
+    const int stream = blockIdx.x * kChainWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (stream >= B) return;
     const int n = in_len[stream];
     const uint8_t *w = in + (int64_t)stream * in_stride;
     uint16_t *d16 = dist16 + (int64_t)stream * stride;
+    uint16_t *head = heads + (int64_t)stream * kHeadEntries;
+    uint4 *head128 = reinterpret_cast<uint4 *>(head);
+    {
+        const uint4 init = make_uint4(0x40004000u, 0x40004000u, 0x40004000u, 0x40004000u);  // (0 - 49152) & 0xFFFF
+        for (int i = lane; i < kHeadEntries / 8; i += 32) __stcg(head128 + i, init);
+    }
+    __syncwarp();
+    for (int base = 0; base < n; base += 32) {
+        if (base && (base & 8191) == 0) {
+            const uint32_t far = (uint32_t)(base - 49152) & 0xFFFFu;
+            for (int i = lane; i < kHeadEntries / 8; i += 32) {
+                uint4 v = __ldcg(head128 + i);
+                uint32_t *q = reinterpret_cast<uint32_t *>(&v);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    uint32_t lo = q[k] & 0xFFFFu, hi = q[k] >> 16;
+                    if (((uint32_t)(base - lo) & 0xFFFFu) >= 32768u) lo = far;
+                    if (((uint32_t)(base - hi) & 0xFFFFu) >= 32768u) hi = far;
+                    q[k] = lo | (hi << 16);
+                }
+                __stcg(head128 + i, v);
+            }
+            __syncwarp();
+        }
+        const int s = base + lane;
+        const bool valid = s >= 1 && s + 2 < n;  // position 0 doubles as NIL in zlib: never a match source
+        uint32_t h = 0x8000u | (uint32_t)lane;   // unique key for lanes that do not insert
+        if (valid) h = hash3(w + s);
+        // previous position with the same hash: the nearest lower lane holding it, else the head table.
+        // Same-hash lanes inside one group are found without a full match: either every inserting lane has one
+        // hash (a run), or all hashes are distinct -- detected by letting every lane store its position and read
+        // the slot back -- or, rarely, the general case (__match_any_sync is a software loop on this part).
+        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+        int dist = 0;
+        uint32_t old = 0;
+        if (valid) old = __ldcg(head + h);
+        const int first = __ffs((int)vmask) - 1;
+        const uint32_t h0 = __shfl_sync(0xffffffffu, h, first < 0 ? 0 : first);
+        const bool uniform = vmask && __ballot_sync(0xffffffffu, valid && h == h0) == vmask;
+        __syncwarp();
+        if (uniform) {
+            if (valid) {
+                const unsigned lower = vmask & ((1u << lane) - 1u);
+                dist = lower ? lane - (31 - __clz((int)lower)) : head_dist(s, old);
+                if ((vmask >> lane) == 1u) __stcg(head + h, (uint16_t)s);
+            }
+        } else {
+            if (valid) __stcg(head + h, (uint16_t)s);
+            __syncwarp();
+            const bool lost = valid && __ldcg(head + h) != (uint16_t)s;
+            if (__ballot_sync(0xffffffffu, lost) == 0u) {  // all distinct: every lane owns its slot
+                if (valid) dist = head_dist(s, old);
+            } else {
+                const unsigned peers = __match_any_sync(0xffffffffu, h);
+                const unsigned lower = peers & ((1u << lane) - 1u);
+                if (valid) dist = lower ? lane - (31 - __clz((int)lower)) : head_dist(s, old);
+                __syncwarp();
+                if (valid && (peers >> lane) == 1u) __stcg(head + h, (uint16_t)s);  // the latest position wins
+            }
+        }
+        if (s < n) d16[s] = (uint16_t)dist;
+        __syncwarp();
+    }
+}
+
+constexpr int kRunWarps = 4;
+__global__ void __launch_bounds__(32 * kRunWarps) k_runs(const uint8_t *__restrict__ in, int64_t in_stride,
+                                                         const int32_t *__restrict__ in_len, const uint16_t *__restrict__ dist16,
+                                                         uint16_t *__restrict__ rb16, ChainRec *__restrict__ recs_all,
+                                                         int64_t stride, int B) {
+    const int stream = blockIdx.x * kRunWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (stream >= B) return;
+    const int n = in_len[stream];
+    const uint8_t *w = in + (int64_t)stream * in_stride;
+    const uint16_t *d16 = dist16 + (int64_t)stream * stride;
     uint16_t *rb = rb16 + (int64_t)stream * stride;
     ChainRec *recs = recs_all + (int64_t)stream * stride;
-    uint32_t *head32 = reinterpret_cast<uint32_t *>(head);
-    for (int i = lane; i < kHeadEntries / 2; i += 32) head32[i] = 0x40004000u;  // (0 - 49152) & 0xFFFF
-    __syncwarp();
-    // The payload is staged 128 positions at a time: stage[i] = w[cbase - 4 + i], i in [0, 136), fetched two
-    // chunks ahead into registers so the dependent part of the loop only touches shared memory.
-    __shared__ __align__(16) uint8_t stage[136];
-    uint32_t *stage32 = reinterpret_cast<uint32_t *>(stage);
-    const uint32_t *w32 = reinterpret_cast<const uint32_t *>(w);  // stream base is 16-byte aligned
-    const int n_words = (n + 3) >> 2;
-    auto fetch = [&](int cbase, int j) -> uint32_t {  // word j of the chunk starting at cbase
-        const int wi = (cbase >> 2) - 1 + j;
-        return (wi >= 0 && wi < n_words) ? __ldg(w32 + wi) : 0u;
-    };
-    uint32_t p0 = fetch(0, lane), p0x = lane < 2 ? fetch(0, 32 + lane) : 0u;
-    uint32_t p1 = fetch(128, lane), p1x = lane < 2 ? fetch(128, 32 + lane) : 0u;
-    int carry = 0;  // rb of position base-1
-    for (int cbase = 0; cbase < n; cbase += 128) {
-        stage32[lane] = p0;
-        if (lane < 2) stage32[32 + lane] = p0x;
-        p0 = p1; p0x = p1x;
-        p1 = fetch(cbase + 256, lane);
-        p1x = lane < 2 ? fetch(cbase + 256, 32 + lane) : 0u;
-        __syncwarp();
-        if (cbase && (cbase & 8191) == 0) {  // sweep: re-park entries older than 32767 (128 divides 8192)
-            const uint32_t far = (uint32_t)(cbase - 49152) & 0xFFFFu;
-            for (int i = lane; i < kHeadEntries / 2; i += 32) {
-                uint32_t v = head32[i];
-                uint32_t lo = v & 0xFFFFu, hi = v >> 16;
-                if (((uint32_t)(cbase - lo) & 0xFFFFu) >= 32768u) lo = far;
-                if (((uint32_t)(cbase - hi) & 0xFFFFu) >= 32768u) hi = far;
-                head32[i] = lo | (hi << 16);
-            }
-            __syncwarp();
-        }
-        // phase A (independent of the head table, so the four groups of the chunk overlap): hashes, validity,
-        // equal-to-previous flags
-        uint32_t hh[4];
-        unsigned vm[4], em[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int s = cbase + 32 * j + lane;
-            const uint8_t *sb = stage + 4 + 32 * j + lane;  // sb[k] = w[s + k], k in [-1, 2]
-            const bool valid = s >= 1 && s + 2 < n;         // position 0 doubles as NIL in zlib: never a match source
-            hh[j] = valid ? hash3(sb) : (0x8000u | (uint32_t)lane);
-            vm[j] = __ballot_sync(0xffffffffu, valid);
-            em[j] = __ballot_sync(0xffffffffu, s >= 1 && s < n && sb[0] == sb[-1]);
-        }
-        // phase B: table lookups / insertions, group after group
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int s = cbase + 32 * j + lane;
-            if (cbase + 32 * j >= n) break;
-            const uint32_t h = hh[j];
-            const unsigned vmask = vm[j];
-            const bool valid = (vmask >> lane) & 1u;
-            // previous position with the same hash: the nearest lower lane holding it, else the head table.
-            // Same-hash lanes inside one group are found without a full match: either every inserting lane has
-            // one hash (a run), or all hashes are distinct -- detected by letting every lane store its position
-            // and read the slot back -- or, rarely, the general case (__match_any_sync is a software loop here).
-            int dist = 0;
-            uint32_t old = 0;
-            if (valid) old = head[h];
-            const int first = __ffs((int)vmask) - 1;
-            const uint32_t h0 = __shfl_sync(0xffffffffu, h, first < 0 ? 0 : first);
-            const bool uniform = vmask && __ballot_sync(0xffffffffu, valid && h == h0) == vmask;
-            __syncwarp();
-            if (uniform) {
-                if (valid) {
-                    const unsigned lower = vmask & ((1u << lane) - 1u);
-                    if (lower) dist = lane - (31 - __clz((int)lower));
-                    else { uint32_t d = (uint32_t)(s - old) & 0xFFFFu; dist = (d >= 1u && d < 32768u) ? (int)d : 0; }
-                    if ((vmask >> lane) == 1u) head[h] = (uint16_t)s;
-                }
-            } else {
-                if (valid) head[h] = (uint16_t)s;
-                __syncwarp();
-                const bool lost = valid && head[h] != (uint16_t)s;
-                if (__ballot_sync(0xffffffffu, lost) == 0u) {  // all distinct: every lane owns its slot
-                    if (valid) { uint32_t d = (uint32_t)(s - old) & 0xFFFFu; dist = (d >= 1u && d < 32768u) ? (int)d : 0; }
-                } else {
-                    const unsigned peers = __match_any_sync(0xffffffffu, h);
-                    const unsigned lower = peers & ((1u << lane) - 1u);
-                    if (valid) {
-                        if (lower) dist = lane - (31 - __clz((int)lower));
-                        else { uint32_t d = (uint32_t)(s - old) & 0xFFFFu; dist = (d >= 1u && d < 32768u) ? (int)d : 0; }
-                    }
-                    __syncwarp();
-                    if (valid && (peers >> lane) == 1u) head[h] = (uint16_t)s;  // the latest position wins
-                }
-            }
-            // count of equal bytes before s from the flags
-            const unsigned zeros_below = ~em[j] & ((2u << lane) - 1u);  // positions <= lane whose flag is 0
-            int back = zeros_below ? lane - (31 - __clz((int)zeros_below)) : lane + 1 + carry;
-            if (back > 65535) back = 65535;
-            carry = __shfl_sync(0xffffffffu, back, 31);
-            if (s < n) { d16[s] = (uint16_t)dist; rb[s] = (uint16_t)back; }
-            __syncwarp();
-        }
+    int carry = 0;  // count of the position just before the group
+    for (int base = 0; base < n; base += 32) {
+        const int s = base + lane;
+        const bool eq = s >= 1 && s < n && w[s] == w[s - 1];
+        const unsigned em = __ballot_sync(0xffffffffu, eq);
+        const unsigned zeros_below = ~em & ((2u << lane) - 1u);  // positions <= lane whose flag is 0
+        int back = zeros_below ? lane - (31 - __clz((int)zeros_below)) : lane + 1 + carry;
+        if (back > 65535) back = 65535;
+        carry = __shfl_sync(0xffffffffu, back, 31);
+        if (s < n) rb[s] = (uint16_t)back;
     }
-    // reverse pass: count of equal bytes after s; assembles the per-position record the chain walks load
     __syncwarp();
-    carry = 0;  // rl of position base+32
+    carry = 0;  // count of the position just after the group
     for (int base = ((n - 1) / 32) * 32; base >= 0; base -= 32) {
         const int s = base + lane;
         const uint8_t c0 = s < n ? w[s] : 0, c1 = s + 1 < n ? w[s + 1] : 0;
@@ -476,14 +474,15 @@ void launch_deflate(const uint8_t *in, int64_t in_stride, const int32_t *in_len,
                     int64_t out_stride, int32_t *out_len, const DeflateWs &ws, cudaStream_t st) {
     if (B == 0) return;
     static bool attr_done = false;
-    const int chain_smem = kHeadEntries * (int)sizeof(uint16_t);
     if (!attr_done) {
-        cudaFuncSetAttribute(k_chains, cudaFuncAttributeMaxDynamicSharedMemorySize, chain_smem);
         cudaFuncSetAttribute(k_block_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlockBuildSmem));
         attr_done = true;
     }
     { CCT_KERNEL(k_chains, st);
-    k_chains<<<B, 32, chain_smem, st>>>(in, in_stride, in_len, ws.dist16, ws.rb16, ws.recs, ws.stride);
+    k_chains<<<(B + kChainWarps - 1) / kChainWarps, 32 * kChainWarps, 0, st>>>(in, in_stride, in_len, ws.dist16, ws.stride, ws.heads, B);
+    }
+    { CCT_KERNEL(k_runs, st);
+    k_runs<<<(B + kRunWarps - 1) / kRunWarps, 32 * kRunWarps, 0, st>>>(in, in_stride, in_len, ws.dist16, ws.rb16, ws.recs, ws.stride, B);
     }
     dim3 gp((unsigned)((max_len + 255) / 256), (unsigned)B);
     { CCT_KERNEL(k_probe, st);
