@@ -79,6 +79,18 @@ __global__ void __launch_bounds__(32 * kInfWarps) k_inflate_sym(StreamSrc src, c
         if (len > 0) inflate_begin(st, src.ptr(i), len); else st.phase = kInfError;
     }
     uint32_t *out = syms + (int64_t)(i < B ? i : 0) * sym_stride;
+    if (LANES == 1) {  // the warp holds a single stream: no reconvergence needed, run the tight loop
+        if (i >= B) return;
+        nsym[i] = 0; out_len[i] = 0; adler_want[i] = 1;
+        if (!mine) return;
+        int olen = 0;
+        uint32_t want = 1;
+        const int len = src.size(i);
+        const int ns = len > 0 ? inflate_symbols(src.ptr(i), len, out, (int)sym_stride, out_cap, tbs[slot], &olen, &want) : -1;
+        if (ns < 0) { status[i] |= 16u; return; }  // CCT_ST_INFLATE
+        nsym[i] = ns; out_len[i] = olen; adler_want[i] = want;
+        return;
+    }
     constexpr unsigned kMask = LANES == 32 ? 0xffffffffu : ((1u << LANES) - 1u);
     // flat state machine: the streams sharing the warp take one step each, then reconverge at the vote
     for (;;) {

@@ -2,7 +2,7 @@
 //
 // Replaces `zlib.compress(data, level = 9)` (reference src/codec/core.py:340).  Stages (see
 // deflate_core.cuh for the decomposition and SURVEY.md Appendix B for the algorithm being matched):
-//   k_chains       hash-chain links for every position (warp per stream, head table in L2-resident global memory)
+//   k_chains       hash-chain links for every position (warp per stream, head table in shared memory)
 //   k_runs         equal-byte run lengths around every position; packs the per-position ChainRec
 //   k_probe        cold-start longest_match over the first kProbeK chain entries, one thread per position
 //   k_walk_spec / k_walk_stitch / k_symscan   deflate_slow's lazy state machine as a windowed speculative walk
@@ -36,7 +36,6 @@ size_t deflate_ws_carve(DeflateWs *ws, void *mem, int B, int64_t max_len) {
     ws->max_blocks = (int)(max_len / kSymEnd + 2);
     ws->dist16 = (uint16_t *)take((size_t)B * ws->stride * sizeof(uint16_t));
     ws->rb16 = (uint16_t *)take((size_t)B * ws->stride * sizeof(uint16_t));
-    ws->heads = (uint16_t *)take((size_t)B * 32768 * sizeof(uint16_t));
     ws->recs = (ChainRec *)take((size_t)B * ws->stride * sizeof(ChainRec));
     ws->mtab = (uint32_t *)take((size_t)B * ws->stride * sizeof(uint32_t));
     ws->mhi = (uint32_t *)take((size_t)B * ws->stride * sizeof(uint32_t));
@@ -56,89 +55,111 @@ size_t deflate_ws_carve(DeflateWs *ws, void *mem, int B, int64_t max_len) {
 // ------------------------------------------------------------------ k_chains / k_runs
 // k_chains: distance from every position to the previous position with the same 3-byte hash (zlib's prev[]),
 // one warp per stream, 32 positions per step.  The 32768-entry head table (low 16 bits of the latest position
-// per hash) lives in global memory so that every stream of the pass is resident at once and the L2 round trips
-// of one stream hide behind the other warps.  Entries are kept unambiguous by a sweep every 8192 positions that
-// re-parks everything older than 32767 at "49152 behind".
+// per hash) lives in shared memory; entries are kept unambiguous by a sweep every 8192 positions that re-parks
+// everything older than 32767 at "49152 behind".  (A global-memory table with every stream resident was
+// measured 3.4x slower: 268 MB of randomly accessed tables do not fit the 126 MB L2.)
 // k_runs: per position, the count of equal bytes before and after it (forward and reverse sweep with a carry),
 // assembled with the link and the first two bytes into the 8-byte ChainRec the chain walks load.
 constexpr int kHeadEntries = 32768;
-constexpr int kChainWarps = 4;
-
-__device__ __forceinline__ int head_dist(int s, uint32_t old) {
-    const uint32_t d = (uint32_t)(s - old) & 0xFFFFu;
-    return (d >= 1u && d < 32768u) ? (int)d : 0;
-}
-
-__global__ void __launch_bounds__(32 * kChainWarps) k_chains(const uint8_t *__restrict__ in, int64_t in_stride,
-                                                             const int32_t *__restrict__ in_len, uint16_t *__restrict__ dist16,
-                                                             int64_t stride, uint16_t *__restrict__ heads, int B) {
-    const int stream = blockIdx.x * kChainWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (stream >= B) return;
+__global__ void __launch_bounds__(32) k_chains(const uint8_t *__restrict__ in, int64_t in_stride,
+                                               const int32_t *__restrict__ in_len, uint16_t *__restrict__ dist16,
+                                               int64_t stride) {
+    extern __shared__ uint16_t head[];
+    const int stream = blockIdx.x, lane = threadIdx.x;
     const int n = in_len[stream];
     const uint8_t *w = in + (int64_t)stream * in_stride;
     uint16_t *d16 = dist16 + (int64_t)stream * stride;
-    uint16_t *head = heads + (int64_t)stream * kHeadEntries;
-    uint4 *head128 = reinterpret_cast<uint4 *>(head);
-    {
-        const uint4 init = make_uint4(0x40004000u, 0x40004000u, 0x40004000u, 0x40004000u);  // (0 - 49152) & 0xFFFF
-        for (int i = lane; i < kHeadEntries / 8; i += 32) __stcg(head128 + i, init);
-    }
+    uint32_t *head32 = reinterpret_cast<uint32_t *>(head);
+    for (int i = lane; i < kHeadEntries / 2; i += 32) head32[i] = 0x40004000u;  // (0 - 49152) & 0xFFFF
     __syncwarp();
-    for (int base = 0; base < n; base += 32) {
-        if (base && (base & 8191) == 0) {
-            const uint32_t far = (uint32_t)(base - 49152) & 0xFFFFu;
-            for (int i = lane; i < kHeadEntries / 8; i += 32) {
-                uint4 v = __ldcg(head128 + i);
-                uint32_t *q = reinterpret_cast<uint32_t *>(&v);
+    // The payload is staged 128 positions at a time: stage[i] = w[cbase - 4 + i], i in [0, 136), fetched two
+    // chunks ahead into registers so the dependent part of the loop only touches shared memory.
+    __shared__ __align__(16) uint8_t stage[136];
+    uint32_t *stage32 = reinterpret_cast<uint32_t *>(stage);
+    const uint32_t *w32 = reinterpret_cast<const uint32_t *>(w);  // stream base is 16-byte aligned
+    const int n_words = (n + 3) >> 2;
+    auto fetch = [&](int cbase, int j) -> uint32_t {  // word j of the chunk starting at cbase
+        const int wi = (cbase >> 2) - 1 + j;
+        return (wi >= 0 && wi < n_words) ? __ldg(w32 + wi) : 0u;
+    };
+    uint32_t p0 = fetch(0, lane), p0x = lane < 2 ? fetch(0, 32 + lane) : 0u;
+    uint32_t p1 = fetch(128, lane), p1x = lane < 2 ? fetch(128, 32 + lane) : 0u;
+    for (int cbase = 0; cbase < n; cbase += 128) {
+        stage32[lane] = p0;
+        if (lane < 2) stage32[32 + lane] = p0x;
+        p0 = p1; p0x = p1x;
+        p1 = fetch(cbase + 256, lane);
+        p1x = lane < 2 ? fetch(cbase + 256, 32 + lane) : 0u;
+        __syncwarp();
+        if (cbase && (cbase & 8191) == 0) {  // sweep: re-park entries older than 32767 (128 divides 8192)
+            const uint32_t far = (uint32_t)(cbase - 49152) & 0xFFFFu;
+            for (int i = lane; i < kHeadEntries / 2; i += 32) {
+                uint32_t v = head32[i];
+                uint32_t lo = v & 0xFFFFu, hi = v >> 16;
+                if (((uint32_t)(cbase - lo) & 0xFFFFu) >= 32768u) lo = far;
+                if (((uint32_t)(cbase - hi) & 0xFFFFu) >= 32768u) hi = far;
+                head32[i] = lo | (hi << 16);
+            }
+            __syncwarp();
+        }
+        // phase A (independent of the head table, so the four groups of the chunk overlap): hashes, validity,
+        // equal-to-previous flags
+        uint32_t hh[4];
+        unsigned vm[4];
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    uint32_t lo = q[k] & 0xFFFFu, hi = q[k] >> 16;
-                    if (((uint32_t)(base - lo) & 0xFFFFu) >= 32768u) lo = far;
-                    if (((uint32_t)(base - hi) & 0xFFFFu) >= 32768u) hi = far;
-                    q[k] = lo | (hi << 16);
+        for (int j = 0; j < 4; j++) {
+            const int s = cbase + 32 * j + lane;
+            const uint8_t *sb = stage + 4 + 32 * j + lane;  // sb[k] = w[s + k], k in [-1, 2]
+            const bool valid = s >= 1 && s + 2 < n;         // position 0 doubles as NIL in zlib: never a match source
+            hh[j] = valid ? hash3(sb) : (0x8000u | (uint32_t)lane);
+            vm[j] = __ballot_sync(0xffffffffu, valid);
+        }
+        // phase B: table lookups / insertions, group after group
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int s = cbase + 32 * j + lane;
+            if (cbase + 32 * j >= n) break;
+            const uint32_t h = hh[j];
+            const unsigned vmask = vm[j];
+            const bool valid = (vmask >> lane) & 1u;
+            // previous position with the same hash: the nearest lower lane holding it, else the head table.
+            // Same-hash lanes inside one group are found without a full match: either every inserting lane has
+            // one hash (a run), or all hashes are distinct -- detected by letting every lane store its position
+            // and read the slot back -- or, rarely, the general case (__match_any_sync is a software loop here).
+            int dist = 0;
+            uint32_t old = 0;
+            if (valid) old = head[h];
+            const int first = __ffs((int)vmask) - 1;
+            const uint32_t h0 = __shfl_sync(0xffffffffu, h, first < 0 ? 0 : first);
+            const bool uniform = vmask && __ballot_sync(0xffffffffu, valid && h == h0) == vmask;
+            __syncwarp();
+            if (uniform) {
+                if (valid) {
+                    const unsigned lower = vmask & ((1u << lane) - 1u);
+                    if (lower) dist = lane - (31 - __clz((int)lower));
+                    else { uint32_t d = (uint32_t)(s - old) & 0xFFFFu; dist = (d >= 1u && d < 32768u) ? (int)d : 0; }
+                    if ((vmask >> lane) == 1u) head[h] = (uint16_t)s;
                 }
-                __stcg(head128 + i, v);
-            }
-            __syncwarp();
-        }
-        const int s = base + lane;
-        const bool valid = s >= 1 && s + 2 < n;  // position 0 doubles as NIL in zlib: never a match source
-        uint32_t h = 0x8000u | (uint32_t)lane;   // unique key for lanes that do not insert
-        if (valid) h = hash3(w + s);
-        // previous position with the same hash: the nearest lower lane holding it, else the head table.
-        // Same-hash lanes inside one group are found without a full match: either every inserting lane has one
-        // hash (a run), or all hashes are distinct -- detected by letting every lane store its position and read
-        // the slot back -- or, rarely, the general case (__match_any_sync is a software loop on this part).
-        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-        int dist = 0;
-        uint32_t old = 0;
-        if (valid) old = __ldcg(head + h);
-        const int first = __ffs((int)vmask) - 1;
-        const uint32_t h0 = __shfl_sync(0xffffffffu, h, first < 0 ? 0 : first);
-        const bool uniform = vmask && __ballot_sync(0xffffffffu, valid && h == h0) == vmask;
-        __syncwarp();
-        if (uniform) {
-            if (valid) {
-                const unsigned lower = vmask & ((1u << lane) - 1u);
-                dist = lower ? lane - (31 - __clz((int)lower)) : head_dist(s, old);
-                if ((vmask >> lane) == 1u) __stcg(head + h, (uint16_t)s);
-            }
-        } else {
-            if (valid) __stcg(head + h, (uint16_t)s);
-            __syncwarp();
-            const bool lost = valid && __ldcg(head + h) != (uint16_t)s;
-            if (__ballot_sync(0xffffffffu, lost) == 0u) {  // all distinct: every lane owns its slot
-                if (valid) dist = head_dist(s, old);
             } else {
-                const unsigned peers = __match_any_sync(0xffffffffu, h);
-                const unsigned lower = peers & ((1u << lane) - 1u);
-                if (valid) dist = lower ? lane - (31 - __clz((int)lower)) : head_dist(s, old);
+                if (valid) head[h] = (uint16_t)s;
                 __syncwarp();
-                if (valid && (peers >> lane) == 1u) __stcg(head + h, (uint16_t)s);  // the latest position wins
+                const bool lost = valid && head[h] != (uint16_t)s;
+                if (__ballot_sync(0xffffffffu, lost) == 0u) {  // all distinct: every lane owns its slot
+                    if (valid) { uint32_t d = (uint32_t)(s - old) & 0xFFFFu; dist = (d >= 1u && d < 32768u) ? (int)d : 0; }
+                } else {
+                    const unsigned peers = __match_any_sync(0xffffffffu, h);
+                    const unsigned lower = peers & ((1u << lane) - 1u);
+                    if (valid) {
+                        if (lower) dist = lane - (31 - __clz((int)lower));
+                        else { uint32_t d = (uint32_t)(s - old) & 0xFFFFu; dist = (d >= 1u && d < 32768u) ? (int)d : 0; }
+                    }
+                    __syncwarp();
+                    if (valid && (peers >> lane) == 1u) head[h] = (uint16_t)s;  // the latest position wins
+                }
             }
+            if (s < n) d16[s] = (uint16_t)dist;
+            __syncwarp();
         }
-        if (s < n) d16[s] = (uint16_t)dist;
-        __syncwarp();
     }
 }
 
@@ -474,12 +495,14 @@ void launch_deflate(const uint8_t *in, int64_t in_stride, const int32_t *in_len,
                     int64_t out_stride, int32_t *out_len, const DeflateWs &ws, cudaStream_t st) {
     if (B == 0) return;
     static bool attr_done = false;
+    const int chain_smem = kHeadEntries * (int)sizeof(uint16_t);
     if (!attr_done) {
+        cudaFuncSetAttribute(k_chains, cudaFuncAttributeMaxDynamicSharedMemorySize, chain_smem);
         cudaFuncSetAttribute(k_block_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlockBuildSmem));
         attr_done = true;
     }
     { CCT_KERNEL(k_chains, st);
-    k_chains<<<(B + kChainWarps - 1) / kChainWarps, 32 * kChainWarps, 0, st>>>(in, in_stride, in_len, ws.dist16, ws.stride, ws.heads, B);
+    k_chains<<<B, 32, chain_smem, st>>>(in, in_stride, in_len, ws.dist16, ws.stride);
     }
     { CCT_KERNEL(k_runs, st);
     k_runs<<<(B + kRunWarps - 1) / kRunWarps, 32 * kRunWarps, 0, st>>>(in, in_stride, in_len, ws.dist16, ws.rb16, ws.recs, ws.stride, B);

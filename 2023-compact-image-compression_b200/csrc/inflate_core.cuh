@@ -30,9 +30,16 @@ CCT_HD int len_base_inf(int idx) {
 CCT_HD int dist_base_inf(int ds) { return ds < 4 ? 1 + ds : 1 + ((2 + (ds & 1)) << ((ds >> 1) - 1)); }
 
 struct BitReader {
+    // LSB-first bit buffer over in[0..len).  After align_input() the read position is 4-byte aligned, so a
+    // refill is one 32-bit load; only the last few bytes of the stream go through the byte path.  Reading past
+    // the end yields zero bits and drives nbits negative, which the callers check at block boundaries.
     const uint8_t *in; int len, pos; uint64_t buf; int nbits; bool bad;
+    CCT_HD void align_input() {
+        while (pos < len && ((uintptr_t)(in + pos) & 3u)) { buf |= (uint64_t)in[pos++] << nbits; nbits += 8; }
+    }
     CCT_HD void refill() {
-        if (nbits <= 32 && pos + 4 <= len && ((uintptr_t)(in + pos) & 3u) == 0) {  // aligned 32-bit fast path
+        if (nbits > 32) return;
+        if (pos + 4 <= len) {
             buf |= (uint64_t)(*reinterpret_cast<const uint32_t *>(in + pos)) << nbits;
             pos += 4; nbits += 32;
             return;
@@ -40,7 +47,7 @@ struct BitReader {
         while (nbits <= 56 && pos < len) { buf |= (uint64_t)in[pos++] << nbits; nbits += 8; }
     }
     CCT_HD uint32_t peek(int n) const { return (uint32_t)(buf & ((1ull << n) - 1)); }
-    CCT_HD void drop(int n) { if (n > nbits) { bad = true; n = nbits; } buf >>= n; nbits -= n; }
+    CCT_HD void drop(int n) { buf >>= n; nbits -= n; if (nbits < 0) bad = true; }
     CCT_HD uint32_t take(int n) { uint32_t v = peek(n); drop(n); return v; }
 };
 
@@ -102,6 +109,7 @@ struct InflateState {
 
 CCT_HD void inflate_begin(InflateState &st, const uint8_t *in, int in_len) {
     st.br = BitReader{in, in_len - 4, 2, 0, 0, false};
+    st.br.align_input();
     st.ns = 0; st.op = 0; st.stored_left = 0; st.last = false; st.adler_want = 1;
     st.phase = kInfHeader;
     if (in_len < 6 || (in[0] & 0x0F) != 8 || (((uint32_t)in[0] << 8) | in[1]) % 31 != 0 || (in[1] & 0x20)) st.phase = kInfError;
@@ -168,9 +176,9 @@ CCT_HD void inflate_step(InflateState &st, InflateTables &tb, uint32_t *syms, in
     if (st.phase == kInfSymbol) {
         br.refill();
         int sym = decode_symbol(br, tb.lit, kLitBits, tb.lcount, tb.lsym);
-        if (sym < 0 || br.bad || st.ns >= sym_cap) { st.phase = kInfError; return; }
+        if (sym < 0 || st.ns >= sym_cap) { st.phase = kInfError; return; }
         if (sym < 256) { syms[st.ns++] = (uint32_t)sym; st.op++; return; }
-        if (sym == 256) { st.phase = st.op > out_cap ? kInfError : (st.last ? kInfTrailer : kInfHeader); return; }
+        if (sym == 256) { st.phase = (br.bad || st.op > out_cap) ? kInfError : (st.last ? kInfTrailer : kInfHeader); return; }
         sym -= 257;
         if (sym >= 29) { st.phase = kInfError; return; }
         const int len = len_base_inf(sym) + (int)br.take(len_extra_bits_inf(sym));
@@ -178,7 +186,7 @@ CCT_HD void inflate_step(InflateState &st, InflateTables &tb, uint32_t *syms, in
         if (ds < 0 || ds >= 30) { st.phase = kInfError; return; }
         br.refill();
         const int dist = dist_base_inf(ds) + (int)br.take(ds < 4 ? 0 : (ds >> 1) - 1);
-        if (br.bad || dist > st.op) { st.phase = kInfError; return; }
+        if (dist > st.op) { st.phase = kInfError; return; }
         syms[st.ns++] = (uint32_t)(len - 3) | ((uint32_t)dist << 8);
         st.op += len;
     } else if (st.phase == kInfHeader) {
@@ -195,6 +203,7 @@ CCT_HD void inflate_step(InflateState &st, InflateTables &tb, uint32_t *syms, in
         }
         if (st.stored_left == 0) st.phase = st.last ? kInfTrailer : kInfHeader;
     } else if (st.phase == kInfTrailer) {  // the Adler-32 trailer follows the last block at the next byte boundary
+        if (br.bad) { st.phase = kInfError; return; }
         br.drop(br.nbits & 7);
         if (br.pos - (br.nbits >> 3) != br.len) { st.phase = kInfError; return; }
         const uint8_t *t = br.in + br.len;
@@ -203,13 +212,47 @@ CCT_HD void inflate_step(InflateState &st, InflateTables &tb, uint32_t *syms, in
     }
 }
 
-// Whole-stream wrapper (CPU harness).  Returns the number of symbols or -1.
+// Whole stream in one call: the same machine with the symbol phase as a tight inner loop (literal fast path,
+// one bounds check per symbol).  This is what a thread runs when it does not share its warp with other streams.
+// Returns the number of symbols or -1.
 CCT_HDN inline int inflate_symbols(const uint8_t *in, int in_len, uint32_t *syms, int sym_cap, int out_cap,
                                    InflateTables &tb, int *out_len, uint32_t *adler_want) {
     InflateState st;
     inflate_begin(st, in, in_len);
-    while (st.phase < kInfDone) inflate_step(st, tb, syms, sym_cap, out_cap);
-    if (st.phase != kInfDone) return -1;
+    BitReader &br = st.br;
+    while (st.phase < kInfDone) {
+        if (st.phase != kInfSymbol) { inflate_step(st, tb, syms, sym_cap, out_cap); continue; }
+        int ns = st.ns, op = st.op;
+        int next = kInfError;
+        while (ns < sym_cap) {
+            br.refill();
+            const uint32_t e = tb.lit[br.buf & ((1u << kLitBits) - 1)];
+            int sym;
+            if (e) {
+                const int l = (int)(e >> 12);
+                br.buf >>= l; br.nbits -= l;
+                sym = (int)(e & 0xFFF);
+                if (sym < 256) { syms[ns++] = (uint32_t)sym; op++; continue; }  // literal fast path
+            } else {
+                sym = decode_symbol(br, tb.lit, kLitBits, tb.lcount, tb.lsym);
+                if (sym < 0) break;
+                if (sym < 256) { syms[ns++] = (uint32_t)sym; op++; continue; }
+            }
+            if (sym == 256) { next = (br.nbits < 0 || op > out_cap) ? kInfError : (st.last ? kInfTrailer : kInfHeader); break; }
+            sym -= 257;
+            if (sym >= 29) break;
+            const int len = len_base_inf(sym) + (int)br.take(len_extra_bits_inf(sym));
+            const int ds = decode_symbol(br, tb.dst, kDstBits, tb.dcount, tb.dsym);
+            if (ds < 0 || ds >= 30) break;
+            br.refill();
+            const int dist = dist_base_inf(ds) + (int)br.take(ds < 4 ? 0 : (ds >> 1) - 1);
+            if (dist > op) break;
+            syms[ns++] = (uint32_t)(len - 3) | ((uint32_t)dist << 8);
+            op += len;
+        }
+        st.ns = ns; st.op = op; st.phase = next;
+    }
+    if (st.phase != kInfDone || br.bad) return -1;
     *out_len = st.op; *adler_want = st.adler_want;
     return st.ns;
 }
