@@ -116,66 +116,81 @@ constexpr int kWalkSteps = 2;   // step cap of the probe reached
 // m+i if m+i < R, "R + whatever follows" if m+i == R, exactly R if m+i > R (R < cap), cap if R == cap.
 // Since only the first-visited candidate attaining the maximum matters, the group is consumed in
 // one step; the chain budget and the distance limit are charged as if every member had been visited.
-CCT_HD int chain_walk(const LzView &v, int s, int cap, int &best, int &bdist, int chain, int max_steps) {
-    const uint8_t *b = v.w + s;
+// The walk is a resumable state machine (chain_begin / chain_step) so the probe kernel can keep every lane
+// of a warp on one step per iteration and hand a finished lane its next position; chain_walk runs it to the end.
+constexpr int kWalkContinue = -1;
+struct ChainState {
+    int s, cap, best, bdist, chain, steps_left, cur, R;
+    uint8_t b0, b1;
+};
+
+CCT_HD void chain_begin(const LzView &v, int s, int cap, int best, int chain, int max_steps, ChainState &c) {
     const ChainRec rs = v.recs[s];
-    const uint8_t b0 = rs.b0, b1 = rs.b1;
-    int R = 0;  // leading run of the target, if it is at least one hash triple long
-    if (rs.rl >= 2) { R = (int)rs.rl + 1; if (R > cap) R = cap; }
-    int cur = s - rs.dist;
-    for (int step = 1;; step++) {
-        CCT_COUNT(0);
-        const ChainRec rc = v.recs[cur];  // one load: link, run lengths and the first two bytes of the candidate
-        const uint8_t *a = v.w + cur;
-        const uint8_t a_best = a[best], a_best1 = a[best - 1];
-        if (rc.rl >= 2) {
-            // cur starts a triple (c,c,c): the chain entries below it inside the run form one group
-            const int m = (int)rc.rl + 1;  // leading c's of the top candidate
-            int t = rc.rb;                 // further candidates of this run below cur
-            if (cur - t < 1) t = cur - 1;  // position 0 is never in a chain
-            const int count_dist = kMaxDist - (s - cur);
-            int nvis = t + 1;
-            if (chain < nvis) nvis = chain;
-            if (count_dist < nvis) nvis = count_dist;
-            if (R && rc.b0 == b0) {
-                const int i_key = m >= R ? 0 : R - m;  // first member with at least R leading c's
-                if (R < cap && m > R) {
-                    if (R > best) { best = R; bdist = s - cur; }
-                } else if (i_key < nvis) {
-                    const int c_al = cur - i_key;
-                    const int L = R < cap ? match_extend(v.w + c_al, b, R, cap) : cap;
-                    if (L > best) { best = L; bdist = s - c_al; if (L >= cap) return kWalkDone; }
-                } else {
-                    const int L = m + nvis - 1;  // only members with fewer than R leading c's were reached
-                    if (L > best) { best = L; bdist = s - (cur - (nvis - 1)); }
-                }
-            }  // else: the target does not start with (c,c,c) (a hash collision): no member matches 3 bytes
-            if (nvis < t + 1) return nvis == count_dist ? kWalkDone : kWalkBudget;
-            chain -= t;
-            cur -= t;
-            if (t) {  // moved to the bottom of the run: its link is the group's way out
-                const int dl = v.recs[cur].dist;
-                if (dl == 0) return kWalkDone;
-                cur -= dl;
-                if (s - cur >= kMaxDist) return kWalkDone;
-                if (--chain == 0) return kWalkBudget;
-                if (step == max_steps) return kWalkSteps;
-                continue;
+    c.s = s; c.cap = cap; c.best = best; c.bdist = 0; c.chain = chain; c.steps_left = max_steps;
+    c.b0 = rs.b0; c.b1 = rs.b1;
+    c.R = 0;  // leading run of the target, if it is at least one hash triple long
+    if (rs.rl >= 2) { c.R = (int)rs.rl + 1; if (c.R > cap) c.R = cap; }
+    c.cur = s - rs.dist;
+}
+
+// One loop step: a single candidate or a whole run group.  Returns kWalkContinue or how the walk ended.
+CCT_HD int chain_step(const LzView &v, ChainState &c) {
+    CCT_COUNT(0);
+    const int s = c.s, cap = c.cap, cur = c.cur;
+    const uint8_t *b = v.w + s;
+    const ChainRec rc = v.recs[cur];  // one load: link, run lengths and the first two bytes of the candidate
+    const uint8_t *a = v.w + cur;
+    const uint8_t a_best = a[c.best], a_best1 = a[c.best - 1];
+    int link_from = cur;
+    int dl = rc.dist;
+    if (rc.rl >= 2) {
+        // cur starts a triple (c,c,c): the chain entries below it inside the run form one group
+        const int m = (int)rc.rl + 1;  // leading c's of the top candidate
+        int t = rc.rb;                 // further candidates of this run below cur
+        if (cur - t < 1) t = cur - 1;  // position 0 is never in a chain
+        const int count_dist = kMaxDist - (s - cur);
+        int nvis = t + 1;
+        if (c.chain < nvis) nvis = c.chain;
+        if (count_dist < nvis) nvis = count_dist;
+        if (c.R && rc.b0 == c.b0) {
+            const int R = c.R;
+            const int i_key = m >= R ? 0 : R - m;  // first member with at least R leading c's
+            if (R < cap && m > R) {
+                if (R > c.best) { c.best = R; c.bdist = s - cur; }
+            } else if (i_key < nvis) {
+                const int c_al = cur - i_key;
+                const int L = R < cap ? match_extend(v.w + c_al, b, R, cap) : cap;
+                if (L > c.best) { c.best = L; c.bdist = s - c_al; if (L >= cap) return kWalkDone; }
+            } else {
+                const int L = m + nvis - 1;  // only members with fewer than R leading c's were reached
+                if (L > c.best) { c.best = L; c.bdist = s - (cur - (nvis - 1)); }
             }
-        } else if (a_best == b[best] && a_best1 == b[best - 1] && rc.b0 == b0 && rc.b1 == b1) {
-            const int len = match_extend(a, b, 2, cap);
-            if (len > best) {
-                best = len; bdist = s - cur;
-                if (len >= cap) return kWalkDone;
-            }
+        }  // else: the target does not start with (c,c,c) (a hash collision): no member matches 3 bytes
+        if (nvis < t + 1) return nvis == count_dist ? kWalkDone : kWalkBudget;
+        c.chain -= t;
+        if (t) { link_from = cur - t; dl = v.recs[link_from].dist; }  // the bottom of the run links onwards
+    } else if (a_best == b[c.best] && a_best1 == b[c.best - 1] && rc.b0 == c.b0 && rc.b1 == c.b1) {
+        const int len = match_extend(a, b, 2, cap);
+        if (len > c.best) {
+            c.best = len; c.bdist = s - cur;
+            if (len >= cap) return kWalkDone;
         }
-        const int dl = rc.dist;
-        if (dl == 0) return kWalkDone;
-        cur -= dl;
-        if (s - cur >= kMaxDist) return kWalkDone;  // cur <= limit
-        if (--chain == 0) return kWalkBudget;
-        if (step == max_steps) return kWalkSteps;
     }
+    if (dl == 0) return kWalkDone;
+    c.cur = link_from - dl;
+    if (s - c.cur >= kMaxDist) return kWalkDone;  // cur <= limit
+    if (--c.chain == 0) return kWalkBudget;
+    if (--c.steps_left == 0) return kWalkSteps;
+    return kWalkContinue;
+}
+
+CCT_HD int chain_walk(const LzView &v, int s, int cap, int &best, int &bdist, int chain, int max_steps) {
+    ChainState c;
+    chain_begin(v, s, cap, best, chain, max_steps, c);
+    int r;
+    while ((r = chain_step(v, c)) == kWalkContinue) {}
+    best = c.best; bdist = c.bdist;
+    return r;
 }
 
 // Cold-start probe (best_len = 2) over at most K loop steps.  longest_match's answer for any prev_length is

@@ -40,6 +40,9 @@ struct BitReader {
     CCT_HD void refill() {
         if (nbits > 32) return;
         if (pos + 4 <= len) {
+#if defined(CCT_STATS) && !defined(__CUDA_ARCH__)
+            if ((uintptr_t)(in + pos) & 3u) abort();  // CPU harness: the GPU would fault on this load
+#endif
             buf |= (uint64_t)(*reinterpret_cast<const uint32_t *>(in + pos)) << nbits;
             pos += 4; nbits += 32;
             return;
@@ -201,7 +204,7 @@ CCT_HD void inflate_step(InflateState &st, InflateTables &tb, uint32_t *syms, in
             else { if (br.pos >= br.len) { st.phase = kInfError; return; } c = br.in[br.pos++]; }
             syms[st.ns++] = c;
         }
-        if (st.stored_left == 0) st.phase = st.last ? kInfTrailer : kInfHeader;
+        if (st.stored_left == 0) { br.align_input(); st.phase = st.last ? kInfTrailer : kInfHeader; }  // bytes were read one by one
     } else if (st.phase == kInfTrailer) {  // the Adler-32 trailer follows the last block at the next byte boundary
         if (br.bad) { st.phase = kInfError; return; }
         br.drop(br.nbits & 7);
