@@ -202,60 +202,23 @@ __global__ void __launch_bounds__(32 * kRunWarps) k_runs(const uint8_t *__restri
 }
 
 // ------------------------------------------------------------------ k_probe
-// Cold-start longest_match for every position (match_probe in deflate_core.cuh), as a per-lane state machine
-// fed from a CTA-wide work counter: chains differ wildly in length (most positions need 0-3 steps, some the
-// full kProbeK), so instead of one position per thread each lane takes ONE chain step per iteration and
-// fetches its next position as soon as its walk ends.  Lanes of a warp stay converged on the step code.
-constexpr int kProbeTile = 2048;    // positions per CTA
+// Cold-start longest_match for every position (match_probe in deflate_core.cuh), one thread per position.
+// (A work-queue variant -- each lane takes one chain step per iteration and fetches a new position when its
+// walk ends -- kept lanes busier but executed more instructions per step and measured 12 % slower.)
 constexpr int kProbeThreads = 256;
 __global__ void __launch_bounds__(kProbeThreads) k_probe(const uint8_t *__restrict__ in, int64_t in_stride,
                                                          const int32_t *__restrict__ in_len, const ChainRec *__restrict__ recs,
                                                          uint32_t *__restrict__ mlo, uint32_t *__restrict__ mhi, int64_t stride) {
     const int stream = blockIdx.y;
     const int n = in_len[stream];
-    const int tile_base = blockIdx.x * kProbeTile;
-    if (tile_base >= n) return;
-    const int tile_end = min(tile_base + kProbeTile, n);
-    __shared__ int next;
-    if (threadIdx.x == 0) next = tile_base;
-    __syncthreads();
+    const int s = blockIdx.x * kProbeThreads + threadIdx.x;
+    if (s >= n) return;
     const int64_t o = (int64_t)stream * stride;
     LzView v{in + (int64_t)stream * in_stride, recs + o, n};
-    uint32_t *lo = mlo + o, *hi = mhi + o;
-    bool busy = false, done = false;
-    int second = 0;        // 0: walk with the 1024 budget, 1: re-walk with 4096 after the first ran out of budget
-    uint32_t first_e = 0;  // result of the 1024-budget walk
-    ChainState c;
-    c.s = 0; c.cap = 0;
-    for (;;) {
-        if (busy) {
-            const int r = chain_step(v, c);
-            if (r != kWalkContinue) {
-                const uint32_t e = r == kWalkSteps ? kProbeIncomplete : (c.best >= kMinMatch ? mtab_pack(c.best, c.bdist) : 0u);
-                if (!second && r == kWalkBudget) {  // more than 1024 candidates: the 4096 budget may see further
-                    first_e = e; second = 1;
-                    chain_begin(v, c.s, c.cap, 2, kChainFull, kProbeK, c);
-                } else {
-                    lo[c.s] = e;
-                    hi[c.s] = second ? first_e : e;
-                    busy = false;
-                }
-            }
-        } else if (!done) {
-            const int s = atomicAdd(&next, 1);
-            if (s >= tile_end) done = true;
-            else {
-                const int look = n - s;
-                const int d0 = look >= kMinMatch ? (int)v.recs[s].dist : 0;
-                if (d0 == 0 || d0 > kMaxDist) { lo[s] = 0; hi[s] = 0; }
-                else {
-                    chain_begin(v, s, look < kMaxMatch ? look : kMaxMatch, 2, kChainGood, kProbeK, c);
-                    busy = true; second = 0;
-                }
-            }
-        }
-        if (__all_sync(0xffffffffu, done)) break;
-    }
+    uint32_t lo, hi;
+    match_probe(v, s, kProbeK, &lo, &hi);
+    mlo[o + s] = lo;
+    mhi[o + s] = hi;
 }
 
 // ------------------------------------------------------------------ parse: k_walk_spec / k_walk_stitch / k_symscan
@@ -548,7 +511,7 @@ void launch_deflate(const uint8_t *in, int64_t in_stride, const int32_t *in_len,
     { CCT_KERNEL(k_runs, st);
     k_runs<<<(B + kRunWarps - 1) / kRunWarps, 32 * kRunWarps, 0, st>>>(in, in_stride, in_len, ws.dist16, ws.rb16, ws.recs, ws.stride, B);
     }
-    dim3 gp((unsigned)((max_len + kProbeTile - 1) / kProbeTile), (unsigned)B);
+    dim3 gp((unsigned)((max_len + kProbeThreads - 1) / kProbeThreads), (unsigned)B);
     { CCT_KERNEL(k_probe, st);
     k_probe<<<gp, kProbeThreads, 0, st>>>(in, in_stride, in_len, ws.recs, ws.mtab, ws.mhi, ws.stride);
     }
