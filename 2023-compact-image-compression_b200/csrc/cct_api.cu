@@ -253,19 +253,54 @@ size_t cct_decode_workspace_bytes(int B, int rows, int cols) {
     return decode_ws_bytes(std::max(B, 1), (int64_t)rows * cols);
 }
 
+}  // extern "C"
+
+namespace {
+// Called on the host around every pass of a batch call: the host-buffer entry points use them to make the
+// compute stream wait for the pass's input copy and to start the pass's output copy.
+struct PassHooks {
+    std::function<int(int first, int count)> before, after;
+    int max_pass = 0;  // 0 = as many images per pass as the workspace holds
+};
+
+int encode_impl(const uint16_t *d_px, int B, int rows, int cols, uint32_t flags, uint8_t *d_out, size_t out_cap,
+                int64_t *d_offsets, uint32_t *d_status, int32_t *d_stats, void *d_ws, size_t ws_bytes, cudaStream_t st,
+                const PassHooks *hooks);
+int decode_impl(const uint8_t *d_in, const int64_t *d_offsets, int B, int rows, int cols, uint16_t *d_px,
+                uint32_t *d_status, void *d_ws, size_t ws_bytes, cudaStream_t st, const PassHooks *hooks);
+}  // namespace
+
+extern "C" {
+
 int cct_encode_batch(const uint16_t *d_px, int B, int rows, int cols, uint32_t flags, uint8_t *d_out, size_t out_cap,
                      int64_t *d_offsets, uint32_t *d_status, int32_t *d_stats, void *d_ws, size_t ws_bytes,
                      void *stream) {
+    return encode_impl(d_px, B, rows, cols, flags, d_out, out_cap, d_offsets, d_status, d_stats, d_ws, ws_bytes,
+                       (cudaStream_t)stream, nullptr);
+}
+
+int cct_decode_batch(const uint8_t *d_in, const int64_t *d_offsets, int B, int rows, int cols, uint16_t *d_px,
+                     uint32_t *d_status, void *d_ws, size_t ws_bytes, void *stream) {
+    return decode_impl(d_in, d_offsets, B, rows, cols, d_px, d_status, d_ws, ws_bytes, (cudaStream_t)stream, nullptr);
+}
+
+}  // extern "C"
+
+namespace {
+
+int encode_impl(const uint16_t *d_px, int B, int rows, int cols, uint32_t flags, uint8_t *d_out, size_t out_cap,
+                int64_t *d_offsets, uint32_t *d_status, int32_t *d_stats, void *d_ws, size_t ws_bytes, cudaStream_t st,
+                const PassHooks *hooks) {
     int rc = check_shape(B, rows, cols);
     if (rc != CCT_OK) return rc;
     if (!d_offsets || (B > 0 && (!d_px || !d_out || !d_status || !d_ws))) return CCT_E_ARG;
     if (cct_device_count() == 0) return CCT_E_NO_DEVICE;
-    cudaStream_t st = (cudaStream_t)stream;
     const int64_t n_px = (int64_t)rows * cols, nb = n_px / kBlock;
     CK(cudaMemsetAsync(d_offsets, 0, sizeof(int64_t), st));
     if (B == 0) return CCT_OK;
-    const int Bc = fit_batch(ws_bytes, B, [&](int b) { EncodeWs w; return encode_ws_carve(&w, nullptr, b, n_px, flags); });
+    int Bc = fit_batch(ws_bytes, B, [&](int b) { EncodeWs w; return encode_ws_carve(&w, nullptr, b, n_px, flags); });
     if (Bc == 0) return CCT_E_WORKSPACE;
+    if (hooks && hooks->max_pass > 0) Bc = std::min(Bc, hooks->max_pass);
     const int32_t *order = nullptr;
     rc = get_order(rows, cols, (flags & CCT_FLAG_FRACTAL) != 0, st, &order);
     if (rc != CCT_OK) return rc;
@@ -276,6 +311,7 @@ int cct_encode_batch(const uint16_t *d_px, int B, int rows, int cols, uint32_t f
         const int b = std::min(Bc, B - first);
         const uint16_t *px = d_px + (int64_t)first * n_px;
         int32_t *stats = d_stats ? d_stats + (int64_t)first * 4 : nullptr;
+        if (hooks && hooks->before && (rc = hooks->before(first, b)) != CCT_OK) return rc;
         CK(cudaMemsetAsync(ws.jump, 0, (size_t)b * nb, st));
         CK(cudaMemsetAsync(ws.taken, 0, (size_t)b * nb, st));
         launch_gather_stats(px, order, ws.hv, ws.info, b, n_px, st);
@@ -291,21 +327,22 @@ int cct_encode_batch(const uint16_t *d_px, int B, int rows, int cols, uint32_t f
                             d_status, st);
         }
         CK(cudaGetLastError());
+        if (hooks && hooks->after && (rc = hooks->after(first, b)) != CCT_OK) return rc;
     }
     return CCT_OK;
 }
 
-int cct_decode_batch(const uint8_t *d_in, const int64_t *d_offsets, int B, int rows, int cols, uint16_t *d_px,
-                     uint32_t *d_status, void *d_ws, size_t ws_bytes, void *stream) {
+int decode_impl(const uint8_t *d_in, const int64_t *d_offsets, int B, int rows, int cols, uint16_t *d_px,
+                uint32_t *d_status, void *d_ws, size_t ws_bytes, cudaStream_t st, const PassHooks *hooks) {
     int rc = check_shape(B, rows, cols);
     if (rc != CCT_OK) return rc;
     if (B > 0 && (!d_in || !d_offsets || !d_px || !d_status || !d_ws)) return CCT_E_ARG;
     if (cct_device_count() == 0) return CCT_E_NO_DEVICE;
     if (B == 0) return CCT_OK;
-    cudaStream_t st = (cudaStream_t)stream;
     const int64_t n_px = (int64_t)rows * cols;
-    const int Bc = fit_batch(ws_bytes, B, [&](int b) { return decode_ws_bytes(b, n_px); });
+    int Bc = fit_batch(ws_bytes, B, [&](int b) { return decode_ws_bytes(b, n_px); });
     if (Bc == 0) return CCT_E_WORKSPACE;
+    if (hooks && hooks->max_pass > 0) Bc = std::min(Bc, hooks->max_pass);
     const int32_t *order = nullptr;
     rc = get_order(rows, cols, true, st, &order);
     if (rc != CCT_OK) return rc;
@@ -313,11 +350,17 @@ int cct_decode_batch(const uint8_t *d_in, const int64_t *d_offsets, int B, int r
     decode_ws_carve(&ws, d_ws, Bc, n_px);
     for (int first = 0; first < B; first += Bc) {
         const int b = std::min(Bc, B - first);
+        if (hooks && hooks->before && (rc = hooks->before(first, b)) != CCT_OK) return rc;
         launch_decode(d_in, d_offsets + first, b, rows, cols, order, d_px + (int64_t)first * n_px, d_status + first, ws, st);
         CK(cudaGetLastError());
+        if (hooks && hooks->after && (rc = hooks->after(first, b)) != CCT_OK) return rc;
     }
     return CCT_OK;
 }
+
+}  // namespace
+
+extern "C" {
 
 int cct_read_header(const uint8_t *f, size_t len, int *rows, int *cols, int *channels, int *bytes_per_channel,
                     uint32_t *flags) {
@@ -403,7 +446,12 @@ namespace {
 
 struct HostCtx {
     int dev = -1;
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr, copy = nullptr;
+    std::vector<cudaEvent_t> events;
+    cudaEvent_t event(size_t i) {
+        while (events.size() <= i) { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); events.push_back(e); }
+        return events[i];
+    }
     void *buf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t cap[6] = {0, 0, 0, 0, 0, 0};
     int ensure(int slot, size_t bytes) {
@@ -427,6 +475,7 @@ int get_ctx(int device, HostCtx **out) {
     if (c.dev < 0) {
         c.dev = device;
         CK(cudaStreamCreateWithFlags(&c.st, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&c.copy, cudaStreamNonBlocking));
     }
     *out = &c;
     return CCT_OK;
@@ -467,9 +516,24 @@ int cct_encode_host(const uint16_t *h_px, int B, int rows, int cols, uint32_t fl
     int64_t *d_off = (int64_t *)c->buf[2];
     uint32_t *d_status = (uint32_t *)(d_off + B + 1);
     int32_t *d_stats = (int32_t *)(d_status + B);
-    CK(cudaMemcpyAsync(d_px, h_px, (size_t)B * n_px * 2, cudaMemcpyHostToDevice, c->st));
-    rc = cct_encode_batch(d_px, B, rows, cols, flags, d_out, arena, d_off, d_status, d_stats, c->buf[3], c->cap[3], c->st);
-    if (rc != CCT_OK) return rc;
+    // pixels go up in slices on the copy stream; each pass of the encoder waits only for its own slices, so the
+    // upload of pass k+1 overlaps the kernels of pass k
+    const int slice = std::max(1, std::min(B, 128));
+    const int n_slices = (B + slice - 1) / slice;
+    for (int k = 0; k < n_slices; k++) {
+        const size_t lo = (size_t)k * slice, cnt = std::min<size_t>(slice, (size_t)B - lo);
+        CK(cudaMemcpyAsync(d_px + lo * n_px, h_px + lo * n_px, cnt * n_px * 2, cudaMemcpyHostToDevice, c->copy));
+        CK(cudaEventRecord(c->event(k), c->copy));
+    }
+    PassHooks hooks;
+    hooks.max_pass = std::max(1024, (B + 3) / 4);
+    hooks.before = [&](int first, int count) -> int {
+        const int last_slice = (first + count - 1) / slice;
+        CK(cudaStreamWaitEvent(c->st, c->event(last_slice), 0));  // slices are recorded in order on one stream
+        return CCT_OK;
+    };
+    rc = encode_impl(d_px, B, rows, cols, flags, d_out, arena, d_off, d_status, d_stats, c->buf[3], c->cap[3], c->st, &hooks);
+    if (rc != CCT_OK) { cudaStreamSynchronize(c->copy); cudaStreamSynchronize(c->st); return rc; }
     CK(cudaMemcpyAsync(h_offsets, d_off, (size_t)(B + 1) * 8, cudaMemcpyDeviceToHost, c->st));
     CK(cudaMemcpyAsync(h_status, d_status, (size_t)B * 4, cudaMemcpyDeviceToHost, c->st));
     if (h_stats) CK(cudaMemcpyAsync(h_stats, d_stats, (size_t)B * 16, cudaMemcpyDeviceToHost, c->st));
@@ -508,11 +572,23 @@ int cct_decode_host(const uint8_t *h_in, const int64_t *h_offsets, int B, int ro
     for (int i = 0; i <= B; i++) rel[i] = h_offsets[i] - base;
     CK(cudaMemcpyAsync(d_in, h_in + base, (size_t)total, cudaMemcpyHostToDevice, c->st));
     CK(cudaMemcpyAsync(d_off, rel.data(), (size_t)(B + 1) * 8, cudaMemcpyHostToDevice, c->st));
-    rc = cct_decode_batch(d_in, d_off, B, rows, cols, d_px, d_status, c->buf[4], c->cap[4], c->st);
-    if (rc != CCT_OK) { cudaStreamSynchronize(c->st); return rc; }
-    CK(cudaMemcpyAsync(h_px, d_px, (size_t)B * n_px * 2, cudaMemcpyDeviceToHost, c->st));
+    // pixels come down pass by pass on the copy stream while the next pass decodes
+    PassHooks hooks;
+    hooks.max_pass = std::max(1024, (B + 3) / 4);
+    int n_ev = 0;
+    hooks.after = [&](int first, int count) -> int {
+        cudaEvent_t e = c->event(n_ev++);
+        CK(cudaEventRecord(e, c->st));
+        CK(cudaStreamWaitEvent(c->copy, e, 0));
+        CK(cudaMemcpyAsync(h_px + (size_t)first * n_px, d_px + (size_t)first * n_px, (size_t)count * n_px * 2,
+                           cudaMemcpyDeviceToHost, c->copy));
+        return CCT_OK;
+    };
+    rc = decode_impl(d_in, d_off, B, rows, cols, d_px, d_status, c->buf[4], c->cap[4], c->st, &hooks);
+    if (rc != CCT_OK) { cudaStreamSynchronize(c->copy); cudaStreamSynchronize(c->st); return rc; }
     CK(cudaMemcpyAsync(h_status, d_status, (size_t)B * 4, cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
+    CK(cudaStreamSynchronize(c->copy));
     return CCT_OK;
 }
 
@@ -522,7 +598,9 @@ void cct_release(void) {
         for (auto &kv : g_ctx) {
             cudaSetDevice(kv.first);
             for (int i = 0; i < 6; i++) if (kv.second.buf[i]) cudaFree(kv.second.buf[i]);
+            for (cudaEvent_t e : kv.second.events) cudaEventDestroy(e);
             if (kv.second.st) cudaStreamDestroy(kv.second.st);
+            if (kv.second.copy) cudaStreamDestroy(kv.second.copy);
         }
         g_ctx.clear();
     }
