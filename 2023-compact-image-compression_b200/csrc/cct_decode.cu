@@ -92,8 +92,13 @@ __global__ void __launch_bounds__(32 * kInfWarps) k_inflate_sym(StreamSrc src, c
         return;
     }
     constexpr unsigned kMask = LANES == 32 ? 0xffffffffu : ((1u << LANES) - 1u);
-    // flat state machine: the streams sharing the warp take one step each, then reconverge at the vote
+    // The streams sharing the warp advance in lock step: one symbol each while all of them are inside a block
+    // (the hot loop), otherwise one step of the flat state machine (block header + tables, stored bytes,
+    // trailer), after which everybody reconverges at the vote.
     for (;;) {
+        while (__all_sync(kMask, st.phase == kInfSymbol || st.phase >= kInfDone) && __any_sync(kMask, st.phase == kInfSymbol)) {
+            if (st.phase == kInfSymbol) inflate_one_symbol(st, tbs[slot], out, (int)sym_stride, out_cap);
+        }
         const bool run = st.phase < kInfDone;
         if (!__any_sync(kMask, run)) break;
         if (run) inflate_step(st, tbs[slot], out, (int)sym_stride, out_cap);

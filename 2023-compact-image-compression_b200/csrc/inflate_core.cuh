@@ -174,24 +174,43 @@ CCT_HDN inline int inflate_header(InflateState &st, InflateTables &tb) {
     return kInfSymbol;
 }
 
+// One literal/length(+distance) symbol of the current block; the hot path of pass 1.  Leaves kInfSymbol at the
+// end of the block or on an error.  Bits past the end of the input read as zero and are caught at the block end.
+CCT_HD void inflate_one_symbol(InflateState &st, const InflateTables &tb, uint32_t *syms, int sym_cap, int out_cap) {
+    BitReader &br = st.br;
+    if (st.ns >= sym_cap) { st.phase = kInfError; return; }
+    br.refill();
+    const uint32_t e = tb.lit[br.buf & ((1u << kLitBits) - 1)];
+    int sym;
+    if (e) {
+        const int l = (int)(e >> 12);
+        br.buf >>= l; br.nbits -= l;
+        sym = (int)(e & 0xFFF);
+    } else {
+        sym = decode_symbol(br, tb.lit, kLitBits, tb.lcount, tb.lsym);
+        if (sym < 0) { st.phase = kInfError; return; }
+    }
+    if (sym < 256) { syms[st.ns++] = (uint32_t)sym; st.op++; return; }
+    if (sym == 256) {
+        st.phase = (br.nbits < 0 || br.bad || st.op > out_cap) ? kInfError : (st.last ? kInfTrailer : kInfHeader);
+        return;
+    }
+    sym -= 257;
+    if (sym >= 29) { st.phase = kInfError; return; }
+    const int len = len_base_inf(sym) + (int)br.take(len_extra_bits_inf(sym));
+    const int ds = decode_symbol(br, tb.dst, kDstBits, tb.dcount, tb.dsym);
+    if (ds < 0 || ds >= 30) { st.phase = kInfError; return; }
+    br.refill();
+    const int dist = dist_base_inf(ds) + (int)br.take(ds < 4 ? 0 : (ds >> 1) - 1);
+    if (dist > st.op) { st.phase = kInfError; return; }
+    syms[st.ns++] = (uint32_t)(len - 3) | ((uint32_t)dist << 8);
+    st.op += len;
+}
+
 CCT_HD void inflate_step(InflateState &st, InflateTables &tb, uint32_t *syms, int sym_cap, int out_cap) {
     BitReader &br = st.br;
     if (st.phase == kInfSymbol) {
-        br.refill();
-        int sym = decode_symbol(br, tb.lit, kLitBits, tb.lcount, tb.lsym);
-        if (sym < 0 || st.ns >= sym_cap) { st.phase = kInfError; return; }
-        if (sym < 256) { syms[st.ns++] = (uint32_t)sym; st.op++; return; }
-        if (sym == 256) { st.phase = (br.bad || st.op > out_cap) ? kInfError : (st.last ? kInfTrailer : kInfHeader); return; }
-        sym -= 257;
-        if (sym >= 29) { st.phase = kInfError; return; }
-        const int len = len_base_inf(sym) + (int)br.take(len_extra_bits_inf(sym));
-        const int ds = decode_symbol(br, tb.dst, kDstBits, tb.dcount, tb.dsym);
-        if (ds < 0 || ds >= 30) { st.phase = kInfError; return; }
-        br.refill();
-        const int dist = dist_base_inf(ds) + (int)br.take(ds < 4 ? 0 : (ds >> 1) - 1);
-        if (dist > st.op) { st.phase = kInfError; return; }
-        syms[st.ns++] = (uint32_t)(len - 3) | ((uint32_t)dist << 8);
-        st.op += len;
+        inflate_one_symbol(st, tb, syms, sym_cap, out_cap);
     } else if (st.phase == kInfHeader) {
         st.phase = inflate_header(st, tb);
     } else if (st.phase == kInfStored) {  // stored bytes become literal symbols, a few per step
@@ -224,36 +243,8 @@ CCT_HDN inline int inflate_symbols(const uint8_t *in, int in_len, uint32_t *syms
     inflate_begin(st, in, in_len);
     BitReader &br = st.br;
     while (st.phase < kInfDone) {
-        if (st.phase != kInfSymbol) { inflate_step(st, tb, syms, sym_cap, out_cap); continue; }
-        int ns = st.ns, op = st.op;
-        int next = kInfError;
-        while (ns < sym_cap) {
-            br.refill();
-            const uint32_t e = tb.lit[br.buf & ((1u << kLitBits) - 1)];
-            int sym;
-            if (e) {
-                const int l = (int)(e >> 12);
-                br.buf >>= l; br.nbits -= l;
-                sym = (int)(e & 0xFFF);
-                if (sym < 256) { syms[ns++] = (uint32_t)sym; op++; continue; }  // literal fast path
-            } else {
-                sym = decode_symbol(br, tb.lit, kLitBits, tb.lcount, tb.lsym);
-                if (sym < 0) break;
-                if (sym < 256) { syms[ns++] = (uint32_t)sym; op++; continue; }
-            }
-            if (sym == 256) { next = (br.nbits < 0 || op > out_cap) ? kInfError : (st.last ? kInfTrailer : kInfHeader); break; }
-            sym -= 257;
-            if (sym >= 29) break;
-            const int len = len_base_inf(sym) + (int)br.take(len_extra_bits_inf(sym));
-            const int ds = decode_symbol(br, tb.dst, kDstBits, tb.dcount, tb.dsym);
-            if (ds < 0 || ds >= 30) break;
-            br.refill();
-            const int dist = dist_base_inf(ds) + (int)br.take(ds < 4 ? 0 : (ds >> 1) - 1);
-            if (dist > op) break;
-            syms[ns++] = (uint32_t)(len - 3) | ((uint32_t)dist << 8);
-            op += len;
-        }
-        st.ns = ns; st.op = op; st.phase = next;
+        while (st.phase == kInfSymbol) inflate_one_symbol(st, tb, syms, sym_cap, out_cap);
+        if (st.phase < kInfDone) inflate_step(st, tb, syms, sym_cap, out_cap);
     }
     if (st.phase != kInfDone || br.bad) return -1;
     *out_len = st.op; *adler_want = st.adler_want;
