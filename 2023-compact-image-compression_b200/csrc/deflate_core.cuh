@@ -121,7 +121,8 @@ constexpr int kWalkSteps = 2;   // step cap of the probe reached
 constexpr int kWalkContinue = -1;
 struct ChainState {
     int s, cap, best, bdist, chain, steps_left, cur, R;
-    uint8_t b0, b1;
+    uint8_t b0, b1;    // target bytes 0, 1
+    uint8_t tb, tb1;   // target bytes best, best-1 (zlib's scan_end / scan_end1)
 };
 
 CCT_HD void chain_begin(const LzView &v, int s, int cap, int best, int chain, int max_steps, ChainState &c) {
@@ -131,6 +132,7 @@ CCT_HD void chain_begin(const LzView &v, int s, int cap, int best, int chain, in
     c.R = 0;  // leading run of the target, if it is at least one hash triple long
     if (rs.rl >= 2) { c.R = (int)rs.rl + 1; if (c.R > cap) c.R = cap; }
     c.cur = s - rs.dist;
+    c.tb = v.w[s + best]; c.tb1 = v.w[s + best - 1];
 }
 
 // One loop step: a single candidate or a whole run group.  Returns kWalkContinue or how the walk ended.
@@ -140,7 +142,6 @@ CCT_HD int chain_step(const LzView &v, ChainState &c) {
     const uint8_t *b = v.w + s;
     const ChainRec rc = v.recs[cur];  // one load: link, run lengths and the first two bytes of the candidate
     const uint8_t *a = v.w + cur;
-    const uint8_t a_best = a[c.best], a_best1 = a[c.best - 1];
     int link_from = cur;
     int dl = rc.dist;
     if (rc.rl >= 2) {
@@ -156,24 +157,25 @@ CCT_HD int chain_step(const LzView &v, ChainState &c) {
             const int R = c.R;
             const int i_key = m >= R ? 0 : R - m;  // first member with at least R leading c's
             if (R < cap && m > R) {
-                if (R > c.best) { c.best = R; c.bdist = s - cur; }
+                if (R > c.best) { c.best = R; c.bdist = s - cur; c.tb = b[R]; c.tb1 = b[R - 1]; }
             } else if (i_key < nvis) {
                 const int c_al = cur - i_key;
                 const int L = R < cap ? match_extend(v.w + c_al, b, R, cap) : cap;
-                if (L > c.best) { c.best = L; c.bdist = s - c_al; if (L >= cap) return kWalkDone; }
+                if (L > c.best) { c.best = L; c.bdist = s - c_al; if (L >= cap) return kWalkDone; c.tb = b[L]; c.tb1 = b[L - 1]; }
             } else {
                 const int L = m + nvis - 1;  // only members with fewer than R leading c's were reached
-                if (L > c.best) { c.best = L; c.bdist = s - (cur - (nvis - 1)); }
+                if (L > c.best) { c.best = L; c.bdist = s - (cur - (nvis - 1)); c.tb = b[L]; c.tb1 = b[L - 1]; }
             }
         }  // else: the target does not start with (c,c,c) (a hash collision): no member matches 3 bytes
         if (nvis < t + 1) return nvis == count_dist ? kWalkDone : kWalkBudget;
         c.chain -= t;
         if (t) { link_from = cur - t; dl = v.recs[link_from].dist; }  // the bottom of the run links onwards
-    } else if (a_best == b[c.best] && a_best1 == b[c.best - 1] && rc.b0 == c.b0 && rc.b1 == c.b1) {
+    } else if (rc.b0 == c.b0 && rc.b1 == c.b1 && a[c.best] == c.tb && a[c.best - 1] == c.tb1) {
         const int len = match_extend(a, b, 2, cap);
         if (len > c.best) {
             c.best = len; c.bdist = s - cur;
             if (len >= cap) return kWalkDone;
+            c.tb = b[len]; c.tb1 = b[len - 1];
         }
     }
     if (dl == 0) return kWalkDone;
@@ -363,26 +365,29 @@ struct SmallTree {  // distance (30 symbols) and bit-length (19 symbols) trees
 
 struct TreeScratch {
     int16_t heap[kHeapSize];
-    uint8_t depth[kHeapSize];
+    // (Freq << 8 | depth) of heap[k]: trees.c's smaller(n, m) = Freq[n] < Freq[m] || (equal && depth[n] <= depth[m])
+    // is exactly key[n] <= key[m]; keeping the keys beside the heap saves the dependent heap[] -> Freq[] load
+    uint32_t hkey[kHeapSize];
     uint16_t bl_count[kMaxBits + 1];
     int heap_len, heap_max;
     int64_t opt_len, static_len;
 };
 
-template <class T>
-CCT_HD bool tree_smaller(const T &t, const uint8_t *depth, int n, int m) {
-    return t.freq[n] < t.freq[m] || (t.freq[n] == t.freq[m] && depth[n] <= depth[m]);
-}
-
-template <class T>
-CCT_HDN inline void pq_down(TreeScratch &s, const T &t, int k) {
-    int v = s.heap[k], j = k << 1;
+CCT_HDN inline void pq_down(TreeScratch &s, int k) {
+    const int v = s.heap[k];
+    const uint32_t vk = s.hkey[k];
+    int j = k << 1;
     while (j <= s.heap_len) {
-        if (j < s.heap_len && tree_smaller(t, s.depth, s.heap[j + 1], s.heap[j])) j++;
-        if (tree_smaller(t, s.depth, v, s.heap[j])) break;
-        s.heap[k] = s.heap[j]; k = j; j <<= 1;
+        uint32_t jk = s.hkey[j];
+        if (j < s.heap_len) {
+            const uint32_t rk = s.hkey[j + 1];
+            if (rk <= jk) { j++; jk = rk; }
+        }
+        if (vk <= jk) break;
+        s.heap[k] = s.heap[j]; s.hkey[k] = jk;
+        k = j; j <<= 1;
     }
-    s.heap[k] = (int16_t)v;
+    s.heap[k] = (int16_t)v; s.hkey[k] = vk;
 }
 
 // kind: 0 literal/length tree, 1 distance tree, 2 bit-length tree
@@ -395,28 +400,34 @@ CCT_HDN inline void build_tree(TreeScratch &s, T &t, int kind) {
     int n, m, max_code = -1, node;
     s.heap_len = 0; s.heap_max = heap_size;
     for (n = 0; n < elems; n++) {
-        if (t.freq[n] != 0) { s.heap[++s.heap_len] = (int16_t)(max_code = n); s.depth[n] = 0; }
+        if (t.freq[n] != 0) { s.heap[++s.heap_len] = (int16_t)(max_code = n); s.hkey[s.heap_len] = (uint32_t)t.freq[n] << 8; }
         else t.len[n] = 0;
     }
     while (s.heap_len < 2) {  // force at least two codes
         node = s.heap[++s.heap_len] = (int16_t)(max_code < 2 ? ++max_code : 0);
-        t.freq[node] = 1; s.depth[node] = 0;
+        t.freq[node] = 1; s.hkey[s.heap_len] = 1u << 8;
         s.opt_len--;
         if (kind == 0) s.static_len -= static_llen(node);
         else if (kind == 1) s.static_len -= 5;
     }
     t.max_code = max_code;
-    for (n = s.heap_len / 2; n >= 1; n--) pq_down(s, t, n);
+    for (n = s.heap_len / 2; n >= 1; n--) pq_down(s, n);
     node = elems;
     do {
-        n = s.heap[1]; s.heap[1] = s.heap[s.heap_len--]; pq_down(s, t, 1);
+        n = s.heap[1];
+        const uint32_t nk = s.hkey[1];
+        s.heap[1] = s.heap[s.heap_len]; s.hkey[1] = s.hkey[s.heap_len]; s.heap_len--;
+        pq_down(s, 1);
         m = s.heap[1];
+        const uint32_t mk = s.hkey[1];
         s.heap[--s.heap_max] = (int16_t)n; s.heap[--s.heap_max] = (int16_t)m;
-        t.freq[node] = (uint16_t)(t.freq[n] + t.freq[m]);
-        s.depth[node] = (uint8_t)((s.depth[n] >= s.depth[m] ? s.depth[n] : s.depth[m]) + 1);
+        const uint32_t f = (nk >> 8) + (mk >> 8);
+        const uint32_t dn = nk & 255u, dm = mk & 255u;
+        t.freq[node] = (uint16_t)f;
         t.dad[n] = t.dad[m] = (uint16_t)node;
         s.heap[1] = (int16_t)node++;
-        pq_down(s, t, 1);
+        s.hkey[1] = ((f & 0xFFFFu) << 8) | (((dn >= dm ? dn : dm) + 1u) & 255u);
+        pq_down(s, 1);
     } while (s.heap_len >= 2);
     s.heap[--s.heap_max] = s.heap[1];
 

@@ -243,8 +243,59 @@ CCT_HDN inline int inflate_symbols(const uint8_t *in, int in_len, uint32_t *syms
     inflate_begin(st, in, in_len);
     BitReader &br = st.br;
     while (st.phase < kInfDone) {
-        while (st.phase == kInfSymbol) inflate_one_symbol(st, tb, syms, sym_cap, out_cap);
-        if (st.phase < kInfDone) inflate_step(st, tb, syms, sym_cap, out_cap);
+        if (st.phase != kInfSymbol) { inflate_step(st, tb, syms, sym_cap, out_cap); continue; }
+        // hot loop: bit buffer, output cursor and the running output length live in locals; the output length
+        // is (symbols written) + (sum of len-1 over matches), so a literal costs no bookkeeping beyond the store
+        uint64_t buf = br.buf;
+        int nbits = br.nbits, pos = br.pos;
+        const uint8_t *in_ = br.in;
+        const int in_len_ = br.len;
+        uint32_t *p = syms + st.ns;
+        uint32_t *const p0 = p, *const pend = syms + sym_cap;
+        int extra = 0;  // sum of (len - 1) over the matches of this block
+        const int op0 = st.op;
+        int next = kInfError;
+        for (;;) {
+            if (nbits <= 32) {
+                if (pos + 4 <= in_len_) { buf |= (uint64_t)(*reinterpret_cast<const uint32_t *>(in_ + pos)) << nbits; pos += 4; nbits += 32; }
+                else while (nbits <= 56 && pos < in_len_) { buf |= (uint64_t)in_[pos++] << nbits; nbits += 8; }
+            }
+            const uint32_t e = tb.lit[(uint32_t)buf & ((1u << kLitBits) - 1)];
+            int sym;
+            if (e) {
+                const int l = (int)(e >> 12);
+                buf >>= l; nbits -= l;
+                sym = (int)(e & 0xFFF);
+            } else {
+                br.buf = buf; br.nbits = nbits; br.pos = pos;
+                sym = decode_symbol(br, tb.lit, kLitBits, tb.lcount, tb.lsym);
+                buf = br.buf; nbits = br.nbits;
+                if (sym < 0) break;
+            }
+            if (p >= pend) break;
+            if (sym < 256) { *p++ = (uint32_t)sym; continue; }  // literal
+            if (sym == 256) {
+                const int op = op0 + (int)(p - p0) + extra;
+                next = (nbits < 0 || op > out_cap) ? kInfError : (st.last ? kInfTrailer : kInfHeader);
+                break;
+            }
+            sym -= 257;
+            if (sym >= 29) break;
+            br.buf = buf; br.nbits = nbits; br.pos = pos;
+            const int len = len_base_inf(sym) + (int)br.take(len_extra_bits_inf(sym));
+            const int ds = decode_symbol(br, tb.dst, kDstBits, tb.dcount, tb.dsym);
+            if (ds < 0 || ds >= 30) break;
+            br.refill();
+            const int dist = dist_base_inf(ds) + (int)br.take(ds < 4 ? 0 : (ds >> 1) - 1);
+            buf = br.buf; nbits = br.nbits; pos = br.pos;
+            if (dist > op0 + (int)(p - p0) + extra) break;
+            *p++ = (uint32_t)(len - 3) | ((uint32_t)dist << 8);
+            extra += len - 1;
+        }
+        br.buf = buf; br.nbits = nbits; br.pos = pos;
+        st.op = op0 + (int)(p - p0) + extra;
+        st.ns = (int)(p - syms);
+        st.phase = next;
     }
     if (st.phase != kInfDone || br.bad) return -1;
     *out_len = st.op; *adler_want = st.adler_want;
