@@ -9,8 +9,6 @@
 //                                                                      k_dec_scatter (value k -> raster index)
 #include <cuda_runtime.h>
 
-#include <cstdlib>
-
 #include "cct_kernels.h"
 #include "inflate_core.cuh"
 
@@ -43,9 +41,9 @@ size_t decode_ws_carve(DecodeWs *ws, void *mem, int B, int64_t n_px) {
 }
 
 // ------------------------------------------------------------------ inflate (two passes)
-// k_inflate_sym   Huffman decode, ONE THREAD PER STREAM (32 streams per warp, each with its own code tables in
-//                 shared memory): the bit-serial part of inflate touches only the bit reader and the tables and
-//                 appends LZ77 symbols to a per-stream list;
+// k_inflate_sym   Huffman decode, one thread per stream with its code tables in shared memory: the bit-serial
+//                 part of inflate touches only the bit reader and the tables and appends LZ77 symbols to a
+//                 per-stream list;
 // k_lz_expand     LZ77 expansion, one warp per stream: 32 symbols at a time, output offsets by a warp scan,
 //                 literals stored in parallel, matches copied by the whole warp in symbol order;
 // k_adler_check   Adler-32 of the expanded bytes against the stream trailer (CTA per stream).
@@ -55,68 +53,29 @@ struct StreamSrc {  // where stream i lives: arena + offsets (with a header to s
     __device__ int size(int i) const { return (off ? (int)(off[i + 1] - off[i]) : len[i]) - skip; }
 };
 
-// LANES streams per warp (lanes 0..LANES-1 each decode one stream), kInfWarps warps per CTA.  Few lanes per
-// warp keep the per-step divergence (literal vs match vs table build) cheap; many warps per SM hide the
-// latency of the bit-serial dependency chain.
+// One stream per warp (lane 0 decodes), kInfWarps warps per CTA.  Sharing a warp between 2-32 streams was
+// measured slower in every form tried (nested loops never reconverge; a flat state machine and a lock-step
+// symbol loop reconverge but execute both sides of every literal/match/refill branch): the bit-serial decoder
+// is bound by the number of warp instructions issued, and one lane per warp issues the fewest.
 constexpr int kInfWarps = 4;
-template <int LANES>
 __global__ void __launch_bounds__(32 * kInfWarps) k_inflate_sym(StreamSrc src, const uint8_t *__restrict__ fl, int B,
                                                                 uint32_t *__restrict__ syms, int64_t sym_stride, int out_cap,
                                                                 int32_t *__restrict__ nsym, int32_t *__restrict__ out_len,
                                                                 uint32_t *__restrict__ adler_want, uint32_t *__restrict__ status) {
     extern __shared__ __align__(16) unsigned char tb_raw[];
     InflateTables *tbs = reinterpret_cast<InflateTables *>(tb_raw);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane >= LANES) return;
-    const int slot = warp * LANES + lane;
-    const int i = (blockIdx.x * kInfWarps + warp) * LANES + lane;
-    const bool mine = i < B && !status[i] && !(fl && !(fl[i] & 4u));
-    InflateState st;
-    st.phase = kInfDone;
-    st.ns = 0; st.op = 0; st.adler_want = 1;
-    if (mine) {
-        const int len = src.size(i);
-        if (len > 0) inflate_begin(st, src.ptr(i), len); else st.phase = kInfError;
-    }
-    uint32_t *out = syms + (int64_t)(i < B ? i : 0) * sym_stride;
-    if (LANES == 1) {  // the warp holds a single stream: no reconvergence needed, run the tight loop
-        if (i >= B) return;
-        nsym[i] = 0; out_len[i] = 0; adler_want[i] = 1;
-        if (!mine) return;
-        int olen = 0;
-        uint32_t want = 1;
-        const int len = src.size(i);
-        const int ns = len > 0 ? inflate_symbols(src.ptr(i), len, out, (int)sym_stride, out_cap, tbs[slot], &olen, &want) : -1;
-        if (ns < 0) { status[i] |= 16u; return; }  // CCT_ST_INFLATE
-        nsym[i] = ns; out_len[i] = olen; adler_want[i] = want;
-        return;
-    }
-    constexpr unsigned kMask = LANES == 32 ? 0xffffffffu : ((1u << LANES) - 1u);
-    // The streams sharing the warp advance in lock step: one symbol each while all of them are inside a block
-    // (the hot loop), otherwise one step of the flat state machine (block header + tables, stored bytes,
-    // trailer), after which everybody reconverges at the vote.
-    for (;;) {
-        while (__all_sync(kMask, st.phase == kInfSymbol || st.phase >= kInfDone) && __any_sync(kMask, st.phase == kInfSymbol)) {
-            if (st.phase == kInfSymbol) inflate_one_symbol(st, tbs[slot], out, (int)sym_stride, out_cap);
-        }
-        const bool run = st.phase < kInfDone;
-        if (!__any_sync(kMask, run)) break;
-        if (run) inflate_step(st, tbs[slot], out, (int)sym_stride, out_cap);
-    }
-    if (i >= B) return;
-    if (!mine) { nsym[i] = 0; out_len[i] = 0; adler_want[i] = 1; return; }
-    if (st.phase != kInfDone) { status[i] |= 16u; nsym[i] = 0; out_len[i] = 0; adler_want[i] = 1; return; }  // CCT_ST_INFLATE
-    nsym[i] = st.ns; out_len[i] = st.op; adler_want[i] = st.adler_want;
-}
-
-template <int LANES>
-static void launch_inflate_sym(StreamSrc src, const uint8_t *fl, int B, const InflateWs &iw, int out_cap, int32_t *out_len,
-                               uint32_t *status, cudaStream_t st) {
-    const int smem = kInfWarps * LANES * (int)sizeof(InflateTables);
-    cudaFuncSetAttribute(k_inflate_sym<LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    const int per_cta = kInfWarps * LANES;
-    k_inflate_sym<LANES><<<(B + per_cta - 1) / per_cta, 32 * kInfWarps, smem, st>>>(src, fl, B, iw.syms, iw.sym_stride, out_cap,
-                                                                                    iw.nsym, out_len, iw.adler, status);
+    const int warp = threadIdx.x >> 5;
+    const int i = blockIdx.x * kInfWarps + warp;
+    if ((threadIdx.x & 31) || i >= B) return;
+    nsym[i] = 0; out_len[i] = 0; adler_want[i] = 1;
+    if (status[i] || (fl && !(fl[i] & 4u))) return;
+    int olen = 0;
+    uint32_t want = 1;
+    const int len = src.size(i);
+    const int ns = len > 0 ? inflate_symbols(src.ptr(i), len, syms + (int64_t)i * sym_stride, (int)sym_stride, out_cap,
+                                             tbs[warp], &olen, &want) : -1;
+    if (ns < 0) { status[i] |= 16u; return; }  // CCT_ST_INFLATE
+    nsym[i] = ns; out_len[i] = olen; adler_want[i] = want;
 }
 
 constexpr int kLzWarps = 4;
@@ -187,15 +146,10 @@ __global__ void __launch_bounds__(256) k_adler_check(const uint8_t *__restrict__
 
 static void launch_inflate_passes(StreamSrc src, const uint8_t *fl, int B, const InflateWs &iw, uint8_t *out,
                                   int64_t out_stride, int32_t *out_len, uint32_t *status, cudaStream_t st) {
-    static int lanes = 0;
-    if (!lanes) { const char *e = getenv("CCT_INF_LANES"); lanes = e ? atoi(e) : 1; }  // tuning knob, default 1
+    const int smem = kInfWarps * (int)sizeof(InflateTables);
     { CCT_KERNEL(k_inflate_sym, st);
-    switch (lanes) {
-        case 2: launch_inflate_sym<2>(src, fl, B, iw, (int)out_stride, out_len, status, st); break;
-        case 4: launch_inflate_sym<4>(src, fl, B, iw, (int)out_stride, out_len, status, st); break;
-        case 8: launch_inflate_sym<8>(src, fl, B, iw, (int)out_stride, out_len, status, st); break;
-        default: launch_inflate_sym<1>(src, fl, B, iw, (int)out_stride, out_len, status, st); break;
-    }
+    k_inflate_sym<<<(B + kInfWarps - 1) / kInfWarps, 32 * kInfWarps, smem, st>>>(src, fl, B, iw.syms, iw.sym_stride, (int)out_stride,
+                                                                                iw.nsym, out_len, iw.adler, status);
     }
     { CCT_KERNEL(k_lz_expand, st);
     k_lz_expand<<<(B + kLzWarps - 1) / kLzWarps, 32 * kLzWarps, 0, st>>>(iw.syms, iw.sym_stride, iw.nsym, out, out_stride, B);

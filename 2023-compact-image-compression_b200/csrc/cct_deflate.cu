@@ -202,13 +202,15 @@ __global__ void __launch_bounds__(32 * kRunWarps) k_runs(const uint8_t *__restri
 }
 
 // ------------------------------------------------------------------ k_probe
-// Cold-start longest_match for every position (match_probe in deflate_core.cuh), one thread per position.
-// (A work-queue variant -- each lane takes one chain step per iteration and fetches a new position when its
-// walk ends -- kept lanes busier but executed more instructions per step and measured 12 % slower.)
+// Cold-start longest_match for every position (match_probe in deflate_core.cuh), one thread per position, 32
+// registers so that 64 warps per SM hide the dependent chain loads.  Chain lengths vary wildly (over half the
+// positions have no chain, some need the full kProbeK steps) and only ~11 of 32 lanes are active on average; two
+// work-queue variants that refill finished lanes from a shared counter (per lane, and in rounds of >= 8 idle
+// lanes) were measured 12 % slower -- the extra state and the refill branch cost more than the idle lanes.
 constexpr int kProbeThreads = 256;
-__global__ void __launch_bounds__(kProbeThreads) k_probe(const uint8_t *__restrict__ in, int64_t in_stride,
-                                                         const int32_t *__restrict__ in_len, const ChainRec *__restrict__ recs,
-                                                         uint32_t *__restrict__ mlo, uint32_t *__restrict__ mhi, int64_t stride) {
+__global__ void __launch_bounds__(kProbeThreads, 8) k_probe(const uint8_t *__restrict__ in, int64_t in_stride,
+                                                            const int32_t *__restrict__ in_len, const ChainRec *__restrict__ recs,
+                                                            uint32_t *__restrict__ mlo, uint32_t *__restrict__ mhi, int64_t stride) {
     const int stream = blockIdx.y;
     const int n = in_len[stream];
     const int s = blockIdx.x * kProbeThreads + threadIdx.x;

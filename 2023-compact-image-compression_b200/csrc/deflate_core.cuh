@@ -87,6 +87,18 @@ struct alignas(8) ChainRec {
     uint8_t b0, b1; // w[p], w[p+1]
 };
 
+CCT_HD ChainRec load_rec(const ChainRec *p) {
+#if defined(__CUDA_ARCH__)
+    const uint2 q = __ldg(reinterpret_cast<const uint2 *>(p));
+    ChainRec r;
+    r.dist = (uint16_t)(q.x & 0xFFFFu); r.rl = (uint16_t)(q.x >> 16);
+    r.rb = (uint16_t)(q.y & 0xFFFFu); r.b0 = (uint8_t)(q.y >> 16); r.b1 = (uint8_t)(q.y >> 24);
+    return r;
+#else
+    return *p;
+#endif
+}
+
 struct LzView {
     const uint8_t *w;       // payload bytes
     const ChainRec *recs;   // per-position record (k_chains)
@@ -122,17 +134,15 @@ constexpr int kWalkContinue = -1;
 struct ChainState {
     int s, cap, best, bdist, chain, steps_left, cur, R;
     uint8_t b0, b1;    // target bytes 0, 1
-    uint8_t tb, tb1;   // target bytes best, best-1 (zlib's scan_end / scan_end1)
 };
 
 CCT_HD void chain_begin(const LzView &v, int s, int cap, int best, int chain, int max_steps, ChainState &c) {
-    const ChainRec rs = v.recs[s];
+    const ChainRec rs = load_rec(v.recs + s);
     c.s = s; c.cap = cap; c.best = best; c.bdist = 0; c.chain = chain; c.steps_left = max_steps;
     c.b0 = rs.b0; c.b1 = rs.b1;
     c.R = 0;  // leading run of the target, if it is at least one hash triple long
     if (rs.rl >= 2) { c.R = (int)rs.rl + 1; if (c.R > cap) c.R = cap; }
     c.cur = s - rs.dist;
-    c.tb = v.w[s + best]; c.tb1 = v.w[s + best - 1];
 }
 
 // One loop step: a single candidate or a whole run group.  Returns kWalkContinue or how the walk ended.
@@ -140,7 +150,7 @@ CCT_HD int chain_step(const LzView &v, ChainState &c) {
     CCT_COUNT(0);
     const int s = c.s, cap = c.cap, cur = c.cur;
     const uint8_t *b = v.w + s;
-    const ChainRec rc = v.recs[cur];  // one load: link, run lengths and the first two bytes of the candidate
+    const ChainRec rc = load_rec(v.recs + cur);  // one 8-byte load: link, run lengths, first two bytes of the candidate
     const uint8_t *a = v.w + cur;
     int link_from = cur;
     int dl = rc.dist;
@@ -157,25 +167,24 @@ CCT_HD int chain_step(const LzView &v, ChainState &c) {
             const int R = c.R;
             const int i_key = m >= R ? 0 : R - m;  // first member with at least R leading c's
             if (R < cap && m > R) {
-                if (R > c.best) { c.best = R; c.bdist = s - cur; c.tb = b[R]; c.tb1 = b[R - 1]; }
+                if (R > c.best) { c.best = R; c.bdist = s - cur; }
             } else if (i_key < nvis) {
                 const int c_al = cur - i_key;
                 const int L = R < cap ? match_extend(v.w + c_al, b, R, cap) : cap;
-                if (L > c.best) { c.best = L; c.bdist = s - c_al; if (L >= cap) return kWalkDone; c.tb = b[L]; c.tb1 = b[L - 1]; }
+                if (L > c.best) { c.best = L; c.bdist = s - c_al; if (L >= cap) return kWalkDone; }
             } else {
                 const int L = m + nvis - 1;  // only members with fewer than R leading c's were reached
-                if (L > c.best) { c.best = L; c.bdist = s - (cur - (nvis - 1)); c.tb = b[L]; c.tb1 = b[L - 1]; }
+                if (L > c.best) { c.best = L; c.bdist = s - (cur - (nvis - 1)); }
             }
         }  // else: the target does not start with (c,c,c) (a hash collision): no member matches 3 bytes
         if (nvis < t + 1) return nvis == count_dist ? kWalkDone : kWalkBudget;
         c.chain -= t;
         if (t) { link_from = cur - t; dl = v.recs[link_from].dist; }  // the bottom of the run links onwards
-    } else if (rc.b0 == c.b0 && rc.b1 == c.b1 && a[c.best] == c.tb && a[c.best - 1] == c.tb1) {
+    } else if (rc.b0 == c.b0 && rc.b1 == c.b1 && a[c.best] == b[c.best] && a[c.best - 1] == b[c.best - 1]) {
         const int len = match_extend(a, b, 2, cap);
         if (len > c.best) {
             c.best = len; c.bdist = s - cur;
             if (len >= cap) return kWalkDone;
-            c.tb = b[len]; c.tb1 = b[len - 1];
         }
     }
     if (dl == 0) return kWalkDone;

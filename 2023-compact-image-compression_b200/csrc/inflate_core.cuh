@@ -99,9 +99,9 @@ CCT_HD int decode_symbol(BitReader &br, const uint16_t *prim, int prim_bits, con
 
 // Pass 1 of inflate: zlib stream -> LZ77 symbols (same packing as the encoder: bits 0..7 literal byte or len-3,
 // bits 8..23 distance, 0 = literal).  Nothing but the bit reader and the code tables is touched, so one
-// thread per stream can run it with its tables in shared memory.  It is written as a flat state machine
-// (`inflate_step` = one block header, one symbol, or a few stored bytes) so that the 32 streams sharing a warp
-// reconverge after every step instead of drifting apart inside nested loops.
+// thread per stream can run it with its tables in shared memory.  `inflate_step` handles everything outside
+// the symbol loop (block header + tables, stored bytes, trailer) as one step of a small state machine;
+// `inflate_symbols` runs the machine with the symbol phase as a tight loop.
 enum { kInfHeader = 0, kInfSymbol = 1, kInfStored = 2, kInfTrailer = 3, kInfDone = 4, kInfError = 5 };
 struct InflateState {
     BitReader br;

@@ -24,28 +24,38 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 PKG = "2023-compact-image-compression_b200"
 
-METRIC = "encode+decode MPix/s (12-bit 512x512 CT batch)"
+METRIC = "encode+decode MPix/s (12-bit 512x512 CT batch)"  # BASELINE.json metric, one number: pixels / (t_encode + t_decode)
+
+
+WORKLOAD = "ct"  # "ct": synth_ct slices (configs[1]); "radiograph": 16-bit synth_radiograph (configs[3])
+
+
+def _gen_seeds(seeds, n):
+    synth = importlib.import_module(PKG + ".synth")
+    if WORKLOAD == "radiograph":
+        return np.stack([synth.synth_radiograph(int(s), n) for s in seeds]) if len(seeds) else np.empty((0, n, n), np.uint16)
+    return synth.synth_ct_batch(seeds, n)
 
 
 def gen_batch(seeds, n, workers):
-    """synth_ct slices for `seeds`, generated in worker processes (called before CUDA is initialised)."""
-    synth = importlib.import_module(PKG + ".synth")
+    """Synthetic slices for `seeds`, generated in worker processes (called before CUDA is initialised)."""
     seeds = list(seeds)
     if workers <= 1 or len(seeds) < 8:
-        return synth.synth_ct_batch(seeds, n)
+        return _gen_seeds(seeds, n)
     from concurrent.futures import ProcessPoolExecutor
     chunks = [seeds[i::workers] for i in range(workers)]
     out = np.empty((len(seeds), n, n), dtype=np.uint16)
     with ProcessPoolExecutor(workers) as ex:
-        for w, arr in enumerate(ex.map(_gen_chunk, [(c, n) for c in chunks])):
+        for w, arr in enumerate(ex.map(_gen_chunk, [(c, n, WORKLOAD) for c in chunks])):
             out[w::workers] = arr
     return out
 
 
 def _gen_chunk(args):
-    seeds, n = args
-    synth = importlib.import_module(PKG + ".synth")
-    return synth.synth_ct_batch(seeds, n)
+    seeds, n, workload = args
+    global WORKLOAD
+    WORKLOAD = workload
+    return _gen_seeds(seeds, n)
 
 
 class ClockSampler:
@@ -112,7 +122,15 @@ def main():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--cpu-sample", type=int, default=512)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="ct", choices=["ct", "radiograph"],
+                    help="ct: synth_ct 12-bit slices (configs[1], the headline); radiograph: 16-bit 2048x2048 (configs[3])")
+    ap.add_argument("--decode-sweep", action="store_true",
+                    help="configs[4]: decode-only MPix/s over batch sizes 1..16384 (one JSON line with a 'sweep' list)")
     args = ap.parse_args()
+    global WORKLOAD
+    WORKLOAD = args.workload
+    if args.workload == "radiograph" and args.size == 512 and args.batch == 4096:
+        args.size, args.batch = 2048, 64
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -149,6 +167,8 @@ def main():
     # ---- our arm -------------------------------------------------------------------------------------------
     workers = max(1, min(32, cores // max(world, 1)))
     distinct = B
+    if args.decode_sweep:
+        distinct = min(B, 512)
     if B * 0.04 / workers > 90:  # keep generation within ~1.5 min on small hosts: tile a smaller distinct set
         distinct = max(64, int(90 * workers / 0.04) // 64 * 64)
     t0 = time.time()
@@ -190,6 +210,35 @@ def main():
         for i in range(4):
             assert h_arena[h_off[i]:h_off[i + 1]].tobytes() == oracle.encode(imgs[i]), "bytestream differs from oracle"
         parity = "4 bytestreams == oracle; round trip exact on the whole batch"
+
+    if args.decode_sweep:  # configs[4]: decode-only throughput vs batch size (seeds repeat beyond the distinct set)
+        sweep = []
+        for Bs in (1, 4, 16, 64, 256, 1024, 4096, 16384):
+            reps = (Bs + B - 1) // B
+            d_sub = d_imgs.repeat(reps, 1, 1)[:Bs].contiguous() if Bs > B else d_imgs[:Bs]
+            try:
+                a_s, o_s, _ = pkg.encode_batch(d_sub)
+                for _ in range(2):
+                    px_s, dst_s = pkg.decode_batch(a_s, o_s, (n, n))
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(args.steps):
+                    px_s, dst_s = pkg.decode_batch(a_s, o_s, (n, n))
+                e1.record()
+                torch.cuda.synchronize()
+                assert torch.equal(px_s.view(torch.int16), d_sub) and not dst_s.any().item()
+                sweep.append({"batch": Bs, "decode_mpix_s": Bs * n_px * args.steps / (e0.elapsed_time(e1) / 1e3) / 1e6})
+            except torch.OutOfMemoryError:
+                sweep.append({"batch": Bs, "decode_mpix_s": None, "note": "out of memory"})
+            del d_sub
+        if rank == 0:
+            print(json.dumps({"metric": "decode-only MPix/s vs batch size (configs[4])", "unit": "MPix/s", "n_gpus": world,
+                              "steps": args.steps, "data": "synthetic", "config": {"workload": f"synth_{WORKLOAD} {n}x{n}"},
+                              "sweep": sweep}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     sampler = ClockSampler(local)
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
@@ -288,8 +337,9 @@ def main():
     line = {"metric": METRIC, "value": total_px / t_all / 1e6, "unit": "MPix/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t_all / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u16", "data": "synthetic",
-            "config": {"workload": f"{B} synth_ct {n}x{n} 12-bit slices per GPU (configs[1]), encode then decode",
-                       "slices_per_gpu": B, "distinct_slices_per_gpu": int(len(base)), "l2": "inputs larger than L2 (2.1 GB raw per GPU)",
+            "config": {"workload": (f"{B} synth_ct {n}x{n} 12-bit slices per GPU (configs[1]), encode then decode" if WORKLOAD == "ct"
+                                    else f"{B} synth_radiograph {n}x{n} 16-bit slices per GPU (configs[3]), encode then decode"),
+                       "slices_per_gpu": B, "distinct_slices_per_gpu": int(len(base)), "l2": f"inputs larger than L2 ({raw / 1e9:.2f} GB raw per GPU)",
                        "parallelism": f"batch sharded over {world} GPU(s), no collective on the data path"},
             "encode_mpix_s": total_px / t_enc / 1e6, "decode_mpix_s": total_px / t_dec / 1e6,
             "raw_gbs": {"encode": 2 * total_px / t_enc / 1e9, "decode": 2 * total_px / t_dec / 1e9},
