@@ -312,13 +312,12 @@ int encode_impl(const uint16_t *d_px, int B, int rows, int cols, uint32_t flags,
         const uint16_t *px = d_px + (int64_t)first * n_px;
         int32_t *stats = d_stats ? d_stats + (int64_t)first * 4 : nullptr;
         if (hooks && hooks->before && (rc = hooks->before(first, b)) != CCT_OK) return rc;
-        CK(cudaMemsetAsync(ws.jump, 0, (size_t)b * nb, st));
-        CK(cudaMemsetAsync(ws.taken, 0, (size_t)b * nb, st));
+        { CCT_KERNEL(m_zero_jump, st); CK(cudaMemsetAsync(ws.jump, 0, (size_t)b * nb, st)); CK(cudaMemsetAsync(ws.taken, 0, (size_t)b * nb, st)); }
         launch_gather_stats(px, order, ws.hv, ws.info, b, n_px, st);
         if (flags & CCT_FLAG_SEGMENTATION) launch_mesh(ws.hv, ws.info, ws.jump, ws.taken, stats, b, n_px, st);
         launch_emit(ws.hv, ws.jump, ws.taken, ws.payload, ws.pstride, ws.plen, d_status + first, stats, b, n_px, st);
         if (flags & CCT_FLAG_DEFLATE) {
-            CK(cudaMemsetAsync(ws.zbuf, 0, (size_t)b * ws.zstride, st));
+            { CCT_KERNEL(m_zero_zbuf, st); CK(cudaMemsetAsync(ws.zbuf, 0, (size_t)b * ws.zstride, st)); }
             launch_deflate(ws.payload, ws.pstride, ws.plen, b, ws.pstride, ws.zbuf, ws.zstride, ws.zlen, ws.dws, st);
             launch_assemble(ws.zbuf, ws.zstride, ws.zlen, b, rows, cols, flags, d_out, (int64_t)out_cap, d_offsets, first,
                             d_status, st);

@@ -517,7 +517,7 @@ void launch_deflate(const uint8_t *in, int64_t in_stride, const int32_t *in_len,
     { CCT_KERNEL(k_probe, st);
     k_probe<<<gp, kProbeThreads, 0, st>>>(in, in_stride, in_len, ws.recs, ws.mtab, ws.mhi, ws.stride);
     }
-    cudaMemsetAsync(ws.flag, 0, (size_t)B * ws.stride, st);
+    { CCT_KERNEL(m_zero_flag, st); cudaMemsetAsync(ws.flag, 0, (size_t)B * ws.stride, st); }
     dim3 gw((unsigned)((ws.max_win + 127) / 128), (unsigned)B);
     { CCT_KERNEL(k_walk_spec, st);
     k_walk_spec<<<gw, 128, 0, st>>>(in, in_stride, in_len, ws.recs, ws.mtab, ws.mhi, ws.flag, ws.rec, ws.exits, ws.stride,
