@@ -5,7 +5,6 @@
 
 #include <algorithm>
 #include <cstdio>
-#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -159,43 +158,6 @@ size_t encode_ws_carve(EncodeWs *ws, void *mem, int B, int64_t n_px, uint32_t fl
     return used;
 }
 
-// ---------------------------------------------------------------- side streams
-// A pass is split into kSplit sub-batches that run on different streams: the stages alternate between
-// issue-bound kernels (k_probe, k_inflate_sym) and latency-bound ones that leave most issue slots empty
-// (k_chains: 3 warps per SM; k_block_build, k_lz_expand, k_walk_spec), so two sub-batches in different stages
-// fill each other's gaps.  Sub-batch 0 runs on the caller's stream, the others on library-owned streams that
-// are forked from / joined to the caller's stream with events.
-constexpr int kMaxSplit = 2;
-struct SideStreams {
-    cudaStream_t side[kMaxSplit - 1] = {};
-    cudaEvent_t fork = nullptr, join[kMaxSplit - 1] = {}, mid[kMaxSplit - 1] = {};
-};
-std::map<int, SideStreams> g_side;  // per device, guarded by g_mu
-
-int get_side(SideStreams **out) {
-    int dev = 0;
-    CK(cudaGetDevice(&dev));
-    std::lock_guard<std::mutex> lk(g_mu);
-    SideStreams &s = g_side[dev];
-    if (!s.fork) {
-        CK(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
-        for (int k = 0; k < kMaxSplit - 1; k++) {
-            CK(cudaStreamCreateWithFlags(&s.side[k], cudaStreamNonBlocking));
-            CK(cudaEventCreateWithFlags(&s.join[k], cudaEventDisableTiming));
-            CK(cudaEventCreateWithFlags(&s.mid[k], cudaEventDisableTiming));
-        }
-    }
-    *out = &s;
-    return CCT_OK;
-}
-
-int split_for(int b) {
-    static int forced = -1;
-    if (forced < 0) { const char *e = getenv("CCT_SPLIT"); forced = e ? std::max(1, std::min(kMaxSplit, atoi(e))) : 0; }
-    if (forced) return b >= forced ? forced : 1;
-    return b >= 256 ? kMaxSplit : 1;  // small batches: every kernel is latency-bound, splitting only adds launches
-}
-
 int check_shape(int B, int rows, int cols) {
     if (B < 0 || rows <= 0 || cols <= 0 || rows > 65535 || cols > 65535) return CCT_E_ARG;
     const int64_t n = (int64_t)rows * cols;
@@ -283,14 +245,12 @@ size_t cct_deflate_bound(size_t len) { return (size_t)align_up(deflate_bound((in
 size_t cct_encode_workspace_bytes(int B, int rows, int cols, uint32_t flags) {
     if (check_shape(B, rows, cols) != CCT_OK) return 0;
     EncodeWs ws;
-    const int b = std::max(B, 1), sp = split_for(b);
-    return (size_t)sp * encode_ws_carve(&ws, nullptr, (b + sp - 1) / sp, (int64_t)rows * cols, flags);
+    return encode_ws_carve(&ws, nullptr, std::max(B, 1), (int64_t)rows * cols, flags);
 }
 
 size_t cct_decode_workspace_bytes(int B, int rows, int cols) {
     if (check_shape(B, rows, cols) != CCT_OK) return 0;
-    const int b = std::max(B, 1), sp = split_for(b);
-    return (size_t)sp * decode_ws_bytes((b + sp - 1) / sp, (int64_t)rows * cols);
+    return decode_ws_bytes(std::max(B, 1), (int64_t)rows * cols);
 }
 
 }  // extern "C"
@@ -338,68 +298,32 @@ int encode_impl(const uint16_t *d_px, int B, int rows, int cols, uint32_t flags,
     const int64_t n_px = (int64_t)rows * cols, nb = n_px / kBlock;
     CK(cudaMemsetAsync(d_offsets, 0, sizeof(int64_t), st));
     if (B == 0) return CCT_OK;
-    // workspace holds `split` sub-batches of ceil(b / split) images side by side
-    auto need = [&](int b) {
-        const int sp = split_for(b);
-        EncodeWs w;
-        return (size_t)sp * encode_ws_carve(&w, nullptr, (b + sp - 1) / sp, n_px, flags);
-    };
-    int Bc = fit_batch(ws_bytes, B, need);
+    int Bc = fit_batch(ws_bytes, B, [&](int b) { EncodeWs w; return encode_ws_carve(&w, nullptr, b, n_px, flags); });
     if (Bc == 0) return CCT_E_WORKSPACE;
     if (hooks && hooks->max_pass > 0) Bc = std::min(Bc, hooks->max_pass);
     const int32_t *order = nullptr;
     rc = get_order(rows, cols, (flags & CCT_FLAG_FRACTAL) != 0, st, &order);
     if (rc != CCT_OK) return rc;
     if (d_stats) CK(cudaMemsetAsync(d_stats, 0, (size_t)B * 4 * sizeof(int32_t), st));
-    SideStreams *ss = nullptr;
-    if ((rc = get_side(&ss)) != CCT_OK) return rc;
-    const int split = split_for(Bc);
-    const int sub_cap = (Bc + split - 1) / split;
-    EncodeWs wss[kMaxSplit];
-    {
-        EncodeWs tmp;
-        const size_t one = encode_ws_carve(&tmp, nullptr, sub_cap, n_px, flags);
-        for (int k = 0; k < split; k++) encode_ws_carve(&wss[k], (char *)d_ws + (size_t)k * one, sub_cap, n_px, flags);
-    }
+    EncodeWs ws;
+    encode_ws_carve(&ws, d_ws, Bc, n_px, flags);
     for (int first = 0; first < B; first += Bc) {
         const int b = std::min(Bc, B - first);
+        const uint16_t *px = d_px + (int64_t)first * n_px;
+        int32_t *stats = d_stats ? d_stats + (int64_t)first * 4 : nullptr;
         if (hooks && hooks->before && (rc = hooks->before(first, b)) != CCT_OK) return rc;
-        if (split > 1) CK(cudaEventRecord(ss->fork, st));
-        int sub_first[kMaxSplit], sub_n[kMaxSplit];
-        for (int k = 0; k < split; k++) {  // everything up to the per-image byte streams, one sub-batch per stream
-            sub_first[k] = first + std::min(b, k * sub_cap);
-            sub_n[k] = std::min(b, (k + 1) * sub_cap) - std::min(b, k * sub_cap);
-            if (sub_n[k] <= 0) continue;
-            cudaStream_t sk = k == 0 ? st : ss->side[k - 1];
-            if (k > 0) CK(cudaStreamWaitEvent(sk, ss->fork, 0));
-            const EncodeWs &ws = wss[k];
-            const int f = sub_first[k], n = sub_n[k];
-            const uint16_t *px = d_px + (int64_t)f * n_px;
-            int32_t *stats = d_stats ? d_stats + (int64_t)f * 4 : nullptr;
-            { CCT_KERNEL(m_zero_jump, sk); CK(cudaMemsetAsync(ws.jump, 0, (size_t)n * nb, sk)); CK(cudaMemsetAsync(ws.taken, 0, (size_t)n * nb, sk)); }
-            launch_gather_stats(px, order, ws.hv, ws.info, n, n_px, sk);
-            if (flags & CCT_FLAG_SEGMENTATION) launch_mesh(ws.hv, ws.info, ws.jump, ws.taken, stats, n, n_px, sk);
-            launch_emit(ws.hv, ws.jump, ws.taken, ws.payload, ws.pstride, ws.plen, d_status + f, stats, n, n_px, sk);
-            if (flags & CCT_FLAG_DEFLATE) {
-                { CCT_KERNEL(m_zero_zbuf, sk); CK(cudaMemsetAsync(ws.zbuf, 0, (size_t)n * ws.zstride, sk)); }
-                launch_deflate(ws.payload, ws.pstride, ws.plen, n, ws.pstride, ws.zbuf, ws.zstride, ws.zlen, ws.dws, sk);
-            }
-            if (k > 0) CK(cudaEventRecord(ss->join[k - 1], sk));
-        }
-        for (int k = 0; k < split; k++) {  // offsets run on from sub-batch to sub-batch: assemble in order on st
-            if (sub_n[k] <= 0) continue;
-            if (k > 0) CK(cudaStreamWaitEvent(st, ss->join[k - 1], 0));
-            const EncodeWs &ws = wss[k];
-            if (flags & CCT_FLAG_DEFLATE)
-                launch_assemble(ws.zbuf, ws.zstride, ws.zlen, sub_n[k], rows, cols, flags, d_out, (int64_t)out_cap, d_offsets,
-                                sub_first[k], d_status, st);
-            else
-                launch_assemble(ws.payload, ws.pstride, ws.plen, sub_n[k], rows, cols, flags, d_out, (int64_t)out_cap, d_offsets,
-                                sub_first[k], d_status, st);
-        }
-        if (split > 1) {  // a side stream may not start the next pass before this pass's arena copies have read its buffers
-            CK(cudaEventRecord(ss->mid[0], st));
-            for (int k = 1; k < split; k++) CK(cudaStreamWaitEvent(ss->side[k - 1], ss->mid[0], 0));
+        { CCT_KERNEL(m_zero_jump, st); CK(cudaMemsetAsync(ws.jump, 0, (size_t)b * nb, st)); CK(cudaMemsetAsync(ws.taken, 0, (size_t)b * nb, st)); }
+        launch_gather_stats(px, order, ws.hv, ws.info, b, n_px, st);
+        if (flags & CCT_FLAG_SEGMENTATION) launch_mesh(ws.hv, ws.info, ws.jump, ws.taken, stats, b, n_px, st);
+        launch_emit(ws.hv, ws.jump, ws.taken, ws.payload, ws.pstride, ws.plen, d_status + first, stats, b, n_px, st);
+        if (flags & CCT_FLAG_DEFLATE) {
+            { CCT_KERNEL(m_zero_zbuf, st); CK(cudaMemsetAsync(ws.zbuf, 0, (size_t)b * ws.zstride, st)); }
+            launch_deflate(ws.payload, ws.pstride, ws.plen, b, ws.pstride, ws.zbuf, ws.zstride, ws.zlen, ws.dws, st);
+            launch_assemble(ws.zbuf, ws.zstride, ws.zlen, b, rows, cols, flags, d_out, (int64_t)out_cap, d_offsets, first,
+                            d_status, st);
+        } else {
+            launch_assemble(ws.payload, ws.pstride, ws.plen, b, rows, cols, flags, d_out, (int64_t)out_cap, d_offsets, first,
+                            d_status, st);
         }
         CK(cudaGetLastError());
         if (hooks && hooks->after && (rc = hooks->after(first, b)) != CCT_OK) return rc;
@@ -415,39 +339,18 @@ int decode_impl(const uint8_t *d_in, const int64_t *d_offsets, int B, int rows, 
     if (cct_device_count() == 0) return CCT_E_NO_DEVICE;
     if (B == 0) return CCT_OK;
     const int64_t n_px = (int64_t)rows * cols;
-    auto need = [&](int b) {
-        const int sp = split_for(b);
-        return (size_t)sp * decode_ws_bytes((b + sp - 1) / sp, n_px);
-    };
-    int Bc = fit_batch(ws_bytes, B, need);
+    int Bc = fit_batch(ws_bytes, B, [&](int b) { return decode_ws_bytes(b, n_px); });
     if (Bc == 0) return CCT_E_WORKSPACE;
     if (hooks && hooks->max_pass > 0) Bc = std::min(Bc, hooks->max_pass);
     const int32_t *order = nullptr;
     rc = get_order(rows, cols, true, st, &order);
     if (rc != CCT_OK) return rc;
-    SideStreams *ss = nullptr;
-    if ((rc = get_side(&ss)) != CCT_OK) return rc;
-    const int split = split_for(Bc);
-    const int sub_cap = (Bc + split - 1) / split;
-    DecodeWs wss[kMaxSplit];
-    {
-        const size_t one = decode_ws_bytes(sub_cap, n_px);
-        for (int k = 0; k < split; k++) decode_ws_carve(&wss[k], (char *)d_ws + (size_t)k * one, sub_cap, n_px);
-    }
+    DecodeWs ws;
+    decode_ws_carve(&ws, d_ws, Bc, n_px);
     for (int first = 0; first < B; first += Bc) {
         const int b = std::min(Bc, B - first);
         if (hooks && hooks->before && (rc = hooks->before(first, b)) != CCT_OK) return rc;
-        if (split > 1) CK(cudaEventRecord(ss->fork, st));
-        for (int k = 0; k < split; k++) {  // files are independent: one sub-batch per stream, joined at the end
-            const int lo = std::min(b, k * sub_cap), n = std::min(b, (k + 1) * sub_cap) - lo;
-            if (n <= 0) continue;
-            cudaStream_t sk = k == 0 ? st : ss->side[k - 1];
-            if (k > 0) CK(cudaStreamWaitEvent(sk, ss->fork, 0));
-            const int f = first + lo;
-            launch_decode(d_in, d_offsets + f, n, rows, cols, order, d_px + (int64_t)f * n_px, d_status + f, wss[k], sk);
-            if (k > 0) CK(cudaEventRecord(ss->join[k - 1], sk));
-        }
-        for (int k = 1; k < split; k++) CK(cudaStreamWaitEvent(st, ss->join[k - 1], 0));
+        launch_decode(d_in, d_offsets + first, b, rows, cols, order, d_px + (int64_t)first * n_px, d_status + first, ws, st);
         CK(cudaGetLastError());
         if (hooks && hooks->after && (rc = hooks->after(first, b)) != CCT_OK) return rc;
     }
@@ -701,16 +604,6 @@ void cct_release(void) {
     std::lock_guard<std::mutex> lk(g_mu);
     for (auto &kv : g_orders) { cudaSetDevice(std::get<0>(kv.first)); cudaFree(kv.second); }
     g_orders.clear();
-    for (auto &kv : g_side) {
-        cudaSetDevice(kv.first);
-        if (kv.second.fork) cudaEventDestroy(kv.second.fork);
-        for (int k = 0; k < kMaxSplit - 1; k++) {
-            if (kv.second.side[k]) cudaStreamDestroy(kv.second.side[k]);
-            if (kv.second.join[k]) cudaEventDestroy(kv.second.join[k]);
-            if (kv.second.mid[k]) cudaEventDestroy(kv.second.mid[k]);
-        }
-    }
-    g_side.clear();
 }
 
 }  // extern "C"
