@@ -387,6 +387,9 @@ CCT_HD uint32_t ops_emit_chunk(const uint8_t *payload, int lo, int hi, int end, 
     int pos = lo + cs.entry, k = cs.op_base, value = cs.val_base;
     const int stop = hi < end ? hi : end;
     uint32_t st = 0;
+    // values are written four at a time (one aligned 8-byte store): a thread owns a contiguous range of vals[],
+    // and 2-byte stores from 32 threads would cost 32 memory transactions per value
+    uint64_t quad = 0;
     while (pos < stop && k < n_px) {
         int delta, kind;
         const int len = op_decode(payload, pos, end, &delta, &kind);
@@ -399,8 +402,16 @@ CCT_HD uint32_t ops_emit_chunk(const uint8_t *payload, int lo, int hi, int end, 
         }
         value += delta;
         if (value < 0 || value > 65535) st |= 32u;  // reference: OverflowError (core.py:506,516)
-        vals[k++] = (uint16_t)value;
+        const int q = k & 3;
+        quad |= (uint64_t)(uint16_t)value << (16 * q);
+        if (q == 3) {
+            if (k - 3 >= cs.op_base) *reinterpret_cast<uint64_t *>(vals + k - 3) = quad;  // vals is 8-byte aligned
+            else for (int j = cs.op_base; j <= k; j++) vals[j] = (uint16_t)(quad >> (16 * (j & 3)));
+            quad = 0;
+        }
+        k++;
     }
+    for (int j = (k & ~3) < cs.op_base ? cs.op_base : (k & ~3); j < k; j++) vals[j] = (uint16_t)(quad >> (16 * (j & 3)));
     return st;
 }
 
