@@ -190,14 +190,14 @@ __global__ void __launch_bounds__(32 * kRunWarps) k_runs(const uint8_t *__restri
     carry = 0;  // count of the position just after the group
     for (int base = ((n - 1) / 32) * 32; base >= 0; base -= 32) {
         const int s = base + lane;
-        const uint8_t c0 = s < n ? w[s] : 0, c1 = s + 1 < n ? w[s + 1] : 0;
+        const uint8_t c0 = s < n ? w[s] : 0, c1 = s + 1 < n ? w[s + 1] : 0, c2 = s + 2 < n ? w[s + 2] : 0;
         const bool eq = s + 1 < n && c0 == c1;
         const unsigned em = __ballot_sync(0xffffffffu, eq);
         const unsigned zeros_above = ~em & ~((1u << lane) - 1u);  // positions >= lane whose flag is 0
         int fwd = zeros_above ? (__ffs((int)zeros_above) - 1) - lane : (32 - lane) + carry;
         if (fwd > 65535) fwd = 65535;
         carry = __shfl_sync(0xffffffffu, fwd, 0);
-        if (s < n) recs[s] = ChainRec{d16[s], (uint16_t)fwd, rb[s], c0, c1};
+        if (s < n) recs[s] = make_rec(d16[s], fwd, rb[s], c0, c1, c2);
     }
 }
 

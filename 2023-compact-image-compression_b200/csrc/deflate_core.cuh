@@ -79,20 +79,30 @@ CCT_HD uint32_t static_lcode(int n) {
 // ------------------------------------------------------------------------------------------------
 // longest_match
 // ------------------------------------------------------------------------------------------------
-// Everything the chain walk needs to know about a position, in one aligned 8-byte load.
+// Everything the chain walk needs to know about a position, in one aligned 8-byte load.  (The walk is bound by
+// the number of distinct memory sectors its divergent loads touch, so the hash triple is carried here too:
+// candidates that merely share the hash, and the first three bytes of real ones, never touch the payload.)
 struct alignas(8) ChainRec {
     uint16_t dist;  // chain link: distance to the previous position with the same hash, 0 = none / >= 32768
-    uint16_t rl;    // number of bytes equal to w[p] immediately after p  (capped at 65535)
-    uint16_t rb;    // number of bytes equal to w[p] immediately before p (capped at 65535)
-    uint8_t b0, b1; // w[p], w[p+1]
+    uint16_t rl;    // number of bytes equal to w[p] immediately after p (capped at 65535)
+    uint16_t x;     // rl >= 2 (p starts a triple (c,c,c)): number of bytes equal to w[p] immediately before p
+                    // (capped at 65535); otherwise w[p+1] | w[p+2] << 8
+    uint8_t b0;     // w[p]
+    uint8_t pad;
 };
+CCT_HD ChainRec make_rec(int dist, int rl, int rb, uint8_t b0, uint8_t b1, uint8_t b2) {
+    ChainRec r;
+    r.dist = (uint16_t)dist; r.rl = (uint16_t)rl; r.b0 = b0; r.pad = 0;
+    r.x = rl >= 2 ? (uint16_t)rb : (uint16_t)(b1 | (b2 << 8));
+    return r;
+}
 
 CCT_HD ChainRec load_rec(const ChainRec *p) {
 #if defined(__CUDA_ARCH__)
     const uint2 q = __ldg(reinterpret_cast<const uint2 *>(p));
     ChainRec r;
     r.dist = (uint16_t)(q.x & 0xFFFFu); r.rl = (uint16_t)(q.x >> 16);
-    r.rb = (uint16_t)(q.y & 0xFFFFu); r.b0 = (uint8_t)(q.y >> 16); r.b1 = (uint8_t)(q.y >> 24);
+    r.x = (uint16_t)(q.y & 0xFFFFu); r.b0 = (uint8_t)(q.y >> 16); r.pad = 0;
     return r;
 #else
     return *p;
@@ -133,13 +143,15 @@ constexpr int kWalkSteps = 2;   // step cap of the probe reached
 constexpr int kWalkContinue = -1;
 struct ChainState {
     int s, cap, best, bdist, chain, steps_left, cur, R;
-    uint8_t b0, b1;    // target bytes 0, 1
+    uint8_t b0;        // target byte 0
+    uint16_t b12;      // target bytes 1, 2 (as in ChainRec::x of a non-run position)
 };
 
 CCT_HD void chain_begin(const LzView &v, int s, int cap, int best, int chain, int max_steps, ChainState &c) {
     const ChainRec rs = load_rec(v.recs + s);
     c.s = s; c.cap = cap; c.best = best; c.bdist = 0; c.chain = chain; c.steps_left = max_steps;
-    c.b0 = rs.b0; c.b1 = rs.b1;
+    c.b0 = rs.b0;
+    c.b12 = rs.rl >= 2 ? (uint16_t)(rs.b0 | (rs.b0 << 8)) : rs.x;
     c.R = 0;  // leading run of the target, if it is at least one hash triple long
     if (rs.rl >= 2) { c.R = (int)rs.rl + 1; if (c.R > cap) c.R = cap; }
     c.cur = s - rs.dist;
@@ -157,7 +169,7 @@ CCT_HD int chain_step(const LzView &v, ChainState &c) {
     if (rc.rl >= 2) {
         // cur starts a triple (c,c,c): the chain entries below it inside the run form one group
         const int m = (int)rc.rl + 1;  // leading c's of the top candidate
-        int t = rc.rb;                 // further candidates of this run below cur
+        int t = rc.x;                  // further candidates of this run below cur
         if (cur - t < 1) t = cur - 1;  // position 0 is never in a chain
         const int count_dist = kMaxDist - (s - cur);
         int nvis = t + 1;
@@ -180,8 +192,9 @@ CCT_HD int chain_step(const LzView &v, ChainState &c) {
         if (nvis < t + 1) return nvis == count_dist ? kWalkDone : kWalkBudget;
         c.chain -= t;
         if (t) { link_from = cur - t; dl = v.recs[link_from].dist; }  // the bottom of the run links onwards
-    } else if (rc.b0 == c.b0 && rc.b1 == c.b1 && a[c.best] == b[c.best] && a[c.best - 1] == b[c.best - 1]) {
-        const int len = match_extend(a, b, 2, cap);
+    } else if (rc.b0 == c.b0 && rc.x == c.b12 && (c.best < kMinMatch || a[c.best] == b[c.best])) {
+        // the hash triple matches (no payload access so far); zlib's scan_end test is only a shortcut for len <= best
+        const int len = match_extend(a, b, cap < kMinMatch ? cap : kMinMatch, cap);
         if (len > c.best) {
             c.best = len; c.bdist = s - cur;
             if (len >= cap) return kWalkDone;

@@ -59,7 +59,7 @@ int64_t hs_deflate2(const uint8_t *src, int n, uint8_t *dst, int64_t cap, int pr
     runs_reference(src, n, rb16, rl16);
     std::vector<ChainRec> recs((size_t)n + 1);
     for (int p = 0; p < n; p++)
-        recs[p] = ChainRec{dist16[p], rl16[p], rb16[p], src[p], (uint8_t)(p + 1 < n ? src[p + 1] : 0)};
+        recs[p] = make_rec(dist16[p], rl16[p], rb16[p], src[p], (uint8_t)(p + 1 < n ? src[p + 1] : 0), (uint8_t)(p + 2 < n ? src[p + 2] : 0));
     LzView v{src, recs.data(), n};
     std::vector<uint32_t> mlo((size_t)n + 1, 0), mhi((size_t)n + 1, 0);
     int64_t n_incomplete = 0;
