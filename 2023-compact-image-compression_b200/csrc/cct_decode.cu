@@ -163,7 +163,7 @@ size_t inflate_ws_carve(InflateWs *iw, void *mem, int B, int64_t out_stride) {
     char *p = (char *)mem;
     size_t used = 0;
     auto take = [&](size_t bytes) { void *r = p ? p + used : nullptr; used += (size_t)align_up((int64_t)bytes, 256); return r; };
-    iw->sym_stride = align_up(out_stride, 4);
+    iw->sym_stride = align_up(out_stride + kInfSlack, 4);  // see inflate_symbols: capacity is checked per refill
     iw->syms = (uint32_t *)take((size_t)B * iw->sym_stride * sizeof(uint32_t));
     iw->nsym = (int32_t *)take((size_t)B * 4);
     iw->adler = (uint32_t *)take((size_t)B * 4);

@@ -10,6 +10,7 @@
 namespace cct {
 
 constexpr int kLitBits = 10;  // primary lookup width, literal/length codes
+constexpr int kInfSlack = 64; // spare symbol slots the symbol buffer must have beyond the largest valid count
 constexpr int kDstBits = 9;   // primary lookup width, distance codes
 
 struct InflateTables {  // per-stream decode tables (shared memory on the device)
@@ -257,6 +258,9 @@ CCT_HDN inline int inflate_symbols(const uint8_t *in, int in_len, uint32_t *syms
         int next = kInfError;
         for (;;) {
             if (nbits <= 32) {
+                // room for the symbols of the next 32+ bits is checked here, not per symbol: at most 32 symbols
+                // are decoded between two refills (kInfSlack = 64 spare slots)
+                if (pend - p < kInfSlack) break;
                 if (pos + 4 <= in_len_) { buf |= (uint64_t)(*reinterpret_cast<const uint32_t *>(in_ + pos)) << nbits; pos += 4; nbits += 32; }
                 else while (nbits <= 56 && pos < in_len_) { buf |= (uint64_t)in_[pos++] << nbits; nbits += 8; }
             }
@@ -272,7 +276,6 @@ CCT_HDN inline int inflate_symbols(const uint8_t *in, int in_len, uint32_t *syms
                 buf = br.buf; nbits = br.nbits;
                 if (sym < 0) break;
             }
-            if (p >= pend) break;
             if (sym < 256) { *p++ = (uint32_t)sym; continue; }  // literal
             if (sym == 256) {
                 const int op = op0 + (int)(p - p0) + extra;
@@ -280,7 +283,7 @@ CCT_HDN inline int inflate_symbols(const uint8_t *in, int in_len, uint32_t *syms
                 break;
             }
             sym -= 257;
-            if (sym >= 29) break;
+            if (sym >= 29 || pend - p < kInfSlack) break;  // (the refills below bypass the capacity check above)
             br.buf = buf; br.nbits = nbits; br.pos = pos;
             const int len = len_base_inf(sym) + (int)br.take(len_extra_bits_inf(sym));
             const int ds = decode_symbol(br, tb.dst, kDstBits, tb.dcount, tb.dsym);

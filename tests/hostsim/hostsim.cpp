@@ -150,10 +150,10 @@ int64_t hs_deflate(const uint8_t *src, int n, uint8_t *dst, int64_t cap, int pro
 
 int hs_inflate(const uint8_t *in, int in_len, uint8_t *out, int out_cap) {
     InflateTables *tb = new InflateTables;
-    std::vector<uint32_t> syms((size_t)out_cap + 1);
+    std::vector<uint32_t> syms((size_t)out_cap + kInfSlack);
     int out_len = 0;
     uint32_t want = 0;
-    int ns = inflate_symbols(in, in_len, syms.data(), out_cap + 1, out_cap, *tb, &out_len, &want);
+    int ns = inflate_symbols(in, in_len, syms.data(), out_cap + kInfSlack, out_cap, *tb, &out_len, &want);
     delete tb;
     if (ns < 0) return -1;
     lz_expand(syms.data(), ns, out);
