@@ -101,34 +101,7 @@ __global__ void __launch_bounds__(32 * kLzWarps) k_lz_expand(const uint32_t *__r
         }
         const int pos = base + incl - len;
         if (len && !dist) o[pos] = (uint8_t)s;
-        // matches whose source lies entirely before this group depend on nothing written here: their bytes are
-        // laid end to end and copied by all lanes at once (the owner of byte t is found with shuffles only)
-        const bool far = dist != 0 && dist >= len && pos - dist + len <= base;
-        const unsigned fmask = __ballot_sync(0xffffffffu, far);
-        if (fmask) {
-            int fincl = far ? len : 0;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                int t = __shfl_up_sync(0xffffffffu, fincl, d);
-                if (lane >= d) fincl += t;
-            }
-            const int ftotal = __shfl_sync(0xffffffffu, fincl, 31);
-            const int foff = fincl - (far ? len : 0);
-            for (int t0 = 0; t0 < ftotal; t0 += 32) {
-                const int t = t0 + lane;
-                int dst = -1, src = 0;
-                unsigned m = fmask;
-                while (m) {  // warp-uniform loop over the far matches of the group
-                    const int l = __ffs((int)m) - 1;
-                    m &= m - 1;
-                    const int lo = __shfl_sync(0xffffffffu, foff, l), ln = __shfl_sync(0xffffffffu, len, l);
-                    const int mp = __shfl_sync(0xffffffffu, pos, l), md = __shfl_sync(0xffffffffu, dist, l);
-                    if (t >= lo && t < lo + ln) { dst = mp + (t - lo); src = dst - md; }
-                }
-                if (dst >= 0) o[dst] = o[src];
-            }
-        }
-        unsigned mm = __ballot_sync(0xffffffffu, dist != 0 && !far);
+        unsigned mm = __ballot_sync(0xffffffffu, dist != 0);
         __syncwarp();
         while (mm) {
             const int l = __ffs((int)mm) - 1;
