@@ -208,15 +208,17 @@ __global__ void __launch_bounds__(32 * kRunWarps) k_runs(const uint8_t *__restri
 // work-queue variants that refill finished lanes from a shared counter (per lane, and in rounds of >= 8 idle
 // lanes) were measured 12 % slower -- the extra state and the refill branch cost more than the idle lanes.
 constexpr int kProbeThreads = 256;
-__global__ void __launch_bounds__(kProbeThreads, 8) k_probe(const uint8_t *__restrict__ in, int64_t in_stride,
+__global__ void __launch_bounds__(kProbeThreads, 8) k_probe(const uint8_t *__restrict__ in, uint32_t in_stride,
                                                             const int32_t *__restrict__ in_len, const ChainRec *__restrict__ recs,
-                                                            uint32_t *__restrict__ mlo, uint32_t *__restrict__ mhi, int64_t stride) {
-    const int stream = blockIdx.y;
+                                                            uint32_t *__restrict__ mlo, uint32_t *__restrict__ mhi, uint32_t stride) {
+    // strides are 32-bit so that re-deriving a per-stream pointer (the kernel runs at 32 registers and the
+    // compiler rematerialises them inside the walk) is one wide multiply-add
+    const uint32_t stream = blockIdx.y;
     const int n = in_len[stream];
     const int s = blockIdx.x * kProbeThreads + threadIdx.x;
     if (s >= n) return;
-    const int64_t o = (int64_t)stream * stride;
-    LzView v{in + (int64_t)stream * in_stride, recs + o, n};
+    const uint64_t o = (uint64_t)stream * stride;
+    LzView v{in + (uint64_t)stream * in_stride, recs + o, n};
     uint32_t lo, hi;
     match_probe(v, s, kProbeK, &lo, &hi);
     mlo[o + s] = lo;
@@ -515,7 +517,7 @@ void launch_deflate(const uint8_t *in, int64_t in_stride, const int32_t *in_len,
     }
     dim3 gp((unsigned)((max_len + kProbeThreads - 1) / kProbeThreads), (unsigned)B);
     { CCT_KERNEL(k_probe, st);
-    k_probe<<<gp, kProbeThreads, 0, st>>>(in, in_stride, in_len, ws.recs, ws.mtab, ws.mhi, ws.stride);
+    k_probe<<<gp, kProbeThreads, 0, st>>>(in, (uint32_t)in_stride, in_len, ws.recs, ws.mtab, ws.mhi, (uint32_t)ws.stride);
     }
     { CCT_KERNEL(m_zero_flag, st); cudaMemsetAsync(ws.flag, 0, (size_t)B * ws.stride, st); }
     dim3 gw((unsigned)((ws.max_win + 127) / 128), (unsigned)B);
