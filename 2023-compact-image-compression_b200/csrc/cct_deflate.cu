@@ -13,6 +13,8 @@
 //   k_offsets / k_copy   .cct header + stream -> caller's arena at scanned offsets
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include "cct_kernels.h"
 #include "deflate_core.cuh"
 
@@ -54,28 +56,89 @@ size_t deflate_ws_carve(DeflateWs *ws, void *mem, int B, int64_t max_len) {
 
 // ------------------------------------------------------------------ k_chains / k_runs
 // k_chains: distance from every position to the previous position with the same 3-byte hash (zlib's prev[]),
-// one warp per stream, 32 positions per step.  The 32768-entry head table (low 16 bits of the latest position
-// per hash) lives in shared memory; entries are kept unambiguous by a sweep every 8192 positions that re-parks
-// everything older than 32767 at "49152 behind".  (A global-memory table with every stream resident was
+// one CTA per stream.  The 32768-entry head table (low 16 bits of the latest position per hash) lives in shared
+// memory, split by hash class between the CTA's warps; entries are kept unambiguous by a sweep every 8192
+// positions that re-parks everything older than 32767 at "49152 behind".  (A global-memory table with every stream resident was
 // measured 3.4x slower: 268 MB of randomly accessed tables do not fit the 126 MB L2.)
 // k_runs: per position, the count of equal bytes before and after it (forward and reverse sweep with a carry),
 // assembled with the link and the first two bytes into the 8-byte ChainRec the chain walks load.
 constexpr int kHeadEntries = 32768;
-__global__ void __launch_bounds__(32) k_chains(const uint8_t *__restrict__ in, int64_t in_stride,
-                                               const int32_t *__restrict__ in_len, uint16_t *__restrict__ dist16,
-                                               int64_t stride) {
-    extern __shared__ uint16_t head[];
-    const int stream = blockIdx.x, lane = threadIdx.x;
+constexpr int kChainWarps = 4;  // hash classes = warps per stream
+constexpr int kRing = 64;       // pending positions per warp
+
+struct ChainSmem {
+    uint8_t stage[kChainWarps][136];
+    uint32_t ring_s[kChainWarps][kRing];
+    uint16_t ring_h[kChainWarps][kRing];
+};
+
+// One table step for up to 32 pending positions of one hash class (cnt lanes active, positions increasing):
+// previous position with the same hash = the nearest lower lane holding it, else the head table; the latest
+// position of every hash ends up in the table.  Same-hash lanes inside a batch are found without a full match:
+// either every lane has one hash (a run), or all hashes are distinct -- detected by letting every lane store its
+// position and read the slot back -- or, rarely, the general case (__match_any_sync is a software loop here).
+__device__ __forceinline__ void chain_batch(uint16_t *__restrict__ tab, uint16_t *__restrict__ d16, int lane, int cnt,
+                                            uint32_t s, uint32_t h) {
+    const bool valid = lane < cnt;
+    const unsigned vmask = cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u);
+    if (!valid) h = 0x8000u | (uint32_t)lane;  // unique key for idle lanes
+    int dist = 0;
+    uint32_t old = 0;
+    if (valid) old = tab[h];
+    const uint32_t h0 = __shfl_sync(0xffffffffu, h, 0);
+    const bool uniform = __ballot_sync(0xffffffffu, valid && h == h0) == vmask;
+    unsigned peers;
+    __syncwarp();
+    if (uniform) {
+        peers = vmask;
+        if (valid && (vmask >> lane) == 1u) tab[h] = (uint16_t)s;
+    } else {
+        if (valid) tab[h] = (uint16_t)s;
+        __syncwarp();
+        const bool lost = valid && tab[h] != (uint16_t)s;
+        if (__ballot_sync(0xffffffffu, lost) == 0u) peers = 1u << lane;  // all distinct: every lane owns its slot
+        else {
+            peers = __match_any_sync(0xffffffffu, h);
+            __syncwarp();
+            if (valid && (peers >> lane) == 1u) tab[h] = (uint16_t)s;  // the latest position wins
+        }
+    }
+    const unsigned lower = peers & ((1u << lane) - 1u);
+    const uint32_t s_low = __shfl_sync(0xffffffffu, s, lower ? 31 - __clz((int)lower) : 0);
+    if (valid) {
+        uint32_t d = lower ? s - s_low : ((s - old) & 0xFFFFu);
+        if (lower ? d >= 32768u : (d < 1u || d >= 32768u)) d = 0;
+        dist = (int)d;
+        d16[s] = (uint16_t)dist;
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(32 * kChainWarps) k_chains(const uint8_t *__restrict__ in, int64_t in_stride,
+                                                             const int32_t *__restrict__ in_len, uint16_t *__restrict__ dist16,
+                                                             int64_t stride) {
+    // One CTA per stream; warp k owns the hashes with (h & 3) == k and a quarter of the head table.  Every warp
+    // scans the whole payload (cheap: staged bytes, one hash per lane), keeps the positions of its own class in a
+    // small ring, and runs the table step on 32 of them at a time.  Classes never interact, so the four warps
+    // need no synchronisation -- four times the warps per SM of a single-warp scan with the same 64 KB of tables.
+    extern __shared__ __align__(16) unsigned char chain_raw[];
+    uint16_t *head = reinterpret_cast<uint16_t *>(chain_raw);
+    ChainSmem &sm = *reinterpret_cast<ChainSmem *>(chain_raw + kHeadEntries * sizeof(uint16_t));
+    const int stream = blockIdx.x, lane = threadIdx.x & 31, k = threadIdx.x >> 5;
     const int n = in_len[stream];
     const uint8_t *w = in + (int64_t)stream * in_stride;
     uint16_t *d16 = dist16 + (int64_t)stream * stride;
-    uint32_t *head32 = reinterpret_cast<uint32_t *>(head);
-    for (int i = lane; i < kHeadEntries / 2; i += 32) head32[i] = 0x40004000u;  // (0 - 49152) & 0xFFFF
+    uint16_t *tab = head + k * (kHeadEntries / kChainWarps);
+    uint32_t *tab32 = reinterpret_cast<uint32_t *>(tab);
+    constexpr int kTabWords = kHeadEntries / kChainWarps / 2;
+    for (int i = lane; i < kTabWords; i += 32) tab32[i] = 0x40004000u;  // (0 - 49152) & 0xFFFF
+    uint8_t *stage = sm.stage[k];
+    uint32_t *stage32 = reinterpret_cast<uint32_t *>(stage);
+    uint32_t *ring_s = sm.ring_s[k];
+    uint16_t *ring_h = sm.ring_h[k];
     __syncwarp();
     // The payload is staged 128 positions at a time: stage[i] = w[cbase - 4 + i], i in [0, 136), fetched two
-    // chunks ahead into registers so the dependent part of the loop only touches shared memory.
-    __shared__ __align__(16) uint8_t stage[136];
-    uint32_t *stage32 = reinterpret_cast<uint32_t *>(stage);
+    // chunks ahead into registers.
     const uint32_t *w32 = reinterpret_cast<const uint32_t *>(w);  // stream base is 16-byte aligned
     const int n_words = (n + 3) >> 2;
     auto fetch = [&](int cbase, int j) -> uint32_t {  // word j of the chunk starting at cbase
@@ -84,6 +147,7 @@ __global__ void __launch_bounds__(32) k_chains(const uint8_t *__restrict__ in, i
     };
     uint32_t p0 = fetch(0, lane), p0x = lane < 2 ? fetch(0, 32 + lane) : 0u;
     uint32_t p1 = fetch(128, lane), p1x = lane < 2 ? fetch(128, 32 + lane) : 0u;
+    int wr = 0, rd = 0;  // ring write / read cursors (warp-uniform)
     for (int cbase = 0; cbase < n; cbase += 128) {
         stage32[lane] = p0;
         if (lane < 2) stage32[32 + lane] = p0x;
@@ -91,76 +155,47 @@ __global__ void __launch_bounds__(32) k_chains(const uint8_t *__restrict__ in, i
         p1 = fetch(cbase + 256, lane);
         p1x = lane < 2 ? fetch(cbase + 256, 32 + lane) : 0u;
         __syncwarp();
-        if (cbase && (cbase & 8191) == 0) {  // sweep: re-park entries older than 32767 (128 divides 8192)
+        if (cbase && (cbase & 8191) == 0) {
+            // sweep: flush what is pending (so the table reflects every position below cbase), then re-park the
+            // entries older than 32767 at "49152 behind" to keep the 16-bit positions unambiguous
+            if (wr != rd) {
+                const int cnt = wr - rd;
+                chain_batch(tab, d16, lane, cnt, ring_s[(rd + lane) & (kRing - 1)], ring_h[(rd + lane) & (kRing - 1)]);
+                rd = wr;
+            }
             const uint32_t far = (uint32_t)(cbase - 49152) & 0xFFFFu;
-            for (int i = lane; i < kHeadEntries / 2; i += 32) {
-                uint32_t v = head32[i];
+            for (int i = lane; i < kTabWords; i += 32) {
+                uint32_t v = tab32[i];
                 uint32_t lo = v & 0xFFFFu, hi = v >> 16;
                 if (((uint32_t)(cbase - lo) & 0xFFFFu) >= 32768u) lo = far;
                 if (((uint32_t)(cbase - hi) & 0xFFFFu) >= 32768u) hi = far;
-                head32[i] = lo | (hi << 16);
+                tab32[i] = lo | (hi << 16);
             }
             __syncwarp();
         }
-        // phase A (independent of the head table, so the four groups of the chunk overlap): hashes, validity,
-        // equal-to-previous flags
-        uint32_t hh[4];
-        unsigned vm[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const int s = cbase + 32 * j + lane;
-            const uint8_t *sb = stage + 4 + 32 * j + lane;  // sb[k] = w[s + k], k in [-1, 2]
+            const uint8_t *sb = stage + 4 + 32 * j + lane;  // sb[i] = w[s + i]
             const bool valid = s >= 1 && s + 2 < n;         // position 0 doubles as NIL in zlib: never a match source
-            hh[j] = valid ? hash3(sb) : (0x8000u | (uint32_t)lane);
-            vm[j] = __ballot_sync(0xffffffffu, valid);
-        }
-        // phase B: table lookups / insertions, group after group
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int s = cbase + 32 * j + lane;
-            if (cbase + 32 * j >= n) break;
-            const uint32_t h = hh[j];
-            const unsigned vmask = vm[j];
-            const bool valid = (vmask >> lane) & 1u;
-            // previous position with the same hash: the nearest lower lane holding it, else the head table.
-            // Same-hash lanes inside one group are found without a full match: either every inserting lane has
-            // one hash (a run), or all hashes are distinct -- detected by letting every lane store its position
-            // and read the slot back -- or, rarely, the general case (__match_any_sync is a software loop here).
-            int dist = 0;
-            uint32_t old = 0;
-            if (valid) old = head[h];
-            const int first = __ffs((int)vmask) - 1;
-            const uint32_t h0 = __shfl_sync(0xffffffffu, h, first < 0 ? 0 : first);
-            const bool uniform = vmask && __ballot_sync(0xffffffffu, valid && h == h0) == vmask;
-            __syncwarp();
-            if (uniform) {
-                if (valid) {
-                    const unsigned lower = vmask & ((1u << lane) - 1u);
-                    if (lower) dist = lane - (31 - __clz((int)lower));
-                    else { uint32_t d = (uint32_t)(s - old) & 0xFFFFu; dist = (d >= 1u && d < 32768u) ? (int)d : 0; }
-                    if ((vmask >> lane) == 1u) head[h] = (uint16_t)s;
-                }
-            } else {
-                if (valid) head[h] = (uint16_t)s;
-                __syncwarp();
-                const bool lost = valid && head[h] != (uint16_t)s;
-                if (__ballot_sync(0xffffffffu, lost) == 0u) {  // all distinct: every lane owns its slot
-                    if (valid) { uint32_t d = (uint32_t)(s - old) & 0xFFFFu; dist = (d >= 1u && d < 32768u) ? (int)d : 0; }
-                } else {
-                    const unsigned peers = __match_any_sync(0xffffffffu, h);
-                    const unsigned lower = peers & ((1u << lane) - 1u);
-                    if (valid) {
-                        if (lower) dist = lane - (31 - __clz((int)lower));
-                        else { uint32_t d = (uint32_t)(s - old) & 0xFFFFu; dist = (d >= 1u && d < 32768u) ? (int)d : 0; }
-                    }
-                    __syncwarp();
-                    if (valid && (peers >> lane) == 1u) head[h] = (uint16_t)s;  // the latest position wins
-                }
+            const uint32_t h = valid ? hash3(sb) : 0u;
+            const bool mine = valid && (h & (kChainWarps - 1)) == (uint32_t)k;
+            const unsigned bal = __ballot_sync(0xffffffffu, mine);
+            if (mine) {
+                const int slot = (wr + __popc(bal & ((1u << lane) - 1u))) & (kRing - 1);
+                ring_s[slot] = (uint32_t)s;
+                ring_h[slot] = (uint16_t)(h >> 2);
             }
-            if (s < n) d16[s] = (uint16_t)dist;
+            if (!valid && s < n && k == 0) d16[s] = 0;
+            wr += __popc(bal);
             __syncwarp();
+            if (wr - rd >= 32) {
+                chain_batch(tab, d16, lane, 32, ring_s[(rd + lane) & (kRing - 1)], ring_h[(rd + lane) & (kRing - 1)]);
+                rd += 32;
+            }
         }
     }
+    if (wr != rd) chain_batch(tab, d16, lane, wr - rd, ring_s[(rd + lane) & (kRing - 1)], ring_h[(rd + lane) & (kRing - 1)]);
 }
 
 constexpr int kRunWarps = 4;
@@ -215,14 +250,15 @@ __global__ void __launch_bounds__(kProbeThreads, 8) k_probe(const uint8_t *__res
     // compiler rematerialises them inside the walk) is one wide multiply-add
     const uint32_t stream = blockIdx.y;
     const int n = in_len[stream];
-    const int s = blockIdx.x * kProbeThreads + threadIdx.x;
-    if (s >= n) return;
     const uint64_t o = (uint64_t)stream * stride;
     LzView v{in + (uint64_t)stream * in_stride, recs + o, n};
-    uint32_t lo, hi;
-    match_probe(v, s, kProbeK, &lo, &hi);
-    mlo[o + s] = lo;
-    mhi[o + s] = hi;
+    // the grid covers the worst-case payload length; CTAs stride over the real one
+    for (int s = blockIdx.x * kProbeThreads + threadIdx.x; s < n; s += gridDim.x * kProbeThreads) {
+        uint32_t lo, hi;
+        match_probe(v, s, kProbeK, &lo, &hi);
+        mlo[o + s] = lo;
+        mhi[o + s] = hi;
+    }
 }
 
 // ------------------------------------------------------------------ parse: k_walk_spec / k_walk_stitch / k_symscan
@@ -503,19 +539,19 @@ void launch_deflate(const uint8_t *in, int64_t in_stride, const int32_t *in_len,
                     int64_t out_stride, int32_t *out_len, const DeflateWs &ws, cudaStream_t st) {
     if (B == 0) return;
     static bool attr_done = false;
-    const int chain_smem = kHeadEntries * (int)sizeof(uint16_t);
+    const int chain_smem = kHeadEntries * (int)sizeof(uint16_t) + (int)sizeof(ChainSmem);
     if (!attr_done) {
         cudaFuncSetAttribute(k_chains, cudaFuncAttributeMaxDynamicSharedMemorySize, chain_smem);
         cudaFuncSetAttribute(k_block_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlockBuildSmem));
         attr_done = true;
     }
     { CCT_KERNEL(k_chains, st);
-    k_chains<<<B, 32, chain_smem, st>>>(in, in_stride, in_len, ws.dist16, ws.stride);
+    k_chains<<<B, 32 * kChainWarps, chain_smem, st>>>(in, in_stride, in_len, ws.dist16, ws.stride);
     }
     { CCT_KERNEL(k_runs, st);
     k_runs<<<(B + kRunWarps - 1) / kRunWarps, 32 * kRunWarps, 0, st>>>(in, in_stride, in_len, ws.dist16, ws.rb16, ws.recs, ws.stride, B);
     }
-    dim3 gp((unsigned)((max_len + kProbeThreads - 1) / kProbeThreads), (unsigned)B);
+    dim3 gp((unsigned)std::min<int64_t>((max_len + kProbeThreads - 1) / kProbeThreads, 512), (unsigned)B);
     { CCT_KERNEL(k_probe, st);
     k_probe<<<gp, kProbeThreads, 0, st>>>(in, (uint32_t)in_stride, in_len, ws.recs, ws.mtab, ws.mhi, (uint32_t)ws.stride);
     }
