@@ -418,6 +418,15 @@ int cct_deflate_batch(const uint8_t *d_in, size_t in_stride, const int32_t *d_in
     return CCT_OK;
 }
 
+int cct_debug_chains(const uint8_t *d_in, size_t in_stride, const int32_t *d_in_len, int B, uint16_t *d_dist16,
+                     size_t stride, void *stream) {
+    if (B < 0 || (B > 0 && (!d_in || !d_in_len || !d_dist16)) || in_stride % 16) return CCT_E_ARG;
+    if (cct_device_count() == 0) return CCT_E_NO_DEVICE;
+    launch_chains(d_in, (int64_t)in_stride, d_in_len, B, d_dist16, (int64_t)stride, (cudaStream_t)stream);
+    CK(cudaGetLastError());
+    return CCT_OK;
+}
+
 size_t cct_inflate_workspace_bytes(int B, size_t out_stride) {
     InflateWs iw;
     return inflate_ws_carve(&iw, nullptr, std::max(B, 1), (int64_t)out_stride);

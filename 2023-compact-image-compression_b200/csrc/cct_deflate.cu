@@ -77,8 +77,8 @@ struct ChainSmem {
 // position of every hash ends up in the table.  Same-hash lanes inside a batch are found without a full match:
 // either every lane has one hash (a run), or all hashes are distinct -- detected by letting every lane store its
 // position and read the slot back -- or, rarely, the general case (__match_any_sync is a software loop here).
-__device__ __forceinline__ void chain_batch(uint16_t *__restrict__ tab, uint16_t *__restrict__ d16, int lane, int cnt,
-                                            uint32_t s, uint32_t h) {
+__device__ __forceinline__ void chain_batch(volatile uint16_t *tab, uint16_t *d16, int lane, int cnt, uint32_t s, uint32_t h) {
+    // `tab` is volatile on purpose: the read-back below must see what the OTHER lanes stored to the same slot
     const bool valid = lane < cnt;
     const unsigned vmask = cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u);
     if (!valid) h = 0x8000u | (uint32_t)lane;  // unique key for idle lanes
@@ -533,6 +533,16 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(const uint8_t *__restrict
     }
     if (tid == 0)  // END_BLOCK closes the block
         or_bits(out32, bit_start + (uint64_t)hdr_bits + d.body_bits - llen[256], lcode[256], llen[256]);
+}
+
+void launch_chains(const uint8_t *in, int64_t in_stride, const int32_t *in_len, int B, uint16_t *dist16, int64_t stride,
+                   cudaStream_t st) {
+    if (B == 0) return;
+    const int chain_smem = kHeadEntries * (int)sizeof(uint16_t) + (int)sizeof(ChainSmem);
+    cudaFuncSetAttribute(k_chains, cudaFuncAttributeMaxDynamicSharedMemorySize, chain_smem);
+    { CCT_KERNEL(k_chains, st);
+    k_chains<<<B, 32 * kChainWarps, chain_smem, st>>>(in, in_stride, in_len, dist16, stride);
+    }
 }
 
 void launch_deflate(const uint8_t *in, int64_t in_stride, const int32_t *in_len, int B, int64_t max_len, uint8_t *out,

@@ -60,6 +60,10 @@ size_t deflate_ws_carve(DeflateWs *ws, void *mem, int B, int64_t max_len);
 void launch_deflate(const uint8_t *in, int64_t in_stride, const int32_t *in_len, int B, int64_t max_len, uint8_t *out,
                     int64_t out_stride, int32_t *out_len, const DeflateWs &ws, cudaStream_t st);
 
+// chain links only (stage tap): dist16[i*stride + p] for stream i
+void launch_chains(const uint8_t *in, int64_t in_stride, const int32_t *in_len, int B, uint16_t *dist16, int64_t stride,
+                   cudaStream_t st);
+
 // ---- cct_decode.cu
 struct InflateWs {
     uint32_t *syms;      // [B][sym_stride] LZ77 symbols of each stream

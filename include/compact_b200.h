@@ -134,6 +134,10 @@ size_t cct_deflate_workspace_bytes(int B, size_t max_len);
 size_t cct_deflate_bound(size_t len);
 int cct_deflate_batch(const uint8_t *d_in, size_t in_stride, const int32_t *d_in_len, int B, size_t max_len,
                       uint8_t *d_out, size_t out_stride, int32_t *d_out_len, void *d_ws, size_t ws_bytes, void *stream);
+/* Stage tap: zlib's hash-chain links.  d_dist16[i*stride + p] = distance from position p of string i to the previous
+ * position with the same 3-byte hash (0 = none or >= 32768; position 0 is never a source). */
+int cct_debug_chains(const uint8_t *d_in, size_t in_stride, const int32_t *d_in_len, int B, uint16_t *d_dist16,
+                     size_t stride, void *stream);
 /* RFC 1950 inflate of B streams (any conformant zlib stream). d_status[i] gets CCT_ST_INFLATE on error
  * (invalid code, output longer than out_stride, truncated input, Adler-32 mismatch). */
 size_t cct_inflate_workspace_bytes(int B, size_t out_stride);

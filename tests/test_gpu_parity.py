@@ -329,3 +329,41 @@ def test_config_batch_roundtrip_4096(torch_cuda, pkg, synth, oracle):
     px, dst = pkg.decode_batch(arena, offsets, (512, 512))
     assert not dst.cpu().numpy().any()
     assert torch_cuda.equal(px.view(torch_cuda.int16), d_imgs)
+
+
+def _ref_chain_links(data: bytes):
+    """zlib's prev[] as distances: previous position with the same hash, position 0 excluded."""
+    w = np.frombuffer(data, dtype=np.uint8).astype(np.int64)
+    n = len(w)
+    out = np.zeros(n, dtype=np.uint16)
+    head = {}
+    for s in range(0, n - 2):
+        h = int(((w[s] << 10) ^ (w[s + 1] << 5) ^ w[s + 2]) & 0x7FFF)
+        p = head.get(h, 0)
+        if p and s - p < 32768:
+            out[s] = s - p
+        head[h] = s
+    return out
+
+
+def test_stage_chain_links(torch_cuda, native):
+    rng = np.random.default_rng(3)
+    blobs = [rng.integers(0, a, size=n, dtype=np.uint8).tobytes() for a in (2, 3, 16, 256) for n in (100, 5000, 40000)]
+    blobs += [bytes(9000) + rng.integers(0, 4, size=3000, dtype=np.uint8).tobytes() + bytes(70000) + b"abc" * 500]
+    L = native.lib()
+    B = len(blobs)
+    stride = (max(len(b) for b in blobs) + 31) // 16 * 16
+    h_in = np.zeros((B, stride), dtype=np.uint8)
+    for i, b in enumerate(blobs):
+        h_in[i, :len(b)] = np.frombuffer(b, dtype=np.uint8)
+    d_in = _dev(torch_cuda, h_in)
+    d_len = _dev(torch_cuda, np.array([len(b) for b in blobs], dtype=np.int32))
+    d_out = torch_cuda.zeros((B, stride), dtype=torch_cuda.int16, device="cuda")
+    native.check(L.cct_debug_chains(d_in.data_ptr(), stride, d_len.data_ptr(), B, d_out.data_ptr(), stride,
+                                    torch_cuda.cuda.current_stream().cuda_stream))
+    torch_cuda.cuda.synchronize()
+    got = d_out.cpu().numpy().view(np.uint16)
+    for i, b in enumerate(blobs):
+        want = _ref_chain_links(b)
+        bad = np.nonzero(got[i, :len(b)] != want)[0]
+        assert len(bad) == 0, (i, len(b), bad[:8], got[i, bad[:8]], want[bad[:8]])
