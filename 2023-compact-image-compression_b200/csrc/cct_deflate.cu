@@ -198,41 +198,127 @@ __global__ void __launch_bounds__(32 * kChainWarps) k_chains(const uint8_t *__re
     if (wr != rd) chain_batch(tab, d16, lane, wr - rd, ring_s[(rd + lane) & (kRing - 1)], ring_h[(rd + lane) & (kRing - 1)]);
 }
 
-constexpr int kRunWarps = 4;
-__global__ void __launch_bounds__(32 * kRunWarps) k_runs(const uint8_t *__restrict__ in, int64_t in_stride,
-                                                         const int32_t *__restrict__ in_len, const uint16_t *__restrict__ dist16,
-                                                         uint16_t *__restrict__ rb16, ChainRec *__restrict__ recs_all,
-                                                         int64_t stride, int B) {
-    const int stream = blockIdx.x * kRunWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (stream >= B) return;
+// Run lengths around every position: rb[p] / rl[p] = number of bytes equal to w[p] immediately before / after p.
+// One CTA per stream; a tile is kRunThreads x kRunPer positions, each thread owns kRunPer consecutive ones.  Inside
+// a thread the counts are a running counter; across threads the value entering a segment comes from a scan with
+// the operator (whole, val) o (whole', val') = whole' ? (whole, val + val') : (false, val')  -- "the run covers my
+// whole segment, so pass on what came in plus my length" -- and across tiles from a carried scalar.
+constexpr int kRunThreads = 256;
+constexpr int kRunPer = 16;
+constexpr int kRunTile = kRunThreads * kRunPer;
+
+struct RunCarry { int whole, val; };
+__device__ __forceinline__ RunCarry run_combine(RunCarry a, RunCarry b) {  // a = earlier part, b = later part
+    return b.whole ? RunCarry{a.whole, a.val + b.val} : RunCarry{0, b.val};
+}
+
+// Block-wide exclusive scan of `mine` in thread order (or reverse thread order): returns what enters this thread's
+// segment, given `carry` entering the tile; *tile_out = what leaves the tile.
+template <bool REVERSE>
+__device__ __forceinline__ int run_scan(RunCarry mine, int carry, RunCarry *warp_tot, int *tile_out) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int vl = REVERSE ? 31 - lane : lane;            // position of this lane in scan order
+    RunCarry incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        RunCarry o;
+        const int src = REVERSE ? lane + d : lane - d;
+        o.whole = __shfl_sync(0xffffffffu, incl.whole, src & 31);
+        o.val = __shfl_sync(0xffffffffu, incl.val, src & 31);
+        if (vl >= d) incl = run_combine(o, incl);
+    }
+    if (vl == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    const int nw = kRunThreads / 32;
+    RunCarry before{1, carry};                            // everything that precedes this warp in scan order
+    RunCarry all{1, carry};
+    for (int q = 0; q < nw; q++) {
+        const int w = REVERSE ? nw - 1 - q : q;
+        if (REVERSE ? w > wid : w < wid) before = run_combine(before, warp_tot[w]);
+        all = run_combine(all, warp_tot[w]);
+    }
+    RunCarry excl;                                        // exclusive within the warp
+    const int src = REVERSE ? lane + 1 : lane - 1;
+    excl.whole = __shfl_sync(0xffffffffu, incl.whole, src & 31);
+    excl.val = __shfl_sync(0xffffffffu, incl.val, src & 31);
+    const RunCarry in = vl == 0 ? before : run_combine(before, excl);
+    *tile_out = all.val;
+    __syncthreads();
+    return in.val;
+}
+
+__global__ void __launch_bounds__(kRunThreads) k_runs(const uint8_t *__restrict__ in, int64_t in_stride,
+                                                      const int32_t *__restrict__ in_len, const uint16_t *__restrict__ dist16,
+                                                      uint16_t *__restrict__ rb16, ChainRec *__restrict__ recs_all,
+                                                      int64_t stride) {
+    const int stream = blockIdx.x, tid = threadIdx.x;
     const int n = in_len[stream];
     const uint8_t *w = in + (int64_t)stream * in_stride;
     const uint16_t *d16 = dist16 + (int64_t)stream * stride;
     uint16_t *rb = rb16 + (int64_t)stream * stride;
     ChainRec *recs = recs_all + (int64_t)stream * stride;
-    int carry = 0;  // count of the position just before the group
-    for (int base = 0; base < n; base += 32) {
-        const int s = base + lane;
-        const bool eq = s >= 1 && s < n && w[s] == w[s - 1];
-        const unsigned em = __ballot_sync(0xffffffffu, eq);
-        const unsigned zeros_below = ~em & ((2u << lane) - 1u);  // positions <= lane whose flag is 0
-        int back = zeros_below ? lane - (31 - __clz((int)zeros_below)) : lane + 1 + carry;
-        if (back > 65535) back = 65535;
-        carry = __shfl_sync(0xffffffffu, back, 31);
-        if (s < n) rb[s] = (uint16_t)back;
+    __shared__ RunCarry warp_tot[kRunThreads / 32];
+    __shared__ uint8_t sb[kRunTile + 4];    // sb[i] = w[base - 1 + i]
+    __shared__ uint16_t sv[kRunTile];       // counts of the tile, so that global traffic stays coalesced
+    // forward: rb.  For a segment, (whole, val) = (all positions equal their predecessor, count at the last position
+    // assuming 0 came in).
+    int carry = 0;  // rb of the position just before the tile
+    for (int base = 0; base < n; base += kRunTile) {
+        for (int i = tid; i < kRunTile + 3; i += kRunThreads) { const int p = base - 1 + i; sb[i] = (p >= 0 && p < n) ? w[p] : 0; }
+        __syncthreads();
+        const int q0 = tid * kRunPer, p0 = base + q0;
+        int cnt = 0, whole = 1;
+        int local[kRunPer];
+#pragma unroll
+        for (int i = 0; i < kRunPer; i++) {
+            const bool eq = p0 + i >= 1 && p0 + i < n && sb[q0 + i + 1] == sb[q0 + i];
+            if (eq) cnt++; else { cnt = 0; whole = 0; }
+            local[i] = cnt;
+        }
+        int tile_out;
+        const int enter = run_scan<false>(RunCarry{whole, cnt}, carry, warp_tot, &tile_out);
+        bool lead = true;  // still inside the run that entered the segment
+#pragma unroll
+        for (int i = 0; i < kRunPer; i++) {
+            lead = lead && local[i] == i + 1;
+            const int v = local[i] + (lead ? enter : 0);
+            sv[q0 + i] = (uint16_t)(v > 65535 ? 65535 : v);
+        }
+        __syncthreads();
+        for (int i = tid; i < kRunTile && base + i < n; i += kRunThreads) rb[base + i] = sv[i];
+        carry = tile_out > 65535 ? 65535 : tile_out;
+        __syncthreads();
     }
-    __syncwarp();
-    carry = 0;  // count of the position just after the group
-    for (int base = ((n - 1) / 32) * 32; base >= 0; base -= 32) {
-        const int s = base + lane;
-        const uint8_t c0 = s < n ? w[s] : 0, c1 = s + 1 < n ? w[s + 1] : 0, c2 = s + 2 < n ? w[s + 2] : 0;
-        const bool eq = s + 1 < n && c0 == c1;
-        const unsigned em = __ballot_sync(0xffffffffu, eq);
-        const unsigned zeros_above = ~em & ~((1u << lane) - 1u);  // positions >= lane whose flag is 0
-        int fwd = zeros_above ? (__ffs((int)zeros_above) - 1) - lane : (32 - lane) + carry;
-        if (fwd > 65535) fwd = 65535;
-        carry = __shfl_sync(0xffffffffu, fwd, 0);
-        if (s < n) recs[s] = make_rec(d16[s], fwd, rb[s], c0, c1, c2);
+    // backward: rl, and the packed record
+    carry = 0;  // rl of the position just after the tile
+    for (int base = ((n - 1) / kRunTile) * kRunTile; base >= 0; base -= kRunTile) {
+        for (int i = tid; i < kRunTile + 3; i += kRunThreads) { const int p = base - 1 + i; sb[i] = (p >= 0 && p < n) ? w[p] : 0; }
+        __syncthreads();
+        const int q0 = tid * kRunPer, p0 = base + q0;
+        int cnt = 0, whole = 1;
+        int local[kRunPer];
+#pragma unroll
+        for (int i = kRunPer - 1; i >= 0; i--) {
+            const bool eq = p0 + i + 1 < n && sb[q0 + i + 1] == sb[q0 + i + 2];
+            if (eq) cnt++; else { cnt = 0; whole = 0; }
+            local[i] = cnt;
+        }
+        int tile_out;
+        const int enter = run_scan<true>(RunCarry{whole, cnt}, carry, warp_tot, &tile_out);
+        bool lead = true;
+#pragma unroll
+        for (int i = kRunPer - 1; i >= 0; i--) {
+            lead = lead && local[i] == kRunPer - i;
+            const int v = local[i] + (lead ? enter : 0);
+            sv[q0 + i] = (uint16_t)(v > 65535 ? 65535 : v);
+        }
+        __syncthreads();
+        for (int i = tid; i < kRunTile && base + i < n; i += kRunThreads) {
+            const int p = base + i;
+            recs[p] = make_rec(d16[p], sv[i], rb[p], sb[i + 1], sb[i + 2], sb[i + 3]);
+        }
+        carry = tile_out > 65535 ? 65535 : tile_out;
+        __syncthreads();
     }
 }
 
@@ -559,7 +645,7 @@ void launch_deflate(const uint8_t *in, int64_t in_stride, const int32_t *in_len,
     k_chains<<<B, 32 * kChainWarps, chain_smem, st>>>(in, in_stride, in_len, ws.dist16, ws.stride);
     }
     { CCT_KERNEL(k_runs, st);
-    k_runs<<<(B + kRunWarps - 1) / kRunWarps, 32 * kRunWarps, 0, st>>>(in, in_stride, in_len, ws.dist16, ws.rb16, ws.recs, ws.stride, B);
+    k_runs<<<B, kRunThreads, 0, st>>>(in, in_stride, in_len, ws.dist16, ws.rb16, ws.recs, ws.stride);
     }
     dim3 gp((unsigned)std::min<int64_t>((max_len + kProbeThreads - 1) / kProbeThreads, 512), (unsigned)B);
     { CCT_KERNEL(k_probe, st);
