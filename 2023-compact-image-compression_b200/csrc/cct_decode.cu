@@ -53,29 +53,141 @@ struct StreamSrc {  // where stream i lives: arena + offsets (with a header to s
     __device__ int size(int i) const { return (off ? (int)(off[i + 1] - off[i]) : len[i]) - skip; }
 };
 
-// One stream per warp (lane 0 decodes), kInfWarps warps per CTA.  Sharing a warp between 2-32 streams was
-// measured slower in every form tried (nested loops never reconverge; a flat state machine and a lock-step
-// symbol loop reconverge but execute both sides of every literal/match/refill branch): the bit-serial decoder
-// is bound by the number of warp instructions issued, and one lane per warp issues the fewest.
-constexpr int kInfWarps = 4;
+// One stream per warp, all lanes decoding (inflate_core.cuh, "Lane-parallel Huffman decode"); kInfWarps warps
+// per CTA, each with its own tables and staging area in shared memory.
+constexpr int kInfWarps = 2;
+constexpr unsigned kFull = 0xffffffffu;
+
+struct StreamBits {  // the stream as aligned 32-bit words; positions are bits from the aligned origin
+    const uint8_t *in; int in_len;       // zlib stream (header, deflate data, Adler-32)
+    const uint32_t *words; uint32_t skew;  // words = in rounded down to 4 bytes, skew = bits between them
+    __device__ __forceinline__ uint32_t word(uint32_t w) const {
+        const uint8_t *b = reinterpret_cast<const uint8_t *>(words + w);
+        if (b >= in && b + 4 <= in + in_len) return __ldg(words + w);
+        uint32_t v = 0;  // the first and last few bytes: only what belongs to the stream, zeros elsewhere
+        for (int k = 0; k < 4; k++) if (b + k >= in && b + k < in + in_len) v |= (uint32_t)b[k] << (8 * k);
+        return v;
+    }
+};
+
+// Warp-cooperative construction of one code's tables from tb.lens[first .. first + nsym).
+__device__ __forceinline__ bool warp_build_code(FastTables &tb, int first, int nsym, bool lit, int lane) {
+    FastCanon &c = lit ? tb.lc : tb.dc;
+    uint16_t *syms = lit ? tb.lsym : tb.dsym;
+    if (lane < 16) c.count[lane] = 0;
+    __syncwarp();
+    fast_count(tb.lens + first, nsym, c, lane, 32);
+    __syncwarp();
+    bool ok = true;
+    if (lane == 0) {
+        ok = fast_ranges(c);
+        if (ok) fast_sort(tb.lens + first, nsym, c, syms, reinterpret_cast<uint16_t *>(tb.stage));
+    }
+    ok = __shfl_sync(kFull, ok, 0);
+    __syncwarp();
+    if (ok) fast_fill(c, syms, lit ? tb.lit : tb.dst, lit ? kFLitBits : kFDstBits, lit, lane, 32);
+    __syncwarp();
+    return ok;
+}
+
+// The symbols of one Huffman block, starting at bit `q` (a true symbol boundary).  Returns false on an error.
+__device__ __forceinline__ bool warp_block_symbols(const StreamBits &sb, uint32_t data_end, FastTables &tb, uint32_t &q,
+                                                   uint32_t *syms, int &ns, int &op, int sym_cap, int out_cap, int lane) {
+    for (;;) {
+        const uint32_t w0 = q >> 5, origin = w0 << 5;
+        for (int j = lane; j < kStageWords; j += 32) tb.stage[stage_slot(j)] = sb.word(w0 + j);
+        __syncwarp();
+        const uint32_t limit = min(q + (uint32_t)(lane + 1) * kSubBits, data_end);
+        uint32_t start = q + (uint32_t)lane * kSubBits, cur = 0xffffffffu;
+        Span r{0u, 0, 0, kSpanRun};
+        int confirmed = 0, last;
+        for (;;) {  // rounds: lanes at and after the first unconfirmed one decode from where their predecessor ended
+            if (lane >= confirmed && start != cur) { decode_span<false>(tb.stage, origin, start, limit, data_end, tb, nullptr, 0, r); cur = start; }
+            const uint32_t prev_end = __shfl_up_sync(kFull, r.end, 1);
+            const unsigned ok = __ballot_sync(kFull, lane == 0 || cur == prev_end);
+            const int c = ok == kFull ? 32 : __ffs((int)~ok) - 1;  // lanes [0, c) decoded from true boundaries
+            const unsigned stops = __ballot_sync(kFull, r.flag != kSpanRun) & (c == 32 ? kFull : ((1u << c) - 1u));
+            if (stops) { last = __ffs((int)stops) - 1; break; }  // the block (or the data) ends in a confirmed lane
+            if (c == 32) { last = 31; break; }
+            confirmed = c;
+            if (lane >= c) start = prev_end;
+        }
+        const int end_flag = __shfl_sync(kFull, r.flag, last);
+        if (end_flag == kSpanBad) return false;
+        const int n = lane <= last ? r.n : 0, bytes = lane <= last ? r.n + r.extra : 0;
+        int in_n = n, in_b = bytes;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int tn = __shfl_up_sync(kFull, in_n, d), tb_ = __shfl_up_sync(kFull, in_b, d);
+            if (lane >= d) { in_n += tn; in_b += tb_; }
+        }
+        const int tot_n = __shfl_sync(kFull, in_n, 31), tot_b = __shfl_sync(kFull, in_b, 31);
+        if (ns + tot_n > sym_cap || op + tot_b > out_cap) return false;
+        Span w{0u, 0, 0, kSpanRun};
+        if (lane <= last) decode_span<true>(tb.stage, origin, cur, limit, data_end, tb, syms + ns + in_n - n, op + in_b - bytes, w);
+        if (__ballot_sync(kFull, w.flag == kSpanFar)) return false;
+        ns += tot_n; op += tot_b;
+        q = __shfl_sync(kFull, r.end, last);
+        __syncwarp();  // the staging area is rewritten next
+        if (end_flag == kSpanEob) return q <= data_end;
+    }
+}
+
 __global__ void __launch_bounds__(32 * kInfWarps) k_inflate_sym(StreamSrc src, const uint8_t *__restrict__ fl, int B,
-                                                                uint32_t *__restrict__ syms, int64_t sym_stride, int out_cap,
+                                                                uint32_t *__restrict__ syms_all, int64_t sym_stride, int out_cap,
                                                                 int32_t *__restrict__ nsym, int32_t *__restrict__ out_len,
                                                                 uint32_t *__restrict__ adler_want, uint32_t *__restrict__ status) {
     extern __shared__ __align__(16) unsigned char tb_raw[];
-    InflateTables *tbs = reinterpret_cast<InflateTables *>(tb_raw);
-    const int warp = threadIdx.x >> 5;
-    const int i = blockIdx.x * kInfWarps + warp;
-    if ((threadIdx.x & 31) || i >= B) return;
-    nsym[i] = 0; out_len[i] = 0; adler_want[i] = 1;
+    FastTables &tb = reinterpret_cast<FastTables *>(tb_raw)[threadIdx.x >> 5];
+    const int i = blockIdx.x * kInfWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= B) return;
+    if (lane == 0) { nsym[i] = 0; out_len[i] = 0; adler_want[i] = 1; }
     if (status[i] || (fl && !(fl[i] & 4u))) return;
-    int olen = 0;
-    uint32_t want = 1;
-    const int len = src.size(i);
-    const int ns = len > 0 ? inflate_symbols(src.ptr(i), len, syms + (int64_t)i * sym_stride, (int)sym_stride, out_cap,
-                                             tbs[warp], &olen, &want) : -1;
-    if (ns < 0) { status[i] |= 16u; return; }  // CCT_ST_INFLATE
-    nsym[i] = ns; out_len[i] = olen; adler_want[i] = want;
+    const uint8_t *in = src.ptr(i);
+    const int in_len = src.size(i);
+    uint32_t *syms = syms_all + (int64_t)i * sym_stride;
+    const int sym_cap = (int)sym_stride;
+    bool good = in_len >= 6 && (in[0] & 0x0F) == 8 && (((uint32_t)in[0] << 8) | in[1]) % 31 == 0 && !(in[1] & 0x20);
+    const int dlen = in_len - 4;  // deflate data ends where the Adler-32 trailer starts
+    StreamBits sb{in, in_len, reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(in) & ~(uintptr_t)3),
+                  8u * (uint32_t)(reinterpret_cast<uintptr_t>(in) & 3u)};
+    const uint32_t data_end = sb.skew + 8u * (uint32_t)(good ? dlen : 0);
+    uint32_t bp = 16;  // bit position in the stream (after the zlib header)
+    int ns = 0, op = 0;
+    bool last = false;
+    while (good && !last) {
+        int type = -1, nlen = 0, ndist = 0;
+        if (lane == 0) {
+            BitReader br{in, dlen, 0, 0, 0, false};
+            br.seek(bp);
+            bool l = false;
+            type = inflate_block_header(br, tb, &l, &nlen, &ndist);
+            if (br.bad) type = -1;
+            last = l;
+            bp = br.tell();
+        }
+        type = __shfl_sync(kFull, type, 0); nlen = __shfl_sync(kFull, nlen, 0); ndist = __shfl_sync(kFull, ndist, 0);
+        last = __shfl_sync(kFull, (int)last, 0) != 0; bp = __shfl_sync(kFull, bp, 0);
+        __syncwarp();
+        if (type < 0) { good = false; break; }
+        if (type == 0) {  // stored: LEN bytes at a byte boundary become literal symbols
+            const int at = (int)(bp >> 3);
+            if (at + nlen > dlen || ns + nlen > sym_cap || op + nlen > out_cap) { good = false; break; }
+            for (int k = lane; k < nlen; k += 32) syms[ns + k] = in[at + k];
+            ns += nlen; op += nlen; bp += 8u * (uint32_t)nlen;
+            continue;
+        }
+        if (!warp_build_code(tb, 0, nlen, true, lane) || !warp_build_code(tb, nlen, ndist, false, lane)) { good = false; break; }
+        uint32_t q = bp + sb.skew;
+        good = warp_block_symbols(sb, data_end, tb, q, syms, ns, op, sym_cap, out_cap, lane);
+        bp = q - sb.skew;
+    }
+    if (good && (int)((bp + 7) >> 3) != dlen) good = false;  // the trailer follows the last block at the next byte boundary
+    if (lane) return;
+    if (!good) { status[i] |= 16u; return; }  // CCT_ST_INFLATE
+    const uint8_t *t = in + dlen;
+    nsym[i] = ns; out_len[i] = op;
+    adler_want[i] = ((uint32_t)t[0] << 24) | ((uint32_t)t[1] << 16) | ((uint32_t)t[2] << 8) | t[3];
 }
 
 constexpr int kLzWarps = 4;
@@ -146,7 +258,7 @@ __global__ void __launch_bounds__(256) k_adler_check(const uint8_t *__restrict__
 
 static void launch_inflate_passes(StreamSrc src, const uint8_t *fl, int B, const InflateWs &iw, uint8_t *out,
                                   int64_t out_stride, int32_t *out_len, uint32_t *status, cudaStream_t st) {
-    const int smem = kInfWarps * (int)sizeof(InflateTables);
+    const int smem = kInfWarps * (int)sizeof(FastTables);
     { CCT_KERNEL(k_inflate_sym, st);
     k_inflate_sym<<<(B + kInfWarps - 1) / kInfWarps, 32 * kInfWarps, smem, st>>>(src, fl, B, iw.syms, iw.sym_stride, (int)out_stride,
                                                                                 iw.nsym, out_len, iw.adler, status);

@@ -50,6 +50,11 @@ struct BitReader {
         }
         while (nbits <= 56 && pos < len) { buf |= (uint64_t)in[pos++] << nbits; nbits += 8; }
     }
+    CCT_HD void seek(uint32_t bitpos) {  // stand at an arbitrary bit of the stream
+        pos = (int)(bitpos >> 3); buf = 0; nbits = 0; bad = false;
+        align_input(); refill(); drop((int)(bitpos & 7u));
+    }
+    CCT_HD uint32_t tell() const { return 8u * (uint32_t)pos - (uint32_t)nbits; }
     CCT_HD uint32_t peek(int n) const { return (uint32_t)(buf & ((1ull << n) - 1)); }
     CCT_HD void drop(int n) { buf >>= n; nbits -= n; if (nbits < 0) bad = true; }
     CCT_HD uint32_t take(int n) { uint32_t v = peek(n); drop(n); return v; }
@@ -303,6 +308,233 @@ CCT_HDN inline int inflate_symbols(const uint8_t *in, int in_len, uint32_t *syms
     if (st.phase != kInfDone || br.bad) return -1;
     *out_len = st.op; *adler_want = st.adler_want;
     return st.ns;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Lane-parallel Huffman decode (the form k_inflate_sym runs; tests/hostsim steps the same scalar pieces)
+// ------------------------------------------------------------------------------------------------
+// One stream is decoded by the 32 lanes of a warp.  Blocks are sequential (a block's header is found only when
+// the previous block ends), but inside a block the bit string is cut into rounds of 32 sub-sequences of
+// kSubBits bits, one per lane.  Lane 0 starts on a true symbol boundary; the others start speculatively at their
+// sub-sequence boundary.  Huffman codes self-synchronise: a decoder started at a wrong bit falls into step with
+// the true symbol sequence after a few symbols.  So every lane decodes to the end of its sub-sequence and reports
+// where its last symbol ended; lane i+1 then restarts from lane i's end.  A lane is CONFIRMED once it started
+// where its confirmed predecessor ended; rounds repeat (normally twice) until every lane up to the end of the
+// block is confirmed, then each lane decodes once more writing its symbols at the offset given by a scan of the
+// symbol counts.  The reader is stateless (two staged words + a funnel shift per peek), so lanes stay in lock step.
+constexpr int kFLitBits = 10, kFDstBits = 9;   // primary lookup widths
+constexpr int kSubBits = 512;                  // bits per lane per round
+constexpr int kSubLanes = 32;
+constexpr int kStageWords = kSubLanes * kSubBits / 32 + 8;      // one round + the longest symbol (48 bits) + peek
+constexpr int kStageAlloc = kStageWords + kStageWords / 16 + 1; // one pad word per 16: lanes start 16 words apart
+CCT_HD int stage_slot(int w) { return w + (w >> 4); }
+
+// table entry: bits 0..3 code length (0 = not in the primary table), 4..7 extra bits, 8..9 kind, 16..31 value
+constexpr uint32_t kEntLit = 0u << 8, kEntLen = 1u << 8, kEntEob = 2u << 8, kEntBad = 3u << 8, kEntKind = 3u << 8;
+
+struct FastCanon {       // canonical description of one prefix code
+    uint32_t lim[16];    // 31-bit left-justified exclusive upper bound of the codes of length <= l
+    uint16_t first[16];  // first code of length l
+    uint16_t offs[16];   // index in the sorted symbol array of the first symbol of length l
+    uint16_t count[16];  // codes of length l
+};
+struct FastTables {      // per-stream decode state in shared memory
+    uint32_t lit[1 << kFLitBits];
+    uint32_t dst[1 << kFDstBits];
+    FastCanon lc, dc;
+    uint16_t lsym[288], dsym[32];   // symbols ordered by (length, symbol)
+    uint8_t lens[320];              // code lengths of the current block: literal/length, then distance
+    uint32_t stage[kStageAlloc];    // the round's bits (padded layout); scratch while a header is parsed
+};
+
+CCT_HD uint32_t brev32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __brev(v);
+#else
+    v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+    v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
+    v = ((v >> 4) & 0x0F0F0F0Fu) | ((v & 0x0F0F0F0Fu) << 4);
+    v = ((v >> 8) & 0x00FF00FFu) | ((v & 0x00FF00FFu) << 8);
+    return (v >> 16) | (v << 16);
+#endif
+}
+
+CCT_HD uint32_t lit_entry(int sym, int l) {
+    if (sym < 256) return (uint32_t)l | kEntLit | ((uint32_t)sym << 16);
+    if (sym == 256) return (uint32_t)l | kEntEob;
+    const int idx = sym - 257;
+    if (idx >= 29) return (uint32_t)l | kEntBad;
+    return (uint32_t)l | ((uint32_t)len_extra_bits_inf(idx) << 4) | kEntLen | ((uint32_t)len_base_inf(idx) << 16);
+}
+CCT_HD uint32_t dst_entry(int sym, int l) {
+    if (sym >= 30) return (uint32_t)l | kEntBad;
+    const int xb = sym < 4 ? 0 : (sym >> 1) - 1;
+    return (uint32_t)l | ((uint32_t)xb << 4) | kEntLen | ((uint32_t)dist_base_inf(sym) << 16);
+}
+
+// The code of `from`..`to` bits at the head of `bits` (LSB-first, as read from the stream), as a table entry;
+// 0 if none.  Canonical codes, left-justified, fill consecutive intervals in order of length, so the length is
+// the first l whose upper bound exceeds the (bit-reversed) head.  Requires: no code shorter than `from` matches.
+CCT_HD uint32_t canon_lookup(const FastCanon &c, const uint16_t *syms, uint32_t bits, int from, int to, bool lit) {
+    const uint32_t v = brev32(bits) >> 1;
+    for (int l = from; l <= to; l++) {
+        if (v < c.lim[l]) {
+            const int sym = syms[c.offs[l] + (int)(v >> (31 - l)) - (int)c.first[l]];
+            return lit ? lit_entry(sym, l) : dst_entry(sym, l);
+        }
+    }
+    return 0u;
+}
+
+// Table construction, split into steps so that a warp can run the parallel ones with all lanes
+// (lane, nl) = (lane id, 32) on the device and (0, 1) on the host; the caller synchronises between steps.
+CCT_HD void fast_count(const uint8_t *lens, int nsym, FastCanon &c, int lane, int nl) {  // c.count zeroed by the caller
+    for (int i = lane; i < nsym; i += nl) {
+        const int l = lens[i];
+        if (l) {
+#if defined(__CUDA_ARCH__)
+            atomicAdd(reinterpret_cast<unsigned int *>(&c.count[l & ~1]), (l & 1) ? 0x10000u : 1u);  // u16 pair
+#else
+            c.count[l]++;
+#endif
+        }
+    }
+}
+// single lane: code ranges; returns false for an over-subscribed set of lengths
+CCT_HDN inline bool fast_ranges(FastCanon &c) {
+    int left = 1;
+    uint32_t code = 0, idx = 0;
+    c.count[0] = 0; c.lim[0] = 0; c.first[0] = 0; c.offs[0] = 0;
+    for (int l = 1; l <= 15; l++) {
+        left = (left << 1) - c.count[l];
+        if (left < 0) return false;
+        c.first[l] = (uint16_t)code; c.offs[l] = (uint16_t)idx;
+        c.lim[l] = (code + c.count[l]) << (31 - l);
+        idx += c.count[l];
+        code = (code + c.count[l]) << 1;
+    }
+    return true;
+}
+// single lane: symbols ordered by (length, symbol).  `next` = 16 scratch counters.
+CCT_HDN inline void fast_sort(const uint8_t *lens, int nsym, const FastCanon &c, uint16_t *syms, uint16_t *next) {
+    for (int l = 0; l < 16; l++) next[l] = c.offs[l];
+    for (int i = 0; i < nsym; i++) if (lens[i]) syms[next[lens[i]]++] = (uint16_t)i;
+}
+CCT_HD void fast_fill(const FastCanon &c, const uint16_t *syms, uint32_t *prim, int prim_bits, bool lit, int lane, int nl) {
+    for (int t = lane; t < (1 << prim_bits); t += nl) prim[t] = canon_lookup(c, syms, (uint32_t)t, 1, prim_bits, lit);
+}
+
+CCT_HD uint32_t stage_peek(const uint32_t *stage, uint32_t rel) {  // 32 bits starting `rel` bits into the staged words
+    const int w = (int)(rel >> 5);
+    const uint32_t lo = stage[stage_slot(w)], hi = stage[stage_slot(w + 1)];
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, rel & 31u);
+#else
+    return (uint32_t)((((uint64_t)hi << 32) | lo) >> (rel & 31u));
+#endif
+}
+
+struct Span { uint32_t end; int n, extra, flag; };  // where the last symbol ended; symbols; sum of (len - 1) over matches
+enum { kSpanRun = 0, kSpanEob = 1, kSpanBad = 2, kSpanFar = 3 };  // ran to the limit / end of block / invalid code or out of data / distance before the start
+
+// Decode the symbols that START in [p, limit).  Positions are in bits from the stream's aligned origin;
+// `origin` is the position of staged word 0, `data_end` the end of the deflate data.  WRITE: symbols -> out[],
+// `op` = bytes produced before this span (distance check).
+template <bool WRITE>
+CCT_HD void decode_span(const uint32_t *stage, uint32_t origin, uint32_t p, uint32_t limit, uint32_t data_end,
+                        const FastTables &tb, uint32_t *out, int op, Span &r) {
+    int n = 0, extra = 0, flag = kSpanRun;
+    while (p < limit) {
+        uint32_t bits = stage_peek(stage, p - origin);
+        uint32_t e = tb.lit[bits & ((1u << kFLitBits) - 1)];
+        if (!e) { e = canon_lookup(tb.lc, tb.lsym, bits, kFLitBits + 1, 15, true); if (!e) { flag = kSpanBad; break; } }
+        const uint32_t kind = e & kEntKind;
+        if (kind == kEntLit) {
+            p += e & 15u;
+            if (WRITE) out[n] = e >> 16;
+            n++;
+            continue;
+        }
+        if (kind != kEntLen) {
+            if (kind == kEntEob) { p += e & 15u; flag = kSpanEob; } else flag = kSpanBad;
+            break;
+        }
+        uint32_t q = p + (e & 15u);
+        bits = stage_peek(stage, q - origin);
+        const uint32_t xb = (e >> 4) & 15u;
+        const int len = (int)(e >> 16) + (int)(bits & ((1u << xb) - 1u));
+        q += xb; bits >>= xb;  // at most 5 bits gone: 27 left for a distance code of at most 15
+        uint32_t d = tb.dst[bits & ((1u << kFDstBits) - 1)];
+        if (!d) { d = canon_lookup(tb.dc, tb.dsym, bits, kFDstBits + 1, 15, false); if (!d) { flag = kSpanBad; break; } }
+        if ((d & kEntKind) != kEntLen) { flag = kSpanBad; break; }
+        q += d & 15u;
+        bits = stage_peek(stage, q - origin);
+        const uint32_t dxb = (d >> 4) & 15u;
+        const int dist = (int)(d >> 16) + (int)(bits & ((1u << dxb) - 1u));
+        q += dxb;
+        if (WRITE) {
+            if (dist > op + n + extra) { flag = kSpanFar; break; }
+            out[n] = (uint32_t)(len - 3) | ((uint32_t)dist << 8);
+        }
+        p = q;
+        n++; extra += len - 1;
+    }
+    if (flag == kSpanRun && p >= data_end) flag = kSpanBad;  // the data ended before the block did
+    r.end = p; r.n = n; r.extra = extra; r.flag = flag;
+}
+
+// Block header (RFC 1951 3.2.3 - 3.2.7), single lane: leaves the code lengths in tb.lens (literal/length codes
+// first, then distance codes) and returns the block type, or -1.  Stored: *nlen = LEN.  `br` stands after the header.
+CCT_HDN inline int inflate_block_header(BitReader &br, FastTables &tb, bool *last, int *nlen, int *ndist) {
+    br.refill();
+    *last = br.take(1) != 0;
+    const int type = (int)br.take(2);
+    if (type == 0) {
+        br.drop(br.nbits & 7);
+        br.refill();
+        const uint32_t len = br.take(16), nl = br.take(16);
+        if (br.bad || (len ^ 0xFFFFu) != nl) return -1;
+        *nlen = (int)len;
+        return 0;
+    }
+    if (type == 3) return -1;
+    uint8_t *lens = tb.lens;
+    if (type == 1) {
+        for (int i = 0; i < 144; i++) lens[i] = 8;
+        for (int i = 144; i < 256; i++) lens[i] = 9;
+        for (int i = 256; i < 280; i++) lens[i] = 7;
+        for (int i = 280; i < 288; i++) lens[i] = 8;
+        for (int i = 0; i < 30; i++) lens[288 + i] = 5;
+        *nlen = 288; *ndist = 30;
+        return 1;
+    }
+    const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+    const int nl = (int)br.take(5) + 257, nd = (int)br.take(5) + 1, ncode = (int)br.take(4) + 4;
+    if (nl > 286 || nd > 30) return -1;
+    uint8_t cl[19];
+    for (int i = 0; i < 19; i++) cl[i] = 0;
+    for (int i = 0; i < ncode; i++) { br.refill(); cl[order[i]] = (uint8_t)br.take(3); }
+    // the code-length code's little tables live in the (idle) staging area
+    uint16_t *prim = reinterpret_cast<uint16_t *>(tb.stage), *cnt = prim + 128, *sy = cnt + 16;
+    if (!build_decode_table(cl, 19, 7, prim, cnt, sy)) return -1;
+    int idx = 0;
+    while (idx < nl + nd) {
+        br.refill();
+        const int sym = decode_symbol(br, prim, 7, cnt, sy);
+        if (sym < 0 || br.bad) return -1;
+        if (sym < 16) lens[idx++] = (uint8_t)sym;
+        else {
+            int rep, val = 0;
+            if (sym == 16) { if (idx == 0) return -1; val = lens[idx - 1]; rep = 3 + (int)br.take(2); }
+            else if (sym == 17) rep = 3 + (int)br.take(3);
+            else rep = 11 + (int)br.take(7);
+            if (idx + rep > nl + nd) return -1;
+            while (rep--) lens[idx++] = (uint8_t)val;
+        }
+    }
+    if (br.bad || lens[256] == 0) return -1;
+    *nlen = nl; *ndist = nd;
+    return 2;
 }
 
 // Pass 2 of inflate, sequential form (CPU harness): symbols -> bytes.

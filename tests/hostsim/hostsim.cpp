@@ -161,6 +161,114 @@ int hs_inflate(const uint8_t *in, int in_len, uint8_t *out, int out_cap) {
     return out_len;
 }
 
+// The lane-parallel Huffman decode of k_inflate_sym, with the 32 lanes stepped one after the other: same tables,
+// same decode_span, same confirmation rule.  `sub_lanes` < 32 narrows the round (more rounds, same result).
+static bool hs_block_symbols(const std::vector<uint32_t> &words, uint32_t data_end, FastTables &tb, uint32_t &q,
+                             uint32_t *syms, int &ns, int &op, int sym_cap, int out_cap, int *max_rounds) {
+    for (;;) {
+        const uint32_t w0 = q >> 5, origin = w0 << 5;
+        for (int j = 0; j < kStageWords; j++) tb.stage[stage_slot(j)] = w0 + j < words.size() ? words[w0 + j] : 0u;
+        uint32_t start[32], cur[32], limit[32];
+        Span r[32];
+        for (int l = 0; l < 32; l++) {
+            limit[l] = std::min(q + (uint32_t)(l + 1) * kSubBits, data_end);
+            start[l] = q + (uint32_t)l * kSubBits; cur[l] = 0xffffffffu; r[l] = Span{0u, 0, 0, kSpanRun};
+        }
+        int confirmed = 0, last = -1, rounds = 0;
+        for (;;) {
+            rounds++;
+            for (int l = confirmed; l < 32; l++)
+                if (start[l] != cur[l]) { decode_span<false>(tb.stage, origin, start[l], limit[l], data_end, tb, nullptr, 0, r[l]); cur[l] = start[l]; }
+            int c = 1;
+            while (c < 32 && cur[c] == r[c - 1].end) c++;
+            for (int l = 0; l < c && last < 0; l++) if (r[l].flag != kSpanRun) last = l;
+            if (last >= 0) break;
+            if (c == 32) { last = 31; break; }
+            confirmed = c;
+            for (int l = 31; l >= c; l--) start[l] = r[l - 1].end;
+        }
+        if (max_rounds && rounds > *max_rounds) *max_rounds = rounds;
+        const int end_flag = r[last].flag;
+        if (end_flag == kSpanBad) return false;
+        int tot_n = 0, tot_b = 0;
+        for (int l = 0; l <= last; l++) { tot_n += r[l].n; tot_b += r[l].n + r[l].extra; }
+        if (ns + tot_n > sym_cap || op + tot_b > out_cap) return false;
+        int on = ns, ob = op;
+        for (int l = 0; l <= last; l++) {
+            Span w;
+            decode_span<true>(tb.stage, origin, cur[l], limit[l], data_end, tb, syms + on, ob, w);
+            if (w.flag == kSpanFar) return false;
+            if (w.n != r[l].n || w.end != r[l].end) abort();
+            on += r[l].n; ob += r[l].n + r[l].extra;
+        }
+        ns += tot_n; op += tot_b;
+        q = r[last].end;
+        if (end_flag == kSpanEob) return q <= data_end;
+    }
+}
+
+// Whole zlib stream through the lane-parallel decoder.  `misalign` (0..3) places the stream at that offset from a
+// 4-byte boundary, as streams inside a .cct arena are.  Returns the output length or -1; *rounds = most
+// confirmation rounds any group of sub-sequences needed.
+int hs_inflate_lanes(const uint8_t *in_, int in_len, uint8_t *out, int out_cap, int misalign, int *rounds) {
+    std::vector<uint8_t> buf((size_t)in_len + 16, 0);
+    memcpy(buf.data() + 4 + misalign, in_, (size_t)in_len);
+    const uint8_t *in = buf.data() + 4 + misalign;
+    const uint8_t *base = buf.data() + 4;  // the aligned origin (buf.data() is at least 8-byte aligned)
+    const uint32_t skew = 8u * (uint32_t)misalign;
+    std::vector<uint32_t> words(((size_t)in_len + misalign + 3) / 4 + 1, 0u);
+    for (size_t k = 0; k < (size_t)in_len; k++) words[(k + misalign) >> 2] |= (uint32_t)in[k] << (8 * ((k + misalign) & 3));
+    (void)base;
+    if (in_len < 6 || (in[0] & 0x0F) != 8 || (((uint32_t)in[0] << 8) | in[1]) % 31 != 0 || (in[1] & 0x20)) return -1;
+    const int dlen = in_len - 4;
+    const uint32_t data_end = skew + 8u * (uint32_t)dlen;
+    const int sym_cap = out_cap + kInfSlack;
+    std::vector<uint32_t> syms((size_t)sym_cap);
+    FastTables *tb = new FastTables;
+    uint32_t bp = 16;
+    int ns = 0, op = 0, mr = 0;
+    bool last = false, good = true;
+    while (good && !last) {
+        BitReader br{in, dlen, 0, 0, 0, false};
+        br.seek(bp);
+        int nlen = 0, ndist = 0;
+        const int type = inflate_block_header(br, *tb, &last, &nlen, &ndist);
+        if (type < 0 || br.bad) { good = false; break; }
+        bp = br.tell();
+        if (type == 0) {
+            const int at = (int)(bp >> 3);
+            if (at + nlen > dlen || ns + nlen > sym_cap || op + nlen > out_cap) { good = false; break; }
+            for (int k = 0; k < nlen; k++) syms[ns + k] = in[at + k];
+            ns += nlen; op += nlen; bp += 8u * (uint32_t)nlen;
+            continue;
+        }
+        for (int pass = 0; pass < 2 && good; pass++) {
+            const bool lit = pass == 0;
+            FastCanon &c = lit ? tb->lc : tb->dc;
+            uint16_t *sy = lit ? tb->lsym : tb->dsym;
+            const uint8_t *lens = tb->lens + (lit ? 0 : nlen);
+            const int n = lit ? nlen : ndist;
+            for (int l = 0; l < 16; l++) c.count[l] = 0;
+            fast_count(lens, n, c, 0, 1);
+            if (!fast_ranges(c)) { good = false; break; }
+            fast_sort(lens, n, c, sy, reinterpret_cast<uint16_t *>(tb->stage));
+            fast_fill(c, sy, lit ? tb->lit : tb->dst, lit ? kFLitBits : kFDstBits, lit, 0, 1);
+        }
+        if (!good) break;
+        uint32_t q = bp + skew;
+        good = hs_block_symbols(words, data_end, *tb, q, syms.data(), ns, op, sym_cap, out_cap, &mr);
+        bp = q - skew;
+    }
+    delete tb;
+    if (rounds) *rounds = mr;
+    if (!good || (int)((bp + 7) >> 3) != dlen) return -1;
+    lz_expand(syms.data(), ns, out);
+    const uint8_t *t = in + dlen;
+    const uint32_t want = ((uint32_t)t[0] << 24) | ((uint32_t)t[1] << 16) | ((uint32_t)t[2] << 8) | t[3];
+    if (adler32_bytes(out, op) != want) return -1;
+    return op;
+}
+
 // payload (ops + EOF) -> raster pixels, via the same three steps as the decode kernels
 uint32_t hs_decode_payload(const uint8_t *payload, int plen, int n_px, const int32_t *order, uint16_t *out) {
     int nb = n_px / kBlock;

@@ -24,6 +24,8 @@ def hostsim():
     L.hs_deflate.restype = C.c_int64
     L.hs_inflate.argtypes = [u8p, C.c_int, u8p, C.c_int]
     L.hs_inflate.restype = C.c_int
+    L.hs_inflate_lanes.argtypes = [u8p, C.c_int, u8p, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    L.hs_inflate_lanes.restype = C.c_int
     L.hs_decode_payload.argtypes = [u8p, C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_uint16)]
     L.hs_decode_payload.restype = C.c_uint32
     L.hs_hilbert.argtypes = [C.c_uint32, C.c_uint32]
@@ -50,6 +52,14 @@ def _hs_inflate(L, z, cap):
     out = np.empty(max(cap, 1), np.uint8)
     r = L.hs_inflate(_p(src, C.c_uint8), len(z), _p(out, C.c_uint8), cap)
     return out[:r].tobytes() if r >= 0 else None
+
+
+def _hs_inflate_lanes(L, z, cap, misalign=0):
+    src = np.frombuffer(z, dtype=np.uint8)
+    out = np.empty(max(cap, 1), np.uint8)
+    rounds = C.c_int(0)
+    r = L.hs_inflate_lanes(_p(src, C.c_uint8), len(z), _p(out, C.c_uint8), cap, misalign, C.byref(rounds))
+    return (out[:r].tobytes() if r >= 0 else None), rounds.value
 
 
 def test_library_exports_every_declared_symbol(pkg):
@@ -139,6 +149,37 @@ def test_inflate_core(hostsim):
     z[len(z) // 2] ^= 0x10
     assert _hs_inflate(hostsim, bytes(z), 256 * 40) is None  # corrupt -> error
     assert _hs_inflate(hostsim, zlib.compress(b"abc" * 100, 9), 10) is None  # output overflow -> error
+
+
+def test_inflate_lane_parallel_core(hostsim, golden_cct):
+    """The lane-parallel Huffman decode of k_inflate_sym (speculative sub-sequences + confirmation), lanes stepped
+    sequentially on the CPU: any conformant stream, any byte alignment, corrupt streams flagged."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_oracle import _deflate_corpus
+    worst = 0
+    for k, data in enumerate(_deflate_corpus()):
+        for level in (0, 1, 6, 9):
+            got, rounds = _hs_inflate_lanes(hostsim, zlib.compress(data, level), len(data), misalign=(k + level) & 3)
+            assert got == data, (len(data), level)
+            worst = max(worst, rounds)
+    assert worst <= 32
+    body = golden_cct[13:]
+    payload = zlib.decompress(body)
+    for m in range(4):
+        got, rounds = _hs_inflate_lanes(hostsim, body, len(payload), misalign=m)
+        assert got == payload and rounds <= 4, rounds
+    # raw deflate features: fixed-Huffman blocks, a single distance code, long codes
+    co = zlib.compressobj(9, zlib.DEFLATED, 15, 9, zlib.Z_FIXED)
+    fixed = co.compress(payload[:50000]) + co.flush()
+    assert _hs_inflate_lanes(hostsim, fixed, 50000)[0] == payload[:50000]
+    rng = np.random.default_rng(5)
+    skew = (rng.geometric(0.02, 200000) % 256).astype(np.uint8).tobytes()  # long tail of rare symbols -> 11..15-bit codes
+    assert _hs_inflate_lanes(hostsim, zlib.compress(skew, 9), len(skew), 1)[0] == skew
+    z = bytearray(zlib.compress(bytes(range(256)) * 40, 9))
+    z[len(z) // 2] ^= 0x10
+    assert _hs_inflate_lanes(hostsim, bytes(z), 256 * 40)[0] is None  # corrupt -> error
+    assert _hs_inflate_lanes(hostsim, zlib.compress(b"abc" * 100, 9), 10)[0] is None  # output overflow -> error
+    assert _hs_inflate_lanes(hostsim, zlib.compress(payload, 9)[:-9], len(payload))[0] is None  # truncated -> error
 
 
 def test_payload_decode_core(hostsim, oracle, synth, golden_cct):
