@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -259,8 +260,13 @@ namespace {
 // Called on the host around every pass of a batch call: the host-buffer entry points use them to make the
 // compute stream wait for the pass's input copy and to start the pass's output copy.
 struct PassHooks {
-    std::function<int(int first, int count)> before, after;
+    std::function<int(int first, int count, cudaStream_t st)> before, after;
     int max_pass = 0;  // 0 = as many images per pass as the workspace holds
+    // optional second lane: odd passes run on `alt_stream` with their own workspace, so that the kernels of two
+    // neighbouring passes overlap on the GPU (per-stream kernels of one pass leave SMs idle that the other fills)
+    cudaStream_t alt_stream = nullptr;
+    void *alt_ws = nullptr;
+    cudaEvent_t ready = nullptr, carry[2] = {nullptr, nullptr};  // set-up done on the main stream; offsets of a pass written
 };
 
 int encode_impl(const uint16_t *d_px, int B, int rows, int cols, uint32_t flags, uint8_t *d_out, size_t out_cap,
@@ -289,8 +295,9 @@ int cct_decode_batch(const uint8_t *d_in, const int64_t *d_offsets, int B, int r
 namespace {
 
 int encode_impl(const uint16_t *d_px, int B, int rows, int cols, uint32_t flags, uint8_t *d_out, size_t out_cap,
-                int64_t *d_offsets, uint32_t *d_status, int32_t *d_stats, void *d_ws, size_t ws_bytes, cudaStream_t st,
+                int64_t *d_offsets, uint32_t *d_status, int32_t *d_stats, void *d_ws, size_t ws_bytes, cudaStream_t st_main,
                 const PassHooks *hooks) {
+    cudaStream_t st = st_main;
     int rc = check_shape(B, rows, cols);
     if (rc != CCT_OK) return rc;
     if (!d_offsets || (B > 0 && (!d_px || !d_out || !d_status || !d_ws))) return CCT_E_ARG;
@@ -305,28 +312,43 @@ int encode_impl(const uint16_t *d_px, int B, int rows, int cols, uint32_t flags,
     rc = get_order(rows, cols, (flags & CCT_FLAG_FRACTAL) != 0, st, &order);
     if (rc != CCT_OK) return rc;
     if (d_stats) CK(cudaMemsetAsync(d_stats, 0, (size_t)B * 4 * sizeof(int32_t), st));
-    EncodeWs ws;
-    encode_ws_carve(&ws, d_ws, Bc, n_px, flags);
-    for (int first = 0; first < B; first += Bc) {
+    EncodeWs wss[2];
+    encode_ws_carve(&wss[0], d_ws, Bc, n_px, flags);
+    const bool two = hooks && hooks->alt_stream && hooks->alt_ws;
+    if (two) {
+        encode_ws_carve(&wss[1], hooks->alt_ws, Bc, n_px, flags);
+        CK(cudaEventRecord(hooks->ready, st_main));
+        CK(cudaStreamWaitEvent(hooks->alt_stream, hooks->ready, 0));
+    }
+    int pass = 0;
+    for (int first = 0; first < B; first += Bc, pass++) {
         const int b = std::min(Bc, B - first);
+        const int lane = two ? (pass & 1) : 0;
+        const EncodeWs &ws = wss[lane];
+        cudaStream_t st = lane ? hooks->alt_stream : st_main;
         const uint16_t *px = d_px + (int64_t)first * n_px;
         int32_t *stats = d_stats ? d_stats + (int64_t)first * 4 : nullptr;
-        if (hooks && hooks->before && (rc = hooks->before(first, b)) != CCT_OK) return rc;
+        if (hooks && hooks->before && (rc = hooks->before(first, b, st)) != CCT_OK) return rc;
         { CCT_KERNEL(m_zero_jump, st); CK(cudaMemsetAsync(ws.jump, 0, (size_t)b * nb, st)); CK(cudaMemsetAsync(ws.taken, 0, (size_t)b * nb, st)); }
         launch_gather_stats(px, order, ws.hv, ws.info, b, n_px, st);
         if (flags & CCT_FLAG_SEGMENTATION) launch_mesh(ws.hv, ws.info, ws.jump, ws.taken, stats, b, n_px, st);
         launch_emit(ws.hv, ws.jump, ws.taken, ws.payload, ws.pstride, ws.plen, d_status + first, stats, b, n_px, st);
+        const uint8_t *body = ws.payload; int64_t body_stride = ws.pstride; const int32_t *body_len = ws.plen;
         if (flags & CCT_FLAG_DEFLATE) {
             { CCT_KERNEL(m_zero_zbuf, st); CK(cudaMemsetAsync(ws.zbuf, 0, (size_t)b * ws.zstride, st)); }
             launch_deflate(ws.payload, ws.pstride, ws.plen, b, ws.pstride, ws.zbuf, ws.zstride, ws.zlen, ws.dws, st);
-            launch_assemble(ws.zbuf, ws.zstride, ws.zlen, b, rows, cols, flags, d_out, (int64_t)out_cap, d_offsets, first,
-                            d_status, st);
-        } else {
-            launch_assemble(ws.payload, ws.pstride, ws.plen, b, rows, cols, flags, d_out, (int64_t)out_cap, d_offsets, first,
-                            d_status, st);
+            body = ws.zbuf; body_stride = ws.zstride; body_len = ws.zlen;
         }
+        // the running offset comes from the previous pass, which ran on the other stream
+        if (two && pass > 0) CK(cudaStreamWaitEvent(st, hooks->carry[(pass - 1) & 1], 0));
+        launch_assemble(body, body_stride, body_len, b, rows, cols, flags, d_out, (int64_t)out_cap, d_offsets, first, d_status, st);
+        if (two) CK(cudaEventRecord(hooks->carry[pass & 1], st));
         CK(cudaGetLastError());
-        if (hooks && hooks->after && (rc = hooks->after(first, b)) != CCT_OK) return rc;
+        if (hooks && hooks->after && (rc = hooks->after(first, b, st)) != CCT_OK) return rc;
+    }
+    if (two) {  // the caller's stream ends after everything
+        CK(cudaEventRecord(hooks->ready, hooks->alt_stream));
+        CK(cudaStreamWaitEvent(st_main, hooks->ready, 0));
     }
     return CCT_OK;
 }
@@ -345,14 +367,27 @@ int decode_impl(const uint8_t *d_in, const int64_t *d_offsets, int B, int rows, 
     const int32_t *order = nullptr;
     rc = get_order(rows, cols, true, st, &order);
     if (rc != CCT_OK) return rc;
-    DecodeWs ws;
-    decode_ws_carve(&ws, d_ws, Bc, n_px);
-    for (int first = 0; first < B; first += Bc) {
+    DecodeWs wss[2];
+    decode_ws_carve(&wss[0], d_ws, Bc, n_px);
+    const bool two = hooks && hooks->alt_stream && hooks->alt_ws;
+    if (two) {
+        decode_ws_carve(&wss[1], hooks->alt_ws, Bc, n_px);
+        CK(cudaEventRecord(hooks->ready, st));
+        CK(cudaStreamWaitEvent(hooks->alt_stream, hooks->ready, 0));
+    }
+    int pass = 0;
+    for (int first = 0; first < B; first += Bc, pass++) {
         const int b = std::min(Bc, B - first);
-        if (hooks && hooks->before && (rc = hooks->before(first, b)) != CCT_OK) return rc;
-        launch_decode(d_in, d_offsets + first, b, rows, cols, order, d_px + (int64_t)first * n_px, d_status + first, ws, st);
+        const int lane = two ? (pass & 1) : 0;
+        cudaStream_t ps = lane ? hooks->alt_stream : st;
+        if (hooks && hooks->before && (rc = hooks->before(first, b, ps)) != CCT_OK) return rc;
+        launch_decode(d_in, d_offsets + first, b, rows, cols, order, d_px + (int64_t)first * n_px, d_status + first, wss[lane], ps);
         CK(cudaGetLastError());
-        if (hooks && hooks->after && (rc = hooks->after(first, b)) != CCT_OK) return rc;
+        if (hooks && hooks->after && (rc = hooks->after(first, b, ps)) != CCT_OK) return rc;
+    }
+    if (two) {
+        CK(cudaEventRecord(hooks->ready, hooks->alt_stream));
+        CK(cudaStreamWaitEvent(st, hooks->ready, 0));
     }
     return CCT_OK;
 }
@@ -454,7 +489,8 @@ namespace {
 
 struct HostCtx {
     int dev = -1;
-    cudaStream_t st = nullptr, copy = nullptr;
+    cudaStream_t st = nullptr, st2 = nullptr, up = nullptr, down = nullptr;  // kernels (two lanes), host->device copies, device->host copies
+    cudaEvent_t ready = nullptr, carry[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> events;
     cudaEvent_t event(size_t i) {
         while (events.size() <= i) { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); events.push_back(e); }
@@ -470,6 +506,8 @@ struct HostCtx {
         cap[slot] = bytes;
         return CCT_OK;
     }
+    void drain() { cudaStreamSynchronize(up); cudaStreamSynchronize(st); cudaStreamSynchronize(st2); cudaStreamSynchronize(down); }
+    void two_lanes(PassHooks &h, int slot) const { h.alt_stream = st2; h.alt_ws = buf[slot]; h.ready = ready; h.carry[0] = carry[0]; h.carry[1] = carry[1]; }
 };
 
 std::mutex g_ctx_mu;
@@ -483,17 +521,29 @@ int get_ctx(int device, HostCtx **out) {
     if (c.dev < 0) {
         c.dev = device;
         CK(cudaStreamCreateWithFlags(&c.st, cudaStreamNonBlocking));
-        CK(cudaStreamCreateWithFlags(&c.copy, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&c.st2, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&c.ready, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c.carry[0], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c.carry[1], cudaEventDisableTiming));
+        CK(cudaStreamCreateWithFlags(&c.up, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&c.down, cudaStreamNonBlocking));
     }
     *out = &c;
     return CCT_OK;
 }
 
-// workspace budget for the host entry points: as many images per pass as fit in ~40 % of free memory
-size_t ws_budget(size_t want) {
-    size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return want;
-    return std::min(want, (size_t)(free_b * 0.4));
+// Images per pass of the host entry points: about 512 MiB of raw pixels, so that the copies of one pass hide
+// behind the kernels of its neighbours while every kernel still sees enough streams to fill the GPU.
+// CCT_HOST_PASS overrides it (0 = one pass).
+int host_pass(int B, size_t n_px) {
+    int per = (int)std::max<size_t>(1, ((size_t)512 << 20) / (n_px * 2));
+    if (const char *e = getenv("CCT_HOST_PASS")) { const int v = atoi(e); per = v > 0 ? v : B; }
+    return std::max(1, std::min(per, B));
+}
+// Neighbouring passes run on two streams unless CCT_HOST_LANES=1.
+bool host_two_lanes(int n_pass) {
+    if (const char *e = getenv("CCT_HOST_LANES")) return atoi(e) > 1 && n_pass > 1;
+    return n_pass > 1;
 }
 
 }  // namespace
@@ -512,44 +562,57 @@ int cct_encode_host(const uint16_t *h_px, int B, int rows, int cols, uint32_t fl
     h_offsets[0] = 0;
     if (B == 0) return CCT_OK;
     const size_t n_px = (size_t)rows * cols;
+    const int n_pass = (B + host_pass(B, n_px) - 1) / host_pass(B, n_px), per = (B + n_pass - 1) / n_pass;  // equal passes
     const size_t arena = std::min(out_cap, (size_t)B * cct_file_bound(rows, cols));
-    const size_t one = cct_encode_workspace_bytes(1, rows, cols, flags);
-    size_t ws_bytes = std::max(one, ws_budget(cct_encode_workspace_bytes(B, rows, cols, flags)));
+    const size_t ws_bytes = cct_encode_workspace_bytes(per, rows, cols, flags);
     if ((rc = c->ensure(0, (size_t)B * n_px * 2))) return rc;
     if ((rc = c->ensure(1, std::max<size_t>(arena, 16)))) return rc;
     if ((rc = c->ensure(2, (size_t)(B + 1) * 8 + (size_t)B * 4 + (size_t)B * 16))) return rc;
     if ((rc = c->ensure(3, ws_bytes))) return rc;
+    const bool two = host_two_lanes(n_pass);
+    if (two && (rc = c->ensure(5, ws_bytes))) return rc;
     uint16_t *d_px = (uint16_t *)c->buf[0];
     uint8_t *d_out = (uint8_t *)c->buf[1];
     int64_t *d_off = (int64_t *)c->buf[2];
     uint32_t *d_status = (uint32_t *)(d_off + B + 1);
     int32_t *d_stats = (int32_t *)(d_status + B);
-    // pixels go up in slices on the copy stream; each pass of the encoder waits only for its own slices, so the
-    // upload of pass k+1 overlaps the kernels of pass k
-    const int slice = std::max(1, std::min(B, 128));
-    const int n_slices = (B + slice - 1) / slice;
-    for (int k = 0; k < n_slices; k++) {
-        const size_t lo = (size_t)k * slice, cnt = std::min<size_t>(slice, (size_t)B - lo);
-        CK(cudaMemcpyAsync(d_px + lo * n_px, h_px + lo * n_px, cnt * n_px * 2, cudaMemcpyHostToDevice, c->copy));
-        CK(cudaEventRecord(c->event(k), c->copy));
+    // Three streams: pixels of every pass go up on `up` (queued at once), the encoder's passes run on `st`, each
+    // waiting only for its own pixels, and the bytes of pass k come down on `down` while pass k+1 is running.
+    for (int k = 0; k < n_pass; k++) {
+        const size_t lo = (size_t)k * per, cnt = std::min<size_t>(per, (size_t)B - lo);
+        CK(cudaMemcpyAsync(d_px + lo * n_px, h_px + lo * n_px, cnt * n_px * 2, cudaMemcpyHostToDevice, c->up));
+        CK(cudaEventRecord(c->event(k), c->up));
     }
-    PassHooks hooks;  // max_pass stays 0: the per-stream kernels need the whole batch resident to fill the GPU
-    hooks.before = [&](int first, int count) -> int {
-        const int last_slice = (first + count - 1) / slice;
-        CK(cudaStreamWaitEvent(c->st, c->event(last_slice), 0));  // slices are recorded in order on one stream
+    bool over = false;
+    auto fetch = [&](int k) -> int {  // bytes of pass k -> host (its offsets have been copied on `st` before event n_pass + k)
+        const int lo = k * per, hi = std::min(B, lo + per);
+        CK(cudaEventSynchronize(c->event(n_pass + k)));
+        const int64_t b0 = h_offsets[lo], b1 = h_offsets[hi];
+        if (b1 > (int64_t)out_cap || b1 > (int64_t)arena) { over = true; return CCT_OK; }
+        if (b1 > b0) CK(cudaMemcpyAsync(h_out + b0, d_out + b0, (size_t)(b1 - b0), cudaMemcpyDeviceToHost, c->down));
         return CCT_OK;
     };
+    PassHooks hooks;
+    hooks.max_pass = per;
+    if (two) c->two_lanes(hooks, 5);
+    hooks.before = [&](int first, int, cudaStream_t ps) -> int {
+        CK(cudaStreamWaitEvent(ps, c->event(first / per), 0));
+        return CCT_OK;
+    };
+    hooks.after = [&](int first, int count, cudaStream_t ps) -> int {
+        const int k = first / per;
+        CK(cudaMemcpyAsync(h_offsets + first + 1, d_off + first + 1, (size_t)count * 8, cudaMemcpyDeviceToHost, ps));
+        CK(cudaEventRecord(c->event(n_pass + k), ps));
+        return k > 0 ? fetch(k - 1) : CCT_OK;  // pass k is queued: now wait for pass k-1 and start its download
+    };
     rc = encode_impl(d_px, B, rows, cols, flags, d_out, arena, d_off, d_status, d_stats, c->buf[3], c->cap[3], c->st, &hooks);
-    if (rc != CCT_OK) { cudaStreamSynchronize(c->copy); cudaStreamSynchronize(c->st); return rc; }
-    CK(cudaMemcpyAsync(h_offsets, d_off, (size_t)(B + 1) * 8, cudaMemcpyDeviceToHost, c->st));
+    if (rc == CCT_OK) rc = fetch(n_pass - 1);
+    if (rc != CCT_OK) { c->drain(); return rc; }
     CK(cudaMemcpyAsync(h_status, d_status, (size_t)B * 4, cudaMemcpyDeviceToHost, c->st));
     if (h_stats) CK(cudaMemcpyAsync(h_stats, d_stats, (size_t)B * 16, cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
-    const int64_t total = h_offsets[B];
-    if ((size_t)total > out_cap) return CCT_E_CAPACITY;
-    CK(cudaMemcpyAsync(h_out, d_out, (size_t)total, cudaMemcpyDeviceToHost, c->st));
-    CK(cudaStreamSynchronize(c->st));
-    return CCT_OK;
+    CK(cudaStreamSynchronize(c->down));
+    return over ? CCT_E_CAPACITY : CCT_OK;
 }
 
 int cct_decode_host(const uint8_t *h_in, const int64_t *h_offsets, int B, int rows, int cols, uint16_t *h_px,
@@ -565,36 +628,51 @@ int cct_decode_host(const uint8_t *h_in, const int64_t *h_offsets, int B, int ro
     const size_t n_px = (size_t)rows * cols;
     const int64_t base = h_offsets[0], total = h_offsets[B] - base;
     if (total < 0) return CCT_E_ARG;
-    const size_t one = cct_decode_workspace_bytes(1, rows, cols);
-    size_t ws_bytes = std::max(one, ws_budget(cct_decode_workspace_bytes(B, rows, cols)));
+    for (int i = 0; i < B; i++) if (h_offsets[i + 1] < h_offsets[i]) return CCT_E_ARG;
+    const int n_pass = (B + host_pass(B, n_px) - 1) / host_pass(B, n_px), per = (B + n_pass - 1) / n_pass;  // equal passes
+    const size_t ws_bytes = cct_decode_workspace_bytes(per, rows, cols);
     if ((rc = c->ensure(0, (size_t)B * n_px * 2))) return rc;
     if ((rc = c->ensure(1, std::max<size_t>((size_t)total, 16)))) return rc;
     if ((rc = c->ensure(2, (size_t)(B + 1) * 8 + (size_t)B * 4))) return rc;
     if ((rc = c->ensure(4, ws_bytes))) return rc;
+    const bool two = host_two_lanes(n_pass);
+    if (two && (rc = c->ensure(5, ws_bytes))) return rc;
     uint16_t *d_px = (uint16_t *)c->buf[0];
     uint8_t *d_in = (uint8_t *)c->buf[1];
     int64_t *d_off = (int64_t *)c->buf[2];
     uint32_t *d_status = (uint32_t *)(d_off + B + 1);
     std::vector<int64_t> rel((size_t)B + 1);
     for (int i = 0; i <= B; i++) rel[i] = h_offsets[i] - base;
-    CK(cudaMemcpyAsync(d_in, h_in + base, (size_t)total, cudaMemcpyHostToDevice, c->st));
-    CK(cudaMemcpyAsync(d_off, rel.data(), (size_t)(B + 1) * 8, cudaMemcpyHostToDevice, c->st));
-    // pixels come down pass by pass on the copy stream while the next pass decodes
-    PassHooks hooks;  // (splitting the batch to overlap more of the copy was measured: 26 % slower end to end)
-    int n_ev = 0;
-    hooks.after = [&](int first, int count) -> int {
-        cudaEvent_t e = c->event(n_ev++);
-        CK(cudaEventRecord(e, c->st));
-        CK(cudaStreamWaitEvent(c->copy, e, 0));
+    CK(cudaMemcpyAsync(d_off, rel.data(), (size_t)(B + 1) * 8, cudaMemcpyHostToDevice, c->up));
+    // files of every pass go up on `up` (queued at once); pass k decodes on `st` as soon as its files are there;
+    // its pixels come down on `down` while pass k+1 decodes
+    for (int k = 0; k < n_pass; k++) {
+        const int lo = k * per, hi = std::min(B, lo + per);
+        if (rel[hi] > rel[lo])
+            CK(cudaMemcpyAsync(d_in + rel[lo], h_in + base + rel[lo], (size_t)(rel[hi] - rel[lo]), cudaMemcpyHostToDevice, c->up));
+        CK(cudaEventRecord(c->event(k), c->up));
+    }
+    PassHooks hooks;
+    hooks.max_pass = per;
+    if (two) c->two_lanes(hooks, 5);
+    hooks.before = [&](int first, int, cudaStream_t ps) -> int {
+        CK(cudaStreamWaitEvent(ps, c->event(first / per), 0));
+        return CCT_OK;
+    };
+    hooks.after = [&](int first, int count, cudaStream_t ps) -> int {
+        cudaEvent_t e = c->event(n_pass + first / per);
+        CK(cudaEventRecord(e, ps));
+        CK(cudaStreamWaitEvent(c->down, e, 0));
         CK(cudaMemcpyAsync(h_px + (size_t)first * n_px, d_px + (size_t)first * n_px, (size_t)count * n_px * 2,
-                           cudaMemcpyDeviceToHost, c->copy));
+                           cudaMemcpyDeviceToHost, c->down));
         return CCT_OK;
     };
     rc = decode_impl(d_in, d_off, B, rows, cols, d_px, d_status, c->buf[4], c->cap[4], c->st, &hooks);
-    if (rc != CCT_OK) { cudaStreamSynchronize(c->copy); cudaStreamSynchronize(c->st); return rc; }
+    if (rc != CCT_OK) { c->drain(); return rc; }
     CK(cudaMemcpyAsync(h_status, d_status, (size_t)B * 4, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->up));  // `rel` must outlive its copy
     CK(cudaStreamSynchronize(c->st));
-    CK(cudaStreamSynchronize(c->copy));
+    CK(cudaStreamSynchronize(c->down));
     return CCT_OK;
 }
 
@@ -606,7 +684,11 @@ void cct_release(void) {
             for (int i = 0; i < 6; i++) if (kv.second.buf[i]) cudaFree(kv.second.buf[i]);
             for (cudaEvent_t e : kv.second.events) cudaEventDestroy(e);
             if (kv.second.st) cudaStreamDestroy(kv.second.st);
-            if (kv.second.copy) cudaStreamDestroy(kv.second.copy);
+            if (kv.second.st2) cudaStreamDestroy(kv.second.st2);
+            if (kv.second.ready) cudaEventDestroy(kv.second.ready);
+            for (cudaEvent_t e : kv.second.carry) if (e) cudaEventDestroy(e);
+            if (kv.second.up) cudaStreamDestroy(kv.second.up);
+            if (kv.second.down) cudaStreamDestroy(kv.second.down);
         }
         g_ctx.clear();
     }

@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(32 * kInfWarps) k_inflate_sym(StreamSrc src, c
 }
 
 constexpr int kLzWarps = 4;
+constexpr int kLzOwn = 16;  // longest match a single lane copies on its own
 __global__ void __launch_bounds__(32 * kLzWarps) k_lz_expand(const uint32_t *__restrict__ syms, int64_t sym_stride,
                                                              const int32_t *__restrict__ nsym, uint8_t *__restrict__ out,
                                                              int64_t out_stride, int B) {
@@ -200,9 +201,11 @@ __global__ void __launch_bounds__(32 * kLzWarps) k_lz_expand(const uint32_t *__r
     const uint32_t *sy = syms + (int64_t)i * sym_stride;
     uint8_t *o = out + (int64_t)i * out_stride;
     int base = 0;
+    uint32_t s_next = lane < ns ? __ldg(sy + lane) : 0u;  // the next group's symbols are fetched a group ahead
     for (int g = 0; g < ns; g += 32) {
         const int k = g + lane;
-        const uint32_t s = k < ns ? sy[k] : 0u;
+        const uint32_t s = s_next;
+        s_next = k + 32 < ns ? __ldg(sy + k + 32) : 0u;
         const int dist = (int)(s >> 8);
         const int len = k < ns ? (dist ? (int)(s & 255u) + 3 : 1) : 0;
         int incl = len;
@@ -213,9 +216,16 @@ __global__ void __launch_bounds__(32 * kLzWarps) k_lz_expand(const uint32_t *__r
         }
         const int pos = base + incl - len;
         if (len && !dist) o[pos] = (uint8_t)s;
-        unsigned mm = __ballot_sync(0xffffffffu, dist != 0);
+        // short matches whose source lies entirely before this group depend on nothing written here: every lane
+        // copies its own (their loads are independent, so the group pays one memory latency for all of them)
+        const bool own = dist != 0 && len <= kLzOwn && dist >= len && pos - dist + len <= base;
+        if (own) {
+            const uint8_t *from = o + pos - dist;
+            for (int j = 0; j < len; j++) o[pos + j] = from[j];
+        }
+        unsigned mm = __ballot_sync(0xffffffffu, dist != 0 && !own);
         __syncwarp();
-        while (mm) {
+        while (mm) {  // the others in symbol order, each copied by the whole warp
             const int l = __ffs((int)mm) - 1;
             mm &= mm - 1;
             const int mpos = __shfl_sync(0xffffffffu, pos, l), mlen = __shfl_sync(0xffffffffu, len, l);
@@ -361,14 +371,45 @@ __global__ void __launch_bounds__(128) k_dec_ops_emit(const uint8_t *__restrict_
     if (st) atomicOr(status + i, st);
 }
 
-// JUMP flags -> unit table, one thread per image (sequential first-unconsumed-block walk, core.py:459-464)
-__global__ void __launch_bounds__(32) k_dec_units(const uint8_t *__restrict__ jflag, int n_px, int32_t *__restrict__ slotA,
-                                                  int32_t *__restrict__ slotB, uint32_t *__restrict__ status, int B) {
-    const int i = blockIdx.x * 32 + threadIdx.x;
+// JUMP flags -> unit table (the first-unconsumed-block walk of core.py:459-464; resolve_units in inflate_core.cuh is
+// the sequential statement), one warp per image.  The walk state (next slot q, next block cur, 64-bit window of
+// blocks already consumed as partners) is kept warp-uniform.  While the window is empty and the next slots carry
+// no JUMP -- the common case -- 32 slots are filled per step; otherwise one unit is resolved per step.
+constexpr int kUnitWarps = 4;
+__global__ void __launch_bounds__(32 * kUnitWarps) k_dec_units(const uint8_t *__restrict__ jflag, int n_px, int32_t *__restrict__ slotA,
+                                                               int32_t *__restrict__ slotB, uint32_t *__restrict__ status, int B) {
+    const int i = blockIdx.x * kUnitWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (i >= B || (status[i] & ~32u)) return;
     const int nb = n_px / kBlock;
-    const uint32_t st = resolve_units(jflag + (int64_t)i * nb, nb, slotA + (int64_t)i * nb, slotB + (int64_t)i * nb);
-    if (st) status[i] |= st;
+    const uint8_t *jf = jflag + (int64_t)i * nb;
+    int32_t *sa = slotA + (int64_t)i * nb, *sb = slotB + (int64_t)i * nb;
+    uint64_t win = 0;  // bit k: block cur + k already consumed as a partner
+    int cur = 0, q = 0;
+    bool bad = false;
+    while (q < nb) {
+        const int j = q + lane < nb ? jf[q + lane] : 1;  // past the end counts as "not plain"
+        const unsigned jm = __ballot_sync(0xffffffffu, j != 0);
+        if (win == 0 && !(jm & 1u)) {  // a stretch of plain units on untouched blocks
+            const int k = jm ? __ffs((int)jm) - 1 : 32;
+            if (lane < k) { sa[q + lane] = cur + lane; sb[q + lane] = -1; }
+            q += k; cur += k;
+            continue;
+        }
+        while (win & 1ull) { win >>= 1; cur++; }
+        const int j0 = __shfl_sync(0xffffffffu, j, 0);
+        if (j0) {
+            const int Bk = cur + j0;
+            if (Bk >= nb || q + 1 >= nb || ((win >> j0) & 1ull)) { bad = true; break; }
+            if (lane < 2) { sa[q + lane] = cur; sb[q + lane] = lane ? (Bk | kSlotSecond) : Bk; }
+            win |= 1ull << j0;
+            q += 2;
+        } else {
+            if (lane == 0) { sa[q] = cur; sb[q] = -1; }
+            q += 1;
+        }
+        win >>= 1; cur++;
+    }
+    if (bad && lane == 0) status[i] |= 64u;
 }
 
 __global__ void __launch_bounds__(256) k_dec_scatter(const uint16_t *__restrict__ vals, const int32_t *__restrict__ slotA,
@@ -419,7 +460,7 @@ void launch_decode(const uint8_t *files, const int64_t *offsets, int B, int rows
     k_dec_ops_emit<<<ge, 128, 0, st>>>(ws.payload, ws.pstride, ws.plen, ws.chunks, ws.max_chunks, n_px, ws.vals, ws.jflag, status);
     }
     { CCT_KERNEL(k_dec_units, st);
-    k_dec_units<<<(B + 31) / 32, 32, 0, st>>>(ws.jflag, n_px, ws.slotA, ws.slotB, status, B);
+    k_dec_units<<<(B + kUnitWarps - 1) / kUnitWarps, 32 * kUnitWarps, 0, st>>>(ws.jflag, n_px, ws.slotA, ws.slotB, status, B);
     }
     dim3 g((unsigned)((n_px + 255) / 256), (unsigned)B);
     { CCT_KERNEL(k_dec_scatter, st);
