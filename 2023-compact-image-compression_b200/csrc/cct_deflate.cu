@@ -337,7 +337,12 @@ __global__ void __launch_bounds__(kProbeThreads, 8) k_probe(const uint8_t *__res
     const uint32_t stream = blockIdx.y;
     const int n = in_len[stream];
     const uint64_t o = (uint64_t)stream * stride;
-    LzView v{in + (uint64_t)stream * in_stride, recs + o, n};
+    const uint8_t *w_s = in + (uint64_t)stream * in_stride;
+    const ChainRec *recs_s = recs + o;
+    // opaque to the compiler: at 32 registers it would otherwise re-derive both bases from the kernel parameters
+    // (nine instructions) at every use inside the walk instead of keeping them
+    asm volatile("" : "+l"(w_s), "+l"(recs_s));
+    LzView v{w_s, recs_s, n};
     // the grid covers the worst-case payload length; CTAs stride over the real one
     for (int s = blockIdx.x * kProbeThreads + threadIdx.x; s < n; s += gridDim.x * kProbeThreads) {
         uint32_t lo, hi;

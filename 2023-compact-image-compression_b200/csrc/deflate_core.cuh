@@ -115,9 +115,16 @@ struct LzView {
     int n;                  // payload length
 };
 
+CCT_HD uint8_t load_byte(const uint8_t *p) {  // payload bytes are read-only for the whole deflate stage
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
 CCT_HD int match_extend(const uint8_t *a, const uint8_t *b, int from, int cap) {
     int len = from;
-    while (len < cap && a[len] == b[len]) len++;
+    while (len < cap && load_byte(a + len) == load_byte(b + len)) len++;
     return len;
 }
 
@@ -192,7 +199,7 @@ CCT_HD int chain_step(const LzView &v, ChainState &c) {
         if (nvis < t + 1) return nvis == count_dist ? kWalkDone : kWalkBudget;
         c.chain -= t;
         if (t) { link_from = cur - t; dl = v.recs[link_from].dist; }  // the bottom of the run links onwards
-    } else if (rc.b0 == c.b0 && rc.x == c.b12 && (c.best < kMinMatch || a[c.best] == b[c.best])) {
+    } else if (rc.b0 == c.b0 && rc.x == c.b12 && (c.best < kMinMatch || load_byte(a + c.best) == load_byte(b + c.best))) {
         // the hash triple matches (no payload access so far); zlib's scan_end test is only a shortcut for len <= best
         const int len = match_extend(a, b, cap < kMinMatch ? cap : kMinMatch, cap);
         if (len > c.best) {
@@ -200,11 +207,12 @@ CCT_HD int chain_step(const LzView &v, ChainState &c) {
             if (len >= cap) return kWalkDone;
         }
     }
-    if (dl == 0) return kWalkDone;
+    // follow the link, charge the budget and the step cap: one exit test on the common path (precedence as in
+    // zlib's loop condition: chain end / distance limit, then the budget; the step cap is ours and comes last)
     c.cur = link_from - dl;
-    if (s - c.cur >= kMaxDist) return kWalkDone;  // cur <= limit
-    if (--c.chain == 0) return kWalkBudget;
-    if (--c.steps_left == 0) return kWalkSteps;
+    const bool done = (dl == 0) | (s - c.cur >= kMaxDist);  // cur <= limit
+    c.chain--; c.steps_left--;
+    if (done | (c.chain == 0) | (c.steps_left == 0)) return done ? kWalkDone : (c.chain == 0 ? kWalkBudget : kWalkSteps);
     return kWalkContinue;
 }
 
@@ -229,14 +237,20 @@ CCT_HD void match_probe(const LzView &v, int s, int K, uint32_t *lo, uint32_t *h
     const int d0 = v.recs[s].dist;
     if (d0 == 0 || d0 > kMaxDist) return;
     const int cap = look < kMaxMatch ? look : kMaxMatch;
-    int best = 2, bdist = 0;
-    int r = chain_walk(v, s, cap, best, bdist, kChainGood, K);
-    const uint32_t e = r == kWalkSteps ? kProbeIncomplete : (best >= kMinMatch ? mtab_pack(best, bdist) : 0u);
+    ChainState c;
+    chain_begin(v, s, cap, 2, kChainGood, K, c);
+    int r;
+    while ((r = chain_step(v, c)) == kWalkContinue) {}
+    const uint32_t e = r == kWalkSteps ? kProbeIncomplete : (c.best >= kMinMatch ? mtab_pack(c.best, c.bdist) : 0u);
     *lo = *hi = e;
     if (r != kWalkBudget) return;
-    best = 2; bdist = 0;
-    r = chain_walk(v, s, cap, best, bdist, kChainFull, K);
-    *lo = r == kWalkSteps ? kProbeIncomplete : (best >= kMinMatch ? mtab_pack(best, bdist) : 0u);
+    // The quartered budget ran out: the walk with the full budget visits the same candidates up to here, so it
+    // simply goes on.  (A run group cut short by the budget left cur and chain untouched and is evaluated again with
+    // the longer count -- its members seen so far are a prefix, so best/bdist come out as from a fresh walk.)
+    if (c.steps_left == 0) { *lo = kProbeIncomplete; return; }  // budget and step cap ran out on the same candidate
+    c.chain += kChainFull - kChainGood;
+    while ((r = chain_step(v, c)) == kWalkContinue) {}
+    *lo = r == kWalkSteps ? kProbeIncomplete : (c.best >= kMinMatch ? mtab_pack(c.best, c.bdist) : 0u);
 }
 
 // Exact longest_match for position s with the parser's prev_length (chain budget 4096, or 1024 once

@@ -281,16 +281,30 @@ def main():
         h_st = torch.zeros(B, dtype=torch.int32).pin_memory()
         h_out = torch.empty((B, n, n), dtype=torch.int16).pin_memory()
 
+        split = [0.0, 0.0]
+
         def e2e_step():
+            ta = time.perf_counter()
             native.check(L.cct_encode_host(h_px.data_ptr(), B, n, n, 7, h_arena_t.data_ptr(), h_arena_t.numel(),
                                            h_off_t.data_ptr(), h_st.data_ptr(), None, local))
+            tb = time.perf_counter()
             native.check(L.cct_decode_host(h_arena_t.data_ptr(), h_off_t.data_ptr(), B, n, n, h_out.data_ptr(),
                                            h_st.data_ptr(), local))
+            split[0] += tb - ta; split[1] += time.perf_counter() - tb
         del arena, px  # free torch's cached copies before the library allocates its own context
         pkg.codec.core._DeviceScratch.clear()
         torch.cuda.empty_cache()
         e2e_step()
         assert torch.equal(h_out, h_px)
+        # the link the end-to-end number is bounded by: pinned-memory copy rates of this box
+        d_tmp = torch.empty_like(d_imgs)
+        link = []
+        for src, dst in ((h_px, d_tmp), (d_tmp, h_out)):
+            torch.cuda.synchronize(); tc = time.perf_counter()
+            dst.copy_(src, non_blocking=True); torch.cuda.synchronize()
+            link.append(src.numel() * 2 / (time.perf_counter() - tc) / 1e9)
+        del d_tmp
+        split[0] = split[1] = 0.0
         if world > 1:
             dist.barrier()
         t1 = time.perf_counter()
@@ -301,7 +315,9 @@ def main():
             dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
         e2e = {"value": total_px / float(t_e2e.item()) / 1e6, "unit": "MPix/s",
                "h2d_bytes_per_step": B * n_px * 2 + F_total + (B + 1) * 8,
-               "d2h_bytes_per_step": F_total + (B + 1) * 8 + B * 4 + B * n_px * 2 + B * 4}
+               "d2h_bytes_per_step": F_total + (B + 1) * 8 + B * 4 + B * n_px * 2 + B * 4,
+               "encode_ms_per_step": split[0] / args.steps * 1e3, "decode_ms_per_step": split[1] / args.steps * 1e3,
+               "pinned_copy_gbs": {"h2d": link[0], "d2h": link[1]}}
 
     if rank != 0:
         if world > 1:
@@ -320,8 +336,16 @@ def main():
     top_name, (top_n, top_ms) = top
     per_launch_s = top_ms / top_n / 1e3
     achieved = stage_bytes[stage_of(top_name)] / per_launch_s / 1e9
+    # DRAM bytes per launch of that kernel, from the committed ncu --set full capture (per stream x this batch)
+    traffic = None
+    tr_files = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_traffic.json")) \
+        if os.path.isdir(os.path.join(ROOT, "profiles")) else []
+    if tr_files:
+        tr = json.load(open(os.path.join(ROOT, "profiles", tr_files[-1]))).get("kernels", {})
+        if top_name in tr:
+            traffic = tr[top_name]["dram_bytes_per_stream"] * B * n_px / (512 * 512)
     roofline = {"bound": "hbm", "kernel": top_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": stage_bytes[stage_of(top_name)],
                 "avg_launch_ms": top_ms / top_n, "share_of_step": top_ms / (t_all * 1e3)}
     path_bytes = (raw + F_total) * args.steps  # 2N + F per image, encode and decode alike

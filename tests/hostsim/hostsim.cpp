@@ -46,6 +46,25 @@ static uint32_t adler32_(const uint8_t *p, int64_t n) {
     return (b << 16) | a;
 }
 
+// The probe as first stated: one complete walk per chain budget.  match_probe (deflate_core.cuh) continues the
+// first walk instead of starting over; every entry it produces is checked against this.
+static void match_probe_two_walks(const LzView &v, int s, int K, uint32_t *lo, uint32_t *hi) {
+    *lo = *hi = 0;
+    const int look = v.n - s;
+    if (look < kMinMatch) return;
+    const int d0 = v.recs[s].dist;
+    if (d0 == 0 || d0 > kMaxDist) return;
+    const int cap = look < kMaxMatch ? look : kMaxMatch;
+    int best = 2, bdist = 0;
+    int r = chain_walk(v, s, cap, best, bdist, kChainGood, K);
+    const uint32_t e = r == kWalkSteps ? kProbeIncomplete : (best >= kMinMatch ? mtab_pack(best, bdist) : 0u);
+    *lo = *hi = e;
+    if (r != kWalkBudget) return;
+    best = 2; bdist = 0;
+    r = chain_walk(v, s, cap, best, bdist, kChainFull, K);
+    *lo = r == kWalkSteps ? kProbeIncomplete : (best >= kMinMatch ? mtab_pack(best, bdist) : 0u);
+}
+
 extern "C" {
 
 // Staged zlib-9 of src[0..n).  probe_k = chain entries examined by the parallel probe.
@@ -65,6 +84,9 @@ int64_t hs_deflate2(const uint8_t *src, int n, uint8_t *dst, int64_t cap, int pr
     int64_t n_incomplete = 0;
     for (int s = 0; s < n; s++) {
         match_probe(v, s, probe_k, &mlo[s], &mhi[s]);
+        uint32_t lo2, hi2;
+        match_probe_two_walks(v, s, probe_k, &lo2, &hi2);
+        if (lo2 != mlo[s] || hi2 != mhi[s]) return -4;
         n_incomplete += ((mlo[s] | mhi[s]) & kProbeIncomplete) != 0;
     }
     ProbeTab mtab{mlo.data(), mhi.data()};
