@@ -467,12 +467,16 @@ __global__ void __launch_bounds__(256) k_adler(const uint8_t *__restrict__ in, i
 }
 
 // ------------------------------------------------------------------ k_block_build
+// One warp per 16383-symbol block.  All lanes histogram the block's symbols (16-byte loads, shared-memory atomics);
+// lane 0 then runs zlib's tree construction verbatim (its tie-breaking lives in the heap order, so it cannot be
+// replaced by a parallel Huffman construction).  That part is a chain of dependent shared-memory accesses, so the
+// kernel's speed is the number of blocks resident per SM: the histogram counters share storage with the priority
+// queue and the block descriptor is assembled where the literal tree's Freq/Dad arrays were (both dead by then).
 struct BlockBuildSmem {
     BlockWork wk;
-    BlockDesc desc;
-    uint32_t lh[kLCodes + 2];
-    uint32_t dh[kDCodes + 2];
 };
+static_assert(sizeof(BlockDesc) <= 2 * kHeapSize * sizeof(uint16_t), "descriptor must fit in lt.freq + lt.dad");
+static_assert((kLCodes + 2 + kDCodes + 2) * sizeof(uint32_t) <= sizeof(TreeScratch::pq), "histogram must fit in the queue");
 
 __global__ void __launch_bounds__(32) k_block_build(const uint32_t *__restrict__ syms, int64_t stride,
                                                     const int32_t *__restrict__ blk_end, int max_blocks,
@@ -486,31 +490,40 @@ __global__ void __launch_bounds__(32) k_block_build(const uint32_t *__restrict__
     uint32_t *z = reinterpret_cast<uint32_t *>(&sm);
     for (int i = lane; i < (int)(sizeof(BlockBuildSmem) / 4); i += 32) z[i] = 0;
     __syncwarp();
+    uint32_t *lh = sm.wk.sc.pq, *dh = sm.wk.sc.pq + kLCodes + 2;
     const int32_t *be = blk_end + (int64_t)stream * max_blocks;
     const uint32_t sym_begin = (uint32_t)blk * kSymEnd;
     const uint32_t ns = blk < nf ? (uint32_t)kSymEnd : (uint32_t)(nsym[stream] - nf * kSymEnd);
     const uint32_t pos_begin = blk == 0 ? 0u : (uint32_t)be[blk - 1];
     const uint32_t pos_end = blk < nf ? (uint32_t)be[blk] : (uint32_t)in_len[stream];
-    const uint32_t *sy = syms + (int64_t)stream * stride + sym_begin;
-    for (uint32_t i = lane; i < ns; i += 32) {
-        uint32_t s = sy[i];
-        if (sym_dist(s) == 0) atomicAdd(&sm.lh[sym_lc(s)], 1u);
-        else { atomicAdd(&sm.lh[257 + len_code(sym_lc(s))], 1u); atomicAdd(&sm.dh[dist_code(sym_dist(s) - 1)], 1u); }
+    const uint32_t *sy = syms + (int64_t)stream * stride + sym_begin;  // stream base is 64-byte aligned
+    auto tally = [&](uint32_t s) {
+        if (sym_dist(s) == 0) atomicAdd(&lh[sym_lc(s)], 1u);
+        else { atomicAdd(&lh[257 + len_code(sym_lc(s))], 1u); atomicAdd(&dh[dist_code(sym_dist(s) - 1)], 1u); }
+    };
+    const uint32_t head = min(ns, (4u - (sym_begin & 3u)) & 3u);  // symbols before the first 16-byte boundary
+    if ((uint32_t)lane < head) tally(sy[lane]);
+    const uint4 *v4 = reinterpret_cast<const uint4 *>(sy + head);
+    const uint32_t nv = (ns - head) >> 2;
+#pragma unroll 4
+    for (uint32_t i = lane; i < nv; i += 32) {
+        const uint4 q = __ldg(v4 + i);
+        tally(q.x); tally(q.y); tally(q.z); tally(q.w);
     }
+    for (uint32_t i = head + 4 * nv + lane; i < ns; i += 32) tally(sy[i]);
     __syncwarp();
-    for (int i = lane; i < kLCodes; i += 32) sm.wk.lt.freq[i] = (uint16_t)sm.lh[i];
-    if (lane < kDCodes) sm.wk.dt.freq[lane] = (uint16_t)sm.dh[lane];
+    for (int i = lane; i < kLCodes; i += 32) sm.wk.lt.freq[i] = (uint16_t)lh[i];
+    if (lane < kDCodes) sm.wk.dt.freq[lane] = (uint16_t)dh[lane];
     __syncwarp();
+    BlockDesc *d = reinterpret_cast<BlockDesc *>(sm.wk.lt.freq);
     if (lane == 0) {
         sm.wk.lt.freq[256] = 1;
-        sm.desc.sym_begin = sym_begin; sm.desc.nsym = ns;
-        sm.desc.pos_begin = pos_begin; sm.desc.stored_len = pos_end - pos_begin;
-        sm.desc.last = blk == nf;
-        build_block(sm.wk, &sm.desc);
+        build_block(sm.wk, d, pos_end - pos_begin, blk == nf);
+        d->sym_begin = sym_begin; d->nsym = ns; d->pos_begin = pos_begin;
     }
     __syncwarp();
     uint32_t *dst = reinterpret_cast<uint32_t *>(desc + (int64_t)stream * max_blocks + blk);
-    const uint32_t *src = reinterpret_cast<const uint32_t *>(&sm.desc);
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(d);
     for (int i = lane; i < (int)(sizeof(BlockDesc) / 4); i += 32) dst[i] = src[i];
 }
 

@@ -384,10 +384,10 @@ constexpr int kLCodes = 286, kDCodes = 30, kBLCodes = 19, kHeapSize = 2 * kLCode
 constexpr int kHdrWords = 160;  // dynamic-block header bit string capacity (worst case 4498 bits)
 
 struct Tree {  // one Huffman tree under construction (ct_data with Freq/Dad/Len/Code split out)
-    uint16_t freq[kHeapSize];
-    uint16_t dad[kHeapSize];
+    alignas(8) uint16_t freq[kHeapSize];  // freq + dad: dead once the tree is built; k_block_build assembles
+    uint16_t dad[kHeapSize];              // the block descriptor in their place
     uint16_t len[kHeapSize];
-    uint16_t code[kHeapSize];
+    uint16_t code[kLCodes + 2];           // leaves only
     int max_code;
 };
 
@@ -395,35 +395,40 @@ struct SmallTree {  // distance (30 symbols) and bit-length (19 symbols) trees
     uint16_t freq[2 * kDCodes + 1];
     uint16_t dad[2 * kDCodes + 1];
     uint16_t len[2 * kDCodes + 1];
-    uint16_t code[2 * kDCodes + 1];
+    uint16_t code[kDCodes + 2];
     int max_code;
 };
 
 struct TreeScratch {
-    int16_t heap[kHeapSize];
-    // (Freq << 8 | depth) of heap[k]: trees.c's smaller(n, m) = Freq[n] < Freq[m] || (equal && depth[n] <= depth[m])
-    // is exactly key[n] <= key[m]; keeping the keys beside the heap saves the dependent heap[] -> Freq[] load
-    uint32_t hkey[kHeapSize];
+    // The priority queue of build_tree, one word per entry: Freq << 16 | depth << 10 | node.  trees.c's
+    // smaller(n, m) = Freq[n] < Freq[m] || (equal && depth[n] <= depth[m]) is exactly (q[n] >> 10) <= (q[m] >> 10);
+    // with the node in the same word a sift level is one 8-byte load of both children instead of a chain of
+    // heap[] -> Freq[] -> depth[] loads.  (Freq <= 16384 + 2 symbols per block, depth <= 22 < 64, node < 573.)
+    alignas(8) uint32_t pq[kHeapSize + 3];
+    int16_t heap[kHeapSize];  // nodes in the order they left the queue (zlib keeps them in the top of its heap array)
     uint16_t bl_count[kMaxBits + 1];
     int heap_len, heap_max;
     int64_t opt_len, static_len;
 };
 
+#if !defined(__CUDACC__)
+struct uint2 { uint32_t x, y; };  // host build of the test harness
+#endif
+constexpr uint32_t kPqNone = 0xFFFFFFFFu;  // sentinel after the last entry: never "smaller" than a real one
+
 CCT_HDN inline void pq_down(TreeScratch &s, int k) {
-    const int v = s.heap[k];
-    const uint32_t vk = s.hkey[k];
+    const uint32_t v = s.pq[k], vk = v >> 10;
     int j = k << 1;
     while (j <= s.heap_len) {
-        uint32_t jk = s.hkey[j];
-        if (j < s.heap_len) {
-            const uint32_t rk = s.hkey[j + 1];
-            if (rk <= jk) { j++; jk = rk; }
-        }
-        if (vk <= jk) break;
-        s.heap[k] = s.heap[j]; s.hkey[k] = jk;
+        // children j (even: 8-byte aligned) and j + 1 (the sentinel when j is the last entry)
+        const uint2 ch = *reinterpret_cast<const uint2 *>(&s.pq[j]);
+        uint32_t c = ch.x;
+        if ((ch.y >> 10) <= (c >> 10)) { j++; c = ch.y; }
+        if (vk <= (c >> 10)) break;
+        s.pq[k] = c;
         k = j; j <<= 1;
     }
-    s.heap[k] = (int16_t)v; s.hkey[k] = vk;
+    s.pq[k] = v;
 }
 
 // kind: 0 literal/length tree, 1 distance tree, 2 bit-length tree
@@ -436,36 +441,37 @@ CCT_HDN inline void build_tree(TreeScratch &s, T &t, int kind) {
     int n, m, max_code = -1, node;
     s.heap_len = 0; s.heap_max = heap_size;
     for (n = 0; n < elems; n++) {
-        if (t.freq[n] != 0) { s.heap[++s.heap_len] = (int16_t)(max_code = n); s.hkey[s.heap_len] = (uint32_t)t.freq[n] << 8; }
+        if (t.freq[n] != 0) { s.pq[++s.heap_len] = ((uint32_t)t.freq[n] << 16) | (uint32_t)(max_code = n); }
         else t.len[n] = 0;
     }
     while (s.heap_len < 2) {  // force at least two codes
-        node = s.heap[++s.heap_len] = (int16_t)(max_code < 2 ? ++max_code : 0);
-        t.freq[node] = 1; s.hkey[s.heap_len] = 1u << 8;
+        node = max_code < 2 ? ++max_code : 0;
+        s.pq[++s.heap_len] = (1u << 16) | (uint32_t)node;
+        t.freq[node] = 1;
         s.opt_len--;
         if (kind == 0) s.static_len -= static_llen(node);
         else if (kind == 1) s.static_len -= 5;
     }
     t.max_code = max_code;
+    s.pq[s.heap_len + 1] = kPqNone;
     for (n = s.heap_len / 2; n >= 1; n--) pq_down(s, n);
     node = elems;
     do {
-        n = s.heap[1];
-        const uint32_t nk = s.hkey[1];
-        s.heap[1] = s.heap[s.heap_len]; s.hkey[1] = s.hkey[s.heap_len]; s.heap_len--;
+        const uint32_t nq = s.pq[1];  // pqremove
+        s.pq[1] = s.pq[s.heap_len]; s.pq[s.heap_len] = kPqNone; s.heap_len--;
         pq_down(s, 1);
-        m = s.heap[1];
-        const uint32_t mk = s.hkey[1];
+        const uint32_t mq = s.pq[1];
+        n = (int)(nq & 1023u); m = (int)(mq & 1023u);
         s.heap[--s.heap_max] = (int16_t)n; s.heap[--s.heap_max] = (int16_t)m;
-        const uint32_t f = (nk >> 8) + (mk >> 8);
-        const uint32_t dn = nk & 255u, dm = mk & 255u;
+        const uint32_t f = (nq >> 16) + (mq >> 16);
+        const uint32_t dn = (nq >> 10) & 63u, dm = (mq >> 10) & 63u;
         t.freq[node] = (uint16_t)f;
         t.dad[n] = t.dad[m] = (uint16_t)node;
-        s.heap[1] = (int16_t)node++;
-        s.hkey[1] = ((f & 0xFFFFu) << 8) | (((dn >= dm ? dn : dm) + 1u) & 255u);
+        s.pq[1] = (f << 16) | ((((dn >= dm ? dn : dm) + 1u) & 63u) << 10) | (uint32_t)node;
+        node++;
         pq_down(s, 1);
     } while (s.heap_len >= 2);
-    s.heap[--s.heap_max] = s.heap[1];
+    s.heap[--s.heap_max] = (int16_t)(s.pq[1] & 1023u);
 
     // gen_bitlen
     int h, bits, overflow = 0;
@@ -577,8 +583,9 @@ struct BlockWork {  // scratch for build_block (shared or local memory)
 };
 
 // lt.freq / dt.freq must hold the block's symbol frequencies (incl. freq[256] = 1) on entry, every
-// other field zero.  Fills desc->type/hdr/hdr_bits/body_bits and the code tables.
-CCT_HDN inline void build_block(BlockWork &wk, BlockDesc *desc) {
+// other field zero.  Fills desc->type/last/stored_len/hdr/hdr_bits/body_bits and the code tables.  `desc` is
+// written only after the three trees are built, so it may occupy the storage of wk.lt.freq / wk.lt.dad.
+CCT_HDN inline void build_block(BlockWork &wk, BlockDesc *desc, uint32_t stored_len, uint32_t last) {
     const uint8_t bl_order[kBLCodes] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
     wk.sc.opt_len = 0; wk.sc.static_len = 0;
     build_tree(wk.sc, wk.lt, 0);
@@ -592,6 +599,7 @@ CCT_HDN inline void build_block(BlockWork &wk, BlockDesc *desc) {
     wk.sc.opt_len += 3 * ((int64_t)max_blindex + 1) + 5 + 5 + 4;
     int64_t opt_lenb = (wk.sc.opt_len + 3 + 7) >> 3, static_lenb = (wk.sc.static_len + 3 + 7) >> 3;
     if (static_lenb <= opt_lenb) opt_lenb = static_lenb;
+    desc->stored_len = stored_len; desc->last = last;
     for (int i = 0; i < kHdrWords; i++) desc->hdr[i] = 0;
     HdrBits hb{desc->hdr, 0};
     if ((int64_t)desc->stored_len + 4 <= opt_lenb) {

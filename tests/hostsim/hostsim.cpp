@@ -124,7 +124,7 @@ int64_t hs_deflate2(const uint8_t *src, int n, uint8_t *dst, int64_t cap, int pr
             if (sym_dist(sy) == 0) wk->lt.freq[sym_lc(sy)]++;
             else { wk->lt.freq[257 + len_code(sym_lc(sy))]++; wk->dt.freq[dist_code(sym_dist(sy) - 1)]++; }
         }
-        build_block(*wk, &d);
+        build_block(*wk, &d, d.stored_len, d.last);
     }
     delete wk;
     // layout + packing
