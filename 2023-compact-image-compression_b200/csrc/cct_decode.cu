@@ -55,7 +55,7 @@ struct StreamSrc {  // where stream i lives: arena + offsets (with a header to s
 
 // One stream per warp, all lanes decoding (inflate_core.cuh, "Lane-parallel Huffman decode"); kInfWarps warps
 // per CTA, each with its own tables and staging area in shared memory.
-constexpr int kInfWarps = 2;
+constexpr int kInfWarps = 4;
 constexpr unsigned kFull = 0xffffffffu;
 
 struct StreamBits {  // the stream as aligned 32-bit words; positions are bits from the aligned origin
@@ -79,13 +79,29 @@ __device__ __forceinline__ bool warp_build_code(FastTables &tb, int first, int n
     fast_count(tb.lens + first, nsym, c, lane, 32);
     __syncwarp();
     bool ok = true;
-    if (lane == 0) {
-        ok = fast_ranges(c);
-        if (ok) fast_sort(tb.lens + first, nsym, c, syms, reinterpret_cast<uint16_t *>(tb.stage));
-    }
+    if (lane == 0) ok = fast_ranges(c);
     ok = __shfl_sync(kFull, ok, 0);
     __syncwarp();
-    if (ok) fast_fill(c, syms, lit ? tb.lit : tb.dst, lit ? kFLitBits : kFDstBits, lit, lane, 32);
+    if (!ok) return false;
+    // symbols ordered by (length, symbol), 32 at a time (fast_sort is the sequential statement): a symbol's slot is
+    // its length's running cursor plus its rank among the lanes holding the same length
+    uint16_t *next = reinterpret_cast<uint16_t *>(tb.stage);
+    if (lane < 16) next[lane] = c.offs[lane];
+    __syncwarp();
+    for (int base = 0; base < nsym; base += 32) {
+        const int i = base + lane;
+        const int l = i < nsym ? tb.lens[first + i] : 0;
+        const unsigned peers = __match_any_sync(kFull, l);
+        const int rank = __popc(peers & ((1u << lane) - 1u));
+        const int start = next[l];
+        __syncwarp();
+        if (l) {
+            syms[start + rank] = (uint16_t)i;
+            if (rank == 0) next[l] = (uint16_t)(start + __popc(peers));
+        }
+        __syncwarp();
+    }
+    fast_fill(c, syms, lit ? tb.lit : tb.dst, lit ? kFLitBits : kFDstBits, lit, lane, 32);
     __syncwarp();
     return ok;
 }

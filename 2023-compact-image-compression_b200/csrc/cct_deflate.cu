@@ -522,6 +522,8 @@ __global__ void __launch_bounds__(32) k_block_build(const uint32_t *__restrict__
         d->sym_begin = sym_begin; d->nsym = ns; d->pos_begin = pos_begin;
     }
     __syncwarp();
+    fill_block_tables(sm.wk, d, lane, 32);
+    __syncwarp();
     uint32_t *dst = reinterpret_cast<uint32_t *>(desc + (int64_t)stream * max_blocks + blk);
     const uint32_t *src = reinterpret_cast<const uint32_t *>(d);
     for (int i = lane; i < (int)(sizeof(BlockDesc) / 4); i += 32) dst[i] = src[i];

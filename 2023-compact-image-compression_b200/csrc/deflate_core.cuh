@@ -63,10 +63,14 @@ CCT_HD int dist_code(int d) {
 CCT_HD int dist_extra_bits(int code) { return code < 4 ? 0 : (code >> 1) - 1; }
 CCT_HD int bl_extra_bits(int code) { return code < 16 ? 0 : (code == 16 ? 2 : (code == 17 ? 3 : 7)); }
 
-CCT_HD uint32_t bit_reverse(uint32_t code, int len) {
+CCT_HD uint32_t bit_reverse(uint32_t code, int len) {  // trees.c bi_reverse: the low `len` bits of code, reversed
+#if defined(__CUDA_ARCH__)
+    return len ? __brev(code) >> (32 - len) : 0u;
+#else
     uint32_t res = 0;
     for (int i = 0; i < len; i++) { res = (res << 1) | (code & 1u); code >>= 1; }
     return res;
+#endif
 }
 // static trees (trees.c tr_static_init): literal/length lengths and bit-reversed codes
 CCT_HD int static_llen(int n) { return n <= 143 ? 8 : (n <= 255 ? 9 : (n <= 279 ? 7 : 8)); }
@@ -610,8 +614,6 @@ CCT_HDN inline void build_block(BlockWork &wk, BlockDesc *desc, uint32_t stored_
         desc->type = 1;
         hb.put((1u << 1) + desc->last, 3);
         desc->body_bits = (uint32_t)wk.sc.static_len;
-        for (int n = 0; n < kLCodes + 2; n++) { desc->lcode[n] = (uint16_t)static_lcode(n); desc->llen[n] = (uint8_t)static_llen(n); }
-        for (int n = 0; n < kDCodes; n++) { desc->dcode[n] = (uint16_t)bit_reverse((uint32_t)n, 5); desc->dlen[n] = 5; }
     } else {
         desc->type = 2;
         hb.put((2u << 1) + desc->last, 3);
@@ -622,10 +624,19 @@ CCT_HDN inline void build_block(BlockWork &wk, BlockDesc *desc, uint32_t stored_
         tree_rle(wk.lt, wk.lt.max_code, (uint16_t *)nullptr, &wk.bt, &hb);
         tree_rle(wk.dt, wk.dt.max_code, (uint16_t *)nullptr, &wk.bt, &hb);
         desc->body_bits = (uint32_t)(wk.sc.opt_len - (hb.nbits - 3));
-        for (int n = 0; n < kLCodes; n++) { desc->lcode[n] = wk.lt.code[n]; desc->llen[n] = (uint8_t)(n <= wk.lt.max_code ? wk.lt.len[n] : 0); }
-        for (int n = 0; n < kDCodes; n++) { desc->dcode[n] = wk.dt.code[n]; desc->dlen[n] = (uint8_t)(n <= wk.dt.max_code ? wk.dt.len[n] : 0); }
     }
     desc->hdr_bits = (uint32_t)hb.nbits;
+}
+
+// The code tables the bit packer reads, after build_block: (lane, nl) = (lane id, 32) on the device, (0, 1) on the host.
+CCT_HD void fill_block_tables(const BlockWork &wk, BlockDesc *desc, int lane, int nl) {
+    if (desc->type == 1) {
+        for (int n = lane; n < kLCodes + 2; n += nl) { desc->lcode[n] = (uint16_t)static_lcode(n); desc->llen[n] = (uint8_t)static_llen(n); }
+        for (int n = lane; n < kDCodes; n += nl) { desc->dcode[n] = (uint16_t)bit_reverse((uint32_t)n, 5); desc->dlen[n] = 5; }
+    } else if (desc->type == 2) {
+        for (int n = lane; n < kLCodes; n += nl) { desc->lcode[n] = wk.lt.code[n]; desc->llen[n] = (uint8_t)(n <= wk.lt.max_code ? wk.lt.len[n] : 0); }
+        for (int n = lane; n < kDCodes; n += nl) { desc->dcode[n] = wk.dt.code[n]; desc->dlen[n] = (uint8_t)(n <= wk.dt.max_code ? wk.dt.len[n] : 0); }
+    }
 }
 
 // bits of one LZ77 symbol under a block's code tables: returns the bit string (LSB-first, <= 48 bits)

@@ -329,8 +329,9 @@ constexpr int kStageWords = kSubLanes * kSubBits / 32 + 8;      // one round + t
 constexpr int kStageAlloc = kStageWords + kStageWords / 16 + 1; // one pad word per 16: lanes start 16 words apart
 CCT_HD int stage_slot(int w) { return w + (w >> 4); }
 
-// table entry: bits 0..3 code length (0 = not in the primary table), 4..7 extra bits, 8..9 kind, 16..31 value
-constexpr uint32_t kEntLit = 0u << 8, kEntLen = 1u << 8, kEntEob = 2u << 8, kEntBad = 3u << 8, kEntKind = 3u << 8;
+// table entry (16 bits, so that a stream's tables stay small enough for 32 streams per SM): bits 0..3 code length
+// (0 = not in the primary table), 4..5 kind, 6..13 literal byte / length index 0..28 / distance symbol 0..29
+constexpr uint32_t kEntLit = 0u << 4, kEntLen = 1u << 4, kEntEob = 2u << 4, kEntBad = 3u << 4, kEntKind = 3u << 4;
 
 struct FastCanon {       // canonical description of one prefix code
     uint32_t lim[16];    // 31-bit left-justified exclusive upper bound of the codes of length <= l
@@ -339,8 +340,8 @@ struct FastCanon {       // canonical description of one prefix code
     uint16_t count[16];  // codes of length l
 };
 struct FastTables {      // per-stream decode state in shared memory
-    uint32_t lit[1 << kFLitBits];
-    uint32_t dst[1 << kFDstBits];
+    uint16_t lit[1 << kFLitBits];
+    uint16_t dst[1 << kFDstBits];
     FastCanon lc, dc;
     uint16_t lsym[288], dsym[32];   // symbols ordered by (length, symbol)
     uint8_t lens[320];              // code lengths of the current block: literal/length, then distance
@@ -360,16 +361,15 @@ CCT_HD uint32_t brev32(uint32_t v) {
 }
 
 CCT_HD uint32_t lit_entry(int sym, int l) {
-    if (sym < 256) return (uint32_t)l | kEntLit | ((uint32_t)sym << 16);
+    if (sym < 256) return (uint32_t)l | kEntLit | ((uint32_t)sym << 6);
     if (sym == 256) return (uint32_t)l | kEntEob;
     const int idx = sym - 257;
     if (idx >= 29) return (uint32_t)l | kEntBad;
-    return (uint32_t)l | ((uint32_t)len_extra_bits_inf(idx) << 4) | kEntLen | ((uint32_t)len_base_inf(idx) << 16);
+    return (uint32_t)l | kEntLen | ((uint32_t)idx << 6);
 }
 CCT_HD uint32_t dst_entry(int sym, int l) {
     if (sym >= 30) return (uint32_t)l | kEntBad;
-    const int xb = sym < 4 ? 0 : (sym >> 1) - 1;
-    return (uint32_t)l | ((uint32_t)xb << 4) | kEntLen | ((uint32_t)dist_base_inf(sym) << 16);
+    return (uint32_t)l | kEntLen | ((uint32_t)sym << 6);
 }
 
 // The code of `from`..`to` bits at the head of `bits` (LSB-first, as read from the stream), as a table entry;
@@ -420,8 +420,8 @@ CCT_HDN inline void fast_sort(const uint8_t *lens, int nsym, const FastCanon &c,
     for (int l = 0; l < 16; l++) next[l] = c.offs[l];
     for (int i = 0; i < nsym; i++) if (lens[i]) syms[next[lens[i]]++] = (uint16_t)i;
 }
-CCT_HD void fast_fill(const FastCanon &c, const uint16_t *syms, uint32_t *prim, int prim_bits, bool lit, int lane, int nl) {
-    for (int t = lane; t < (1 << prim_bits); t += nl) prim[t] = canon_lookup(c, syms, (uint32_t)t, 1, prim_bits, lit);
+CCT_HD void fast_fill(const FastCanon &c, const uint16_t *syms, uint16_t *prim, int prim_bits, bool lit, int lane, int nl) {
+    for (int t = lane; t < (1 << prim_bits); t += nl) prim[t] = (uint16_t)canon_lookup(c, syms, (uint32_t)t, 1, prim_bits, lit);
 }
 
 CCT_HD uint32_t stage_peek(const uint32_t *stage, uint32_t rel) {  // 32 bits starting `rel` bits into the staged words
@@ -451,7 +451,7 @@ CCT_HD void decode_span(const uint32_t *stage, uint32_t origin, uint32_t p, uint
         const uint32_t kind = e & kEntKind;
         if (kind == kEntLit) {
             p += e & 15u;
-            if (WRITE) out[n] = e >> 16;
+            if (WRITE) out[n] = e >> 6;
             n++;
             continue;
         }
@@ -459,19 +459,22 @@ CCT_HD void decode_span(const uint32_t *stage, uint32_t origin, uint32_t p, uint
             if (kind == kEntEob) { p += e & 15u; flag = kSpanEob; } else flag = kSpanBad;
             break;
         }
-        uint32_t q = p + (e & 15u);
+        // the length's extra bits are still in `bits` (15 + 5 <= 32); one more peek covers the distance code and
+        // its extra bits (15 + 13 <= 32)
+        const uint32_t l = e & 15u;
+        const int li = (int)(e >> 6);
+        const uint32_t xb = (uint32_t)len_extra_bits_inf(li);
+        const int len = len_base_inf(li) + (int)((bits >> l) & ((1u << xb) - 1u));
+        uint32_t q = p + l + xb;
         bits = stage_peek(stage, q - origin);
-        const uint32_t xb = (e >> 4) & 15u;
-        const int len = (int)(e >> 16) + (int)(bits & ((1u << xb) - 1u));
-        q += xb; bits >>= xb;  // at most 5 bits gone: 27 left for a distance code of at most 15
         uint32_t d = tb.dst[bits & ((1u << kFDstBits) - 1)];
         if (!d) { d = canon_lookup(tb.dc, tb.dsym, bits, kFDstBits + 1, 15, false); if (!d) { flag = kSpanBad; break; } }
         if ((d & kEntKind) != kEntLen) { flag = kSpanBad; break; }
-        q += d & 15u;
-        bits = stage_peek(stage, q - origin);
-        const uint32_t dxb = (d >> 4) & 15u;
-        const int dist = (int)(d >> 16) + (int)(bits & ((1u << dxb) - 1u));
-        q += dxb;
+        const uint32_t dl = d & 15u;
+        const int ds = (int)(d >> 6);
+        const uint32_t dxb = ds < 4 ? 0u : (uint32_t)(ds >> 1) - 1u;
+        const int dist = dist_base_inf(ds) + (int)((bits >> dl) & ((1u << dxb) - 1u));
+        q += dl + dxb;
         if (WRITE) {
             if (dist > op + n + extra) { flag = kSpanFar; break; }
             out[n] = (uint32_t)(len - 3) | ((uint32_t)dist << 8);

@@ -125,6 +125,7 @@ int64_t hs_deflate2(const uint8_t *src, int n, uint8_t *dst, int64_t cap, int pr
             else { wk->lt.freq[257 + len_code(sym_lc(sy))]++; wk->dt.freq[dist_code(sym_dist(sy) - 1)]++; }
         }
         build_block(*wk, &d, d.stored_len, d.last);
+        fill_block_tables(*wk, &d, 0, 1);
     }
     delete wk;
     // layout + packing
