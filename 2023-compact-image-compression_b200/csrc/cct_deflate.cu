@@ -37,7 +37,6 @@ size_t deflate_ws_carve(DeflateWs *ws, void *mem, int B, int64_t max_len) {
     ws->stride = align_up(max_len + 16, 16);
     ws->max_blocks = (int)(max_len / kSymEnd + 2);
     ws->dist16 = (uint16_t *)take((size_t)B * ws->stride * sizeof(uint16_t));
-    ws->rb16 = (uint16_t *)take((size_t)B * ws->stride * sizeof(uint16_t));
     ws->recs = (ChainRec *)take((size_t)B * ws->stride * sizeof(ChainRec));
     ws->mtab = (uint32_t *)take((size_t)B * ws->stride * sizeof(uint32_t));
     ws->mhi = (uint32_t *)take((size_t)B * ws->stride * sizeof(uint32_t));
@@ -198,127 +197,138 @@ __global__ void __launch_bounds__(32 * kChainWarps) k_chains(const uint8_t *__re
     if (wr != rd) chain_batch(tab, d16, lane, wr - rd, ring_s[(rd + lane) & (kRing - 1)], ring_h[(rd + lane) & (kRing - 1)]);
 }
 
-// Run lengths around every position: rb[p] / rl[p] = number of bytes equal to w[p] immediately before / after p.
-// One CTA per stream; a tile is kRunThreads x kRunPer positions, each thread owns kRunPer consecutive ones.  Inside
-// a thread the counts are a running counter; across threads the value entering a segment comes from a scan with
-// the operator (whole, val) o (whole', val') = whole' ? (whole, val + val') : (false, val')  -- "the run covers my
-// whole segment, so pass on what came in plus my length" -- and across tiles from a carried scalar.
-constexpr int kRunThreads = 256;
-constexpr int kRunPer = 16;
-constexpr int kRunTile = kRunThreads * kRunPer;
+// Run lengths around every position: rb[p] / rl[p] = number of bytes equal to w[p] immediately before / after p,
+// packed with the chain link and the first bytes into the ChainRec the walks load.  One warp owns a chunk of
+// kRunChunk positions, 32 per step, one position per lane: "where did the current run start" is a ballot and a
+// count-leading-zeros, the value entering the next step one shuffle -- no shared memory, coalesced loads and stores.
+// Chunks are independent once the count entering each is known, so the work is three launches:
+//   k_run_edges  per chunk: (does one run cover the whole chunk?, count leaving it if nothing came in), both ways
+//   k_run_link   per stream: warp scan of those summaries -> the count entering every chunk from either side
+//   k_run_recs   per chunk: counts of every position, records written out
+// The summaries combine as (whole, val) o (whole', val') = whole' ? (whole, val + val') : (false, val').
+constexpr int kRunChunk = 512;
+constexpr int kRunSteps = kRunChunk / 32;
+constexpr int kRunWarps = 8;
+constexpr unsigned kAll = 0xffffffffu;
 
 struct RunCarry { int whole, val; };
 __device__ __forceinline__ RunCarry run_combine(RunCarry a, RunCarry b) {  // a = earlier part, b = later part
     return b.whole ? RunCarry{a.whole, a.val + b.val} : RunCarry{0, b.val};
 }
 
-// Block-wide exclusive scan of `mine` in thread order (or reverse thread order): returns what enters this thread's
-// segment, given `carry` entering the tile; *tile_out = what leaves the tile.
-template <bool REVERSE>
-__device__ __forceinline__ int run_scan(RunCarry mine, int carry, RunCarry *warp_tot, int *tile_out) {
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int vl = REVERSE ? 31 - lane : lane;            // position of this lane in scan order
-    RunCarry incl = mine;
+// The chunk's bytes, one per lane per step (c[j] = w[base + 32 j + lane], 0 past the end), and the bytes around it.
+struct RunBytes { uint32_t c[kRunSteps]; uint32_t before, after; };  // before = w[base - 1]; after: lanes 0,1 hold w[base + 512 + lane]
+__device__ __forceinline__ void run_bytes(RunBytes &r, const uint8_t *w, int n, int base, int lane) {
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        RunCarry o;
-        const int src = REVERSE ? lane + d : lane - d;
-        o.whole = __shfl_sync(0xffffffffu, incl.whole, src & 31);
-        o.val = __shfl_sync(0xffffffffu, incl.val, src & 31);
-        if (vl >= d) incl = run_combine(o, incl);
-    }
-    if (vl == 31) warp_tot[wid] = incl;
-    __syncthreads();
-    const int nw = kRunThreads / 32;
-    RunCarry before{1, carry};                            // everything that precedes this warp in scan order
-    RunCarry all{1, carry};
-    for (int q = 0; q < nw; q++) {
-        const int w = REVERSE ? nw - 1 - q : q;
-        if (REVERSE ? w > wid : w < wid) before = run_combine(before, warp_tot[w]);
-        all = run_combine(all, warp_tot[w]);
-    }
-    RunCarry excl;                                        // exclusive within the warp
-    const int src = REVERSE ? lane + 1 : lane - 1;
-    excl.whole = __shfl_sync(0xffffffffu, incl.whole, src & 31);
-    excl.val = __shfl_sync(0xffffffffu, incl.val, src & 31);
-    const RunCarry in = vl == 0 ? before : run_combine(before, excl);
-    *tile_out = all.val;
-    __syncthreads();
-    return in.val;
+    for (int j = 0; j < kRunSteps; j++) { const int p = base + 32 * j + lane; r.c[j] = p < n ? __ldg(w + p) : 0u; }
+    r.before = base > 0 ? __ldg(w + base - 1) : 0u;
+    const int q = base + kRunChunk + lane;
+    r.after = (lane < 2 && q < n) ? __ldg(w + q) : 0u;
+}
+// step j: mask of lanes whose byte equals the byte before it / after it (false outside the payload)
+__device__ __forceinline__ unsigned run_eq_prev(const RunBytes &r, int j, int n, int base, int lane) {
+    const uint32_t prev_group = j ? r.c[j - 1] : 0u;
+    uint32_t pc = __shfl_up_sync(kAll, r.c[j], 1);
+    const uint32_t last_of_prev = __shfl_sync(kAll, prev_group, 31);
+    if (lane == 0) pc = j ? last_of_prev : r.before;
+    const int p = base + 32 * j + lane;
+    return __ballot_sync(kAll, p >= 1 && p < n && r.c[j] == pc);
+}
+__device__ __forceinline__ unsigned run_eq_next(const RunBytes &r, int j, int n, int base, int lane) {
+    const uint32_t next_group = j + 1 < kRunSteps ? r.c[j + 1] : r.after;
+    uint32_t nc = __shfl_down_sync(kAll, r.c[j], 1);
+    const uint32_t first_of_next = __shfl_sync(kAll, next_group, 0);
+    if (lane == 31) nc = first_of_next;
+    const int p = base + 32 * j + lane;
+    return __ballot_sync(kAll, p + 1 < n && r.c[j] == nc);
 }
 
-__global__ void __launch_bounds__(kRunThreads) k_runs(const uint8_t *__restrict__ in, int64_t in_stride,
-                                                      const int32_t *__restrict__ in_len, const uint16_t *__restrict__ dist16,
-                                                      uint16_t *__restrict__ rb16, ChainRec *__restrict__ recs_all,
-                                                      int64_t stride) {
-    const int stream = blockIdx.x, tid = threadIdx.x;
-    const int n = in_len[stream];
-    const uint8_t *w = in + (int64_t)stream * in_stride;
-    const uint16_t *d16 = dist16 + (int64_t)stream * stride;
-    uint16_t *rb = rb16 + (int64_t)stream * stride;
-    ChainRec *recs = recs_all + (int64_t)stream * stride;
-    __shared__ RunCarry warp_tot[kRunThreads / 32];
-    __shared__ uint8_t sb[kRunTile + 4];    // sb[i] = w[base - 1 + i]
-    __shared__ uint16_t sv[kRunTile];       // counts of the tile, so that global traffic stays coalesced
-    // forward: rb.  For a segment, (whole, val) = (all positions equal their predecessor, count at the last position
-    // assuming 0 came in).
-    int carry = 0;  // rb of the position just before the tile
-    for (int base = 0; base < n; base += kRunTile) {
-        for (int i = tid; i < kRunTile + 3; i += kRunThreads) { const int p = base - 1 + i; sb[i] = (p >= 0 && p < n) ? w[p] : 0; }
-        __syncthreads();
-        const int q0 = tid * kRunPer, p0 = base + q0;
-        int cnt = 0, whole = 1;
-        int local[kRunPer];
+__global__ void __launch_bounds__(32 * kRunWarps) k_run_edges(const uint8_t *__restrict__ in, int64_t in_stride,
+                                                             const int32_t *__restrict__ in_len, int4 *__restrict__ edges, int max_chunks) {
+    const int stream = blockIdx.y, chunk = blockIdx.x * kRunWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int base = chunk * kRunChunk, n = in_len[stream];
+    if (base >= n) return;
+    RunBytes r;
+    run_bytes(r, in + (int64_t)stream * in_stride, n, base, lane);
+    int fw = 1, fv = 0, bw = 1, bv = 0;
 #pragma unroll
-        for (int i = 0; i < kRunPer; i++) {
-            const bool eq = p0 + i >= 1 && p0 + i < n && sb[q0 + i + 1] == sb[q0 + i];
-            if (eq) cnt++; else { cnt = 0; whole = 0; }
-            local[i] = cnt;
-        }
-        int tile_out;
-        const int enter = run_scan<false>(RunCarry{whole, cnt}, carry, warp_tot, &tile_out);
-        bool lead = true;  // still inside the run that entered the segment
-#pragma unroll
-        for (int i = 0; i < kRunPer; i++) {
-            lead = lead && local[i] == i + 1;
-            const int v = local[i] + (lead ? enter : 0);
-            sv[q0 + i] = (uint16_t)(v > 65535 ? 65535 : v);
-        }
-        __syncthreads();
-        for (int i = tid; i < kRunTile && base + i < n; i += kRunThreads) rb[base + i] = sv[i];
-        carry = tile_out > 65535 ? 65535 : tile_out;
-        __syncthreads();
+    for (int j = 0; j < kRunSteps; j++) {
+        const unsigned m = run_eq_prev(r, j, n, base, lane);
+        if (m == kAll) fv += 32; else { fw = 0; fv = __clz((int)~m); }  // equal flags at the top of the group
     }
-    // backward: rl, and the packed record
-    carry = 0;  // rl of the position just after the tile
-    for (int base = ((n - 1) / kRunTile) * kRunTile; base >= 0; base -= kRunTile) {
-        for (int i = tid; i < kRunTile + 3; i += kRunThreads) { const int p = base - 1 + i; sb[i] = (p >= 0 && p < n) ? w[p] : 0; }
-        __syncthreads();
-        const int q0 = tid * kRunPer, p0 = base + q0;
-        int cnt = 0, whole = 1;
-        int local[kRunPer];
 #pragma unroll
-        for (int i = kRunPer - 1; i >= 0; i--) {
-            const bool eq = p0 + i + 1 < n && sb[q0 + i + 1] == sb[q0 + i + 2];
-            if (eq) cnt++; else { cnt = 0; whole = 0; }
-            local[i] = cnt;
-        }
-        int tile_out;
-        const int enter = run_scan<true>(RunCarry{whole, cnt}, carry, warp_tot, &tile_out);
-        bool lead = true;
+    for (int j = kRunSteps - 1; j >= 0; j--) {
+        const unsigned m = run_eq_next(r, j, n, base, lane);
+        if (m == kAll) bv += 32; else { bw = 0; bv = __ffs((int)~m) - 1; }  // equal flags at the bottom of the group
+    }
+    if (lane == 0) edges[(int64_t)stream * max_chunks + chunk] = make_int4(fw, fv, bw, bv);
+}
+
+// enters[chunk] = (count entering the chunk from the left, count entering it from the right); one warp per stream
+__global__ void __launch_bounds__(32 * kRunWarps) k_run_link(const int32_t *__restrict__ in_len, const int4 *__restrict__ edges,
+                                                            int2 *__restrict__ enters, int max_chunks, int B) {
+    const int stream = blockIdx.x * kRunWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (stream >= B) return;
+    const int nt = (in_len[stream] + kRunChunk - 1) / kRunChunk;
+    const int4 *e = edges + (int64_t)stream * max_chunks;
+    int2 *o = enters + (int64_t)stream * max_chunks;
+    for (int dir = 0; dir < 2; dir++) {
+        int carry = 0;
+        for (int t0 = 0; t0 < nt; t0 += 32) {
+            const int k = t0 + lane;                      // k-th chunk in scan order
+            const int t = dir ? nt - 1 - k : k;
+            RunCarry incl{1, 0};
+            if (k < nt) { const int4 v = e[t]; incl = dir ? RunCarry{v.z, v.w} : RunCarry{v.x, v.y}; }
 #pragma unroll
-        for (int i = kRunPer - 1; i >= 0; i--) {
-            lead = lead && local[i] == kRunPer - i;
-            const int v = local[i] + (lead ? enter : 0);
-            sv[q0 + i] = (uint16_t)(v > 65535 ? 65535 : v);
+            for (int d = 1; d < 32; d <<= 1) {
+                RunCarry a{__shfl_up_sync(kAll, incl.whole, d), __shfl_up_sync(kAll, incl.val, d)};
+                if (lane >= d) incl = run_combine(a, incl);
+            }
+            RunCarry excl{__shfl_up_sync(kAll, incl.whole, 1), __shfl_up_sync(kAll, incl.val, 1)};
+            if (lane == 0) excl = RunCarry{1, 0};
+            const int in_val = run_combine(RunCarry{1, carry}, excl).val;
+            if (k < nt) { if (dir) o[t].y = in_val; else o[t].x = in_val; }
+            const RunCarry tot{__shfl_sync(kAll, incl.whole, 31), __shfl_sync(kAll, incl.val, 31)};
+            carry = run_combine(RunCarry{1, carry}, tot).val;
         }
-        __syncthreads();
-        for (int i = tid; i < kRunTile && base + i < n; i += kRunThreads) {
-            const int p = base + i;
-            recs[p] = make_rec(d16[p], sv[i], rb[p], sb[i + 1], sb[i + 2], sb[i + 3]);
-        }
-        carry = tile_out > 65535 ? 65535 : tile_out;
-        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(32 * kRunWarps) k_run_recs(const uint8_t *__restrict__ in, int64_t in_stride,
+                                                            const int32_t *__restrict__ in_len, const uint16_t *__restrict__ dist16,
+                                                            const int2 *__restrict__ enters, int max_chunks,
+                                                            ChainRec *__restrict__ recs_all, int64_t stride) {
+    const int stream = blockIdx.y, chunk = blockIdx.x * kRunWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int base = chunk * kRunChunk, n = in_len[stream];
+    if (base >= n) return;
+    const uint16_t *d16 = dist16 + (int64_t)stream * stride;
+    ChainRec *recs = recs_all + (int64_t)stream * stride;
+    RunBytes r;
+    run_bytes(r, in + (int64_t)stream * in_stride, n, base, lane);
+    const int2 enter = enters[(int64_t)stream * max_chunks + chunk];
+    uint32_t rb[kRunSteps];
+    int carry = enter.x;  // count of the position just before the group
+#pragma unroll
+    for (int j = 0; j < kRunSteps; j++) {
+        const unsigned m = run_eq_prev(r, j, n, base, lane);
+        const unsigned zeros_below = ~m & ((2u << lane) - 1u);  // positions <= lane whose flag is 0
+        const int back = zeros_below ? lane - (31 - __clz((int)zeros_below)) : lane + 1 + carry;
+        carry = __shfl_sync(kAll, back, 31);
+        rb[j] = (uint32_t)min(back, 65535);
+    }
+    carry = enter.y;  // count of the position just after the group
+#pragma unroll
+    for (int j = kRunSteps - 1; j >= 0; j--) {
+        const unsigned m = run_eq_next(r, j, n, base, lane);
+        const unsigned zeros_above = ~m & ~((1u << lane) - 1u);  // positions >= lane whose flag is 0
+        const int fwd = zeros_above ? (__ffs((int)zeros_above) - 1) - lane : (32 - lane) + carry;
+        carry = __shfl_sync(kAll, fwd, 0);
+        // w[p + 1], w[p + 2]: the next lanes' bytes, or the first lanes of the next group
+        const uint32_t next_group = j + 1 < kRunSteps ? r.c[j + 1] : r.after;
+        const uint32_t a1 = __shfl_sync(kAll, r.c[j], (lane + 1) & 31), n1 = __shfl_sync(kAll, next_group, (lane + 1) & 31);
+        const uint32_t a2 = __shfl_sync(kAll, r.c[j], (lane + 2) & 31), n2 = __shfl_sync(kAll, next_group, (lane + 2) & 31);
+        const int p = base + 32 * j + lane;
+        if (p < n) store_rec(recs + p, make_rec(d16[p], min(fwd, 65535), (int)rb[j], (uint8_t)r.c[j], (uint8_t)(lane < 31 ? a1 : n1), (uint8_t)(lane < 30 ? a2 : n2)));
     }
 }
 
@@ -664,8 +674,20 @@ void launch_deflate(const uint8_t *in, int64_t in_stride, const int32_t *in_len,
     { CCT_KERNEL(k_chains, st);
     k_chains<<<B, 32 * kChainWarps, chain_smem, st>>>(in, in_stride, in_len, ws.dist16, ws.stride);
     }
-    { CCT_KERNEL(k_runs, st);
-    k_runs<<<B, kRunThreads, 0, st>>>(in, in_stride, in_len, ws.dist16, ws.rb16, ws.recs, ws.stride);
+    {   // the chunk summaries live in arrays the parse fills later
+        const int max_chunks = (int)((max_len + kRunChunk - 1) / kRunChunk);
+        int4 *edges = reinterpret_cast<int4 *>(ws.rec);
+        int2 *enters = reinterpret_cast<int2 *>(ws.mhi);
+        dim3 gt((unsigned)((max_chunks + kRunWarps - 1) / kRunWarps), (unsigned)B);
+        { CCT_KERNEL(k_run_edges, st);
+        k_run_edges<<<gt, 32 * kRunWarps, 0, st>>>(in, in_stride, in_len, edges, max_chunks);
+        }
+        { CCT_KERNEL(k_run_link, st);
+        k_run_link<<<(B + kRunWarps - 1) / kRunWarps, 32 * kRunWarps, 0, st>>>(in_len, edges, enters, max_chunks, B);
+        }
+        { CCT_KERNEL(k_run_recs, st);
+        k_run_recs<<<gt, 32 * kRunWarps, 0, st>>>(in, in_stride, in_len, ws.dist16, enters, max_chunks, ws.recs, ws.stride);
+        }
     }
     dim3 gp((unsigned)std::min<int64_t>((max_len + kProbeThreads - 1) / kProbeThreads, 512), (unsigned)B);
     { CCT_KERNEL(k_probe, st);

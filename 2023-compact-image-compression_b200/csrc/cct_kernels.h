@@ -36,7 +36,6 @@ void launch_emit(const uint16_t *hv, const uint8_t *jump, const uint8_t *taken, 
 // ---- cct_deflate.cu
 struct DeflateWs {  // device scratch for one pass over B streams of capacity max_len
     uint16_t *dist16;    // [B][stride] chain links
-    uint16_t *rb16;      // [B][stride] equal bytes before each position
     ChainRec *recs;      // [B][stride] per-position record read by the chain walks
     uint32_t *mtab, *mhi;  // [B][stride] probe table: entries for chain budget 4096 / 1024
     uint32_t *syms;      // [B][stride] dense LZ77 symbols

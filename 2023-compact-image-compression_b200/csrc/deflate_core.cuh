@@ -101,6 +101,14 @@ CCT_HD ChainRec make_rec(int dist, int rl, int rb, uint8_t b0, uint8_t b1, uint8
     return r;
 }
 
+CCT_HD void store_rec(ChainRec *p, const ChainRec &r) {  // one 8-byte store (the compiler would emit three)
+#if defined(__CUDA_ARCH__)
+    *reinterpret_cast<uint2 *>(p) = make_uint2((uint32_t)r.dist | ((uint32_t)r.rl << 16), (uint32_t)r.x | ((uint32_t)r.b0 << 16));
+#else
+    *p = r;
+#endif
+}
+
 CCT_HD ChainRec load_rec(const ChainRec *p) {
 #if defined(__CUDA_ARCH__)
     const uint2 q = __ldg(reinterpret_cast<const uint2 *>(p));
