@@ -260,8 +260,9 @@ namespace {
 // Called on the host around every pass of a batch call: the host-buffer entry points use them to make the
 // compute stream wait for the pass's input copy and to start the pass's output copy.
 struct PassHooks {
-    std::function<int(int first, int count, cudaStream_t st)> before, after;
+    std::function<int(int pass, int first, int count, cudaStream_t st)> before, after;
     int max_pass = 0;  // 0 = as many images per pass as the workspace holds
+    const std::vector<int> *starts = nullptr;  // optional schedule: pass k covers [starts[k], starts[k + 1]), each <= max_pass
     // optional second lane: odd passes run on `alt_stream` with their own workspace, so that the kernels of two
     // neighbouring passes overlap on the GPU (per-stream kernels of one pass leave SMs idle that the other fills)
     cudaStream_t alt_stream = nullptr;
@@ -320,15 +321,16 @@ int encode_impl(const uint16_t *d_px, int B, int rows, int cols, uint32_t flags,
         CK(cudaEventRecord(hooks->ready, st_main));
         CK(cudaStreamWaitEvent(hooks->alt_stream, hooks->ready, 0));
     }
+    if (hooks && hooks->starts) for (size_t k = 0; k + 1 < hooks->starts->size(); k++) if ((*hooks->starts)[k + 1] - (*hooks->starts)[k] > Bc) return CCT_E_WORKSPACE;
     int pass = 0;
-    for (int first = 0; first < B; first += Bc, pass++) {
-        const int b = std::min(Bc, B - first);
+    for (int first = 0, b = 0; first < B; first += b, pass++) {
+        b = hooks && hooks->starts ? (*hooks->starts)[pass + 1] - first : std::min(Bc, B - first);
         const int lane = two ? (pass & 1) : 0;
         const EncodeWs &ws = wss[lane];
         cudaStream_t st = lane ? hooks->alt_stream : st_main;
         const uint16_t *px = d_px + (int64_t)first * n_px;
         int32_t *stats = d_stats ? d_stats + (int64_t)first * 4 : nullptr;
-        if (hooks && hooks->before && (rc = hooks->before(first, b, st)) != CCT_OK) return rc;
+        if (hooks && hooks->before && (rc = hooks->before(pass, first, b, st)) != CCT_OK) return rc;
         { CCT_KERNEL(m_zero_jump, st); CK(cudaMemsetAsync(ws.jump, 0, (size_t)b * nb, st)); CK(cudaMemsetAsync(ws.taken, 0, (size_t)b * nb, st)); }
         launch_gather_stats(px, order, ws.hv, ws.info, b, n_px, st);
         if (flags & CCT_FLAG_SEGMENTATION) launch_mesh(ws.hv, ws.info, ws.jump, ws.taken, stats, b, n_px, st);
@@ -344,7 +346,7 @@ int encode_impl(const uint16_t *d_px, int B, int rows, int cols, uint32_t flags,
         launch_assemble(body, body_stride, body_len, b, rows, cols, flags, d_out, (int64_t)out_cap, d_offsets, first, d_status, st);
         if (two) CK(cudaEventRecord(hooks->carry[pass & 1], st));
         CK(cudaGetLastError());
-        if (hooks && hooks->after && (rc = hooks->after(first, b, st)) != CCT_OK) return rc;
+        if (hooks && hooks->after && (rc = hooks->after(pass, first, b, st)) != CCT_OK) return rc;
     }
     if (two) {  // the caller's stream ends after everything
         CK(cudaEventRecord(hooks->ready, hooks->alt_stream));
@@ -375,15 +377,16 @@ int decode_impl(const uint8_t *d_in, const int64_t *d_offsets, int B, int rows, 
         CK(cudaEventRecord(hooks->ready, st));
         CK(cudaStreamWaitEvent(hooks->alt_stream, hooks->ready, 0));
     }
+    if (hooks && hooks->starts) for (size_t k = 0; k + 1 < hooks->starts->size(); k++) if ((*hooks->starts)[k + 1] - (*hooks->starts)[k] > Bc) return CCT_E_WORKSPACE;
     int pass = 0;
-    for (int first = 0; first < B; first += Bc, pass++) {
-        const int b = std::min(Bc, B - first);
+    for (int first = 0, b = 0; first < B; first += b, pass++) {
+        b = hooks && hooks->starts ? (*hooks->starts)[pass + 1] - first : std::min(Bc, B - first);
         const int lane = two ? (pass & 1) : 0;
         cudaStream_t ps = lane ? hooks->alt_stream : st;
-        if (hooks && hooks->before && (rc = hooks->before(first, b, ps)) != CCT_OK) return rc;
+        if (hooks && hooks->before && (rc = hooks->before(pass, first, b, ps)) != CCT_OK) return rc;
         launch_decode(d_in, d_offsets + first, b, rows, cols, order, d_px + (int64_t)first * n_px, d_status + first, wss[lane], ps);
         CK(cudaGetLastError());
-        if (hooks && hooks->after && (rc = hooks->after(first, b, ps)) != CCT_OK) return rc;
+        if (hooks && hooks->after && (rc = hooks->after(pass, first, b, ps)) != CCT_OK) return rc;
     }
     if (two) {
         CK(cudaEventRecord(hooks->ready, hooks->alt_stream));
@@ -532,13 +535,25 @@ int get_ctx(int device, HostCtx **out) {
     return CCT_OK;
 }
 
-// Images per pass of the host entry points: about 512 MiB of raw pixels, so that the copies of one pass hide
-// behind the kernels of its neighbours while every kernel still sees enough streams to fill the GPU.
-// CCT_HOST_PASS overrides it (0 = one pass).
-int host_pass(int B, size_t n_px) {
+// Pass schedule of the host entry points: about 512 MiB of raw pixels per pass, so that the copies of one pass hide
+// behind the kernels of its neighbours while every kernel still sees enough streams to fill the GPU; the first pass
+// is a quarter of that, because its upload (encode) / its kernels (decode) are the part nothing can hide.
+// CCT_HOST_PASS overrides the pass size (0 = one pass).  Returns the largest pass.
+int host_schedule(int B, size_t n_px, std::vector<int> &starts) {
     int per = (int)std::max<size_t>(1, ((size_t)512 << 20) / (n_px * 2));
     if (const char *e = getenv("CCT_HOST_PASS")) { const int v = atoi(e); per = v > 0 ? v : B; }
-    return std::max(1, std::min(per, B));
+    per = std::max(1, std::min(per, B));
+    starts.clear();
+    starts.push_back(0);
+    if (B > per) {
+        const int lead = std::max(1, per / 4);
+        const int rest = B - lead, n = (rest + per - 1) / per, each = (rest + n - 1) / n;  // equal passes after the first
+        starts.push_back(lead);
+        for (int k = 1; k < n; k++) starts.push_back(lead + k * each);
+        per = std::max(lead, each);
+    }
+    starts.push_back(B);
+    return per;
 }
 // Neighbouring passes run on two streams unless CCT_HOST_LANES=1.
 bool host_two_lanes(int n_pass) {
@@ -562,7 +577,8 @@ int cct_encode_host(const uint16_t *h_px, int B, int rows, int cols, uint32_t fl
     h_offsets[0] = 0;
     if (B == 0) return CCT_OK;
     const size_t n_px = (size_t)rows * cols;
-    const int n_pass = (B + host_pass(B, n_px) - 1) / host_pass(B, n_px), per = (B + n_pass - 1) / n_pass;  // equal passes
+    std::vector<int> starts;
+    const int per = host_schedule(B, n_px, starts), n_pass = (int)starts.size() - 1;
     const size_t arena = std::min(out_cap, (size_t)B * cct_file_bound(rows, cols));
     const size_t ws_bytes = cct_encode_workspace_bytes(per, rows, cols, flags);
     if ((rc = c->ensure(0, (size_t)B * n_px * 2))) return rc;
@@ -579,13 +595,13 @@ int cct_encode_host(const uint16_t *h_px, int B, int rows, int cols, uint32_t fl
     // Three streams: pixels of every pass go up on `up` (queued at once), the encoder's passes run on `st`, each
     // waiting only for its own pixels, and the bytes of pass k come down on `down` while pass k+1 is running.
     for (int k = 0; k < n_pass; k++) {
-        const size_t lo = (size_t)k * per, cnt = std::min<size_t>(per, (size_t)B - lo);
+        const size_t lo = (size_t)starts[k], cnt = (size_t)(starts[k + 1] - starts[k]);
         CK(cudaMemcpyAsync(d_px + lo * n_px, h_px + lo * n_px, cnt * n_px * 2, cudaMemcpyHostToDevice, c->up));
         CK(cudaEventRecord(c->event(k), c->up));
     }
     bool over = false;
     auto fetch = [&](int k) -> int {  // bytes of pass k -> host (its offsets have been copied on `st` before event n_pass + k)
-        const int lo = k * per, hi = std::min(B, lo + per);
+        const int lo = starts[k], hi = starts[k + 1];
         CK(cudaEventSynchronize(c->event(n_pass + k)));
         const int64_t b0 = h_offsets[lo], b1 = h_offsets[hi];
         if (b1 > (int64_t)out_cap || b1 > (int64_t)arena) { over = true; return CCT_OK; }
@@ -594,13 +610,13 @@ int cct_encode_host(const uint16_t *h_px, int B, int rows, int cols, uint32_t fl
     };
     PassHooks hooks;
     hooks.max_pass = per;
+    hooks.starts = &starts;
     if (two) c->two_lanes(hooks, 5);
-    hooks.before = [&](int first, int, cudaStream_t ps) -> int {
-        CK(cudaStreamWaitEvent(ps, c->event(first / per), 0));
+    hooks.before = [&](int k, int, int, cudaStream_t ps) -> int {
+        CK(cudaStreamWaitEvent(ps, c->event(k), 0));
         return CCT_OK;
     };
-    hooks.after = [&](int first, int count, cudaStream_t ps) -> int {
-        const int k = first / per;
+    hooks.after = [&](int k, int first, int count, cudaStream_t ps) -> int {
         CK(cudaMemcpyAsync(h_offsets + first + 1, d_off + first + 1, (size_t)count * 8, cudaMemcpyDeviceToHost, ps));
         CK(cudaEventRecord(c->event(n_pass + k), ps));
         return k > 0 ? fetch(k - 1) : CCT_OK;  // pass k is queued: now wait for pass k-1 and start its download
@@ -629,7 +645,8 @@ int cct_decode_host(const uint8_t *h_in, const int64_t *h_offsets, int B, int ro
     const int64_t base = h_offsets[0], total = h_offsets[B] - base;
     if (total < 0) return CCT_E_ARG;
     for (int i = 0; i < B; i++) if (h_offsets[i + 1] < h_offsets[i]) return CCT_E_ARG;
-    const int n_pass = (B + host_pass(B, n_px) - 1) / host_pass(B, n_px), per = (B + n_pass - 1) / n_pass;  // equal passes
+    std::vector<int> starts;
+    const int per = host_schedule(B, n_px, starts), n_pass = (int)starts.size() - 1;
     const size_t ws_bytes = cct_decode_workspace_bytes(per, rows, cols);
     if ((rc = c->ensure(0, (size_t)B * n_px * 2))) return rc;
     if ((rc = c->ensure(1, std::max<size_t>((size_t)total, 16)))) return rc;
@@ -647,20 +664,21 @@ int cct_decode_host(const uint8_t *h_in, const int64_t *h_offsets, int B, int ro
     // files of every pass go up on `up` (queued at once); pass k decodes on `st` as soon as its files are there;
     // its pixels come down on `down` while pass k+1 decodes
     for (int k = 0; k < n_pass; k++) {
-        const int lo = k * per, hi = std::min(B, lo + per);
+        const int lo = starts[k], hi = starts[k + 1];
         if (rel[hi] > rel[lo])
             CK(cudaMemcpyAsync(d_in + rel[lo], h_in + base + rel[lo], (size_t)(rel[hi] - rel[lo]), cudaMemcpyHostToDevice, c->up));
         CK(cudaEventRecord(c->event(k), c->up));
     }
     PassHooks hooks;
     hooks.max_pass = per;
+    hooks.starts = &starts;
     if (two) c->two_lanes(hooks, 5);
-    hooks.before = [&](int first, int, cudaStream_t ps) -> int {
-        CK(cudaStreamWaitEvent(ps, c->event(first / per), 0));
+    hooks.before = [&](int k, int, int, cudaStream_t ps) -> int {
+        CK(cudaStreamWaitEvent(ps, c->event(k), 0));
         return CCT_OK;
     };
-    hooks.after = [&](int first, int count, cudaStream_t ps) -> int {
-        cudaEvent_t e = c->event(n_pass + first / per);
+    hooks.after = [&](int k, int first, int count, cudaStream_t ps) -> int {
+        cudaEvent_t e = c->event(n_pass + k);
         CK(cudaEventRecord(e, ps));
         CK(cudaStreamWaitEvent(c->down, e, 0));
         CK(cudaMemcpyAsync(h_px + (size_t)first * n_px, d_px + (size_t)first * n_px, (size_t)count * n_px * 2,

@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(32 * kChainWarps) k_chains(const uint8_t *__re
 //   k_run_link   per stream: warp scan of those summaries -> the count entering every chunk from either side
 //   k_run_recs   per chunk: counts of every position, records written out
 // The summaries combine as (whole, val) o (whole', val') = whole' ? (whole, val + val') : (false, val').
-constexpr int kRunChunk = 512;
+constexpr int kRunChunk = 256;
 constexpr int kRunSteps = kRunChunk / 32;
 constexpr int kRunWarps = 8;
 constexpr unsigned kAll = 0xffffffffu;
@@ -217,7 +217,7 @@ __device__ __forceinline__ RunCarry run_combine(RunCarry a, RunCarry b) {  // a 
 }
 
 // The chunk's bytes, one per lane per step (c[j] = w[base + 32 j + lane], 0 past the end), and the bytes around it.
-struct RunBytes { uint32_t c[kRunSteps]; uint32_t before, after; };  // before = w[base - 1]; after: lanes 0,1 hold w[base + 512 + lane]
+struct RunBytes { uint32_t c[kRunSteps]; uint32_t before, after; };  // before = w[base - 1]; after: lanes 0,1 hold w[base + kRunChunk + lane]
 __device__ __forceinline__ void run_bytes(RunBytes &r, const uint8_t *w, int n, int base, int lane) {
 #pragma unroll
     for (int j = 0; j < kRunSteps; j++) { const int p = base + 32 * j + lane; r.c[j] = p < n ? __ldg(w + p) : 0u; }
@@ -306,6 +306,9 @@ __global__ void __launch_bounds__(32 * kRunWarps) k_run_recs(const uint8_t *__re
     RunBytes r;
     run_bytes(r, in + (int64_t)stream * in_stride, n, base, lane);
     const int2 enter = enters[(int64_t)stream * max_chunks + chunk];
+    uint32_t link[kRunSteps];  // chain links of the chunk, fetched up front with the bytes (all loads in flight at once)
+#pragma unroll
+    for (int j = 0; j < kRunSteps; j++) { const int p = base + 32 * j + lane; link[j] = p < n ? __ldg(d16 + p) : 0u; }
     uint32_t rb[kRunSteps];
     int carry = enter.x;  // count of the position just before the group
 #pragma unroll
@@ -328,7 +331,7 @@ __global__ void __launch_bounds__(32 * kRunWarps) k_run_recs(const uint8_t *__re
         const uint32_t a1 = __shfl_sync(kAll, r.c[j], (lane + 1) & 31), n1 = __shfl_sync(kAll, next_group, (lane + 1) & 31);
         const uint32_t a2 = __shfl_sync(kAll, r.c[j], (lane + 2) & 31), n2 = __shfl_sync(kAll, next_group, (lane + 2) & 31);
         const int p = base + 32 * j + lane;
-        if (p < n) store_rec(recs + p, make_rec(d16[p], min(fwd, 65535), (int)rb[j], (uint8_t)r.c[j], (uint8_t)(lane < 31 ? a1 : n1), (uint8_t)(lane < 30 ? a2 : n2)));
+        if (p < n) store_rec(recs + p, make_rec((int)link[j], min(fwd, 65535), (int)rb[j], (uint8_t)r.c[j], (uint8_t)(lane < 31 ? a1 : n1), (uint8_t)(lane < 30 ? a2 : n2)));
     }
 }
 
