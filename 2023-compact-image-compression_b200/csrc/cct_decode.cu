@@ -53,9 +53,9 @@ struct StreamSrc {  // where stream i lives: arena + offsets (with a header to s
     __device__ int size(int i) const { return (off ? (int)(off[i + 1] - off[i]) : len[i]) - skip; }
 };
 
-// One stream per warp, all lanes decoding (inflate_core.cuh, "Lane-parallel Huffman decode"); kInfWarps warps
-// per CTA, each with its own tables and staging area in shared memory.
-constexpr int kInfWarps = 4;
+// One stream per CTA of kSubLanes threads, all lanes decoding (inflate_core.cuh, "Lane-parallel Huffman decode");
+// the stream's tables, the staged bits of the round and the few words the lanes exchange live in shared memory.
+constexpr int kInfWarps = kSubLanes / 32;
 constexpr unsigned kFull = 0xffffffffu;
 
 struct StreamBits {  // the stream as aligned 32-bit words; positions are bits from the aligned origin
@@ -70,94 +70,128 @@ struct StreamBits {  // the stream as aligned 32-bit words; positions are bits f
     }
 };
 
-// Warp-cooperative construction of one code's tables from tb.lens[first .. first + nsym).
-__device__ __forceinline__ bool warp_build_code(FastTables &tb, int first, int nsym, bool lit, int lane) {
+struct InflateShared {
+    FastTables tb;
+    uint32_t ends[kSubLanes];                      // where each lane's last symbol ended
+    unsigned ok_mask[kInfWarps], stop_mask[kInfWarps];
+    int warp_n[kInfWarps], warp_b[kInfWarps];      // symbols / bytes per warp (scan)
+    int end_flag; uint32_t end_pos;                // of the lane that closes the round
+    int type, nlen, ndist, last; uint32_t bp;      // block header, from thread 0
+    int ok;
+};
+
+// Construction of one code's tables from tb.lens[first .. first + nsym) by the whole CTA.
+__device__ __forceinline__ bool cta_build_code(InflateShared &sh, int first, int nsym, bool lit) {
+    FastTables &tb = sh.tb;
+    const int tid = threadIdx.x, lane = tid & 31;
     FastCanon &c = lit ? tb.lc : tb.dc;
     uint16_t *syms = lit ? tb.lsym : tb.dsym;
-    if (lane < 16) c.count[lane] = 0;
-    __syncwarp();
-    fast_count(tb.lens + first, nsym, c, lane, 32);
-    __syncwarp();
-    bool ok = true;
-    if (lane == 0) ok = fast_ranges(c);
-    ok = __shfl_sync(kFull, ok, 0);
-    __syncwarp();
-    if (!ok) return false;
-    // symbols ordered by (length, symbol), 32 at a time (fast_sort is the sequential statement): a symbol's slot is
-    // its length's running cursor plus its rank among the lanes holding the same length
-    uint16_t *next = reinterpret_cast<uint16_t *>(tb.stage);
-    if (lane < 16) next[lane] = c.offs[lane];
-    __syncwarp();
-    for (int base = 0; base < nsym; base += 32) {
-        const int i = base + lane;
-        const int l = i < nsym ? tb.lens[first + i] : 0;
-        const unsigned peers = __match_any_sync(kFull, l);
-        const int rank = __popc(peers & ((1u << lane) - 1u));
-        const int start = next[l];
+    if (tid < 16) c.count[tid] = 0;
+    __syncthreads();
+    fast_count(tb.lens + first, nsym, c, tid, kSubLanes);
+    __syncthreads();
+    if (tid == 0) sh.ok = fast_ranges(c);
+    __syncthreads();
+    if (!sh.ok) return false;
+    if (tid < 32) {
+        // symbols ordered by (length, symbol), 32 at a time by the first warp (fast_sort is the sequential
+        // statement): a symbol's slot is its length's running cursor plus its rank among the lanes of equal length
+        uint16_t *next = reinterpret_cast<uint16_t *>(tb.stage);
+        if (lane < 16) next[lane] = c.offs[lane];
         __syncwarp();
-        if (l) {
-            syms[start + rank] = (uint16_t)i;
-            if (rank == 0) next[l] = (uint16_t)(start + __popc(peers));
+        for (int base = 0; base < nsym; base += 32) {
+            const int i = base + lane;
+            const int l = i < nsym ? tb.lens[first + i] : 0;
+            const unsigned peers = __match_any_sync(kFull, l);
+            const int rank = __popc(peers & ((1u << lane) - 1u));
+            const int start = next[l];
+            __syncwarp();
+            if (l) {
+                syms[start + rank] = (uint16_t)i;
+                if (rank == 0) next[l] = (uint16_t)(start + __popc(peers));
+            }
+            __syncwarp();
         }
-        __syncwarp();
     }
-    fast_fill(c, syms, lit ? tb.lit : tb.dst, lit ? kFLitBits : kFDstBits, lit, lane, 32);
-    __syncwarp();
-    return ok;
+    __syncthreads();
+    fast_fill(c, syms, lit ? tb.lit : tb.dst, lit ? kFLitBits : kFDstBits, lit, tid, kSubLanes);
+    __syncthreads();
+    return true;
 }
 
 // The symbols of one Huffman block, starting at bit `q` (a true symbol boundary).  Returns false on an error.
-__device__ __forceinline__ bool warp_block_symbols(const StreamBits &sb, uint32_t data_end, FastTables &tb, uint32_t &q,
-                                                   uint32_t *syms, int &ns, int &op, int sym_cap, int out_cap, int lane) {
+// Every thread of the CTA calls it; q, ns, op are kept identical in all threads.
+__device__ __forceinline__ bool cta_block_symbols(const StreamBits &sb, uint32_t data_end, InflateShared &sh, uint32_t &q,
+                                                  uint32_t *syms, int &ns, int &op, int sym_cap, int out_cap) {
+    FastTables &tb = sh.tb;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (;;) {
         const uint32_t w0 = q >> 5, origin = w0 << 5;
-        for (int j = lane; j < kStageWords; j += 32) tb.stage[stage_slot(j)] = sb.word(w0 + j);
-        __syncwarp();
-        const uint32_t limit = min(q + (uint32_t)(lane + 1) * kSubBits, data_end);
-        uint32_t start = q + (uint32_t)lane * kSubBits, cur = 0xffffffffu;
+        for (int j = tid; j < kStageWords; j += kSubLanes) tb.stage[stage_slot(j)] = sb.word(w0 + j);
+        __syncthreads();
+        const uint32_t limit = min(q + (uint32_t)(tid + 1) * kSubBits, data_end);
+        uint32_t start = q + (uint32_t)tid * kSubBits, cur = 0xffffffffu;
         Span r{0u, 0, 0, kSpanRun};
-        int confirmed = 0, last;
+        int confirmed = 0, last = -1;
         for (;;) {  // rounds: lanes at and after the first unconfirmed one decode from where their predecessor ended
-            if (lane >= confirmed && start != cur) { decode_span<false>(tb.stage, origin, start, limit, data_end, tb, nullptr, 0, r); cur = start; }
-            const uint32_t prev_end = __shfl_up_sync(kFull, r.end, 1);
-            const unsigned ok = __ballot_sync(kFull, lane == 0 || cur == prev_end);
-            const int c = ok == kFull ? 32 : __ffs((int)~ok) - 1;  // lanes [0, c) decoded from true boundaries
-            const unsigned stops = __ballot_sync(kFull, r.flag != kSpanRun) & (c == 32 ? kFull : ((1u << c) - 1u));
-            if (stops) { last = __ffs((int)stops) - 1; break; }  // the block (or the data) ends in a confirmed lane
-            if (c == 32) { last = 31; break; }
+            if (tid >= confirmed && start != cur) { decode_span<false>(tb.stage, origin, start, limit, data_end, tb, nullptr, 0, r); cur = start; }
+            sh.ends[tid] = r.end;
+            __syncthreads();
+            const uint32_t prev_end = tid ? sh.ends[tid - 1] : 0u;
+            const unsigned okm = __ballot_sync(kFull, tid == 0 || cur == prev_end);
+            const unsigned stm = __ballot_sync(kFull, r.flag != kSpanRun);
+            if (lane == 0) { sh.ok_mask[warp] = okm; sh.stop_mask[warp] = stm; }
+            __syncthreads();
+            int c = 0;  // lanes [0, c) decoded from true boundaries
+            for (int w = 0; w < kInfWarps; w++) {
+                const unsigned m = sh.ok_mask[w];
+                if (m == kFull) c += 32; else { c += __ffs((int)~m) - 1; break; }
+            }
+            for (int w = 0; w < kInfWarps && last < 0 && 32 * w < c; w++) {  // the block (or the data) ends in a confirmed lane?
+                const int k = c - 32 * w;
+                const unsigned m = sh.stop_mask[w] & (k >= 32 ? kFull : ((1u << k) - 1u));
+                if (m) last = 32 * w + __ffs((int)m) - 1;
+            }
+            if (last >= 0) break;
+            if (c == kSubLanes) { last = kSubLanes - 1; break; }
             confirmed = c;
-            if (lane >= c) start = prev_end;
+            if (tid >= c) start = prev_end;
         }
-        const int end_flag = __shfl_sync(kFull, r.flag, last);
-        if (end_flag == kSpanBad) return false;
-        const int n = lane <= last ? r.n : 0, bytes = lane <= last ? r.n + r.extra : 0;
+        if (tid == last) { sh.end_flag = r.flag; sh.end_pos = r.end; }
+        const int n = tid <= last ? r.n : 0, bytes = tid <= last ? r.n + r.extra : 0;
         int in_n = n, in_b = bytes;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const int tn = __shfl_up_sync(kFull, in_n, d), tb_ = __shfl_up_sync(kFull, in_b, d);
             if (lane >= d) { in_n += tn; in_b += tb_; }
         }
-        const int tot_n = __shfl_sync(kFull, in_n, 31), tot_b = __shfl_sync(kFull, in_b, 31);
+        if (lane == 31) { sh.warp_n[warp] = in_n; sh.warp_b[warp] = in_b; }
+        __syncthreads();
+        const int end_flag = sh.end_flag;
+        if (end_flag == kSpanBad) return false;
+        int off_n = 0, off_b = 0, tot_n = 0, tot_b = 0;
+        for (int w = 0; w < kInfWarps; w++) {
+            if (w < warp) { off_n += sh.warp_n[w]; off_b += sh.warp_b[w]; }
+            tot_n += sh.warp_n[w]; tot_b += sh.warp_b[w];
+        }
         if (ns + tot_n > sym_cap || op + tot_b > out_cap) return false;
         Span w{0u, 0, 0, kSpanRun};
-        if (lane <= last) decode_span<true>(tb.stage, origin, cur, limit, data_end, tb, syms + ns + in_n - n, op + in_b - bytes, w);
-        if (__ballot_sync(kFull, w.flag == kSpanFar)) return false;
+        if (tid <= last) decode_span<true>(tb.stage, origin, cur, limit, data_end, tb, syms + ns + off_n + in_n - n, op + off_b + in_b - bytes, w);
         ns += tot_n; op += tot_b;
-        q = __shfl_sync(kFull, r.end, last);
-        __syncwarp();  // the staging area is rewritten next
+        q = sh.end_pos;
+        if (__syncthreads_or(w.flag == kSpanFar)) return false;  // (also: the staging area is rewritten next)
         if (end_flag == kSpanEob) return q <= data_end;
     }
 }
 
-__global__ void __launch_bounds__(32 * kInfWarps) k_inflate_sym(StreamSrc src, const uint8_t *__restrict__ fl, int B,
-                                                                uint32_t *__restrict__ syms_all, int64_t sym_stride, int out_cap,
-                                                                int32_t *__restrict__ nsym, int32_t *__restrict__ out_len,
-                                                                uint32_t *__restrict__ adler_want, uint32_t *__restrict__ status) {
-    extern __shared__ __align__(16) unsigned char tb_raw[];
-    FastTables &tb = reinterpret_cast<FastTables *>(tb_raw)[threadIdx.x >> 5];
-    const int i = blockIdx.x * kInfWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (i >= B) return;
-    if (lane == 0) { nsym[i] = 0; out_len[i] = 0; adler_want[i] = 1; }
+__global__ void __launch_bounds__(kSubLanes) k_inflate_sym(StreamSrc src, const uint8_t *__restrict__ fl, int B,
+                                                           uint32_t *__restrict__ syms_all, int64_t sym_stride, int out_cap,
+                                                           int32_t *__restrict__ nsym, int32_t *__restrict__ out_len,
+                                                           uint32_t *__restrict__ adler_want, uint32_t *__restrict__ status) {
+    extern __shared__ __align__(16) unsigned char inf_raw[];
+    InflateShared &sh = *reinterpret_cast<InflateShared *>(inf_raw);
+    const int i = blockIdx.x, tid = threadIdx.x;
+    if (tid == 0) { nsym[i] = 0; out_len[i] = 0; adler_want[i] = 1; }
     if (status[i] || (fl && !(fl[i] & 4u))) return;
     const uint8_t *in = src.ptr(i);
     const int in_len = src.size(i);
@@ -172,34 +206,34 @@ __global__ void __launch_bounds__(32 * kInfWarps) k_inflate_sym(StreamSrc src, c
     int ns = 0, op = 0;
     bool last = false;
     while (good && !last) {
-        int type = -1, nlen = 0, ndist = 0;
-        if (lane == 0) {
+        if (tid == 0) {
             BitReader br{in, dlen, 0, 0, 0, false};
             br.seek(bp);
             bool l = false;
-            type = inflate_block_header(br, tb, &l, &nlen, &ndist);
+            int nlen = 0, ndist = 0;
+            int type = inflate_block_header(br, sh.tb, &l, &nlen, &ndist);
             if (br.bad) type = -1;
-            last = l;
-            bp = br.tell();
+            sh.type = type; sh.nlen = nlen; sh.ndist = ndist; sh.last = l; sh.bp = br.tell();
         }
-        type = __shfl_sync(kFull, type, 0); nlen = __shfl_sync(kFull, nlen, 0); ndist = __shfl_sync(kFull, ndist, 0);
-        last = __shfl_sync(kFull, (int)last, 0) != 0; bp = __shfl_sync(kFull, bp, 0);
-        __syncwarp();
+        __syncthreads();
+        const int type = sh.type, nlen = sh.nlen, ndist = sh.ndist;
+        last = sh.last != 0; bp = sh.bp;
         if (type < 0) { good = false; break; }
         if (type == 0) {  // stored: LEN bytes at a byte boundary become literal symbols
             const int at = (int)(bp >> 3);
             if (at + nlen > dlen || ns + nlen > sym_cap || op + nlen > out_cap) { good = false; break; }
-            for (int k = lane; k < nlen; k += 32) syms[ns + k] = in[at + k];
+            for (int k = tid; k < nlen; k += kSubLanes) syms[ns + k] = in[at + k];
             ns += nlen; op += nlen; bp += 8u * (uint32_t)nlen;
+            __syncthreads();  // sh.type is rewritten by the next header
             continue;
         }
-        if (!warp_build_code(tb, 0, nlen, true, lane) || !warp_build_code(tb, nlen, ndist, false, lane)) { good = false; break; }
+        if (!cta_build_code(sh, 0, nlen, true) || !cta_build_code(sh, nlen, ndist, false)) { good = false; break; }
         uint32_t q = bp + sb.skew;
-        good = warp_block_symbols(sb, data_end, tb, q, syms, ns, op, sym_cap, out_cap, lane);
+        good = cta_block_symbols(sb, data_end, sh, q, syms, ns, op, sym_cap, out_cap);
         bp = q - sb.skew;
     }
     if (good && (int)((bp + 7) >> 3) != dlen) good = false;  // the trailer follows the last block at the next byte boundary
-    if (lane) return;
+    if (tid) return;
     if (!good) { status[i] |= 16u; return; }  // CCT_ST_INFLATE
     const uint8_t *t = in + dlen;
     nsym[i] = ns; out_len[i] = op;
@@ -284,10 +318,9 @@ __global__ void __launch_bounds__(256) k_adler_check(const uint8_t *__restrict__
 
 static void launch_inflate_passes(StreamSrc src, const uint8_t *fl, int B, const InflateWs &iw, uint8_t *out,
                                   int64_t out_stride, int32_t *out_len, uint32_t *status, cudaStream_t st) {
-    const int smem = kInfWarps * (int)sizeof(FastTables);
     { CCT_KERNEL(k_inflate_sym, st);
-    k_inflate_sym<<<(B + kInfWarps - 1) / kInfWarps, 32 * kInfWarps, smem, st>>>(src, fl, B, iw.syms, iw.sym_stride, (int)out_stride,
-                                                                                iw.nsym, out_len, iw.adler, status);
+    k_inflate_sym<<<B, kSubLanes, sizeof(InflateShared), st>>>(src, fl, B, iw.syms, iw.sym_stride, (int)out_stride,
+                                                             iw.nsym, out_len, iw.adler, status);
     }
     { CCT_KERNEL(k_lz_expand, st);
     k_lz_expand<<<(B + kLzWarps - 1) / kLzWarps, 32 * kLzWarps, 0, st>>>(iw.syms, iw.sym_stride, iw.nsym, out, out_stride, B);

@@ -313,10 +313,10 @@ CCT_HDN inline int inflate_symbols(const uint8_t *in, int in_len, uint32_t *syms
 // ------------------------------------------------------------------------------------------------
 // Lane-parallel Huffman decode (the form k_inflate_sym runs; tests/hostsim steps the same scalar pieces)
 // ------------------------------------------------------------------------------------------------
-// One stream is decoded by the 32 lanes of a warp.  Blocks are sequential (a block's header is found only when
-// the previous block ends), but inside a block the bit string is cut into rounds of 32 sub-sequences of
-// kSubBits bits, one per lane.  Lane 0 starts on a true symbol boundary; the others start speculatively at their
-// sub-sequence boundary.  Huffman codes self-synchronise: a decoder started at a wrong bit falls into step with
+// One stream is decoded by the kSubLanes threads of a CTA.  Blocks are sequential (a block's header is found only
+// when the previous block ends), but inside a block the bit string is cut into rounds of kSubLanes sub-sequences
+// of kSubBits bits, one per lane.  Lane 0 starts on a true symbol boundary; the others start speculatively at
+// their sub-sequence boundary.  Huffman codes self-synchronise: a decoder started at a wrong bit falls into step with
 // the true symbol sequence after a few symbols.  So every lane decodes to the end of its sub-sequence and reports
 // where its last symbol ended; lane i+1 then restarts from lane i's end.  A lane is CONFIRMED once it started
 // where its confirmed predecessor ended; rounds repeat (normally twice) until every lane up to the end of the
@@ -324,7 +324,7 @@ CCT_HDN inline int inflate_symbols(const uint8_t *in, int in_len, uint32_t *syms
 // symbol counts.  The reader is stateless (two staged words + a funnel shift per peek), so lanes stay in lock step.
 constexpr int kFLitBits = 10, kFDstBits = 9;   // primary lookup widths
 constexpr int kSubBits = 512;                  // bits per lane per round
-constexpr int kSubLanes = 32;
+constexpr int kSubLanes = 128;                 // sub-sequences per round = threads per stream
 constexpr int kStageWords = kSubLanes * kSubBits / 32 + 8;      // one round + the longest symbol (48 bits) + peek
 constexpr int kStageAlloc = kStageWords + kStageWords / 16 + 1; // one pad word per 16: lanes start 16 words apart
 CCT_HD int stage_slot(int w) { return w + (w >> 4); }

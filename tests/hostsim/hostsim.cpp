@@ -184,31 +184,31 @@ int hs_inflate(const uint8_t *in, int in_len, uint8_t *out, int out_cap) {
     return out_len;
 }
 
-// The lane-parallel Huffman decode of k_inflate_sym, with the 32 lanes stepped one after the other: same tables,
-// same decode_span, same confirmation rule.  `sub_lanes` < 32 narrows the round (more rounds, same result).
+// The lane-parallel Huffman decode of k_inflate_sym, with the kSubLanes lanes stepped one after the other: same
+// tables, same decode_span, same confirmation rule.
 static bool hs_block_symbols(const std::vector<uint32_t> &words, uint32_t data_end, FastTables &tb, uint32_t &q,
                              uint32_t *syms, int &ns, int &op, int sym_cap, int out_cap, int *max_rounds) {
     for (;;) {
         const uint32_t w0 = q >> 5, origin = w0 << 5;
         for (int j = 0; j < kStageWords; j++) tb.stage[stage_slot(j)] = w0 + j < words.size() ? words[w0 + j] : 0u;
-        uint32_t start[32], cur[32], limit[32];
-        Span r[32];
-        for (int l = 0; l < 32; l++) {
+        uint32_t start[kSubLanes], cur[kSubLanes], limit[kSubLanes];
+        Span r[kSubLanes];
+        for (int l = 0; l < kSubLanes; l++) {
             limit[l] = std::min(q + (uint32_t)(l + 1) * kSubBits, data_end);
             start[l] = q + (uint32_t)l * kSubBits; cur[l] = 0xffffffffu; r[l] = Span{0u, 0, 0, kSpanRun};
         }
         int confirmed = 0, last = -1, rounds = 0;
         for (;;) {
             rounds++;
-            for (int l = confirmed; l < 32; l++)
+            for (int l = confirmed; l < kSubLanes; l++)
                 if (start[l] != cur[l]) { decode_span<false>(tb.stage, origin, start[l], limit[l], data_end, tb, nullptr, 0, r[l]); cur[l] = start[l]; }
             int c = 1;
-            while (c < 32 && cur[c] == r[c - 1].end) c++;
+            while (c < kSubLanes && cur[c] == r[c - 1].end) c++;
             for (int l = 0; l < c && last < 0; l++) if (r[l].flag != kSpanRun) last = l;
             if (last >= 0) break;
-            if (c == 32) { last = 31; break; }
+            if (c == kSubLanes) { last = kSubLanes - 1; break; }
             confirmed = c;
-            for (int l = 31; l >= c; l--) start[l] = r[l - 1].end;
+            for (int l = kSubLanes - 1; l >= c; l--) start[l] = r[l - 1].end;
         }
         if (max_rounds && rounds > *max_rounds) *max_rounds = rounds;
         const int end_flag = r[last].flag;
