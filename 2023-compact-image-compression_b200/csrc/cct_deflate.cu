@@ -217,13 +217,13 @@ __device__ __forceinline__ RunCarry run_combine(RunCarry a, RunCarry b) {  // a 
 }
 
 // The chunk's bytes, one per lane per step (c[j] = w[base + 32 j + lane], 0 past the end), and the bytes around it.
-struct RunBytes { uint32_t c[kRunSteps]; uint32_t before, after; };  // before = w[base - 1]; after: lanes 0,1 hold w[base + kRunChunk + lane]
+struct RunBytes { uint32_t c[kRunSteps]; uint32_t before, after; };  // before = w[base - 1]; after: lanes 0..2 hold w[base + kRunChunk + lane]
 __device__ __forceinline__ void run_bytes(RunBytes &r, const uint8_t *w, int n, int base, int lane) {
 #pragma unroll
     for (int j = 0; j < kRunSteps; j++) { const int p = base + 32 * j + lane; r.c[j] = p < n ? __ldg(w + p) : 0u; }
     r.before = base > 0 ? __ldg(w + base - 1) : 0u;
     const int q = base + kRunChunk + lane;
-    r.after = (lane < 2 && q < n) ? __ldg(w + q) : 0u;
+    r.after = (lane < 3 && q < n) ? __ldg(w + q) : 0u;
 }
 // step j: mask of lanes whose byte equals the byte before it / after it (false outside the payload)
 __device__ __forceinline__ unsigned run_eq_prev(const RunBytes &r, int j, int n, int base, int lane) {
@@ -303,8 +303,9 @@ __global__ void __launch_bounds__(32 * kRunWarps) k_run_recs(const uint8_t *__re
     if (base >= n) return;
     const uint16_t *d16 = dist16 + (int64_t)stream * stride;
     ChainRec *recs = recs_all + (int64_t)stream * stride;
+    const uint8_t *w = in + (int64_t)stream * in_stride;
     RunBytes r;
-    run_bytes(r, in + (int64_t)stream * in_stride, n, base, lane);
+    run_bytes(r, w, n, base, lane);
     const int2 enter = enters[(int64_t)stream * max_chunks + chunk];
     uint32_t link[kRunSteps];  // chain links of the chunk, fetched up front with the bytes (all loads in flight at once)
 #pragma unroll
@@ -326,12 +327,26 @@ __global__ void __launch_bounds__(32 * kRunWarps) k_run_recs(const uint8_t *__re
         const unsigned zeros_above = ~m & ~((1u << lane) - 1u);  // positions >= lane whose flag is 0
         const int fwd = zeros_above ? (__ffs((int)zeros_above) - 1) - lane : (32 - lane) + carry;
         carry = __shfl_sync(kAll, fwd, 0);
-        // w[p + 1], w[p + 2]: the next lanes' bytes, or the first lanes of the next group
+        // w[p + 1 .. p + 3]: the next lanes' bytes, or the first lanes of the next group
         const uint32_t next_group = j + 1 < kRunSteps ? r.c[j + 1] : r.after;
-        const uint32_t a1 = __shfl_sync(kAll, r.c[j], (lane + 1) & 31), n1 = __shfl_sync(kAll, next_group, (lane + 1) & 31);
-        const uint32_t a2 = __shfl_sync(kAll, r.c[j], (lane + 2) & 31), n2 = __shfl_sync(kAll, next_group, (lane + 2) & 31);
+        uint32_t quad = r.c[j];
+#pragma unroll
+        for (int i = 1; i <= 3; i++) {
+            const uint32_t a = __shfl_sync(kAll, r.c[j], (lane + i) & 31), nx = __shfl_sync(kAll, next_group, (lane + i) & 31);
+            quad |= (lane + i < 32 ? a : nx) << (8 * i);
+        }
         const int p = base + 32 * j + lane;
-        if (p < n) store_rec(recs + p, make_rec((int)link[j], min(fwd, 65535), (int)rb[j], (uint8_t)r.c[j], (uint8_t)(lane < 31 ? a1 : n1), (uint8_t)(lane < 30 ? a2 : n2)));
+        if (p < n) {
+            const int rl = min(fwd, 65535);
+            ChainRec rec = pack_rec_plain((int)link[j], rl, quad);
+            if (rl >= 2) {
+                // a run position: the link of the bottom of its run group and the byte after the run (one address per
+                // run, so the lanes of a run share the loads)
+                const int bottom = max(p - (int)rb[j], 1), q = p + rl + 1;
+                rec = pack_rec_run((int)__ldg(d16 + bottom), rl, (int)rb[j], r.c[j], (rl < 65535 && q < n) ? (uint32_t)__ldg(w + q) : 0u);
+            }
+            store_rec(recs + p, rec);
+        }
     }
 }
 

@@ -84,26 +84,50 @@ CCT_HD uint32_t static_lcode(int n) {
 // longest_match
 // ------------------------------------------------------------------------------------------------
 // Everything the chain walk needs to know about a position, in one aligned 8-byte load.  (The walk is bound by
-// the number of distinct memory sectors its divergent loads touch, so the hash triple is carried here too:
-// candidates that merely share the hash, and the first three bytes of real ones, never touch the payload.)
-struct alignas(8) ChainRec {
-    uint16_t dist;  // chain link: distance to the previous position with the same hash, 0 = none / >= 32768
-    uint16_t rl;    // number of bytes equal to w[p] immediately after p (capped at 65535)
-    uint16_t x;     // rl >= 2 (p starts a triple (c,c,c)): number of bytes equal to w[p] immediately before p
-                    // (capped at 65535); otherwise w[p+1] | w[p+2] << 8
-    uint8_t b0;     // w[p]
-    uint8_t pad;
-};
-CCT_HD ChainRec make_rec(int dist, int rl, int rb, uint8_t b0, uint8_t b1, uint8_t b2) {
-    ChainRec r;
-    r.dist = (uint16_t)dist; r.rl = (uint16_t)rl; r.b0 = b0; r.pad = 0;
-    r.x = rl >= 2 ? (uint16_t)rb : (uint16_t)(b1 | (b2 << 8));
-    return r;
+// the instructions it issues and the distinct memory sectors its divergent loads touch, so a record carries enough
+// of the payload that the common candidate -- same hash, at most three matching bytes -- never touches the payload.)
+//   a.lo16  link: distance to the previous position with the same hash, 0 = none / >= 32768.  For a run position
+//           (rl >= 2) it is the link of the BOTTOM of its run group, position max(p - rb, 1): the position's own link
+//           is then implied (1 inside a run, because p-1 starts the same triple; 0 at position 1) and the group step
+//           needs the bottom's.
+//   a.hi16  rl: number of bytes equal to w[p] immediately after p (capped at 65535)
+//   b       rl <  2: w[p] | w[p+1] << 8 | w[p+2] << 16 | w[p+3] << 24   (0 past the end)
+//           rl >= 2: rb | w[p] << 16 | ba << 24 with rb = number of bytes equal to w[p] immediately before p (capped at
+//                    65535) and ba = w[p + rl + 1], the first byte after the run (0 past the end or when rl is capped)
+struct alignas(8) ChainRec { uint32_t a, b; };
+CCT_HD int rec_link(const ChainRec &r) { return (int)(r.a & 0xFFFFu); }
+CCT_HD int rec_rl(const ChainRec &r) { return (int)(r.a >> 16); }
+CCT_HD bool rec_is_run(const ChainRec &r) { return r.a >= 0x20000u; }
+CCT_HD int rec_rb(const ChainRec &r) { return (int)(r.b & 0xFFFFu); }            // run records only
+CCT_HD uint32_t rec_run_byte(const ChainRec &r) { return (r.b >> 16) & 0xFFu; }  // run records only
+CCT_HD uint32_t rec_after(const ChainRec &r) { return r.b >> 24; }               // run records only
+// the position's own chain link
+CCT_HD int rec_own_dist(const ChainRec &r, int p) { return (rec_is_run(r) && rec_rb(r)) ? (p >= 2 ? 1 : 0) : rec_link(r); }
+// the first four payload bytes at the position (byte 3 of a run record: the run goes on, or the byte after it)
+CCT_HD uint32_t rec_quad(const ChainRec &r) {
+    if (!rec_is_run(r)) return r.b;
+    const uint32_t c = rec_run_byte(r);
+    return c * 0x010101u | ((rec_rl(r) >= 3 ? c : rec_after(r)) << 24);
+}
+CCT_HD ChainRec pack_rec_plain(int link, int rl, uint32_t quad) { return ChainRec{(uint32_t)link | ((uint32_t)rl << 16), quad}; }
+CCT_HD ChainRec pack_rec_run(int bottom_link, int rl, int rb, uint32_t c, uint32_t after) {
+    return ChainRec{(uint32_t)bottom_link | ((uint32_t)rl << 16), (uint32_t)rb | (c << 16) | (after << 24)};
+}
+// The record of position p from the plain arrays (dist16 = own links, rl / rb = capped run counts).
+CCT_HD ChainRec make_rec(const uint8_t *w, int n, const uint16_t *dist16, int p, int rl, int rb) {
+    if (rl >= 2) {
+        const int bottom = p - rb < 1 ? 1 : p - rb;
+        const int q = p + rl + 1;
+        return pack_rec_run(dist16[bottom], rl, rb, w[p], (rl < 65535 && q < n) ? w[q] : 0u);
+    }
+    uint32_t quad = 0;
+    for (int i = 0; i < 4; i++) if (p + i < n) quad |= (uint32_t)w[p + i] << (8 * i);
+    return pack_rec_plain(dist16[p], rl, quad);
 }
 
-CCT_HD void store_rec(ChainRec *p, const ChainRec &r) {  // one 8-byte store (the compiler would emit three)
+CCT_HD void store_rec(ChainRec *p, const ChainRec &r) {  // one 8-byte store
 #if defined(__CUDA_ARCH__)
-    *reinterpret_cast<uint2 *>(p) = make_uint2((uint32_t)r.dist | ((uint32_t)r.rl << 16), (uint32_t)r.x | ((uint32_t)r.b0 << 16));
+    *reinterpret_cast<uint2 *>(p) = make_uint2(r.a, r.b);
 #else
     *p = r;
 #endif
@@ -112,10 +136,7 @@ CCT_HD void store_rec(ChainRec *p, const ChainRec &r) {  // one 8-byte store (th
 CCT_HD ChainRec load_rec(const ChainRec *p) {
 #if defined(__CUDA_ARCH__)
     const uint2 q = __ldg(reinterpret_cast<const uint2 *>(p));
-    ChainRec r;
-    r.dist = (uint16_t)(q.x & 0xFFFFu); r.rl = (uint16_t)(q.x >> 16);
-    r.x = (uint16_t)(q.y & 0xFFFFu); r.b0 = (uint8_t)(q.y >> 16); r.pad = 0;
-    return r;
+    return ChainRec{q.x, q.y};
 #else
     return *p;
 #endif
@@ -123,7 +144,7 @@ CCT_HD ChainRec load_rec(const ChainRec *p) {
 
 struct LzView {
     const uint8_t *w;       // payload bytes
-    const ChainRec *recs;   // per-position record (k_chains)
+    const ChainRec *recs;   // per-position record (k_run_recs)
     int n;                  // payload length
 };
 
@@ -156,52 +177,55 @@ constexpr int kWalkSteps = 2;   // step cap of the probe reached
 // of c, the match length of the i-th member is known in closed form from its count of leading c's, m + i:
 // m+i if m+i < R, "R + whatever follows" if m+i == R, exactly R if m+i > R (R < cap), cap if R == cap.
 // Since only the first-visited candidate attaining the maximum matters, the group is consumed in
-// one step; the chain budget and the distance limit are charged as if every member had been visited.
-// The walk is a resumable state machine (chain_begin / chain_step) so the probe kernel can keep every lane
-// of a warp on one step per iteration and hand a finished lane its next position; chain_walk runs it to the end.
+// one step; the chain budget and the distance limit are charged as if every member had been visited.  "Whatever
+// follows" starts with the byte after either run, which both records carry: the payload is read only when they agree.
+// A single candidate is compared through the four payload bytes in its record: a candidate that merely shares the
+// hash, or matches exactly three bytes, is settled without touching the payload.
+// The walk is a resumable state machine (chain_begin / chain_step); chain_walk runs it to the end.
 constexpr int kWalkContinue = -1;
 struct ChainState {
     int s, cap, best, bdist, chain, steps_left, cur, R;
-    uint8_t b0;        // target byte 0
-    uint16_t b12;      // target bytes 1, 2 (as in ChainRec::x of a non-run position)
+    uint32_t quad;   // target bytes 0..3
+    uint32_t after;  // R != 0: the byte after the target's run (meaningful when R < cap)
 };
 
-CCT_HD void chain_begin(const LzView &v, int s, int cap, int best, int chain, int max_steps, ChainState &c) {
+// Returns the target's own chain link (0: no chain).
+CCT_HD int chain_begin(const LzView &v, int s, int cap, int best, int chain, int max_steps, ChainState &c) {
     const ChainRec rs = load_rec(v.recs + s);
     c.s = s; c.cap = cap; c.best = best; c.bdist = 0; c.chain = chain; c.steps_left = max_steps;
-    c.b0 = rs.b0;
-    c.b12 = rs.rl >= 2 ? (uint16_t)(rs.b0 | (rs.b0 << 8)) : rs.x;
-    c.R = 0;  // leading run of the target, if it is at least one hash triple long
-    if (rs.rl >= 2) { c.R = (int)rs.rl + 1; if (c.R > cap) c.R = cap; }
-    c.cur = s - rs.dist;
+    c.quad = rec_quad(rs);
+    c.R = 0; c.after = 0;  // leading run of the target, if it is at least one hash triple long
+    if (rec_is_run(rs)) { c.R = rec_rl(rs) + 1; if (c.R > cap) c.R = cap; c.after = rec_after(rs); }
+    const int own = rec_own_dist(rs, s);
+    c.cur = s - own;
+    return own;
 }
 
 // One loop step: a single candidate or a whole run group.  Returns kWalkContinue or how the walk ended.
 CCT_HD int chain_step(const LzView &v, ChainState &c) {
     CCT_COUNT(0);
     const int s = c.s, cap = c.cap, cur = c.cur;
-    const uint8_t *b = v.w + s;
-    const ChainRec rc = load_rec(v.recs + cur);  // one 8-byte load: link, run lengths, first two bytes of the candidate
-    const uint8_t *a = v.w + cur;
+    const ChainRec rc = load_rec(v.recs + cur);  // one 8-byte load: link, run lengths, first bytes of the candidate
+    const int dl = rec_link(rc);
     int link_from = cur;
-    int dl = rc.dist;
-    if (rc.rl >= 2) {
+    if (rec_is_run(rc)) {
         // cur starts a triple (c,c,c): the chain entries below it inside the run form one group
-        const int m = (int)rc.rl + 1;  // leading c's of the top candidate
-        int t = rc.x;                  // further candidates of this run below cur
+        const int m = rec_rl(rc) + 1;  // leading c's of the top candidate
+        int t = rec_rb(rc);            // further candidates of this run below cur
         if (cur - t < 1) t = cur - 1;  // position 0 is never in a chain
         const int count_dist = kMaxDist - (s - cur);
         int nvis = t + 1;
         if (c.chain < nvis) nvis = c.chain;
         if (count_dist < nvis) nvis = count_dist;
-        if (c.R && rc.b0 == c.b0) {
+        if (c.R && rec_run_byte(rc) == (c.quad & 0xFFu)) {
             const int R = c.R;
             const int i_key = m >= R ? 0 : R - m;  // first member with at least R leading c's
             if (R < cap && m > R) {
                 if (R > c.best) { c.best = R; c.bdist = s - cur; }
             } else if (i_key < nvis) {
-                const int c_al = cur - i_key;
-                const int L = R < cap ? match_extend(v.w + c_al, b, R, cap) : cap;
+                const int c_al = cur - i_key;  // R < cap: exactly R leading c's, then the byte after the group's run
+                int L = cap;
+                if (R < cap) L = rec_after(rc) != c.after ? R : match_extend(v.w + c_al, v.w + s, R + 1, cap);
                 if (L > c.best) { c.best = L; c.bdist = s - c_al; if (L >= cap) return kWalkDone; }
             } else {
                 const int L = m + nvis - 1;  // only members with fewer than R leading c's were reached
@@ -210,13 +234,20 @@ CCT_HD int chain_step(const LzView &v, ChainState &c) {
         }  // else: the target does not start with (c,c,c) (a hash collision): no member matches 3 bytes
         if (nvis < t + 1) return nvis == count_dist ? kWalkDone : kWalkBudget;
         c.chain -= t;
-        if (t) { link_from = cur - t; dl = v.recs[link_from].dist; }  // the bottom of the run links onwards
-    } else if (rc.b0 == c.b0 && rc.x == c.b12 && (c.best < kMinMatch || load_byte(a + c.best) == load_byte(b + c.best))) {
-        // the hash triple matches (no payload access so far); zlib's scan_end test is only a shortcut for len <= best
-        const int len = match_extend(a, b, cap < kMinMatch ? cap : kMinMatch, cap);
-        if (len > c.best) {
-            c.best = len; c.bdist = s - cur;
-            if (len >= cap) return kWalkDone;
+        link_from = cur - t;  // the bottom of the run links onwards (its link is the one in the record)
+    } else {
+        const uint32_t x = rc.b ^ c.quad;
+        if ((x & 0xFFFFFFu) == 0) {  // the hash triple matches
+            int len = cap < kMinMatch ? cap : kMinMatch;
+            if (x == 0 && cap > kMinMatch) {
+                // four bytes match: the payload decides (zlib's scan_end test is only a shortcut for len <= best)
+                const uint8_t *a = v.w + cur, *b = v.w + s;
+                len = (c.best > kMinMatch && load_byte(a + c.best) != load_byte(b + c.best)) ? 0 : match_extend(a, b, kMinMatch + 1, cap);
+            }
+            if (len > c.best) {
+                c.best = len; c.bdist = s - cur;
+                if (len >= cap) return kWalkDone;
+            }
         }
     }
     // follow the link, charge the budget and the step cap: one exit test on the common path (precedence as in
@@ -246,11 +277,10 @@ CCT_HD void match_probe(const LzView &v, int s, int K, uint32_t *lo, uint32_t *h
     *lo = *hi = 0;
     const int look = v.n - s;
     if (look < kMinMatch) return;
-    const int d0 = v.recs[s].dist;
-    if (d0 == 0 || d0 > kMaxDist) return;
     const int cap = look < kMaxMatch ? look : kMaxMatch;
     ChainState c;
-    chain_begin(v, s, cap, 2, kChainGood, K, c);
+    const int d0 = chain_begin(v, s, cap, 2, kChainGood, K, c);
+    if (d0 == 0 || d0 > kMaxDist) return;
     int r;
     while ((r = chain_step(v, c)) == kWalkContinue) {}
     const uint32_t e = r == kWalkSteps ? kProbeIncomplete : (c.best >= kMinMatch ? mtab_pack(c.best, c.bdist) : 0u);

@@ -52,7 +52,7 @@ static void match_probe_two_walks(const LzView &v, int s, int K, uint32_t *lo, u
     *lo = *hi = 0;
     const int look = v.n - s;
     if (look < kMinMatch) return;
-    const int d0 = v.recs[s].dist;
+    const int d0 = rec_own_dist(v.recs[s], s);
     if (d0 == 0 || d0 > kMaxDist) return;
     const int cap = look < kMaxMatch ? look : kMaxMatch;
     int best = 2, bdist = 0;
@@ -78,7 +78,7 @@ int64_t hs_deflate2(const uint8_t *src, int n, uint8_t *dst, int64_t cap, int pr
     runs_reference(src, n, rb16, rl16);
     std::vector<ChainRec> recs((size_t)n + 1);
     for (int p = 0; p < n; p++)
-        recs[p] = make_rec(dist16[p], rl16[p], rb16[p], src[p], (uint8_t)(p + 1 < n ? src[p + 1] : 0), (uint8_t)(p + 2 < n ? src[p + 2] : 0));
+        recs[p] = make_rec(src, n, dist16.data(), p, rl16[p], rb16[p]);
     LzView v{src, recs.data(), n};
     std::vector<uint32_t> mlo((size_t)n + 1, 0), mhi((size_t)n + 1, 0);
     int64_t n_incomplete = 0;
