@@ -20,7 +20,10 @@
 
 namespace cct {
 
-constexpr int kWalkWin = 1024;  // positions per speculative parse window
+#ifndef CCT_WALK_WIN
+#define CCT_WALK_WIN 1024
+#endif
+constexpr int kWalkWin = CCT_WALK_WIN;  // positions per speculative parse window
 constexpr int kProbeK = 64;  // loop steps of the parallel probe (run groups count as one step)
 
 static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
@@ -42,7 +45,8 @@ size_t deflate_ws_carve(DeflateWs *ws, void *mem, int B, int64_t max_len) {
     ws->mhi = (uint32_t *)take((size_t)B * ws->stride * sizeof(uint32_t));
     ws->syms = ws->mtab;  // the dense symbol array reuses the probe table once the walk is over
     ws->rec = (uint32_t *)take((size_t)B * ws->stride * sizeof(uint32_t));
-    ws->flag = (uint8_t *)take((size_t)B * ws->stride);
+    ws->mask_stride = align_up(ws->stride / 32 + 1, 4);
+    ws->mask = (uint32_t *)take((size_t)B * ws->mask_stride * sizeof(uint32_t));
     ws->max_win = (int)(max_len / kWalkWin + 1);
     ws->exits = (Walk *)take((size_t)B * ws->max_win * sizeof(Walk));
     ws->blk_end = (int32_t *)take((size_t)B * ws->max_blocks * sizeof(int32_t));
@@ -62,7 +66,11 @@ size_t deflate_ws_carve(DeflateWs *ws, void *mem, int B, int64_t max_len) {
 // k_runs: per position, the count of equal bytes before and after it (forward and reverse sweep with a carry),
 // assembled with the link and the first two bytes into the 8-byte ChainRec the chain walks load.
 constexpr int kHeadEntries = 32768;
-constexpr int kChainWarps = 4;  // hash classes = warps per stream
+#ifndef CCT_CHAIN_WARPS_LOG2
+#define CCT_CHAIN_WARPS_LOG2 2
+#endif
+constexpr int kChainWarpsLog2 = CCT_CHAIN_WARPS_LOG2;
+constexpr int kChainWarps = 1 << kChainWarpsLog2;  // hash classes = warps per stream
 constexpr int kRing = 64;       // pending positions per warp
 
 struct ChainSmem {
@@ -183,7 +191,7 @@ __global__ void __launch_bounds__(32 * kChainWarps) k_chains(const uint8_t *__re
             if (mine) {
                 const int slot = (wr + __popc(bal & ((1u << lane) - 1u))) & (kRing - 1);
                 ring_s[slot] = (uint32_t)s;
-                ring_h[slot] = (uint16_t)(h >> 2);
+                ring_h[slot] = (uint16_t)(h >> kChainWarpsLog2);
             }
             if (!valid && s < n && k == 0) d16[s] = 0;
             wr += __popc(bal);
@@ -380,16 +388,30 @@ __global__ void __launch_bounds__(kProbeThreads, 8) k_probe(const uint8_t *__res
     }
 }
 
-// ------------------------------------------------------------------ parse: k_walk_spec / k_walk_stitch / k_symscan
+// ------------------------------------------------------------------ parse: k_next / k_walk_spec / k_walk_stitch / k_symscan
 // deflate_slow's lazy state machine, re-indexed by symbol start (deflate_core.cuh):
-//   k_walk_spec    one thread per kWalkWin-position window walks it speculatively from a cold start
+//   k_next         one thread per position: the symbol a walk standing there emits, from the probe table alone
+//                  (coalesced; kSymSlow where the step needs match_full or depends on the walk's history)
+//   k_walk_spec    one thread per kWalkWin-position window walks it speculatively from a cold start: one 4-byte
+//                  entry per symbol, symbol starts collected in a bit mask (32 positions per word)
 //   k_walk_stitch  one thread per stream joins the windows: it re-walks only until the true path meets the
 //                  speculative one (typically a few symbols), then adopts the window's recorded exit state
-//   k_symscan      CTA per stream: prefix sum of the symbol-start flags -> dense symbol array, block boundaries
+//   k_symscan      CTA per stream: prefix sum over the mask -> dense symbol array, block boundaries
+__global__ void __launch_bounds__(256) k_next(const uint8_t *__restrict__ in, int64_t in_stride, const int32_t *__restrict__ in_len,
+                                              const uint32_t *__restrict__ mlo, const uint32_t *__restrict__ mhi,
+                                              uint32_t *__restrict__ rec, int64_t stride) {
+    const int stream = blockIdx.y;
+    const int n = in_len[stream];
+    const int64_t o = (int64_t)stream * stride;
+    LzView v{in + (int64_t)stream * in_stride, nullptr, n};
+    const ProbeTab mt{mlo + o, mhi + o};
+    for (int p = blockIdx.x * 256 + threadIdx.x; p < n; p += gridDim.x * 256) rec[o + p] = walk_precompute(v, mt, p);
+}
+
 __global__ void __launch_bounds__(128) k_walk_spec(const uint8_t *__restrict__ in, int64_t in_stride,
                                                    const int32_t *__restrict__ in_len, const ChainRec *__restrict__ recs,
-                                                   const uint32_t *__restrict__ mlo, const uint32_t *__restrict__ mhi, uint8_t *__restrict__ flag,
-                                                   uint32_t *__restrict__ rec, Walk *__restrict__ exits, int64_t stride,
+                                                   const uint32_t *__restrict__ mlo, const uint32_t *__restrict__ mhi, uint32_t *__restrict__ mask,
+                                                   int64_t mask_stride, uint32_t *__restrict__ rec, Walk *__restrict__ exits, int64_t stride,
                                                    int max_win) {
     const int stream = blockIdx.y;
     const int k = blockIdx.x * 128 + threadIdx.x;
@@ -398,32 +420,32 @@ __global__ void __launch_bounds__(128) k_walk_spec(const uint8_t *__restrict__ i
     if (ws >= n) return;
     const int64_t o = (int64_t)stream * stride;
     LzView v{in + (int64_t)stream * in_stride, recs + o, n};
-    exits[(int64_t)stream * max_win + k] = walk_window(v, ProbeTab{mlo + o, mhi + o}, ws, min(ws + kWalkWin, n), flag + o, rec + o);
+    exits[(int64_t)stream * max_win + k] = walk_window(v, ProbeTab{mlo + o, mhi + o}, ws, min(ws + kWalkWin, n),
+                                                       mask + (int64_t)stream * mask_stride, rec + o);
 }
 
 __global__ void __launch_bounds__(128) k_walk_stitch(const uint8_t *__restrict__ in, int64_t in_stride,
                                                     const int32_t *__restrict__ in_len, const ChainRec *__restrict__ recs,
-                                                    const uint32_t *__restrict__ mlo, const uint32_t *__restrict__ mhi, uint8_t *__restrict__ flag,
-                                                    uint32_t *__restrict__ rec, const Walk *__restrict__ exits, int64_t stride,
+                                                    const uint32_t *__restrict__ mlo, const uint32_t *__restrict__ mhi, uint32_t *__restrict__ mask,
+                                                    int64_t mask_stride, uint32_t *__restrict__ rec, const Walk *__restrict__ exits, int64_t stride,
                                                     int max_win, int B) {
     // one warp per stream, lane 0 walks: streams diverge completely, so sharing a warp would serialise them
     const int stream = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (stream >= B || (threadIdx.x & 31)) return;
     const int64_t o = (int64_t)stream * stride;
     LzView v{in + (int64_t)stream * in_stride, recs + o, in_len[stream]};
-    walk_stitch(v, ProbeTab{mlo + o, mhi + o}, kWalkWin, flag + o, rec + o, exits + (int64_t)stream * max_win);
+    walk_stitch(v, ProbeTab{mlo + o, mhi + o}, kWalkWin, mask + (int64_t)stream * mask_stride, rec + o, exits + (int64_t)stream * max_win);
 }
 
 constexpr int kScanThreads = 256;
-constexpr int kScanPer = 16;  // positions per thread per tile
-__global__ void __launch_bounds__(kScanThreads) k_symscan(const int32_t *__restrict__ in_len, const uint8_t *__restrict__ flag,
-                                                          const uint32_t *__restrict__ rec, uint32_t *__restrict__ syms,
+__global__ void __launch_bounds__(kScanThreads) k_symscan(const int32_t *__restrict__ in_len, const uint32_t *__restrict__ mask,
+                                                          int64_t mask_stride, const uint32_t *__restrict__ rec, uint32_t *__restrict__ syms,
                                                           int64_t stride, int32_t *__restrict__ blk_end, int max_blocks,
                                                           int32_t *__restrict__ nsym, int32_t *__restrict__ nflush) {
     const int stream = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n = in_len[stream];
     const int64_t o = (int64_t)stream * stride;
-    const uint8_t *fl = flag + o;
+    const uint32_t *mk = mask + (int64_t)stream * mask_stride;
     const uint32_t *rc = rec + o;
     uint32_t *out = syms + o;
     int32_t *be = blk_end + (int64_t)stream * max_blocks;
@@ -431,14 +453,11 @@ __global__ void __launch_bounds__(kScanThreads) k_symscan(const int32_t *__restr
     __shared__ int carry_s;
     if (tid == 0) carry_s = 0;
     __syncthreads();
-    for (int base = 0; base < n; base += kScanThreads * kScanPer) {
-        const int p0 = base + tid * kScanPer;
-        uint4 f4 = make_uint4(0, 0, 0, 0);
-        if (p0 < n) f4 = *reinterpret_cast<const uint4 *>(fl + p0);  // stride is a multiple of 16; tail bytes are zero
-        const uint32_t fw[4] = {f4.x, f4.y, f4.z, f4.w};
-        int cnt = 0;
-#pragma unroll
-        for (int j = 0; j < 4; j++) cnt += __popc(fw[j] & 0x01010101u);
+    const int n_words = (n + 31) >> 5;
+    for (int base = 0; base < n_words; base += kScanThreads) {  // one mask word (32 positions) per thread per tile
+        const int wi = base + tid;
+        uint32_t bits = wi < n_words ? mk[wi] : 0u;
+        const int cnt = __popc(bits);
         int incl = cnt;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -452,15 +471,11 @@ __global__ void __launch_bounds__(kScanThreads) k_symscan(const int32_t *__restr
         int idx = carry_s + woff + incl - cnt;
         __syncthreads();
         if (tid == 0) carry_s += total;
-        if (cnt) {
-#pragma unroll
-            for (int j = 0; j < kScanPer; j++) {
-                if ((fw[j >> 2] >> (8 * (j & 3))) & 1u) {
-                    const int p = p0 + j;
-                    if (idx > 0 && idx % kSymEnd == 0) be[idx / kSymEnd - 1] = p;
-                    out[idx++] = rc[p];
-                }
-            }
+        while (bits) {
+            const int p = (wi << 5) + __ffs((int)bits) - 1;
+            bits &= bits - 1;
+            if (idx > 0 && idx % kSymEnd == 0) be[idx / kSymEnd - 1] = p;
+            out[idx++] = rc[p] & ~kSymSlow;
         }
         __syncthreads();
     }
@@ -711,18 +726,22 @@ void launch_deflate(const uint8_t *in, int64_t in_stride, const int32_t *in_len,
     { CCT_KERNEL(k_probe, st);
     k_probe<<<gp, kProbeThreads, 0, st>>>(in, (uint32_t)in_stride, in_len, ws.recs, ws.mtab, ws.mhi, (uint32_t)ws.stride);
     }
-    { CCT_KERNEL(m_zero_flag, st); cudaMemsetAsync(ws.flag, 0, (size_t)B * ws.stride, st); }
+    dim3 gn((unsigned)std::min<int64_t>((max_len + 255) / 256, 512), (unsigned)B);
+    { CCT_KERNEL(k_next, st);
+    k_next<<<gn, 256, 0, st>>>(in, in_stride, in_len, ws.mtab, ws.mhi, ws.rec, ws.stride);
+    }
     dim3 gw((unsigned)((ws.max_win + 127) / 128), (unsigned)B);
     { CCT_KERNEL(k_walk_spec, st);
-    k_walk_spec<<<gw, 128, 0, st>>>(in, in_stride, in_len, ws.recs, ws.mtab, ws.mhi, ws.flag, ws.rec, ws.exits, ws.stride,
-                                    ws.max_win);
+    k_walk_spec<<<gw, 128, 0, st>>>(in, in_stride, in_len, ws.recs, ws.mtab, ws.mhi, ws.mask, ws.mask_stride, ws.rec, ws.exits,
+                                    ws.stride, ws.max_win);
     }
     { CCT_KERNEL(k_walk_stitch, st);
-    k_walk_stitch<<<(B + 3) / 4, 128, 0, st>>>(in, in_stride, in_len, ws.recs, ws.mtab, ws.mhi, ws.flag, ws.rec, ws.exits,
-                                                ws.stride, ws.max_win, B);
+    k_walk_stitch<<<(B + 3) / 4, 128, 0, st>>>(in, in_stride, in_len, ws.recs, ws.mtab, ws.mhi, ws.mask, ws.mask_stride, ws.rec,
+                                                ws.exits, ws.stride, ws.max_win, B);
     }
     { CCT_KERNEL(k_symscan, st);
-    k_symscan<<<B, kScanThreads, 0, st>>>(in_len, ws.flag, ws.rec, ws.syms, ws.stride, ws.blk_end, ws.max_blocks, ws.nsym, ws.nflush);
+    k_symscan<<<B, kScanThreads, 0, st>>>(in_len, ws.mask, ws.mask_stride, ws.rec, ws.syms, ws.stride, ws.blk_end, ws.max_blocks,
+                                          ws.nsym, ws.nflush);
     }
     { CCT_KERNEL(k_adler, st);
     k_adler<<<B, 256, 0, st>>>(in, in_stride, in_len, ws.adler);

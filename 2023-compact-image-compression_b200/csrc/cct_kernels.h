@@ -39,8 +39,9 @@ struct DeflateWs {  // device scratch for one pass over B streams of capacity ma
     ChainRec *recs;      // [B][stride] per-position record read by the chain walks
     uint32_t *mtab, *mhi;  // [B][stride] probe table: entries for chain budget 4096 / 1024
     uint32_t *syms;      // [B][stride] dense LZ77 symbols
-    uint32_t *rec;       // [B][stride] symbol decided at each symbol start
-    uint8_t *flag;       // [B][stride] 1 = a symbol starts here
+    uint32_t *rec;       // [B][stride] symbol a walk standing at each position emits (k_next; slow steps recorded by the walks)
+    uint32_t *mask;      // [B][mask_stride] bit p = a symbol starts at position p
+    int64_t mask_stride; // words per stream
     Walk *exits;         // [B][max_win] state each speculative window was left with
     int max_win;
     int32_t *blk_end;    // [B][max_blocks]

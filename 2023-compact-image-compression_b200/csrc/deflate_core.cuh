@@ -364,15 +364,68 @@ CCT_HD bool walk_same_state(const ProbeTab &mt, const Walk &a, const Walk &b) {
     return e == mt.hi[a.p] && !(e & kProbeIncomplete);
 }
 
-// Speculative walk of window [ws, we): assumes a cold symbol start at ws.  Marks flag[p] = 1 and records
-// rec[p] = symbol for every symbol start it visits; returns the state it leaves the window with.
-CCT_HD Walk walk_window(const LzView &v, const ProbeTab &mtab, int ws, int we, uint8_t *flag, uint32_t *rec) {
+// The step as a function of the position alone.  From a cold start at p the machine needs lookup(p, 2) and, if that
+// finds a match of length l0, lookup(p + 1, l0); when both come straight from complete table entries the symbol and
+// the next start are known without walking -- and a walk that arrives at p+1 with the pending match this step found
+// continues exactly like a cold one there, provided the pending entry is the one a cold lookup reads (always the case
+// below good_length; above it the two budget tables must agree).  walk_precompute evaluates this for every position
+// in parallel (k_next): sym[p] = the symbol a walk standing at p emits (the advance follows from it), or kSymSlow
+// when the step needs match_full or depends on how the walk got there.  The walks themselves (walk_window /
+// walk_stitch) then chase one 4-byte entry per symbol and fall back to walk_step only on kSymSlow entries, whose
+// symbol they record in place with the marker kept.
+constexpr uint32_t kSymSlow = 0x80000000u;
+CCT_HD int sym_advance(uint32_t sym) { return sym_dist(sym & ~kSymSlow) ? sym_lc(sym) + kMinMatch : 1; }
+
+CCT_HD uint32_t walk_precompute(const LzView &v, const ProbeTab &mt, int p) {
+    const uint32_t lit = sym_pack(v.w[p], 0);
+    const int look = v.n - p;
+    if (look < kMinMatch) return lit;
+    const uint32_t e = mt.lo[p];  // lookup(p, 2)
+    if (e & kProbeIncomplete) return kSymSlow;
+    if (e == 0) return lit;
+    const int l0 = mtab_len(e), d0 = mtab_dist(e);
+    if (l0 == kMinMatch && d0 > kTooFar) return lit;
+    const uint32_t match = sym_pack(l0 - kMinMatch, d0);
+    const int look1 = look - 1;  // lookup(p + 1, l0)
+    if (look1 < kMinMatch) return match;
+    const uint32_t e1 = l0 >= kGoodLen ? mt.hi[p + 1] : mt.lo[p + 1];
+    if (e1 == 0 || l0 >= kMaxMatch || l0 >= look1) return match;
+    if (e1 & kProbeIncomplete) return kSymSlow;
+    if (mtab_len(e1) <= l0) return match;  // (a longer match is at least 4 long: the TOO_FAR rule cannot apply)
+    if (l0 >= kGoodLen && mt.lo[p + 1] != e1) return kSymSlow;  // the pending match is not what a cold lookup reads
+    return lit;
+}
+
+// One symbol of a walk over the precomputed table.  `record`: store the symbol of a slow step (the true walk and the
+// speculative window walks do; the stitch's re-run of a speculative walk does not).
+CCT_HD void walk_step_tab(const LzView &v, const ProbeTab &mtab, uint32_t *sym, Walk &w, bool record) {
+    const int q = w.p;
+    if (w.pl == 0) {
+        const uint32_t s = sym[q];
+        if (!(s & kSymSlow)) { w.p = q + sym_advance(s); return; }
+    }
+    const uint32_t s = walk_step(v, mtab, w);
+    if (record) sym[q] = s | kSymSlow;
+}
+
+// Symbol starts are kept as a bit mask, one 32-bit word per 32 positions.
+CCT_HD void mark_set(uint32_t *mask, int p) { mask[p >> 5] |= 1u << (p & 31); }
+CCT_HD void mark_clear(uint32_t *mask, int p) { mask[p >> 5] &= ~(1u << (p & 31)); }
+
+// Speculative walk of window [ws, we) (ws a multiple of 32): assumes a cold symbol start at ws.  Writes the mask words
+// of the window (bits of the symbol starts it visits, zeros elsewhere) and returns the state it leaves the window with.
+CCT_HD Walk walk_window(const LzView &v, const ProbeTab &mtab, int ws, int we, uint32_t *mask, uint32_t *sym) {
     Walk w{ws, 0, 0};
+    int word = ws >> 5;
+    uint32_t bits = 0;
     while (w.p < we) {
         const int q = w.p;
-        rec[q] = walk_step(v, mtab, w);
-        flag[q] = 1;
+        walk_step_tab(v, mtab, sym, w, true);
+        while (word < (q >> 5)) { mask[word++] = bits; bits = 0; }
+        bits |= 1u << (q & 31);
     }
+    const int last = (we + 31) >> 5;
+    while (word < last) { mask[word++] = bits; bits = 0; }
     return w;
 }
 
@@ -380,7 +433,7 @@ CCT_HD Walk walk_window(const LzView &v, const ProbeTab &mtab, int ws, int we, u
 // speculative walk S of the window in position order; S's marks that T does not confirm are cleared, T's
 // symbols are recorded, and as soon as both stand on the same symbol start in the same state the rest of the
 // window's speculation is accepted wholesale (T jumps to the recorded exit state).
-CCT_HDN inline void walk_stitch(const LzView &v, const ProbeTab &mtab, int win, uint8_t *flag, uint32_t *rec,
+CCT_HDN inline void walk_stitch(const LzView &v, const ProbeTab &mtab, int win, uint32_t *mask, uint32_t *sym,
                                 const Walk *exits) {
     Walk T{0, 0, 0};
     const int n = v.n;
@@ -393,16 +446,15 @@ CCT_HDN inline void walk_stitch(const LzView &v, const ProbeTab &mtab, int win, 
             if (!t_in && !s_in) break;
             if (t_in && s_in && T.p == S.p) {
                 if (walk_same_state(mtab, T, S)) { T = exits[k]; break; }
-                const int q = T.p;  // same start, different pending match over an incomplete probe: both move on
-                rec[q] = walk_step(v, mtab, T);
-                walk_step(v, mtab, S);
+                // same start, different pending match over an incomplete probe: both move on
+                walk_step_tab(v, mtab, sym, S, false);  // (first: T's step may rewrite the entry S must still see as slow)
+                walk_step_tab(v, mtab, sym, T, true);
             } else if (s_in && (!t_in || S.p < T.p)) {
-                flag[S.p] = 0;  // not on the true path
-                walk_step(v, mtab, S);
+                mark_clear(mask, S.p);  // not on the true path
+                walk_step_tab(v, mtab, sym, S, false);
             } else {
-                const int q = T.p;
-                rec[q] = walk_step(v, mtab, T);
-                flag[q] = 1;
+                mark_set(mask, T.p);
+                walk_step_tab(v, mtab, sym, T, true);
             }
         }
     }

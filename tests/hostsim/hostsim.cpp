@@ -93,17 +93,18 @@ int64_t hs_deflate2(const uint8_t *src, int n, uint8_t *dst, int64_t cap, int pr
     long long c1 = cct_stat[0];
     // speculative windows -> stitch -> compaction (the three parse kernels, sequentially)
     const int win = parse_win > 0 ? parse_win : 1024;
-    std::vector<uint8_t> flag((size_t)n + 1, 0);
+    std::vector<uint32_t> mask((size_t)n / 32 + 2, 0xFFFFFFFFu);  // (garbage: the window walks must write every word)
     std::vector<uint32_t> rec((size_t)n + 1, 0);
+    for (int p = 0; p < n; p++) rec[p] = walk_precompute(v, mtab, p);
     std::vector<Walk> exits((size_t)n / win + 2);
-    for (int k = 0, ws = 0; ws < n; k++, ws += win) exits[k] = walk_window(v, mtab, ws, std::min(ws + win, n), flag.data(), rec.data());
-    walk_stitch(v, mtab, win, flag.data(), rec.data(), exits.data());
+    for (int k = 0, ws = 0; ws < n; k++, ws += win) exits[k] = walk_window(v, mtab, ws, std::min(ws + win, n), mask.data(), rec.data());
+    walk_stitch(v, mtab, win, mask.data(), rec.data(), exits.data());
     std::vector<uint32_t> syms((size_t)n + 1);
     std::vector<int32_t> blk_end((size_t)n / kSymEnd + 2);
     int nsym = 0;
-    for (int p = 0; p < n; p++) if (flag[p]) {
+    for (int p = 0; p < n; p++) if ((mask[p >> 5] >> (p & 31)) & 1u) {
         if (nsym > 0 && nsym % kSymEnd == 0) blk_end[nsym / kSymEnd - 1] = p;
-        syms[nsym++] = rec[p];
+        syms[nsym++] = rec[p] & ~kSymSlow;
     }
     int n_flush = finish_blocks(nsym, nsym ? syms[nsym - 1] : 0u, n, blk_end.data());
     long long c2 = cct_stat[0];
