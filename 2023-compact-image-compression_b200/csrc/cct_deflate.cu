@@ -400,12 +400,43 @@ __global__ void __launch_bounds__(kProbeThreads, 8) k_probe(const uint8_t *__res
 __global__ void __launch_bounds__(256) k_next(const uint8_t *__restrict__ in, int64_t in_stride, const int32_t *__restrict__ in_len,
                                               const uint32_t *__restrict__ mlo, const uint32_t *__restrict__ mhi,
                                               uint32_t *__restrict__ rec, int64_t stride) {
+    // four positions per thread: 16-byte loads of the table entries and stores of the symbols (strides are multiples
+    // of 16 elements, so a quad never straddles a stream); the entry after the quad is the next thread's first
     const int stream = blockIdx.y;
     const int n = in_len[stream];
     const int64_t o = (int64_t)stream * stride;
-    LzView v{in + (int64_t)stream * in_stride, nullptr, n};
-    const ProbeTab mt{mlo + o, mhi + o};
-    for (int p = blockIdx.x * 256 + threadIdx.x; p < n; p += gridDim.x * 256) rec[o + p] = walk_precompute(v, mt, p);
+    const uint8_t *w = in + (int64_t)stream * in_stride;
+    const uint32_t *lo = mlo + o, *hi = mhi + o;
+    for (int p0 = (blockIdx.x * 256 + threadIdx.x) * 4; p0 < n; p0 += gridDim.x * 1024) {
+        const uint4 e4 = *reinterpret_cast<const uint4 *>(lo + p0);
+        const uint32_t e[5] = {e4.x, e4.y, e4.z, e4.w, p0 + 4 < n ? lo[p0 + 4] : 0u};
+        const uint32_t w4 = *reinterpret_cast<const uint32_t *>(w + p0);  // payload rows are padded to 16 bytes
+        uint32_t out[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int p = p0 + i, look = n - p;
+            const uint32_t lit = sym_pack((w4 >> (8 * i)) & 0xFFu, 0);
+            uint32_t r = lit;  // walk_precompute (deflate_core.cuh) with the entries held in registers
+            if (look >= kMinMatch) {
+                const uint32_t e0 = e[i];
+                const int l0 = mtab_len(e0), d0 = mtab_dist(e0);
+                if (e0 & kProbeIncomplete) r = kSymSlow;
+                else if (e0 != 0 && !(l0 == kMinMatch && d0 > kTooFar)) {
+                    r = sym_pack(l0 - kMinMatch, d0);
+                    const int look1 = look - 1;
+                    if (look1 >= kMinMatch) {
+                        const uint32_t e1 = l0 >= kGoodLen ? hi[p + 1] : e[i + 1];
+                        if (!(e1 == 0 || l0 >= kMaxMatch || l0 >= look1)) {
+                            if (e1 & kProbeIncomplete) r = kSymSlow;
+                            else if (mtab_len(e1) > l0) r = (l0 >= kGoodLen && e[i + 1] != e1) ? kSymSlow : lit;
+                        }
+                    }
+                }
+            }
+            out[i] = r;
+        }
+        *reinterpret_cast<uint4 *>(rec + o + p0) = make_uint4(out[0], out[1], out[2], out[3]);
+    }
 }
 
 __global__ void __launch_bounds__(128) k_walk_spec(const uint8_t *__restrict__ in, int64_t in_stride,
@@ -471,11 +502,19 @@ __global__ void __launch_bounds__(kScanThreads) k_symscan(const int32_t *__restr
         int idx = carry_s + woff + incl - cnt;
         __syncthreads();
         if (tid == 0) carry_s += total;
-        while (bits) {
-            const int p = (wi << 5) + __ffs((int)bits) - 1;
-            bits &= bits - 1;
-            if (idx > 0 && idx % kSymEnd == 0) be[idx / kSymEnd - 1] = p;
-            out[idx++] = rc[p] & ~kSymSlow;
+        // compaction, a word at a time by the whole warp: lane l looks at position 32 j + l of word j, so the symbol
+        // loads and the dense stores are coalesced
+        const int wbase = base + (wid << 5);
+#pragma unroll 4
+        for (int j = 0; j < 32; j++) {
+            const uint32_t bj = __shfl_sync(0xffffffffu, bits, j);
+            const int ij = __shfl_sync(0xffffffffu, idx, j);
+            if ((bj >> lane) & 1u) {
+                const int p = ((wbase + j) << 5) + lane;
+                const int at = ij + __popc(bj & ((1u << lane) - 1u));
+                if (at > 0 && at % kSymEnd == 0) be[at / kSymEnd - 1] = p;
+                out[at] = rc[p] & ~kSymSlow;
+            }
         }
         __syncthreads();
     }
@@ -726,7 +765,7 @@ void launch_deflate(const uint8_t *in, int64_t in_stride, const int32_t *in_len,
     { CCT_KERNEL(k_probe, st);
     k_probe<<<gp, kProbeThreads, 0, st>>>(in, (uint32_t)in_stride, in_len, ws.recs, ws.mtab, ws.mhi, (uint32_t)ws.stride);
     }
-    dim3 gn((unsigned)std::min<int64_t>((max_len + 255) / 256, 512), (unsigned)B);
+    dim3 gn((unsigned)std::min<int64_t>((max_len + 1023) / 1024, 512), (unsigned)B);
     { CCT_KERNEL(k_next, st);
     k_next<<<gn, 256, 0, st>>>(in, in_stride, in_len, ws.mtab, ws.mhi, ws.rec, ws.stride);
     }
