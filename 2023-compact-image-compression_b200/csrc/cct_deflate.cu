@@ -83,7 +83,7 @@ struct ChainSmem {
 // previous position with the same hash = the nearest lower lane holding it, else the head table; the latest
 // position of every hash ends up in the table.  Same-hash lanes inside a batch are found without a full match:
 // either every lane has one hash (a run), or all hashes are distinct -- detected by letting every lane store its
-// position and read the slot back -- or, rarely, the general case (__match_any_sync is a software loop here).
+// position and read the slot back -- or a few hashes repeat, and the lanes that lost their slot name them.
 __device__ __forceinline__ void chain_batch(volatile uint16_t *tab, uint16_t *d16, int lane, int cnt, uint32_t s, uint32_t h) {
     // `tab` is volatile on purpose: the read-back below must see what the OTHER lanes stored to the same slot
     const bool valid = lane < cnt;
@@ -103,9 +103,17 @@ __device__ __forceinline__ void chain_batch(volatile uint16_t *tab, uint16_t *d1
         if (valid) tab[h] = (uint16_t)s;
         __syncwarp();
         const bool lost = valid && tab[h] != (uint16_t)s;
-        if (__ballot_sync(0xffffffffu, lost) == 0u) peers = 1u << lane;  // all distinct: every lane owns its slot
-        else {
-            peers = __match_any_sync(0xffffffffu, h);
+        unsigned lm = __ballot_sync(0xffffffffu, lost);
+        peers = 1u << lane;  // all distinct: every lane owns its slot
+        if (lm) {
+            // a few hashes occur more than once (a third of the batches, about three hashes each): one ballot per such
+            // hash, found through the lanes that lost the slot (__match_any_sync is a software loop over all 32 lanes here)
+            do {
+                const uint32_t hl = __shfl_sync(0xffffffffu, h, __ffs((int)lm) - 1);
+                const unsigned eq = __ballot_sync(0xffffffffu, h == hl);
+                if (h == hl) peers = eq;
+                lm &= ~eq;
+            } while (lm);
             __syncwarp();
             if (valid && (peers >> lane) == 1u) tab[h] = (uint16_t)s;  // the latest position wins
         }
