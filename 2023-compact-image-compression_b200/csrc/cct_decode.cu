@@ -465,21 +465,34 @@ __global__ void __launch_bounds__(256) k_dec_scatter(const uint16_t *__restrict_
                                                      const int32_t *__restrict__ slotB, const int32_t *__restrict__ order,
                                                      const uint8_t *__restrict__ fl, const uint32_t *__restrict__ status,
                                                      uint16_t *__restrict__ px, int n_px) {
+    // four consecutive ops per thread (same unit slot): one 8-byte load of the values, and for a plain unit one
+    // 16-byte load of the four traversal entries
     const int i = blockIdx.y;
-    const int k = blockIdx.x * 256 + threadIdx.x;
-    if (k >= n_px || (status[i] & ~32u)) return;  // overflow still writes (mod 2^16), everything else leaves zeros
+    const int k0 = (blockIdx.x * 256 + threadIdx.x) * 4;
+    if (k0 >= n_px || (status[i] & ~32u)) return;  // overflow still writes (mod 2^16), everything else leaves zeros
     const int nb = n_px / kBlock;
-    const int32_t *sa = slotA + (int64_t)i * nb, *sb = slotB + (int64_t)i * nb;
-    int q = k >> 4, t = k & 15;
-    int32_t A = sa[q], Bf = sb[q];
-    int32_t pos;  // position along the (un-meshed) traversal
-    if (Bf < 0) pos = A * kBlock + t;
-    else {
-        int m = t + ((Bf & kSlotSecond) ? 16 : 0);
-        pos = ((m & 1) ? (Bf & ~kSlotSecond) : A) * kBlock + (m >> 1);
+    const int q = k0 >> 4, t0 = k0 & 15;
+    const int32_t A = slotA[(int64_t)i * nb + q], Bf = slotB[(int64_t)i * nb + q];
+    const bool fractal = (fl[i] & 1u) != 0;  // fractal flag off: raster order (core.py:426-427)
+    const uint2 v2 = *reinterpret_cast<const uint2 *>(vals + (int64_t)i * n_px + k0);
+    const uint16_t v[4] = {(uint16_t)(v2.x & 0xFFFFu), (uint16_t)(v2.x >> 16), (uint16_t)(v2.y & 0xFFFFu), (uint16_t)(v2.y >> 16)};
+    int32_t r[4];  // raster indices
+    if (Bf < 0) {
+        const int32_t pos = A * kBlock + t0;  // position along the (un-meshed) traversal
+        if (fractal) { const int4 o4 = __ldg(reinterpret_cast<const int4 *>(order + pos)); r[0] = o4.x; r[1] = o4.y; r[2] = o4.z; r[3] = o4.w; }
+        else { r[0] = pos; r[1] = pos + 1; r[2] = pos + 2; r[3] = pos + 3; }
+    } else {
+        const int m0 = t0 + ((Bf & kSlotSecond) ? 16 : 0);  // ops of a meshed pair alternate between its two blocks
+        const int32_t pa = A * kBlock + (m0 >> 1), pb = (Bf & ~kSlotSecond) * kBlock + (m0 >> 1);
+        r[0] = pa; r[1] = pb; r[2] = pa + 1; r[3] = pb + 1;
+        if (fractal) {
+#pragma unroll
+            for (int e = 0; e < 4; e++) r[e] = __ldg(order + r[e]);
+        }
     }
-    int32_t r = (fl[i] & 1u) ? __ldg(order + pos) : pos;  // fractal flag off: raster order (core.py:426-427)
-    px[(int64_t)i * n_px + r] = vals[(int64_t)i * n_px + k];
+    uint16_t *dst = px + (int64_t)i * n_px;
+#pragma unroll
+    for (int e = 0; e < 4; e++) dst[r[e]] = v[e];
 }
 
 void launch_decode(const uint8_t *files, const int64_t *offsets, int B, int rows, int cols, const int32_t *order_fractal,
@@ -511,7 +524,7 @@ void launch_decode(const uint8_t *files, const int64_t *offsets, int B, int rows
     { CCT_KERNEL(k_dec_units, st);
     k_dec_units<<<(B + kUnitWarps - 1) / kUnitWarps, 32 * kUnitWarps, 0, st>>>(ws.jflag, n_px, ws.slotA, ws.slotB, status, B);
     }
-    dim3 g((unsigned)((n_px + 255) / 256), (unsigned)B);
+    dim3 g((unsigned)((n_px / 4 + 255) / 256), (unsigned)B);
     { CCT_KERNEL(k_dec_scatter, st);
     k_dec_scatter<<<g, 256, 0, st>>>(ws.vals, ws.slotA, ws.slotB, order_fractal, ws.fl, status, px, n_px);
     }

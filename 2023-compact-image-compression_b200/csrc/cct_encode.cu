@@ -187,9 +187,11 @@ __device__ __forceinline__ int op_bytes(int delta, uint8_t *out) {
 }
 
 constexpr int kEmitThreads = 256;
+constexpr int kEmitUnitMax = 1 + 4 * kBlock;  // JUMP + 32 FULL ops
 // One CTA per image; tiles of kEmitThreads blocks; each thread sizes its unit (16 px, or 32 px + JUMP for a
-// meshed pair, nothing for a block taken as a partner), a block-wide exclusive scan places it, then the
-// thread writes its bytes.
+// meshed pair, nothing for a block taken as a partner), a block-wide exclusive scan places it, the thread writes
+// its bytes into a shared-memory image of the tile, and the CTA copies the tile out in aligned 16-byte stores (the
+// bytes past the last 16-byte boundary stay in shared memory and lead the next tile).
 __global__ void __launch_bounds__(kEmitThreads) k_emit(const uint16_t *__restrict__ hv, const uint8_t *__restrict__ jump,
                                                        const uint8_t *__restrict__ taken, uint8_t *__restrict__ payload,
                                                        int64_t pstride, int32_t *__restrict__ plen, uint32_t *__restrict__ status,
@@ -198,13 +200,12 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit(const uint16_t *__restric
     const uint16_t *h = hv + (int64_t)img * n_px;
     const uint8_t *jp = jump + (int64_t)img * nb;
     const uint8_t *tk = taken + (int64_t)img * nb;
-    uint8_t *out = payload + (int64_t)img * pstride;
+    uint8_t *out = payload + (int64_t)img * pstride;  // 16-byte aligned (pstride is a multiple of 16)
     __shared__ int warp_sum[kEmitThreads / 32];
-    __shared__ int carry_s;
     __shared__ int red_full[kEmitThreads / 32], red_dom[kEmitThreads / 32];
-    if (tid == 0) carry_s = 0;
-    __syncthreads();
+    __shared__ __align__(16) uint8_t tile[kEmitThreads * kEmitUnitMax + 32];
     int n_full = 0, dom = 0;
+    int done = 0;  // payload bytes before this tile (every thread keeps its own copy); done & 15 of them still sit in tile[]
     for (int base = 0; base < nb; base += kEmitThreads) {
         int b = base + tid;
         int size = 0, j = 0, prevv = 0;
@@ -243,15 +244,11 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit(const uint16_t *__restric
         }
         if (lane == 31) warp_sum[wid] = incl;
         __syncthreads();
-        int woff = 0;
-        for (int w = 0; w < wid; w++) woff += warp_sum[w];
-        int tile_total = 0;
-        for (int w = 0; w < kEmitThreads / 32; w++) tile_total += warp_sum[w];
-        int off = carry_s + woff + incl - size;
-        __syncthreads();
-        if (tid == 0) carry_s += tile_total;
+        int woff = 0, tile_total = 0;
+        for (int w = 0; w < kEmitThreads / 32; w++) { if (w < wid) woff += warp_sum[w]; tile_total += warp_sum[w]; }
+        const int held = done & 15;
         if (active) {
-            uint8_t *o = out + off;
+            uint8_t *o = tile + held + woff + incl - size;
             if (j) *o++ = (uint8_t)(0x80 | j);  // JUMP (core.py:290-294)
             int pv = prevv;
 #pragma unroll
@@ -261,15 +258,24 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit(const uint16_t *__restric
             }
         }
         __syncthreads();
+        const int end = held + tile_total, full = end & ~15;
+        uint4 *dst = reinterpret_cast<uint4 *>(out + (done - held));
+        for (int c = tid; c < (full >> 4); c += kEmitThreads) dst[c] = reinterpret_cast<const uint4 *>(tile)[c];
+        uint8_t keep = 0;
+        if (tid < end - full) keep = tile[full + tid];
+        __syncthreads();
+        if (tid < end - full) tile[tid] = keep;
+        done += tile_total;
+        // (the next tile's writes come after its first barrier)
     }
     // reductions for Encoder.info / status
     for (int o = 16; o; o >>= 1) { n_full += __shfl_xor_sync(0xffffffffu, n_full, o); dom |= __shfl_xor_sync(0xffffffffu, dom, o); }
     if (lane == 0) { red_full[wid] = n_full; red_dom[wid] = dom; }
     __syncthreads();
+    if (tid < (done & 15)) out[(done & ~15) + tid] = tile[tid];  // what the last tile left behind
     if (tid == 0) {
-        int total = carry_s;
-        out[total] = (uint8_t)kEOF;  // core.py:329-330
-        plen[img] = total + 1;
+        out[done] = (uint8_t)kEOF;  // core.py:329-330
+        plen[img] = done + 1;
         int nf = 0, dm = 0;
         for (int w = 0; w < kEmitThreads / 32; w++) { nf += red_full[w]; dm |= red_dom[w]; }
         if (stats) { stats[4 * img + 0] = (int32_t)(n_px - nf); stats[4 * img + 1] = nf; }
