@@ -383,19 +383,101 @@ __global__ void __launch_bounds__(128) k_dec_rawcopy(const uint8_t *__restrict__
     if (threadIdx.x == 0) { plen[i] = n; if (n < len) status[i] |= 64u; }
 }
 
-// Op stream -> values, in three parallel passes over fixed chunks (see inflate_core.cuh).
-__global__ void __launch_bounds__(128) k_dec_ops_scan(const uint8_t *__restrict__ payload, int64_t pstride,
-                                                      const int32_t *__restrict__ plen, OpsChunkSum *__restrict__ cs,
-                                                      int max_chunks, const uint32_t *__restrict__ status) {
-    const int i = blockIdx.y;
-    const int t = blockIdx.x * 128 + threadIdx.x;  // chunk * 2 + entry state
-    const int c = t >> 1, e = t & 1;
-    const int n = plen[i];
-    if (status[i] || c * kOpsChunk >= n) return;
-    int nops, dsum, ex;
-    ops_scan_chunk(payload + (int64_t)i * pstride, c * kOpsChunk, (c + 1) * kOpsChunk, n - 1, e, &nops, &dsum, &ex);
-    OpsChunkSum &o = cs[(int64_t)i * max_chunks + c];
-    o.nops[e] = nops; o.dsum[e] = dsum; o.exit_state[e] = (uint8_t)ex;
+// Op stream -> values, in three parallel passes over fixed chunks (inflate_core.cuh states them sequentially:
+// ops_scan_chunk / ops_link_chunks / ops_emit_chunk).  Here a WARP owns a chunk and a lane a byte: byte t starts an op
+// iff the number of FULL-tagged bytes (1110xxxx) immediately before it is even -- the byte after a byte without that
+// tag always starts an op, and inside a run of tagged bytes starts alternate -- so the op starts of 32 bytes follow
+// from one ballot and a few word operations (op_starts), op indices from a popc, values from a warp prefix sum.
+// The only state crossing a 32-byte step (and a chunk) is "the first byte is the low byte of a FULL op".
+constexpr int kOpsWarps = 4;
+__device__ __forceinline__ uint32_t op_starts(uint32_t E, uint32_t entry) {
+    // E: FULL-tagged bytes of the step; entry: byte 0 is the low byte of an op begun before.  Runs of tagged bytes
+    // alternate start / low byte from their first byte on: R = (E + starts) ^ E covers each such run and the byte
+    // after it, split by the parity of the run's first position (a run continuing an op begun before counts as
+    // starting at -1).
+    const uint32_t kEven = 0x55555555u;
+    uint32_t edges = E & ~(E << 1);
+    uint32_t even_starts = edges & kEven, odd_starts = edges & ~kEven;
+    if (entry & E & 1u) { even_starts &= ~1u; odd_starts |= 1u; }
+    const uint32_t re = (E + even_starts) ^ E, ro = (E + odd_starts) ^ E;
+    uint32_t S = (re & kEven) | (ro & ~kEven) | ~(re | ro);
+    if (entry & ~E & 1u) S &= ~1u;
+    return S;
+}
+
+// One 32-byte step of a chunk: the lane's byte, the byte after it, and which lanes lie before `stop`.
+struct OpsStep { uint32_t b, nb; bool valid; };
+__device__ __forceinline__ OpsStep ops_step_bytes(uint32_t word, uint32_t word_next, int i, int pos0, int stop, int lane) {
+    // `word`: the lane's 4 bytes of the current 128-byte group (byte 4 * lane + j of the group), `word_next`: same of the next
+    OpsStep r;
+    const int idx = 32 * i + lane;
+    r.b = (__shfl_sync(0xffffffffu, word, idx >> 2) >> (8 * (idx & 3))) & 0xFFu;
+    const int idn = idx + 1;
+    const uint32_t wn = __shfl_sync(0xffffffffu, word, (idn >> 2) & 31), wx = __shfl_sync(0xffffffffu, word_next, 0);
+    r.nb = ((idn < 128 ? wn : wx) >> (8 * (idn & 3))) & 0xFFu;
+    r.valid = pos0 + lane < stop;
+    return r;
+}
+__device__ __forceinline__ int op_delta(uint32_t b, uint32_t nb, bool full) {
+    if (full) { const int u = (int)(((b & 0xFu) << 8) | nb); return u > 2048 ? u - 4096 : u; }  // signed(x, 12), core.py:500-506
+    if (b & 0x80u) return 0;  // any other tag: the reference leaves the pixel unchanged
+    const int x = (int)(b & 0x7Fu);
+    return x > 64 ? x - 128 : x;  // signed(x, 7), core.py:513-516
+}
+
+__global__ void __launch_bounds__(32 * kOpsWarps) k_dec_ops_scan(const uint8_t *__restrict__ payload, int64_t pstride,
+                                                                 const int32_t *__restrict__ plen, OpsChunkSum *__restrict__ cs,
+                                                                 int max_chunks, const uint32_t *__restrict__ status) {
+    const int i = blockIdx.y, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * kOpsWarps + (threadIdx.x >> 5);
+    const int n = plen[i], lo = c * kOpsChunk;
+    if (status[i] || lo >= n) return;
+    const int end = n - 1, hi = lo + kOpsChunk, stop = hi < end ? hi : end;
+    const uint32_t *row = reinterpret_cast<const uint32_t *>(payload + (int64_t)i * pstride);  // 16-byte aligned, padded
+    const int row_words = (int)(pstride >> 2);
+    auto group = [&](int g) { const int wi = ((lo + 128 * g) >> 2) + lane; return wi < row_words ? __ldg(row + wi) : 0u; };
+    // counts and delta sums for both entry states; once both walks agree on the state they share one accumulator
+    int n0 = 0, s0 = 0, n1 = 0, s1 = 0, nc = 0, sc = 0;
+    uint32_t e0 = 0, e1 = 1;
+    uint32_t word = group(0);
+    for (int g = 0; g < kOpsChunk / 128 && lo + 128 * g < stop; g++) {
+        const uint32_t word_next = group(g + 1);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int pos0 = lo + 128 * g + 32 * k;
+            if (pos0 >= stop) break;
+            const OpsStep st = ops_step_bytes(word, word_next, k, pos0, stop, lane);
+            const bool tagged = st.valid && (st.b & 0xF0u) == 0xE0u;
+            const uint32_t E = __ballot_sync(0xffffffffu, tagged);
+            const bool jump = (st.b & 0xC0u) == 0x80u;
+            const bool full = tagged && pos0 + lane + 1 < end;
+            const bool op = st.valid && !jump && (!tagged || full);  // a pixel op if this byte starts one
+            const int d = op_delta(st.b, st.nb, full);
+            if (e0 == e1) {
+                const uint32_t S = op_starts(E, e0);
+                if (op && ((S >> lane) & 1u)) { nc++; sc += d; }
+                e0 = e1 = (E & S) >> 31;
+            } else {
+                const uint32_t S0 = op_starts(E, e0), S1 = op_starts(E, e1);
+                if (op && ((S0 >> lane) & 1u)) { n0++; s0 += d; }
+                if (op && ((S1 >> lane) & 1u)) { n1++; s1 += d; }
+                e0 = (E & S0) >> 31; e1 = (E & S1) >> 31;
+            }
+        }
+        word = word_next;
+    }
+    n0 += nc; s0 += sc; n1 += nc; s1 += sc;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        n0 += __shfl_xor_sync(0xffffffffu, n0, o); s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        n1 += __shfl_xor_sync(0xffffffffu, n1, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    }
+    if (lane == 0) {
+        OpsChunkSum &o = cs[(int64_t)i * max_chunks + c];
+        const bool more = hi < end;  // a FULL op begun on the last byte of the chunk ends in the next one
+        o.nops[0] = n0; o.dsum[0] = s0; o.exit_state[0] = (uint8_t)(more ? e0 : 0u);
+        o.nops[1] = n1; o.dsum[1] = s1; o.exit_state[1] = (uint8_t)(more ? e1 : 0u);
+    }
 }
 
 __global__ void __launch_bounds__(128) k_dec_ops_link(const int32_t *__restrict__ plen, OpsChunkSum *__restrict__ cs,
@@ -406,18 +488,62 @@ __global__ void __launch_bounds__(128) k_dec_ops_link(const int32_t *__restrict_
     status[i] |= ops_link_chunks(cs + (int64_t)i * max_chunks, n_chunks, n_px);
 }
 
-__global__ void __launch_bounds__(128) k_dec_ops_emit(const uint8_t *__restrict__ payload, int64_t pstride,
-                                                      const int32_t *__restrict__ plen, const OpsChunkSum *__restrict__ cs,
-                                                      int max_chunks, int n_px, uint16_t *__restrict__ vals,
-                                                      uint8_t *__restrict__ jflag, uint32_t *__restrict__ status) {
-    const int i = blockIdx.y;
-    const int c = blockIdx.x * 128 + threadIdx.x;
-    const int n = plen[i];
-    if ((status[i] & ~32u) || c * kOpsChunk >= n) return;
-    const uint32_t st = ops_emit_chunk(payload + (int64_t)i * pstride, c * kOpsChunk, (c + 1) * kOpsChunk, n - 1,
-                                       cs[(int64_t)i * max_chunks + c], n_px, vals + (int64_t)i * n_px,
-                                       jflag + (int64_t)i * (n_px / kBlock));
-    if (st) atomicOr(status + i, st);
+__global__ void __launch_bounds__(32 * kOpsWarps) k_dec_ops_emit(const uint8_t *__restrict__ payload, int64_t pstride,
+                                                                 const int32_t *__restrict__ plen, const OpsChunkSum *__restrict__ cs,
+                                                                 int max_chunks, int n_px, uint16_t *__restrict__ vals,
+                                                                 uint8_t *__restrict__ jflag, uint32_t *__restrict__ status) {
+    const int i = blockIdx.y, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * kOpsWarps + (threadIdx.x >> 5);
+    const int n = plen[i], lo = c * kOpsChunk;
+    if ((status[i] & ~32u) || lo >= n) return;
+    const int end = n - 1, hi = lo + kOpsChunk, stop = hi < end ? hi : end;
+    const uint32_t *row = reinterpret_cast<const uint32_t *>(payload + (int64_t)i * pstride);
+    const int row_words = (int)(pstride >> 2);
+    auto group = [&](int g) { const int wi = ((lo + 128 * g) >> 2) + lane; return wi < row_words ? __ldg(row + wi) : 0u; };
+    const OpsChunkSum sum = cs[(int64_t)i * max_chunks + c];
+    uint32_t e = sum.entry;
+    int k_base = sum.op_base, v_base = sum.val_base;  // ops and value before the step
+    uint16_t *va = vals + (int64_t)i * n_px;
+    uint8_t *jf = jflag + (int64_t)i * (n_px / kBlock);
+    uint32_t bad = 0;
+    const uint32_t below = (1u << lane) - 1u;
+    uint32_t word = group(0);
+    for (int g = 0; g < kOpsChunk / 128 && lo + 128 * g < stop && k_base < n_px; g++) {
+        const uint32_t word_next = group(g + 1);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int pos0 = lo + 128 * g + 32 * k;
+            if (pos0 >= stop) break;
+            const OpsStep st = ops_step_bytes(word, word_next, k, pos0, stop, lane);
+            const bool tagged = st.valid && (st.b & 0xF0u) == 0xE0u;
+            const uint32_t E = __ballot_sync(0xffffffffu, tagged);
+            const uint32_t S = op_starts(E, e);
+            e = (E & S) >> 31;
+            const bool start = st.valid && ((S >> lane) & 1u);
+            const bool jump = start && (st.b & 0xC0u) == 0x80u;
+            const bool full = tagged && pos0 + lane + 1 < end;
+            const bool op = start && !jump && (!tagged || full);
+            const uint32_t P = __ballot_sync(0xffffffffu, op);
+            const int kk = k_base + __popc(P & below);  // pixel ops before this byte
+            int v = op ? op_delta(st.b, st.nb, full) : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+            const int value = v_base + v;
+            if (op && kk < n_px) {
+                if (value < 0 || value > 65535) bad |= 32u;  // reference: OverflowError (core.py:506,516)
+                va[kk] = (uint16_t)value;
+            }
+            if (jump && kk < n_px) {
+                if ((kk & 15) == 0) jf[kk >> 4] = (uint8_t)(st.b & 0x3Fu);  // JUMP distance (core.py:484-494)
+                else bad |= 64u;  // a JUMP inside a unit is never produced by the encoder
+            }
+            k_base += __popc(P);
+            v_base += __shfl_sync(0xffffffffu, v, 31);
+        }
+        word = word_next;
+    }
+    bad = __reduce_or_sync(0xffffffffu, bad);
+    if (bad && lane == 0) atomicOr(status + i, bad);
 }
 
 // JUMP flags -> unit table (the first-unconsumed-block walk of core.py:459-464; resolve_units in inflate_core.cuh is
@@ -511,15 +637,15 @@ void launch_decode(const uint8_t *files, const int64_t *offsets, int B, int rows
     { CCT_KERNEL(k_dec_rawcopy, st);
     k_dec_rawcopy<<<B, 128, 0, st>>>(files, offsets, ws.fl, ws.payload, ws.pstride, ws.plen, status);
     }
-    dim3 gs((unsigned)((2 * ws.max_chunks + 127) / 128), (unsigned)B), ge((unsigned)((ws.max_chunks + 127) / 128), (unsigned)B);
+    dim3 gs((unsigned)((ws.max_chunks + kOpsWarps - 1) / kOpsWarps), (unsigned)B), ge = gs;
     { CCT_KERNEL(k_dec_ops_scan, st);
-    k_dec_ops_scan<<<gs, 128, 0, st>>>(ws.payload, ws.pstride, ws.plen, ws.chunks, ws.max_chunks, status);
+    k_dec_ops_scan<<<gs, 32 * kOpsWarps, 0, st>>>(ws.payload, ws.pstride, ws.plen, ws.chunks, ws.max_chunks, status);
     }
     { CCT_KERNEL(k_dec_ops_link, st);
     k_dec_ops_link<<<(B + 127) / 128, 128, 0, st>>>(ws.plen, ws.chunks, ws.max_chunks, n_px, status, B);
     }
     { CCT_KERNEL(k_dec_ops_emit, st);
-    k_dec_ops_emit<<<ge, 128, 0, st>>>(ws.payload, ws.pstride, ws.plen, ws.chunks, ws.max_chunks, n_px, ws.vals, ws.jflag, status);
+    k_dec_ops_emit<<<ge, 32 * kOpsWarps, 0, st>>>(ws.payload, ws.pstride, ws.plen, ws.chunks, ws.max_chunks, n_px, ws.vals, ws.jflag, status);
     }
     { CCT_KERNEL(k_dec_units, st);
     k_dec_units<<<(B + kUnitWarps - 1) / kUnitWarps, 32 * kUnitWarps, 0, st>>>(ws.jflag, n_px, ws.slotA, ws.slotB, status, B);

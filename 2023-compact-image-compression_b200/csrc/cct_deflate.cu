@@ -371,7 +371,11 @@ __global__ void __launch_bounds__(32 * kRunWarps) k_run_recs(const uint8_t *__re
 // registers so that 64 warps per SM hide the dependent chain loads.  Chain lengths vary wildly (over half the
 // positions have no chain, some need the full kProbeK steps) and only ~11 of 32 lanes are active on average; two
 // work-queue variants that refill finished lanes from a shared counter (per lane, and in rounds of >= 8 idle
-// lanes) were measured 12 % slower -- the extra state and the refill branch cost more than the idle lanes.
+// lanes) were measured 12 % slower -- the extra state and the refill branch cost more than the idle lanes.  Running
+// the walk in phases with growing step caps (2/4/10/48) and compacting the open walks in between halves the warp
+// steps on paper, yet measured 9 % slower with the phases inside one CTA (shared-memory queues, barriers) and 20 %
+// slower as separate kernels over per-stream queues: the late phases are chains of dependent L2 loads with nothing
+// else to issue, while here the short walks of other warps fill those gaps.
 constexpr int kProbeThreads = 256;
 __global__ void __launch_bounds__(kProbeThreads, 8) k_probe(const uint8_t *__restrict__ in, uint32_t in_stride,
                                                             const int32_t *__restrict__ in_len, const ChainRec *__restrict__ recs,
