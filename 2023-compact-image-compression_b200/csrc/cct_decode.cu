@@ -384,46 +384,84 @@ __global__ void __launch_bounds__(128) k_dec_rawcopy(const uint8_t *__restrict__
 }
 
 // Op stream -> values, in three parallel passes over fixed chunks (inflate_core.cuh states them sequentially:
-// ops_scan_chunk / ops_link_chunks / ops_emit_chunk).  Here a WARP owns a chunk and a lane a byte: byte t starts an op
-// iff the number of FULL-tagged bytes (1110xxxx) immediately before it is even -- the byte after a byte without that
-// tag always starts an op, and inside a run of tagged bytes starts alternate -- so the op starts of 32 bytes follow
-// from one ballot and a few word operations (op_starts), op indices from a popc, values from a warp prefix sum.
-// The only state crossing a 32-byte step (and a chunk) is "the first byte is the low byte of a FULL op".
+// ops_scan_chunk / ops_link_chunks / ops_emit_chunk).  Here a WARP owns a chunk and takes it 128 bytes at a time, a
+// lane four bytes (one word).  Byte t starts an op iff the number of FULL-tagged bytes (1110xxxx) immediately before
+// it is even: the byte after a byte without that tag always starts an op, and inside a run of tagged bytes starts
+// alternate.  So a lane needs one bit from outside its word -- the parity of the tagged run that reaches its first
+// byte -- and that is the parity of the tagged tail of the nearest lower lane that is not tagged throughout (whole
+// tagged words in between add four each), found with two ballots.  Op indices and values then come from one warp
+// prefix sum over the lanes' packed (delta sum, op count).  The only state crossing a step (and a chunk) is "the first
+// byte is the low byte of a FULL op"; k_dec_ops_scan finds the state entering its chunk by looking BACK over the
+// tagged bytes before it, so a chunk is summarised once, not once per possible entry state.
 constexpr int kOpsWarps = 4;
-__device__ __forceinline__ uint32_t op_starts(uint32_t E, uint32_t entry) {
-    // E: FULL-tagged bytes of the step; entry: byte 0 is the low byte of an op begun before.  Runs of tagged bytes
-    // alternate start / low byte from their first byte on: R = (E + starts) ^ E covers each such run and the byte
-    // after it, split by the parity of the run's first position (a run continuing an op begun before counts as
-    // starting at -1).
-    const uint32_t kEven = 0x55555555u;
-    uint32_t edges = E & ~(E << 1);
-    uint32_t even_starts = edges & kEven, odd_starts = edges & ~kEven;
-    if (entry & E & 1u) { even_starts &= ~1u; odd_starts |= 1u; }
-    const uint32_t re = (E + even_starts) ^ E, ro = (E + odd_starts) ^ E;
-    uint32_t S = (re & kEven) | (ro & ~kEven) | ~(re | ro);
-    if (entry & ~E & 1u) S &= ~1u;
-    return S;
-}
+constexpr int kOpsGroup = 128;  // bytes per warp step
 
-// One 32-byte step of a chunk: the lane's byte, the byte after it, and which lanes lie before `stop`.
-struct OpsStep { uint32_t b, nb; bool valid; };
-__device__ __forceinline__ OpsStep ops_step_bytes(uint32_t word, uint32_t word_next, int i, int pos0, int stop, int lane) {
-    // `word`: the lane's 4 bytes of the current 128-byte group (byte 4 * lane + j of the group), `word_next`: same of the next
-    OpsStep r;
-    const int idx = 32 * i + lane;
-    r.b = (__shfl_sync(0xffffffffu, word, idx >> 2) >> (8 * (idx & 3))) & 0xFFu;
-    const int idn = idx + 1;
-    const uint32_t wn = __shfl_sync(0xffffffffu, word, (idn >> 2) & 31), wx = __shfl_sync(0xffffffffu, word_next, 0);
-    r.nb = ((idn < 128 ? wn : wx) >> (8 * (idn & 3))) & 0xFFu;
-    r.valid = pos0 + lane < stop;
-    return r;
-}
 __device__ __forceinline__ int op_delta(uint32_t b, uint32_t nb, bool full) {
     if (full) { const int u = (int)(((b & 0xFu) << 8) | nb); return u > 2048 ? u - 4096 : u; }  // signed(x, 12), core.py:500-506
     if (b & 0x80u) return 0;  // any other tag: the reference leaves the pixel unchanged
     const int x = (int)(b & 0x7Fu);
     return x > 64 ? x - 128 : x;  // signed(x, 7), core.py:513-516
 }
+
+// One lane's share of a step: word = payload bytes [pos, pos + 4), nb0 = the byte after them.
+struct OpsLane {
+    uint32_t ops;    // bit j: byte j starts a pixel op
+    uint32_t jumps;  // bit j: byte j is a JUMP
+    int d[4];        // delta of the op starting at byte j (0 where none)
+};
+__device__ __forceinline__ OpsLane ops_lane(uint32_t word, uint32_t nb0, int pos, int stop, int end, uint32_t &carry, int lane) {
+    uint32_t tags = 0, valid = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t bj = (word >> (8 * j)) & 0xFFu;
+        if (pos + j < stop) { valid |= 1u << j; if ((bj & 0xF0u) == 0xE0u) tags |= 1u << j; }
+    }
+    // parity of the tagged run reaching byte 0 of this lane
+    const uint32_t tail = (uint32_t)__clz((int)~(tags << 28));  // tagged bytes at the top of the word (4: all of them)
+    const uint32_t open = __ballot_sync(0xffffffffu, tags != 0xFu), odd = __ballot_sync(0xffffffffu, tail & 1u);
+    const uint32_t lower = open & ((1u << lane) - 1u);
+    uint32_t e = lower ? (odd >> (31 - __clz((int)lower))) & 1u : carry;
+    carry = open ? (odd >> (31 - __clz((int)open))) & 1u : carry;
+    OpsLane r;
+    r.ops = r.jumps = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t bj = (word >> (8 * j)) & 0xFFu, nbj = j < 3 ? (word >> (8 * j + 8)) & 0xFFu : nb0;
+        const bool tag = (tags >> j) & 1u, start = !e && ((valid >> j) & 1u);
+        e = (!e && tag) ? 1u : 0u;
+        const bool jump = start && (bj & 0xC0u) == 0x80u;
+        const bool full = tag && pos + j + 1 < end;
+        const bool op = start && !jump && (!tag || full);
+        r.d[j] = op ? op_delta(bj, nbj, full) : 0;
+        if (op) r.ops |= 1u << j;
+        if (jump) r.jumps |= 1u << j;
+    }
+    return r;
+}
+
+// The words of a chunk, 128 bytes per step: the lane's word and the byte after it.
+struct OpsReader {
+    const uint32_t *row;
+    int row_words, lo, lane;
+    uint32_t word;
+    __device__ __forceinline__ uint32_t fetch(int g) const {
+        const int wi = ((lo + kOpsGroup * g) >> 2) + lane;
+        return wi < row_words ? __ldg(row + wi) : 0u;
+    }
+    __device__ __forceinline__ void init(const uint8_t *payload_row, int64_t pstride, int lo_, int lane_) {
+        row = reinterpret_cast<const uint32_t *>(payload_row);  // 16-byte aligned, padded
+        row_words = (int)(pstride >> 2); lo = lo_; lane = lane_;
+        word = fetch(0);
+    }
+    // returns the lane's word of group g and sets nb0; prefetches group g + 1
+    __device__ __forceinline__ uint32_t step(int g, uint32_t &nb0) {
+        const uint32_t cur = word, next = fetch(g + 1);
+        const uint32_t up = __shfl_down_sync(0xffffffffu, cur, 1), wrap = __shfl_sync(0xffffffffu, next, 0);
+        nb0 = (lane == 31 ? wrap : up) & 0xFFu;
+        word = next;
+        return cur;
+    }
+};
 
 __global__ void __launch_bounds__(32 * kOpsWarps) k_dec_ops_scan(const uint8_t *__restrict__ payload, int64_t pstride,
                                                                  const int32_t *__restrict__ plen, OpsChunkSum *__restrict__ cs,
@@ -433,50 +471,33 @@ __global__ void __launch_bounds__(32 * kOpsWarps) k_dec_ops_scan(const uint8_t *
     const int n = plen[i], lo = c * kOpsChunk;
     if (status[i] || lo >= n) return;
     const int end = n - 1, hi = lo + kOpsChunk, stop = hi < end ? hi : end;
-    const uint32_t *row = reinterpret_cast<const uint32_t *>(payload + (int64_t)i * pstride);  // 16-byte aligned, padded
-    const int row_words = (int)(pstride >> 2);
-    auto group = [&](int g) { const int wi = ((lo + 128 * g) >> 2) + lane; return wi < row_words ? __ldg(row + wi) : 0u; };
-    // counts and delta sums for both entry states; once both walks agree on the state they share one accumulator
-    int n0 = 0, s0 = 0, n1 = 0, s1 = 0, nc = 0, sc = 0;
-    uint32_t e0 = 0, e1 = 1;
-    uint32_t word = group(0);
-    for (int g = 0; g < kOpsChunk / 128 && lo + 128 * g < stop; g++) {
-        const uint32_t word_next = group(g + 1);
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int pos0 = lo + 128 * g + 32 * k;
-            if (pos0 >= stop) break;
-            const OpsStep st = ops_step_bytes(word, word_next, k, pos0, stop, lane);
-            const bool tagged = st.valid && (st.b & 0xF0u) == 0xE0u;
-            const uint32_t E = __ballot_sync(0xffffffffu, tagged);
-            const bool jump = (st.b & 0xC0u) == 0x80u;
-            const bool full = tagged && pos0 + lane + 1 < end;
-            const bool op = st.valid && !jump && (!tagged || full);  // a pixel op if this byte starts one
-            const int d = op_delta(st.b, st.nb, full);
-            if (e0 == e1) {
-                const uint32_t S = op_starts(E, e0);
-                if (op && ((S >> lane) & 1u)) { nc++; sc += d; }
-                e0 = e1 = (E & S) >> 31;
-            } else {
-                const uint32_t S0 = op_starts(E, e0), S1 = op_starts(E, e1);
-                if (op && ((S0 >> lane) & 1u)) { n0++; s0 += d; }
-                if (op && ((S1 >> lane) & 1u)) { n1++; s1 += d; }
-                e0 = (E & S0) >> 31; e1 = (E & S1) >> 31;
-            }
-        }
-        word = word_next;
+    const uint8_t *row = payload + (int64_t)i * pstride;
+    // state entering the chunk: parity of the run of tagged bytes that ends at lo - 1
+    uint32_t carry = 0;
+    for (int back = lo - 1; back >= 0; back -= 32) {
+        const int p = back - lane;
+        const uint32_t t = __ballot_sync(0xffffffffu, p >= 0 && (__ldg(row + p) & 0xF0u) == 0xE0u);
+        const int run = __ffs((int)~t) - 1;  // -1: all 32 tagged
+        if (run >= 0) { carry ^= (uint32_t)run & 1u; break; }
     }
-    n0 += nc; s0 += sc; n1 += nc; s1 += sc;
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        n0 += __shfl_xor_sync(0xffffffffu, n0, o); s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-        n1 += __shfl_xor_sync(0xffffffffu, n1, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    OpsReader rd;
+    rd.init(row, pstride, lo, lane);
+    int cnt = 0, sum = 0;
+    for (int g = 0; g < kOpsChunk / kOpsGroup && lo + kOpsGroup * g < stop; g++) {
+        uint32_t nb0;
+        const uint32_t word = rd.step(g, nb0);
+        const OpsLane L = ops_lane(word, nb0, lo + kOpsGroup * g + 4 * lane, stop, end, carry, lane);
+        cnt += __popc(L.ops);
+        sum += L.d[0] + L.d[1] + L.d[2] + L.d[3];
     }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { cnt += __shfl_xor_sync(0xffffffffu, cnt, o); sum += __shfl_xor_sync(0xffffffffu, sum, o); }
     if (lane == 0) {
+        // both entry slots carry the one true summary (ops_link_chunks starts from state 0 and follows exit_state, which
+        // reproduces `entry` for every chunk); a FULL op begun on the last byte of the chunk ends in the next one
         OpsChunkSum &o = cs[(int64_t)i * max_chunks + c];
-        const bool more = hi < end;  // a FULL op begun on the last byte of the chunk ends in the next one
-        o.nops[0] = n0; o.dsum[0] = s0; o.exit_state[0] = (uint8_t)(more ? e0 : 0u);
-        o.nops[1] = n1; o.dsum[1] = s1; o.exit_state[1] = (uint8_t)(more ? e1 : 0u);
+        const uint8_t ex = (uint8_t)(hi < end ? carry : 0u);
+        o.nops[0] = o.nops[1] = cnt; o.dsum[0] = o.dsum[1] = sum; o.exit_state[0] = o.exit_state[1] = ex;
     }
 }
 
@@ -492,55 +513,53 @@ __global__ void __launch_bounds__(32 * kOpsWarps) k_dec_ops_emit(const uint8_t *
                                                                  const int32_t *__restrict__ plen, const OpsChunkSum *__restrict__ cs,
                                                                  int max_chunks, int n_px, uint16_t *__restrict__ vals,
                                                                  uint8_t *__restrict__ jflag, uint32_t *__restrict__ status) {
+    __shared__ uint16_t stage[kOpsWarps][kOpsGroup];  // values of one step in op order, written out coalesced
     const int i = blockIdx.y, lane = threadIdx.x & 31;
     const int c = blockIdx.x * kOpsWarps + (threadIdx.x >> 5);
     const int n = plen[i], lo = c * kOpsChunk;
     if ((status[i] & ~32u) || lo >= n) return;
     const int end = n - 1, hi = lo + kOpsChunk, stop = hi < end ? hi : end;
-    const uint32_t *row = reinterpret_cast<const uint32_t *>(payload + (int64_t)i * pstride);
-    const int row_words = (int)(pstride >> 2);
-    auto group = [&](int g) { const int wi = ((lo + 128 * g) >> 2) + lane; return wi < row_words ? __ldg(row + wi) : 0u; };
     const OpsChunkSum sum = cs[(int64_t)i * max_chunks + c];
-    uint32_t e = sum.entry;
+    uint32_t carry = sum.entry;
     int k_base = sum.op_base, v_base = sum.val_base;  // ops and value before the step
     uint16_t *va = vals + (int64_t)i * n_px;
     uint8_t *jf = jflag + (int64_t)i * (n_px / kBlock);
+    uint16_t *sv = stage[threadIdx.x >> 5];
     uint32_t bad = 0;
-    const uint32_t below = (1u << lane) - 1u;
-    uint32_t word = group(0);
-    for (int g = 0; g < kOpsChunk / 128 && lo + 128 * g < stop && k_base < n_px; g++) {
-        const uint32_t word_next = group(g + 1);
+    OpsReader rd;
+    rd.init(payload + (int64_t)i * pstride, pstride, lo, lane);
+    for (int g = 0; g < kOpsChunk / kOpsGroup && lo + kOpsGroup * g < stop && k_base < n_px; g++) {
+        uint32_t nb0;
+        const uint32_t word = rd.step(g, nb0);
+        const OpsLane L = ops_lane(word, nb0, lo + kOpsGroup * g + 4 * lane, stop, end, carry, lane);
+        // inclusive warp scan of (delta sum << 8 | op count): at most 128 ops per step, so the count never carries
+        const int mine = (L.d[0] + L.d[1] + L.d[2] + L.d[3]) * 256 + __popc(L.ops);
+        int incl = mine;
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int pos0 = lo + 128 * g + 32 * k;
-            if (pos0 >= stop) break;
-            const OpsStep st = ops_step_bytes(word, word_next, k, pos0, stop, lane);
-            const bool tagged = st.valid && (st.b & 0xF0u) == 0xE0u;
-            const uint32_t E = __ballot_sync(0xffffffffu, tagged);
-            const uint32_t S = op_starts(E, e);
-            e = (E & S) >> 31;
-            const bool start = st.valid && ((S >> lane) & 1u);
-            const bool jump = start && (st.b & 0xC0u) == 0x80u;
-            const bool full = tagged && pos0 + lane + 1 < end;
-            const bool op = start && !jump && (!tagged || full);
-            const uint32_t P = __ballot_sync(0xffffffffu, op);
-            const int kk = k_base + __popc(P & below);  // pixel ops before this byte
-            int v = op ? op_delta(st.b, st.nb, full) : 0;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        const int total = __shfl_sync(0xffffffffu, incl, 31), excl = incl - mine;
+        int kk = excl & 0xFF, value = v_base + (excl >> 8);
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
-            const int value = v_base + v;
-            if (op && kk < n_px) {
-                if (value < 0 || value > 65535) bad |= 32u;  // reference: OverflowError (core.py:506,516)
-                va[kk] = (uint16_t)value;
+        for (int j = 0; j < 4; j++) {
+            if ((L.jumps >> j) & 1u) {
+                const int k = k_base + kk;
+                if (k < n_px) {
+                    if ((k & 15) == 0) jf[k >> 4] = (uint8_t)((word >> (8 * j)) & 0x3Fu);  // JUMP distance (core.py:484-494)
+                    else bad |= 64u;  // a JUMP inside a unit is never produced by the encoder
+                }
             }
-            if (jump && kk < n_px) {
-                if ((kk & 15) == 0) jf[kk >> 4] = (uint8_t)(st.b & 0x3Fu);  // JUMP distance (core.py:484-494)
-                else bad |= 64u;  // a JUMP inside a unit is never produced by the encoder
+            if ((L.ops >> j) & 1u) {
+                value += L.d[j];
+                if (k_base + kk < n_px && (value < 0 || value > 65535)) bad |= 32u;  // reference: OverflowError (core.py:506,516)
+                sv[kk++] = (uint16_t)value;
             }
-            k_base += __popc(P);
-            v_base += __shfl_sync(0xffffffffu, v, 31);
         }
-        word = word_next;
+        __syncwarp();
+        const int cnt = min(total & 0xFF, n_px - k_base);
+        for (int t = lane; t < cnt; t += 32) va[k_base + t] = sv[t];
+        __syncwarp();
+        k_base += total & 0xFF;
+        v_base += total >> 8;
     }
     bad = __reduce_or_sync(0xffffffffu, bad);
     if (bad && lane == 0) atomicOr(status + i, bad);
