@@ -181,8 +181,7 @@ constexpr int kWalkSteps = 2;   // step cap of the probe reached
 // follows" starts with the byte after either run, which both records carry: the payload is read only when they agree.
 // A single candidate is compared through the four payload bytes in its record: a candidate that merely shares the
 // hash, or matches exactly three bytes, is settled without touching the payload.
-// The walk is a resumable state machine (chain_begin / chain_step); chain_walk runs it to the end.
-constexpr int kWalkContinue = -1;
+// The walk is resumable (chain_begin / chain_run): match_probe raises the budget of a walk that ran out of it.
 struct ChainState {
     int s, cap, best, bdist, chain, steps_left, cur, R;
     uint32_t quad;   // target bytes 0..3
@@ -201,69 +200,80 @@ CCT_HD int chain_begin(const LzView &v, int s, int cap, int best, int chain, int
     return own;
 }
 
-// One loop step: a single candidate or a whole run group.  Returns kWalkContinue or how the walk ended.
-CCT_HD int chain_step(const LzView &v, ChainState &c) {
-    CCT_COUNT(0);
-    const int s = c.s, cap = c.cap, cur = c.cur;
-    const ChainRec rc = load_rec(v.recs + cur);  // one 8-byte load: link, run lengths, first bytes of the candidate
-    const int dl = rec_link(rc);
-    int link_from = cur;
-    if (rec_is_run(rc)) {
-        // cur starts a triple (c,c,c): the chain entries below it inside the run form one group
-        const int m = rec_rl(rc) + 1;  // leading c's of the top candidate
-        int t = rec_rb(rc);            // further candidates of this run below cur
-        if (cur - t < 1) t = cur - 1;  // position 0 is never in a chain
-        const int count_dist = kMaxDist - (s - cur);
-        int nvis = t + 1;
-        if (c.chain < nvis) nvis = c.chain;
-        if (count_dist < nvis) nvis = count_dist;
-        if (c.R && rec_run_byte(rc) == (c.quad & 0xFFu)) {
-            const int R = c.R;
-            const int i_key = m >= R ? 0 : R - m;  // first member with at least R leading c's
-            if (R < cap && m > R) {
-                if (R > c.best) { c.best = R; c.bdist = s - cur; }
-            } else if (i_key < nvis) {
-                const int c_al = cur - i_key;  // R < cap: exactly R leading c's, then the byte after the group's run
-                int L = cap;
-                if (R < cap) L = rec_after(rc) != c.after ? R : match_extend(v.w + c_al, v.w + s, R + 1, cap);
-                if (L > c.best) { c.best = L; c.bdist = s - c_al; if (L >= cap) return kWalkDone; }
-            } else {
-                const int L = m + nvis - 1;  // only members with fewer than R leading c's were reached
-                if (L > c.best) { c.best = L; c.bdist = s - (cur - (nvis - 1)); }
-            }
-        }  // else: the target does not start with (c,c,c) (a hash collision): no member matches 3 bytes
-        if (nvis < t + 1) return nvis == count_dist ? kWalkDone : kWalkBudget;
-        c.chain -= t;
-        link_from = cur - t;  // the bottom of the run links onwards (its link is the one in the record)
-    } else {
-        const uint32_t x = rc.b ^ c.quad;
-        if ((x & 0xFFFFFFu) == 0) {  // the hash triple matches
-            int len = cap < kMinMatch ? cap : kMinMatch;
-            if (x == 0 && cap > kMinMatch) {
-                // four bytes match: the payload decides (zlib's scan_end test is only a shortcut for len <= best)
-                const uint8_t *a = v.w + cur, *b = v.w + s;
-                len = (c.best > kMinMatch && load_byte(a + c.best) != load_byte(b + c.best)) ? 0 : match_extend(a, b, kMinMatch + 1, cap);
-            }
-            if (len > c.best) {
-                c.best = len; c.bdist = s - cur;
-                if (len >= cap) return kWalkDone;
+// Runs the walk until it ends (one loop step = a single candidate or a whole run group) and returns how it ended;
+// the state is left such that a walk cut short by the budget or the step cap can go on (c.chain / c.steps_left
+// raised by the caller).  The chain budget and the step cap both drop by one per step, so the loop carries the step
+// count and the (constant) difference: one counter, one exit test.
+CCT_HD int chain_run(const LzView &v, ChainState &c) {
+    const int s = c.s, cap = c.cap;
+    int cur = c.cur, best = c.best, bdist = c.bdist, steps = c.steps_left;
+    int diff = c.chain - steps;       // chain = steps + diff
+    int lim = diff < 0 ? -diff : 0;   // steps == lim: the budget (diff < 0) or the step cap ran out
+    int r;
+    for (;;) {
+        CCT_COUNT(0);
+        const ChainRec rc = load_rec(v.recs + cur);  // one 8-byte load: link, run lengths, first bytes of the candidate
+        const int dl = rec_link(rc);
+        int link_from = cur;
+        if (rec_is_run(rc)) {
+            // cur starts a triple (c,c,c): the chain entries below it inside the run form one group
+            const int chain = steps + diff;
+            const int m = rec_rl(rc) + 1;  // leading c's of the top candidate
+            int t = rec_rb(rc);            // further candidates of this run below cur
+            if (cur - t < 1) t = cur - 1;  // position 0 is never in a chain
+            const int count_dist = kMaxDist - (s - cur);
+            int nvis = t + 1;
+            if (chain < nvis) nvis = chain;
+            if (count_dist < nvis) nvis = count_dist;
+            if (c.R && rec_run_byte(rc) == (c.quad & 0xFFu)) {
+                const int R = c.R;
+                const int i_key = m >= R ? 0 : R - m;  // first member with at least R leading c's
+                if (R < cap && m > R) {
+                    if (R > best) { best = R; bdist = s - cur; }
+                } else if (i_key < nvis) {
+                    const int c_al = cur - i_key;  // R < cap: exactly R leading c's, then the byte after the group's run
+                    int L = cap;
+                    if (R < cap) L = rec_after(rc) != c.after ? R : match_extend(v.w + c_al, v.w + s, R + 1, cap);
+                    if (L > best) { best = L; bdist = s - c_al; if (L >= cap) { r = kWalkDone; break; } }
+                } else {
+                    const int L = m + nvis - 1;  // only members with fewer than R leading c's were reached
+                    if (L > best) { best = L; bdist = s - (cur - (nvis - 1)); }
+                }
+            }  // else: the target does not start with (c,c,c) (a hash collision): no member matches 3 bytes
+            if (nvis < t + 1) { r = nvis == count_dist ? kWalkDone : kWalkBudget; break; }
+            diff -= t;  // chain -= t
+            lim = diff < 0 ? -diff : 0;
+            link_from = cur - t;  // the bottom of the run links onwards (its link is the one in the record)
+        } else {
+            const uint32_t x = rc.b ^ c.quad;
+            if ((x & 0xFFFFFFu) == 0) {  // the hash triple matches
+                int len = cap < kMinMatch ? cap : kMinMatch;
+                if (x == 0 && cap > kMinMatch) {
+                    // four bytes match: the payload decides (zlib's scan_end test is only a shortcut for len <= best)
+                    const uint8_t *a = v.w + cur, *b = v.w + s;
+                    len = (best > kMinMatch && load_byte(a + best) != load_byte(b + best)) ? 0 : match_extend(a, b, kMinMatch + 1, cap);
+                }
+                if (len > best) {
+                    best = len; bdist = s - cur;
+                    if (len >= cap) { r = kWalkDone; break; }
+                }
             }
         }
+        // follow the link, charge the budget and the step cap: one exit test on the common path (precedence as in
+        // zlib's loop condition: chain end / distance limit, then the budget; the step cap is ours and comes last)
+        cur = link_from - dl;
+        const bool done = (dl == 0) | (s - cur >= kMaxDist);  // cur <= limit
+        steps--;
+        if (done | (steps == lim)) { r = done ? kWalkDone : (steps + diff == 0 ? kWalkBudget : kWalkSteps); break; }
     }
-    // follow the link, charge the budget and the step cap: one exit test on the common path (precedence as in
-    // zlib's loop condition: chain end / distance limit, then the budget; the step cap is ours and comes last)
-    c.cur = link_from - dl;
-    const bool done = (dl == 0) | (s - c.cur >= kMaxDist);  // cur <= limit
-    c.chain--; c.steps_left--;
-    if (done | (c.chain == 0) | (c.steps_left == 0)) return done ? kWalkDone : (c.chain == 0 ? kWalkBudget : kWalkSteps);
-    return kWalkContinue;
+    c.cur = cur; c.best = best; c.bdist = bdist; c.chain = steps + diff; c.steps_left = steps;
+    return r;
 }
 
 CCT_HD int chain_walk(const LzView &v, int s, int cap, int &best, int &bdist, int chain, int max_steps) {
     ChainState c;
     chain_begin(v, s, cap, best, chain, max_steps, c);
-    int r;
-    while ((r = chain_step(v, c)) == kWalkContinue) {}
+    const int r = chain_run(v, c);
     best = c.best; bdist = c.bdist;
     return r;
 }
@@ -281,8 +291,7 @@ CCT_HD void match_probe(const LzView &v, int s, int K, uint32_t *lo, uint32_t *h
     ChainState c;
     const int d0 = chain_begin(v, s, cap, 2, kChainGood, K, c);
     if (d0 == 0 || d0 > kMaxDist) return;
-    int r;
-    while ((r = chain_step(v, c)) == kWalkContinue) {}
+    int r = chain_run(v, c);
     const uint32_t e = r == kWalkSteps ? kProbeIncomplete : (c.best >= kMinMatch ? mtab_pack(c.best, c.bdist) : 0u);
     *lo = *hi = e;
     if (r != kWalkBudget) return;
@@ -291,7 +300,7 @@ CCT_HD void match_probe(const LzView &v, int s, int K, uint32_t *lo, uint32_t *h
     // the longer count -- its members seen so far are a prefix, so best/bdist come out as from a fresh walk.)
     if (c.steps_left == 0) { *lo = kProbeIncomplete; return; }  // budget and step cap ran out on the same candidate
     c.chain += kChainFull - kChainGood;
-    while ((r = chain_step(v, c)) == kWalkContinue) {}
+    r = chain_run(v, c);
     *lo = r == kWalkSteps ? kProbeIncomplete : (c.best >= kMinMatch ? mtab_pack(c.best, c.bdist) : 0u);
 }
 
