@@ -509,6 +509,32 @@ struct HostCtx {
         cap[slot] = bytes;
         return CCT_OK;
     }
+    // CCT_HOST_TRACE=1: device timeline of a host-buffer call (copies and passes), printed to stderr at its end
+    std::vector<std::pair<std::string, cudaEvent_t>> marks;
+    bool tracing = false;
+    void mark(const char *what, int k, cudaStream_t s) {
+        if (!tracing) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, s);
+        marks.emplace_back(std::string(what) + " " + std::to_string(k), e);
+    }
+    void trace_begin(cudaStream_t s) {
+        const char *e = getenv("CCT_HOST_TRACE");
+        tracing = e && atoi(e) > 0;
+        mark("begin", 0, s);
+    }
+    void trace_end(const char *call) {
+        if (!tracing) return;
+        for (size_t i = 1; i < marks.size(); i++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, marks[0].second, marks[i].second);
+            fprintf(stderr, "[cct trace] %s %-14s %8.3f ms\n", call, marks[i].first.c_str(), ms);
+        }
+        for (auto &m : marks) cudaEventDestroy(m.second);
+        marks.clear();
+        tracing = false;
+    }
     void drain() { cudaStreamSynchronize(up); cudaStreamSynchronize(st); cudaStreamSynchronize(st2); cudaStreamSynchronize(down); }
     void two_lanes(PassHooks &h, int slot) const { h.alt_stream = st2; h.alt_ws = buf[slot]; h.ready = ready; h.carry[0] = carry[0]; h.carry[1] = carry[1]; }
 };
@@ -536,21 +562,35 @@ int get_ctx(int device, HostCtx **out) {
 }
 
 // Pass schedule of the host entry points: about 512 MiB of raw pixels per pass, so that the copies of one pass hide
-// behind the kernels of its neighbours while every kernel still sees enough streams to fill the GPU; the first pass
-// is a quarter of that, because its upload (encode) / its kernels (decode) are the part nothing can hide.
-// CCT_HOST_PASS overrides the pass size (0 = one pass).  Returns the largest pass.
-int host_schedule(int B, size_t n_px, std::vector<int> &starts) {
+// behind the kernels of its neighbours while every kernel still sees enough streams to fill the GPU.  The batch opens
+// with shorter passes, because the upload (encode) / the kernels (decode) of the first pass are the part nothing can
+// hide: a quarter and a half pass for encode, whose bound is the kernels; an eighth, a quarter and a half for decode,
+// whose bound is the download of 2 bytes per pixel -- it has to start as early as possible and then never wait (the
+// first pixels cannot come before ~8 ms: one stream alone takes that long through the bit-serial inflate).
+// CCT_HOST_PASS overrides the pass size (0 = one pass), CCT_HOST_LEADS the opening ("8,4,2" = those fractions).
+// Returns the largest pass.
+int host_schedule(int B, size_t n_px, std::vector<int> &starts, bool decode) {
     int per = (int)std::max<size_t>(1, ((size_t)512 << 20) / (n_px * 2));
     if (const char *e = getenv("CCT_HOST_PASS")) { const int v = atoi(e); per = v > 0 ? v : B; }
     per = std::max(1, std::min(per, B));
+    std::vector<int> div = decode ? std::vector<int>{8, 4, 2} : std::vector<int>{4, 2};
+    if (const char *e = getenv("CCT_HOST_LEADS")) {
+        div.clear();
+        for (const char *q = e; *q;) { const int v = atoi(q); if (v > 0) div.push_back(v); while (*q && *q != ',') q++; if (*q) q++; }
+    }
     starts.clear();
     starts.push_back(0);
     if (B > per) {
-        const int lead = std::max(1, per / 4);
-        const int rest = B - lead, n = (rest + per - 1) / per, each = (rest + n - 1) / n;  // equal passes after the first
-        starts.push_back(lead);
-        for (int k = 1; k < n; k++) starts.push_back(lead + k * each);
-        per = std::max(lead, each);
+        int at = 0, largest = 0;
+        for (int d : div) {
+            const int lead = std::max(1, per / d);
+            if (at + lead >= B) break;
+            at += lead; largest = std::max(largest, lead);
+            starts.push_back(at);
+        }
+        const int rest = B - at, n = (rest + per - 1) / per, each = (rest + n - 1) / n;  // equal passes after the opening
+        for (int k = 1; k < n; k++) starts.push_back(at + k * each);
+        per = std::max(largest, each);
     }
     starts.push_back(B);
     return per;
@@ -578,7 +618,7 @@ int cct_encode_host(const uint16_t *h_px, int B, int rows, int cols, uint32_t fl
     if (B == 0) return CCT_OK;
     const size_t n_px = (size_t)rows * cols;
     std::vector<int> starts;
-    const int per = host_schedule(B, n_px, starts), n_pass = (int)starts.size() - 1;
+    const int per = host_schedule(B, n_px, starts, false), n_pass = (int)starts.size() - 1;
     const size_t arena = std::min(out_cap, (size_t)B * cct_file_bound(rows, cols));
     const size_t ws_bytes = cct_encode_workspace_bytes(per, rows, cols, flags);
     if ((rc = c->ensure(0, (size_t)B * n_px * 2))) return rc;
@@ -594,10 +634,12 @@ int cct_encode_host(const uint16_t *h_px, int B, int rows, int cols, uint32_t fl
     int32_t *d_stats = (int32_t *)(d_status + B);
     // Three streams: pixels of every pass go up on `up` (queued at once), the encoder's passes run on `st`, each
     // waiting only for its own pixels, and the bytes of pass k come down on `down` while pass k+1 is running.
+    c->trace_begin(c->up);
     for (int k = 0; k < n_pass; k++) {
         const size_t lo = (size_t)starts[k], cnt = (size_t)(starts[k + 1] - starts[k]);
         CK(cudaMemcpyAsync(d_px + lo * n_px, h_px + lo * n_px, cnt * n_px * 2, cudaMemcpyHostToDevice, c->up));
         CK(cudaEventRecord(c->event(k), c->up));
+        c->mark("up", k, c->up);
     }
     bool over = false;
     auto fetch = [&](int k) -> int {  // bytes of pass k -> host (its offsets have been copied on `st` before event n_pass + k)
@@ -606,6 +648,7 @@ int cct_encode_host(const uint16_t *h_px, int B, int rows, int cols, uint32_t fl
         const int64_t b0 = h_offsets[lo], b1 = h_offsets[hi];
         if (b1 > (int64_t)out_cap || b1 > (int64_t)arena) { over = true; return CCT_OK; }
         if (b1 > b0) CK(cudaMemcpyAsync(h_out + b0, d_out + b0, (size_t)(b1 - b0), cudaMemcpyDeviceToHost, c->down));
+        c->mark("down", k, c->down);
         return CCT_OK;
     };
     PassHooks hooks;
@@ -614,9 +657,11 @@ int cct_encode_host(const uint16_t *h_px, int B, int rows, int cols, uint32_t fl
     if (two) c->two_lanes(hooks, 5);
     hooks.before = [&](int k, int, int, cudaStream_t ps) -> int {
         CK(cudaStreamWaitEvent(ps, c->event(k), 0));
+        c->mark("start", k, ps);
         return CCT_OK;
     };
     hooks.after = [&](int k, int first, int count, cudaStream_t ps) -> int {
+        c->mark("end", k, ps);
         CK(cudaMemcpyAsync(h_offsets + first + 1, d_off + first + 1, (size_t)count * 8, cudaMemcpyDeviceToHost, ps));
         CK(cudaEventRecord(c->event(n_pass + k), ps));
         return k > 0 ? fetch(k - 1) : CCT_OK;  // pass k is queued: now wait for pass k-1 and start its download
@@ -628,6 +673,7 @@ int cct_encode_host(const uint16_t *h_px, int B, int rows, int cols, uint32_t fl
     if (h_stats) CK(cudaMemcpyAsync(h_stats, d_stats, (size_t)B * 16, cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
     CK(cudaStreamSynchronize(c->down));
+    c->trace_end("encode");
     return over ? CCT_E_CAPACITY : CCT_OK;
 }
 
@@ -646,7 +692,7 @@ int cct_decode_host(const uint8_t *h_in, const int64_t *h_offsets, int B, int ro
     if (total < 0) return CCT_E_ARG;
     for (int i = 0; i < B; i++) if (h_offsets[i + 1] < h_offsets[i]) return CCT_E_ARG;
     std::vector<int> starts;
-    const int per = host_schedule(B, n_px, starts), n_pass = (int)starts.size() - 1;
+    const int per = host_schedule(B, n_px, starts, true), n_pass = (int)starts.size() - 1;
     const size_t ws_bytes = cct_decode_workspace_bytes(per, rows, cols);
     if ((rc = c->ensure(0, (size_t)B * n_px * 2))) return rc;
     if ((rc = c->ensure(1, std::max<size_t>((size_t)total, 16)))) return rc;
@@ -660,6 +706,7 @@ int cct_decode_host(const uint8_t *h_in, const int64_t *h_offsets, int B, int ro
     uint32_t *d_status = (uint32_t *)(d_off + B + 1);
     std::vector<int64_t> rel((size_t)B + 1);
     for (int i = 0; i <= B; i++) rel[i] = h_offsets[i] - base;
+    c->trace_begin(c->up);
     CK(cudaMemcpyAsync(d_off, rel.data(), (size_t)(B + 1) * 8, cudaMemcpyHostToDevice, c->up));
     // files of every pass go up on `up` (queued at once); pass k decodes on `st` as soon as its files are there;
     // its pixels come down on `down` while pass k+1 decodes
@@ -668,6 +715,7 @@ int cct_decode_host(const uint8_t *h_in, const int64_t *h_offsets, int B, int ro
         if (rel[hi] > rel[lo])
             CK(cudaMemcpyAsync(d_in + rel[lo], h_in + base + rel[lo], (size_t)(rel[hi] - rel[lo]), cudaMemcpyHostToDevice, c->up));
         CK(cudaEventRecord(c->event(k), c->up));
+        c->mark("up", k, c->up);
     }
     PassHooks hooks;
     hooks.max_pass = per;
@@ -675,14 +723,17 @@ int cct_decode_host(const uint8_t *h_in, const int64_t *h_offsets, int B, int ro
     if (two) c->two_lanes(hooks, 5);
     hooks.before = [&](int k, int, int, cudaStream_t ps) -> int {
         CK(cudaStreamWaitEvent(ps, c->event(k), 0));
+        c->mark("start", k, ps);
         return CCT_OK;
     };
     hooks.after = [&](int k, int first, int count, cudaStream_t ps) -> int {
+        c->mark("end", k, ps);
         cudaEvent_t e = c->event(n_pass + k);
         CK(cudaEventRecord(e, ps));
         CK(cudaStreamWaitEvent(c->down, e, 0));
         CK(cudaMemcpyAsync(h_px + (size_t)first * n_px, d_px + (size_t)first * n_px, (size_t)count * n_px * 2,
                            cudaMemcpyDeviceToHost, c->down));
+        c->mark("down", k, c->down);
         return CCT_OK;
     };
     rc = decode_impl(d_in, d_off, B, rows, cols, d_px, d_status, c->buf[4], c->cap[4], c->st, &hooks);
@@ -691,6 +742,7 @@ int cct_decode_host(const uint8_t *h_in, const int64_t *h_offsets, int B, int ro
     CK(cudaStreamSynchronize(c->up));  // `rel` must outlive its copy
     CK(cudaStreamSynchronize(c->st));
     CK(cudaStreamSynchronize(c->down));
+    c->trace_end("decode");
     return CCT_OK;
 }
 
