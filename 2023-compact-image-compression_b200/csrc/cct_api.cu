@@ -251,7 +251,9 @@ size_t cct_encode_workspace_bytes(int B, int rows, int cols, uint32_t flags) {
 
 size_t cct_decode_workspace_bytes(int B, int rows, int cols) {
     if (check_shape(B, rows, cols) != CCT_OK) return 0;
-    return decode_ws_bytes(std::max(B, 1), (int64_t)rows * cols);
+    const int b = std::max(B, 1);
+    const int64_t n_px = (int64_t)rows * cols;
+    return std::max(decode_ws_bytes(b, n_px), 2 * decode_ws_bytes((b + 1) / 2, n_px));  // one pass, or two halves side by side
 }
 
 }  // extern "C"
@@ -269,6 +271,23 @@ struct PassHooks {
     void *alt_ws = nullptr;
     cudaEvent_t ready = nullptr, carry[2] = {nullptr, nullptr};  // set-up done on the main stream; offsets of a pass written
 };
+
+// Library-owned second stream of a device for cct_decode_batch (one per device, created on first use).
+constexpr int kSplitMin = 512;  // images; below that every kernel is latency-bound and a split only adds launches
+struct SideLane { cudaStream_t stream = nullptr; cudaEvent_t ready = nullptr; };
+std::map<int, SideLane> g_side;  // guarded by g_mu
+int get_side(SideLane **out) {
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_mu);
+    SideLane &s = g_side[dev];
+    if (!s.stream) {
+        CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming));
+    }
+    *out = &s;
+    return CCT_OK;
+}
 
 int encode_impl(const uint16_t *d_px, int B, int rows, int cols, uint32_t flags, uint8_t *d_out, size_t out_cap,
                 int64_t *d_offsets, uint32_t *d_status, int32_t *d_stats, void *d_ws, size_t ws_bytes, cudaStream_t st,
@@ -288,6 +307,29 @@ int cct_encode_batch(const uint16_t *d_px, int B, int rows, int cols, uint32_t f
 
 int cct_decode_batch(const uint8_t *d_in, const int64_t *d_offsets, int B, int rows, int cols, uint16_t *d_px,
                      uint32_t *d_status, void *d_ws, size_t ws_bytes, void *stream) {
+    // A large batch is decoded as two halves on two streams (the caller's and a library-owned one, forked from and
+    // joined to it with events): the bit-serial stages are bound by the latency of one stream, not by the GPU --
+    // k_lz_expand keeps one warp per stream busy, k_dec_units one warp per image -- so the halves fill each other's
+    // idle issue slots (the half that finished k_inflate_sym expands while the other still decodes Huffman codes).
+    // CCT_DEC_SPLIT=0 turns it off.
+    static const int parts = [] { const char *e = getenv("CCT_DEC_SPLIT"); return e ? atoi(e) : 2; }();
+    if (parts > 1 && B >= kSplitMin && check_shape(B, rows, cols) == CCT_OK && d_ws) {
+        const int each = (B + parts - 1) / parts;
+        const size_t one = decode_ws_bytes(each, (int64_t)rows * cols);
+        SideLane *side = nullptr;
+        if (2 * one <= ws_bytes && get_side(&side) == CCT_OK) {
+            std::vector<int> starts;
+            for (int k = 0; k < parts; k++) starts.push_back(std::min(B, k * each));
+            starts.push_back(B);
+            PassHooks hooks;
+            hooks.max_pass = each;
+            hooks.starts = &starts;
+            hooks.alt_stream = side->stream;
+            hooks.alt_ws = (char *)d_ws + one;
+            hooks.ready = side->ready;
+            return decode_impl(d_in, d_offsets, B, rows, cols, d_px, d_status, d_ws, one, (cudaStream_t)stream, &hooks);
+        }
+    }
     return decode_impl(d_in, d_offsets, B, rows, cols, d_px, d_status, d_ws, ws_bytes, (cudaStream_t)stream, nullptr);
 }
 
@@ -765,6 +807,8 @@ void cct_release(void) {
     std::lock_guard<std::mutex> lk(g_mu);
     for (auto &kv : g_orders) { cudaSetDevice(std::get<0>(kv.first)); cudaFree(kv.second); }
     g_orders.clear();
+    for (auto &kv : g_side) { cudaSetDevice(kv.first); if (kv.second.stream) cudaStreamDestroy(kv.second.stream); if (kv.second.ready) cudaEventDestroy(kv.second.ready); }
+    g_side.clear();
 }
 
 }  // extern "C"

@@ -519,10 +519,10 @@ struct uint2 { uint32_t x, y; };  // host build of the test harness
 #endif
 constexpr uint32_t kPqNone = 0xFFFFFFFFu;  // sentinel after the last entry: never "smaller" than a real one
 
-CCT_HDN inline void pq_down(TreeScratch &s, int k) {
+CCT_HDN inline void pq_down(TreeScratch &s, int k, const int heap_len) {  // (heap_len by value: s.pq stores would force a reload)
     const uint32_t v = s.pq[k], vk = v >> 10;
     int j = k << 1;
-    while (j <= s.heap_len) {
+    while (j <= heap_len) {
         // children j (even: 8-byte aligned) and j + 1 (the sentinel when j is the last entry)
         const uint2 ch = *reinterpret_cast<const uint2 *>(&s.pq[j]);
         uint32_t c = ch.x;
@@ -542,45 +542,47 @@ CCT_HDN inline void build_tree(TreeScratch &s, T &t, int kind) {
     const int max_length = kind == 2 ? 7 : kMaxBits;
     const int heap_size = 2 * elems + 1;  // zlib uses one HEAP_SIZE array; only relative order matters
     int n, m, max_code = -1, node;
-    s.heap_len = 0; s.heap_max = heap_size;
+    // the queue length, the stack cursor and the two cost sums live in registers (the struct sits in shared memory)
+    int heap_len = 0, heap_max = heap_size;
+    int64_t opt_len = s.opt_len, static_len = s.static_len;
     for (n = 0; n < elems; n++) {
-        if (t.freq[n] != 0) { s.pq[++s.heap_len] = ((uint32_t)t.freq[n] << 16) | (uint32_t)(max_code = n); }
+        if (t.freq[n] != 0) { s.pq[++heap_len] = ((uint32_t)t.freq[n] << 16) | (uint32_t)(max_code = n); }
         else t.len[n] = 0;
     }
-    while (s.heap_len < 2) {  // force at least two codes
+    while (heap_len < 2) {  // force at least two codes
         node = max_code < 2 ? ++max_code : 0;
-        s.pq[++s.heap_len] = (1u << 16) | (uint32_t)node;
+        s.pq[++heap_len] = (1u << 16) | (uint32_t)node;
         t.freq[node] = 1;
-        s.opt_len--;
-        if (kind == 0) s.static_len -= static_llen(node);
-        else if (kind == 1) s.static_len -= 5;
+        opt_len--;
+        if (kind == 0) static_len -= static_llen(node);
+        else if (kind == 1) static_len -= 5;
     }
     t.max_code = max_code;
-    s.pq[s.heap_len + 1] = kPqNone;
-    for (n = s.heap_len / 2; n >= 1; n--) pq_down(s, n);
+    s.pq[heap_len + 1] = kPqNone;
+    for (n = heap_len / 2; n >= 1; n--) pq_down(s, n, heap_len);
     node = elems;
     do {
         const uint32_t nq = s.pq[1];  // pqremove
-        s.pq[1] = s.pq[s.heap_len]; s.pq[s.heap_len] = kPqNone; s.heap_len--;
-        pq_down(s, 1);
+        s.pq[1] = s.pq[heap_len]; s.pq[heap_len] = kPqNone; heap_len--;
+        pq_down(s, 1, heap_len);
         const uint32_t mq = s.pq[1];
         n = (int)(nq & 1023u); m = (int)(mq & 1023u);
-        s.heap[--s.heap_max] = (int16_t)n; s.heap[--s.heap_max] = (int16_t)m;
+        s.heap[--heap_max] = (int16_t)n; s.heap[--heap_max] = (int16_t)m;
         const uint32_t f = (nq >> 16) + (mq >> 16);
         const uint32_t dn = (nq >> 10) & 63u, dm = (mq >> 10) & 63u;
         t.freq[node] = (uint16_t)f;
         t.dad[n] = t.dad[m] = (uint16_t)node;
         s.pq[1] = (f << 16) | ((((dn >= dm ? dn : dm) + 1u) & 63u) << 10) | (uint32_t)node;
         node++;
-        pq_down(s, 1);
-    } while (s.heap_len >= 2);
-    s.heap[--s.heap_max] = (int16_t)(s.pq[1] & 1023u);
+        pq_down(s, 1, heap_len);
+    } while (heap_len >= 2);
+    s.heap[--heap_max] = (int16_t)(s.pq[1] & 1023u);
 
     // gen_bitlen
     int h, bits, overflow = 0;
     for (bits = 0; bits <= kMaxBits; bits++) s.bl_count[bits] = 0;
-    t.len[s.heap[s.heap_max]] = 0;
-    for (h = s.heap_max + 1; h < heap_size; h++) {
+    t.len[s.heap[heap_max]] = 0;
+    for (h = heap_max + 1; h < heap_size; h++) {
         n = s.heap[h];
         bits = t.len[t.dad[n]] + 1;
         if (bits > max_length) { bits = max_length; overflow++; }
@@ -589,9 +591,10 @@ CCT_HDN inline void build_tree(TreeScratch &s, T &t, int kind) {
         s.bl_count[bits]++;
         int xbits = 0;
         if (n >= base) xbits = kind == 0 ? len_extra_bits(n - base) : (kind == 1 ? dist_extra_bits(n) : bl_extra_bits(n));
-        s.opt_len += (int64_t)t.freq[n] * (bits + xbits);
-        if (kind == 0) s.static_len += (int64_t)t.freq[n] * (static_llen(n) + xbits);
-        else if (kind == 1) s.static_len += (int64_t)t.freq[n] * (5 + xbits);
+        const int f = t.freq[n];
+        opt_len += f * (bits + xbits);
+        if (kind == 0) static_len += f * (static_llen(n) + xbits);
+        else if (kind == 1) static_len += f * (5 + xbits);
     }
     if (overflow) {
         do {
@@ -606,13 +609,14 @@ CCT_HDN inline void build_tree(TreeScratch &s, T &t, int kind) {
                 m = s.heap[--h];
                 if (m > max_code) continue;
                 if (t.len[m] != (unsigned)bits) {
-                    s.opt_len += ((int64_t)bits - t.len[m]) * t.freq[m];
+                    opt_len += ((int64_t)bits - t.len[m]) * t.freq[m];
                     t.len[m] = (uint16_t)bits;
                 }
                 n--;
             }
         }
     }
+    s.heap_len = heap_len; s.heap_max = heap_max; s.opt_len = opt_len; s.static_len = static_len;
     // gen_codes
     uint32_t next_code[kMaxBits + 1], code = 0;
     next_code[0] = 0;

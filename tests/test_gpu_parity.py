@@ -308,6 +308,60 @@ def test_errors_and_domain(torch_cuda, pkg, oracle, native):
     assert rc == native.E_CAPACITY and (st[0] & native.ST_CAPACITY)
 
 
+def _tagged_run_image(seed, rows, cols, order):
+    """Pixels whose op stream holds long runs of bytes that LOOK like FULL tags: a ramp of +229 per op is the byte
+    pair E0 E5, so k steps are 2k tagged bytes in a row (op starts alternate inside them), with run lengths and
+    phases that put them across 32-byte steps, 128-byte groups and the 1 KB chunks of k_dec_ops_scan/emit."""
+    rng = np.random.default_rng(seed)
+    n = rows * cols
+    vals = np.empty(n, dtype=np.int64)
+    v, k = 0, 0
+    while k < n:
+        up = int(rng.integers(1, 270))
+        for _ in range(up):
+            if k >= n or v + 229 > 65535:
+                break
+            v += 229; vals[k] = v; k += 1
+        for _ in range(int(rng.integers(0, 40))):  # plain DELTA ops in between (one byte each): shifts the phase
+            if k >= n:
+                break
+            v = max(0, min(65535, v + int(rng.integers(-60, 61)))); vals[k] = v; k += 1
+        while v > 3000 and k < n:  # back down in FULL steps whose low byte is no tag
+            v -= 2000; vals[k] = v; k += 1
+    img = np.empty(n, dtype=np.uint16)
+    img[order] = vals.astype(np.uint16)
+    return img.reshape(rows, cols)
+
+
+@pytest.mark.parametrize("shape,flags", [((128, 128), 7), ((128, 128), 4), ((64, 256), 5), ((512, 512), 6)])
+def test_op_stream_tagged_runs(torch_cuda, pkg, oracle, shape, flags):
+    """Decode of op streams with long FULL-tag look-alike runs (SURVEY A.5's 2-state automaton at its worst)."""
+    rows, cols = shape
+    fractal, seg, deflate = bool(flags & 1), bool(flags & 2), bool(flags & 4)
+    cfg = pkg.default_config()
+    tr = cfg["encoder"]["transforms"]
+    tr["fractal"], tr["segmentation"] = fractal, seg
+    cfg["encoder"]["deflate_compression"] = deflate
+    order = oracle.curve(rows, cols).astype(np.int64) if fractal else np.arange(rows * cols)
+    for seed in range(3):
+        img = _tagged_run_image(seed, rows, cols, order)
+        want = oracle.encode(img, fractal=fractal, seg=seg, deflate=deflate)
+        if not seg:  # (meshing reorders the blocks, and with them the runs)
+            payload = zlib.decompress(want[13:]) if deflate else want[13:]
+            tagged = (np.frombuffer(payload, dtype=np.uint8) & 0xF0) == 0xE0
+            longest = max(len(r) for r in "".join("1" if t else "0" for t in tagged).split("0"))
+            assert longest > 400, "the generator should produce tagged runs longer than a warp step"
+        assert pkg.Encoder(cfg, img).encode() == want
+        try:
+            want_px = oracle.decode(want)
+        except OverflowError:  # meshing can take a ramp out of the reference's lossless domain (SURVEY A.6 #6)
+            with pytest.raises(OverflowError):
+                pkg.Decoder(cfg, want).decode()
+            continue
+        assert np.array_equal(want_px, img)
+        assert pkg.Decoder(cfg, want).decode() == img.tobytes()
+
+
 def test_config_batch_roundtrip_4096(torch_cuda, pkg, synth, oracle):
     """BASELINE.json configs[1] at full size through size-independent properties: every bytestream length and a
     checksum of checksums equal the oracle's, and decode(encode(x)) == x for all 4096 slices."""
