@@ -45,6 +45,7 @@ size_t deflate_ws_carve(DeflateWs *ws, void *mem, int B, int64_t max_len) {
     ws->mhi = (uint32_t *)take((size_t)B * ws->stride * sizeof(uint32_t));
     ws->syms = ws->mtab;  // the dense symbol array reuses the probe table once the walk is over
     ws->rec = (uint32_t *)take((size_t)B * ws->stride * sizeof(uint32_t));
+    ws->probe_next = (uint32_t *)take(kMaxSm * sizeof(uint32_t));
     ws->mask_stride = align_up(ws->stride / 32 + 1, 4);
     ws->mask = (uint32_t *)take((size_t)B * ws->mask_stride * sizeof(uint32_t));
     ws->max_win = (int)(max_len / kWalkWin + 1);
@@ -376,27 +377,51 @@ __global__ void __launch_bounds__(32 * kRunWarps) k_run_recs(const uint8_t *__re
 // steps on paper, yet measured 9 % slower with the phases inside one CTA (shared-memory queues, barriers) and 20 %
 // slower as separate kernels over per-stream queues: the late phases are chains of dependent L2 loads with nothing
 // else to issue, while here the short walks of other warps fill those gaps.
-constexpr int kProbeThreads = 256;
-__global__ void __launch_bounds__(kProbeThreads, 8) k_probe(const uint8_t *__restrict__ in, uint32_t in_stride,
-                                                            const int32_t *__restrict__ in_len, const ChainRec *__restrict__ recs,
-                                                            uint32_t *__restrict__ mlo, uint32_t *__restrict__ mhi, uint32_t stride) {
-    // strides are 32-bit so that re-deriving a per-stream pointer (the kernel runs at 32 registers and the
-    // compiler rematerialises them inside the walk) is one wide multiply-add
-    const uint32_t stream = blockIdx.y;
-    const int n = in_len[stream];
-    const uint64_t o = (uint64_t)stream * stride;
-    const uint8_t *w_s = in + (uint64_t)stream * in_stride;
-    const ChainRec *recs_s = recs + o;
-    // opaque to the compiler: at 32 registers it would otherwise re-derive both bases from the kernel parameters
-    // (nine instructions) at every use inside the walk instead of keeping them
-    asm volatile("" : "+l"(w_s), "+l"(recs_s));
-    LzView v{w_s, recs_s, n};
-    // the grid covers the worst-case payload length; CTAs stride over the real one
-    for (int s = blockIdx.x * kProbeThreads + threadIdx.x; s < n; s += gridDim.x * kProbeThreads) {
-        uint32_t lo, hi;
-        match_probe(v, s, kProbeK, &lo, &hi);
-        mlo[o + s] = lo;
-        mhi[o + s] = hi;
+constexpr int kProbeThreads = 128;
+constexpr int kProbeUnit = 128;  // consecutive positions a warp takes at a time
+__device__ __forceinline__ uint32_t sm_id() { uint32_t r; asm("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
+
+// The walks of neighbouring positions read the same 256 KB of records (the 32 K positions before them), far too much
+// to share when the warps of an SM sit on tiles scattered over the batch (L1 hit rate 36 %, and the kernel is bound
+// by the latency of those loads: six CTAs per SM instead of eight cost 20 %).  So the kernel is persistent and
+// places work by SM: the units (kProbeUnit positions) of the whole batch are cut into one contiguous range per SM,
+// and a warp takes the next unit of the range of the SM it runs on -- the 64 warps of an SM walk 8 K consecutive
+// positions of one stream and share their window in L1.  A warp whose range is used up moves on to the next SM's.
+__global__ void __launch_bounds__(kProbeThreads, 16) k_probe(const uint8_t *__restrict__ in, uint32_t in_stride,
+                                                             const int32_t *__restrict__ in_len, const ChainRec *__restrict__ recs,
+                                                             uint32_t *__restrict__ mlo, uint32_t *__restrict__ mhi, uint32_t stride,
+                                                             uint32_t units_per_stream, uint32_t total_units,
+                                                             uint32_t *__restrict__ sm_next, uint32_t n_sm) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t per = (total_units + n_sm - 1) / n_sm;
+    const uint32_t home = sm_id() % n_sm;
+    for (uint32_t hop = 0; hop < n_sm; hop++) {
+        const uint32_t sm = home + hop < n_sm ? home + hop : home + hop - n_sm;
+        const uint32_t lo_u = sm * per, hi_u = min(total_units, lo_u + per);
+        for (;;) {
+            uint32_t u = 0;
+            if (lane == 0) u = lo_u + atomicAdd(sm_next + sm, 1u);
+            u = __shfl_sync(0xffffffffu, u, 0);
+            if (u >= hi_u) break;
+            const uint32_t stream = u / units_per_stream, first = (u - stream * units_per_stream) * kProbeUnit;
+            const int n = in_len[stream];
+            if ((int)first >= n) continue;
+            // strides are 32-bit so that re-deriving a per-stream pointer is one wide multiply-add
+            const uint64_t o = (uint64_t)stream * stride;
+            const uint8_t *w_s = in + (uint64_t)stream * in_stride;
+            const ChainRec *recs_s = recs + o;
+            // opaque to the compiler: at 32 registers it would otherwise re-derive both bases from the kernel
+            // parameters (nine instructions) at every use inside the walk instead of keeping them
+            asm volatile("" : "+l"(w_s), "+l"(recs_s));
+            LzView v{w_s, recs_s, n};
+#pragma unroll 1
+            for (int s = (int)(first + lane); s < (int)first + kProbeUnit && s < n; s += 32) {
+                uint32_t lo, hi;
+                match_probe(v, s, kProbeK, &lo, &hi);
+                mlo[o + s] = lo;
+                mhi[o + s] = hi;
+            }
+        }
     }
 }
 
@@ -708,8 +733,20 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(const uint8_t *__restrict
     const int per = (ns + kPackThreads - 1) / kPackThreads;
     const int i0 = min(ns, tid * per), i1 = min(ns, i0 + per);
     const uint32_t *sy = syms + (int64_t)stream * stride + d.sym_begin;
+    // a thread's symbols are consecutive (its bits are, too), so its loads stride the warp: eight at a time, so that
+    // their latencies overlap
     uint32_t bits = 0;
-    for (int i = i0; i < i1; i++) bits += (uint32_t)sym_nbits(sy[i], llen, dlen);
+    {
+        int i = i0;
+        for (; i + 8 <= i1; i += 8) {
+            uint32_t q[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) q[j] = __ldg(sy + i + j);
+#pragma unroll
+            for (int j = 0; j < 8; j++) bits += (uint32_t)sym_nbits(q[j], llen, dlen);
+        }
+        for (; i < i1; i++) bits += (uint32_t)sym_nbits(__ldg(sy + i), llen, dlen);
+    }
     uint32_t incl = bits;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -723,12 +760,21 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(const uint8_t *__restrict
     const uint64_t start = bit_start + (uint64_t)hdr_bits + woff + incl - bits;
     if (i1 > i0) {
         BitSink sink{out32 + (start >> 5), 0ull, (int)(start & 31), true};
-        for (int i = i0; i < i1; i++) {
+        auto emit = [&](uint32_t sym) {
             int nb;
-            unsigned long long b = sym_bits(sy[i], lcode, llen, dcode, dlen, &nb);
+            unsigned long long b = sym_bits(sym, lcode, llen, dcode, dlen, &nb);
             if (nb > 32) { sink.put((uint32_t)b, 32); sink.put((uint32_t)(b >> 32), nb - 32); }
             else sink.put((uint32_t)b, nb);
+        };
+        int i = i0;
+        for (; i + 8 <= i1; i += 8) {
+            uint32_t q[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) q[j] = __ldg(sy + i + j);
+#pragma unroll
+            for (int j = 0; j < 8; j++) emit(q[j]);
         }
+        for (; i < i1; i++) emit(__ldg(sy + i));
         sink.finish();
     }
     if (tid == 0)  // END_BLOCK closes the block
@@ -773,9 +819,15 @@ void launch_deflate(const uint8_t *in, int64_t in_stride, const int32_t *in_len,
         k_run_recs<<<gt, 32 * kRunWarps, 0, st>>>(in, in_stride, in_len, ws.dist16, enters, max_chunks, ws.recs, ws.stride);
         }
     }
-    dim3 gp((unsigned)std::min<int64_t>((max_len + kProbeThreads - 1) / kProbeThreads, 512), (unsigned)B);
-    { CCT_KERNEL(k_probe, st);
-    k_probe<<<gp, kProbeThreads, 0, st>>>(in, (uint32_t)in_stride, in_len, ws.recs, ws.mtab, ws.mhi, (uint32_t)ws.stride);
+    {
+        static int n_sm = 0;
+        if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+        const uint32_t units_per_stream = (uint32_t)((max_len + kProbeUnit - 1) / kProbeUnit);
+        { CCT_KERNEL(m_zero_probe, st); cudaMemsetAsync(ws.probe_next, 0, kMaxSm * sizeof(uint32_t), st); }
+        CCT_KERNEL(k_probe, st);
+        k_probe<<<n_sm * 16, kProbeThreads, 0, st>>>(in, (uint32_t)in_stride, in_len, ws.recs, ws.mtab, ws.mhi, (uint32_t)ws.stride,
+                                                     units_per_stream, units_per_stream * (uint32_t)B, ws.probe_next,
+                                                     (uint32_t)std::min(n_sm, kMaxSm));
     }
     dim3 gn((unsigned)std::min<int64_t>((max_len + 1023) / 1024, 512), (unsigned)B);
     { CCT_KERNEL(k_next, st);

@@ -34,12 +34,14 @@ void launch_emit(const uint16_t *hv, const uint8_t *jump, const uint8_t *taken, 
                  int32_t *plen, uint32_t *status, int32_t *stats, int B, int64_t n_px, cudaStream_t st);
 
 // ---- cct_deflate.cu
+constexpr int kMaxSm = 256;
 struct DeflateWs {  // device scratch for one pass over B streams of capacity max_len
     uint16_t *dist16;    // [B][stride] chain links
     ChainRec *recs;      // [B][stride] per-position record read by the chain walks
     uint32_t *mtab, *mhi;  // [B][stride] probe table: entries for chain budget 4096 / 1024
     uint32_t *syms;      // [B][stride] dense LZ77 symbols
     uint32_t *rec;       // [B][stride] symbol a walk standing at each position emits (k_next; slow steps recorded by the walks)
+    uint32_t *probe_next; // [kMaxSm] next unit of each SM's range (k_probe)
     uint32_t *mask;      // [B][mask_stride] bit p = a symbol starts at position p
     int64_t mask_stride; // words per stream
     Walk *exits;         // [B][max_win] state each speculative window was left with
