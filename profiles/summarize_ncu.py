@@ -83,7 +83,9 @@ def full(src, out_txt, traffic_json, streams, note):
             for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                 i = head.index(m)
                 by += float(r[i].replace(",", "")) * UNIT_BYTES.get(units[i], 1.0)
-            traffic[short(r[ik])] = {"dram_bytes_per_stream": by / streams, "streams_in_capture": streams}
+            t = traffic.setdefault(short(r[ik]), {"dram_bytes_per_stream": 0.0, "streams_in_capture": streams, "launches": 0})
+            t["dram_bytes_per_stream"] += by / streams  # a kernel launched once per half batch: the halves add up
+            t["launches"] += 1
     json.dump({"source": note, "kernels": traffic}, open(traffic_json, "w"), indent=1)
     print(f"{len(rows)} kernels -> {out_txt}, {traffic_json}")
 
