@@ -94,6 +94,9 @@ int cct_encode_batch(const uint16_t *d_px, int B, int rows, int cols, uint32_t f
  *   d_in       byte arena; file i is d_in[d_offsets[i] .. d_offsets[i+1])
  *   d_px       [B][rows][cols] uint16 output (output.tobytes(), core.py:543)
  * The transform flags are read from each file's header (core.py:397-401), as the reference does.
+ * Batches of 512 images and more are decoded as two halves that overlap on `stream` and on a library-owned stream
+ * (forked from and joined to `stream` with events: work queued on `stream` after the call still sees the finished
+ * pixels); cct_decode_workspace_bytes covers both halves.  CCT_DEC_SPLIT=0 in the environment turns this off.
  */
 int cct_decode_batch(const uint8_t *d_in, const int64_t *d_offsets, int B, int rows, int cols, uint16_t *d_px,
                      uint32_t *d_status, void *d_ws, size_t ws_bytes, void *stream);
