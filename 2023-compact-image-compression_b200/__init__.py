@@ -6,6 +6,8 @@ repository root.  Layout:
   csrc/      hand-written sm_100a CUDA kernels + the C ABI (include/compact_b200.h) -> libcompact_b200.so
   codec/     host-side mirror of the reference's `codec.core` (Encoder / Decoder) + batch entry points
   synth.py   seeded synthetic CT / radiograph generators used by tests and bench
+  evaluate.py  the reference's compression-ratio study (scripts/evaluate.py) on arrays, CCT column from the GPU
+  shard.py   contiguous shards of a batch over the ranks of one box
 """
 from . import _native  # noqa: F401
 from .codec.core import (DEFAULT_CONFIG, Decoder, Encoder, decode_batch, default_config, encode_batch,  # noqa: F401

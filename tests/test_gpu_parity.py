@@ -421,3 +421,20 @@ def test_stage_chain_links(torch_cuda, native):
         want = _ref_chain_links(b)
         bad = np.nonzero(got[i, :len(b)] != want)[0]
         assert len(bad) == 0, (i, len(b), bad[:8], got[i, bad[:8]], want[bad[:8]])
+
+
+def test_evaluate_harness(torch_cuda, pkg, synth, oracle, tmp_path):
+    """The ratio study of scripts/evaluate.py on arrays: the CCT column is the reference encoder's size."""
+    import importlib
+    ev = importlib.import_module(pkg.__name__ + ".evaluate")
+    imgs = np.stack([synth.synth_ct(s, 128) for s in range(6)])
+    rows = ev.comparison_batch(imgs)
+    for i, r in enumerate(rows):
+        assert r[ev.RAW] == imgs[i].nbytes
+        assert r[ev.CCT] == len(oracle.encode(imgs[i]))
+        assert r[ev.ZIP] == len(zlib.compress(imgs[i].tobytes()))
+        assert 0 < r[ev.PNG] < r[ev.RAW]
+    ev.write_csv(rows, str(tmp_path / "results.csv"))
+    lines = open(tmp_path / "results.csv").read().splitlines()
+    assert lines[0] == "File,Raw,ZIP,PNG,CCT" and len(lines) == 7
+    assert ev.ratios(rows)["CCT"] > ev.ratios(rows)["ZIP"]
