@@ -62,13 +62,14 @@ def _is_tensor(x) -> bool:
 # ---------------------------------------------------------------------------------------------- batch API
 
 class _DeviceScratch:
-    """Per-device cached workspace tensors for the device-pointer entry points."""
+    """Cached workspace tensors for the device-pointer entry points, one per (device, stream): calls on different
+    streams may run at the same time and must not share scratch.  Results are never handed out from here."""
     cache: dict = {}
 
     @classmethod
     def get(cls, device, key: str, nbytes: int):
         torch = _torch()
-        k = (str(device), key)
+        k = (str(device), int(torch.cuda.current_stream(device).cuda_stream), key)
         t = cls.cache.get(k)
         if t is None or t.numel() < nbytes:
             cls.cache[k] = t = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
@@ -107,7 +108,7 @@ def encode_batch(images, config=None, return_stats: bool = False):
             cap = max(B, 1) * int(L.cct_file_bound(rows, cols)) if rows * cols % 16 == 0 else 16
             one = int(L.cct_encode_workspace_bytes(1, rows, cols, flags))
             want = int(L.cct_encode_workspace_bytes(B, rows, cols, flags))
-            arena = _DeviceScratch.get(dev, "enc_arena", cap)
+            arena = torch.empty(max(cap, 256), dtype=torch.uint8, device=dev)  # the caller's: a fresh tensor per call
             ws = _DeviceScratch.get(dev, "enc_ws", _ws_budget(dev, want, one)) if one else arena
             offsets = torch.empty(B + 1, dtype=torch.int64, device=dev)
             status = torch.empty(max(B, 1), dtype=torch.int32, device=dev)

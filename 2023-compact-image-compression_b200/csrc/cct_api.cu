@@ -274,7 +274,7 @@ struct PassHooks {
 
 // Library-owned second stream of a device for cct_decode_batch (one per device, created on first use).
 constexpr int kSplitMin = 512;  // images; below that every kernel is latency-bound and a split only adds launches
-struct SideLane { cudaStream_t stream = nullptr; cudaEvent_t ready = nullptr; };
+struct SideLane { cudaStream_t stream = nullptr; cudaEvent_t ready = nullptr; std::mutex mu; };  // mu: one call at a time queues work on it
 std::map<int, SideLane> g_side;  // guarded by g_mu
 int get_side(SideLane **out) {
     int dev = 0;
@@ -327,6 +327,7 @@ int cct_decode_batch(const uint8_t *d_in, const int64_t *d_offsets, int B, int r
             hooks.alt_stream = side->stream;
             hooks.alt_ws = (char *)d_ws + one;
             hooks.ready = side->ready;
+            std::lock_guard<std::mutex> lk(side->mu);  // the fork/join event is shared: host threads queue their calls in turn
             return decode_impl(d_in, d_offsets, B, rows, cols, d_px, d_status, d_ws, one, (cudaStream_t)stream, &hooks);
         }
     }

@@ -438,3 +438,32 @@ def test_evaluate_harness(torch_cuda, pkg, synth, oracle, tmp_path):
     lines = open(tmp_path / "results.csv").read().splitlines()
     assert lines[0] == "File,Raw,ZIP,PNG,CCT" and len(lines) == 7
     assert ev.ratios(rows)["CCT"] > ev.ratios(rows)["ZIP"]
+
+
+def test_two_streams_and_owned_results(torch_cuda, pkg, synth):
+    """Calls on two CUDA streams run at the same time without sharing scratch, and a result stays valid after the
+    next call (the arena belongs to the caller)."""
+    torch = torch_cuda
+    base = np.stack([synth.synth_ct(s, 128) for s in range(24)])
+    a = torch.from_numpy(np.concatenate([base] * 25).view(np.int16)).cuda()          # 600 images: decode in two halves
+    b = torch.from_numpy(np.concatenate([base[::-1]] * 25).view(np.int16).copy()).cuda()
+    ref_a = pkg.encode_batch(a)
+    ref_b = pkg.encode_batch(b)
+    torch.cuda.synchronize()
+    want_a = (ref_a[0][:int(ref_a[1][-1])].clone(), ref_a[1].clone())
+    want_b = (ref_b[0][:int(ref_b[1][-1])].clone(), ref_b[1].clone())
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(3):
+        with torch.cuda.stream(s1):
+            ea = pkg.encode_batch(a)
+            da, sa = pkg.decode_batch(ea[0], ea[1], (128, 128))
+        with torch.cuda.stream(s2):
+            eb = pkg.encode_batch(b)
+            db, sb = pkg.decode_batch(eb[0], eb[1], (128, 128))
+        torch.cuda.synchronize()
+        assert torch.equal(ea[1], want_a[1]) and torch.equal(ea[0][:want_a[0].numel()], want_a[0])
+        assert torch.equal(eb[1], want_b[1]) and torch.equal(eb[0][:want_b[0].numel()], want_b[0])
+        assert torch.equal(da.view(torch.int16), a) and torch.equal(db.view(torch.int16), b)
+        assert not sa.any().item() and not sb.any().item()
+    # the first results are still what they were
+    assert torch.equal(ref_a[0][:want_a[0].numel()], want_a[0]) and torch.equal(ref_b[0][:want_b[0].numel()], want_b[0])
