@@ -72,10 +72,9 @@ constexpr int kHeadEntries = 32768;
 #endif
 constexpr int kChainWarpsLog2 = CCT_CHAIN_WARPS_LOG2;
 constexpr int kChainWarps = 1 << kChainWarpsLog2;  // hash classes = warps per stream
-constexpr int kRing = 64;       // pending positions per warp
+constexpr int kRing = 256;      // pending positions per warp: up to 31 waiting + the 128 a scan step can add
 
 struct ChainSmem {
-    uint8_t stage[kChainWarps][136];
     uint32_t ring_s[kChainWarps][kRing];
     uint16_t ring_h[kChainWarps][kRing];
 };
@@ -134,9 +133,10 @@ __global__ void __launch_bounds__(32 * kChainWarps) k_chains(const uint8_t *__re
                                                              const int32_t *__restrict__ in_len, uint16_t *__restrict__ dist16,
                                                              int64_t stride) {
     // One CTA per stream; warp k owns the hashes with (h & 3) == k and a quarter of the head table.  Every warp
-    // scans the whole payload (cheap: staged bytes, one hash per lane), keeps the positions of its own class in a
-    // small ring, and runs the table step on 32 of them at a time.  Classes never interact, so the four warps
-    // need no synchronisation -- four times the warps per SM of a single-warp scan with the same 64 KB of tables.
+    // scans the whole payload, 128 positions per step with four consecutive positions per lane (the lane's word and
+    // the next lane's: a funnel shift gives the three bytes of each position), keeps the positions of its own class
+    // in a ring, and runs the table step on 32 of them at a time.  Classes never interact, so the four warps need
+    // no synchronisation -- four times the warps per SM of a single-warp scan with the same 64 KB of tables.
     extern __shared__ __align__(16) unsigned char chain_raw[];
     uint16_t *head = reinterpret_cast<uint16_t *>(chain_raw);
     ChainSmem &sm = *reinterpret_cast<ChainSmem *>(chain_raw + kHeadEntries * sizeof(uint16_t));
@@ -148,37 +148,35 @@ __global__ void __launch_bounds__(32 * kChainWarps) k_chains(const uint8_t *__re
     uint32_t *tab32 = reinterpret_cast<uint32_t *>(tab);
     constexpr int kTabWords = kHeadEntries / kChainWarps / 2;
     for (int i = lane; i < kTabWords; i += 32) tab32[i] = 0x40004000u;  // (0 - 49152) & 0xFFFF
-    uint8_t *stage = sm.stage[k];
-    uint32_t *stage32 = reinterpret_cast<uint32_t *>(stage);
     uint32_t *ring_s = sm.ring_s[k];
     uint16_t *ring_h = sm.ring_h[k];
     __syncwarp();
-    // The payload is staged 128 positions at a time: stage[i] = w[cbase - 4 + i], i in [0, 136), fetched two
-    // chunks ahead into registers.
+    // positions that are in no chain (position 0 doubles as NIL in zlib; the last two have no hash triple)
+    if (k == 0 && lane < 3) { const int s = lane == 0 ? 0 : n - 3 + lane; if (s >= 0 && s < n) d16[s] = 0; }
     const uint32_t *w32 = reinterpret_cast<const uint32_t *>(w);  // stream base is 16-byte aligned
     const int n_words = (n + 3) >> 2;
-    auto fetch = [&](int cbase, int j) -> uint32_t {  // word j of the chunk starting at cbase
-        const int wi = (cbase >> 2) - 1 + j;
-        return (wi >= 0 && wi < n_words) ? __ldg(w32 + wi) : 0u;
+    auto fetch = [&](int cbase) -> uint32_t {  // the lane's word of the 128-byte chunk starting at cbase
+        const int wi = (cbase >> 2) + lane;
+        return wi < n_words ? __ldg(w32 + wi) : 0u;
     };
-    uint32_t p0 = fetch(0, lane), p0x = lane < 2 ? fetch(0, 32 + lane) : 0u;
-    uint32_t p1 = fetch(128, lane), p1x = lane < 2 ? fetch(128, 32 + lane) : 0u;
+    auto flush = [&](int &rd, int wr, int at_least) {  // table steps while `at_least` positions are pending
+        while (wr - rd >= at_least && wr != rd) {
+            const int cnt = min(32, wr - rd);
+            chain_batch(tab, d16, lane, cnt, ring_s[(rd + lane) & (kRing - 1)], ring_h[(rd + lane) & (kRing - 1)]);
+            rd += cnt;
+        }
+    };
+    uint32_t cur = fetch(0), nxt = fetch(128);  // chunks are fetched two ahead
     int wr = 0, rd = 0;  // ring write / read cursors (warp-uniform)
+    const unsigned below = (1u << lane) - 1u;
     for (int cbase = 0; cbase < n; cbase += 128) {
-        stage32[lane] = p0;
-        if (lane < 2) stage32[32 + lane] = p0x;
-        p0 = p1; p0x = p1x;
-        p1 = fetch(cbase + 256, lane);
-        p1x = lane < 2 ? fetch(cbase + 256, 32 + lane) : 0u;
-        __syncwarp();
+        const uint32_t a = cur, nn = nxt;
+        cur = nn;
+        nxt = fetch(cbase + 256);
         if (cbase && (cbase & 8191) == 0) {
             // sweep: flush what is pending (so the table reflects every position below cbase), then re-park the
             // entries older than 32767 at "49152 behind" to keep the 16-bit positions unambiguous
-            if (wr != rd) {
-                const int cnt = wr - rd;
-                chain_batch(tab, d16, lane, cnt, ring_s[(rd + lane) & (kRing - 1)], ring_h[(rd + lane) & (kRing - 1)]);
-                rd = wr;
-            }
+            flush(rd, wr, 1);
             const uint32_t far = (uint32_t)(cbase - 49152) & 0xFFFFu;
             for (int i = lane; i < kTabWords; i += 32) {
                 uint32_t v = tab32[i];
@@ -189,29 +187,40 @@ __global__ void __launch_bounds__(32 * kChainWarps) k_chains(const uint8_t *__re
             }
             __syncwarp();
         }
+        // bytes 4..7 after the lane's word: the next lane's word, or the next chunk's first
+        const uint32_t up = __shfl_down_sync(0xffffffffu, a, 1), wrap = __shfl_sync(0xffffffffu, nn, 0);
+        const uint32_t b = lane == 31 ? wrap : up;
+        const int s0 = cbase + 4 * lane;
+        uint32_t hh[4];
+        unsigned mine = 0;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            const int s = cbase + 32 * j + lane;
-            const uint8_t *sb = stage + 4 + 32 * j + lane;  // sb[i] = w[s + i]
-            const bool valid = s >= 1 && s + 2 < n;         // position 0 doubles as NIL in zlib: never a match source
-            const uint32_t h = valid ? hash3(sb) : 0u;
-            const bool mine = valid && (h & (kChainWarps - 1)) == (uint32_t)k;
-            const unsigned bal = __ballot_sync(0xffffffffu, mine);
-            if (mine) {
-                const int slot = (wr + __popc(bal & ((1u << lane) - 1u))) & (kRing - 1);
-                ring_s[slot] = (uint32_t)s;
-                ring_h[slot] = (uint16_t)(h >> kChainWarpsLog2);
-            }
-            if (!valid && s < n && k == 0) d16[s] = 0;
-            wr += __popc(bal);
-            __syncwarp();
-            if (wr - rd >= 32) {
-                chain_batch(tab, d16, lane, 32, ring_s[(rd + lane) & (kRing - 1)], ring_h[(rd + lane) & (kRing - 1)]);
-                rd += 32;
+            const uint32_t t = __funnelshift_r(a, b, 8 * j);  // bytes of position s0 + j, low byte first
+            hh[j] = (((t & 0xFFu) << 10) ^ ((t >> 3) & 0x1FE0u) ^ ((t >> 16) & 0xFFu)) & 0x7FFFu;  // hash3
+            const int s = s0 + j;
+            if (s >= 1 && s + 2 < n && (hh[j] & (kChainWarps - 1)) == (uint32_t)k) mine |= 1u << j;
+        }
+        // ring slots in position order: the lanes below first, then this lane's own earlier positions
+        int before = 0, total = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const unsigned bal = __ballot_sync(0xffffffffu, (mine >> j) & 1u);
+            before += __popc(bal & below);
+            total += __popc(bal);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if ((mine >> j) & 1u) {
+                const int slot = (wr + before + __popc(mine & ((1u << j) - 1u))) & (kRing - 1);
+                ring_s[slot] = (uint32_t)(s0 + j);
+                ring_h[slot] = (uint16_t)(hh[j] >> kChainWarpsLog2);
             }
         }
+        wr += total;
+        __syncwarp();
+        flush(rd, wr, 32);
     }
-    if (wr != rd) chain_batch(tab, d16, lane, wr - rd, ring_s[(rd + lane) & (kRing - 1)], ring_h[(rd + lane) & (kRing - 1)]);
+    flush(rd, wr, 1);
 }
 
 // Run lengths around every position: rb[p] / rl[p] = number of bytes equal to w[p] immediately before / after p,
