@@ -191,15 +191,22 @@ __global__ void __launch_bounds__(32 * kChainWarps) k_chains(const uint8_t *__re
         const uint32_t up = __shfl_down_sync(0xffffffffu, a, 1), wrap = __shfl_sync(0xffffffffu, nn, 0);
         const uint32_t b = lane == 31 ? wrap : up;
         const int s0 = cbase + 4 * lane;
+        // positions with a hash triple that may enter a chain: all four, except in the first and the last chunks
+        unsigned ok = 0xFu;
+        if (cbase == 0 || cbase + 130 >= n) {  // (warp-uniform)
+            ok = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) if (s0 + j >= 1 && s0 + j + 2 < n) ok |= 1u << j;
+        }
         uint32_t hh[4];
         unsigned mine = 0;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const uint32_t t = __funnelshift_r(a, b, 8 * j);  // bytes of position s0 + j, low byte first
             hh[j] = (((t & 0xFFu) << 10) ^ ((t >> 3) & 0x1FE0u) ^ ((t >> 16) & 0xFFu)) & 0x7FFFu;  // hash3
-            const int s = s0 + j;
-            if (s >= 1 && s + 2 < n && (hh[j] & (kChainWarps - 1)) == (uint32_t)k) mine |= 1u << j;
+            if ((hh[j] & (kChainWarps - 1)) == (uint32_t)k) mine |= 1u << j;
         }
+        mine &= ok;
         // ring slots in position order: the lanes below first, then this lane's own earlier positions
         int before = 0, total = 0;
 #pragma unroll
@@ -208,12 +215,13 @@ __global__ void __launch_bounds__(32 * kChainWarps) k_chains(const uint8_t *__re
             before += __popc(bal & below);
             total += __popc(bal);
         }
+        int slot = wr + before;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             if ((mine >> j) & 1u) {
-                const int slot = (wr + before + __popc(mine & ((1u << j) - 1u))) & (kRing - 1);
-                ring_s[slot] = (uint32_t)(s0 + j);
-                ring_h[slot] = (uint16_t)(hh[j] >> kChainWarpsLog2);
+                ring_s[slot & (kRing - 1)] = (uint32_t)(s0 + j);
+                ring_h[slot & (kRing - 1)] = (uint16_t)(hh[j] >> kChainWarpsLog2);
+                slot++;
             }
         }
         wr += total;
