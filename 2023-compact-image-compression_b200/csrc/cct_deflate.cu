@@ -137,6 +137,9 @@ __global__ void __launch_bounds__(32 * kChainWarps) k_chains(const uint8_t *__re
     // the next lane's: a funnel shift gives the three bytes of each position), keeps the positions of its own class
     // in a ring, and runs the table step on 32 of them at a time.  Classes never interact, so the four warps need
     // no synchronisation -- four times the warps per SM of a single-warp scan with the same 64 KB of tables.
+    // (Sharing the scan instead -- each warp hashes a quarter of every 128 positions and files them into all four
+    // rings, two barriers per step for the offsets -- has 40 % fewer instructions and measured 26 % slower: the table
+    // steps are latency-bound and the barriers make every warp wait for the slowest one's.)
     extern __shared__ __align__(16) unsigned char chain_raw[];
     uint16_t *head = reinterpret_cast<uint16_t *>(chain_raw);
     ChainSmem &sm = *reinterpret_cast<ChainSmem *>(chain_raw + kHeadEntries * sizeof(uint16_t));
