@@ -409,13 +409,21 @@ struct OpsLane {
     uint32_t jumps;  // bit j: byte j is a JUMP
     int d[4];        // delta of the op starting at byte j (0 where none)
 };
+// kEdge: the step may reach `stop` or the last byte before `end` (otherwise every byte is valid and every FULL op whole)
+template <bool kEdge>
 __device__ __forceinline__ OpsLane ops_lane(uint32_t word, uint32_t nb0, int pos, int stop, int end, uint32_t &carry, int lane) {
-    uint32_t tags = 0, valid = 0;
+    uint32_t tags = 0, valid = 0xFu;
+    if (kEdge) {
+        valid = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) if (pos + j < stop) valid |= 1u << j;
+    }
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         const uint32_t bj = (word >> (8 * j)) & 0xFFu;
-        if (pos + j < stop) { valid |= 1u << j; if ((bj & 0xF0u) == 0xE0u) tags |= 1u << j; }
+        if ((bj & 0xF0u) == 0xE0u) tags |= 1u << j;
     }
+    tags &= valid;
     // parity of the tagged run reaching byte 0 of this lane
     const uint32_t tail = (uint32_t)__clz((int)~(tags << 28));  // tagged bytes at the top of the word (4: all of them)
     const uint32_t open = __ballot_sync(0xffffffffu, tags != 0xFu), odd = __ballot_sync(0xffffffffu, tail & 1u);
@@ -430,7 +438,7 @@ __device__ __forceinline__ OpsLane ops_lane(uint32_t word, uint32_t nb0, int pos
         const bool tag = (tags >> j) & 1u, start = !e && ((valid >> j) & 1u);
         e = (!e && tag) ? 1u : 0u;
         const bool jump = start && (bj & 0xC0u) == 0x80u;
-        const bool full = tag && pos + j + 1 < end;
+        const bool full = tag && (!kEdge || pos + j + 1 < end);
         const bool op = start && !jump && (!tag || full);
         r.d[j] = op ? op_delta(bj, nbj, full) : 0;
         if (op) r.ops |= 1u << j;
@@ -486,7 +494,10 @@ __global__ void __launch_bounds__(32 * kOpsWarps) k_dec_ops_scan(const uint8_t *
     for (int g = 0; g < kOpsChunk / kOpsGroup && lo + kOpsGroup * g < stop; g++) {
         uint32_t nb0;
         const uint32_t word = rd.step(g, nb0);
-        const OpsLane L = ops_lane(word, nb0, lo + kOpsGroup * g + 4 * lane, stop, end, carry, lane);
+        const int pos0 = lo + kOpsGroup * g;
+        const bool edge = pos0 + kOpsGroup > stop || pos0 + kOpsGroup >= end;  // (warp-uniform)
+        const OpsLane L = edge ? ops_lane<true>(word, nb0, pos0 + 4 * lane, stop, end, carry, lane)
+                               : ops_lane<false>(word, nb0, pos0 + 4 * lane, stop, end, carry, lane);
         cnt += __popc(L.ops);
         sum += L.d[0] + L.d[1] + L.d[2] + L.d[3];
     }
@@ -531,7 +542,10 @@ __global__ void __launch_bounds__(32 * kOpsWarps) k_dec_ops_emit(const uint8_t *
     for (int g = 0; g < kOpsChunk / kOpsGroup && lo + kOpsGroup * g < stop && k_base < n_px; g++) {
         uint32_t nb0;
         const uint32_t word = rd.step(g, nb0);
-        const OpsLane L = ops_lane(word, nb0, lo + kOpsGroup * g + 4 * lane, stop, end, carry, lane);
+        const int pos0 = lo + kOpsGroup * g;
+        const bool edge = pos0 + kOpsGroup > stop || pos0 + kOpsGroup >= end;  // (warp-uniform)
+        const OpsLane L = edge ? ops_lane<true>(word, nb0, pos0 + 4 * lane, stop, end, carry, lane)
+                               : ops_lane<false>(word, nb0, pos0 + 4 * lane, stop, end, carry, lane);
         // inclusive warp scan of (delta sum << 8 | op count): at most 128 ops per step, so the count never carries
         const int mine = (L.d[0] + L.d[1] + L.d[2] + L.d[3]) * 256 + __popc(L.ops);
         int incl = mine;
