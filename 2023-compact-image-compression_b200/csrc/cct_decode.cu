@@ -649,9 +649,26 @@ __global__ void __launch_bounds__(256) k_dec_scatter(const uint16_t *__restrict_
             for (int e = 0; e < 4; e++) r[e] = __ldg(order + r[e]);
         }
     }
+    // The kernel is bound by the sectors its scattered 2-byte stores touch.  Four consecutive positions of a Hilbert
+    // traversal are a 2x2 cell, so the four pixels are two horizontal pairs {even index, +1} in one of three
+    // matchings: those go out as two 4-byte stores (selects, not branches: neighbouring lanes differ in orientation).
     uint16_t *dst = px + (int64_t)i * n_px;
+    const bool m1 = ((r[0] ^ r[1]) == 1) & ((r[2] ^ r[3]) == 1);  // (0,1) (2,3)
+    const bool m2 = ((r[1] ^ r[2]) == 1) & ((r[3] ^ r[0]) == 1);  // (1,2) (3,0)
+    const bool m3 = ((r[0] ^ r[2]) == 1) & ((r[1] ^ r[3]) == 1);  // (0,2) (1,3): meshed units
+    if (m1 | m2 | m3) {
+        const int32_t a0 = m2 ? r[1] : r[0], a1 = m1 ? r[1] : r[2];
+        const int32_t b0 = m1 ? r[2] : (m2 ? r[3] : r[1]), b1 = m2 ? r[0] : r[3];
+        const uint32_t va0 = m2 ? v[1] : v[0], va1 = m1 ? v[1] : v[2];
+        const uint32_t vb0 = m1 ? v[2] : (m2 ? v[3] : v[1]), vb1 = m2 ? v[0] : v[3];
+        // the even index is the low half of the word
+        *reinterpret_cast<uint32_t *>(dst + (a0 & ~1)) = (a0 & 1) ? (va1 | (va0 << 16)) : (va0 | (va1 << 16));
+        *reinterpret_cast<uint32_t *>(dst + (b0 & ~1)) = (b0 & 1) ? (vb1 | (vb0 << 16)) : (vb0 | (vb1 << 16));
+        (void)a1; (void)b1;
+    } else {
 #pragma unroll
-    for (int e = 0; e < 4; e++) dst[r[e]] = v[e];
+        for (int e = 0; e < 4; e++) dst[r[e]] = v[e];
+    }
 }
 
 void launch_decode(const uint8_t *files, const int64_t *offsets, int B, int rows, int cols, const int32_t *order_fractal,
