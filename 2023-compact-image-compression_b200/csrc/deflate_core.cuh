@@ -510,7 +510,6 @@ struct TreeScratch {
     alignas(8) uint32_t pq[kHeapSize + 3];
     int16_t heap[kHeapSize];  // nodes in the order they left the queue (zlib keeps them in the top of its heap array)
     uint16_t bl_count[kMaxBits + 1];
-    uint16_t next_code[kMaxBits + 1];  // gen_codes' running code per length (here, not on the stack: it is indexed by data)
     int heap_len, heap_max;
     int64_t opt_len, static_len;
 };
@@ -619,10 +618,9 @@ CCT_HDN inline void build_tree(TreeScratch &s, T &t, int kind) {
     }
     s.heap_len = heap_len; s.heap_max = heap_max; s.opt_len = opt_len; s.static_len = static_len;
     // gen_codes
-    uint32_t code = 0;
-    uint16_t *next_code = s.next_code;
+    uint32_t next_code[kMaxBits + 1], code = 0;
     next_code[0] = 0;
-    for (bits = 1; bits <= kMaxBits; bits++) { code = (code + s.bl_count[bits - 1]) << 1; next_code[bits] = (uint16_t)(code & 0xFFFFu); }
+    for (bits = 1; bits <= kMaxBits; bits++) { code = (code + s.bl_count[bits - 1]) << 1; next_code[bits] = code & 0xFFFFu; }
     for (n = 0; n <= max_code; n++) {
         int len = t.len[n];
         if (len == 0) continue;
