@@ -755,23 +755,39 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(const uint8_t *__restrict
     if (tid < kDCodes + 2) { dcode[tid] = d.dcode[tid]; dlen[tid] = d.dlen[tid]; }
     __syncthreads();
     const int ns = (int)d.nsym;
-    const int per = (ns + kPackThreads - 1) / kPackThreads;
-    const int i0 = min(ns, tid * per), i1 = min(ns, i0 + per);
+    // A thread's symbols are consecutive (its bits are, too), so its loads stride the warp.  The runs are cut on
+    // 16-byte boundaries of the symbol array -- `mis` symbols before the block's first one is such a boundary -- so a
+    // thread fetches its run in 16-byte loads, two at a time (a quarter of the requests of 4-byte loads; the first and
+    // last quad of the block may reach outside it: those symbols are skipped, the array is padded).
     const uint32_t *sy = syms + (int64_t)stream * stride + d.sym_begin;
-    // a thread's symbols are consecutive (its bits are, too), so its loads stride the warp: eight at a time, so that
-    // their latencies overlap
-    uint32_t bits = 0;
-    {
-        int i = i0;
-        for (; i + 8 <= i1; i += 8) {
-            uint32_t q[8];
+    const int mis = (int)(d.sym_begin & 3u);
+    const uint4 *quads = reinterpret_cast<const uint4 *>(sy - mis);
+    const int nq = (mis + ns + 3) >> 2;                                  // quads covering the block
+    const int per = (nq + kPackThreads - 1) / kPackThreads;              // quads per thread
+    const int q0 = min(nq, tid * per), q1 = min(nq, q0 + per);
+    const int lo = mis, hi = mis + ns;                                   // the block's symbols in quad coordinates
+    auto for_each = [&](auto &&fn) {
+        int q = q0;
+        for (; q + 2 <= q1; q += 2) {
+            const uint4 u = __ldg(quads + q), v = __ldg(quads + q + 1);
+            const uint32_t sym[8] = {u.x, u.y, u.z, u.w, v.x, v.y, v.z, v.w};
+            if (4 * q >= lo && 4 * q + 8 <= hi) {
 #pragma unroll
-            for (int j = 0; j < 8; j++) q[j] = __ldg(sy + i + j);
+                for (int j = 0; j < 8; j++) fn(sym[j]);
+            } else {
 #pragma unroll
-            for (int j = 0; j < 8; j++) bits += (uint32_t)sym_nbits(q[j], llen, dlen);
+                for (int j = 0; j < 8; j++) if (4 * q + j >= lo && 4 * q + j < hi) fn(sym[j]);
+            }
         }
-        for (; i < i1; i++) bits += (uint32_t)sym_nbits(__ldg(sy + i), llen, dlen);
-    }
+        for (; q < q1; q++) {
+            const uint4 u = __ldg(quads + q);
+            const uint32_t sym[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) if (4 * q + j >= lo && 4 * q + j < hi) fn(sym[j]);
+        }
+    };
+    uint32_t bits = 0;
+    for_each([&](uint32_t sym) { bits += (uint32_t)sym_nbits(sym, llen, dlen); });
     uint32_t incl = bits;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -783,23 +799,14 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(const uint8_t *__restrict
     uint32_t woff = 0;
     for (int w = 0; w < wid; w++) woff += warp_sum[w];
     const uint64_t start = bit_start + (uint64_t)hdr_bits + woff + incl - bits;
-    if (i1 > i0) {
+    if (bits) {
         BitSink sink{out32 + (start >> 5), 0ull, (int)(start & 31), true};
-        auto emit = [&](uint32_t sym) {
+        for_each([&](uint32_t sym) {
             int nb;
             unsigned long long b = sym_bits(sym, lcode, llen, dcode, dlen, &nb);
             if (nb > 32) { sink.put((uint32_t)b, 32); sink.put((uint32_t)(b >> 32), nb - 32); }
             else sink.put((uint32_t)b, nb);
-        };
-        int i = i0;
-        for (; i + 8 <= i1; i += 8) {
-            uint32_t q[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) q[j] = __ldg(sy + i + j);
-#pragma unroll
-            for (int j = 0; j < 8; j++) emit(q[j]);
-        }
-        for (; i < i1; i++) emit(__ldg(sy + i));
+        });
         sink.finish();
     }
     if (tid == 0)  // END_BLOCK closes the block
