@@ -789,6 +789,16 @@ int cct_decode_host(const uint8_t *h_in, const int64_t *h_offsets, int B, int ro
     return CCT_OK;
 }
 
+int cct_debug_host_schedule(int B, size_t n_px, int decode, int32_t *starts, int cap) {
+    if (B < 0 || n_px == 0 || !starts) return CCT_E_ARG;
+    std::vector<int> st;
+    if (B == 0) { if (cap < 1) return CCT_E_ARG; starts[0] = 0; return 0; }
+    host_schedule(B, n_px, st, decode != 0);
+    if ((int)st.size() > cap) return CCT_E_ARG;
+    for (size_t k = 0; k < st.size(); k++) starts[k] = st[k];
+    return (int)st.size() - 1;
+}
+
 void cct_release(void) {
     {
         std::lock_guard<std::mutex> lk(g_ctx_mu);

@@ -141,6 +141,10 @@ int cct_deflate_batch(const uint8_t *d_in, size_t in_stride, const int32_t *d_in
  * position with the same 3-byte hash (0 = none or >= 32768; position 0 is never a source). */
 int cct_debug_chains(const uint8_t *d_in, size_t in_stride, const int32_t *d_in_len, int B, uint16_t *d_dist16,
                      size_t stride, void *stream);
+/* Host logic tap (needs no device): the pass schedule cct_encode_host (decode = 0) / cct_decode_host (decode = 1)
+ * use for B images of n_px pixels.  Writes the first image of every pass and then B to starts[0 .. n_pass] and returns
+ * n_pass, or CCT_E_ARG when `cap` entries do not hold them. */
+int cct_debug_host_schedule(int B, size_t n_px, int decode, int32_t *starts, int cap);
 /* RFC 1950 inflate of B streams (any conformant zlib stream). d_status[i] gets CCT_ST_INFLATE on error
  * (invalid code, output longer than out_stride, truncated input, Adler-32 mismatch). */
 size_t cct_inflate_workspace_bytes(int B, size_t out_stride);

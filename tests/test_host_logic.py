@@ -242,3 +242,27 @@ def test_sharded_index_gather_gloo_world2(tmp_path):
     for p in procs:
         out, err = p.communicate(timeout=120)
         assert p.returncode == 0 and "ok" in out, err[-2000:]
+
+
+def test_host_pass_schedule(pkg):
+    """The pass schedule of the host-buffer entry points (pure host logic): passes tile the batch in order, none is
+    empty or larger than the 512 MiB pass, and the batch opens with the short passes that start the pipeline."""
+    import ctypes as C
+    L = pkg._native.lib()
+    buf = (C.c_int32 * 64)()
+    per = (512 << 20) // (512 * 512 * 2)
+    for decode in (0, 1):
+        for B in (0, 1, 7, per, per + 1, 4096, 16384):
+            n = L.cct_debug_host_schedule(B, 512 * 512, decode, buf, 64)
+            assert n >= (1 if B else 0)
+            starts = list(buf[:n + 1])
+            assert starts[0] == 0 and starts[-1] == B
+            sizes = [b - a for a, b in zip(starts, starts[1:])]
+            assert all(0 < s <= per for s in sizes) or B == 0
+            if B > per:
+                leads = [per // 8, per // 4, per // 2] if decode else [per // 4, per // 2]
+                assert sizes[:len(leads)] == leads
+                assert max(sizes[len(leads):]) - min(sizes[len(leads):-1] or [sizes[-1]]) <= max(sizes[len(leads):])  # equal passes, a shorter last one
+            else:
+                assert sizes == ([B] if B else [])
+    assert L.cct_debug_host_schedule(4096, 512 * 512, 0, buf, 2) < 0  # too few entries
