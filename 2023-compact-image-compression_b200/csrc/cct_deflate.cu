@@ -2,10 +2,11 @@
 //
 // Replaces `zlib.compress(data, level = 9)` (reference src/codec/core.py:340).  Stages (see
 // deflate_core.cuh for the decomposition and SURVEY.md Appendix B for the algorithm being matched):
-//   k_chains       hash-chain links for every position (warp per stream, head table in shared memory)
-//   k_runs         equal-byte run lengths around every position; packs the per-position ChainRec
-//   k_probe        cold-start longest_match over the first kProbeK chain entries, one thread per position
-//   k_walk_spec / k_walk_stitch / k_symscan   deflate_slow's lazy state machine as a windowed speculative walk
+//   k_chains       hash-chain links for every position (CTA per stream, warp per hash class, head table in shared memory)
+//   k_run_edges / k_run_link / k_run_recs   equal-byte run lengths around every position; packs the per-position ChainRec
+//   k_probe        cold-start longest_match over the first kProbeK chain entries, one thread per position (persistent,
+//                  work placed by SM)
+//   k_next / k_walk_spec / k_walk_stitch / k_symscan   deflate_slow's lazy state machine as a windowed speculative walk
 //   k_adler        Adler-32 of the payload (CTA per stream)
 //   k_block_build  per 16383-symbol block: histograms, build_tree x3, block-type choice, header bits
 //   k_layout       bit offsets of the blocks of each stream, stream length, zlib header/trailer
