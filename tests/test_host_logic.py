@@ -266,3 +266,18 @@ def test_host_pass_schedule(pkg):
             else:
                 assert sizes == ([B] if B else [])
     assert L.cct_debug_host_schedule(4096, 512 * 512, 0, buf, 2) < 0  # too few entries
+
+
+def test_evaluate_host_helpers(pkg, tmp_path):
+    """The host-side pieces of the ratio study (scripts/evaluate.py:124-139): CSV layout, mean ratios, PNG size."""
+    import importlib
+    ev = importlib.import_module(pkg.__name__ + ".evaluate")
+    rows = [{ev.FILE: "(0000)", ev.RAW: 1000, ev.ZIP: 500, ev.PNG: 400, ev.CCT: 250},
+            {ev.FILE: "(0001)", ev.RAW: 1000, ev.ZIP: 250, ev.PNG: 500, ev.CCT: 200}]
+    ev.write_csv(rows, str(tmp_path / "r.csv"))
+    assert open(tmp_path / "r.csv").read() == "File,Raw,ZIP,PNG,CCT\n(0000),1000,500,400,250\n(0001),1000,250,500,200"
+    r = ev.ratios(rows)
+    assert r == {ev.ZIP: 3.0, ev.PNG: 2.25, ev.CCT: 4.5}
+    flat = np.zeros((64, 64), dtype=np.uint16)
+    noisy = np.random.default_rng(0).integers(0, 4096, (64, 64)).astype(np.uint16)
+    assert 0 < ev._png_size(flat) < ev._png_size(noisy) < 2 * noisy.nbytes
