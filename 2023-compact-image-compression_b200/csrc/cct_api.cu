@@ -168,8 +168,11 @@ int check_shape(int B, int rows, int cols) {
     return CCT_OK;
 }
 
+// Images per pass: several kernels index the image with gridDim.y, which is limited to 65535.
+constexpr int kMaxPass = 65535;
 int fit_batch(size_t ws_bytes, int B, const std::function<size_t(int)> &need) {
     if (B == 0) return 0;
+    B = std::min(B, kMaxPass);
     if (need(B) <= ws_bytes) return B;
     if (need(1) > ws_bytes) return 0;
     int lo = 1, hi = B;  // need(lo) fits, need(hi) does not
@@ -313,7 +316,7 @@ int cct_decode_batch(const uint8_t *d_in, const int64_t *d_offsets, int B, int r
     // idle issue slots (the half that finished k_inflate_sym expands while the other still decodes Huffman codes).
     // CCT_DEC_SPLIT=0 turns it off.
     static const int parts = [] { const char *e = getenv("CCT_DEC_SPLIT"); return e ? atoi(e) : 2; }();
-    if (parts > 1 && B >= kSplitMin && check_shape(B, rows, cols) == CCT_OK && d_ws) {
+    if (parts > 1 && B >= kSplitMin && (B + parts - 1) / parts <= kMaxPass && check_shape(B, rows, cols) == CCT_OK && d_ws) {
         const int each = (B + parts - 1) / parts;
         const size_t one = decode_ws_bytes(each, (int64_t)rows * cols);
         SideLane *side = nullptr;
@@ -615,7 +618,7 @@ int get_ctx(int device, HostCtx **out) {
 int host_schedule(int B, size_t n_px, std::vector<int> &starts, bool decode) {
     int per = (int)std::max<size_t>(1, ((size_t)512 << 20) / (n_px * 2));
     if (const char *e = getenv("CCT_HOST_PASS")) { const int v = atoi(e); per = v > 0 ? v : B; }
-    per = std::max(1, std::min(per, B));
+    per = std::max(1, std::min(std::min(per, B), kMaxPass));
     std::vector<int> div = decode ? std::vector<int>{8, 4, 2} : std::vector<int>{4, 2};
     if (const char *e = getenv("CCT_HOST_LEADS")) {
         div.clear();

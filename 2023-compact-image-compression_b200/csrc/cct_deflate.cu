@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <mutex>
 
 #include "cct_kernels.h"
 #include "deflate_core.cuh"
@@ -814,11 +815,31 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(const uint8_t *__restrict
         or_bits(out32, bit_start + (uint64_t)hdr_bits + d.body_bits - llen[256], lcode[256], llen[256]);
 }
 
+// Per-device launch state: opt-in shared-memory sizes are a property of (function, device) and the SM count of the
+// device, so both are kept per device (several devices may be driven from one process through cct_*_host).
+struct DevState { int n_sm = 0; };
+static const DevState &dev_state() {
+    static std::mutex mu;
+    static DevState per_dev[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev = std::min(std::max(dev, 0), 63);
+    std::lock_guard<std::mutex> lk(mu);
+    DevState &d = per_dev[dev];
+    if (!d.n_sm) {
+        const int chain_smem = kHeadEntries * (int)sizeof(uint16_t) + (int)sizeof(ChainSmem);
+        cudaFuncSetAttribute(k_chains, cudaFuncAttributeMaxDynamicSharedMemorySize, chain_smem);
+        cudaFuncSetAttribute(k_block_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlockBuildSmem));
+        cudaDeviceGetAttribute(&d.n_sm, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return d;
+}
+
 void launch_chains(const uint8_t *in, int64_t in_stride, const int32_t *in_len, int B, uint16_t *dist16, int64_t stride,
                    cudaStream_t st) {
     if (B == 0) return;
     const int chain_smem = kHeadEntries * (int)sizeof(uint16_t) + (int)sizeof(ChainSmem);
-    cudaFuncSetAttribute(k_chains, cudaFuncAttributeMaxDynamicSharedMemorySize, chain_smem);
+    dev_state();
     { CCT_KERNEL(k_chains, st);
     k_chains<<<B, 32 * kChainWarps, chain_smem, st>>>(in, in_stride, in_len, dist16, stride);
     }
@@ -827,13 +848,8 @@ void launch_chains(const uint8_t *in, int64_t in_stride, const int32_t *in_len, 
 void launch_deflate(const uint8_t *in, int64_t in_stride, const int32_t *in_len, int B, int64_t max_len, uint8_t *out,
                     int64_t out_stride, int32_t *out_len, const DeflateWs &ws, cudaStream_t st) {
     if (B == 0) return;
-    static bool attr_done = false;
     const int chain_smem = kHeadEntries * (int)sizeof(uint16_t) + (int)sizeof(ChainSmem);
-    if (!attr_done) {
-        cudaFuncSetAttribute(k_chains, cudaFuncAttributeMaxDynamicSharedMemorySize, chain_smem);
-        cudaFuncSetAttribute(k_block_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlockBuildSmem));
-        attr_done = true;
-    }
+    const DevState &dev = dev_state();
     { CCT_KERNEL(k_chains, st);
     k_chains<<<B, 32 * kChainWarps, chain_smem, st>>>(in, in_stride, in_len, ws.dist16, ws.stride);
     }
@@ -853,9 +869,8 @@ void launch_deflate(const uint8_t *in, int64_t in_stride, const int32_t *in_len,
         }
     }
     {
-        static int n_sm = 0;
         // (asking for an all-L1 carve-out made the kernel 38 % slower: fewer CTAs fit once no shared memory is configured)
-        if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+        const int n_sm = dev.n_sm;
         const uint32_t units_per_stream = (uint32_t)((max_len + kProbeUnit - 1) / kProbeUnit);
         { CCT_KERNEL(m_zero_probe, st); cudaMemsetAsync(ws.probe_next, 0, kMaxSm * sizeof(uint32_t), st); }
         CCT_KERNEL(k_probe, st);
