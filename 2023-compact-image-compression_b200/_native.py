@@ -88,8 +88,8 @@ def lib():
     L.cct_inflate_batch.argtypes = [u8p, sz, vp, C.c_int, u8p, sz, vp, vp, vp, sz, vp]
     L.cct_debug_host_schedule.restype = C.c_int
     L.cct_debug_host_schedule.argtypes = [C.c_int, sz, C.c_int, vp, C.c_int]
-    L.cct_debug_chains.restype = C.c_int
-    L.cct_debug_chains.argtypes = [u8p, sz, vp, C.c_int, vp, sz, vp]
+    L.cct_debug_match_tables.restype = C.c_int
+    L.cct_debug_match_tables.argtypes = [u8p, sz, vp, C.c_int, sz, vp, vp, vp, sz, vp, sz, vp]
     L.cct_inflate_workspace_bytes.restype = sz
     L.cct_inflate_workspace_bytes.argtypes = [C.c_int, sz]
     L.cct_launch_count.restype = C.c_longlong
@@ -117,7 +117,7 @@ EXPORTS = ["cct_version", "cct_strerror", "cct_last_cuda_error", "cct_device_cou
            "cct_encode_workspace_bytes", "cct_decode_workspace_bytes", "cct_encode_batch", "cct_decode_batch",
            "cct_read_header", "cct_encode_host", "cct_decode_host", "cct_release", "cct_payload_bound",
            "cct_debug_encode_stages", "cct_deflate_workspace_bytes", "cct_deflate_bound", "cct_deflate_batch",
-           "cct_inflate_batch", "cct_inflate_workspace_bytes", "cct_debug_chains", "cct_debug_host_schedule", "cct_launch_count", "cct_profile_enable", "cct_profile_read"]
+           "cct_inflate_batch", "cct_inflate_workspace_bytes", "cct_debug_match_tables", "cct_debug_host_schedule", "cct_launch_count", "cct_profile_enable", "cct_profile_read"]
 
 
 def check(code: int):

@@ -502,12 +502,21 @@ int cct_deflate_batch(const uint8_t *d_in, size_t in_stride, const int32_t *d_in
     return CCT_OK;
 }
 
-int cct_debug_chains(const uint8_t *d_in, size_t in_stride, const int32_t *d_in_len, int B, uint16_t *d_dist16,
-                     size_t stride, void *stream) {
-    if (B < 0 || (B > 0 && (!d_in || !d_in_len || !d_dist16)) || in_stride % 16) return CCT_E_ARG;
+int cct_debug_match_tables(const uint8_t *d_in, size_t in_stride, const int32_t *d_in_len, int B, size_t max_len,
+                           uint64_t *d_ent, uint32_t *d_lo, uint32_t *d_hi, size_t stride, void *d_ws, size_t ws_bytes,
+                           void *stream) {
+    if (B < 0 || (B > 0 && (!d_in || !d_in_len || !d_ws)) || in_stride % 16 || max_len > (1u << 27) || stride < max_len) return CCT_E_ARG;
     if (cct_device_count() == 0) return CCT_E_NO_DEVICE;
-    launch_chains(d_in, (int64_t)in_stride, d_in_len, B, d_dist16, (int64_t)stride, (cudaStream_t)stream);
+    if (deflate_ws_bytes(std::max(B, 1), (int64_t)max_len) > ws_bytes) return CCT_E_WORKSPACE;
+    if (B == 0) return CCT_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    DeflateWs ws;
+    deflate_ws_carve(&ws, d_ws, B, (int64_t)max_len);
+    launch_probe_tables(d_in, (int64_t)in_stride, d_in_len, B, (int64_t)max_len, ws, st);
     CK(cudaGetLastError());
+    if (d_ent) CK(cudaMemcpy2DAsync(d_ent, stride * 8, ws.ent, (size_t)ws.stride * 8, max_len * 8, (size_t)B, cudaMemcpyDeviceToDevice, st));
+    if (d_lo) CK(cudaMemcpy2DAsync(d_lo, stride * 4, ws.mtab, (size_t)ws.stride * 4, max_len * 4, (size_t)B, cudaMemcpyDeviceToDevice, st));
+    if (d_hi) CK(cudaMemcpy2DAsync(d_hi, stride * 4, ws.mhi, (size_t)ws.stride * 4, max_len * 4, (size_t)B, cudaMemcpyDeviceToDevice, st));
     return CCT_OK;
 }
 

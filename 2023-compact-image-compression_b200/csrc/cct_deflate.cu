@@ -2,10 +2,11 @@
 //
 // Replaces `zlib.compress(data, level = 9)` (reference src/codec/core.py:340).  Stages (see
 // deflate_core.cuh for the decomposition and SURVEY.md Appendix B for the algorithm being matched):
-//   k_chains       hash-chain links for every position (CTA per stream, warp per hash class, head table in shared memory)
-//   k_run_edges / k_run_link / k_run_recs   equal-byte run lengths around every position; packs the per-position ChainRec
-//   k_probe        cold-start longest_match over the first kProbeK chain entries, one thread per position (persistent,
-//                  work placed by SM)
+//   k_run_edges / k_run_link / k_run_counts   equal-byte run lengths around every position
+//   k_hs_hist / k_hs_scan / k_hs_split / k_hs_bins   the positions of every stream sorted by (3-byte hash, position):
+//                  a hash chain is then a contiguous piece of the sorted array
+//   k_bprobe       cold-start longest_match for every position, one thread per sorted entry scanning the entries
+//                  below it (coalesced), results scattered by position
 //   k_next / k_walk_spec / k_walk_stitch / k_symscan   deflate_slow's lazy state machine as a windowed speculative walk
 //   k_adler        Adler-32 of the payload (CTA per stream)
 //   k_block_build  per 16383-symbol block: histograms, build_tree x3, block-type choice, header bits
@@ -26,7 +27,8 @@ namespace cct {
 #define CCT_WALK_WIN 1024
 #endif
 constexpr int kWalkWin = CCT_WALK_WIN;  // positions per speculative parse window
-constexpr int kProbeK = 64;  // loop steps of the parallel probe (run groups count as one step)
+constexpr int kHsBins = 128;   // bins of the first sort pass: the top 7 bits of the hash
+constexpr int kHsTile = 4096;  // positions per tile of the first sort pass
 
 static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
@@ -41,13 +43,17 @@ size_t deflate_ws_carve(DeflateWs *ws, void *mem, int B, int64_t max_len) {
     auto take = [&](size_t bytes) { void *r = p ? p + used : nullptr; used += (size_t)align_up((int64_t)bytes, 256); return r; };
     ws->stride = align_up(max_len + 16, 16);
     ws->max_blocks = (int)(max_len / kSymEnd + 2);
-    ws->dist16 = (uint16_t *)take((size_t)B * ws->stride * sizeof(uint16_t));
-    ws->recs = (ChainRec *)take((size_t)B * ws->stride * sizeof(ChainRec));
-    ws->mtab = (uint32_t *)take((size_t)B * ws->stride * sizeof(uint32_t));
-    ws->mhi = (uint32_t *)take((size_t)B * ws->stride * sizeof(uint32_t));
+    ws->ent = (SortEnt *)take((size_t)B * ws->stride * sizeof(SortEnt));
+    ws->runs = (uint32_t *)take((size_t)B * ws->stride * sizeof(uint32_t));
+    ws->mtab = (uint32_t *)take((size_t)B * ws->stride * 2 * sizeof(uint32_t));  // both probe tables, one block
+    ws->mhi = ws->mtab ? ws->mtab + (size_t)B * ws->stride : nullptr;
+    ws->p1 = (SortEnt *)ws->mtab;  // pass-1 output of the sort (8 bytes per position): dead before k_bprobe fills the tables
     ws->syms = ws->mtab;  // the dense symbol array reuses the probe table once the walk is over
     ws->rec = (uint32_t *)take((size_t)B * ws->stride * sizeof(uint32_t));
-    ws->probe_next = (uint32_t *)take(kMaxSm * sizeof(uint32_t));
+    ws->counters = (uint32_t *)take(64 * sizeof(uint32_t));
+    ws->max_tiles = (int)((max_len + kHsTile - 1) / kHsTile);
+    ws->thist = (uint32_t *)take((size_t)B * ws->max_tiles * kHsBins * sizeof(uint32_t));
+    ws->binbase = (uint32_t *)take((size_t)B * (kHsBins + 1) * sizeof(uint32_t));
     ws->mask_stride = align_up(ws->stride / 32 + 1, 4);
     ws->mask = (uint32_t *)take((size_t)B * ws->mask_stride * sizeof(uint32_t));
     ws->max_win = (int)(max_len / kWalkWin + 1);
@@ -60,190 +66,15 @@ size_t deflate_ws_carve(DeflateWs *ws, void *mem, int B, int64_t max_len) {
     return used;
 }
 
-// ------------------------------------------------------------------ k_chains / k_runs
-// k_chains: distance from every position to the previous position with the same 3-byte hash (zlib's prev[]),
-// one CTA per stream.  The 32768-entry head table (low 16 bits of the latest position per hash) lives in shared
-// memory, split by hash class between the CTA's warps; entries are kept unambiguous by a sweep every 8192
-// positions that re-parks everything older than 32767 at "49152 behind".  (A global-memory table with every stream resident was
-// measured 3.4x slower: 268 MB of randomly accessed tables do not fit the 126 MB L2.)
-// k_runs: per position, the count of equal bytes before and after it (forward and reverse sweep with a carry),
-// assembled with the link and the first two bytes into the 8-byte ChainRec the chain walks load.
-constexpr int kHeadEntries = 32768;
-#ifndef CCT_CHAIN_WARPS_LOG2
-#define CCT_CHAIN_WARPS_LOG2 2
-#endif
-constexpr int kChainWarpsLog2 = CCT_CHAIN_WARPS_LOG2;
-constexpr int kChainWarps = 1 << kChainWarpsLog2;  // hash classes = warps per stream
-constexpr int kRing = 256;      // pending positions per warp: up to 31 waiting + the 128 a scan step can add
-
-struct ChainSmem {
-    uint32_t ring_s[kChainWarps][kRing];
-    uint16_t ring_h[kChainWarps][kRing];
-};
-
-// One table step for up to 32 pending positions of one hash class (cnt lanes active, positions increasing):
-// previous position with the same hash = the nearest lower lane holding it, else the head table; the latest
-// position of every hash ends up in the table.  Same-hash lanes inside a batch are found without a full match:
-// either every lane has one hash (a run), or all hashes are distinct -- detected by letting every lane store its
-// position and read the slot back -- or a few hashes repeat, and the lanes that lost their slot name them.
-__device__ __forceinline__ void chain_batch(volatile uint16_t *tab, uint16_t *d16, int lane, int cnt, uint32_t s, uint32_t h) {
-    // `tab` is volatile on purpose: the read-back below must see what the OTHER lanes stored to the same slot
-    const bool valid = lane < cnt;
-    const unsigned vmask = cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u);
-    if (!valid) h = 0x8000u | (uint32_t)lane;  // unique key for idle lanes
-    int dist = 0;
-    uint32_t old = 0;
-    if (valid) old = tab[h];
-    const uint32_t h0 = __shfl_sync(0xffffffffu, h, 0);
-    const bool uniform = __ballot_sync(0xffffffffu, valid && h == h0) == vmask;
-    unsigned peers;
-    __syncwarp();
-    if (uniform) {
-        peers = vmask;
-        if (valid && (vmask >> lane) == 1u) tab[h] = (uint16_t)s;
-    } else {
-        if (valid) tab[h] = (uint16_t)s;
-        __syncwarp();
-        const bool lost = valid && tab[h] != (uint16_t)s;
-        unsigned lm = __ballot_sync(0xffffffffu, lost);
-        peers = 1u << lane;  // all distinct: every lane owns its slot
-        if (lm) {
-            // a few hashes occur more than once (a third of the batches, about three hashes each): one ballot per such
-            // hash, found through the lanes that lost the slot (__match_any_sync is a software loop over all 32 lanes here)
-            do {
-                const uint32_t hl = __shfl_sync(0xffffffffu, h, __ffs((int)lm) - 1);
-                const unsigned eq = __ballot_sync(0xffffffffu, h == hl);
-                if (h == hl) peers = eq;
-                lm &= ~eq;
-            } while (lm);
-            __syncwarp();
-            if (valid && (peers >> lane) == 1u) tab[h] = (uint16_t)s;  // the latest position wins
-        }
-    }
-    const unsigned lower = peers & ((1u << lane) - 1u);
-    const uint32_t s_low = __shfl_sync(0xffffffffu, s, lower ? 31 - __clz((int)lower) : 0);
-    if (valid) {
-        uint32_t d = lower ? s - s_low : ((s - old) & 0xFFFFu);
-        if (lower ? d >= 32768u : (d < 1u || d >= 32768u)) d = 0;
-        dist = (int)d;
-        d16[s] = (uint16_t)dist;
-    }
-    __syncwarp();
-}
-
-__global__ void __launch_bounds__(32 * kChainWarps) k_chains(const uint8_t *__restrict__ in, int64_t in_stride,
-                                                             const int32_t *__restrict__ in_len, uint16_t *__restrict__ dist16,
-                                                             int64_t stride) {
-    // One CTA per stream; warp k owns the hashes with (h & 3) == k and a quarter of the head table.  Every warp
-    // scans the whole payload, 128 positions per step with four consecutive positions per lane (the lane's word and
-    // the next lane's: a funnel shift gives the three bytes of each position), keeps the positions of its own class
-    // in a ring, and runs the table step on 32 of them at a time.  Classes never interact, so the four warps need
-    // no synchronisation -- four times the warps per SM of a single-warp scan with the same 64 KB of tables.
-    // (Sharing the scan instead -- each warp hashes a quarter of every 128 positions and files them into all four
-    // rings, two barriers per step for the offsets -- has 40 % fewer instructions and measured 26 % slower: the table
-    // steps are latency-bound and the barriers make every warp wait for the slowest one's.)
-    extern __shared__ __align__(16) unsigned char chain_raw[];
-    uint16_t *head = reinterpret_cast<uint16_t *>(chain_raw);
-    ChainSmem &sm = *reinterpret_cast<ChainSmem *>(chain_raw + kHeadEntries * sizeof(uint16_t));
-    const int stream = blockIdx.x, lane = threadIdx.x & 31, k = threadIdx.x >> 5;
-    const int n = in_len[stream];
-    const uint8_t *w = in + (int64_t)stream * in_stride;
-    uint16_t *d16 = dist16 + (int64_t)stream * stride;
-    uint16_t *tab = head + k * (kHeadEntries / kChainWarps);
-    uint32_t *tab32 = reinterpret_cast<uint32_t *>(tab);
-    constexpr int kTabWords = kHeadEntries / kChainWarps / 2;
-    for (int i = lane; i < kTabWords; i += 32) tab32[i] = 0x40004000u;  // (0 - 49152) & 0xFFFF
-    uint32_t *ring_s = sm.ring_s[k];
-    uint16_t *ring_h = sm.ring_h[k];
-    __syncwarp();
-    // positions that are in no chain (position 0 doubles as NIL in zlib; the last two have no hash triple)
-    if (k == 0 && lane < 3) { const int s = lane == 0 ? 0 : n - 3 + lane; if (s >= 0 && s < n) d16[s] = 0; }
-    const uint32_t *w32 = reinterpret_cast<const uint32_t *>(w);  // stream base is 16-byte aligned
-    const int n_words = (n + 3) >> 2;
-    auto fetch = [&](int cbase) -> uint32_t {  // the lane's word of the 128-byte chunk starting at cbase
-        const int wi = (cbase >> 2) + lane;
-        return wi < n_words ? __ldg(w32 + wi) : 0u;
-    };
-    auto flush = [&](int &rd, int wr, int at_least) {  // table steps while `at_least` positions are pending
-        while (wr - rd >= at_least && wr != rd) {
-            const int cnt = min(32, wr - rd);
-            chain_batch(tab, d16, lane, cnt, ring_s[(rd + lane) & (kRing - 1)], ring_h[(rd + lane) & (kRing - 1)]);
-            rd += cnt;
-        }
-    };
-    uint32_t cur = fetch(0), nxt = fetch(128);  // chunks are fetched two ahead
-    int wr = 0, rd = 0;  // ring write / read cursors (warp-uniform)
-    const unsigned below = (1u << lane) - 1u;
-    for (int cbase = 0; cbase < n; cbase += 128) {
-        const uint32_t a = cur, nn = nxt;
-        cur = nn;
-        nxt = fetch(cbase + 256);
-        if (cbase && (cbase & 8191) == 0) {
-            // sweep: flush what is pending (so the table reflects every position below cbase), then re-park the
-            // entries older than 32767 at "49152 behind" to keep the 16-bit positions unambiguous
-            flush(rd, wr, 1);
-            const uint32_t far = (uint32_t)(cbase - 49152) & 0xFFFFu;
-            for (int i = lane; i < kTabWords; i += 32) {
-                uint32_t v = tab32[i];
-                uint32_t lo = v & 0xFFFFu, hi = v >> 16;
-                if (((uint32_t)(cbase - lo) & 0xFFFFu) >= 32768u) lo = far;
-                if (((uint32_t)(cbase - hi) & 0xFFFFu) >= 32768u) hi = far;
-                tab32[i] = lo | (hi << 16);
-            }
-            __syncwarp();
-        }
-        // bytes 4..7 after the lane's word: the next lane's word, or the next chunk's first
-        const uint32_t up = __shfl_down_sync(0xffffffffu, a, 1), wrap = __shfl_sync(0xffffffffu, nn, 0);
-        const uint32_t b = lane == 31 ? wrap : up;
-        const int s0 = cbase + 4 * lane;
-        // positions with a hash triple that may enter a chain: all four, except in the first and the last chunks
-        unsigned ok = 0xFu;
-        if (cbase == 0 || cbase + 130 >= n) {  // (warp-uniform)
-            ok = 0;
-#pragma unroll
-            for (int j = 0; j < 4; j++) if (s0 + j >= 1 && s0 + j + 2 < n) ok |= 1u << j;
-        }
-        uint32_t hh[4];
-        unsigned mine = 0;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const uint32_t t = __funnelshift_r(a, b, 8 * j);  // bytes of position s0 + j, low byte first
-            hh[j] = (((t & 0xFFu) << 10) ^ ((t >> 3) & 0x1FE0u) ^ ((t >> 16) & 0xFFu)) & 0x7FFFu;  // hash3
-            if ((hh[j] & (kChainWarps - 1)) == (uint32_t)k) mine |= 1u << j;
-        }
-        mine &= ok;
-        // ring slots in position order: the lanes below first, then this lane's own earlier positions
-        int before = 0, total = 0;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const unsigned bal = __ballot_sync(0xffffffffu, (mine >> j) & 1u);
-            before += __popc(bal & below);
-            total += __popc(bal);
-        }
-        int slot = wr + before;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            if ((mine >> j) & 1u) {
-                ring_s[slot & (kRing - 1)] = (uint32_t)(s0 + j);
-                ring_h[slot & (kRing - 1)] = (uint16_t)(hh[j] >> kChainWarpsLog2);
-                slot++;
-            }
-        }
-        wr += total;
-        __syncwarp();
-        flush(rd, wr, 32);
-    }
-    flush(rd, wr, 1);
-}
-
+// ------------------------------------------------------------------ k_run_*
 // Run lengths around every position: rb[p] / rl[p] = number of bytes equal to w[p] immediately before / after p,
-// packed with the chain link and the first bytes into the ChainRec the walks load.  One warp owns a chunk of
+// packed into runs[p] = rl | rb << 16 (each capped at 65535) for the group step of the scan.  One warp owns a chunk of
 // kRunChunk positions, 32 per step, one position per lane: "where did the current run start" is a ballot and a
 // count-leading-zeros, the value entering the next step one shuffle -- no shared memory, coalesced loads and stores.
 // Chunks are independent once the count entering each is known, so the work is three launches:
 //   k_run_edges  per chunk: (does one run cover the whole chunk?, count leaving it if nothing came in), both ways
 //   k_run_link   per stream: warp scan of those summaries -> the count entering every chunk from either side
-//   k_run_recs   per chunk: counts of every position, records written out
+//   k_run_counts per chunk: counts of every position, written out
 // The summaries combine as (whole, val) o (whole', val') = whole' ? (whole, val + val') : (false, val').
 constexpr int kRunChunk = 256;
 constexpr int kRunSteps = kRunChunk / 32;
@@ -333,22 +164,16 @@ __global__ void __launch_bounds__(32 * kRunWarps) k_run_link(const int32_t *__re
     }
 }
 
-__global__ void __launch_bounds__(32 * kRunWarps) k_run_recs(const uint8_t *__restrict__ in, int64_t in_stride,
-                                                            const int32_t *__restrict__ in_len, const uint16_t *__restrict__ dist16,
-                                                            const int2 *__restrict__ enters, int max_chunks,
-                                                            ChainRec *__restrict__ recs_all, int64_t stride) {
+__global__ void __launch_bounds__(32 * kRunWarps) k_run_counts(const uint8_t *__restrict__ in, int64_t in_stride,
+                                                              const int32_t *__restrict__ in_len, const int2 *__restrict__ enters,
+                                                              int max_chunks, uint32_t *__restrict__ runs_all, int64_t stride) {
     const int stream = blockIdx.y, chunk = blockIdx.x * kRunWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     const int base = chunk * kRunChunk, n = in_len[stream];
     if (base >= n) return;
-    const uint16_t *d16 = dist16 + (int64_t)stream * stride;
-    ChainRec *recs = recs_all + (int64_t)stream * stride;
-    const uint8_t *w = in + (int64_t)stream * in_stride;
+    uint32_t *runs = runs_all + (int64_t)stream * stride;
     RunBytes r;
-    run_bytes(r, w, n, base, lane);
+    run_bytes(r, in + (int64_t)stream * in_stride, n, base, lane);
     const int2 enter = enters[(int64_t)stream * max_chunks + chunk];
-    uint32_t link[kRunSteps];  // chain links of the chunk, fetched up front with the bytes (all loads in flight at once)
-#pragma unroll
-    for (int j = 0; j < kRunSteps; j++) { const int p = base + 32 * j + lane; link[j] = p < n ? __ldg(d16 + p) : 0u; }
     uint32_t rb[kRunSteps];
     int carry = enter.x;  // count of the position just before the group
 #pragma unroll
@@ -366,88 +191,317 @@ __global__ void __launch_bounds__(32 * kRunWarps) k_run_recs(const uint8_t *__re
         const unsigned zeros_above = ~m & ~((1u << lane) - 1u);  // positions >= lane whose flag is 0
         const int fwd = zeros_above ? (__ffs((int)zeros_above) - 1) - lane : (32 - lane) + carry;
         carry = __shfl_sync(kAll, fwd, 0);
-        // w[p + 1 .. p + 3]: the next lanes' bytes, or the first lanes of the next group
-        const uint32_t next_group = j + 1 < kRunSteps ? r.c[j + 1] : r.after;
-        uint32_t quad = r.c[j];
-#pragma unroll
-        for (int i = 1; i <= 3; i++) {
-            const uint32_t a = __shfl_sync(kAll, r.c[j], (lane + i) & 31), nx = __shfl_sync(kAll, next_group, (lane + i) & 31);
-            quad |= (lane + i < 32 ? a : nx) << (8 * i);
-        }
         const int p = base + 32 * j + lane;
-        if (p < n) {
-            const int rl = min(fwd, 65535);
-            ChainRec rec = pack_rec_plain((int)link[j], rl, quad);
-            if (rl >= 2) {
-                // a run position: the link of the bottom of its run group and the byte after the run (one address per
-                // run, so the lanes of a run share the loads)
-                const int bottom = max(p - (int)rb[j], 1), q = p + rl + 1;
-                rec = pack_rec_run((int)__ldg(d16 + bottom), rl, (int)rb[j], r.c[j], (rl < 65535 && q < n) ? (uint32_t)__ldg(w + q) : 0u);
+        if (p < n) runs[p] = (uint32_t)min(fwd, 65535) | (rb[j] << 16);
+    }
+}
+
+// ------------------------------------------------------------------ k_hs_*: positions sorted by (hash, position)
+// The chain members of a stream (positions 1 .. n-3) are sorted by their 15-bit hash, stably, so that every hash
+// bucket lists its positions in increasing order -- zlib's chain, read backwards (deflate_core.cuh, "longest_match
+// over hash-sorted positions").  Two radix passes, most significant digit first:
+//   pass 1  by the top 7 bits (128 bins), the usual three launches over tiles of kHsTile positions:
+//           k_hs_hist   per tile: how many positions fall into each bin
+//           k_hs_scan   per stream: bin starts, and for every tile the offset of its share of each bin
+//           k_hs_split  per tile: (position, first four bytes) written to p1[] at bin start + offset + rank inside the tile
+//   pass 2  by the low 8 bits, one warp per (stream, bin): digit histogram, scan, ranked scatter of the finished
+//           8-byte entries (position, flags, first four bytes) into ent[] -- a bin is a contiguous piece of p1[] and of
+//           ent[], and is small enough (n / 128 positions on average) that its second read comes from L1/L2.  The
+//           payload itself is read once, coalesced, by pass 1.
+// Ranks inside a group of 32 keys: the lanes holding the same digit (key_peers), and of those the ones below.
+constexpr int kHsThreads = 256;
+constexpr int kHsWarps = kHsThreads / 32;
+constexpr int kHsRows = kHsTile / kHsThreads;  // 32-position rows per warp
+
+// Lanes of the warp holding the same key (BITS significant bits; idle lanes pass valid = false and match nobody).
+// One ballot per bit: MATCH.ANY costs about two cycles per DISTINCT key among the lanes (measured 62 cycles per warp for
+// random 8-bit keys, profiles/r02_match_bench.txt), which is the usual case here; a row inside a run -- all keys
+// equal -- is settled by one vote.
+template <int BITS>
+__device__ __forceinline__ unsigned key_peers(uint32_t key, bool valid) {
+    const uint32_t k0 = __shfl_sync(kAll, key, 0);
+    if (__all_sync(kAll, valid && key == k0)) return kAll;
+    unsigned peers = __ballot_sync(kAll, valid);
+#pragma unroll
+    for (int b = 0; b < BITS; b++) {
+        const bool bit = (key >> b) & 1u;
+        const unsigned bal = __ballot_sync(kAll, bit);
+        peers &= bit ? bal : ~bal;
+    }
+    return valid ? peers : 0u;
+}
+
+// Tile bytes [base, base + kHsTile + 3) -> shared memory (zero past the end), then the hash digit of each position.
+struct HsTileSmem { uint32_t words[kHsTile / 4 + 4]; };
+__device__ __forceinline__ void hs_stage(HsTileSmem &sm, const uint8_t *__restrict__ w, int n, int base) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(w + base);  // base is a multiple of 16, the row 16-byte aligned
+    uint4 *dst = reinterpret_cast<uint4 *>(sm.words);
+    for (int i = threadIdx.x; i < kHsTile / 16 + 1; i += kHsThreads) {
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (base + 16 * i < n) v = __ldg(src + i);  // (the 16 bytes may reach past n: those never enter a valid hash)
+        dst[i] = v;
+    }
+}
+__device__ __forceinline__ uint32_t hs_hash_at(const HsTileSmem &sm, int off) {  // hash3 of the bytes at tile offset off
+    const uint32_t a = sm.words[off >> 2], b = sm.words[(off >> 2) + 1];
+    return hash_quad(__funnelshift_r(a, b, (off & 3) * 8));
+}
+
+__global__ void __launch_bounds__(kHsThreads) k_hs_hist(const uint8_t *__restrict__ in, int64_t in_stride,
+                                                        const int32_t *__restrict__ in_len, uint32_t *__restrict__ thist,
+                                                        int max_tiles) {
+    __shared__ HsTileSmem sm;
+    __shared__ uint32_t hist[kHsBins];
+    const int stream = blockIdx.y, tile = blockIdx.x, n = in_len[stream], base = tile * kHsTile;
+    if (base >= n) return;
+    if (threadIdx.x < kHsBins) hist[threadIdx.x] = 0;
+    hs_stage(sm, in + (int64_t)stream * in_stride, n, base);
+    __syncthreads();
+#pragma unroll 4
+    for (int r = 0; r < kHsRows; r++) {
+        const int off = r * kHsThreads + threadIdx.x, p = base + off;
+        const bool valid = p >= 1 && p + 2 < n;
+        const uint32_t d = hs_hash_at(sm, off) >> 8;
+        const uint32_t d0 = __shfl_sync(kAll, d, 0);
+        if (__all_sync(kAll, valid && d == d0)) {  // a run: one add for the warp
+            if ((threadIdx.x & 31) == 0) atomicAdd(&hist[d0], 32u);
+        } else if (valid) atomicAdd(&hist[d], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < kHsBins) thist[((int64_t)stream * max_tiles + tile) * kHsBins + threadIdx.x] = hist[threadIdx.x];
+}
+
+// counts -> absolute offsets inside the stream: thist[tile][bin] = start of the tile's share of the bin;
+// binbase[stream][bin] = start of the bin (binbase[stream][128] = number of chain members)
+__global__ void __launch_bounds__(kHsBins) k_hs_scan(const int32_t *__restrict__ in_len, uint32_t *__restrict__ thist, int max_tiles,
+                                                     uint32_t *__restrict__ binbase) {
+    __shared__ uint32_t tot[kHsBins];
+    const int stream = blockIdx.x, d = threadIdx.x, n = in_len[stream];
+    const int nt = (n + kHsTile - 1) / kHsTile;
+    uint32_t *h = thist + (int64_t)stream * max_tiles * kHsBins + d;
+    uint32_t run = 0;
+    for (int t = 0; t < nt; t++) { const uint32_t c = h[(int64_t)t * kHsBins]; h[(int64_t)t * kHsBins] = run; run += c; }
+    tot[d] = run;
+    __syncthreads();
+    uint32_t start = 0;  // exclusive scan over the bins (128 values: a serial sum per thread is as fast as anything)
+    for (int k = 0; k < d; k++) start += tot[k];
+    for (int t = 0; t < nt; t++) h[(int64_t)t * kHsBins] += start;
+    binbase[(int64_t)stream * (kHsBins + 1) + d] = start;
+    if (d == kHsBins - 1) binbase[(int64_t)stream * (kHsBins + 1) + kHsBins] = start + run;
+}
+
+__global__ void __launch_bounds__(kHsThreads) k_hs_split(const uint8_t *__restrict__ in, int64_t in_stride,
+                                                         const int32_t *__restrict__ in_len, const uint32_t *__restrict__ thist,
+                                                         int max_tiles, SortEnt *__restrict__ p1_all, int64_t stride) {
+    __shared__ HsTileSmem sm;
+    __shared__ uint32_t wc[kHsWarps][kHsBins];  // per warp: count of each bin, then the offset of the warp's share
+    const int stream = blockIdx.y, tile = blockIdx.x, n = in_len[stream], base = tile * kHsTile;
+    if (base >= n) return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < kHsWarps * kHsBins; i += kHsThreads) (&wc[0][0])[i] = 0;
+    hs_stage(sm, in + (int64_t)stream * in_stride, n, base);
+    __syncthreads();
+    // warp `wid` owns the 32 * kHsRows consecutive positions from base + wid * 32 * kHsRows: (warp, row, lane) is
+    // position order, so ranks taken in that order keep the sort stable
+    uint32_t key[kHsRows];  // bin | rank inside the warp's share << 8   (0xFFFFFFFF: not a chain member)
+    const unsigned below = (1u << lane) - 1u;
+#pragma unroll
+    for (int r = 0; r < kHsRows; r++) {
+        const int off = (wid * kHsRows + r) * 32 + lane, p = base + off;
+        const bool valid = p >= 1 && p + 2 < n;
+        const uint32_t d = hs_hash_at(sm, off) >> 8;
+        const unsigned peers = key_peers<7>(d, valid);
+        uint32_t old = 0;
+        if (valid) old = wc[wid][d];
+        __syncwarp();
+        if (valid && (peers >> lane) == 1u) wc[wid][d] = old + (uint32_t)__popc(peers);  // the highest peer books the group
+        __syncwarp();
+        key[r] = valid ? (d | ((old + (uint32_t)__popc(peers & below)) << 8)) : 0xFFFFFFFFu;
+    }
+    __syncthreads();
+    if (threadIdx.x < kHsBins) {
+        uint32_t run = thist[((int64_t)stream * max_tiles + tile) * kHsBins + threadIdx.x];
+        for (int k = 0; k < kHsWarps; k++) { const uint32_t c = wc[k][threadIdx.x]; wc[k][threadIdx.x] = run; run += c; }
+    }
+    __syncthreads();
+    SortEnt *p1 = p1_all + (int64_t)stream * stride;
+#pragma unroll
+    for (int r = 0; r < kHsRows; r++) {
+        if (key[r] == 0xFFFFFFFFu) continue;
+        const int off = (wid * kHsRows + r) * 32 + lane, p = base + off;
+        uint32_t q = __funnelshift_r(sm.words[off >> 2], sm.words[(off >> 2) + 1], (off & 3) * 8);
+        if (p + 3 >= n) q &= 0x00FFFFFFu;  // (the staged bytes may reach past the end of the payload)
+        *reinterpret_cast<uint2 *>(p1 + wc[wid][key[r] & 0xFFu] + (key[r] >> 8)) = make_uint2((uint32_t)p, q);
+    }
+}
+
+// pass 2: one CTA per (stream, bin), bins handed out through a counter (they differ in size by orders of magnitude:
+// the bin of the zero run holds a quarter of a CT payload).  A bin is worked off in chunks of kBinChunk entries held in
+// registers, warp w owning rows 8w .. 8w+7 of the chunk so that (chunk, warp, row, lane) is position order:
+//   digit totals   a bin of one chunk (the usual case) gets them from the ranking itself; a longer one from a first
+//                  sweep over its entries (shared-memory histogram)
+//   per chunk      rank inside the warp (key_peers + per-warp counters), offsets of the warps' shares, scatter of the
+//                  finished entries -- the bin's piece of ent[] is a few KB, so the 8-byte stores meet in L2.
+constexpr int kBinThreads = 256;
+constexpr int kBinWarps = kBinThreads / 32;
+constexpr int kBinRows = 8;                                  // rows (of 32 entries) per warp and chunk
+constexpr int kBinChunk = kBinThreads * kBinRows;            // 2048 entries
+struct BinSmem {
+    uint32_t wc[kBinWarps][256];  // per warp: count of each digit in the chunk, then the offset of the warp's share
+    uint32_t run[256];            // next free slot of each digit
+    uint32_t first[256];          // first slot of each digit (its lowest position gets kEntFirst)
+    uint32_t warp_sum[kBinWarps];
+    int unit;
+};
+
+__device__ __forceinline__ void bin_rank_chunk(BinSmem &sm, const uint2 *__restrict__ src, int S, int c0, uint2 (&pq)[kBinRows],
+                                               uint32_t (&key)[kBinRows]) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned below = (1u << lane) - 1u;
+#pragma unroll
+    for (int r = 0; r < kBinRows; r++) {
+        const int k = c0 + (wid * kBinRows + r) * 32 + lane;
+        pq[r] = k < S ? __ldg(src + k) : make_uint2(0xFFFFFFFFu, 0u);
+    }
+#pragma unroll
+    for (int r = 0; r < kBinRows; r++) {
+        const bool valid = pq[r].x != 0xFFFFFFFFu;
+        const uint32_t d = hash_quad(pq[r].y) & 0xFFu;
+        const unsigned peers = key_peers<8>(d, valid);
+        uint32_t old = 0;
+        if (valid) old = sm.wc[wid][d];
+        __syncwarp();
+        if (valid && (peers >> lane) == 1u) sm.wc[wid][d] = old + (uint32_t)__popc(peers);  // the highest peer books the group
+        __syncwarp();
+        key[r] = valid ? (d | ((old + (uint32_t)__popc(peers & below)) << 8)) : 0xFFFFFFFFu;
+    }
+}
+
+__global__ void __launch_bounds__(kBinThreads) k_hs_bins(const uint32_t *__restrict__ binbase, const SortEnt *__restrict__ p1_all,
+                                                         SortEnt *__restrict__ ent_all, int64_t stride, int total_bins,
+                                                         uint32_t *__restrict__ next_unit) {
+    __shared__ BinSmem sm;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (;;) {
+        __syncthreads();  // (the previous bin is done with sm)
+        if (tid == 0) sm.unit = (int)atomicAdd(next_unit, 1u);
+        for (int i = tid; i < kBinWarps * 256; i += kBinThreads) (&sm.wc[0][0])[i] = 0;
+        sm.run[tid] = 0;
+        __syncthreads();
+        const int unit = sm.unit;
+        if (unit >= total_bins) return;
+        const int stream = unit / kHsBins, bin = unit - stream * kHsBins;
+        const uint32_t lo = binbase[(int64_t)stream * (kHsBins + 1) + bin], hi = binbase[(int64_t)stream * (kHsBins + 1) + bin + 1];
+        const int S = (int)(hi - lo);
+        if (S == 0) continue;
+        const uint2 *src = reinterpret_cast<const uint2 *>(p1_all + (int64_t)stream * stride + lo);
+        SortEnt *ent = ent_all + (int64_t)stream * stride + lo;
+        const bool single = S <= kBinChunk;
+        uint2 pq[kBinRows];
+        uint32_t key[kBinRows];
+        // digit totals -> sm.run[d]
+        if (single) {
+            bin_rank_chunk(sm, src, S, 0, pq, key);
+            __syncthreads();
+            uint32_t t = 0;
+#pragma unroll
+            for (int w = 0; w < kBinWarps; w++) t += sm.wc[w][tid];
+            sm.run[tid] = t;
+        } else {
+            for (int k0 = 0; k0 < S; k0 += kBinThreads * 4) {
+                uint32_t q[4];
+#pragma unroll
+                for (int r = 0; r < 4; r++) { const int k = k0 + r * kBinThreads + tid; q[r] = k < S ? __ldg(src + k).y : 0u; }
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    const bool valid = k0 + r * kBinThreads + tid < S;
+                    const uint32_t d = hash_quad(q[r]) & 0xFFu;
+                    const uint32_t d0 = __shfl_sync(kAll, d, 0);
+                    if (__all_sync(kAll, valid && d == d0)) { if (lane == 0) atomicAdd(&sm.run[d0], 32u); }  // a run: one add for the warp
+                    else if (valid) atomicAdd(&sm.run[d], 1u);
+                }
             }
-            store_rec(recs + p, rec);
+        }
+        __syncthreads();
+        {   // exclusive scan of the 256 totals (one per thread)
+            const uint32_t t = sm.run[tid];
+            uint32_t incl = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(kAll, incl, o); if (lane >= o) incl += u; }
+            if (lane == 31) sm.warp_sum[wid] = incl;
+            __syncthreads();
+            uint32_t off = 0;
+#pragma unroll
+            for (int w = 0; w < kBinWarps; w++) if (w < wid) off += sm.warp_sum[w];
+            const uint32_t start = off + incl - t;
+            sm.run[tid] = start;
+            sm.first[tid] = start;
+        }
+        for (int c0 = 0; c0 < S; c0 += kBinChunk) {
+            if (!single) {
+                __syncthreads();  // (the previous chunk's scatter has read wc)
+                for (int i = tid; i < kBinWarps * 256; i += kBinThreads) (&sm.wc[0][0])[i] = 0;
+                __syncthreads();
+                bin_rank_chunk(sm, src, S, c0, pq, key);
+            }
+            __syncthreads();
+            {   // the warps' shares of digit `tid` follow one another from the digit's next free slot
+                uint32_t run = sm.run[tid];
+#pragma unroll
+                for (int w = 0; w < kBinWarps; w++) { const uint32_t c = sm.wc[w][tid]; sm.wc[w][tid] = run; run += c; }
+                sm.run[tid] = run;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < kBinRows; r++) {
+                if (key[r] == 0xFFFFFFFFu) continue;
+                const uint32_t d = key[r] & 0xFFu, idx = sm.wc[wid][d] + (key[r] >> 8), q = pq[r].y;
+                uint32_t a = pq[r].x;
+                if (quad_is_run(q)) a |= kEntRun;
+                if (idx == sm.first[d]) a |= kEntFirst;
+                *reinterpret_cast<uint2 *>(ent + idx) = make_uint2(a, q);
+            }
         }
     }
 }
 
-// ------------------------------------------------------------------ k_probe
-// Cold-start longest_match for every position (match_probe in deflate_core.cuh), one thread per position, 32
-// registers so that 64 warps per SM hide the dependent chain loads.  Chain lengths vary wildly (over half the
-// positions have no chain, some need the full kProbeK steps) and only ~11 of 32 lanes are active on average; two
-// work-queue variants that refill finished lanes from a shared counter (per lane, and in rounds of >= 8 idle
-// lanes) were measured 12 % slower -- the extra state and the refill branch cost more than the idle lanes.  Running
-// the walk in phases with growing step caps (2/4/10/48) and compacting the open walks in between halves the warp
-// steps on paper, yet measured 9 % slower with the phases inside one CTA (shared-memory queues, barriers) and 20 %
-// slower as separate kernels over per-stream queues: the late phases are chains of dependent L2 loads with nothing
-// else to issue, while here the short walks of other warps fill those gaps.
-constexpr int kProbeThreads = 128;
-constexpr int kProbeUnit = 128;  // consecutive positions a warp takes at a time
-__device__ __forceinline__ uint32_t sm_id() { uint32_t r; asm("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
-
-// The walks of neighbouring positions read the same 256 KB of records (the 32 K positions before them), far too much
-// to share when the warps of an SM sit on tiles scattered over the batch (L1 hit rate 36 %, and the kernel is bound
-// by the latency of those loads: six CTAs per SM instead of eight cost 20 %).  So the kernel is persistent and
-// places work by SM: the units (kProbeUnit positions) of the whole batch are cut into one contiguous range per SM,
-// and a warp takes the next unit of the range of the SM it runs on -- the 64 warps of an SM walk 8 K consecutive
-// positions of one stream and share their window in L1.  A warp whose range is used up moves on to the next SM's.
-// (Halving the window with a 4-byte "hot" word per position -- link, run flag and the 11 bits of the first two bytes
-// the hash does not determine, the full record opened only on a key match or a run group -- measured 20 % SLOWER:
-// run groups and true matches then cost two dependent loads, and lanes on the two record formats diverge.  On top of
-// this placement, giving every position 2-10 steps first and finishing the open walks 32 at a time from a per-warp
-// shared-memory queue -- 27 % fewer warp steps on paper -- changed nothing: 30.7 ms against 30.2.)
-__global__ void __launch_bounds__(kProbeThreads, 16) k_probe(const uint8_t *__restrict__ in, uint32_t in_stride,
-                                                             const int32_t *__restrict__ in_len, const ChainRec *__restrict__ recs,
-                                                             uint32_t *__restrict__ mlo, uint32_t *__restrict__ mhi, uint32_t stride,
-                                                             uint32_t units_per_stream, uint32_t total_units,
-                                                             uint32_t *__restrict__ sm_next, uint32_t n_sm) {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t per = (total_units + n_sm - 1) / n_sm;
-    const uint32_t home = sm_id() % n_sm;
-    for (uint32_t hop = 0; hop < n_sm; hop++) {
-        const uint32_t sm = home + hop < n_sm ? home + hop : home + hop - n_sm;
-        const uint32_t lo_u = sm * per, hi_u = min(total_units, lo_u + per);
-        for (;;) {
-            uint32_t u = 0;
-            if (lane == 0) u = lo_u + atomicAdd(sm_next + sm, 1u);
-            u = __shfl_sync(0xffffffffu, u, 0);
-            if (u >= hi_u) break;
-            const uint32_t stream = u / units_per_stream, first = (u - stream * units_per_stream) * kProbeUnit;
-            const int n = in_len[stream];
-            if ((int)first >= n) continue;
-            // strides are 32-bit so that re-deriving a per-stream pointer is one wide multiply-add
-            const uint64_t o = (uint64_t)stream * stride;
-            const uint8_t *w_s = in + (uint64_t)stream * in_stride;
-            const ChainRec *recs_s = recs + o;
-            // opaque to the compiler: at 32 registers it would otherwise re-derive both bases from the kernel
-            // parameters (nine instructions) at every use inside the walk instead of keeping them
-            asm volatile("" : "+l"(w_s), "+l"(recs_s));
-            LzView v{w_s, recs_s, n};
-#pragma unroll 1
-            for (int s = (int)(first + lane); s < (int)first + kProbeUnit && s < n; s += 32) {
-                uint32_t lo, hi;
-                match_probe(v, s, kProbeK, &lo, &hi);
-                mlo[o + s] = lo;
-                mhi[o + s] = hi;
-            }
+// ------------------------------------------------------------------ k_bprobe
+// longest_match from a cold start for every chain member, one thread per entry of the sorted array (bucket_probe in
+// deflate_core.cuh): the lanes of a warp hold neighbouring targets of one bucket and step down the entries below them
+// together, so the candidate loads are coalesced 8-byte reads of one contiguous piece of ent[].  Results are scattered
+// by position: mlo[p] = the entry for chain budget 4096, with kProbeHiDiff set where the budget-1024 entry differs (then
+// it is written to mhi[p]; otherwise mhi[p] is left alone).
+constexpr int kBprobeThreads = 256;
+__global__ void __launch_bounds__(kBprobeThreads) k_bprobe(const uint8_t *__restrict__ in, int64_t in_stride,
+                                                           const int32_t *__restrict__ in_len, const SortEnt *__restrict__ ent_all,
+                                                           const uint32_t *__restrict__ runs_all, uint32_t *__restrict__ mlo_all,
+                                                           uint32_t *__restrict__ mhi_all, int64_t stride) {
+    const int stream = blockIdx.y, n = in_len[stream];
+    const int members = n >= 4 ? n - 3 : 0;
+    const int64_t o = (int64_t)stream * stride;
+    uint32_t *mlo = mlo_all + o, *mhi = mhi_all + o;
+    if (blockIdx.x == 0 && threadIdx.x < 3) {  // positions that are in no chain: 0 and the last two
+        const int p = threadIdx.x == 0 ? 0 : n - 3 + (int)threadIdx.x;
+        if (p >= 0 && p < n && (threadIdx.x == 0 || p >= 1)) mlo[p] = 0;
+    }
+    BucketView v{in + (int64_t)stream * in_stride, ent_all + o, runs_all + o, n};
+    // (the walks are warp-wide: all 32 lanes go round together, lanes past the end idle)
+    const int lane = threadIdx.x & 31;
+    for (int i0 = blockIdx.x * kBprobeThreads + (threadIdx.x & ~31); i0 < members; i0 += gridDim.x * kBprobeThreads) {
+        const int i = i0 + lane;
+        const bool valid = i < members;
+        uint32_t lo, hi;
+        const bool settled = bucket_probe_quick(v, i, valid, &lo);
+        hi = lo;
+        if (__any_sync(0xffffffffu, !settled)) {
+            uint32_t glo, ghi;
+            bucket_probe(v, i, !settled, &glo, &ghi);
+            if (!settled) { lo = glo; hi = ghi; }
+        }
+        if (valid) {
+            const int p = ent_pos(load_ent(v.ent + i));
+            if (lo != hi) { mhi[p] = hi; lo |= kProbeHiDiff; }
+            mlo[p] = lo;
         }
     }
 }
@@ -455,7 +509,7 @@ __global__ void __launch_bounds__(kProbeThreads, 16) k_probe(const uint8_t *__re
 // ------------------------------------------------------------------ parse: k_next / k_walk_spec / k_walk_stitch / k_symscan
 // deflate_slow's lazy state machine, re-indexed by symbol start (deflate_core.cuh):
 //   k_next         one thread per position: the symbol a walk standing there emits, from the probe table alone
-//                  (coalesced; kSymSlow where the step needs match_full or depends on the walk's history)
+//                  (coalesced; kSymSlow where the step depends on the walk's history)
 //   k_walk_spec    one thread per kWalkWin-position window walks it speculatively from a cold start: one 4-byte
 //                  entry per symbol, symbol starts collected in a bit mask (32 positions per word)
 //   k_walk_stitch  one thread per stream joins the windows: it re-walks only until the true path meets the
@@ -473,7 +527,10 @@ __global__ void __launch_bounds__(256) k_next(const uint8_t *__restrict__ in, in
     const uint32_t *lo = mlo + o, *hi = mhi + o;
     for (int p0 = (blockIdx.x * 256 + threadIdx.x) * 4; p0 < n; p0 += gridDim.x * 1024) {
         const uint4 e4 = *reinterpret_cast<const uint4 *>(lo + p0);
-        const uint32_t e[5] = {e4.x, e4.y, e4.z, e4.w, p0 + 4 < n ? lo[p0 + 4] : 0u};
+        const uint32_t f[5] = {e4.x, e4.y, e4.z, e4.w, p0 + 4 < n ? lo[p0 + 4] : 0u};  // entries with the kProbeHiDiff flag
+        uint32_t e[5];
+#pragma unroll
+        for (int i = 0; i < 5; i++) e[i] = f[i] & ~kProbeHiDiff;
         const uint32_t w4 = *reinterpret_cast<const uint32_t *>(w + p0);  // payload rows are padded to 16 bytes
         uint32_t out[4];
 #pragma unroll
@@ -484,15 +541,13 @@ __global__ void __launch_bounds__(256) k_next(const uint8_t *__restrict__ in, in
             if (look >= kMinMatch) {
                 const uint32_t e0 = e[i];
                 const int l0 = mtab_len(e0), d0 = mtab_dist(e0);
-                if (e0 & kProbeIncomplete) r = kSymSlow;
-                else if (e0 != 0 && !(l0 == kMinMatch && d0 > kTooFar)) {
+                if (e0 != 0 && !(l0 == kMinMatch && d0 > kTooFar)) {
                     r = sym_pack(l0 - kMinMatch, d0);
                     const int look1 = look - 1;
                     if (look1 >= kMinMatch) {
-                        const uint32_t e1 = l0 >= kGoodLen ? hi[p + 1] : e[i + 1];
+                        const uint32_t e1 = (l0 >= kGoodLen && (f[i + 1] & kProbeHiDiff)) ? hi[p + 1] : e[i + 1];
                         if (!(e1 == 0 || l0 >= kMaxMatch || l0 >= look1)) {
-                            if (e1 & kProbeIncomplete) r = kSymSlow;
-                            else if (mtab_len(e1) > l0) r = (l0 >= kGoodLen && e[i + 1] != e1) ? kSymSlow : lit;
+                            if (mtab_len(e1) > l0) r = (l0 >= kGoodLen && e[i + 1] != e1) ? kSymSlow : lit;
                         }
                     }
                 }
@@ -504,7 +559,7 @@ __global__ void __launch_bounds__(256) k_next(const uint8_t *__restrict__ in, in
 }
 
 __global__ void __launch_bounds__(128) k_walk_spec(const uint8_t *__restrict__ in, int64_t in_stride,
-                                                   const int32_t *__restrict__ in_len, const ChainRec *__restrict__ recs,
+                                                   const int32_t *__restrict__ in_len,
                                                    const uint32_t *__restrict__ mlo, const uint32_t *__restrict__ mhi, uint32_t *__restrict__ mask,
                                                    int64_t mask_stride, uint32_t *__restrict__ rec, Walk *__restrict__ exits, int64_t stride,
                                                    int max_win) {
@@ -514,13 +569,13 @@ __global__ void __launch_bounds__(128) k_walk_spec(const uint8_t *__restrict__ i
     const int ws = k * kWalkWin;
     if (ws >= n) return;
     const int64_t o = (int64_t)stream * stride;
-    LzView v{in + (int64_t)stream * in_stride, recs + o, n};
+    LzView v{in + (int64_t)stream * in_stride, n};
     exits[(int64_t)stream * max_win + k] = walk_window(v, ProbeTab{mlo + o, mhi + o}, ws, min(ws + kWalkWin, n),
                                                        mask + (int64_t)stream * mask_stride, rec + o);
 }
 
 __global__ void __launch_bounds__(128) k_walk_stitch(const uint8_t *__restrict__ in, int64_t in_stride,
-                                                    const int32_t *__restrict__ in_len, const ChainRec *__restrict__ recs,
+                                                    const int32_t *__restrict__ in_len,
                                                     const uint32_t *__restrict__ mlo, const uint32_t *__restrict__ mhi, uint32_t *__restrict__ mask,
                                                     int64_t mask_stride, uint32_t *__restrict__ rec, const Walk *__restrict__ exits, int64_t stride,
                                                     int max_win, int B) {
@@ -528,7 +583,7 @@ __global__ void __launch_bounds__(128) k_walk_stitch(const uint8_t *__restrict__
     const int stream = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (stream >= B || (threadIdx.x & 31)) return;
     const int64_t o = (int64_t)stream * stride;
-    LzView v{in + (int64_t)stream * in_stride, recs + o, in_len[stream]};
+    LzView v{in + (int64_t)stream * in_stride, in_len[stream]};
     walk_stitch(v, ProbeTab{mlo + o, mhi + o}, kWalkWin, mask + (int64_t)stream * mask_stride, rec + o, exits + (int64_t)stream * max_win);
 }
 
@@ -815,45 +870,24 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(const uint8_t *__restrict
         or_bits(out32, bit_start + (uint64_t)hdr_bits + d.body_bits - llen[256], lcode[256], llen[256]);
 }
 
-// Per-device launch state: opt-in shared-memory sizes are a property of (function, device) and the SM count of the
-// device, so both are kept per device (several devices may be driven from one process through cct_*_host).
-struct DevState { int n_sm = 0; };
-static const DevState &dev_state() {
+// Per-device launch state: opt-in shared-memory sizes are a property of (function, device), so they are set once per
+// device (several devices may be driven from one process through cct_*_host).
+static void dev_setup() {
     static std::mutex mu;
-    static DevState per_dev[64];
+    static bool done[64];
     int dev = 0;
     cudaGetDevice(&dev);
     dev = std::min(std::max(dev, 0), 63);
     std::lock_guard<std::mutex> lk(mu);
-    DevState &d = per_dev[dev];
-    if (!d.n_sm) {
-        const int chain_smem = kHeadEntries * (int)sizeof(uint16_t) + (int)sizeof(ChainSmem);
-        cudaFuncSetAttribute(k_chains, cudaFuncAttributeMaxDynamicSharedMemorySize, chain_smem);
-        cudaFuncSetAttribute(k_block_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlockBuildSmem));
-        cudaDeviceGetAttribute(&d.n_sm, cudaDevAttrMultiProcessorCount, dev);
-    }
-    return d;
+    if (done[dev]) return;
+    cudaFuncSetAttribute(k_block_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlockBuildSmem));
+    done[dev] = true;
 }
 
-void launch_chains(const uint8_t *in, int64_t in_stride, const int32_t *in_len, int B, uint16_t *dist16, int64_t stride,
-                   cudaStream_t st) {
-    if (B == 0) return;
-    const int chain_smem = kHeadEntries * (int)sizeof(uint16_t) + (int)sizeof(ChainSmem);
-    dev_state();
-    { CCT_KERNEL(k_chains, st);
-    k_chains<<<B, 32 * kChainWarps, chain_smem, st>>>(in, in_stride, in_len, dist16, stride);
-    }
-}
-
-void launch_deflate(const uint8_t *in, int64_t in_stride, const int32_t *in_len, int B, int64_t max_len, uint8_t *out,
-                    int64_t out_stride, int32_t *out_len, const DeflateWs &ws, cudaStream_t st) {
-    if (B == 0) return;
-    const int chain_smem = kHeadEntries * (int)sizeof(uint16_t) + (int)sizeof(ChainSmem);
-    const DevState &dev = dev_state();
-    { CCT_KERNEL(k_chains, st);
-    k_chains<<<B, 32 * kChainWarps, chain_smem, st>>>(in, in_stride, in_len, ws.dist16, ws.stride);
-    }
-    {   // the chunk summaries live in arrays the parse fills later
+// run counts, hash sort and probe tables of B streams (the first half of launch_deflate; also the stage tap)
+static void launch_match_tables(const uint8_t *in, int64_t in_stride, const int32_t *in_len, int B, int64_t max_len,
+                                const DeflateWs &ws, cudaStream_t st) {
+    {   // the chunk summaries live in arrays that are filled later
         const int max_chunks = (int)((max_len + kRunChunk - 1) / kRunChunk);
         int4 *edges = reinterpret_cast<int4 *>(ws.rec);
         int2 *enters = reinterpret_cast<int2 *>(ws.mhi);
@@ -864,31 +898,59 @@ void launch_deflate(const uint8_t *in, int64_t in_stride, const int32_t *in_len,
         { CCT_KERNEL(k_run_link, st);
         k_run_link<<<(B + kRunWarps - 1) / kRunWarps, 32 * kRunWarps, 0, st>>>(in_len, edges, enters, max_chunks, B);
         }
-        { CCT_KERNEL(k_run_recs, st);
-        k_run_recs<<<gt, 32 * kRunWarps, 0, st>>>(in, in_stride, in_len, ws.dist16, enters, max_chunks, ws.recs, ws.stride);
+        { CCT_KERNEL(k_run_counts, st);
+        k_run_counts<<<gt, 32 * kRunWarps, 0, st>>>(in, in_stride, in_len, enters, max_chunks, ws.runs, ws.stride);
         }
     }
-    {
-        // (asking for an all-L1 carve-out made the kernel 38 % slower: fewer CTAs fit once no shared memory is configured)
-        const int n_sm = dev.n_sm;
-        const uint32_t units_per_stream = (uint32_t)((max_len + kProbeUnit - 1) / kProbeUnit);
-        { CCT_KERNEL(m_zero_probe, st); cudaMemsetAsync(ws.probe_next, 0, kMaxSm * sizeof(uint32_t), st); }
-        CCT_KERNEL(k_probe, st);
-        k_probe<<<n_sm * 16, kProbeThreads, 0, st>>>(in, (uint32_t)in_stride, in_len, ws.recs, ws.mtab, ws.mhi, (uint32_t)ws.stride,
-                                                     units_per_stream, units_per_stream * (uint32_t)B, ws.probe_next,
-                                                     (uint32_t)std::min(n_sm, kMaxSm));
+    dim3 gtile((unsigned)ws.max_tiles, (unsigned)B);
+    { CCT_KERNEL(k_hs_hist, st);
+    k_hs_hist<<<gtile, kHsThreads, 0, st>>>(in, in_stride, in_len, ws.thist, ws.max_tiles);
     }
+    { CCT_KERNEL(k_hs_scan, st);
+    k_hs_scan<<<B, kHsBins, 0, st>>>(in_len, ws.thist, ws.max_tiles, ws.binbase);
+    }
+    { CCT_KERNEL(k_hs_split, st);
+    k_hs_split<<<gtile, kHsThreads, 0, st>>>(in, in_stride, in_len, ws.thist, ws.max_tiles, ws.p1, ws.stride);
+    }
+    {
+        const int64_t total_bins = (int64_t)B * kHsBins;
+        int dev = 0, n_sm = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        const int64_t ctas = std::min<int64_t>(total_bins, (int64_t)n_sm * 8);
+        { CCT_KERNEL(m_zero_counters, st); cudaMemsetAsync(ws.counters, 0, 64 * sizeof(uint32_t), st); }
+        CCT_KERNEL(k_hs_bins, st);
+        k_hs_bins<<<(unsigned)ctas, kBinThreads, 0, st>>>(ws.binbase, ws.p1, ws.ent, ws.stride, (int)total_bins, ws.counters);
+    }
+    {
+        dim3 gp((unsigned)std::min<int64_t>((max_len + kBprobeThreads - 1) / kBprobeThreads, 32), (unsigned)B);
+        CCT_KERNEL(k_bprobe, st);
+        k_bprobe<<<gp, kBprobeThreads, 0, st>>>(in, in_stride, in_len, ws.ent, ws.runs, ws.mtab, ws.mhi, ws.stride);
+    }
+}
+
+void launch_probe_tables(const uint8_t *in, int64_t in_stride, const int32_t *in_len, int B, int64_t max_len,
+                         const DeflateWs &ws, cudaStream_t st) {
+    if (B == 0) return;
+    launch_match_tables(in, in_stride, in_len, B, max_len, ws, st);
+}
+
+void launch_deflate(const uint8_t *in, int64_t in_stride, const int32_t *in_len, int B, int64_t max_len, uint8_t *out,
+                    int64_t out_stride, int32_t *out_len, const DeflateWs &ws, cudaStream_t st) {
+    if (B == 0) return;
+    dev_setup();
+    launch_match_tables(in, in_stride, in_len, B, max_len, ws, st);
     dim3 gn((unsigned)std::min<int64_t>((max_len + 1023) / 1024, 512), (unsigned)B);
     { CCT_KERNEL(k_next, st);
     k_next<<<gn, 256, 0, st>>>(in, in_stride, in_len, ws.mtab, ws.mhi, ws.rec, ws.stride);
     }
     dim3 gw((unsigned)((ws.max_win + 127) / 128), (unsigned)B);
     { CCT_KERNEL(k_walk_spec, st);
-    k_walk_spec<<<gw, 128, 0, st>>>(in, in_stride, in_len, ws.recs, ws.mtab, ws.mhi, ws.mask, ws.mask_stride, ws.rec, ws.exits,
+    k_walk_spec<<<gw, 128, 0, st>>>(in, in_stride, in_len, ws.mtab, ws.mhi, ws.mask, ws.mask_stride, ws.rec, ws.exits,
                                     ws.stride, ws.max_win);
     }
     { CCT_KERNEL(k_walk_stitch, st);
-    k_walk_stitch<<<(B + 3) / 4, 128, 0, st>>>(in, in_stride, in_len, ws.recs, ws.mtab, ws.mhi, ws.mask, ws.mask_stride, ws.rec,
+    k_walk_stitch<<<(B + 3) / 4, 128, 0, st>>>(in, in_stride, in_len, ws.mtab, ws.mhi, ws.mask, ws.mask_stride, ws.rec,
                                                 ws.exits, ws.stride, ws.max_win, B);
     }
     { CCT_KERNEL(k_symscan, st);

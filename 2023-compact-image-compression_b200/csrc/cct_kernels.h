@@ -8,7 +8,7 @@
 namespace cct {
 
 struct BlockDesc;
-struct ChainRec;
+struct SortEnt;
 struct Walk;
 struct OpsChunkSum;
 
@@ -34,14 +34,17 @@ void launch_emit(const uint16_t *hv, const uint8_t *jump, const uint8_t *taken, 
                  int32_t *plen, uint32_t *status, int32_t *stats, int B, int64_t n_px, cudaStream_t st);
 
 // ---- cct_deflate.cu
-constexpr int kMaxSm = 256;
 struct DeflateWs {  // device scratch for one pass over B streams of capacity max_len
-    uint16_t *dist16;    // [B][stride] chain links
-    ChainRec *recs;      // [B][stride] per-position record read by the chain walks
-    uint32_t *mtab, *mhi;  // [B][stride] probe table: entries for chain budget 4096 / 1024
+    SortEnt *ent;        // [B][stride] chain members sorted by (hash, position)
+    uint32_t *runs;      // [B][stride] equal bytes after / before every position
+    SortEnt *p1;         // [B][stride] (position, bytes) split by the top hash digit (first pass of the sort; aliases mtab + mhi)
+    uint32_t *counters;  // [64] work counters of the persistent kernels (zeroed before each)
+    uint32_t *thist;     // [B][max_tiles][128] per-tile bin counts, then offsets
+    uint32_t *binbase;   // [B][129] bin starts
+    int max_tiles;
+    uint32_t *mtab, *mhi;  // [B][stride] probe table: entries for chain budget 4096 / (where flagged) 1024
     uint32_t *syms;      // [B][stride] dense LZ77 symbols
     uint32_t *rec;       // [B][stride] symbol a walk standing at each position emits (k_next; slow steps recorded by the walks)
-    uint32_t *probe_next; // [kMaxSm] next unit of each SM's range (k_probe)
     uint32_t *mask;      // [B][mask_stride] bit p = a symbol starts at position p
     int64_t mask_stride; // words per stream
     Walk *exits;         // [B][max_win] state each speculative window was left with
@@ -62,9 +65,9 @@ size_t deflate_ws_carve(DeflateWs *ws, void *mem, int B, int64_t max_len);
 void launch_deflate(const uint8_t *in, int64_t in_stride, const int32_t *in_len, int B, int64_t max_len, uint8_t *out,
                     int64_t out_stride, int32_t *out_len, const DeflateWs &ws, cudaStream_t st);
 
-// chain links only (stage tap): dist16[i*stride + p] for stream i
-void launch_chains(const uint8_t *in, int64_t in_stride, const int32_t *in_len, int B, uint16_t *dist16, int64_t stride,
-                   cudaStream_t st);
+// sorted chain members and probe tables only (stage tap): fills ws.ent, ws.mtab, ws.mhi
+void launch_probe_tables(const uint8_t *in, int64_t in_stride, const int32_t *in_len, int B, int64_t max_len,
+                         const DeflateWs &ws, cudaStream_t st);
 
 // ---- cct_decode.cu
 struct InflateWs {

@@ -5,14 +5,13 @@
 // What is restated: the reference's entropy stage is `zlib.compress(data, level = 9)`
 // (reference src/codec/core.py:340) = system libz 1.3 `deflate_slow` + `trees.c` (third-party, not in the
 // reference tree; algorithm recorded in SURVEY.md Appendix B).  The decomposition used here:
-//   1. hash chains are parse-independent (every position is inserted exactly once, in order), so
-//      `dist16[s]` = distance to the previous position with the same 3-byte hash is a pure function
-//      of the data (kernel k_chains);
-//   2. `match_probe` runs longest_match from a cold start (best = 2) over the first K chain entries
-//      for EVERY position in parallel and records (len, dist, complete?) in a table;
+//   1. hash chains are parse-independent (every position is inserted exactly once, in order): the chain of a
+//      position is the list of earlier positions with its 3-byte hash, so with the positions SORTED by
+//      (hash, position) (kernels k_hs_*) it is the piece of the sorted array just below the position;
+//   2. `bucket_probe` runs longest_match from a cold start (best = 2) for EVERY position in parallel, scanning
+//      that piece, and records (len, dist) for both chain budgets in a table;
 //   3. zlib's lazy-evaluation state machine is walked over symbol starts: speculatively per window in
-//      parallel (`walk_window`), then stitched per stream (`walk_stitch`); where the probe was incomplete
-//      it falls back to `match_full`, the exact longest_match loop;
+//      parallel (`walk_window`), then stitched per stream (`walk_stitch`);
 //   4. `build_block` restates _tr_flush_block's tree construction and block-type choice;
 //   5. the symbol bits are then packed in parallel from the code tables.
 #pragma once
@@ -31,8 +30,9 @@ namespace cct {
 // ------------------------------------------------------------------------------------------------
 // symbol / table encodings
 // ------------------------------------------------------------------------------------------------
-// mtab entry: bits 0..8 best length (0 = no match), bits 9..23 distance, bit 31 = probe incomplete
-constexpr uint32_t kProbeIncomplete = 0x80000000u;
+// probe-table entry: bits 0..8 best length (0 = no match), bits 9..23 distance; in the budget-4096 table bit 30 says
+// that the budget-1024 entry differs (and is stored in the second table; otherwise that table holds nothing)
+constexpr uint32_t kProbeHiDiff = 0x40000000u;
 CCT_HD uint32_t mtab_pack(int len, int dist) { return (uint32_t)len | ((uint32_t)dist << 9); }
 CCT_HD int mtab_len(uint32_t e) { return (int)(e & 511u); }
 CCT_HD int mtab_dist(uint32_t e) { return (int)((e >> 9) & 32767u); }
@@ -81,71 +81,11 @@ CCT_HD uint32_t static_lcode(int n) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// longest_match
+// longest_match over hash-sorted positions
 // ------------------------------------------------------------------------------------------------
-// Everything the chain walk needs to know about a position, in one aligned 8-byte load.  (The walk is bound by
-// the instructions it issues and the distinct memory sectors its divergent loads touch, so a record carries enough
-// of the payload that the common candidate -- same hash, at most three matching bytes -- never touches the payload.)
-//   a.lo16  link: distance to the previous position with the same hash, 0 = none / >= 32768.  For a run position
-//           (rl >= 2) it is the link of the BOTTOM of its run group, position max(p - rb, 1): the position's own link
-//           is then implied (1 inside a run, because p-1 starts the same triple; 0 at position 1) and the group step
-//           needs the bottom's.
-//   a.hi16  rl: number of bytes equal to w[p] immediately after p (capped at 65535)
-//   b       rl <  2: w[p] | w[p+1] << 8 | w[p+2] << 16 | w[p+3] << 24   (0 past the end)
-//           rl >= 2: rb | w[p] << 16 | ba << 24 with rb = number of bytes equal to w[p] immediately before p (capped at
-//                    65535) and ba = w[p + rl + 1], the first byte after the run (0 past the end or when rl is capped)
-struct alignas(8) ChainRec { uint32_t a, b; };
-CCT_HD int rec_link(const ChainRec &r) { return (int)(r.a & 0xFFFFu); }
-CCT_HD int rec_rl(const ChainRec &r) { return (int)(r.a >> 16); }
-CCT_HD bool rec_is_run(const ChainRec &r) { return r.a >= 0x20000u; }
-CCT_HD int rec_rb(const ChainRec &r) { return (int)(r.b & 0xFFFFu); }            // run records only
-CCT_HD uint32_t rec_run_byte(const ChainRec &r) { return (r.b >> 16) & 0xFFu; }  // run records only
-CCT_HD uint32_t rec_after(const ChainRec &r) { return r.b >> 24; }               // run records only
-// the position's own chain link
-CCT_HD int rec_own_dist(const ChainRec &r, int p) { return (rec_is_run(r) && rec_rb(r)) ? (p >= 2 ? 1 : 0) : rec_link(r); }
-// the first four payload bytes at the position (byte 3 of a run record: the run goes on, or the byte after it)
-CCT_HD uint32_t rec_quad(const ChainRec &r) {
-    if (!rec_is_run(r)) return r.b;
-    const uint32_t c = rec_run_byte(r);
-    return c * 0x010101u | ((rec_rl(r) >= 3 ? c : rec_after(r)) << 24);
-}
-CCT_HD ChainRec pack_rec_plain(int link, int rl, uint32_t quad) { return ChainRec{(uint32_t)link | ((uint32_t)rl << 16), quad}; }
-CCT_HD ChainRec pack_rec_run(int bottom_link, int rl, int rb, uint32_t c, uint32_t after) {
-    return ChainRec{(uint32_t)bottom_link | ((uint32_t)rl << 16), (uint32_t)rb | (c << 16) | (after << 24)};
-}
-// The record of position p from the plain arrays (dist16 = own links, rl / rb = capped run counts).
-CCT_HD ChainRec make_rec(const uint8_t *w, int n, const uint16_t *dist16, int p, int rl, int rb) {
-    if (rl >= 2) {
-        const int bottom = p - rb < 1 ? 1 : p - rb;
-        const int q = p + rl + 1;
-        return pack_rec_run(dist16[bottom], rl, rb, w[p], (rl < 65535 && q < n) ? w[q] : 0u);
-    }
-    uint32_t quad = 0;
-    for (int i = 0; i < 4; i++) if (p + i < n) quad |= (uint32_t)w[p + i] << (8 * i);
-    return pack_rec_plain(dist16[p], rl, quad);
-}
-
-CCT_HD void store_rec(ChainRec *p, const ChainRec &r) {  // one 8-byte store
-#if defined(__CUDA_ARCH__)
-    *reinterpret_cast<uint2 *>(p) = make_uint2(r.a, r.b);
-#else
-    *p = r;
-#endif
-}
-
-CCT_HD ChainRec load_rec(const ChainRec *p) {
-#if defined(__CUDA_ARCH__)
-    const uint2 q = __ldg(reinterpret_cast<const uint2 *>(p));
-    return ChainRec{q.x, q.y};
-#else
-    return *p;
-#endif
-}
-
 struct LzView {
-    const uint8_t *w;       // payload bytes
-    const ChainRec *recs;   // per-position record (k_run_recs)
-    int n;                  // payload length
+    const uint8_t *w;  // payload bytes
+    int n;             // payload length
 };
 
 CCT_HD uint8_t load_byte(const uint8_t *p) {  // payload bytes are read-only for the whole deflate stage
@@ -161,160 +101,238 @@ CCT_HD int match_extend(const uint8_t *a, const uint8_t *b, int from, int cap) {
     return len;
 }
 
-// How a chain walk ended.
-constexpr int kWalkDone = 0;    // chain end, distance limit or a match of the maximum useful length
-constexpr int kWalkBudget = 1;  // chain budget exhausted
-constexpr int kWalkSteps = 2;   // step cap of the probe reached
+// A hash chain is nothing but the positions of one hash value in decreasing order, so with the positions of a
+// stream SORTED by (hash, position) the chain of a target is the run of entries just below it in the sorted array:
+// the pointer chase of longest_match becomes a scan of contiguous 8-byte entries (coalesced over the lanes of a warp,
+// which hold neighbouring targets of the same bucket), and the links -- zlib's prev[] -- are never materialised.
+// One entry per chain member (positions 1 .. n-3; position 0 doubles as NIL in zlib and is never a candidate):
+//   a   position | kEntRun (the position starts a triple (c,c,c)) | kEntFirst (lowest position of its hash bucket)
+//   q   w[p] | w[p+1] << 8 | w[p+2] << 16 | w[p+3] << 24   (0 past the end)
+// One scan step handles either a single candidate or a whole RUN GROUP.  When the candidate `cur` starts with a triple
+// (c,c,c), the chain entries below cur inside that run are exactly the consecutive positions cur-1, cur-2, ... down to
+// the run start (all have the hash of (c,c,c)), hence consecutive entries of the sorted array.  If the target does not
+// itself start with (c,c,c) -- the chain only shares the hash -- none of them matches 3 bytes.  If it starts with R >= 3
+// copies of c, the match length of the i-th member is known in closed form from its count of leading c's, m + i:
+// m+i if m+i < R, "R + whatever follows" if m+i == R, exactly R if m+i > R (R < cap), cap if R == cap.  Since only the
+// first-visited candidate attaining the maximum matters, the group is consumed in one step and the scan
+// jumps over its lower members; the chain budget and the distance limit are charged as if every member had been
+// visited.  "Whatever follows" starts with the byte after either run: the payload is compared only when they agree.
+// The run lengths around a position come from runs[p] = rl | rb << 16 (the bytes equal to w[p] immediately after /
+// before p, both capped at 65535), read only on a run member.  A single candidate is compared through the four
+// payload bytes in its entry: one that merely shares the hash, or matches exactly three bytes, never touches the payload.
+constexpr uint32_t kEntRun = 0x80000000u, kEntFirst = 0x40000000u, kEntPos = 0x3FFFFFFFu;
+struct alignas(8) SortEnt { uint32_t a, q; };
+CCT_HD int ent_pos(const SortEnt &e) { return (int)(e.a & kEntPos); }
+CCT_HD bool quad_is_run(uint32_t q) { return ((q ^ (q >> 8)) & 0xFFFFu) == 0; }  // bytes 0, 1 and 2 are equal
+CCT_HD uint32_t hash_quad(uint32_t q) { return (((q & 0xFFu) << 10) ^ ((q >> 3) & 0x1FE0u) ^ ((q >> 16) & 0xFFu)) & 0x7FFFu; }  // hash3 of bytes 0..2
 
-// longest_match's candidate loop (deflate.c), walking the chain of position s from its head.
-//   best / bdist   in: best_len to beat (prev_length, or 2 for a cold start); out: result
-//   chain          number of candidates that may still be visited (max_chain_length, quartered by the caller)
-//   max_steps      cap on LOOP STEPS (not candidates) for the parallel probe
-// One loop step handles either a single candidate or a whole RUN GROUP.  When the candidate `cur` starts with
-// a triple (c,c,c), the chain entries below cur inside that run are exactly the consecutive positions cur-1,
-// cur-2, ... down to the run start (all have the hash of (c,c,c)).  If the target does not itself start with
-// (c,c,c) -- the chain only shares the hash -- none of them matches 3 bytes.  If it starts with R >= 3 copies
-// of c, the match length of the i-th member is known in closed form from its count of leading c's, m + i:
-// m+i if m+i < R, "R + whatever follows" if m+i == R, exactly R if m+i > R (R < cap), cap if R == cap.
-// Since only the first-visited candidate attaining the maximum matters, the group is consumed in
-// one step; the chain budget and the distance limit are charged as if every member had been visited.  "Whatever
-// follows" starts with the byte after either run, which both records carry: the payload is read only when they agree.
-// A single candidate is compared through the four payload bytes in its record: a candidate that merely shares the
-// hash, or matches exactly three bytes, is settled without touching the payload.
-// The walk is resumable (chain_begin / chain_run): match_probe raises the budget of a walk that ran out of it.
-struct ChainState {
-    int s, cap, best, bdist, chain, steps_left, cur, R;
-    uint32_t quad;   // target bytes 0..3
-    uint32_t after;  // R != 0: the byte after the target's run (meaningful when R < cap)
-};
-
-// Returns the target's own chain link (0: no chain).
-CCT_HD int chain_begin(const LzView &v, int s, int cap, int best, int chain, int max_steps, ChainState &c) {
-    const ChainRec rs = load_rec(v.recs + s);
-    c.s = s; c.cap = cap; c.best = best; c.bdist = 0; c.chain = chain; c.steps_left = max_steps;
-    c.quad = rec_quad(rs);
-    c.R = 0; c.after = 0;  // leading run of the target, if it is at least one hash triple long
-    if (rec_is_run(rs)) { c.R = rec_rl(rs) + 1; if (c.R > cap) c.R = cap; c.after = rec_after(rs); }
-    const int own = rec_own_dist(rs, s);
-    c.cur = s - own;
-    return own;
+CCT_HD SortEnt load_ent(const SortEnt *p) {
+#if defined(__CUDA_ARCH__)
+    const uint2 v = __ldg(reinterpret_cast<const uint2 *>(p));
+    return SortEnt{v.x, v.y};
+#else
+    return *p;
+#endif
+}
+// four payload bytes at any address (little-endian), as two aligned word loads on the device (payload rows are
+// 16-byte aligned and padded, so the second word is inside the row whenever the first byte wanted from it is)
+CCT_HD uint32_t load_u32_unaligned(const uint8_t *p) {
+#if defined(__CUDA_ARCH__)
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+    const uint32_t sh = ((uint32_t)a & 3u) * 8u;
+    const uint32_t lo = __ldg(w);
+    return sh ? __funnelshift_r(lo, __ldg(w + 1), sh) : lo;
+#else
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+#endif
+}
+CCT_HD int count_trailing_zeros(uint32_t v) {  // v != 0
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)v) - 1;
+#else
+    return __builtin_ctz(v);
+#endif
+}
+CCT_HD uint32_t load_u32(const uint32_t *p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
 }
 
-// Runs the walk until it ends (one loop step = a single candidate or a whole run group) and returns how it ended;
-// the state is left such that a walk cut short by the budget or the step cap can go on (c.chain / c.steps_left
-// raised by the caller).  The chain budget and the step cap both drop by one per step, so the loop carries the step
-// count and the (constant) difference: one counter, one exit test.
-CCT_HD int chain_run(const LzView &v, ChainState &c) {
-    const int s = c.s, cap = c.cap;
-    int cur = c.cur, best = c.best, bdist = c.bdist, steps = c.steps_left;
-    int diff = c.chain - steps;       // chain = steps + diff
-    int lim = diff < 0 ? -diff : 0;   // steps == lim: the budget (diff < 0) or the step cap ran out
-    int r;
-    for (;;) {
-        CCT_COUNT(0);
-        const ChainRec rc = load_rec(v.recs + cur);  // one 8-byte load: link, run lengths, first bytes of the candidate
-        const int dl = rec_link(rc);
-        int link_from = cur;
-        if (rec_is_run(rc)) {
+struct BucketView {
+    const uint8_t *w;       // payload bytes
+    const SortEnt *ent;     // chain members sorted by (hash, position)
+    const uint32_t *runs;   // per position: rl | rb << 16
+    int n;                  // payload length
+};
+// the byte after the run a run member sits in (0 past the end or when the count is capped), as the group step needs it
+CCT_HD uint32_t run_after(const BucketView &v, int p, int rl) {
+    const int q = p + rl + 1;
+    return (rl < 65535 && q < v.n) ? (uint32_t)load_byte(v.w + q) : 0u;
+}
+
+// Both walks below are written for a whole warp: every lane calls them together (a lane without a target passes
+// active = false) and the candidate loops run while ANY lane is still walking, finished lanes idling.  The loops must
+// be warp-uniform: with a plain per-thread loop the compiler gives the branches inside the body no reconvergence point
+// before the loop exit, lanes that differ once never meet again, and the warp ends up stepping its lanes one after the
+// other (measured: 6.5 of 32 threads per instruction).  On the host a "warp" is one thread.
+#if defined(__CUDA_ARCH__)
+#define CCT_WARP_ANY(p) __any_sync(0xffffffffu, (p))
+#else
+#define CCT_WARP_ANY(p) (p)
+#endif
+
+// longest_match's candidate loop for the target at sorted index i, from a cold start (best_len 2), for both chain
+// budgets: *lo for prev_length < good_length (4096 candidates), *hi for prev_length >= good_length (1024).  Same
+// decisions, in the same order, as zlib's loop: a candidate replaces the best only when strictly longer, the
+// distance limit ends the walk before the budget does, a match of the maximum useful length ends it at once.
+// This is the general walk; bucket_probe_quick below settles most targets with far fewer instructions.
+CCT_HD void bucket_probe(const BucketView &v, int i, bool active, uint32_t *lo, uint32_t *hi) {
+    *lo = *hi = 0;
+    const SortEnt *pj = v.ent + i;  // the scan moves a pointer down the sorted array
+    SortEnt e{0u, 0u};              // the candidate
+    int s = 0, cap = 0, limit = 0, R = 0;
+    uint32_t quad = 0, after = 0;
+    if (active) {
+        const SortEnt me = load_ent(pj);
+        s = ent_pos(me);
+        const int look = v.n - s;
+        if (look < kMinMatch || (me.a & kEntFirst)) active = false;
+        else {
+            cap = look < kMaxMatch ? look : kMaxMatch;
+            quad = me.q;
+            if (me.a & kEntRun) {  // R = leading run of the target (at least one hash triple long), after = the byte after it
+                const int rl = (int)(load_u32(v.runs + s) & 0xFFFFu);
+                R = rl + 1 < cap ? rl + 1 : cap;
+                after = run_after(v, s, rl);  // (meaningful when R < cap)
+            }
+            e = load_ent(--pj);
+            if (s - ent_pos(e) > kMaxDist) active = false;  // deflate_slow's test on hash_head
+            limit = s - kMaxDist;                           // every further candidate must lie above it
+        }
+    }
+    int best = 2, bdist = 0, chain = kChainGood;
+    bool second = false;  // the walk with the full budget continues the quartered one
+    while (CCT_WARP_ANY(active)) {
+        if (!active) continue;
+        CCT_COUNT(2);
+        int end = 0;  // how the walk ends: 0 not yet, 1 chain end / distance limit / maximum length, 2 chain budget
+        const int cur = ent_pos(e);
+        uint32_t bottom_a = e.a;  // flags of the entry whose predecessor the walk moves on to
+        if (e.a & kEntRun) {
             // cur starts a triple (c,c,c): the chain entries below it inside the run form one group
-            const int chain = steps + diff;
-            const int m = rec_rl(rc) + 1;  // leading c's of the top candidate
-            int t = rec_rb(rc);            // further candidates of this run below cur
-            if (cur - t < 1) t = cur - 1;  // position 0 is never in a chain
+            const uint32_t ri = load_u32(v.runs + cur);
+            const int rl_g = (int)(ri & 0xFFFFu), m = rl_g + 1;  // leading c's of the top candidate
+            int t = (int)(ri >> 16);                              // further candidates of this run below cur
+            if (cur - t < 1) t = cur - 1;                         // position 0 is never in a chain
             const int count_dist = kMaxDist - (s - cur);
             int nvis = t + 1;
             if (chain < nvis) nvis = chain;
             if (count_dist < nvis) nvis = count_dist;
-            if (c.R && rec_run_byte(rc) == (c.quad & 0xFFu)) {
-                const int R = c.R;
+            if (R && (e.q & 0xFFu) == (quad & 0xFFu)) {
                 const int i_key = m >= R ? 0 : R - m;  // first member with at least R leading c's
                 if (R < cap && m > R) {
                     if (R > best) { best = R; bdist = s - cur; }
                 } else if (i_key < nvis) {
                     const int c_al = cur - i_key;  // R < cap: exactly R leading c's, then the byte after the group's run
                     int L = cap;
-                    if (R < cap) L = rec_after(rc) != c.after ? R : match_extend(v.w + c_al, v.w + s, R + 1, cap);
-                    if (L > best) { best = L; bdist = s - c_al; if (L >= cap) { r = kWalkDone; break; } }
+                    if (R < cap) L = run_after(v, cur, rl_g) != after ? R : match_extend(v.w + c_al, v.w + s, R + 1, cap);
+                    if (L > best) { best = L; bdist = s - c_al; if (L >= cap) end = 1; }
                 } else {
                     const int L = m + nvis - 1;  // only members with fewer than R leading c's were reached
                     if (L > best) { best = L; bdist = s - (cur - (nvis - 1)); }
                 }
             }  // else: the target does not start with (c,c,c) (a hash collision): no member matches 3 bytes
-            if (nvis < t + 1) { r = nvis == count_dist ? kWalkDone : kWalkBudget; break; }
-            diff -= t;  // chain -= t
-            lim = diff < 0 ? -diff : 0;
-            link_from = cur - t;  // the bottom of the run links onwards (its link is the one in the record)
-        } else {
-            const uint32_t x = rc.b ^ c.quad;
-            if ((x & 0xFFFFFFu) == 0) {  // the hash triple matches
-                int len = cap < kMinMatch ? cap : kMinMatch;
-                if (x == 0 && cap > kMinMatch) {
-                    // four bytes match: the payload decides (zlib's scan_end test is only a shortcut for len <= best)
-                    const uint8_t *a = v.w + cur, *b = v.w + s;
-                    len = (best > kMinMatch && load_byte(a + best) != load_byte(b + best)) ? 0 : match_extend(a, b, kMinMatch + 1, cap);
-                }
-                if (len > best) {
-                    best = len; bdist = s - cur;
-                    if (len >= cap) { r = kWalkDone; break; }
-                }
+            if (!end && nvis < t + 1) end = nvis == count_dist ? 1 : 2;
+            if (!end && t) { chain -= t; pj -= t; bottom_a = load_ent(pj).a; }
+        } else if (((e.q ^ quad) & 0xFFFFFFu) == 0) {  // the hash triple matches
+            int len = cap < kMinMatch ? cap : kMinMatch;
+            if (e.q == quad && cap > kMinMatch) {
+                // four bytes match: the payload decides (zlib's scan_end test is only a shortcut for len <= best)
+                const uint8_t *a = v.w + cur, *b = v.w + s;
+                len = (best > kMinMatch && load_byte(a + best) != load_byte(b + best)) ? 0 : match_extend(a, b, kMinMatch + 1, cap);
+            }
+            if (len > best) { best = len; bdist = s - cur; if (len >= cap) end = 1; }
+        }
+        if (!end) {
+            // move on to the previous member of the bucket: the distance limit comes before the budget, as in zlib's
+            // loop condition
+            if (bottom_a & kEntFirst) end = 1;
+            else {
+                e = load_ent(--pj);
+                chain--;
+                if (ent_pos(e) <= limit) end = 1;
+                else if (chain == 0) end = 2;
             }
         }
-        // follow the link, charge the budget and the step cap: one exit test on the common path (precedence as in
-        // zlib's loop condition: chain end / distance limit, then the budget; the step cap is ours and comes last)
-        cur = link_from - dl;
-        const bool done = (dl == 0) | (s - cur >= kMaxDist);  // cur <= limit
-        steps--;
-        if (done | (steps == lim)) { r = done ? kWalkDone : (steps + diff == 0 ? kWalkBudget : kWalkSteps); break; }
+        if (!end) continue;
+        const uint32_t r = best >= kMinMatch ? mtab_pack(best, bdist) : 0u;
+        if (!second) *hi = r;
+        *lo = r;
+        if (end != 2 || second) { active = false; continue; }
+        // The quartered budget ran out: the walk with the full budget visits the same candidates up to here, so it
+        // simply goes on.  (A run group cut short by the budget left pj and chain untouched and is evaluated again with
+        // the longer count -- its members seen so far are a prefix, so best/bdist come out as from a fresh walk.)
+        second = true;
+        chain += kChainFull - kChainGood;
     }
-    c.cur = cur; c.best = best; c.bdist = bdist; c.chain = steps + diff; c.steps_left = steps;
-    return r;
 }
 
-CCT_HD int chain_walk(const LzView &v, int s, int cap, int &best, int &bdist, int chain, int max_steps) {
-    ChainState c;
-    chain_begin(v, s, cap, best, chain, max_steps, c);
-    const int r = chain_run(v, c);
-    best = c.best; bdist = c.bdist;
-    return r;
-}
-
-// Cold-start probe (best_len = 2) over at most K loop steps.  longest_match's answer for any prev_length is
-// "the first-visited candidate attaining the maximum length, if that is longer" (SURVEY B.4); prev_length only
-// changes the chain budget (4096, quartered to 1024 once prev_length >= good_length 32), so the probe records
-// one entry per budget: *lo for prev_length < 32, *hi for prev_length >= 32.  They differ only when the chain
-// holds more than 1024 candidates.  An entry is kProbeIncomplete when the step cap ended the walk first.
-CCT_HD void match_probe(const LzView &v, int s, int K, uint32_t *lo, uint32_t *hi) {
-    *lo = *hi = 0;
-    const int look = v.n - s;
-    if (look < kMinMatch) return;
-    const int cap = look < kMaxMatch ? look : kMaxMatch;
-    ChainState c;
-    const int d0 = chain_begin(v, s, cap, 2, kChainGood, K, c);
-    if (d0 == 0 || d0 > kMaxDist) return;
-    int r = chain_run(v, c);
-    const uint32_t e = r == kWalkSteps ? kProbeIncomplete : (c.best >= kMinMatch ? mtab_pack(c.best, c.bdist) : 0u);
-    *lo = *hi = e;
-    if (r != kWalkBudget) return;
-    // The quartered budget ran out: the walk with the full budget visits the same candidates up to here, so it
-    // simply goes on.  (A run group cut short by the budget left cur and chain untouched and is evaluated again with
-    // the longer count -- its members seen so far are a prefix, so best/bdist come out as from a fresh walk.)
-    if (c.steps_left == 0) { *lo = kProbeIncomplete; return; }  // budget and step cap ran out on the same candidate
-    c.chain += kChainFull - kChainGood;
-    r = chain_run(v, c);
-    *lo = r == kWalkSteps ? kProbeIncomplete : (c.best >= kMinMatch ? mtab_pack(c.best, c.bdist) : 0u);
-}
-
-// Exact longest_match for position s with the parser's prev_length (chain budget 4096, or 1024 once
-// prev_length >= good_length 32).  Requires: valid head, prev_len < 258, prev_len < look.
-// Returns the improved length (> prev_len) and its distance, or 0.
-CCT_HD int match_full(const LzView &v, int s, int prev_len, int *out_dist) {
-    const int look = v.n - s;
-    const int cap = look < kMaxMatch ? look : kMaxMatch;
-    int best = prev_len, bdist = 0;
-    CCT_COUNT(1);
-    chain_walk(v, s, cap, best, bdist, prev_len >= kGoodLen ? kChainGood : kChainFull, 0x7FFFFFFF);
-    *out_dist = bdist;
-    return best > prev_len ? best : 0;
+// The same walk for the common target -- an ordinary position whose chain holds ordinary positions, none matching
+// eight bytes or more, and ends within the quartered budget: one 8-byte load per candidate, a second (unaligned) load
+// only for a candidate that matches four bytes.  Most candidates DO start with the target's three bytes (the hash is
+// all but injective on small deltas).  Returns false as soon as the walk meets anything else (the caller then runs
+// bucket_probe from the start); true with the table entry, valid for both budgets, otherwise (and for idle lanes).
+CCT_HD bool bucket_probe_quick(const BucketView &v, int i, bool active, uint32_t *out) {
+    *out = 0;
+    // state of the lane's walk: 0 walking, 1 settled, 2 left to the general walk  (an integer, not two bools: the
+    // compiler keeps bools that live across the loop as packed bytes and spends a third of the loop shuffling them)
+    uint32_t state = 1;
+    const SortEnt *pj = v.ent + i;
+    SortEnt e{0u, 0u};
+    int s = 0, limit = 0;
+    uint32_t quad = 0;
+    if (active) {
+        const SortEnt me = load_ent(pj);
+        s = ent_pos(me);
+        quad = me.q;
+        limit = s - kMaxDist;
+        if (me.a & kEntFirst) state = 1;  // no chain: no match, whatever the budget
+        else if ((me.a & kEntRun) || v.n - s < 8) state = 2;  // (the loop assumes a length cap >= 8)
+        else {
+            e = load_ent(--pj);
+            state = s - ent_pos(e) > kMaxDist ? 1u : 0u;  // deflate_slow's test on hash_head
+        }
+    }
+    int best = 2, bdist = 0, chain = kChainGood;
+    while (CCT_WARP_ANY(state == 0)) {
+        if (state == 0) {  // (one short divergent region per round: everything else is selects)
+            CCT_COUNT(3);
+            const uint32_t ea = e.a, x = e.q ^ quad;
+            const int cur = (int)(ea & kEntPos);
+            int len = (x & 0xFFFFFFu) == 0 ? kMinMatch : 0;
+            uint32_t st = (ea & kEntFirst) ? 1u : 0u;  // the lowest position of the bucket: the chain ends after it
+            if (ea & kEntRun) st = 2;                   // a run member: the general walk takes over
+            else if (x == 0) {
+                const uint32_t y = load_u32_unaligned(v.w + cur + 4) ^ load_u32_unaligned(v.w + s + 4);
+                if (y == 0) st = 2;  // eight bytes match
+                len = 4 + (count_trailing_zeros(y | 0x80000000u) >> 3);
+            }
+            if (len > best) { best = len; bdist = s - cur; }  // (len < 8 <= cap: never the maximum length)
+            if (st == 0) {
+                e = load_ent(--pj);
+                chain--;
+                if (ent_pos(e) <= limit) st = 1;  // the distance limit comes before the budget
+                else if (chain == 0) st = 2;      // more than 1024 candidates: the two budgets may differ
+            }
+            state = st;
+        }
+    }
+    if (state == 1 && best >= kMinMatch) *out = mtab_pack(best, bdist);
+    return state == 1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -328,9 +346,10 @@ CCT_HD int match_full(const LzView &v, int s, int prev_len, int *out_dist) {
 //         no cur                      -> LITERAL(w[p]);  next start p+1, cold
 //         search at p+1 beats cur     -> LITERAL(w[p]);  next start p+1, pending = that longer match
 //         otherwise                   -> MATCH(cur);     next start p+len, cold
-// A search result comes from the probe table when the probe was complete (then it does not depend on
-// prev_length beyond "must be longer", so a pending match at p is simply the table entry of p and the walk
-// state is a function of p alone) and from match_full otherwise.  Because the state is (almost always) a
+// A search result comes from the probe table: it does not depend on prev_length beyond "must be longer" and
+// the chain budget (one table per budget; they differ only where a chain holds more than 1024 candidates), so a
+// pending match at p is simply the table entry of p and the walk state is a function of p alone wherever the
+// two tables agree.  Because the state is (almost always) a
 // function of p, walks started at different positions coincide from the first symbol start they share: the
 // parse is done speculatively per window in parallel (walk_window), then stitched by one sequential pass per
 // stream that only re-walks up to the point where the true path joins the speculative one (walk_stitch).
@@ -342,14 +361,16 @@ struct ProbeTab {
     const uint32_t *lo, *hi;  // entries for chain budget 4096 (prev_length < 32) and 1024 (prev_length >= 32)
 };
 
+CCT_HD uint32_t probe_lo(const ProbeTab &mt, int p) { return mt.lo[p] & ~kProbeHiDiff; }
+CCT_HD uint32_t probe_hi(const ProbeTab &mt, int p) { const uint32_t e = mt.lo[p]; return (e & kProbeHiDiff) ? mt.hi[p] : e; }
+
 CCT_HD bool lookup_match(const LzView &v, const ProbeTab &mt, int p, int prev_len, int *len, int *dist) {
     const int look = v.n - p;
     if (look < kMinMatch) return false;
-    const uint32_t e = prev_len >= kGoodLen ? mt.hi[p] : mt.lo[p];
+    const uint32_t e = prev_len >= kGoodLen ? probe_hi(mt, p) : probe_lo(mt, p);
     if (e == 0 || prev_len >= kMaxMatch || prev_len >= look) return false;
     int ml = 0, md = 0;
-    if (e & kProbeIncomplete) ml = match_full(v, p, prev_len, &md);
-    else if (mtab_len(e) > prev_len) { ml = mtab_len(e); md = mtab_dist(e); }
+    if (mtab_len(e) > prev_len) { ml = mtab_len(e); md = mtab_dist(e); }
     if (ml == kMinMatch && md > kTooFar) ml = 0;
     *len = ml; *dist = md;
     return ml != 0;
@@ -369,8 +390,7 @@ CCT_HD uint32_t walk_step(const LzView &v, const ProbeTab &mtab, Walk &w) {
 // Do two walks standing on the same symbol start continue identically?
 CCT_HD bool walk_same_state(const ProbeTab &mt, const Walk &a, const Walk &b) {
     if (a.pl == b.pl && a.pd == b.pd) return true;
-    const uint32_t e = mt.lo[a.p];  // one complete entry for both budgets: the state is a function of the position
-    return e == mt.hi[a.p] && !(e & kProbeIncomplete);
+    return !(mt.lo[a.p] & kProbeHiDiff);  // one entry for both budgets: the state is a function of the position
 }
 
 // The step as a function of the position alone.  From a cold start at p the machine needs lookup(p, 2) and, if that
@@ -379,7 +399,7 @@ CCT_HD bool walk_same_state(const ProbeTab &mt, const Walk &a, const Walk &b) {
 // continues exactly like a cold one there, provided the pending entry is the one a cold lookup reads (always the case
 // below good_length; above it the two budget tables must agree).  walk_precompute evaluates this for every position
 // in parallel (k_next): sym[p] = the symbol a walk standing at p emits (the advance follows from it), or kSymSlow
-// when the step needs match_full or depends on how the walk got there.  The walks themselves (walk_window /
+// when the step depends on how the walk got there.  The walks themselves (walk_window /
 // walk_stitch) then chase one 4-byte entry per symbol and fall back to walk_step only on kSymSlow entries, whose
 // symbol they record in place with the marker kept.
 constexpr uint32_t kSymSlow = 0x80000000u;
@@ -389,19 +409,17 @@ CCT_HD uint32_t walk_precompute(const LzView &v, const ProbeTab &mt, int p) {
     const uint32_t lit = sym_pack(v.w[p], 0);
     const int look = v.n - p;
     if (look < kMinMatch) return lit;
-    const uint32_t e = mt.lo[p];  // lookup(p, 2)
-    if (e & kProbeIncomplete) return kSymSlow;
+    const uint32_t e = probe_lo(mt, p);  // lookup(p, 2)
     if (e == 0) return lit;
     const int l0 = mtab_len(e), d0 = mtab_dist(e);
     if (l0 == kMinMatch && d0 > kTooFar) return lit;
     const uint32_t match = sym_pack(l0 - kMinMatch, d0);
     const int look1 = look - 1;  // lookup(p + 1, l0)
     if (look1 < kMinMatch) return match;
-    const uint32_t e1 = l0 >= kGoodLen ? mt.hi[p + 1] : mt.lo[p + 1];
+    const uint32_t e1 = l0 >= kGoodLen ? probe_hi(mt, p + 1) : probe_lo(mt, p + 1);
     if (e1 == 0 || l0 >= kMaxMatch || l0 >= look1) return match;
-    if (e1 & kProbeIncomplete) return kSymSlow;
     if (mtab_len(e1) <= l0) return match;  // (a longer match is at least 4 long: the TOO_FAR rule cannot apply)
-    if (l0 >= kGoodLen && mt.lo[p + 1] != e1) return kSymSlow;  // the pending match is not what a cold lookup reads
+    if (l0 >= kGoodLen && probe_lo(mt, p + 1) != e1) return kSymSlow;  // the pending match is not what a cold lookup reads
     return lit;
 }
 

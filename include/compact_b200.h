@@ -137,10 +137,17 @@ size_t cct_deflate_workspace_bytes(int B, size_t max_len);
 size_t cct_deflate_bound(size_t len);
 int cct_deflate_batch(const uint8_t *d_in, size_t in_stride, const int32_t *d_in_len, int B, size_t max_len,
                       uint8_t *d_out, size_t out_stride, int32_t *d_out_len, void *d_ws, size_t ws_bytes, void *stream);
-/* Stage tap: zlib's hash-chain links.  d_dist16[i*stride + p] = distance from position p of string i to the previous
- * position with the same 3-byte hash (0 = none or >= 32768; position 0 is never a source). */
-int cct_debug_chains(const uint8_t *d_in, size_t in_stride, const int32_t *d_in_len, int B, uint16_t *d_dist16,
-                     size_t stride, void *stream);
+/* Stage tap: the match finder of the DEFLATE stage (zlib's longest_match, reference src/codec/core.py:340 via libz).
+ *   d_ent [B][stride] 8-byte entries: the chain members of string i (positions 1 .. len-3) sorted by (3-byte hash,
+ *         position); low word = position | 0x80000000 (starts a byte triple c,c,c) | 0x40000000 (first of its hash
+ *         bucket), high word = the four bytes at the position (0 past the end)
+ *   d_lo  [B][stride] uint32 per position: longest_match from a cold start with chain budget 4096 as
+ *         len | dist << 9 (0 = none); bit 30 set = the budget-1024 result differs and is in d_hi at the same index
+ *   d_hi  [B][stride] uint32, defined only where d_lo has bit 30 set
+ * Any of the three may be NULL; stride (elements) >= max_len; the workspace is cct_deflate_workspace_bytes(B, max_len). */
+int cct_debug_match_tables(const uint8_t *d_in, size_t in_stride, const int32_t *d_in_len, int B, size_t max_len,
+                           uint64_t *d_ent, uint32_t *d_lo, uint32_t *d_hi, size_t stride, void *d_ws, size_t ws_bytes,
+                           void *stream);
 /* Host logic tap (needs no device): the pass schedule cct_encode_host (decode = 0) / cct_decode_host (decode = 1)
  * use for B images of n_px pixels.  Writes the first image of every pass and then B to starts[0 .. n_pass] and returns
  * n_pass, or CCT_E_ARG when `cap` entries do not hold them. */

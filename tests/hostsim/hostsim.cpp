@@ -46,51 +46,74 @@ static uint32_t adler32_(const uint8_t *p, int64_t n) {
     return (b << 16) | a;
 }
 
-// The probe as first stated: one complete walk per chain budget.  match_probe (deflate_core.cuh) continues the
-// first walk instead of starting over; every entry it produces is checked against this.
-static void match_probe_two_walks(const LzView &v, int s, int K, uint32_t *lo, uint32_t *hi) {
-    *lo = *hi = 0;
-    const int look = v.n - s;
-    if (look < kMinMatch) return;
-    const int d0 = rec_own_dist(v.recs[s], s);
-    if (d0 == 0 || d0 > kMaxDist) return;
+// zlib's longest_match candidate loop, candidate by candidate over the chain links (no run shortcuts): the ground
+// truth the sorted scan is checked against.  Cold start (best_len 2) with the given chain budget.
+static uint32_t lm_reference(const uint8_t *w, int n, const uint16_t *dist16, int s, int budget) {
+    const int look = n - s;
+    if (look < kMinMatch || dist16[s] == 0 || dist16[s] > kMaxDist) return 0;
     const int cap = look < kMaxMatch ? look : kMaxMatch;
-    int best = 2, bdist = 0;
-    int r = chain_walk(v, s, cap, best, bdist, kChainGood, K);
-    const uint32_t e = r == kWalkSteps ? kProbeIncomplete : (best >= kMinMatch ? mtab_pack(best, bdist) : 0u);
-    *lo = *hi = e;
-    if (r != kWalkBudget) return;
-    best = 2; bdist = 0;
-    r = chain_walk(v, s, cap, best, bdist, kChainFull, K);
-    *lo = r == kWalkSteps ? kProbeIncomplete : (best >= kMinMatch ? mtab_pack(best, bdist) : 0u);
+    int best = 2, bdist = 0, cur = s - dist16[s];
+    for (;;) {
+        int len = 0;
+        while (len < cap && w[cur + len] == w[s + len]) len++;
+        if (len > best) { best = len; bdist = s - cur; if (len >= cap) break; }
+        if (dist16[cur] == 0) break;
+        cur -= dist16[cur];
+        if (s - cur >= kMaxDist) break;
+        if (--budget == 0) break;
+    }
+    return best >= kMinMatch ? mtab_pack(best, bdist) : 0u;
+}
+
+// Chain members of a stream sorted by (hash, position) and the run counts, as the sort kernels produce them.
+static void sorted_reference(const uint8_t *w, int n, std::vector<SortEnt> &ent, std::vector<uint32_t> &runs) {
+    std::vector<uint16_t> rb16, rl16;
+    runs_reference(w, n, rb16, rl16);
+    runs.assign((size_t)n + 1, 0);
+    for (int p = 0; p < n; p++) runs[p] = (uint32_t)rl16[p] | ((uint32_t)rb16[p] << 16);
+    std::vector<std::pair<uint32_t, int>> key;
+    for (int p = 1; p + 2 < n; p++) key.push_back({hash3(w + p), p});
+    std::stable_sort(key.begin(), key.end(), [](const auto &a, const auto &b) { return a.first < b.first; });
+    ent.assign(key.size() + 1, SortEnt{0, 0});
+    for (size_t i = 0; i < key.size(); i++) {
+        const int p = key[i].second;
+        uint32_t q = 0;
+        for (int k = 0; k < 4; k++) if (p + k < n) q |= (uint32_t)w[p + k] << (8 * k);
+        uint32_t a = (uint32_t)p;
+        if (quad_is_run(q)) a |= kEntRun;
+        if (i == 0 || key[i - 1].first != key[i].first) a |= kEntFirst;
+        ent[i] = SortEnt{a, q};
+    }
 }
 
 extern "C" {
 
-// Staged zlib-9 of src[0..n).  probe_k = chain entries examined by the parallel probe.
-// stats[0] = symbols, [1] = blocks, [2] = incomplete probe entries, [3] = probe loop steps, [4] = loop steps of the
-// on-demand searches made by the walk (stats must hold 5 values if non-null).
-int64_t hs_deflate2(const uint8_t *src, int n, uint8_t *dst, int64_t cap, int probe_k, int parse_win, int64_t *stats) {
-    long long c0 = cct_stat[0];
-    std::vector<uint16_t> dist16;
-    chains_reference(src, n, dist16);
-    std::vector<uint16_t> rb16, rl16;
-    runs_reference(src, n, rb16, rl16);
-    std::vector<ChainRec> recs((size_t)n + 1);
-    for (int p = 0; p < n; p++)
-        recs[p] = make_rec(src, n, dist16.data(), p, rl16[p], rb16[p]);
-    LzView v{src, recs.data(), n};
-    std::vector<uint32_t> mlo((size_t)n + 1, 0), mhi((size_t)n + 1, 0);
+// Staged zlib-9 of src[0..n).
+// stats[0] = symbols, [1] = blocks, [2] = positions whose two chain budgets give different matches, [3] = scan steps
+// of the probe, [4] = 0 (stats must hold 5 values if non-null).
+int64_t hs_deflate2(const uint8_t *src, int n, uint8_t *dst, int64_t cap, int parse_win, int64_t *stats) {
+    long long c0 = cct_stat[2];
+    std::vector<uint8_t> wbuf(src, src + n);
+    wbuf.resize((size_t)n + 16, 0);
+    src = wbuf.data();
+    std::vector<SortEnt> ent;
+    std::vector<uint32_t> runs;
+    sorted_reference(src, n, ent, runs);
+    BucketView bv{src, ent.data(), runs.data(), n};
+    LzView v{src, n};
+    std::vector<uint32_t> mlo((size_t)n + 1, 0), mhi((size_t)n + 1, 0xDEADBEEFu);  // (mhi is read only where flagged)
     int64_t n_incomplete = 0;
-    for (int s = 0; s < n; s++) {
-        match_probe(v, s, probe_k, &mlo[s], &mhi[s]);
-        uint32_t lo2, hi2;
-        match_probe_two_walks(v, s, probe_k, &lo2, &hi2);
-        if (lo2 != mlo[s] || hi2 != mhi[s]) return -4;
-        n_incomplete += ((mlo[s] | mhi[s]) & kProbeIncomplete) != 0;
+    const int members = n >= 4 ? n - 3 : 0;
+    for (int i = 0; i < members; i++) {
+        const int p = ent_pos(ent[i]);
+        uint32_t lo, hi;
+        if (bucket_probe_quick(bv, i, true, &lo)) hi = lo;
+        else bucket_probe(bv, i, true, &lo, &hi);
+        if (lo != hi) { mhi[p] = hi; lo |= kProbeHiDiff; n_incomplete++; }
+        mlo[p] = lo;
     }
     ProbeTab mtab{mlo.data(), mhi.data()};
-    long long c1 = cct_stat[0];
+    long long c1 = cct_stat[2];
     // speculative windows -> stitch -> compaction (the three parse kernels, sequentially)
     const int win = parse_win > 0 ? parse_win : 1024;
     std::vector<uint32_t> mask((size_t)n / 32 + 2, 0xFFFFFFFFu);  // (garbage: the window walks must write every word)
@@ -107,7 +130,7 @@ int64_t hs_deflate2(const uint8_t *src, int n, uint8_t *dst, int64_t cap, int pr
         syms[nsym++] = rec[p] & ~kSymSlow;
     }
     int n_flush = finish_blocks(nsym, nsym ? syms[nsym - 1] : 0u, n, blk_end.data());
-    long long c2 = cct_stat[0];
+    long long c2 = cct_stat[2];
     int nblk = n_flush + 1;
     std::vector<BlockDesc> desc((size_t)nblk);
     BlockWork *wk = new BlockWork;
@@ -166,10 +189,60 @@ int64_t hs_deflate2(const uint8_t *src, int n, uint8_t *dst, int64_t cap, int pr
     return len;
 }
 
+// Probe tables from the hash-sorted scan (bucket_probe) against zlib's candidate loop over the chain links.
+// Returns the number of differing entries (0 = identical).  steps[0] = scan steps of the general walk, steps[1] =
+// targets the quick walk settles (steps must hold 2 values if non-null).
+int64_t hs_probe_check(const uint8_t *src, int n, int64_t *steps) {
+    std::vector<uint8_t> w(src, src + n);
+    w.resize((size_t)n + 16, 0);
+    std::vector<uint16_t> dist16;
+    chains_reference(w.data(), n, dist16);
+    std::vector<SortEnt> ent;
+    std::vector<uint32_t> runs;
+    sorted_reference(w.data(), n, ent, runs);
+    BucketView bv{w.data(), ent.data(), runs.data(), n};
+    std::vector<uint32_t> lo((size_t)n + 1, 0), hi((size_t)n + 1, 0);
+    const long long c0 = cct_stat[2];
+    const int members = n >= 4 ? n - 3 : 0;
+    int64_t bad = 0, quick = 0;
+    for (int i = 0; i < members; i++) {
+        const int p = ent_pos(ent[i]);
+        bucket_probe(bv, i, true, &lo[p], &hi[p]);
+        uint32_t q;
+        if (bucket_probe_quick(bv, i, true, &q)) { quick++; if (q != lo[p] || q != hi[p]) bad++; }  // the short cut agrees wherever it settles
+    }
+    if (steps) { steps[0] = cct_stat[2] - c0; steps[1] = quick; }
+    for (int s = 0; s < n; s++)
+        if (lm_reference(w.data(), n, dist16.data(), s, kChainFull) != lo[s] || lm_reference(w.data(), n, dist16.data(), s, kChainGood) != hi[s]) bad++;
+    return bad;
+}
+
+// What cct_debug_match_tables returns for one string: ent[n] (8-byte entries, n-3 of them used), lo[n], hi[n]
+// (lo with kProbeHiDiff where hi differs; hi meaningful only there).
+void hs_match_tables(const uint8_t *src, int n, uint64_t *ent_out, uint32_t *lo_out, uint32_t *hi_out) {
+    std::vector<uint8_t> w(src, src + n);
+    w.resize((size_t)n + 16, 0);
+    std::vector<SortEnt> ent;
+    std::vector<uint32_t> runs;
+    sorted_reference(w.data(), n, ent, runs);
+    BucketView bv{w.data(), ent.data(), runs.data(), n};
+    const int members = n >= 4 ? n - 3 : 0;
+    for (int p = 0; p < n; p++) { lo_out[p] = 0; hi_out[p] = 0; }
+    for (int i = 0; i < members; i++) {
+        const int p = ent_pos(ent[i]);
+        uint32_t lo, hi;
+        if (bucket_probe_quick(bv, i, true, &lo)) hi = lo;
+        else bucket_probe(bv, i, true, &lo, &hi);
+        if (lo != hi) { hi_out[p] = hi; lo |= kProbeHiDiff; }
+        lo_out[p] = lo;
+        ent_out[i] = (uint64_t)ent[i].a | ((uint64_t)ent[i].q << 32);
+    }
+}
+
 void hs_stats(long long *out, int reset) { for (int i = 0; i < 8; i++) { out[i] = cct_stat[i]; if (reset) cct_stat[i] = 0; } }
 
-int64_t hs_deflate(const uint8_t *src, int n, uint8_t *dst, int64_t cap, int probe_k, int64_t *stats) {
-    return hs_deflate2(src, n, dst, cap, probe_k, 1024, stats);
+int64_t hs_deflate(const uint8_t *src, int n, uint8_t *dst, int64_t cap, int64_t *stats) {
+    return hs_deflate2(src, n, dst, cap, 1024, stats);
 }
 
 int hs_inflate(const uint8_t *in, int in_len, uint8_t *out, int out_cap) {

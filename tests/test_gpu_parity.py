@@ -385,42 +385,67 @@ def test_config_batch_roundtrip_4096(torch_cuda, pkg, synth, oracle):
     assert torch_cuda.equal(px.view(torch_cuda.int16), d_imgs)
 
 
-def _ref_chain_links(data: bytes):
-    """zlib's prev[] as distances: previous position with the same hash, position 0 excluded."""
-    w = np.frombuffer(data, dtype=np.uint8).astype(np.int64)
-    n = len(w)
-    out = np.zeros(n, dtype=np.uint16)
-    head = {}
-    for s in range(0, n - 2):
-        h = int(((w[s] << 10) ^ (w[s + 1] << 5) ^ w[s + 2]) & 0x7FFF)
-        p = head.get(h, 0)
-        if p and s - p < 32768:
-            out[s] = s - p
-        head[h] = s
-    return out
+@pytest.fixture(scope="module")
+def hostsim():
+    """The product's scalar cores compiled for the CPU (tests/hostsim): the expected intermediate results."""
+    import os
+    import subprocess
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim")
+    subprocess.run(["make", "-C", here], check=True, stdout=subprocess.DEVNULL)
+    L = C.CDLL(os.path.join(here, "libcct_hostsim.so"))
+    L.hs_match_tables.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.hs_match_tables.restype = None
+    return L
 
 
-def test_stage_chain_links(torch_cuda, native):
+def test_stage_match_tables(torch_cuda, native, hostsim, oracle, synth):
+    """The match finder of the DEFLATE stage: hash-sorted chain members (k_hs_*) and the longest_match tables
+    (k_bprobe) against the same cores run sequentially on the CPU over a reference sort."""
+    torch = torch_cuda
     rng = np.random.default_rng(3)
     blobs = [rng.integers(0, a, size=n, dtype=np.uint8).tobytes() for a in (2, 3, 16, 256) for n in (100, 5000, 40000)]
     blobs += [bytes(9000) + rng.integers(0, 4, size=3000, dtype=np.uint8).tobytes() + bytes(70000) + b"abc" * 500]
+    blobs += [b"", b"a", b"abc", b"aaaa", bytes(4097), bytes(4096) + b"ab"]
+    blobs += [oracle.encode(synth.synth_ct(s, 256), detail=True)[1]["payload"] for s in (0, 1)]
     L = native.lib()
     B = len(blobs)
-    stride = (max(len(b) for b in blobs) + 31) // 16 * 16
+    max_len = max(len(b) for b in blobs)
+    stride = (max_len + 31) // 16 * 16
     h_in = np.zeros((B, stride), dtype=np.uint8)
     for i, b in enumerate(blobs):
         h_in[i, :len(b)] = np.frombuffer(b, dtype=np.uint8)
-    d_in = _dev(torch_cuda, h_in)
-    d_len = _dev(torch_cuda, np.array([len(b) for b in blobs], dtype=np.int32))
-    d_out = torch_cuda.zeros((B, stride), dtype=torch_cuda.int16, device="cuda")
-    native.check(L.cct_debug_chains(d_in.data_ptr(), stride, d_len.data_ptr(), B, d_out.data_ptr(), stride,
-                                    torch_cuda.cuda.current_stream().cuda_stream))
-    torch_cuda.cuda.synchronize()
-    got = d_out.cpu().numpy().view(np.uint16)
-    for i, b in enumerate(blobs):
-        want = _ref_chain_links(b)
-        bad = np.nonzero(got[i, :len(b)] != want)[0]
-        assert len(bad) == 0, (i, len(b), bad[:8], got[i, bad[:8]], want[bad[:8]])
+    h_in[:, :] |= 0  # (rows are zero past the end here; the kernels must not depend on it: see the garbage pass below)
+    for garbage in (False, True):
+        if garbage:
+            for i, b in enumerate(blobs):
+                h_in[i, len(b):] = rng.integers(0, 256, size=stride - len(b), dtype=np.uint8)
+        d_in = _dev(torch, h_in)
+        d_len = _dev(torch, np.array([len(b) for b in blobs], dtype=np.int32))
+        d_ent = torch.zeros((B, stride), dtype=torch.int64, device="cuda")
+        d_lo = torch.zeros((B, stride), dtype=torch.int32, device="cuda")
+        d_hi = torch.zeros((B, stride), dtype=torch.int32, device="cuda")
+        ws = torch.empty(int(L.cct_deflate_workspace_bytes(B, max_len)), dtype=torch.uint8, device="cuda")
+        native.check(L.cct_debug_match_tables(d_in.data_ptr(), stride, d_len.data_ptr(), B, max_len, d_ent.data_ptr(),
+                                              d_lo.data_ptr(), d_hi.data_ptr(), stride, ws.data_ptr(), ws.numel(),
+                                              torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        g_ent = d_ent.cpu().numpy().view(np.uint64)
+        g_lo = d_lo.cpu().numpy().view(np.uint32)
+        g_hi = d_hi.cpu().numpy().view(np.uint32)
+        for i, b in enumerate(blobs):
+            n = len(b)
+            src = np.frombuffer(b, dtype=np.uint8) if n else np.zeros(1, np.uint8)
+            w_ent = np.zeros(max(n, 1), np.uint64)
+            w_lo = np.zeros(max(n, 1), np.uint32)
+            w_hi = np.zeros(max(n, 1), np.uint32)
+            hostsim.hs_match_tables(src.ctypes.data, n, w_ent.ctypes.data, w_lo.ctypes.data, w_hi.ctypes.data)
+            m = max(n - 3, 0)
+            bad = np.nonzero(g_ent[i, :m] != w_ent[:m])[0]
+            assert len(bad) == 0, ("sorted entries", i, n, bad[:4], g_ent[i, bad[:4]], w_ent[bad[:4]])
+            bad = np.nonzero(g_lo[i, :n] != w_lo[:n])[0]
+            assert len(bad) == 0, ("budget-4096 table", i, n, bad[:4], g_lo[i, bad[:4]], w_lo[bad[:4]])
+            flagged = (w_lo[:n] & 0x40000000) != 0
+            assert (g_hi[i, :n][flagged] == w_hi[:n][flagged]).all(), ("budget-1024 table", i, n)
 
 
 def test_evaluate_harness(torch_cuda, pkg, synth, oracle, tmp_path):

@@ -20,7 +20,11 @@ def hostsim():
     subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "hostsim")], check=True, stdout=subprocess.DEVNULL)
     L = C.CDLL(os.path.join(ROOT, "tests", "hostsim", "libcct_hostsim.so"))
     u8p = C.POINTER(C.c_uint8)
-    L.hs_deflate.argtypes = [u8p, C.c_int, u8p, C.c_int64, C.c_int, C.POINTER(C.c_int64)]
+    L.hs_deflate.argtypes = [u8p, C.c_int, u8p, C.c_int64, C.POINTER(C.c_int64)]
+    L.hs_deflate2.argtypes = [u8p, C.c_int, u8p, C.c_int64, C.c_int, C.POINTER(C.c_int64)]
+    L.hs_deflate2.restype = C.c_int64
+    L.hs_probe_check.argtypes = [u8p, C.c_int, C.POINTER(C.c_int64)]
+    L.hs_probe_check.restype = C.c_int64
     L.hs_deflate.restype = C.c_int64
     L.hs_inflate.argtypes = [u8p, C.c_int, u8p, C.c_int]
     L.hs_inflate.restype = C.c_int
@@ -37,12 +41,13 @@ def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t))
 
 
-def _hs_deflate(L, data, k):
+def _hs_deflate(L, data, win=1024):
+    """Staged zlib-9 through the product's scalar cores; `win` = positions per speculative parse window."""
     src = np.frombuffer(data, dtype=np.uint8) if data else np.zeros(1, np.uint8)
     cap = len(data) + len(data) // 1000 * 6 + 1024
     out = np.empty(cap, np.uint8)
     st = (C.c_int64 * 5)()
-    r = L.hs_deflate(_p(src, C.c_uint8), len(data), _p(out, C.c_uint8), cap, k, st)
+    r = L.hs_deflate2(_p(src, C.c_uint8), len(data), _p(out, C.c_uint8), cap, win, st)
     assert r >= 0, r
     return out[:r].tobytes()
 
@@ -117,8 +122,23 @@ def test_staged_deflate_cores_match_libz(hostsim):
     from test_oracle import _deflate_corpus
     for data in _deflate_corpus():
         ref = zlib.compress(data, 9)
-        for k in (1, 4, 32):
-            assert _hs_deflate(hostsim, data, k) == ref, (len(data), k)
+        for win in (32, 1024):
+            assert _hs_deflate(hostsim, data, win) == ref, (len(data), win)
+
+
+def test_sorted_scan_matches_zlib_candidate_loop(hostsim):
+    """bucket_probe (longest_match as a scan of hash-sorted positions, run groups in closed form) against zlib's
+    candidate-by-candidate loop over the chain links, both chain budgets, on inputs with long chains and runs."""
+    rng = np.random.default_rng(5)
+    blobs = [rng.integers(0, a, size=n, dtype=np.uint8).tobytes() for a, n in ((2, 12000), (4, 20000), (256, 30000))]
+    blobs.append(bytes(70000))
+    blobs.append(np.repeat(rng.integers(0, 3, 4000, dtype=np.uint8), rng.integers(1, 40, 4000)).tobytes())
+    blobs.append(b"abcabcabd" * 4000 + rng.integers(0, 255, 3000, dtype=np.uint8).tobytes())
+    blobs.append(bytes(40000) + b"\x01" + bytes(300) + b"\x02" + bytes(5000) + b"\x00\x20\x00" * 50 + bytes(100))
+    blobs += [b"", b"a", b"ab", b"abc", b"aaaa", b"abcabc"]
+    for b in blobs:
+        src = np.frombuffer(b, dtype=np.uint8) if b else np.zeros(1, np.uint8)
+        assert hostsim.hs_probe_check(_p(src, C.c_uint8), len(b), None) == 0, len(b)
 
 
 def test_staged_deflate_block_boundaries(hostsim):
@@ -126,9 +146,9 @@ def test_staged_deflate_block_boundaries(hostsim):
     lits = rng.permutation(np.arange(256, dtype=np.uint8).repeat(200))
     for n in (16382, 16383, 16384, 16385, 32766, 32767):
         data = lits[:n].tobytes()
-        assert _hs_deflate(hostsim, data, 32) == zlib.compress(data, 9), n
+        assert _hs_deflate(hostsim, data) == zlib.compress(data, 9), n
         data2 = data + data[-40:]
-        assert _hs_deflate(hostsim, data2, 32) == zlib.compress(data2, 9), n
+        assert _hs_deflate(hostsim, data2) == zlib.compress(data2, 9), n
 
 
 def test_staged_deflate_on_codec_payloads(hostsim, oracle, synth, golden_cct):
@@ -136,7 +156,7 @@ def test_staged_deflate_on_codec_payloads(hostsim, oracle, synth, golden_cct):
     payloads += [oracle.encode(synth.synth_ct(s), detail=True)[1]["payload"] for s in (0, 1)]
     payloads.append(oracle.encode(synth.random_walk_image(3, 64, 64), detail=True)[1]["payload"])
     for p in payloads:
-        assert _hs_deflate(hostsim, p, 32) == zlib.compress(p, 9)
+        assert _hs_deflate(hostsim, p) == zlib.compress(p, 9)
 
 
 def test_inflate_core(hostsim):
