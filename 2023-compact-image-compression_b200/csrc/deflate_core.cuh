@@ -281,11 +281,17 @@ CCT_HD void bucket_probe(const BucketView &v, int i, bool active, uint32_t *lo, 
     }
 }
 
-// The same walk for the common target -- an ordinary position whose chain holds ordinary positions, none matching
-// eight bytes or more, and ends within the quartered budget: one 8-byte load per candidate, a second (unaligned) load
-// only for a candidate that matches four bytes.  Most candidates DO start with the target's three bytes (the hash is
-// all but injective on small deltas).  Returns false as soon as the walk meets anything else (the caller then runs
-// bucket_probe from the start); true with the table entry, valid for both budgets, otherwise (and for idle lanes).
+// The same walk for the common targets, with far fewer instructions.  Returns false when the walk meets anything it
+// does not handle (the caller then runs bucket_probe from the start); true with the table entry, valid for both
+// budgets, otherwise (and for idle lanes).
+//   * An ordinary position whose chain holds ordinary positions, none matching eight bytes or more, and ends within the
+//     quartered budget: one 8-byte load and a few selects per candidate.  Most candidates DO start with the target's
+//     three bytes (the hash is all but injective on small deltas) and are settled from the entry alone; the few that
+//     match four bytes are only noted (a bit per candidate) and measured after every 32 candidates -- inside the loop
+//     the two lanes that need the payload would stall the other thirty.  The result does not depend on that order: it
+//     is the longest candidate, the nearest among equals.
+//   * A position inside a byte run with at least the maximum match length still to go: its predecessor matches that
+//     much, at distance 1, and nothing can beat it.
 CCT_HD bool bucket_probe_quick(const BucketView &v, int i, bool active, uint32_t *out) {
     *out = 0;
     // state of the lane's walk: 0 walking, 1 settled, 2 left to the general walk  (an integer, not two bools: the
@@ -293,42 +299,56 @@ CCT_HD bool bucket_probe_quick(const BucketView &v, int i, bool active, uint32_t
     uint32_t state = 1;
     const SortEnt *pj = v.ent + i;
     SortEnt e{0u, 0u};
-    int s = 0, limit = 0;
+    int s = 0, limit = 0, best = 2, bdist = 0;
     uint32_t quad = 0;
     if (active) {
         const SortEnt me = load_ent(pj);
         s = ent_pos(me);
         quad = me.q;
         limit = s - kMaxDist;
+        const int look = v.n - s;
         if (me.a & kEntFirst) state = 1;  // no chain: no match, whatever the budget
-        else if ((me.a & kEntRun) || v.n - s < 8) state = 2;  // (the loop assumes a length cap >= 8)
+        else if (me.a & kEntRun) {
+            state = 2;
+            const uint32_t ri = load_u32(v.runs + s);
+            const int cap = look < kMaxMatch ? look : kMaxMatch;
+            if ((int)(ri & 0xFFFFu) + 1 >= cap && (ri >> 16) != 0 && s >= 2) { best = cap; bdist = 1; state = 1; }
+        } else if (look < 8) state = 2;  // (the loop assumes a length cap >= 8)
         else {
             e = load_ent(--pj);
             state = s - ent_pos(e) > kMaxDist ? 1u : 0u;  // deflate_slow's test on hash_head
         }
     }
-    int best = 2, bdist = 0, chain = kChainGood;
-    while (CCT_WARP_ANY(state == 0)) {
-        if (state == 0) {  // (one short divergent region per round: everything else is selects)
-            CCT_COUNT(3);
-            const uint32_t ea = e.a, x = e.q ^ quad;
-            const int cur = (int)(ea & kEntPos);
-            int len = (x & 0xFFFFFFu) == 0 ? kMinMatch : 0;
-            uint32_t st = (ea & kEntFirst) ? 1u : 0u;  // the lowest position of the bucket: the chain ends after it
-            if (ea & kEntRun) st = 2;                   // a run member: the general walk takes over
-            else if (x == 0) {
+    // The candidates are visited in rounds of 32; a lane notes in `quads` (bit k = k-th candidate of the round) which
+    // ones match four bytes.  After the round those are measured; kChainGood / 32 rounds exhaust the quartered budget.
+    const SortEnt *round_top = pj;  // the first candidate of the round
+    for (int round = 0; CCT_WARP_ANY(state == 0); round++) {
+        if (round == kChainGood / 32) { if (state == 0) state = 2; break; }  // more than 1024 candidates: the budgets may differ
+        uint32_t quads = 0;
+        round_top = pj;
+        for (uint32_t bit = 1; bit != 0 && CCT_WARP_ANY(state == 0); bit <<= 1) {
+            if (state == 0) {
+                CCT_COUNT(3);
+                const uint32_t ea = e.a, x = e.q ^ quad;
+                if ((x & 0xFFFFFFu) == 0 && best < kMinMatch) { best = kMinMatch; bdist = s - (int)(ea & kEntPos); }
+                if (x == 0) quads |= bit;
+                if (ea >= kEntFirst) state = (ea & kEntRun) ? 2u : 1u;  // a run member: the general walk takes over;
+                else {                                                  // the lowest position of the bucket: the chain ends
+                    e = load_ent(--pj);
+                    if (ent_pos(e) <= limit) state = 1;  // the distance limit
+                }
+            }
+        }
+        while (CCT_WARP_ANY(quads != 0 && state != 2)) {  // nearest first: a later candidate must be strictly longer
+            if (quads != 0 && state != 2) {
+                const int k = count_trailing_zeros(quads);
+                quads &= quads - 1;
+                const int cur = ent_pos(load_ent(round_top - k));
                 const uint32_t y = load_u32_unaligned(v.w + cur + 4) ^ load_u32_unaligned(v.w + s + 4);
-                if (y == 0) st = 2;  // eight bytes match
-                len = 4 + (count_trailing_zeros(y | 0x80000000u) >> 3);
+                if (y == 0) state = 2;  // eight bytes match: the general walk counts the rest
+                const int len = 4 + (count_trailing_zeros(y | 0x80000000u) >> 3);  // (< 8 <= cap: never the maximum length)
+                if (len > best) { best = len; bdist = s - cur; }
             }
-            if (len > best) { best = len; bdist = s - cur; }  // (len < 8 <= cap: never the maximum length)
-            if (st == 0) {
-                e = load_ent(--pj);
-                chain--;
-                if (ent_pos(e) <= limit) st = 1;  // the distance limit comes before the budget
-                else if (chain == 0) st = 2;      // more than 1024 candidates: the two budgets may differ
-            }
-            state = st;
         }
     }
     if (state == 1 && best >= kMinMatch) *out = mtab_pack(best, bdist);
