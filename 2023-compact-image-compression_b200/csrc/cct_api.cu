@@ -546,6 +546,7 @@ int cct_inflate_batch(const uint8_t *d_in, size_t in_stride, const int32_t *d_in
 namespace {
 
 struct HostCtx {
+    std::mutex mu;  // one host-buffer call at a time per device; calls to different devices run side by side
     int dev = -1;
     cudaStream_t st = nullptr, st2 = nullptr, up = nullptr, down = nullptr;  // kernels (two lanes), host->device copies, device->host copies
     cudaEvent_t ready = nullptr, carry[2] = {nullptr, nullptr};
@@ -594,13 +595,40 @@ struct HostCtx {
     void two_lanes(PassHooks &h, int slot) const { h.alt_stream = st2; h.alt_ws = buf[slot]; h.ready = ready; h.carry[0] = carry[0]; h.carry[1] = carry[1]; }
 };
 
-std::mutex g_ctx_mu;
+std::mutex g_ctx_mu;  // guards the map only
 std::map<int, HostCtx> g_ctx;
+
+// The host entry points switch to the requested device and give the caller's current device back when they return.
+struct DeviceGuard {
+    int prev = -1;
+    DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; } }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// Pageable caller memory is page-locked for the duration of a call (cudaHostRegister): copies from pageable memory go
+// through the driver's staging buffer and block the host, which would run the passes of the pipeline one after the
+// other.  Memory that is already pinned (cudaHostAlloc, torch pin_memory) is left alone.  CCT_HOST_PIN=0 turns it off.
+struct HostPin {
+    void *p = nullptr;
+    HostPin(const void *ptr, size_t bytes) {
+        static const bool on = [] { const char *e = getenv("CCT_HOST_PIN"); return !e || atoi(e) != 0; }();
+        if (!on || !ptr || bytes < ((size_t)1 << 20)) return;
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return; }
+        if (a.type != cudaMemoryTypeUnregistered) return;
+        if (cudaHostRegister(const_cast<void *>(ptr), bytes, cudaHostRegisterDefault) == cudaSuccess) p = const_cast<void *>(ptr);
+        else cudaGetLastError();
+    }
+    ~HostPin() { if (p) cudaHostUnregister(p); }
+    HostPin(const HostPin &) = delete;
+    HostPin &operator=(const HostPin &) = delete;
+};
 
 int get_ctx(int device, HostCtx **out) {
     if (cct_device_count() == 0) return CCT_E_NO_DEVICE;
     if (device < 0) CK(cudaGetDevice(&device));
     CK(cudaSetDevice(device));
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
     HostCtx &c = g_ctx[device];
     if (c.dev < 0) {
         c.dev = device;
@@ -665,16 +693,18 @@ int cct_encode_host(const uint16_t *h_px, int B, int rows, int cols, uint32_t fl
     int rc = check_shape(B, rows, cols);
     if (rc != CCT_OK) return rc;
     if (!h_offsets || (B > 0 && (!h_px || !h_out || !h_status))) return CCT_E_ARG;
-    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    DeviceGuard restore;
     HostCtx *c = nullptr;
     rc = get_ctx(device, &c);
     if (rc != CCT_OK) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
     h_offsets[0] = 0;
     if (B == 0) return CCT_OK;
     const size_t n_px = (size_t)rows * cols;
     std::vector<int> starts;
     const int per = host_schedule(B, n_px, starts, false), n_pass = (int)starts.size() - 1;
     const size_t arena = std::min(out_cap, (size_t)B * cct_file_bound(rows, cols));
+    HostPin pin_px(h_px, (size_t)B * n_px * 2), pin_out(h_out, arena), pin_off(h_offsets, (size_t)(B + 1) * 8);
     const size_t ws_bytes = cct_encode_workspace_bytes(per, rows, cols, flags);
     if ((rc = c->ensure(0, (size_t)B * n_px * 2))) return rc;
     if ((rc = c->ensure(1, std::max<size_t>(arena, 16)))) return rc;
@@ -737,14 +767,16 @@ int cct_decode_host(const uint8_t *h_in, const int64_t *h_offsets, int B, int ro
     int rc = check_shape(B, rows, cols);
     if (rc != CCT_OK) return rc;
     if (B > 0 && (!h_in || !h_offsets || !h_px || !h_status)) return CCT_E_ARG;
-    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    DeviceGuard restore;
     HostCtx *c = nullptr;
     rc = get_ctx(device, &c);
     if (rc != CCT_OK) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
     if (B == 0) return CCT_OK;
     const size_t n_px = (size_t)rows * cols;
     const int64_t base = h_offsets[0], total = h_offsets[B] - base;
     if (total < 0) return CCT_E_ARG;
+    HostPin pin_in(h_in + base, (size_t)total), pin_px(h_px, (size_t)B * n_px * 2);
     for (int i = 0; i < B; i++) if (h_offsets[i + 1] < h_offsets[i]) return CCT_E_ARG;
     std::vector<int> starts;
     const int per = host_schedule(B, n_px, starts, true), n_pass = (int)starts.size() - 1;

@@ -395,6 +395,7 @@ __global__ void __launch_bounds__(128) k_dec_rawcopy(const uint8_t *__restrict__
 // tagged bytes before it, so a chunk is summarised once, not once per possible entry state.
 constexpr int kOpsWarps = 4;
 constexpr int kOpsGroup = 128;  // bytes per warp step
+constexpr int kOpsLookBack = 2048;  // bytes a chunk looks back for its entry state before it is summarised for both
 
 __device__ __forceinline__ int op_delta(uint32_t b, uint32_t nb, bool full) {
     if (full) { const int u = (int)(((b & 0xFu) << 8) | nb); return u > 2048 ? u - 4096 : u; }  // signed(x, 12), core.py:500-506
@@ -480,35 +481,44 @@ __global__ void __launch_bounds__(32 * kOpsWarps) k_dec_ops_scan(const uint8_t *
     if (status[i] || lo >= n) return;
     const int end = n - 1, hi = lo + kOpsChunk, stop = hi < end ? hi : end;
     const uint8_t *row = payload + (int64_t)i * pstride;
-    // state entering the chunk: parity of the run of tagged bytes that ends at lo - 1
+    // state entering the chunk: parity of the run of tagged bytes that ends at lo - 1.  The look-back is bounded
+    // (a crafted payload of FULL-tag look-alikes would otherwise make every chunk rescan all that precedes it): when
+    // kOpsLookBack bytes do not settle the parity, the chunk is summarised for both entry states and k_dec_ops_link,
+    // which walks the chunks in order, picks the true one.
     uint32_t carry = 0;
-    for (int back = lo - 1; back >= 0; back -= 32) {
+    bool both = lo > 0;
+    for (int back = lo - 1, step = 0; back >= 0 && step < kOpsLookBack / 32; back -= 32, step++) {
         const int p = back - lane;
         const uint32_t t = __ballot_sync(0xffffffffu, p >= 0 && (__ldg(row + p) & 0xF0u) == 0xE0u);
         const int run = __ffs((int)~t) - 1;  // -1: all 32 tagged
-        if (run >= 0) { carry ^= (uint32_t)run & 1u; break; }
+        if (run >= 0) { carry ^= (uint32_t)run & 1u; both = false; break; }
     }
-    OpsReader rd;
-    rd.init(row, pstride, lo, lane);
-    int cnt = 0, sum = 0;
-    for (int g = 0; g < kOpsChunk / kOpsGroup && lo + kOpsGroup * g < stop; g++) {
-        uint32_t nb0;
-        const uint32_t word = rd.step(g, nb0);
-        const int pos0 = lo + kOpsGroup * g;
-        const bool edge = pos0 + kOpsGroup > stop || pos0 + kOpsGroup >= end;  // (warp-uniform)
-        const OpsLane L = edge ? ops_lane<true>(word, nb0, pos0 + 4 * lane, stop, end, carry, lane)
-                               : ops_lane<false>(word, nb0, pos0 + 4 * lane, stop, end, carry, lane);
-        cnt += __popc(L.ops);
-        sum += L.d[0] + L.d[1] + L.d[2] + L.d[3];
-    }
+    for (int e = 0; e < (both ? 2 : 1); e++) {
+        if (both) carry = (uint32_t)e;
+        const uint32_t entry = carry;
+        OpsReader rd;
+        rd.init(row, pstride, lo, lane);
+        int cnt = 0, sum = 0;
+        for (int g = 0; g < kOpsChunk / kOpsGroup && lo + kOpsGroup * g < stop; g++) {
+            uint32_t nb0;
+            const uint32_t word = rd.step(g, nb0);
+            const int pos0 = lo + kOpsGroup * g;
+            const bool edge = pos0 + kOpsGroup > stop || pos0 + kOpsGroup >= end;  // (warp-uniform)
+            const OpsLane L = edge ? ops_lane<true>(word, nb0, pos0 + 4 * lane, stop, end, carry, lane)
+                                   : ops_lane<false>(word, nb0, pos0 + 4 * lane, stop, end, carry, lane);
+            cnt += __popc(L.ops);
+            sum += L.d[0] + L.d[1] + L.d[2] + L.d[3];
+        }
 #pragma unroll
-    for (int o = 16; o; o >>= 1) { cnt += __shfl_xor_sync(0xffffffffu, cnt, o); sum += __shfl_xor_sync(0xffffffffu, sum, o); }
-    if (lane == 0) {
-        // both entry slots carry the one true summary (ops_link_chunks starts from state 0 and follows exit_state, which
-        // reproduces `entry` for every chunk); a FULL op begun on the last byte of the chunk ends in the next one
-        OpsChunkSum &o = cs[(int64_t)i * max_chunks + c];
-        const uint8_t ex = (uint8_t)(hi < end ? carry : 0u);
-        o.nops[0] = o.nops[1] = cnt; o.dsum[0] = o.dsum[1] = sum; o.exit_state[0] = o.exit_state[1] = ex;
+        for (int o = 16; o; o >>= 1) { cnt += __shfl_xor_sync(0xffffffffu, cnt, o); sum += __shfl_xor_sync(0xffffffffu, sum, o); }
+        if (lane == 0) {
+            // a settled chunk stores its one true summary in both entry slots (ops_link_chunks starts from state 0 and
+            // follows exit_state, which reproduces `entry` for every chunk); a FULL op begun on the last byte of the
+            // chunk ends in the next one
+            OpsChunkSum &o = cs[(int64_t)i * max_chunks + c];
+            const uint8_t ex = (uint8_t)(hi < end ? carry : 0u);
+            for (uint32_t slot = both ? entry : 0u; slot <= (both ? entry : 1u); slot++) { o.nops[slot] = cnt; o.dsum[slot] = sum; o.exit_state[slot] = ex; }
+        }
     }
 }
 

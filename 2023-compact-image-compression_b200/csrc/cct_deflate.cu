@@ -27,7 +27,7 @@ namespace cct {
 #define CCT_WALK_WIN 1024
 #endif
 constexpr int kWalkWin = CCT_WALK_WIN;  // positions per speculative parse window
-constexpr int kHsBins = 128;   // bins of the first sort pass: the top 7 bits of the hash
+constexpr int kHsBins = 128;   // bins of the first sort pass (sort_digit1)
 constexpr int kHsTile = 4096;  // positions per tile of the first sort pass
 
 static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
@@ -199,12 +199,14 @@ __global__ void __launch_bounds__(32 * kRunWarps) k_run_counts(const uint8_t *__
 // ------------------------------------------------------------------ k_hs_*: positions sorted by (hash, position)
 // The chain members of a stream (positions 1 .. n-3) are sorted by their 15-bit hash, stably, so that every hash
 // bucket lists its positions in increasing order -- zlib's chain, read backwards (deflate_core.cuh, "longest_match
-// over hash-sorted positions").  Two radix passes, most significant digit first:
-//   pass 1  by the top 7 bits (128 bins), the usual three launches over tiles of kHsTile positions:
+// over hash-sorted positions").  The order of the buckets among themselves is irrelevant, so the sort key is the hash
+// re-expressed as two digits that spread a CT payload evenly (sort_digit1 / sort_digit2 in deflate_core.cuh: the top
+// seven bits alone put two thirds of the positions into bins too large for one chunk of pass 2).  Two radix passes:
+//   pass 1  by the 7-bit digit (128 bins), the usual three launches over tiles of kHsTile positions:
 //           k_hs_hist   per tile: how many positions fall into each bin
 //           k_hs_scan   per stream: bin starts, and for every tile the offset of its share of each bin
 //           k_hs_split  per tile: (position, first four bytes) written to p1[] at bin start + offset + rank inside the tile
-//   pass 2  by the low 8 bits, one warp per (stream, bin): digit histogram, scan, ranked scatter of the finished
+//   pass 2  by the 8-bit digit, one CTA per (stream, bin): digit histogram, scan, ranked scatter of the finished
 //           8-byte entries (position, flags, first four bytes) into ent[] -- a bin is a contiguous piece of p1[] and of
 //           ent[], and is small enough (n / 128 positions on average) that its second read comes from L1/L2.  The
 //           payload itself is read once, coalesced, by pass 1.
@@ -261,7 +263,7 @@ __global__ void __launch_bounds__(kHsThreads) k_hs_hist(const uint8_t *__restric
     for (int r = 0; r < kHsRows; r++) {
         const int off = r * kHsThreads + threadIdx.x, p = base + off;
         const bool valid = p >= 1 && p + 2 < n;
-        const uint32_t d = hs_hash_at(sm, off) >> 8;
+        const uint32_t d = sort_digit1(hs_hash_at(sm, off));
         const uint32_t d0 = __shfl_sync(kAll, d, 0);
         if (__all_sync(kAll, valid && d == d0)) {  // a run: one add for the warp
             if ((threadIdx.x & 31) == 0) atomicAdd(&hist[d0], 32u);
@@ -290,7 +292,7 @@ __global__ void __launch_bounds__(kHsBins) k_hs_scan(const int32_t *__restrict__
     if (d == kHsBins - 1) binbase[(int64_t)stream * (kHsBins + 1) + kHsBins] = start + run;
 }
 
-__global__ void __launch_bounds__(kHsThreads) k_hs_split(const uint8_t *__restrict__ in, int64_t in_stride,
+__global__ void __launch_bounds__(kHsThreads, 6) k_hs_split(const uint8_t *__restrict__ in, int64_t in_stride,
                                                          const int32_t *__restrict__ in_len, const uint32_t *__restrict__ thist,
                                                          int max_tiles, SortEnt *__restrict__ p1_all, int64_t stride) {
     __shared__ HsTileSmem sm;
@@ -309,7 +311,7 @@ __global__ void __launch_bounds__(kHsThreads) k_hs_split(const uint8_t *__restri
     for (int r = 0; r < kHsRows; r++) {
         const int off = (wid * kHsRows + r) * 32 + lane, p = base + off;
         const bool valid = p >= 1 && p + 2 < n;
-        const uint32_t d = hs_hash_at(sm, off) >> 8;
+        const uint32_t d = sort_digit1(hs_hash_at(sm, off));
         const unsigned peers = key_peers<7>(d, valid);
         uint32_t old = 0;
         if (valid) old = wc[wid][d];
@@ -358,26 +360,29 @@ __device__ __forceinline__ void bin_rank_chunk(BinSmem &sm, const uint2 *__restr
                                                uint32_t (&key)[kBinRows]) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned below = (1u << lane) - 1u;
+    const int w0 = c0 + wid * kBinRows * 32;  // the warp's first entry
 #pragma unroll
     for (int r = 0; r < kBinRows; r++) {
-        const int k = c0 + (wid * kBinRows + r) * 32 + lane;
+        const int k = w0 + r * 32 + lane;
         pq[r] = k < S ? __ldg(src + k) : make_uint2(0xFFFFFFFFu, 0u);
+        key[r] = 0xFFFFFFFFu;
     }
 #pragma unroll
     for (int r = 0; r < kBinRows; r++) {
+        if (w0 + r * 32 >= S) break;  // (warp-uniform: the rows past the end of the bin cost nothing)
         const bool valid = pq[r].x != 0xFFFFFFFFu;
-        const uint32_t d = hash_quad(pq[r].y) & 0xFFu;
+        const uint32_t d = sort_digit2(hash_quad(pq[r].y));
         const unsigned peers = key_peers<8>(d, valid);
         uint32_t old = 0;
         if (valid) old = sm.wc[wid][d];
         __syncwarp();
         if (valid && (peers >> lane) == 1u) sm.wc[wid][d] = old + (uint32_t)__popc(peers);  // the highest peer books the group
         __syncwarp();
-        key[r] = valid ? (d | ((old + (uint32_t)__popc(peers & below)) << 8)) : 0xFFFFFFFFu;
+        if (valid) key[r] = d | ((old + (uint32_t)__popc(peers & below)) << 8);
     }
 }
 
-__global__ void __launch_bounds__(kBinThreads) k_hs_bins(const uint32_t *__restrict__ binbase, const SortEnt *__restrict__ p1_all,
+__global__ void __launch_bounds__(kBinThreads, 5) k_hs_bins(const uint32_t *__restrict__ binbase, const SortEnt *__restrict__ p1_all,
                                                          SortEnt *__restrict__ ent_all, int64_t stride, int total_bins,
                                                          uint32_t *__restrict__ next_unit) {
     __shared__ BinSmem sm;
@@ -409,13 +414,13 @@ __global__ void __launch_bounds__(kBinThreads) k_hs_bins(const uint32_t *__restr
             sm.run[tid] = t;
         } else {
             for (int k0 = 0; k0 < S; k0 += kBinThreads * 4) {
-                uint32_t q[4];
+                uint2 q[4];
 #pragma unroll
-                for (int r = 0; r < 4; r++) { const int k = k0 + r * kBinThreads + tid; q[r] = k < S ? __ldg(src + k).y : 0u; }
+                for (int r = 0; r < 4; r++) { const int k = k0 + r * kBinThreads + tid; q[r] = k < S ? __ldg(src + k) : make_uint2(0u, 0u); }
 #pragma unroll
                 for (int r = 0; r < 4; r++) {
                     const bool valid = k0 + r * kBinThreads + tid < S;
-                    const uint32_t d = hash_quad(q[r]) & 0xFFu;
+                    const uint32_t d = sort_digit2(hash_quad(q[r].y));
                     const uint32_t d0 = __shfl_sync(kAll, d, 0);
                     if (__all_sync(kAll, valid && d == d0)) { if (lane == 0) atomicAdd(&sm.run[d0], 32u); }  // a run: one add for the warp
                     else if (valid) atomicAdd(&sm.run[d], 1u);
@@ -472,7 +477,7 @@ __global__ void __launch_bounds__(kBinThreads) k_hs_bins(const uint32_t *__restr
 // by position: mlo[p] = the entry for chain budget 4096, with kProbeHiDiff set where the budget-1024 entry differs (then
 // it is written to mhi[p]; otherwise mhi[p] is left alone).
 constexpr int kBprobeThreads = 256;
-__global__ void __launch_bounds__(kBprobeThreads) k_bprobe(const uint8_t *__restrict__ in, int64_t in_stride,
+__global__ void __launch_bounds__(kBprobeThreads, 6) k_bprobe(const uint8_t *__restrict__ in, int64_t in_stride,
                                                            const int32_t *__restrict__ in_len, const SortEnt *__restrict__ ent_all,
                                                            const uint32_t *__restrict__ runs_all, uint32_t *__restrict__ mlo_all,
                                                            uint32_t *__restrict__ mhi_all, int64_t stride) {
@@ -490,16 +495,17 @@ __global__ void __launch_bounds__(kBprobeThreads) k_bprobe(const uint8_t *__rest
     for (int i0 = blockIdx.x * kBprobeThreads + (threadIdx.x & ~31); i0 < members; i0 += gridDim.x * kBprobeThreads) {
         const int i = i0 + lane;
         const bool valid = i < members;
+        const SortEnt me = valid ? load_ent(v.ent + i) : SortEnt{kEntFirst, 0u};
         uint32_t lo, hi;
-        const bool settled = bucket_probe_quick(v, i, valid, &lo);
+        const bool settled = bucket_probe_quick(v, i, me, valid, &lo);
         hi = lo;
         if (__any_sync(0xffffffffu, !settled)) {
             uint32_t glo, ghi;
-            bucket_probe(v, i, !settled, &glo, &ghi);
+            bucket_probe(v, i, me, !settled, &glo, &ghi);
             if (!settled) { lo = glo; hi = ghi; }
         }
         if (valid) {
-            const int p = ent_pos(load_ent(v.ent + i));
+            const int p = ent_pos(me);
             if (lo != hi) { mhi[p] = hi; lo |= kProbeHiDiff; }
             mlo[p] = lo;
         }
@@ -719,7 +725,9 @@ __global__ void __launch_bounds__(32) k_block_build(const uint32_t *__restrict__
     BlockDesc *d = reinterpret_cast<BlockDesc *>(sm.wk.lt.freq);
     if (lane == 0) {
         sm.wk.lt.freq[256] = 1;
-        build_block(sm.wk, d, pos_end - pos_begin, blk == nf);
+        // loop top of the iteration that flushes the block: the start of its last symbol + 1, or the end of the input
+        const int64_t top = blk < nf ? (int64_t)pos_end - sym_advance(sy[ns - 1]) + 1 : (int64_t)in_len[stream];
+        build_block(sm.wk, d, pos_end - pos_begin, blk == nf, (int64_t)pos_begin >= window_base_at(top, in_len[stream]));
         d->sym_begin = sym_begin; d->nsym = ns; d->pos_begin = pos_begin;
     }
     __syncwarp();

@@ -118,13 +118,22 @@ CCT_HD int match_extend(const uint8_t *a, const uint8_t *b, int from, int cap) {
 // jumps over its lower members; the chain budget and the distance limit are charged as if every member had been
 // visited.  "Whatever follows" starts with the byte after either run: the payload is compared only when they agree.
 // The run lengths around a position come from runs[p] = rl | rb << 16 (the bytes equal to w[p] immediately after /
-// before p, both capped at 65535), read only on a run member.  A single candidate is compared through the four
-// payload bytes in its entry: one that merely shares the hash, or matches exactly three bytes, never touches the payload.
+// before p, both capped at 65535), read only on a run member.  (Carrying the counts in the entries of run members
+// instead saves the walk a dependent load and measured 1 ms faster there, but cost the two sort passes 1.7 ms.)
+// A single candidate is compared through the four payload bytes in its entry: one that merely shares the hash, or
+// matches exactly three bytes, never touches the payload.
 constexpr uint32_t kEntRun = 0x80000000u, kEntFirst = 0x40000000u, kEntPos = 0x3FFFFFFFu;
 struct alignas(8) SortEnt { uint32_t a, q; };
 CCT_HD int ent_pos(const SortEnt &e) { return (int)(e.a & kEntPos); }
 CCT_HD bool quad_is_run(uint32_t q) { return ((q ^ (q >> 8)) & 0xFFFFu) == 0; }  // bytes 0, 1 and 2 are equal
 CCT_HD uint32_t hash_quad(uint32_t q) { return (((q & 0xFFu) << 10) ^ ((q >> 3) & 0x1FE0u) ^ ((q >> 16) & 0xFFu)) & 0x7FFFu; }  // hash3 of bytes 0..2
+
+// The sort key of a position: its 15-bit hash as (digit1 << 8) | digit2.  Any bijection of the hash would do -- only the
+// positions of one bucket must end up together, in increasing order; this one folds the high bits into the low seven
+// so that the first pass of the sort fills its 128 bins evenly.
+CCT_HD uint32_t sort_digit1(uint32_t h) { return (h ^ (h >> 7)) & 0x7Fu; }
+CCT_HD uint32_t sort_digit2(uint32_t h) { return h >> 7; }
+CCT_HD uint32_t sort_key(uint32_t h) { return (sort_digit1(h) << 8) | sort_digit2(h); }
 
 CCT_HD SortEnt load_ent(const SortEnt *p) {
 #if defined(__CUDA_ARCH__)
@@ -190,14 +199,13 @@ CCT_HD uint32_t run_after(const BucketView &v, int p, int rl) {
 // decisions, in the same order, as zlib's loop: a candidate replaces the best only when strictly longer, the
 // distance limit ends the walk before the budget does, a match of the maximum useful length ends it at once.
 // This is the general walk; bucket_probe_quick below settles most targets with far fewer instructions.
-CCT_HD void bucket_probe(const BucketView &v, int i, bool active, uint32_t *lo, uint32_t *hi) {
+CCT_HD void bucket_probe(const BucketView &v, int i, const SortEnt &me, bool active, uint32_t *lo, uint32_t *hi) {
     *lo = *hi = 0;
     const SortEnt *pj = v.ent + i;  // the scan moves a pointer down the sorted array
     SortEnt e{0u, 0u};              // the candidate
     int s = 0, cap = 0, limit = 0, R = 0;
     uint32_t quad = 0, after = 0;
     if (active) {
-        const SortEnt me = load_ent(pj);
         s = ent_pos(me);
         const int look = v.n - s;
         if (look < kMinMatch || (me.a & kEntFirst)) active = false;
@@ -292,7 +300,7 @@ CCT_HD void bucket_probe(const BucketView &v, int i, bool active, uint32_t *lo, 
 //     is the longest candidate, the nearest among equals.
 //   * A position inside a byte run with at least the maximum match length still to go: its predecessor matches that
 //     much, at distance 1, and nothing can beat it.
-CCT_HD bool bucket_probe_quick(const BucketView &v, int i, bool active, uint32_t *out) {
+CCT_HD bool bucket_probe_quick(const BucketView &v, int i, const SortEnt &me, bool active, uint32_t *out) {
     *out = 0;
     // state of the lane's walk: 0 walking, 1 settled, 2 left to the general walk  (an integer, not two bools: the
     // compiler keeps bools that live across the loop as packed bytes and spends a third of the loop shuffling them)
@@ -302,7 +310,6 @@ CCT_HD bool bucket_probe_quick(const BucketView &v, int i, bool active, uint32_t
     int s = 0, limit = 0, best = 2, bdist = 0;
     uint32_t quad = 0;
     if (active) {
-        const SortEnt me = load_ent(pj);
         s = ent_pos(me);
         quad = me.q;
         limit = s - kMaxDist;
@@ -727,10 +734,26 @@ struct BlockWork {  // scratch for build_block (shared or local memory)
     Tree lt; SmallTree dt, bt; TreeScratch sc;
 };
 
+// Start of zlib's 64 KiB window when deflate_slow's loop stands at position t (deflate.c fill_window): the window slides
+// by 32 KiB at the first loop top where fewer than MIN_LOOKAHEAD (262) bytes are left in it -- or, once the input is
+// exhausted, at every loop top -- and strstart has reached wsize + MAX_DIST (65274) inside it.  A block whose first byte
+// lies before the window (block_start < 0) cannot be emitted as a stored block (_tr_flush_block: buf == NULL).  The loop
+// top of the iteration that flushes a block is the start of the block's last symbol + 1 (the end of input for the last
+// block).
+CCT_HD int64_t window_base_at(int64_t t, int64_t n) {
+    int64_t k = t >= 65275 ? (t - 65275) / 32768 + 1 : 0;  // slides that have certainly happened
+    for (;; k++) {
+        const int64_t base = 32768 * k;
+        const int64_t thr = n >= base + 65536 ? base + 65275 : (base + 65274 > n - 261 ? base + 65274 : n - 261);
+        if (t < thr) return base;
+    }
+}
+
 // lt.freq / dt.freq must hold the block's symbol frequencies (incl. freq[256] = 1) on entry, every
-// other field zero.  Fills desc->type/last/stored_len/hdr/hdr_bits/body_bits and the code tables.  `desc` is
+// other field zero; can_store = the block's first byte is still inside zlib's window when it is flushed.  Fills
+// desc->type/last/stored_len/hdr/hdr_bits/body_bits and the code tables.  `desc` is
 // written only after the three trees are built, so it may occupy the storage of wk.lt.freq / wk.lt.dad.
-CCT_HDN inline void build_block(BlockWork &wk, BlockDesc *desc, uint32_t stored_len, uint32_t last) {
+CCT_HDN inline void build_block(BlockWork &wk, BlockDesc *desc, uint32_t stored_len, uint32_t last, bool can_store) {
     const uint8_t bl_order[kBLCodes] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
     wk.sc.opt_len = 0; wk.sc.static_len = 0;
     build_tree(wk.sc, wk.lt, 0);
@@ -747,7 +770,7 @@ CCT_HDN inline void build_block(BlockWork &wk, BlockDesc *desc, uint32_t stored_
     desc->stored_len = stored_len; desc->last = last;
     for (int i = 0; i < kHdrWords; i++) desc->hdr[i] = 0;
     HdrBits hb{desc->hdr, 0};
-    if ((int64_t)desc->stored_len + 4 <= opt_lenb) {
+    if (can_store && (int64_t)desc->stored_len + 4 <= opt_lenb) {
         desc->type = 0;
         hb.put((0u << 1) + desc->last, 3);
         desc->body_bits = 0;

@@ -107,11 +107,28 @@ def stage_of(kernel):
         return "front"
     if kernel in ("k_gather_stats", "k_mesh", "k_emit"):
         return "front"        # reads 2N, writes P
-    if kernel in ("k_dec_inflate",):
+    if kernel.startswith(("k_inflate", "k_lz_expand", "k_adler_check")):
         return "inflate"      # reads F, writes P (K6)
     if kernel.startswith("k_dec_"):
         return "back"         # reads P, writes 2N (K7-K8)
     return "deflate"          # reads P, writes F (K5)
+
+
+def distinct_slices(B, workers, sweep=False):
+    """Distinct synthetic slices generated per GPU (the batch tiles them when the host is too small to generate all)."""
+    distinct = min(B, 512) if sweep else B
+    if B * 0.04 / workers > 90:  # keep generation within ~1.5 min on small hosts: tile a smaller distinct set
+        distinct = max(64, int(90 * workers / 0.04) // 64 * 64)
+    return min(distinct, B)
+
+
+def workload_config(B, n, world, distinct):
+    """The `config` object of the JSON line: the same for both arms (the reference arm times a sample of it)."""
+    raw = 2 * B * n * n
+    return {"workload": (f"{B} synth_ct {n}x{n} 12-bit slices per GPU (configs[1]), encode then decode" if WORKLOAD == "ct"
+                         else f"{B} synth_radiograph {n}x{n} 16-bit slices per GPU (configs[3]), encode then decode"),
+            "slices_per_gpu": B, "distinct_slices_per_gpu": int(distinct), "l2": f"inputs larger than L2 ({raw / 1e9:.2f} GB raw per GPU)",
+            "parallelism": f"batch sharded over {world} GPU(s), no collective on the data path"}
 
 
 def main():
@@ -157,7 +174,7 @@ def main():
         line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "MPix/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": (te + td) / args.steps * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16", "data": "synthetic",
-                "config": {"workload": f"{B} synth_ct {n}x{n} 12-bit slices per GPU (configs[1])", "sample_slices": S},
+                "config": workload_config(B, n, world, distinct_slices(B, max(1, min(32, cores // max(world, 1))))),
                 "encode_mpix_s": S * n_px * args.steps / te / 1e6, "decode_mpix_s": S * n_px * args.steps / td / 1e6,
                 "cpu_baseline": {"value": val, "unit": "MPix/s", "cores": nthreads, "kind": "port",
                                  "sample": f"{S} synth_ct slices x {args.steps} steps, oracle C port + libz, {nthreads} threads"},
@@ -168,11 +185,7 @@ def main():
 
     # ---- our arm -------------------------------------------------------------------------------------------
     workers = max(1, min(32, cores // max(world, 1)))
-    distinct = B
-    if args.decode_sweep:
-        distinct = min(B, 512)
-    if B * 0.04 / workers > 90:  # keep generation within ~1.5 min on small hosts: tile a smaller distinct set
-        distinct = max(64, int(90 * workers / 0.04) // 64 * 64)
+    distinct = distinct_slices(B, workers, args.decode_sweep)
     t0 = time.time()
     base = gen_batch([(rank * B + i) % (1 << 31) for i in range(min(distinct, B))], n, workers)
     imgs = base if len(base) == B else np.concatenate([base] * ((B + len(base) - 1) // len(base)))[:B]
@@ -363,10 +376,7 @@ def main():
     line = {"metric": METRIC, "value": total_px / t_all / 1e6, "unit": "MPix/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t_all / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u16", "data": "synthetic",
-            "config": {"workload": (f"{B} synth_ct {n}x{n} 12-bit slices per GPU (configs[1]), encode then decode" if WORKLOAD == "ct"
-                                    else f"{B} synth_radiograph {n}x{n} 16-bit slices per GPU (configs[3]), encode then decode"),
-                       "slices_per_gpu": B, "distinct_slices_per_gpu": int(len(base)), "l2": f"inputs larger than L2 ({raw / 1e9:.2f} GB raw per GPU)",
-                       "parallelism": f"batch sharded over {world} GPU(s), no collective on the data path"},
+            "config": workload_config(B, n, world, len(base)),
             "encode_mpix_s": total_px / t_enc / 1e6, "decode_mpix_s": total_px / t_dec / 1e6,
             "raw_gbs": {"encode": 2 * total_px / t_enc / 1e9, "decode": 2 * total_px / t_dec / 1e9},
             "compression_ratio": raw / F_total, "roofline": roofline, "roofline_path": path, "cpu_baseline": cpu,

@@ -107,8 +107,10 @@ int cct_read_header(const uint8_t *h_file, size_t len, int *rows, int *cols, int
 
 /*
  * Host-buffer entry points (what `Encoder(config, ndarray).encode()` binds to): pixels and files live in
- * host memory; the call owns a per-device context (workspace, pinned staging, stream), copies in,
- * runs the kernels, copies out and synchronises.  device < 0 selects the current device.
+ * host memory; the call owns a per-device context (device buffers, workspace, streams), page-locks pageable caller
+ * buffers for its duration (cudaHostRegister; already pinned memory is used as it is; CCT_HOST_PIN=0 disables this),
+ * copies in, runs the kernels, copies out and synchronises.  device < 0 selects the current device; the caller's
+ * current device is restored on return, and calls for different devices may run concurrently from different threads.
  *   h_out / out_cap as above; returns CCT_E_CAPACITY if the arena is too small (h_offsets is still valid
  *   so the caller can resize and retry).
  */

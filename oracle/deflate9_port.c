@@ -315,6 +315,19 @@ static void flush_block(bitw *w, const sym_t *sym, int nsym, const uint8_t *buf,
 /* ---------------------------------------------------------------- LZ77 lazy parse (deflate_slow) */
 
 /* Optional trace of the parse: one record per emitted symbol. */
+/* Start of zlib's 64 KiB window when deflate_slow's loop stands at position t (deflate.c fill_window): the window
+ * slides by 32 KiB at the first loop top where fewer than MIN_LOOKAHEAD (262) bytes are left in it -- or, once the
+ * input is exhausted, at every loop top -- and strstart has reached wsize + MAX_DIST (65274) inside it.  A block whose
+ * first byte lies before the window (block_start < 0) cannot be emitted as a stored block (_tr_flush_block: buf == NULL). */
+static int64_t window_base_at(int64_t t, int64_t n) {
+    int64_t k = t >= 65275 ? (t - 65275) / 32768 + 1 : 0; /* slides that have certainly happened */
+    for (;; k++) {
+        int64_t base = 32768 * k;
+        int64_t thr = n >= base + 65536 ? base + 65275 : (base + 65274 > n - 261 ? base + 65274 : n - 261);
+        if (t < thr) return base;
+    }
+}
+
 typedef struct { int32_t pos; uint16_t dist; uint16_t len; } d9_symrec; /* len==0: literal at pos */
 
 static int64_t lz_parse(const uint8_t *src, int64_t n, bitw *w, d9_symrec *trace, int64_t trace_cap, int64_t *n_trace) {
@@ -330,6 +343,7 @@ static int64_t lz_parse(const uint8_t *src, int64_t n, bitw *w, d9_symrec *trace
 #define INSERT(p, hh) do { unsigned k_ = HASH(p); (hh) = head[k_]; prev[p] = (hh); head[k_] = (int32_t)(p); } while (0)
 #define TRACE(p, d, l) do { if (trace && nt < trace_cap) { trace[nt].pos = (int32_t)(p); trace[nt].dist = (uint16_t)(d); trace[nt].len = (uint16_t)(l); } nt++; } while (0)
     while (s < n) {
+        const int64_t top = s; /* strstart at the loop top: fill_window runs here, nowhere else in the iteration */
         int64_t look = n - s;
         int32_t hh = 0;
         if (look >= MIN_MATCH) INSERT(s, hh);
@@ -373,7 +387,7 @@ static int64_t lz_parse(const uint8_t *src, int64_t n, bitw *w, d9_symrec *trace
             } while (--reps != 0);
             avail = 0; match_len = MIN_MATCH - 1; s++;
             if (nsym == SYM_END) {
-                flush_block(w, sym, nsym, src + block_start, s - block_start, 0);
+                flush_block(w, sym, nsym, block_start >= window_base_at(top, n) ? src + block_start : NULL, s - block_start, 0);
                 total_sym += nsym; nsym = 0; block_start = s;
             }
         } else if (avail) {
@@ -381,7 +395,7 @@ static int64_t lz_parse(const uint8_t *src, int64_t n, bitw *w, d9_symrec *trace
             TRACE(s - 1, 0, 0);
             g_stats.n_literals++;
             if (nsym == SYM_END) {
-                flush_block(w, sym, nsym, src + block_start, s - block_start, 0);
+                flush_block(w, sym, nsym, block_start >= window_base_at(top, n) ? src + block_start : NULL, s - block_start, 0);
                 total_sym += nsym; nsym = 0; block_start = s;
             }
             s++;
@@ -394,7 +408,7 @@ static int64_t lz_parse(const uint8_t *src, int64_t n, bitw *w, d9_symrec *trace
         TRACE(n - 1, 0, 0);
         g_stats.n_literals++;
     }
-    flush_block(w, sym, nsym, src + block_start, n - block_start, 1);
+    flush_block(w, sym, nsym, block_start >= window_base_at(n, n) ? src + block_start : NULL, n - block_start, 1);
     total_sym += nsym;
     if (n_trace) *n_trace = nt;
     free(head); free(prev); free(sym);

@@ -72,7 +72,7 @@ static void sorted_reference(const uint8_t *w, int n, std::vector<SortEnt> &ent,
     runs.assign((size_t)n + 1, 0);
     for (int p = 0; p < n; p++) runs[p] = (uint32_t)rl16[p] | ((uint32_t)rb16[p] << 16);
     std::vector<std::pair<uint32_t, int>> key;
-    for (int p = 1; p + 2 < n; p++) key.push_back({hash3(w + p), p});
+    for (int p = 1; p + 2 < n; p++) key.push_back({sort_key(hash3(w + p)), p});
     std::stable_sort(key.begin(), key.end(), [](const auto &a, const auto &b) { return a.first < b.first; });
     ent.assign(key.size() + 1, SortEnt{0, 0});
     for (size_t i = 0; i < key.size(); i++) {
@@ -107,8 +107,8 @@ int64_t hs_deflate2(const uint8_t *src, int n, uint8_t *dst, int64_t cap, int pa
     for (int i = 0; i < members; i++) {
         const int p = ent_pos(ent[i]);
         uint32_t lo, hi;
-        if (bucket_probe_quick(bv, i, true, &lo)) hi = lo;
-        else bucket_probe(bv, i, true, &lo, &hi);
+        if (bucket_probe_quick(bv, i, ent[i], true, &lo)) hi = lo;
+        else bucket_probe(bv, i, ent[i], true, &lo, &hi);
         if (lo != hi) { mhi[p] = hi; lo |= kProbeHiDiff; n_incomplete++; }
         mlo[p] = lo;
     }
@@ -148,7 +148,8 @@ int64_t hs_deflate2(const uint8_t *src, int n, uint8_t *dst, int64_t cap, int pa
             if (sym_dist(sy) == 0) wk->lt.freq[sym_lc(sy)]++;
             else { wk->lt.freq[257 + len_code(sym_lc(sy))]++; wk->dt.freq[dist_code(sym_dist(sy) - 1)]++; }
         }
-        build_block(*wk, &d, d.stored_len, d.last);
+        const int64_t top = b < n_flush ? (int64_t)blk_end[b] - sym_advance(syms[d.sym_begin + d.nsym - 1]) + 1 : (int64_t)n;
+        build_block(*wk, &d, d.stored_len, d.last, (int64_t)d.pos_begin >= window_base_at(top, n));
         fill_block_tables(*wk, &d, 0, 1);
     }
     delete wk;
@@ -207,9 +208,9 @@ int64_t hs_probe_check(const uint8_t *src, int n, int64_t *steps) {
     int64_t bad = 0, quick = 0;
     for (int i = 0; i < members; i++) {
         const int p = ent_pos(ent[i]);
-        bucket_probe(bv, i, true, &lo[p], &hi[p]);
+        bucket_probe(bv, i, ent[i], true, &lo[p], &hi[p]);
         uint32_t q;
-        if (bucket_probe_quick(bv, i, true, &q)) { quick++; if (q != lo[p] || q != hi[p]) bad++; }  // the short cut agrees wherever it settles
+        if (bucket_probe_quick(bv, i, ent[i], true, &q)) { quick++; if (q != lo[p] || q != hi[p]) bad++; }  // the short cut agrees wherever it settles
     }
     if (steps) { steps[0] = cct_stat[2] - c0; steps[1] = quick; }
     for (int s = 0; s < n; s++)
@@ -231,8 +232,8 @@ void hs_match_tables(const uint8_t *src, int n, uint64_t *ent_out, uint32_t *lo_
     for (int i = 0; i < members; i++) {
         const int p = ent_pos(ent[i]);
         uint32_t lo, hi;
-        if (bucket_probe_quick(bv, i, true, &lo)) hi = lo;
-        else bucket_probe(bv, i, true, &lo, &hi);
+        if (bucket_probe_quick(bv, i, ent[i], true, &lo)) hi = lo;
+        else bucket_probe(bv, i, ent[i], true, &lo, &hi);
         if (lo != hi) { hi_out[p] = hi; lo |= kProbeHiDiff; }
         lo_out[p] = lo;
         ent_out[i] = (uint64_t)ent[i].a | ((uint64_t)ent[i].q << 32);

@@ -333,6 +333,52 @@ def _tagged_run_image(seed, rows, cols, order):
     return img.reshape(rows, cols)
 
 
+def _endless_tagged_image(seed, rows, cols, order):
+    """An op stream that is tagged bytes almost throughout: +229 per op (bytes E0 E5) on the way up, -283 (EE E5) on
+    the way down, a single DELTA op every few thousand bytes to flip the phase.  Runs of tagged bytes far longer than
+    the look-back of k_dec_ops_scan: those chunks are summarised for both entry states."""
+    rng = np.random.default_rng(seed)
+    n = rows * cols
+    vals = np.empty(n, dtype=np.int64)
+    v, k, up = 300, 0, True
+    next_flip = int(rng.integers(1500, 4000))
+    while k < n:
+        if k == next_flip:
+            v += 1 if v < 60000 else -1
+            next_flip += int(rng.integers(1500, 4000))
+        elif up:
+            if v + 229 > 65535: up = False; continue
+            v += 229
+        else:
+            if v - 283 < 0: up = True; continue
+            v -= 283
+        vals[k] = v; k += 1
+    img = np.empty(n, dtype=np.uint16)
+    img[order] = vals.astype(np.uint16)
+    return img.reshape(rows, cols)
+
+
+@pytest.mark.parametrize("shape,flags", [((128, 128), 5), ((128, 128), 4), ((256, 256), 5)])
+def test_op_stream_tagged_beyond_look_back(torch_cuda, pkg, oracle, shape, flags):
+    rows, cols = shape
+    fractal, deflate = bool(flags & 1), bool(flags & 4)
+    cfg = pkg.default_config()
+    tr = cfg["encoder"]["transforms"]
+    tr["fractal"], tr["segmentation"] = fractal, False
+    cfg["encoder"]["deflate_compression"] = deflate
+    order = oracle.curve(rows, cols).astype(np.int64) if fractal else np.arange(rows * cols)
+    for seed in range(2):
+        img = _endless_tagged_image(seed, rows, cols, order)
+        want = oracle.encode(img, fractal=fractal, seg=False, deflate=deflate)
+        payload = zlib.decompress(want[13:]) if deflate else want[13:]
+        tagged = (np.frombuffer(payload, dtype=np.uint8) & 0xF0) == 0xE0
+        longest = max(len(r) for r in "".join("1" if t else "0" for t in tagged).split("0"))
+        assert longest > 2048 + 1024, longest
+        assert pkg.Encoder(cfg, img).encode() == want
+        assert np.array_equal(oracle.decode(want), img)
+        assert pkg.Decoder(cfg, want).decode() == img.tobytes()
+
+
 @pytest.mark.parametrize("shape,flags", [((128, 128), 7), ((128, 128), 4), ((64, 256), 5), ((512, 512), 6)])
 def test_op_stream_tagged_runs(torch_cuda, pkg, oracle, shape, flags):
     """Decode of op streams with long FULL-tag look-alike runs (SURVEY A.5's 2-state automaton at its worst)."""
@@ -360,6 +406,35 @@ def test_op_stream_tagged_runs(torch_cuda, pkg, oracle, shape, flags):
             continue
         assert np.array_equal(want_px, img)
         assert pkg.Decoder(cfg, want).decode() == img.tobytes()
+
+
+def test_second_device_in_one_process(torch_cuda, pkg, native, synth, oracle):
+    """One process driving two GPUs: opt-in shared-memory sizes and SM counts are kept per device, the host entry
+    points select the device they are given and hand the caller's current device back."""
+    torch = torch_cuda
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    imgs = np.stack([synth.synth_ct(s, 128) for s in range(6)])
+    want = [oracle.encode(im) for im in imgs]
+    for dev in (0, 1, 0):
+        d = torch.from_numpy(imgs.view(np.int16)).to(f"cuda:{dev}")
+        arena, offsets, status = pkg.encode_batch(d)
+        px, dst = pkg.decode_batch(arena, offsets, (128, 128))
+        torch.cuda.synchronize(dev)
+        h, off = arena.cpu().numpy(), offsets.cpu().numpy()
+        assert [h[off[i]:off[i + 1]].tobytes() for i in range(6)] == want, dev
+        assert torch.equal(px.view(torch.int16), d) and not status.any().item() and not dst.any().item()
+    # host-buffer entry points on the device that is not current
+    L = native.lib()
+    torch.cuda.set_device(0)
+    cap = int(L.cct_file_bound(128, 128)) * 6
+    arena = np.zeros(cap, np.uint8); off = np.zeros(7, np.int64); st = np.zeros(6, np.uint32)
+    native.check(L.cct_encode_host(imgs.ctypes.data, 6, 128, 128, 7, arena.ctypes.data, cap, off.ctypes.data, st.ctypes.data, None, 1))
+    assert [arena[off[i]:off[i + 1]].tobytes() for i in range(6)] == want
+    back = np.zeros_like(imgs); dst = np.zeros(6, np.uint32)
+    native.check(L.cct_decode_host(arena.ctypes.data, off.ctypes.data, 6, 128, 128, back.ctypes.data, dst.ctypes.data, 1))
+    assert np.array_equal(back, imgs) and not dst.any()
+    assert torch.cuda.current_device() == 0
 
 
 def test_config_batch_roundtrip_4096(torch_cuda, pkg, synth, oracle):
