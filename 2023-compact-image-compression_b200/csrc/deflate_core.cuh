@@ -333,28 +333,34 @@ CCT_HD bool bucket_probe_quick(const BucketView &v, int i, const SortEnt &me, bo
         if (round == kChainGood / 32) { if (state == 0) state = 2; break; }  // more than 1024 candidates: the budgets may differ
         uint32_t quads = 0;
         round_top = pj;
-        for (uint32_t bit = 1; bit != 0 && CCT_WARP_ANY(state == 0); bit <<= 1) {
+        for (uint32_t bit = 1; bit != 0 && CCT_WARP_ANY(state == 0); bit <<= 2) {
             if (state == 0) {
-                CCT_COUNT(3);
-                const uint32_t ea = e.a, x = e.q ^ quad;
-                if ((x & 0xFFFFFFu) == 0 && best < kMinMatch) { best = kMinMatch; bdist = s - (int)(ea & kEntPos); }
-                if (x == 0) quads |= bit;
-                if (ea >= kEntFirst) state = (ea & kEntRun) ? 2u : 1u;  // a run member: the general walk takes over;
-                else {                                                  // the lowest position of the bucket: the chain ends
-                    e = load_ent(--pj);
-                    if (ent_pos(e) <= limit) state = 1;  // the distance limit
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                for (int half = 0; half < 2; half++) {  // two candidates per vote
+                    CCT_COUNT(3);
+                    const uint32_t ea = e.a, x = e.q ^ quad;
+                    if ((x & 0xFFFFFFu) == 0 && best < kMinMatch) { best = kMinMatch; bdist = s - (int)(ea & kEntPos); }
+                    if (x == 0) quads |= bit << half;
+                    if (ea >= kEntFirst) { state = (ea & kEntRun) ? 2u : 1u; break; }  // a run member: the general walk takes over;
+                    e = load_ent(--pj);                                                // the lowest position of the bucket: the chain ends
+                    if (ent_pos(e) <= limit) { state = 1; break; }  // the distance limit
                 }
             }
         }
-        while (CCT_WARP_ANY(quads != 0 && state != 2)) {  // nearest first: a later candidate must be strictly longer
-            if (quads != 0 && state != 2) {
-                const int k = count_trailing_zeros(quads);
-                quads &= quads - 1;
-                const int cur = ent_pos(load_ent(round_top - k));
-                const uint32_t y = load_u32_unaligned(v.w + cur + 4) ^ load_u32_unaligned(v.w + s + 4);
-                if (y == 0) state = 2;  // eight bytes match: the general walk counts the rest
-                const int len = 4 + (count_trailing_zeros(y | 0x80000000u) >> 3);  // (< 8 <= cap: never the maximum length)
-                if (len > best) { best = len; bdist = s - cur; }
+        if (CCT_WARP_ANY(quads != 0 && state != 2)) {  // nearest first: a later candidate must be strictly longer
+            const uint32_t quad2 = (quads != 0 && state != 2) ? load_u32_unaligned(v.w + s + 4) : 0u;
+            while (CCT_WARP_ANY(quads != 0 && state != 2)) {
+                if (quads != 0 && state != 2) {
+                    const int k = count_trailing_zeros(quads);
+                    quads &= quads - 1;
+                    const int cur = ent_pos(load_ent(round_top - k));
+                    const uint32_t y = load_u32_unaligned(v.w + cur + 4) ^ quad2;
+                    if (y == 0) state = 2;  // eight bytes match: the general walk counts the rest
+                    const int len = 4 + (count_trailing_zeros(y | 0x80000000u) >> 3);  // (< 8 <= cap: never the maximum length)
+                    if (len > best) { best = len; bdist = s - cur; }
+                }
             }
         }
     }

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 ncu capture of selected kernels (run on the GPU box from the repository root through gpurun, one GPU).
-# Usage: profiles/capture_ncu_r02.sh <tag> <kernel regex>   -> gpurun_out/<tag>_raw.csv, <tag>_src_<kernel>.csv
+# Usage: profiles/capture_ncu_kernels.sh <tag> <kernel regex>   -> gpurun_out/<tag>_raw.csv, <tag>_src_<kernel>.csv
 set -e
 tag=${1:-cap}
 rx=${2:-k_bprobe}
