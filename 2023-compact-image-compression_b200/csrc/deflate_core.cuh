@@ -299,7 +299,8 @@ CCT_HD void bucket_probe(const BucketView &v, int i, const SortEnt &me, bool act
 //     the two lanes that need the payload would stall the other thirty.  The result does not depend on that order: it
 //     is the longest candidate, the nearest among equals.
 //   * A position inside a byte run with at least the maximum match length still to go: its predecessor matches that
-//     much, at distance 1, and nothing can beat it.
+//     much, at distance 1, and nothing can beat it.  Likewise one with more than 4096 run members below it: they all
+//     match exactly the rest of the run and use up the chain budget before anything else is seen.
 CCT_HD bool bucket_probe_quick(const BucketView &v, int i, const SortEnt &me, bool active, uint32_t *out) {
     *out = 0;
     // state of the lane's walk: 0 walking, 1 settled, 2 left to the general walk  (an integer, not two bools: the
@@ -318,8 +319,11 @@ CCT_HD bool bucket_probe_quick(const BucketView &v, int i, const SortEnt &me, bo
         else if (me.a & kEntRun) {
             state = 2;
             const uint32_t ri = load_u32(v.runs + s);
-            const int cap = look < kMaxMatch ? look : kMaxMatch;
-            if ((int)(ri & 0xFFFFu) + 1 >= cap && (ri >> 16) != 0 && s >= 2) { best = cap; bdist = 1; state = 1; }
+            const int cap = look < kMaxMatch ? look : kMaxMatch, R = (int)(ri & 0xFFFFu) + 1, rb = (int)(ri >> 16);
+            // members of the target's own run below it (position 0 is never one): they are visited first, all give R
+            const int own = rb < s - 1 ? rb : s - 1;
+            if (own >= 1 && R >= cap) { best = cap; bdist = 1; state = 1; }
+            else if (own > kChainFull) { best = R; bdist = 1; state = 1; }  // ... and exhaust either chain budget
         } else if (look < 8) state = 2;  // (the loop assumes a length cap >= 8)
         else {
             e = load_ent(--pj);
