@@ -346,7 +346,10 @@ __global__ void __launch_bounds__(kHsThreads, 6) k_hs_split(const uint8_t *__res
 //                  finished entries -- the bin's piece of ent[] is a few KB, so the 8-byte stores meet in L2.
 constexpr int kBinThreads = 256;
 constexpr int kBinWarps = kBinThreads / 32;
-constexpr int kBinRows = 8;                                  // rows (of 32 entries) per warp and chunk
+#ifndef CCT_BIN_ROWS
+#define CCT_BIN_ROWS 8
+#endif
+constexpr int kBinRows = CCT_BIN_ROWS;                       // rows (of 32 entries) per warp and chunk
 constexpr int kBinChunk = kBinThreads * kBinRows;            // 2048 entries
 struct BinSmem {
     uint32_t wc[kBinWarps][256];  // per warp: count of each digit in the chunk, then the offset of the warp's share
@@ -476,8 +479,15 @@ __global__ void __launch_bounds__(kBinThreads, 5) k_hs_bins(const uint32_t *__re
 // together, so the candidate loads are coalesced 8-byte reads of one contiguous piece of ent[].  Results are scattered
 // by position: mlo[p] = the entry for chain budget 4096, with kProbeHiDiff set where the budget-1024 entry differs (then
 // it is written to mhi[p]; otherwise mhi[p] is left alone).
-constexpr int kBprobeThreads = 256;
-__global__ void __launch_bounds__(kBprobeThreads, 6) k_bprobe(const uint8_t *__restrict__ in, int64_t in_stride,
+#ifndef CCT_BPROBE_THREADS
+#define CCT_BPROBE_THREADS 128
+#endif
+#ifndef CCT_BPROBE_CTAS
+#define CCT_BPROBE_CTAS 32
+#endif
+constexpr int kBprobeThreads = CCT_BPROBE_THREADS;
+constexpr int kBprobeCtas = CCT_BPROBE_CTAS;  // CTAs per stream (each strides over the stream's sorted entries)
+__global__ void __launch_bounds__(kBprobeThreads, 1536 / kBprobeThreads) k_bprobe(const uint8_t *__restrict__ in, int64_t in_stride,
                                                            const int32_t *__restrict__ in_len, const SortEnt *__restrict__ ent_all,
                                                            const uint32_t *__restrict__ runs_all, uint32_t *__restrict__ mlo_all,
                                                            uint32_t *__restrict__ mhi_all, int64_t stride) {
@@ -931,7 +941,7 @@ static void launch_match_tables(const uint8_t *in, int64_t in_stride, const int3
         k_hs_bins<<<(unsigned)ctas, kBinThreads, 0, st>>>(ws.binbase, ws.p1, ws.ent, ws.stride, (int)total_bins, ws.counters);
     }
     {
-        dim3 gp((unsigned)std::min<int64_t>((max_len + kBprobeThreads - 1) / kBprobeThreads, 32), (unsigned)B);
+        dim3 gp((unsigned)std::min<int64_t>((max_len + kBprobeThreads - 1) / kBprobeThreads, kBprobeCtas), (unsigned)B);
         CCT_KERNEL(k_bprobe, st);
         k_bprobe<<<gp, kBprobeThreads, 0, st>>>(in, in_stride, in_len, ws.ent, ws.runs, ws.mtab, ws.mhi, ws.stride);
     }
