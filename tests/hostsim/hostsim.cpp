@@ -383,6 +383,7 @@ uint32_t hs_decode_payload(const uint8_t *payload, int plen, int n_px, const int
 }
 
 uint32_t hs_hilbert(uint32_t n, uint32_t d) { return hilbert_d2raster(n, d); }
+int64_t hs_window_base(int64_t t, int64_t n) { return window_base_at(t, n); }
 int hs_len_code(int lc) { return len_code(lc); }
 int hs_dist_code(int d) { return dist_code(d); }
 

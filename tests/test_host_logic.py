@@ -159,6 +159,45 @@ def test_staged_deflate_on_codec_payloads(hostsim, oracle, synth, golden_cct):
         assert _hs_deflate(hostsim, p) == zlib.compress(p, 9)
 
 
+def _zlib_window_bases(n, tops):
+    """deflate.c's window bookkeeping replayed: fill_window runs at a loop top when fewer than MIN_LOOKAHEAD bytes are
+    left in the 64 KiB window and slides it by 32 KiB once strstart >= wsize + MAX_DIST.  Returns the window base in
+    effect at each of the given loop-top positions (ascending)."""
+    base, data_end, out = 0, min(n, 65536), []
+    for t in tops:
+        if data_end - t < 262:               # lookahead < MIN_LOOKAHEAD: fill_window()
+            while True:
+                if t - base >= 32768 + 32506:
+                    base += 32768
+                if data_end == n:            # avail_in == 0
+                    break
+                data_end = min(n, base + 65536)
+                if data_end - t >= 262 or data_end == n:
+                    break
+        out.append(base)
+    return out
+
+
+def test_window_base_rule(hostsim):
+    """window_base_at (the stored-block rule of build_block) against a replay of zlib's fill_window bookkeeping, for
+    loop tops every few bytes and at every slide threshold, inputs ending at awkward places."""
+    hostsim.hs_window_base.argtypes = [C.c_int64, C.c_int64]
+    hostsim.hs_window_base.restype = C.c_int64
+    rng = np.random.default_rng(9)
+    for n in (1000, 65273, 65274, 65275, 65536, 65537, 65600, 98041, 98042, 98043, 98304, 131072, 200000, 1000003):
+        tops = sorted(set(rng.integers(0, n + 1, size=400).tolist()) | {0, n} |
+                      {b + d for b in range(65270, n + 1, 32768) for d in range(0, 12) if b + d <= n} |
+                      {max(0, n - 262 + d) for d in range(-3, 4)})
+        # every loop top must be replayed in order for the bookkeeping to evolve as in zlib: walk all positions the
+        # parse could stand on (a step of at most 258) -- here simply every position, then sample
+        every = _zlib_window_bases(n, range(0, n + 1)) if n <= 200000 else None
+        for t in tops:
+            got = hostsim.hs_window_base(t, n)
+            if every is not None:
+                assert got == every[t], (n, t, got, every[t])
+            assert got % 32768 == 0 and got <= max(0, t - 32506) and (t < 65275 + got or n < got + 65536)
+
+
 def test_inflate_core(hostsim):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from test_oracle import _deflate_corpus
