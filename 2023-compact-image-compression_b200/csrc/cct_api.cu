@@ -650,7 +650,9 @@ int get_ctx(int device, HostCtx **out) {
 // hide: a quarter and a half pass for encode, whose bound is the kernels; an eighth, a quarter and a half for decode,
 // whose bound is the download of 2 bytes per pixel -- it has to start as early as possible and then never wait (the
 // first pixels cannot come before ~8 ms: one stream alone takes that long through the bit-serial inflate).
-// CCT_HOST_PASS overrides the pass size (0 = one pass), CCT_HOST_LEADS the opening ("8,4,2" = those fractions).
+// Encode also closes with a half and a quarter pass: the download of the last pass's bytes is the tail of the call.
+// CCT_HOST_PASS overrides the pass size (0 = one pass), CCT_HOST_LEADS the opening ("8,4,2" = those fractions),
+// CCT_HOST_TAILS the closing passes.
 // Returns the largest pass.
 int host_schedule(int B, size_t n_px, std::vector<int> &starts, bool decode) {
     int per = (int)std::max<size_t>(1, ((size_t)512 << 20) / (n_px * 2));
@@ -660,6 +662,12 @@ int host_schedule(int B, size_t n_px, std::vector<int> &starts, bool decode) {
     if (const char *e = getenv("CCT_HOST_LEADS")) {
         div.clear();
         for (const char *q = e; *q;) { const int v = atoi(q); if (v > 0) div.push_back(v); while (*q && *q != ',') q++; if (*q) q++; }
+    }
+    // closing passes (encode): the download of the last pass is the part nothing can hide either
+    std::vector<int> tails = decode ? std::vector<int>{} : std::vector<int>{2, 4};
+    if (const char *e = getenv("CCT_HOST_TAILS")) {
+        tails.clear();
+        for (const char *q = e; *q;) { const int v = atoi(q); if (v > 0) tails.push_back(v); while (*q && *q != ',') q++; if (*q) q++; }
     }
     starts.clear();
     starts.push_back(0);
@@ -671,8 +679,17 @@ int host_schedule(int B, size_t n_px, std::vector<int> &starts, bool decode) {
             at += lead; largest = std::max(largest, lead);
             starts.push_back(at);
         }
-        const int rest = B - at, n = (rest + per - 1) / per, each = (rest + n - 1) / n;  // equal passes after the opening
+        std::vector<int> closing;  // sizes of the closing passes, in order
+        int tail_sum = 0;
+        for (int d : tails) {
+            const int t = std::max(1, per / d);
+            if (at + tail_sum + t + per > B) break;  // keep at least one full pass in the middle
+            closing.push_back(t); tail_sum += t; largest = std::max(largest, t);
+        }
+        const int rest = B - at - tail_sum, n = (rest + per - 1) / per, each = (rest + n - 1) / n;  // equal passes in between
         for (int k = 1; k < n; k++) starts.push_back(at + k * each);
+        int pos = at + rest;
+        for (int t : closing) { starts.push_back(pos); pos += t; }
         per = std::max(largest, each);
     }
     starts.push_back(B);
