@@ -251,11 +251,13 @@ __global__ void __launch_bounds__(32 * kLzWarps) k_lz_expand(const uint32_t *__r
     const uint32_t *sy = syms + (int64_t)i * sym_stride;
     uint8_t *o = out + (int64_t)i * out_stride;
     int base = 0;
-    uint32_t s_next = lane < ns ? __ldg(sy + lane) : 0u;  // the next group's symbols are fetched a group ahead
+    uint32_t s_next = lane < ns ? __ldg(sy + lane) : 0u;  // the symbols are fetched two groups ahead
+    uint32_t s_next2 = lane + 32 < ns ? __ldg(sy + lane + 32) : 0u;
     for (int g = 0; g < ns; g += 32) {
         const int k = g + lane;
         const uint32_t s = s_next;
-        s_next = k + 32 < ns ? __ldg(sy + k + 32) : 0u;
+        s_next = s_next2;
+        s_next2 = k + 64 < ns ? __ldg(sy + k + 64) : 0u;
         const int dist = (int)(s >> 8);
         const int len = k < ns ? (dist ? (int)(s & 255u) + 3 : 1) : 0;
         int incl = len;
@@ -270,8 +272,16 @@ __global__ void __launch_bounds__(32 * kLzWarps) k_lz_expand(const uint32_t *__r
         // copies its own (their loads are independent, so the group pays one memory latency for all of them)
         const bool own = dist != 0 && len <= kLzOwn && dist >= len && pos - dist + len <= base;
         if (own) {
+            // the first four bytes are loaded before any is stored: the compiler cannot tell that source and destination
+            // never overlap, so a plain copy loop queues every load behind the store before it -- one memory latency
+            // per byte, and most matches are three or four bytes long
             const uint8_t *from = o + pos - dist;
-            for (int j = 0; j < len; j++) o[pos + j] = from[j];
+            const uint8_t b0 = from[0], b1 = from[1], b2 = from[2];
+            uint8_t b3 = 0;
+            if (len > 3) b3 = from[3];
+            o[pos] = b0; o[pos + 1] = b1; o[pos + 2] = b2;
+            if (len > 3) o[pos + 3] = b3;
+            for (int j = 4; j < len; j++) o[pos + j] = from[j];
         }
         unsigned mm = __ballot_sync(0xffffffffu, dist != 0 && !own);
         __syncwarp();
