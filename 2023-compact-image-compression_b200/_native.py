@@ -96,6 +96,8 @@ def lib():
     L.cct_launch_count.argtypes = [C.c_int]
     L.cct_profile_enable.restype = C.c_int
     L.cct_profile_enable.argtypes = [C.c_int]
+    L.cct_profile_select.restype = C.c_int
+    L.cct_profile_select.argtypes = [C.c_char_p]
     L.cct_profile_read.restype = C.c_int
     L.cct_profile_read.argtypes = [C.c_char_p, sz]
     _lib = L
@@ -117,7 +119,7 @@ EXPORTS = ["cct_version", "cct_strerror", "cct_last_cuda_error", "cct_device_cou
            "cct_encode_workspace_bytes", "cct_decode_workspace_bytes", "cct_encode_batch", "cct_decode_batch",
            "cct_read_header", "cct_encode_host", "cct_decode_host", "cct_release", "cct_payload_bound",
            "cct_debug_encode_stages", "cct_deflate_workspace_bytes", "cct_deflate_bound", "cct_deflate_batch",
-           "cct_inflate_batch", "cct_inflate_workspace_bytes", "cct_debug_match_tables", "cct_debug_host_schedule", "cct_launch_count", "cct_profile_enable", "cct_profile_read"]
+           "cct_inflate_batch", "cct_inflate_workspace_bytes", "cct_debug_match_tables", "cct_debug_host_schedule", "cct_launch_count", "cct_profile_enable", "cct_profile_select", "cct_profile_read"]
 
 
 def check(code: int):

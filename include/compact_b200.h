@@ -166,6 +166,8 @@ int cct_inflate_batch(const uint8_t *d_in, size_t in_stride, const int32_t *d_in
  * cct_profile_read synchronises the device and writes "<kernel> <launches> <total_ms>\n" lines. */
 long long cct_launch_count(int reset);
 int cct_profile_enable(int on);
+/* Time only the kernels named here (comma- or space-separated; NULL or "" = every kernel again). */
+int cct_profile_select(const char *names);
 int cct_profile_read(char *buf, size_t cap);
 
 #ifdef __cplusplus
