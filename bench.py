@@ -141,6 +141,8 @@ def main():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--cpu-sample", type=int, default=512)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile-all", action="store_true",
+                    help="event-time every kernel inside the timed region (no extra warm-up step; used by profiles/capture_ncu.sh)")
     ap.add_argument("--workload", default="ct", choices=["ct", "radiograph"],
                     help="ct: synth_ct 12-bit slices (configs[1], the headline); radiograph: 16-bit 2048x2048 (configs[3])")
     ap.add_argument("--decode-sweep", action="store_true",
@@ -258,12 +260,14 @@ def main():
     # per-kernel CUDA events: every kernel during one extra warm-up step, only the largest few inside the timed region
     # (two event records around each of the ~115 launches of a step cost about 2 % of it)
     L.cct_profile_select(None)
-    L.cct_profile_enable(1)
-    step()
-    L.cct_profile_enable(0)
-    prof_all = native.profile_read()
-    top_names = [k for k, _ in sorted(((k, v) for k, v in prof_all.items() if k.startswith("k_")), key=lambda kv: -kv[1][1])[:6]]
-    L.cct_profile_select(",".join(top_names).encode())
+    prof_all = {}
+    if not args.profile_all:
+        L.cct_profile_enable(1)
+        step()
+        L.cct_profile_enable(0)
+        prof_all = native.profile_read()
+        top_names = [k for k, _ in sorted(((k, v) for k, v in prof_all.items() if k.startswith("k_")), key=lambda kv: -kv[1][1])[:6]]
+        L.cct_profile_select(",".join(top_names).encode())
     sampler = ClockSampler(local)
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     L.cct_launch_count(1)

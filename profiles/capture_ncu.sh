@@ -10,7 +10,7 @@
 set -e
 round=${1:-r02}
 tag=${2:-cap}
-A="--batch 1184 --steps 1 --warmup 1 --no-e2e --cpu-sample 32"   # 1184 slices = 8 streams per SM
+A="--batch 1184 --steps 1 --warmup 1 --no-e2e --cpu-sample 32 --profile-all"   # 1184 slices = 8 streams per SM
 mkdir -p gpurun_out
 python bench.py $A > gpurun_out/${tag}_plain.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${tag}_launches.csv \

@@ -4,7 +4,7 @@
 set -e
 tag=${1:-cap}
 rx=${2:-k_bprobe}
-A="--batch 1184 --steps 1 --warmup 1 --no-e2e --cpu-sample 32"   # 1184 slices = 8 streams per SM
+A="--batch 1184 --steps 1 --warmup 1 --no-e2e --cpu-sample 32 --profile-all"   # 1184 slices = 8 streams per SM
 mkdir -p gpurun_out
 python bench.py $A > gpurun_out/${tag}_plain.log 2>&1
 ncu --set full --clock-control none --import-source on --kernel-name regex:"$rx" --launch-skip-before-match 0 -c 12 -f \
