@@ -499,7 +499,13 @@ __global__ void __launch_bounds__(kBprobeThreads, 1536 / kBprobeThreads) k_bprob
         const int p = threadIdx.x == 0 ? 0 : n - 3 + (int)threadIdx.x;
         if (p >= 0 && p < n && (threadIdx.x == 0 || p >= 1)) mlo[p] = 0;
     }
-    BucketView v{in + (int64_t)stream * in_stride, ent_all + o, runs_all + o, n};
+    const uint8_t *w_s = in + (int64_t)stream * in_stride;
+    const SortEnt *ent_s = ent_all + o;
+    const uint32_t *runs_s = runs_all + o;
+    // opaque to the compiler: it would otherwise re-derive the three bases from the kernel parameters (six instructions)
+    // at every use inside the walks instead of keeping them
+    asm volatile("" : "+l"(w_s), "+l"(ent_s), "+l"(runs_s));
+    BucketView v{w_s, ent_s, runs_s, n};
     // (the walks are warp-wide: all 32 lanes go round together, lanes past the end idle)
     const int lane = threadIdx.x & 31;
     for (int i0 = blockIdx.x * kBprobeThreads + (threadIdx.x & ~31); i0 < members; i0 += gridDim.x * kBprobeThreads) {
