@@ -250,6 +250,7 @@ __global__ void __launch_bounds__(32 * kLzWarps) k_lz_expand(const uint32_t *__r
     const int ns = nsym[i];
     const uint32_t *sy = syms + (int64_t)i * sym_stride;
     uint8_t *o = out + (int64_t)i * out_stride;
+    asm volatile("" : "+l"(sy), "+l"(o));  // (keeps the two bases in registers instead of re-deriving them from the parameters)
     int base = 0;
     uint32_t s_next = lane < ns ? __ldg(sy + lane) : 0u;  // the symbols are fetched two groups ahead
     uint32_t s_next2 = lane + 32 < ns ? __ldg(sy + lane + 32) : 0u;

@@ -327,6 +327,7 @@ __global__ void __launch_bounds__(kHsThreads, 6) k_hs_split(const uint8_t *__res
     }
     __syncthreads();
     SortEnt *p1 = p1_all + (int64_t)stream * stride;
+    asm volatile("" : "+l"(p1));  // (kept in registers: the stores below would re-derive it from the parameters)
 #pragma unroll
     for (int r = 0; r < kHsRows; r++) {
         if (key[r] == 0xFFFFFFFFu) continue;
@@ -404,6 +405,7 @@ __global__ void __launch_bounds__(kBinThreads, 5) k_hs_bins(const uint32_t *__re
         if (S == 0) continue;
         const uint2 *src = reinterpret_cast<const uint2 *>(p1_all + (int64_t)stream * stride + lo);
         SortEnt *ent = ent_all + (int64_t)stream * stride + lo;
+        asm volatile("" : "+l"(src), "+l"(ent));  // (kept in registers instead of re-derived from the parameters)
         const bool single = S <= kBinChunk;
         uint2 pq[kBinRows];
         uint32_t key[kBinRows];
@@ -504,7 +506,7 @@ __global__ void __launch_bounds__(kBprobeThreads, 1536 / kBprobeThreads) k_bprob
     const uint32_t *runs_s = runs_all + o;
     // opaque to the compiler: it would otherwise re-derive the three bases from the kernel parameters (six instructions)
     // at every use inside the walks instead of keeping them
-    asm volatile("" : "+l"(w_s), "+l"(ent_s), "+l"(runs_s));
+    asm volatile("" : "+l"(w_s), "+l"(ent_s), "+l"(runs_s), "+l"(mlo), "+l"(mhi));
     BucketView v{w_s, ent_s, runs_s, n};
     // (the walks are warp-wide: all 32 lanes go round together, lanes past the end idle)
     const int lane = threadIdx.x & 31;
@@ -591,9 +593,13 @@ __global__ void __launch_bounds__(128) k_walk_spec(const uint8_t *__restrict__ i
     const int ws = k * kWalkWin;
     if (ws >= n) return;
     const int64_t o = (int64_t)stream * stride;
-    LzView v{in + (int64_t)stream * in_stride, n};
-    exits[(int64_t)stream * max_win + k] = walk_window(v, ProbeTab{mlo + o, mhi + o}, ws, min(ws + kWalkWin, n),
-                                                       mask + (int64_t)stream * mask_stride, rec + o);
+    const uint8_t *w_s = in + (int64_t)stream * in_stride;
+    const uint32_t *lo_s = mlo + o, *hi_s = mhi + o;
+    uint32_t *rec_s = rec + o, *mask_s = mask + (int64_t)stream * mask_stride;
+    // opaque to the compiler, which would otherwise re-derive the bases from the kernel parameters inside the walk
+    asm volatile("" : "+l"(w_s), "+l"(lo_s), "+l"(hi_s), "+l"(rec_s), "+l"(mask_s));
+    LzView v{w_s, n};
+    exits[(int64_t)stream * max_win + k] = walk_window(v, ProbeTab{lo_s, hi_s}, ws, min(ws + kWalkWin, n), mask_s, rec_s);
 }
 
 __global__ void __launch_bounds__(128) k_walk_stitch(const uint8_t *__restrict__ in, int64_t in_stride,
@@ -843,6 +849,7 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(const uint8_t *__restrict
     const uint32_t *sy = syms + (int64_t)stream * stride + d.sym_begin;
     const int mis = (int)(d.sym_begin & 3u);
     const uint4 *quads = reinterpret_cast<const uint4 *>(sy - mis);
+    asm volatile("" : "+l"(quads), "+l"(out32));  // (kept in registers: the loops below would re-derive them from the parameters)
     const int nq = (mis + ns + 3) >> 2;                                  // quads covering the block
     const int per = (nq + kPackThreads - 1) / kPackThreads;              // quads per thread
     const int q0 = min(nq, tid * per), q1 = min(nq, q0 + per);
