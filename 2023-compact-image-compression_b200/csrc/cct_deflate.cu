@@ -226,9 +226,19 @@ __device__ __forceinline__ unsigned key_peers(uint32_t key, bool valid) {
     unsigned peers = __ballot_sync(kAll, valid);
 #pragma unroll
     for (int b = 0; b < BITS; b++) {
-        const bool bit = (key >> b) & 1u;
-        const unsigned bal = __ballot_sync(kAll, bit);
-        peers &= bit ? bal : ~bal;
+        // peers &= ballot(bit b of key) ^ (bit b ? 0 : ~0), in four instructions (mask test straight into a predicate,
+        // vote, select, one LOP3); the compiler's own sequence for the C++ statement takes six
+        asm("{\n\t"
+            ".reg .pred p;\n\t"
+            ".reg .b32 t, bal, m;\n\t"
+            "and.b32 t, %1, %2;\n\t"
+            "setp.ne.u32 p, t, 0;\n\t"
+            "vote.sync.ballot.b32 bal, p, 0xffffffff;\n\t"
+            "selp.b32 m, 0, 0xffffffff, p;\n\t"
+            "xor.b32 bal, bal, m;\n\t"
+            "and.b32 %0, %0, bal;\n\t"
+            "}"
+            : "+r"(peers) : "r"(key), "r"(1u << b));
     }
     return valid ? peers : 0u;
 }
