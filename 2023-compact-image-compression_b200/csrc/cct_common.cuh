@@ -60,4 +60,32 @@ CCT_HD uint32_t hilbert_d2raster(uint32_t n, uint32_t d) {
     return y * n + x;
 }
 
+#if defined(__CUDACC__)
+// Adler-32 building blocks: sa += sum of d_i, sb += sum of d_i * (n - i) over the calling thread's share of w[0..n)
+// (A = 1 + sa, B = n + sb, both mod 65521).  Sixteen bytes per load where the row is 16-byte aligned, and two
+// instructions per word: the byte sum (vsadu4) and the byte sum weighted 0,1,2,3 (dp4a).
+__device__ __forceinline__ void adler_sums(const uint8_t *w, int n, int tid, int nthreads, unsigned long long &sa,
+                                           unsigned long long &sb) {
+    const uint4 *v = reinterpret_cast<const uint4 *>(w);
+    const int nv = (reinterpret_cast<uintptr_t>(w) & 15u) ? 0 : n >> 4;  // (a row that is not 16-byte aligned goes byte by byte)
+    for (int i = tid; i < nv; i += nthreads) {
+        const uint4 q = v[i];
+        const uint32_t x[4] = {q.x, q.y, q.z, q.w};
+        uint32_t s = 0, t = 0;  // s = sum of the 16 bytes, t = sum of j * byte_j, j = 0..15
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t sk = __vsadu4(x[k], 0u);
+            s += sk;
+            t += __dp4a(x[k], 0x03020100u, 0u) + 4u * (uint32_t)k * sk;
+        }
+        sa += s;
+        sb += (unsigned long long)s * (unsigned long long)(n - 16 * i) - t;
+    }
+    for (int i = (nv << 4) + tid; i < n; i += nthreads) {
+        const unsigned long long d = w[i];
+        sa += d; sb += d * (unsigned long long)(n - i);
+    }
+}
+#endif
+
 }  // namespace cct

@@ -311,10 +311,7 @@ __global__ void __launch_bounds__(256) k_adler_check(const uint8_t *__restrict__
     const int n = len[i];
     const uint8_t *w = data + (int64_t)i * stride;
     unsigned long long sa = 0, sb = 0;  // A = 1 + sum d ; B = n + sum d * (n - idx)   (mod 65521)
-    for (int k = tid; k < n; k += 256) {
-        unsigned long long d = w[k];
-        sa += d; sb += d * (unsigned long long)(n - k);
-    }
+    adler_sums(w, n, tid, 256, sa, sb);
     __shared__ unsigned long long ra[8], rb[8];
     for (int o = 16; o; o >>= 1) { sa += __shfl_xor_sync(0xffffffffu, sa, o); sb += __shfl_xor_sync(0xffffffffu, sb, o); }
     if ((tid & 31) == 0) { ra[tid >> 5] = sa; rb[tid >> 5] = sb % 65521ull; }

@@ -690,10 +690,7 @@ __global__ void __launch_bounds__(256) k_adler(const uint8_t *__restrict__ in, i
     const uint8_t *w = in + (int64_t)stream * in_stride;
     // A = 1 + sum d_i ; B = n + sum d_i * (n - i)   (mod 65521)
     unsigned long long sa = 0, sb = 0;
-    for (int i = tid; i < n; i += 256) {
-        unsigned long long d = w[i];
-        sa += d; sb += d * (unsigned long long)(n - i);
-    }
+    adler_sums(w, n, tid, 256, sa, sb);
     __shared__ unsigned long long ra[8], rb[8];
     for (int o = 16; o; o >>= 1) { sa += __shfl_xor_sync(0xffffffffu, sa, o); sb += __shfl_xor_sync(0xffffffffu, sb, o); }
     if ((tid & 31) == 0) { ra[tid >> 5] = sa; rb[tid >> 5] = sb % 65521ull; }
