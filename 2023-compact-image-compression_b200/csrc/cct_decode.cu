@@ -530,12 +530,59 @@ __global__ void __launch_bounds__(32 * kOpsWarps) k_dec_ops_scan(const uint8_t *
     }
 }
 
-__global__ void __launch_bounds__(128) k_dec_ops_link(const int32_t *__restrict__ plen, OpsChunkSum *__restrict__ cs,
-                                                      int max_chunks, int n_px, uint32_t *__restrict__ status, int B) {
-    const int i = blockIdx.x * 128 + threadIdx.x;
+// The chunk summaries of an image are chained by a warp: a chunk is a map from its entry state s (0/1) to (exit state,
+// ops, delta sum), maps compose associatively, so 32 chunks are linked by one warp scan of such maps and the result is
+// applied to the state, op count and value carried in from the chunks before (ops_link_chunks is the sequential
+// statement of the same thing).
+struct OpsMap { uint32_t next; int n0, n1, d0, d1; };  // next: bit s = exit state for entry state s
+__device__ __forceinline__ OpsMap ops_then(const OpsMap &a, const OpsMap &b) {  // a first, then b
+    const uint32_t s0 = a.next & 1u, s1 = (a.next >> 1) & 1u;
+    OpsMap r;
+    r.next = ((b.next >> s0) & 1u) | (((b.next >> s1) & 1u) << 1);
+    r.n0 = a.n0 + (s0 ? b.n1 : b.n0); r.d0 = a.d0 + (s0 ? b.d1 : b.d0);
+    r.n1 = a.n1 + (s1 ? b.n1 : b.n0); r.d1 = a.d1 + (s1 ? b.d1 : b.d0);
+    return r;
+}
+constexpr int kLinkWarps = 4;
+__global__ void __launch_bounds__(32 * kLinkWarps) k_dec_ops_link(const int32_t *__restrict__ plen, OpsChunkSum *__restrict__ cs_all,
+                                                                  int max_chunks, int n_px, uint32_t *__restrict__ status, int B) {
+    const int i = blockIdx.x * kLinkWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (i >= B || status[i]) return;
     const int n_chunks = (plen[i] + kOpsChunk - 1) / kOpsChunk;
-    status[i] |= ops_link_chunks(cs + (int64_t)i * max_chunks, n_chunks, n_px);
+    OpsChunkSum *cs = cs_all + (int64_t)i * max_chunks;
+    uint32_t state = 0;
+    int ops = 0, val = 0;
+    for (int base = 0; base < n_chunks; base += 32) {
+        const int c = base + lane;
+        OpsMap m{2u, 0, 0, 0, 0};  // identity past the end
+        if (c < n_chunks) {
+            const OpsChunkSum v = cs[c];
+            m = OpsMap{(uint32_t)(v.exit_state[0] & 1u) | ((uint32_t)(v.exit_state[1] & 1u) << 1), v.nops[0], v.nops[1], v.dsum[0], v.dsum[1]};
+        }
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            OpsMap a;
+            a.next = __shfl_up_sync(0xffffffffu, m.next, d);
+            a.n0 = __shfl_up_sync(0xffffffffu, m.n0, d); a.n1 = __shfl_up_sync(0xffffffffu, m.n1, d);
+            a.d0 = __shfl_up_sync(0xffffffffu, m.d0, d); a.d1 = __shfl_up_sync(0xffffffffu, m.d1, d);
+            if (lane >= d) m = ops_then(a, m);
+        }
+        OpsMap ex;  // the chunks of this group before the lane's own
+        ex.next = __shfl_up_sync(0xffffffffu, m.next, 1);
+        ex.n0 = __shfl_up_sync(0xffffffffu, m.n0, 1); ex.n1 = __shfl_up_sync(0xffffffffu, m.n1, 1);
+        ex.d0 = __shfl_up_sync(0xffffffffu, m.d0, 1); ex.d1 = __shfl_up_sync(0xffffffffu, m.d1, 1);
+        if (lane == 0) ex = OpsMap{2u, 0, 0, 0, 0};
+        if (c < n_chunks) {
+            cs[c].entry = (uint8_t)((ex.next >> state) & 1u);
+            cs[c].op_base = ops + (state ? ex.n1 : ex.n0);
+            cs[c].val_base = val + (state ? ex.d1 : ex.d0);
+        }
+        const uint32_t tn = __shfl_sync(0xffffffffu, m.next, 31);
+        const int t_n = __shfl_sync(0xffffffffu, state ? m.n1 : m.n0, 31), t_d = __shfl_sync(0xffffffffu, state ? m.d1 : m.d0, 31);
+        ops += t_n; val += t_d;
+        state = (tn >> state) & 1u;
+    }
+    if (lane == 0 && ops < n_px) status[i] |= 64u;
 }
 
 __global__ void __launch_bounds__(32 * kOpsWarps) k_dec_ops_emit(const uint8_t *__restrict__ payload, int64_t pstride,
@@ -710,7 +757,7 @@ void launch_decode(const uint8_t *files, const int64_t *offsets, int B, int rows
     k_dec_ops_scan<<<gs, 32 * kOpsWarps, 0, st>>>(ws.payload, ws.pstride, ws.plen, ws.chunks, ws.max_chunks, status);
     }
     { CCT_KERNEL(k_dec_ops_link, st);
-    k_dec_ops_link<<<(B + 127) / 128, 128, 0, st>>>(ws.plen, ws.chunks, ws.max_chunks, n_px, status, B);
+    k_dec_ops_link<<<(B + kLinkWarps - 1) / kLinkWarps, 32 * kLinkWarps, 0, st>>>(ws.plen, ws.chunks, ws.max_chunks, n_px, status, B);
     }
     { CCT_KERNEL(k_dec_ops_emit, st);
     k_dec_ops_emit<<<ge, 32 * kOpsWarps, 0, st>>>(ws.payload, ws.pstride, ws.plen, ws.chunks, ws.max_chunks, n_px, ws.vals, ws.jflag, status);
