@@ -322,7 +322,7 @@ CCT_HDN inline int inflate_symbols(const uint8_t *in, int in_len, uint32_t *syms
 // where its confirmed predecessor ended; rounds repeat (normally twice) until every lane up to the end of the
 // block is confirmed, then each lane decodes once more writing its symbols at the offset given by a scan of the
 // symbol counts.  The reader is stateless (two staged words + a funnel shift per peek), so lanes stay in lock step.
-constexpr int kFLitBits = 10, kFDstBits = 9;   // primary lookup widths
+constexpr int kFLitBits = 11, kFDstBits = 9;   // primary lookup widths (11 literal bits: codes of 11 bits are common in a CT block, and the slow path runs with two or three lanes of a warp)
 constexpr int kSubBits = 512;                  // bits per lane per round
 constexpr int kSubLanes = 128;                 // sub-sequences per round = threads per stream
 constexpr int kStageWords = kSubLanes * kSubBits / 32 + 8;      // one round + the longest symbol (48 bits) + peek
