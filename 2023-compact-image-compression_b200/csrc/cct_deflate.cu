@@ -171,6 +171,7 @@ __global__ void __launch_bounds__(32 * kRunWarps) k_run_counts(const uint8_t *__
     const int base = chunk * kRunChunk, n = in_len[stream];
     if (base >= n) return;
     uint32_t *runs = runs_all + (int64_t)stream * stride;
+    asm volatile("" : "+l"(runs));  // (kept in registers instead of re-derived from the parameters)
     RunBytes r;
     run_bytes(r, in + (int64_t)stream * in_stride, n, base, lane);
     const int2 enter = enters[(int64_t)stream * max_chunks + chunk];
@@ -637,6 +638,7 @@ __global__ void __launch_bounds__(kScanThreads) k_symscan(const int32_t *__restr
     const uint32_t *rc = rec + o;
     uint32_t *out = syms + o;
     int32_t *be = blk_end + (int64_t)stream * max_blocks;
+    asm volatile("" : "+l"(mk), "+l"(rc), "+l"(out), "+l"(be));  // (kept in registers instead of re-derived from the parameters)
     __shared__ int warp_sum[kScanThreads / 32];
     __shared__ int carry_s;
     if (tid == 0) carry_s = 0;
