@@ -656,6 +656,7 @@ __global__ void __launch_bounds__(32 * kUnitWarps) k_dec_units(const uint8_t *__
     const int nb = n_px / kBlock;
     const uint8_t *jf = jflag + (int64_t)i * nb;
     int32_t *sa = slotA + (int64_t)i * nb, *sb = slotB + (int64_t)i * nb;
+    asm volatile("" : "+l"(jf), "+l"(sa), "+l"(sb));  // (kept in registers: the loops below would re-derive them from the kernel parameters)
     uint64_t win = 0;  // bit k: block cur + k already consumed as a partner
     int cur = 0, q = 0;
     bool bad = false;

@@ -201,6 +201,7 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit(const uint16_t *__restric
     const uint8_t *jp = jump + (int64_t)img * nb;
     const uint8_t *tk = taken + (int64_t)img * nb;
     uint8_t *out = payload + (int64_t)img * pstride;  // 16-byte aligned (pstride is a multiple of 16)
+    asm volatile("" : "+l"(h), "+l"(jp), "+l"(tk), "+l"(out));  // (kept in registers: the loops below would re-derive them from the kernel parameters)
     __shared__ int warp_sum[kEmitThreads / 32];
     __shared__ int red_full[kEmitThreads / 32], red_dom[kEmitThreads / 32];
     __shared__ __align__(16) uint8_t tile[kEmitThreads * kEmitUnitMax + 32];
