@@ -73,6 +73,7 @@ struct StreamBits {  // the stream as aligned 32-bit words; positions are bits f
 struct InflateShared {
     FastTables tb;
     uint32_t ends[kSubLanes];                      // where each lane's last symbol ended
+    uint32_t marks[kMarkWords][kSubLanes];         // sync marks of each lane's list (inflate_core.cuh)
     unsigned ok_mask[kInfWarps], stop_mask[kInfWarps];
     int warp_n[kInfWarps], warp_b[kInfWarps];      // symbols / bytes per warp (scan)
     int end_flag; uint32_t end_pos;                // of the lane that closes the round
@@ -133,8 +134,14 @@ __device__ __forceinline__ bool cta_block_symbols(const StreamBits &sb, uint32_t
         uint32_t start = q + (uint32_t)tid * kSubBits, cur = 0xffffffffu;
         Span r{0u, 0, 0, kSpanRun};
         int confirmed = 0, last = -1;
+        bool again = false;
         for (;;) {  // rounds: lanes at and after the first unconfirmed one decode from where their predecessor ended
-            if (tid >= confirmed && start != cur) { decode_span<false>(tb.stage, origin, start, limit, data_end, tb, nullptr, 0, r); cur = start; }
+            if (tid >= confirmed && start != cur) {
+                decode_span_marks<kSubLanes>(tb.stage, origin, q + (uint32_t)tid * kSubBits, start, limit, data_end, tb,
+                                             &sh.marks[0][tid], again, r);
+                cur = start;
+            }
+            again = true;
             sh.ends[tid] = r.end;
             __syncthreads();
             const uint32_t prev_end = tid ? sh.ends[tid - 1] : 0u;
@@ -211,11 +218,30 @@ __global__ void __launch_bounds__(kSubLanes) k_inflate_sym(StreamSrc src, const 
             br.seek(bp);
             bool l = false;
             int nlen = 0, ndist = 0;
-            int type = inflate_block_header(br, sh.tb, &l, &nlen, &ndist);
+            int type = inflate_block_header(br, sh.tb, &l, &nlen, &ndist, false);
             if (br.bad) type = -1;
             sh.type = type; sh.nlen = nlen; sh.ndist = ndist; sh.last = l; sh.bp = br.tell();
         }
         __syncthreads();
+        if (sh.type == 2) {  // the code lengths: every thread looks up what starts at its bits, thread 0 follows the chain
+            uint32_t *stage = sh.tb.stage;
+            const uint32_t hq = sh.bp + sb.skew, w0 = hq >> 5, sk = hq & 31u;
+            for (int j = tid; j < kClWords; j += kSubLanes) stage[kClWordAt + j] = sb.word(w0 + j);
+            __syncthreads();
+            const uint16_t *prim = reinterpret_cast<const uint16_t *>(stage);
+            uint16_t *ent = reinterpret_cast<uint16_t *>(stage + kClEntAt);
+            for (int b = tid; b < kClBits; b += kSubLanes) {
+                const uint32_t rel = sk + (uint32_t)b;
+                ent[b] = cl_entry(prim, __funnelshift_r(stage[kClWordAt + (rel >> 5)], stage[kClWordAt + (rel >> 5) + 1], rel & 31u));
+            }
+            __syncthreads();
+            if (tid == 0) {
+                uint32_t used = 0;
+                if (!cl_walk(ent, sh.nlen + sh.ndist, sh.tb.lens, &used) || sh.bp + used > 8u * (uint32_t)dlen) sh.type = -1;
+                sh.bp += used;
+            }
+            __syncthreads();
+        }
         const int type = sh.type, nlen = sh.nlen, ndist = sh.ndist;
         last = sh.last != 0; bp = sh.bp;
         if (type < 0) { good = false; break; }

@@ -486,9 +486,87 @@ CCT_HD void decode_span(const uint32_t *stage, uint32_t origin, uint32_t p, uint
     r.end = p; r.n = n; r.extra = extra; r.flag = flag;
 }
 
+// Sync marks.  A lane that decodes its sub-sequence again from another start falls into step with its earlier
+// list after a few symbols, and from there on the result is known.  The earlier list is remembered as one mark per
+// 32-bit word of the lane's window (kSubBits + the longest symbol): the offset of the first symbol boundary in
+// the word (kMarkNone: none), how many symbols start in the word and their extra bytes.  Two lists that have the same
+// first boundary in a word are the same list from that boundary on.
+constexpr int kMarkWords = kSubBits / 32 + 2;
+constexpr uint32_t kMarkNone = 63u;
+CCT_HD uint32_t mark_pack(uint32_t off, int cnt, int ext) { return off | ((uint32_t)cnt << 6) | ((uint32_t)ext << 12); }
+
+// decode_span<false> from `p` for the lane whose window starts at `base`, keeping marks[w * MS] up to date.  With
+// `again`, marks[] and r describe the lane's previous list: the decode stops at the first word both lists enter at
+// the same bit, and the rest of r comes from the marks.  Without it every mark is written.
+template <int MS>
+CCT_HD void decode_span_marks(const uint32_t *stage, uint32_t origin, uint32_t base, uint32_t p, uint32_t limit,
+                              uint32_t data_end, const FastTables &tb, uint32_t *marks, bool again, Span &r) {
+    int n = 0, extra = 0, flag = kSpanRun;
+    int wcur = 0;
+    if (p < base) p = base;  // the lane before ended short of its sub-sequence: the block ends there, or it decodes again
+    if (p < limit) {
+        wcur = (int)((p - base) >> 5);
+        for (int w = 0; w < wcur; w++) marks[w * MS] = kMarkNone;  // the list starts later than the previous one did
+        uint32_t off = (p - base) & 31u;
+        int n0 = 0, e0 = 0;  // n, extra when the word was entered
+        for (;;) {
+            // p is the first boundary of this list in word wcur
+            if (again && (marks[wcur * MS] & 63u) == off) {
+                for (int w = wcur; w < kMarkWords; w++) {
+                    const uint32_t m = marks[w * MS];
+                    n += (int)((m >> 6) & 63u); extra += (int)(m >> 12);
+                }
+                r.n = n; r.extra = extra;  // r.end and r.flag stand
+                return;
+            }
+            int wn = wcur;
+            do {  // the symbols that start in word wcur
+                uint32_t bits = stage_peek(stage, p - origin);
+                uint32_t e = tb.lit[bits & ((1u << kFLitBits) - 1)];
+                if (!e) { e = canon_lookup(tb.lc, tb.lsym, bits, kFLitBits + 1, 15, true); if (!e) { flag = kSpanBad; break; } }
+                const uint32_t kind = e & kEntKind;
+                if (kind == kEntLit) {
+                    p += e & 15u;
+                    n++;
+                } else {
+                    if (kind != kEntLen) {
+                        if (kind == kEntEob) { p += e & 15u; flag = kSpanEob; } else flag = kSpanBad;
+                        break;
+                    }
+                    const uint32_t l = e & 15u;
+                    const int li = (int)(e >> 6);
+                    const uint32_t xb = (uint32_t)len_extra_bits_inf(li);
+                    const int len = len_base_inf(li) + (int)((bits >> l) & ((1u << xb) - 1u));
+                    const uint32_t q = p + l + xb;
+                    bits = stage_peek(stage, q - origin);
+                    uint32_t d = tb.dst[bits & ((1u << kFDstBits) - 1)];
+                    if (!d) { d = canon_lookup(tb.dc, tb.dsym, bits, kFDstBits + 1, 15, false); if (!d) { flag = kSpanBad; break; } }
+                    if ((d & kEntKind) != kEntLen) { flag = kSpanBad; break; }
+                    const int ds = (int)(d >> 6);
+                    const uint32_t dxb = ds < 4 ? 0u : (uint32_t)(ds >> 1) - 1u;
+                    p = q + (d & 15u) + dxb;
+                    n++; extra += len - 1;
+                }
+                wn = (int)((p - base) >> 5);
+            } while (wn == wcur && p < limit);
+            marks[wcur * MS] = mark_pack(off, n - n0, extra - e0);
+            if (flag != kSpanRun || p >= limit) break;
+            for (int w = wcur + 1; w < wn; w++) marks[w * MS] = kMarkNone;  // a symbol longer than a word
+            wcur = wn; off = (p - base) & 31u; n0 = n; e0 = extra;
+        }
+        wcur++;
+    }
+    for (int w = wcur; w < kMarkWords; w++) marks[w * MS] = kMarkNone;
+    if (flag == kSpanRun && p >= data_end) flag = kSpanBad;  // the data ended before the block did
+    r.end = p; r.n = n; r.extra = extra; r.flag = flag;
+}
+
 // Block header (RFC 1951 3.2.3 - 3.2.7), single lane: leaves the code lengths in tb.lens (literal/length codes
 // first, then distance codes) and returns the block type, or -1.  Stored: *nlen = LEN.  `br` stands after the header.
-CCT_HDN inline int inflate_block_header(BitReader &br, FastTables &tb, bool *last, int *nlen, int *ndist) {
+// With `lengths` off a dynamic block's code lengths are left to cl_entry / cl_walk: `br` stands at their first bit
+// and the code-length code's table is at the start of the staging area.
+CCT_HDN inline int inflate_block_header(BitReader &br, FastTables &tb, bool *last, int *nlen, int *ndist,
+                                        bool lengths = true) {
     br.refill();
     *last = br.take(1) != 0;
     const int type = (int)br.take(2);
@@ -520,6 +598,7 @@ CCT_HDN inline int inflate_block_header(BitReader &br, FastTables &tb, bool *las
     // the code-length code's little tables live in the (idle) staging area
     uint16_t *prim = reinterpret_cast<uint16_t *>(tb.stage), *cnt = prim + 128, *sy = cnt + 16;
     if (!build_decode_table(cl, 19, 7, prim, cnt, sy)) return -1;
+    if (!lengths) { *nlen = nl; *ndist = nd; return br.bad ? -1 : 2; }
     int idx = 0;
     while (idx < nl + nd) {
         br.refill();
@@ -538,6 +617,40 @@ CCT_HDN inline int inflate_block_header(BitReader &br, FastTables &tb, bool *las
     if (br.bad || lens[256] == 0) return -1;
     *nlen = nl; *ndist = nd;
     return 2;
+}
+
+// The code lengths of a dynamic block, in two steps.  The code-length symbols are at most 7 bits plus at most 7 extra
+// bits and every one of them yields a length, so the nlen + ndist <= 316 lengths take fewer than kClBits bits.
+// cl_entry   what a code-length symbol starting at a given bit would be (any thread, any bit): symbol | bits it takes
+//            << 5 | value of its extra bits << 9, 0 for an unused code.  `bits` = 14 or more stream bits from there.
+// cl_walk    follows the entries from bit 0 and writes the lengths (one thread).
+constexpr int kClBits = 2240, kClWords = kClBits / 32 + 2;
+constexpr int kClWordAt = 96, kClEntAt = 192;  // where the header's words and entries sit in the staging area (32-bit words)
+static_assert(kClEntAt + kClBits / 2 <= kStageAlloc && kClWordAt + kClWords <= kClEntAt, "the staging area holds a header");
+CCT_HD uint16_t cl_entry(const uint16_t *prim, uint32_t bits) {
+    const uint32_t e = prim[bits & 127u];
+    if (!e) return 0;
+    const uint32_t l = e >> 12, sym = e & 0xFFFu;
+    const uint32_t xb = sym < 16 ? 0u : sym == 16 ? 2u : sym == 17 ? 3u : 7u;
+    return (uint16_t)(sym | ((l + xb) << 5) | (((bits >> l) & ((1u << xb) - 1u)) << 9));
+}
+CCT_HDN inline bool cl_walk(const uint16_t *ent, int total, uint8_t *lens, uint32_t *used) {
+    uint32_t b = 0;
+    int idx = 0;
+    while (idx < total) {
+        if (b >= (uint32_t)kClBits) return false;
+        const uint32_t e = ent[b];
+        if (!e) return false;
+        const uint32_t sym = e & 31u;
+        b += (e >> 5) & 15u;
+        if (sym < 16) { lens[idx++] = (uint8_t)sym; continue; }
+        int rep = (int)(e >> 9) + (sym == 18 ? 11 : 3), val = 0;
+        if (sym == 16) { if (idx == 0) return false; val = lens[idx - 1]; }
+        if (idx + rep > total) return false;
+        while (rep--) lens[idx++] = (uint8_t)val;
+    }
+    *used = b;
+    return lens[256] != 0;
 }
 
 // Pass 2 of inflate, sequential form (CPU harness): symbols -> bytes.

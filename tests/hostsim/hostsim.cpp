@@ -273,10 +273,20 @@ static bool hs_block_symbols(const std::vector<uint32_t> &words, uint32_t data_e
             start[l] = q + (uint32_t)l * kSubBits; cur[l] = 0xffffffffu; r[l] = Span{0u, 0, 0, kSpanRun};
         }
         int confirmed = 0, last = -1, rounds = 0;
+        static uint32_t marks[kMarkWords][kSubLanes];
         for (;;) {
             rounds++;
             for (int l = confirmed; l < kSubLanes; l++)
-                if (start[l] != cur[l]) { decode_span<false>(tb.stage, origin, start[l], limit[l], data_end, tb, nullptr, 0, r[l]); cur[l] = start[l]; }
+                if (start[l] != cur[l]) {
+                    decode_span_marks<kSubLanes>(tb.stage, origin, q + (uint32_t)l * kSubBits, start[l], limit[l], data_end, tb,
+                                                 &marks[0][l], rounds > 1, r[l]);
+                    {  // the shortcut gives what the plain decode gives
+                        Span chk;
+                        decode_span<false>(tb.stage, origin, std::max(start[l], q + (uint32_t)l * kSubBits), limit[l], data_end, tb, nullptr, 0, chk);
+                        if (chk.end != r[l].end || chk.n != r[l].n || chk.extra != r[l].extra || chk.flag != r[l].flag) abort();
+                    }
+                    cur[l] = start[l];
+                }
             int c = 1;
             while (c < kSubLanes && cur[c] == r[c - 1].end) c++;
             for (int l = 0; l < c && last < 0; l++) if (r[l].flag != kSpanRun) last = l;
@@ -330,9 +340,24 @@ int hs_inflate_lanes(const uint8_t *in_, int in_len, uint8_t *out, int out_cap, 
         BitReader br{in, dlen, 0, 0, 0, false};
         br.seek(bp);
         int nlen = 0, ndist = 0;
-        const int type = inflate_block_header(br, *tb, &last, &nlen, &ndist);
+        const int type = inflate_block_header(br, *tb, &last, &nlen, &ndist, false);
         if (type < 0 || br.bad) { good = false; break; }
         bp = br.tell();
+        if (type == 2) {  // as k_inflate_sym: an entry per bit, then the walk
+            uint32_t *stage = tb->stage;
+            const uint32_t hq = bp + skew, w0 = hq >> 5, sk = hq & 31u;
+            for (int j = 0; j < kClWords; j++) stage[kClWordAt + j] = w0 + j < words.size() ? words[w0 + j] : 0u;
+            const uint16_t *prim = reinterpret_cast<const uint16_t *>(stage);
+            uint16_t *ent = reinterpret_cast<uint16_t *>(stage + kClEntAt);
+            for (int b = 0; b < kClBits; b++) {
+                const uint32_t rel = sk + (uint32_t)b;
+                const uint64_t two = ((uint64_t)stage[kClWordAt + (rel >> 5) + 1] << 32) | stage[kClWordAt + (rel >> 5)];
+                ent[b] = cl_entry(prim, (uint32_t)(two >> (rel & 31u)));
+            }
+            uint32_t used = 0;
+            if (!cl_walk(ent, nlen + ndist, tb->lens, &used) || bp + used > 8u * (uint32_t)dlen) { good = false; break; }
+            bp += used;
+        }
         if (type == 0) {
             const int at = (int)(bp >> 3);
             if (at + nlen > dlen || ns + nlen > sym_cap || op + nlen > out_cap) { good = false; break; }
