@@ -267,66 +267,168 @@ __global__ void __launch_bounds__(kSubLanes) k_inflate_sym(StreamSrc src, const 
 }
 
 constexpr int kLzWarps = 4;
-constexpr int kLzOwn = 16;  // longest match a single lane copies on its own
+constexpr int kLzOwn = 16;              // longest match a single lane copies on its own
+constexpr int kLzPer = 4;               // symbols per lane per step
+constexpr int kLzStep = 32 * kLzPer;
+constexpr int kLzSpan = 2048;           // most bytes a step may produce through the ring (more: one group at a time, through global memory)
+constexpr int kLzRing = 4096;           // bytes of recent output a warp keeps in shared memory
+constexpr int kLzBack = 512;            // bytes put back into the ring after a step that went around it
+static_assert(kLzRing >= kLzSpan + kLzBack && kLzBack >= 258 + 16, "a source that is not yet in global memory is in the ring");
+
+// 32 symbols (one per lane) expanded straight into global memory at ob + base: literals in parallel, short matches whose
+// source lies before the group by their own lane, the rest in symbol order by the whole warp.
+__device__ __forceinline__ void lz_group_global(uint8_t *ob, uint32_t s, bool valid, int &base, int lane) {
+    const int dist = (int)(s >> 8);
+    const int len = valid ? (dist ? (int)(s & 255u) + 3 : 1) : 0;
+    int incl = len;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    const int pos = base + incl - len;
+    if (len && !dist) ob[pos] = (uint8_t)s;
+    const bool own = dist != 0 && len <= kLzOwn && dist >= len && pos - dist + len <= base;
+    if (own) {  // the first bytes are loaded before any is stored: the compiler cannot tell that the two never overlap
+        const uint8_t *from = ob + pos - dist;
+        const uint8_t b0 = from[0], b1 = from[1], b2 = from[2];
+        uint8_t b3 = 0;
+        if (len > 3) b3 = from[3];
+        ob[pos] = b0; ob[pos + 1] = b1; ob[pos + 2] = b2;
+        if (len > 3) ob[pos + 3] = b3;
+        for (int j = 4; j < len; j++) ob[pos + j] = from[j];
+    }
+    unsigned mm = __ballot_sync(0xffffffffu, dist != 0 && !own);
+    __syncwarp();
+    while (mm) {
+        const int l = __ffs((int)mm) - 1;
+        mm &= mm - 1;
+        const int mpos = __shfl_sync(0xffffffffu, pos, l), mlen = __shfl_sync(0xffffffffu, len, l);
+        const int mdist = __shfl_sync(0xffffffffu, dist, l);
+        const uint8_t *from = ob + mpos - mdist;
+        if (mdist >= mlen) {
+            for (int j = lane; j < mlen; j += 32) ob[mpos + j] = from[j];
+        } else {  // overlapping copy: the source repeats with period mdist
+            for (int j = lane; j < mlen; j += 32) ob[mpos + j] = from[j % mdist];
+        }
+        __syncwarp();
+    }
+    base += __shfl_sync(0xffffffffu, incl, 31);
+}
+
+// One warp per stream, kLzStep symbols per step (kLzPer consecutive ones per lane).  A step's bytes are assembled in a
+// ring in shared memory and leave for global memory as whole 16-byte units; `fl` is how far that has got.  A match
+// whose source ends at or before fl reads global memory -- all those of a step at once, one memory latency for the lot;
+// the others (the source reaches into the step, or the last few bytes before it) are copied ring to ring in symbol
+// order.  Positions are offsets from `ob`, the stream's first byte rounded down to 16 bytes.
 __global__ void __launch_bounds__(32 * kLzWarps) k_lz_expand(const uint32_t *__restrict__ syms, int64_t sym_stride,
                                                              const int32_t *__restrict__ nsym, uint8_t *__restrict__ out,
                                                              int64_t out_stride, int B) {
+    __shared__ __align__(16) uint8_t ring_all[kLzWarps][kLzRing];
     const int i = blockIdx.x * kLzWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (i >= B) return;
+    constexpr unsigned kAll = 0xffffffffu;
+    constexpr int M = kLzRing - 1;
+    uint8_t *ring = ring_all[threadIdx.x >> 5];
     const int ns = nsym[i];
-    const uint32_t *sy = syms + (int64_t)i * sym_stride;
+    const uint32_t *sy = syms + (int64_t)i * sym_stride;  // 16-byte aligned (sym_stride is a multiple of 4 words)
     uint8_t *o = out + (int64_t)i * out_stride;
-    asm volatile("" : "+l"(sy), "+l"(o));  // (keeps the two bases in registers instead of re-deriving them from the parameters)
-    int base = 0;
-    uint32_t s_next = lane < ns ? __ldg(sy + lane) : 0u;  // the symbols are fetched two groups ahead
-    uint32_t s_next2 = lane + 32 < ns ? __ldg(sy + lane + 32) : 0u;
-    for (int g = 0; g < ns; g += 32) {
-        const int k = g + lane;
-        const uint32_t s = s_next;
-        s_next = s_next2;
-        s_next2 = k + 64 < ns ? __ldg(sy + k + 64) : 0u;
-        const int dist = (int)(s >> 8);
-        const int len = k < ns ? (dist ? (int)(s & 255u) + 3 : 1) : 0;
-        int incl = len;
+    const int a0 = (int)(reinterpret_cast<uintptr_t>(o) & 15u);
+    uint8_t *ob = o - a0;
+    asm volatile("" : "+l"(sy), "+l"(ob));  // (keeps the two bases in registers instead of re-deriving them from the parameters)
+    int base = a0, fl = a0;  // [a0, base) is produced, [a0, fl) is in global memory
+    uint4 nx = 4 * lane < ns ? __ldg(reinterpret_cast<const uint4 *>(sy + 4 * lane)) : make_uint4(0u, 0u, 0u, 0u);
+    for (int g = 0; g < ns; g += kLzStep) {
+        const int k0 = g + kLzPer * lane;
+        const uint4 q = nx;
+        nx = k0 + kLzStep < ns ? __ldg(reinterpret_cast<const uint4 *>(sy + k0 + kLzStep)) : make_uint4(0u, 0u, 0u, 0u);
+        // (what follows the last symbol in its 16-byte word is not a symbol)
+        const uint32_t s0 = q.x, s1 = k0 + 1 < ns ? q.y : 0u, s2 = k0 + 2 < ns ? q.z : 0u, s3 = k0 + 3 < ns ? q.w : 0u;
+        const int d0 = (int)(s0 >> 8), d1 = (int)(s1 >> 8), d2 = (int)(s2 >> 8), d3 = (int)(s3 >> 8);
+        const int l0 = k0 < ns ? (d0 ? (int)(s0 & 255u) + 3 : 1) : 0, l1 = k0 + 1 < ns ? (d1 ? (int)(s1 & 255u) + 3 : 1) : 0;
+        const int l2 = k0 + 2 < ns ? (d2 ? (int)(s2 & 255u) + 3 : 1) : 0, l3 = k0 + 3 < ns ? (d3 ? (int)(s3 & 255u) + 3 : 1) : 0;
+        const int tot = l0 + l1 + l2 + l3;
+        int incl = tot;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            int t = __shfl_up_sync(0xffffffffu, incl, d);
+            int t = __shfl_up_sync(kAll, incl, d);
             if (lane >= d) incl += t;
         }
-        const int pos = base + incl - len;
-        if (len && !dist) o[pos] = (uint8_t)s;
-        // short matches whose source lies entirely before this group depend on nothing written here: every lane
-        // copies its own (their loads are independent, so the group pays one memory latency for all of them)
-        const bool own = dist != 0 && len <= kLzOwn && dist >= len && pos - dist + len <= base;
-        if (own) {
-            // the first four bytes are loaded before any is stored: the compiler cannot tell that source and destination
-            // never overlap, so a plain copy loop queues every load behind the store before it -- one memory latency
-            // per byte, and most matches are three or four bytes long
-            const uint8_t *from = o + pos - dist;
-            const uint8_t b0 = from[0], b1 = from[1], b2 = from[2];
-            uint8_t b3 = 0;
-            if (len > 3) b3 = from[3];
-            o[pos] = b0; o[pos + 1] = b1; o[pos + 2] = b2;
-            if (len > 3) o[pos + 3] = b3;
-            for (int j = 4; j < len; j++) o[pos + j] = from[j];
+        const int span = __shfl_sync(kAll, incl, 31), end = base + span;
+        if (span > kLzSpan) {  // long matches all over: what the ring holds goes out, then group by group in global memory
+            for (int p = fl + lane; p < base; p += 32) ob[p] = ring[p & M];
+            __syncwarp();
+            for (int t = 0; t < kLzPer; t++) {
+                const int k = g + 32 * t + lane;
+                lz_group_global(ob, k < ns ? __ldg(sy + k) : 0u, k < ns, base, lane);
+            }
+            fl = base;
+            for (int p = max(a0, base - kLzBack) + lane; p < base; p += 32) ring[p & M] = ob[p];
+            __syncwarp();
+            continue;
         }
-        unsigned mm = __ballot_sync(0xffffffffu, dist != 0 && !own);
+        const int p0 = base + incl - tot, p1 = p0 + l0, p2 = p1 + l1, p3 = p2 + l2;
+        // literals and the short matches whose source is in global memory
+        const bool f0 = d0 && l0 <= kLzOwn && p0 - d0 + l0 <= fl, f1 = d1 && l1 <= kLzOwn && p1 - d1 + l1 <= fl;
+        const bool f2 = d2 && l2 <= kLzOwn && p2 - d2 + l2 <= fl, f3 = d3 && l3 <= kLzOwn && p3 - d3 + l3 <= fl;
+        unsigned pm = (d0 && !f0 ? 1u : 0u) | (d1 && !f1 ? 2u : 0u) | (d2 && !f2 ? 4u : 0u) | (d3 && !f3 ? 8u : 0u);
+        uint8_t b00 = 0, b01 = 0, b02 = 0, b03 = 0, b10 = 0, b11 = 0, b12 = 0, b13 = 0;
+        uint8_t b20 = 0, b21 = 0, b22 = 0, b23 = 0, b30 = 0, b31 = 0, b32 = 0, b33 = 0;
+        if (f0) { const uint8_t *f = ob + p0 - d0; b00 = f[0]; b01 = f[1]; b02 = f[2]; if (l0 > 3) b03 = f[3]; }
+        if (f1) { const uint8_t *f = ob + p1 - d1; b10 = f[0]; b11 = f[1]; b12 = f[2]; if (l1 > 3) b13 = f[3]; }
+        if (f2) { const uint8_t *f = ob + p2 - d2; b20 = f[0]; b21 = f[1]; b22 = f[2]; if (l2 > 3) b23 = f[3]; }
+        if (f3) { const uint8_t *f = ob + p3 - d3; b30 = f[0]; b31 = f[1]; b32 = f[2]; if (l3 > 3) b33 = f[3]; }
+        if (l0 && !d0) ring[p0 & M] = (uint8_t)s0;
+        if (l1 && !d1) ring[p1 & M] = (uint8_t)s1;
+        if (l2 && !d2) ring[p2 & M] = (uint8_t)s2;
+        if (l3 && !d3) ring[p3 & M] = (uint8_t)s3;
+#define CCT_LZ_FAR(f, p, d, l, x0, x1, x2, x3)                                                     \
+        if (f) {                                                                                   \
+            ring[p & M] = x0; ring[(p + 1) & M] = x1; ring[(p + 2) & M] = x2;                      \
+            if (l > 3) ring[(p + 3) & M] = x3;                                                     \
+            for (int t = 4; t < l; t++) ring[(p + t) & M] = ob[p - d + t];                         \
+        }
+        CCT_LZ_FAR(f0, p0, d0, l0, b00, b01, b02, b03)
+        CCT_LZ_FAR(f1, p1, d1, l1, b10, b11, b12, b13)
+        CCT_LZ_FAR(f2, p2, d2, l2, b20, b21, b22, b23)
+        CCT_LZ_FAR(f3, p3, d3, l3, b30, b31, b32, b33)
+#undef CCT_LZ_FAR
         __syncwarp();
-        while (mm) {  // the others in symbol order, each copied by the whole warp
-            const int l = __ffs((int)mm) - 1;
-            mm &= mm - 1;
-            const int mpos = __shfl_sync(0xffffffffu, pos, l), mlen = __shfl_sync(0xffffffffu, len, l);
-            const int mdist = __shfl_sync(0xffffffffu, dist, l);
-            const uint8_t *from = o + mpos - mdist;
-            if (mdist >= mlen) {
-                for (int j = lane; j < mlen; j += 32) o[mpos + j] = from[j];
+        // the rest in symbol order, each by the whole warp
+        unsigned bl = __ballot_sync(kAll, pm != 0);
+        while (bl) {
+            const int l = __ffs((int)bl) - 1;
+            const unsigned pml = __shfl_sync(kAll, pm, l);
+            const int j = __ffs((int)pml) - 1;
+            const int pj = j == 0 ? p0 : j == 1 ? p1 : j == 2 ? p2 : p3;
+            const int lj = j == 0 ? l0 : j == 1 ? l1 : j == 2 ? l2 : l3;
+            const int dj = j == 0 ? d0 : j == 1 ? d1 : j == 2 ? d2 : d3;
+            const int mpos = __shfl_sync(kAll, pj, l), mlen = __shfl_sync(kAll, lj, l), mdist = __shfl_sync(kAll, dj, l);
+            const int src = mpos - mdist;
+            if (src + mlen <= fl) {  // (a long one) from global memory
+                for (int t = lane; t < mlen; t += 32) ring[(mpos + t) & M] = ob[src + t];
+            } else if (mdist >= mlen) {
+                for (int t = lane; t < mlen; t += 32) ring[(mpos + t) & M] = ring[(src + t) & M];
             } else {  // overlapping copy: the source repeats with period mdist
-                for (int j = lane; j < mlen; j += 32) o[mpos + j] = from[j % mdist];
+                for (int t = lane; t < mlen; t += 32) ring[(mpos + t) & M] = ring[(src + t % mdist) & M];
             }
             __syncwarp();
+            if (lane == l) pm &= pm - 1;
+            if ((pml & (pml - 1)) == 0) bl &= bl - 1;
         }
-        base += __shfl_sync(0xffffffffu, incl, 31);
+        // whole 16-byte units leave for global memory
+        if (fl & 15) {  // (the stream does not start on a 16-byte boundary)
+            const int h = min((fl + 15) & ~15, end);
+            if (fl + lane < h) ob[fl + lane] = ring[(fl + lane) & M];
+            fl = h;
+        }
+        for (int u = fl + 16 * lane; u + 16 <= end; u += 512)
+            *reinterpret_cast<uint4 *>(ob + u) = *reinterpret_cast<const uint4 *>(ring + (u & M));
+        if (!(fl & 15)) fl = max(fl, end & ~15);
+        base = end;
+        __syncwarp();
     }
+    for (int p = fl + lane; p < base; p += 32) ob[p] = ring[p & M];
 }
 
 __global__ void __launch_bounds__(256) k_adler_check(const uint8_t *__restrict__ data, int64_t stride,
