@@ -73,7 +73,12 @@ struct StreamBits {  // the stream as aligned 32-bit words; positions are bits f
 struct InflateShared {
     FastTables tb;
     uint32_t ends[kSubLanes];                      // where each lane's last symbol ended
+#ifndef CCT_INF_MARKS
+#define CCT_INF_MARKS 0  // sync marks (inflate_core.cuh) save a tenth of the decoding but cost two resident CTAs per SM: 10.6 ms against 8.4
+#endif
+#if CCT_INF_MARKS
     uint32_t marks[kMarkWords][kSubLanes];         // sync marks of each lane's list (inflate_core.cuh)
+#endif
     unsigned ok_mask[kInfWarps], stop_mask[kInfWarps];
     int warp_n[kInfWarps], warp_b[kInfWarps];      // symbols / bytes per warp (scan)
     int end_flag; uint32_t end_pos;                // of the lane that closes the round
@@ -86,7 +91,7 @@ __device__ __forceinline__ bool cta_build_code(InflateShared &sh, int first, int
     FastTables &tb = sh.tb;
     const int tid = threadIdx.x, lane = tid & 31;
     FastCanon &c = lit ? tb.lc : tb.dc;
-    uint16_t *syms = lit ? tb.lsym : tb.dsym;
+    uint32_t *syms = lit ? tb.lsym : tb.dsym;
     if (tid < 16) c.count[tid] = 0;
     __syncthreads();
     fast_count(tb.lens + first, nsym, c, tid, kSubLanes);
@@ -108,14 +113,14 @@ __device__ __forceinline__ bool cta_build_code(InflateShared &sh, int first, int
             const int start = next[l];
             __syncwarp();
             if (l) {
-                syms[start + rank] = (uint16_t)i;
+                syms[start + rank] = lit ? lit_entry(i, 0) : dst_entry(i, 0);
                 if (rank == 0) next[l] = (uint16_t)(start + __popc(peers));
             }
             __syncwarp();
         }
     }
     __syncthreads();
-    fast_fill(c, syms, lit ? tb.lit : tb.dst, lit ? kFLitBits : kFDstBits, lit, tid, kSubLanes);
+    fast_fill(c, syms, tb.tab + (lit ? 0 : kFDstAt), lit ? kFLitBits : kFDstBits, tid, kSubLanes);
     __syncthreads();
     return true;
 }
@@ -134,11 +139,15 @@ __device__ __forceinline__ bool cta_block_symbols(const StreamBits &sb, uint32_t
         uint32_t start = q + (uint32_t)tid * kSubBits, cur = 0xffffffffu;
         Span r{0u, 0, 0, kSpanRun};
         int confirmed = 0, last = -1;
-        bool again = false;
+        [[maybe_unused]] bool again = false;
         for (;;) {  // rounds: lanes at and after the first unconfirmed one decode from where their predecessor ended
             if (tid >= confirmed && start != cur) {
+#if CCT_INF_MARKS
                 decode_span_marks<kSubLanes>(tb.stage, origin, q + (uint32_t)tid * kSubBits, start, limit, data_end, tb,
                                              &sh.marks[0][tid], again, r);
+#else
+                decode_span<false>(tb.stage, origin, start, limit, data_end, tb, nullptr, 0, r);
+#endif
                 cur = start;
             }
             again = true;

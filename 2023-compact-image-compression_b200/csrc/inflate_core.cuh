@@ -322,15 +322,19 @@ CCT_HDN inline int inflate_symbols(const uint8_t *in, int in_len, uint32_t *syms
 // where its confirmed predecessor ended; rounds repeat (normally twice) until every lane up to the end of the
 // block is confirmed, then each lane decodes once more writing its symbols at the offset given by a scan of the
 // symbol counts.  The reader is stateless (two staged words + a funnel shift per peek), so lanes stay in lock step.
-constexpr int kFLitBits = 11, kFDstBits = 9;   // primary lookup widths (11 literal bits: codes of 11 bits are common in a CT block, and the slow path runs with two or three lanes of a warp)
+#ifndef CCT_FLIT_BITS
+#define CCT_FLIT_BITS 11
+#endif
+constexpr int kFLitBits = CCT_FLIT_BITS, kFDstBits = 9;   // primary lookup widths (11 literal bits: codes of 11 bits are common in a CT block, and the slow path runs with two or three lanes of a warp)
+constexpr int kFDstAt = 1 << kFLitBits;         // where the distance entries start in FastTables::tab
 constexpr int kSubBits = 512;                  // bits per lane per round
 constexpr int kSubLanes = 128;                 // sub-sequences per round = threads per stream
 constexpr int kStageWords = kSubLanes * kSubBits / 32 + 8;      // one round + the longest symbol (48 bits) + peek
 constexpr int kStageAlloc = kStageWords + kStageWords / 16 + 1; // one pad word per 16: lanes start 16 words apart
 CCT_HD int stage_slot(int w) { return w + (w >> 4); }
 
-// table entry (16 bits, so that a stream's tables stay small enough for 32 streams per SM): bits 0..3 code length
-// (0 = not in the primary table), 4..5 kind, 6..13 literal byte / length index 0..28 / distance symbol 0..29
+// table entry: bits 0..3 code length (0 = not in the primary table), 4..5 kind, 6..9 number of extra bits, 16..31 base
+// value (the literal byte, the smallest length or distance of the code)
 constexpr uint32_t kEntLit = 0u << 4, kEntLen = 1u << 4, kEntEob = 2u << 4, kEntBad = 3u << 4, kEntKind = 3u << 4;
 
 struct FastCanon {       // canonical description of one prefix code
@@ -340,10 +344,9 @@ struct FastCanon {       // canonical description of one prefix code
     uint16_t count[16];  // codes of length l
 };
 struct FastTables {      // per-stream decode state in shared memory
-    uint16_t lit[1 << kFLitBits];
-    uint16_t dst[1 << kFDstBits];
+    uint32_t tab[(1 << kFLitBits) + (1 << kFDstBits)];  // literal/length entries, then (at kFDstAt) distance entries
     FastCanon lc, dc;
-    uint16_t lsym[288], dsym[32];   // symbols ordered by (length, symbol)
+    uint32_t lsym[288], dsym[32];   // symbols ordered by (length, symbol), as table entries less the code length
     uint8_t lens[320];              // code lengths of the current block: literal/length, then distance
     uint32_t stage[kStageAlloc];    // the round's bits (padded layout); scratch while a header is parsed
 };
@@ -361,27 +364,25 @@ CCT_HD uint32_t brev32(uint32_t v) {
 }
 
 CCT_HD uint32_t lit_entry(int sym, int l) {
-    if (sym < 256) return (uint32_t)l | kEntLit | ((uint32_t)sym << 6);
+    if (sym < 256) return (uint32_t)l | kEntLit | ((uint32_t)sym << 16);
     if (sym == 256) return (uint32_t)l | kEntEob;
     const int idx = sym - 257;
     if (idx >= 29) return (uint32_t)l | kEntBad;
-    return (uint32_t)l | kEntLen | ((uint32_t)idx << 6);
+    return (uint32_t)l | kEntLen | ((uint32_t)len_extra_bits_inf(idx) << 6) | ((uint32_t)len_base_inf(idx) << 16);
 }
 CCT_HD uint32_t dst_entry(int sym, int l) {
     if (sym >= 30) return (uint32_t)l | kEntBad;
-    return (uint32_t)l | kEntLen | ((uint32_t)sym << 6);
+    return (uint32_t)l | kEntLen | ((uint32_t)(sym < 4 ? 0 : (sym >> 1) - 1) << 6) | ((uint32_t)dist_base_inf(sym) << 16);
 }
 
 // The code of `from`..`to` bits at the head of `bits` (LSB-first, as read from the stream), as a table entry;
 // 0 if none.  Canonical codes, left-justified, fill consecutive intervals in order of length, so the length is
 // the first l whose upper bound exceeds the (bit-reversed) head.  Requires: no code shorter than `from` matches.
-CCT_HD uint32_t canon_lookup(const FastCanon &c, const uint16_t *syms, uint32_t bits, int from, int to, bool lit) {
+// `syms` holds the symbols in canonical order, each as its table entry less the code length.
+CCT_HD uint32_t canon_lookup(const FastCanon &c, const uint32_t *syms, uint32_t bits, int from, int to) {
     const uint32_t v = brev32(bits) >> 1;
     for (int l = from; l <= to; l++) {
-        if (v < c.lim[l]) {
-            const int sym = syms[c.offs[l] + (int)(v >> (31 - l)) - (int)c.first[l]];
-            return lit ? lit_entry(sym, l) : dst_entry(sym, l);
-        }
+        if (v < c.lim[l]) return syms[c.offs[l] + (int)(v >> (31 - l)) - (int)c.first[l]] | (uint32_t)l;
     }
     return 0u;
 }
@@ -416,12 +417,12 @@ CCT_HDN inline bool fast_ranges(FastCanon &c) {
     return true;
 }
 // single lane: symbols ordered by (length, symbol).  `next` = 16 scratch counters.
-CCT_HDN inline void fast_sort(const uint8_t *lens, int nsym, const FastCanon &c, uint16_t *syms, uint16_t *next) {
+CCT_HDN inline void fast_sort(const uint8_t *lens, int nsym, const FastCanon &c, uint32_t *syms, uint16_t *next, bool lit) {
     for (int l = 0; l < 16; l++) next[l] = c.offs[l];
-    for (int i = 0; i < nsym; i++) if (lens[i]) syms[next[lens[i]]++] = (uint16_t)i;
+    for (int i = 0; i < nsym; i++) if (lens[i]) syms[next[lens[i]]++] = lit ? lit_entry(i, 0) : dst_entry(i, 0);
 }
-CCT_HD void fast_fill(const FastCanon &c, const uint16_t *syms, uint16_t *prim, int prim_bits, bool lit, int lane, int nl) {
-    for (int t = lane; t < (1 << prim_bits); t += nl) prim[t] = (uint16_t)canon_lookup(c, syms, (uint32_t)t, 1, prim_bits, lit);
+CCT_HD void fast_fill(const FastCanon &c, const uint32_t *syms, uint32_t *prim, int prim_bits, int lane, int nl) {
+    for (int t = lane; t < (1 << prim_bits); t += nl) prim[t] = canon_lookup(c, syms, (uint32_t)t, 1, prim_bits);
 }
 
 CCT_HD uint32_t stage_peek(const uint32_t *stage, uint32_t rel) {  // 32 bits starting `rel` bits into the staged words
@@ -437,55 +438,6 @@ CCT_HD uint32_t stage_peek(const uint32_t *stage, uint32_t rel) {  // 32 bits st
 struct Span { uint32_t end; int n, extra, flag; };  // where the last symbol ended; symbols; sum of (len - 1) over matches
 enum { kSpanRun = 0, kSpanEob = 1, kSpanBad = 2, kSpanFar = 3 };  // ran to the limit / end of block / invalid code or out of data / distance before the start
 
-// Decode the symbols that START in [p, limit).  Positions are in bits from the stream's aligned origin;
-// `origin` is the position of staged word 0, `data_end` the end of the deflate data.  WRITE: symbols -> out[],
-// `op` = bytes produced before this span (distance check).
-template <bool WRITE>
-CCT_HD void decode_span(const uint32_t *stage, uint32_t origin, uint32_t p, uint32_t limit, uint32_t data_end,
-                        const FastTables &tb, uint32_t *out, int op, Span &r) {
-    int n = 0, extra = 0, flag = kSpanRun;
-    while (p < limit) {
-        uint32_t bits = stage_peek(stage, p - origin);
-        uint32_t e = tb.lit[bits & ((1u << kFLitBits) - 1)];
-        if (!e) { e = canon_lookup(tb.lc, tb.lsym, bits, kFLitBits + 1, 15, true); if (!e) { flag = kSpanBad; break; } }
-        const uint32_t kind = e & kEntKind;
-        if (kind == kEntLit) {
-            p += e & 15u;
-            if (WRITE) out[n] = e >> 6;
-            n++;
-            continue;
-        }
-        if (kind != kEntLen) {
-            if (kind == kEntEob) { p += e & 15u; flag = kSpanEob; } else flag = kSpanBad;
-            break;
-        }
-        // the length's extra bits are still in `bits` (15 + 5 <= 32); one more peek covers the distance code and
-        // its extra bits (15 + 13 <= 32)
-        const uint32_t l = e & 15u;
-        const int li = (int)(e >> 6);
-        const uint32_t xb = (uint32_t)len_extra_bits_inf(li);
-        const int len = len_base_inf(li) + (int)((bits >> l) & ((1u << xb) - 1u));
-        uint32_t q = p + l + xb;
-        bits = stage_peek(stage, q - origin);
-        uint32_t d = tb.dst[bits & ((1u << kFDstBits) - 1)];
-        if (!d) { d = canon_lookup(tb.dc, tb.dsym, bits, kFDstBits + 1, 15, false); if (!d) { flag = kSpanBad; break; } }
-        if ((d & kEntKind) != kEntLen) { flag = kSpanBad; break; }
-        const uint32_t dl = d & 15u;
-        const int ds = (int)(d >> 6);
-        const uint32_t dxb = ds < 4 ? 0u : (uint32_t)(ds >> 1) - 1u;
-        const int dist = dist_base_inf(ds) + (int)((bits >> dl) & ((1u << dxb) - 1u));
-        q += dl + dxb;
-        if (WRITE) {
-            if (dist > op + n + extra) { flag = kSpanFar; break; }
-            out[n] = (uint32_t)(len - 3) | ((uint32_t)dist << 8);
-        }
-        p = q;
-        n++; extra += len - 1;
-    }
-    if (flag == kSpanRun && p >= data_end) flag = kSpanBad;  // the data ended before the block did
-    r.end = p; r.n = n; r.extra = extra; r.flag = flag;
-}
-
 // Sync marks.  A lane that decodes its sub-sequence again from another start falls into step with its earlier
 // list after a few symbols, and from there on the result is known.  The earlier list is remembered as one mark per
 // 32-bit word of the lane's window (kSubBits + the longest symbol): the offset of the first symbol boundary in
@@ -495,70 +447,93 @@ constexpr int kMarkWords = kSubBits / 32 + 2;
 constexpr uint32_t kMarkNone = 63u;
 CCT_HD uint32_t mark_pack(uint32_t off, int cnt, int ext) { return off | ((uint32_t)cnt << 6) | ((uint32_t)ext << 12); }
 
-// decode_span<false> from `p` for the lane whose window starts at `base`, keeping marks[w * MS] up to date.  With
-// `again`, marks[] and r describe the lane's previous list: the decode stops at the first word both lists enter at
-// the same bit, and the rest of r comes from the marks.  Without it every mark is written.
+// Decode the symbols that START in [p, limit).  Positions are in bits from the stream's aligned origin;
+// `origin` is the position of staged word 0, `data_end` the end of the deflate data.  WRITE: symbols -> out[],
+// `op` = bytes produced before this span (distance check).
+//
+// One pass of the loop reads ONE code -- literal/length, or the distance that follows a length -- and both kinds go
+// through the same instructions: a table entry carries the code length, the number of extra bits and the base value,
+// so "value = base + extra bits" is all there is to either.  The lanes of a warp therefore stay together whatever mix
+// of literals and matches each one meets (a loop that handles a whole match in one pass runs with a dozen of its 32
+// lanes active).
+//
+// MARKS (for the lane whose window starts at `base`): marks[w * MS] is kept up to date.  With `again`, marks[] and r
+// describe the lane's previous list: the decode stops at the first word both lists enter at the same bit, and the rest
+// of r comes from the marks.  Without it every mark is written.
+template <bool WRITE, bool MARKS, int MS>
+CCT_HD void decode_core(const uint32_t *stage, uint32_t origin, uint32_t base, uint32_t p, uint32_t limit, uint32_t data_end,
+                        const FastTables &tb, uint32_t *marks, bool again, uint32_t *out, int op, Span &r) {
+    int n = 0, extra = 0, flag = kSpanRun;
+    int wcur = 0, n0 = 0, e0 = 0;  // the word of the current symbol; n, extra when it was entered
+    uint32_t off = 0;
+    if (MARKS && p < base) p = base;  // the lane before ended short of its sub-sequence: the block ends there, or it decodes again
+    if (p < limit) {
+        if (MARKS) {
+            wcur = (int)((p - base) >> 5);
+            for (int w = 0; w < wcur; w++) marks[w * MS] = kMarkNone;  // the list starts later than the previous one did
+            off = (p - base) & 31u;
+        }
+        uint32_t mode = 0;  // 1: a length has been read, its distance is next
+        int len = 0;
+        bool fresh = MARKS;  // p is the first boundary of this list in word wcur
+        for (;;) {
+            if (MARKS && fresh) {
+                fresh = false;
+                if (again && (marks[wcur * MS] & 63u) == off) {
+                    for (int w = wcur; w < kMarkWords; w++) {
+                        const uint32_t m = marks[w * MS];
+                        n += (int)((m >> 6) & 63u); extra += (int)(m >> 12);
+                    }
+                    r.n = n; r.extra = extra;  // r.end and r.flag stand
+                    return;
+                }
+            }
+            const uint32_t bits = stage_peek(stage, p - origin);
+            uint32_t e = tb.tab[mode ? kFDstAt + (bits & ((1u << kFDstBits) - 1)) : (bits & ((1u << kFLitBits) - 1))];
+            if (!e) {
+                e = canon_lookup(mode ? tb.dc : tb.lc, mode ? tb.dsym : tb.lsym, bits, mode ? kFDstBits + 1 : kFLitBits + 1, 15);
+                if (!e) { flag = kSpanBad; break; }
+            }
+            const uint32_t l = e & 15u, xb = (e >> 6) & 15u, kind = e & kEntKind;
+            if (mode ? kind != kEntLen : kind > kEntLen) {
+                if (!mode && kind == kEntEob) { p += l; flag = kSpanEob; } else flag = kSpanBad;
+                break;
+            }
+            const int val = (int)(e >> 16) + (int)((bits >> l) & ((1u << xb) - 1u));  // (l + xb <= 28 bits of the 32)
+            p += l + xb;
+            if (!mode && kind == kEntLen) { len = val; mode = 1; continue; }
+            if (WRITE) {
+                if (mode && val > op + n + extra) { flag = kSpanFar; break; }
+                out[n] = mode ? (uint32_t)(len - 3) | ((uint32_t)val << 8) : (uint32_t)val;
+            }
+            n++;
+            if (mode) { extra += len - 1; mode = 0; }
+            if (p >= limit) break;
+            if (MARKS) {
+                const int wn = (int)((p - base) >> 5);
+                if (wn != wcur) {  // the next symbol starts in a later word
+                    marks[wcur * MS] = mark_pack(off, n - n0, extra - e0);
+                    for (int w = wcur + 1; w < wn; w++) marks[w * MS] = kMarkNone;  // a symbol longer than a word
+                    wcur = wn; off = (p - base) & 31u; n0 = n; e0 = extra;
+                    fresh = true;
+                }
+            }
+        }
+        if (MARKS) { marks[wcur * MS] = mark_pack(off, n - n0, extra - e0); wcur++; }
+    }
+    if (MARKS) for (int w = wcur; w < kMarkWords; w++) marks[w * MS] = kMarkNone;
+    if (flag == kSpanRun && p >= data_end) flag = kSpanBad;  // the data ended before the block did
+    r.end = p; r.n = n; r.extra = extra; r.flag = flag;
+}
+template <bool WRITE>
+CCT_HD void decode_span(const uint32_t *stage, uint32_t origin, uint32_t p, uint32_t limit, uint32_t data_end,
+                        const FastTables &tb, uint32_t *out, int op, Span &r) {
+    decode_core<WRITE, false, 1>(stage, origin, 0u, p, limit, data_end, tb, nullptr, false, out, op, r);
+}
 template <int MS>
 CCT_HD void decode_span_marks(const uint32_t *stage, uint32_t origin, uint32_t base, uint32_t p, uint32_t limit,
                               uint32_t data_end, const FastTables &tb, uint32_t *marks, bool again, Span &r) {
-    int n = 0, extra = 0, flag = kSpanRun;
-    int wcur = 0;
-    if (p < base) p = base;  // the lane before ended short of its sub-sequence: the block ends there, or it decodes again
-    if (p < limit) {
-        wcur = (int)((p - base) >> 5);
-        for (int w = 0; w < wcur; w++) marks[w * MS] = kMarkNone;  // the list starts later than the previous one did
-        uint32_t off = (p - base) & 31u;
-        int n0 = 0, e0 = 0;  // n, extra when the word was entered
-        for (;;) {
-            // p is the first boundary of this list in word wcur
-            if (again && (marks[wcur * MS] & 63u) == off) {
-                for (int w = wcur; w < kMarkWords; w++) {
-                    const uint32_t m = marks[w * MS];
-                    n += (int)((m >> 6) & 63u); extra += (int)(m >> 12);
-                }
-                r.n = n; r.extra = extra;  // r.end and r.flag stand
-                return;
-            }
-            int wn = wcur;
-            do {  // the symbols that start in word wcur
-                uint32_t bits = stage_peek(stage, p - origin);
-                uint32_t e = tb.lit[bits & ((1u << kFLitBits) - 1)];
-                if (!e) { e = canon_lookup(tb.lc, tb.lsym, bits, kFLitBits + 1, 15, true); if (!e) { flag = kSpanBad; break; } }
-                const uint32_t kind = e & kEntKind;
-                if (kind == kEntLit) {
-                    p += e & 15u;
-                    n++;
-                } else {
-                    if (kind != kEntLen) {
-                        if (kind == kEntEob) { p += e & 15u; flag = kSpanEob; } else flag = kSpanBad;
-                        break;
-                    }
-                    const uint32_t l = e & 15u;
-                    const int li = (int)(e >> 6);
-                    const uint32_t xb = (uint32_t)len_extra_bits_inf(li);
-                    const int len = len_base_inf(li) + (int)((bits >> l) & ((1u << xb) - 1u));
-                    const uint32_t q = p + l + xb;
-                    bits = stage_peek(stage, q - origin);
-                    uint32_t d = tb.dst[bits & ((1u << kFDstBits) - 1)];
-                    if (!d) { d = canon_lookup(tb.dc, tb.dsym, bits, kFDstBits + 1, 15, false); if (!d) { flag = kSpanBad; break; } }
-                    if ((d & kEntKind) != kEntLen) { flag = kSpanBad; break; }
-                    const int ds = (int)(d >> 6);
-                    const uint32_t dxb = ds < 4 ? 0u : (uint32_t)(ds >> 1) - 1u;
-                    p = q + (d & 15u) + dxb;
-                    n++; extra += len - 1;
-                }
-                wn = (int)((p - base) >> 5);
-            } while (wn == wcur && p < limit);
-            marks[wcur * MS] = mark_pack(off, n - n0, extra - e0);
-            if (flag != kSpanRun || p >= limit) break;
-            for (int w = wcur + 1; w < wn; w++) marks[w * MS] = kMarkNone;  // a symbol longer than a word
-            wcur = wn; off = (p - base) & 31u; n0 = n; e0 = extra;
-        }
-        wcur++;
-    }
-    for (int w = wcur; w < kMarkWords; w++) marks[w * MS] = kMarkNone;
-    if (flag == kSpanRun && p >= data_end) flag = kSpanBad;  // the data ended before the block did
-    r.end = p; r.n = n; r.extra = extra; r.flag = flag;
+    decode_core<false, true, MS>(stage, origin, base, p, limit, data_end, tb, marks, again, nullptr, 0, r);
 }
 
 // Block header (RFC 1951 3.2.3 - 3.2.7), single lane: leaves the code lengths in tb.lens (literal/length codes

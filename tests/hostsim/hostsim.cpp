@@ -368,14 +368,14 @@ int hs_inflate_lanes(const uint8_t *in_, int in_len, uint8_t *out, int out_cap, 
         for (int pass = 0; pass < 2 && good; pass++) {
             const bool lit = pass == 0;
             FastCanon &c = lit ? tb->lc : tb->dc;
-            uint16_t *sy = lit ? tb->lsym : tb->dsym;
+            uint32_t *sy = lit ? tb->lsym : tb->dsym;
             const uint8_t *lens = tb->lens + (lit ? 0 : nlen);
             const int n = lit ? nlen : ndist;
             for (int l = 0; l < 16; l++) c.count[l] = 0;
             fast_count(lens, n, c, 0, 1);
             if (!fast_ranges(c)) { good = false; break; }
-            fast_sort(lens, n, c, sy, reinterpret_cast<uint16_t *>(tb->stage));
-            fast_fill(c, sy, lit ? tb->lit : tb->dst, lit ? kFLitBits : kFDstBits, lit, 0, 1);
+            fast_sort(lens, n, c, sy, reinterpret_cast<uint16_t *>(tb->stage), lit);
+            fast_fill(c, sy, tb->tab + (lit ? 0 : kFDstAt), lit ? kFLitBits : kFDstBits, 0, 1);
         }
         if (!good) break;
         uint32_t q = bp + skew;
