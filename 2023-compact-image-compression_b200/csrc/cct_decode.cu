@@ -55,6 +55,9 @@ struct StreamSrc {  // where stream i lives: arena + offsets (with a header to s
 
 // One stream per CTA of kSubLanes threads, all lanes decoding (inflate_core.cuh, "Lane-parallel Huffman decode");
 // the stream's tables, the staged bits of the round and the few words the lanes exchange live in shared memory.
+#ifndef CCT_INF_CTAS
+#define CCT_INF_CTAS 10  // resident CTAs per SM the register budget is set for (shared memory allows ten)
+#endif
 constexpr int kInfWarps = kSubLanes / 32;
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -200,7 +203,7 @@ __device__ __forceinline__ bool cta_block_symbols(const StreamBits &sb, uint32_t
     }
 }
 
-__global__ void __launch_bounds__(kSubLanes) k_inflate_sym(StreamSrc src, const uint8_t *__restrict__ fl, int B,
+__global__ void __launch_bounds__(kSubLanes, CCT_INF_CTAS) k_inflate_sym(StreamSrc src, const uint8_t *__restrict__ fl, int B,
                                                            uint32_t *__restrict__ syms_all, int64_t sym_stride, int out_cap,
                                                            int32_t *__restrict__ nsym, int32_t *__restrict__ out_len,
                                                            uint32_t *__restrict__ adler_want, uint32_t *__restrict__ status) {
