@@ -68,16 +68,19 @@ size_t deflate_ws_carve(DeflateWs *ws, void *mem, int B, int64_t max_len) {
 
 // ------------------------------------------------------------------ k_run_*
 // Run lengths around every position: rb[p] / rl[p] = number of bytes equal to w[p] immediately before / after p,
-// packed into runs[p] = rl | rb << 16 (each capped at 65535) for the group step of the scan.  One warp owns a chunk of
-// kRunChunk positions, 32 per step, one position per lane: "where did the current run start" is a ballot and a
-// count-leading-zeros, the value entering the next step one shuffle -- no shared memory, coalesced loads and stores.
+// packed into runs[p] = rl | rb << 16 (each capped at 65535) for the group step of the scan.  Everything follows from
+// one flag per position, E[p] = (w[p] == w[p - 1]): rb counts the flags set up to p, rl those set from p + 1 on.
+// One warp owns a chunk of kRunChunk positions, 128 per step: a lane takes one aligned 32-bit word of the payload, its
+// four flags are one SIMD byte compare, and "where is the nearest cleared flag" is a ballot of the lanes whose four
+// flags are not all set, a count-leading-zeros and one shuffle -- no shared memory, 4-byte loads, 16-byte stores.
 // Chunks are independent once the count entering each is known, so the work is three launches:
 //   k_run_edges  per chunk: (does one run cover the whole chunk?, count leaving it if nothing came in), both ways
 //   k_run_link   per stream: warp scan of those summaries -> the count entering every chunk from either side
 //   k_run_counts per chunk: counts of every position, written out
 // The summaries combine as (whole, val) o (whole', val') = whole' ? (whole, val + val') : (false, val').
-constexpr int kRunChunk = 256;
-constexpr int kRunSteps = kRunChunk / 32;
+// (The payload rows are 16-byte aligned: include/compact_b200.h.)
+constexpr int kRunChunk = 1024;
+constexpr int kRunSteps = kRunChunk / 128;
 constexpr int kRunWarps = 8;
 constexpr unsigned kAll = 0xffffffffu;
 
@@ -86,50 +89,62 @@ __device__ __forceinline__ RunCarry run_combine(RunCarry a, RunCarry b) {  // a 
     return b.whole ? RunCarry{a.whole, a.val + b.val} : RunCarry{0, b.val};
 }
 
-// The chunk's bytes, one per lane per step (c[j] = w[base + 32 j + lane], 0 past the end), and the bytes around it.
-struct RunBytes { uint32_t c[kRunSteps]; uint32_t before, after; };  // before = w[base - 1]; after: lanes 0..2 hold w[base + kRunChunk + lane]
-__device__ __forceinline__ void run_bytes(RunBytes &r, const uint8_t *w, int n, int base, int lane) {
+// The flags of a chunk: nibble j of `e` = E of the lane's four positions in step j (position base + 128 j + 4 lane + k
+// in bit k); `after` = E[base + kRunChunk] (the same in every lane).
+struct RunFlags { uint32_t e, after; };
+__device__ __forceinline__ RunFlags run_flags(const uint32_t *words, int n, int base, int lane) {
+    const int end = n;
+    RunFlags r{0u, 0u};
+    uint32_t last = base > 0 ? __ldg(words + (base >> 2) - 1) : 0u;  // the word before the step's (lane 0 needs its top byte)
 #pragma unroll
-    for (int j = 0; j < kRunSteps; j++) { const int p = base + 32 * j + lane; r.c[j] = p < n ? __ldg(w + p) : 0u; }
-    r.before = base > 0 ? __ldg(w + base - 1) : 0u;
-    const int q = base + kRunChunk + lane;
-    r.after = (lane < 3 && q < n) ? __ldg(w + q) : 0u;
+    for (int j = 0; j < kRunSteps; j++) {
+        const int p0 = base + 128 * j + 4 * lane;
+        const uint32_t w = p0 < end ? __ldg(words + (p0 >> 2)) : 0u;
+        uint32_t pb = __shfl_up_sync(kAll, w, 1);
+        if (lane == 0) pb = last;
+        last = __shfl_sync(kAll, w, 31);
+        const uint32_t cmp = __vcmpeq4(w, (w << 8) | (pb >> 24));  // byte k: 0xff where w[p0 + k] == w[p0 + k - 1]
+        // E is defined for 1 <= p < n
+        const int lo = 1 - p0, hi = end - p0;
+        const uint32_t vm = (lo <= 0 ? 0xffffffffu : lo >= 4 ? 0u : 0xffffffffu << (8 * lo)) &
+                            (hi >= 4 ? 0xffffffffu : hi <= 0 ? 0u : 0xffffffffu >> (8 * (4 - hi)));
+        r.e |= (((cmp & vm & 0x01010101u) * 0x01020408u) >> 24) << (4 * j);  // bit 0 of each byte -> a nibble
+    }
+    const int q = base + kRunChunk;
+    if (q < end) r.after = (__ldg(words + (q >> 2)) & 0xFFu) == (last >> 24) ? 1u : 0u;
+    return r;
 }
-// step j: mask of lanes whose byte equals the byte before it / after it (false outside the payload)
-__device__ __forceinline__ unsigned run_eq_prev(const RunBytes &r, int j, int n, int base, int lane) {
-    const uint32_t prev_group = j ? r.c[j - 1] : 0u;
-    uint32_t pc = __shfl_up_sync(kAll, r.c[j], 1);
-    const uint32_t last_of_prev = __shfl_sync(kAll, prev_group, 31);
-    if (lane == 0) pc = j ? last_of_prev : r.before;
-    const int p = base + 32 * j + lane;
-    return __ballot_sync(kAll, p >= 1 && p < n && r.c[j] == pc);
-}
-__device__ __forceinline__ unsigned run_eq_next(const RunBytes &r, int j, int n, int base, int lane) {
-    const uint32_t next_group = j + 1 < kRunSteps ? r.c[j + 1] : r.after;
-    uint32_t nc = __shfl_down_sync(kAll, r.c[j], 1);
-    const uint32_t first_of_next = __shfl_sync(kAll, next_group, 0);
-    if (lane == 31) nc = first_of_next;
-    const int p = base + 32 * j + lane;
-    return __ballot_sync(kAll, p + 1 < n && r.c[j] == nc);
+__device__ __forceinline__ int top_ones(uint32_t nib) { return __clz((int)~(nib << 28)); }    // set flags at the top of a nibble (0..4)
+__device__ __forceinline__ int low_ones(uint32_t nib) { return __ffs((int)(~nib & 0x1Fu | 0x10u)) - 1; }  // ... at the bottom
+// the nibble of "next" flags F[p] = E[p + 1] of the lane's positions in step j
+__device__ __forceinline__ uint32_t run_next_nibble(const RunFlags &r, int j, int lane) {
+    const uint32_t e4 = (r.e >> (4 * j)) & 0xFu;
+    uint32_t nb = __shfl_down_sync(kAll, e4, 1) & 1u;
+    const uint32_t wrap = j + 1 < kRunSteps ? __shfl_sync(kAll, (r.e >> (4 * (j + 1) & 31)) & 1u, 0) : r.after;
+    if (lane == 31) nb = wrap;
+    return (e4 >> 1) | (nb << 3);
 }
 
 __global__ void __launch_bounds__(32 * kRunWarps) k_run_edges(const uint8_t *__restrict__ in, int64_t in_stride,
                                                              const int32_t *__restrict__ in_len, int4 *__restrict__ edges, int max_chunks) {
     const int stream = blockIdx.y, chunk = blockIdx.x * kRunWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    const int base = chunk * kRunChunk, n = in_len[stream];
+    const int n = in_len[stream], base = chunk * kRunChunk;
     if (base >= n) return;
-    RunBytes r;
-    run_bytes(r, in + (int64_t)stream * in_stride, n, base, lane);
+    const RunFlags r = run_flags(reinterpret_cast<const uint32_t *>(in + (int64_t)stream * in_stride), n, base, lane);
     int fw = 1, fv = 0, bw = 1, bv = 0;
 #pragma unroll
     for (int j = 0; j < kRunSteps; j++) {
-        const unsigned m = run_eq_prev(r, j, n, base, lane);
-        if (m == kAll) fv += 32; else { fw = 0; fv = __clz((int)~m); }  // equal flags at the top of the group
+        const uint32_t e4 = (r.e >> (4 * j)) & 0xFu;
+        const unsigned open = __ballot_sync(kAll, e4 != 0xFu);  // lanes with a cleared flag
+        if (!open) fv += 128;
+        else { const int l = 31 - __clz((int)open); fw = 0; fv = __shfl_sync(kAll, top_ones(e4), l) + 4 * (31 - l); }
     }
 #pragma unroll
     for (int j = kRunSteps - 1; j >= 0; j--) {
-        const unsigned m = run_eq_next(r, j, n, base, lane);
-        if (m == kAll) bv += 32; else { bw = 0; bv = __ffs((int)~m) - 1; }  // equal flags at the bottom of the group
+        const uint32_t f4 = run_next_nibble(r, j, lane);
+        const unsigned open = __ballot_sync(kAll, f4 != 0xFu);
+        if (!open) bv += 128;
+        else { const int l = __ffs((int)open) - 1; bw = 0; bv = __shfl_sync(kAll, low_ones(f4), l) + 4 * l; }
     }
     if (lane == 0) edges[(int64_t)stream * max_chunks + chunk] = make_int4(fw, fv, bw, bv);
 }
@@ -168,32 +183,48 @@ __global__ void __launch_bounds__(32 * kRunWarps) k_run_counts(const uint8_t *__
                                                               const int32_t *__restrict__ in_len, const int2 *__restrict__ enters,
                                                               int max_chunks, uint32_t *__restrict__ runs_all, int64_t stride) {
     const int stream = blockIdx.y, chunk = blockIdx.x * kRunWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    const int base = chunk * kRunChunk, n = in_len[stream];
+    const int n = in_len[stream], base = chunk * kRunChunk;
     if (base >= n) return;
     uint32_t *runs = runs_all + (int64_t)stream * stride;
     asm volatile("" : "+l"(runs));  // (kept in registers instead of re-derived from the parameters)
-    RunBytes r;
-    run_bytes(r, in + (int64_t)stream * in_stride, n, base, lane);
+    const RunFlags r = run_flags(reinterpret_cast<const uint32_t *>(in + (int64_t)stream * in_stride), n, base, lane);
     const int2 enter = enters[(int64_t)stream * max_chunks + chunk];
-    uint32_t rb[kRunSteps];
-    int carry = enter.x;  // count of the position just before the group
+    uint32_t rb[kRunSteps];  // the four counts of step j, a byte each would not do: two 16-bit halves per word, two words
+    uint32_t rb2[kRunSteps];
+    const unsigned below = (1u << lane) - 1u;
+    int carry = enter.x;  // count of the position just before the step
 #pragma unroll
     for (int j = 0; j < kRunSteps; j++) {
-        const unsigned m = run_eq_prev(r, j, n, base, lane);
-        const unsigned zeros_below = ~m & ((2u << lane) - 1u);  // positions <= lane whose flag is 0
-        const int back = zeros_below ? lane - (31 - __clz((int)zeros_below)) : lane + 1 + carry;
-        carry = __shfl_sync(kAll, back, 31);
-        rb[j] = (uint32_t)min(back, 65535);
+        const uint32_t e4 = (r.e >> (4 * j)) & 0xFu;
+        const unsigned open = __ballot_sync(kAll, e4 != 0xFu) & below;  // lanes below with a cleared flag
+        const int l = open ? 31 - __clz((int)open) : 0;
+        const int t = __shfl_sync(kAll, top_ones(e4), l);
+        const int ent = open ? t + 4 * (lane - l - 1) : carry + 4 * lane;  // count of the position just before the lane's four
+        const int b0 = (e4 & 1u) ? ent + 1 : 0, b1 = (e4 & 2u) ? b0 + 1 : 0, b2 = (e4 & 4u) ? b1 + 1 : 0, b3 = (e4 & 8u) ? b2 + 1 : 0;
+        carry = __shfl_sync(kAll, b3, 31);
+        rb[j] = (uint32_t)min(b0, 65535) | ((uint32_t)min(b1, 65535) << 16);
+        rb2[j] = (uint32_t)min(b2, 65535) | ((uint32_t)min(b3, 65535) << 16);
     }
-    carry = enter.y;  // count of the position just after the group
+    const unsigned above = ~below & ~(1u << lane);
+    carry = enter.y;  // count of the position just after the step
 #pragma unroll
     for (int j = kRunSteps - 1; j >= 0; j--) {
-        const unsigned m = run_eq_next(r, j, n, base, lane);
-        const unsigned zeros_above = ~m & ~((1u << lane) - 1u);  // positions >= lane whose flag is 0
-        const int fwd = zeros_above ? (__ffs((int)zeros_above) - 1) - lane : (32 - lane) + carry;
-        carry = __shfl_sync(kAll, fwd, 0);
-        const int p = base + 32 * j + lane;
-        if (p < n) runs[p] = (uint32_t)min(fwd, 65535) | (rb[j] << 16);
+        const uint32_t f4 = run_next_nibble(r, j, lane);
+        const unsigned open = __ballot_sync(kAll, f4 != 0xFu) & above;  // lanes above with a cleared flag
+        const int l = open ? __ffs((int)open) - 1 : 0;
+        const int t = __shfl_sync(kAll, low_ones(f4), l);
+        const int ext = open ? t + 4 * (l - lane - 1) : carry + 4 * (31 - lane);  // count of the position just after the lane's four
+        const int f3 = (f4 & 8u) ? ext + 1 : 0, f2 = (f4 & 4u) ? f3 + 1 : 0, f1 = (f4 & 2u) ? f2 + 1 : 0, f0 = (f4 & 1u) ? f1 + 1 : 0;
+        carry = __shfl_sync(kAll, f0, 0);
+        const int p0 = base + 128 * j + 4 * lane;
+        const uint4 v = make_uint4((uint32_t)min(f0, 65535) | (rb[j] << 16), (uint32_t)min(f1, 65535) | (rb[j] & 0xFFFF0000u),
+                                   (uint32_t)min(f2, 65535) | (rb2[j] << 16), (uint32_t)min(f3, 65535) | (rb2[j] & 0xFFFF0000u));
+        if (p0 + 4 <= n) *reinterpret_cast<uint4 *>(runs + p0) = v;
+        else {
+            if (p0 < n) runs[p0] = v.x;
+            if (p0 + 1 < n) runs[p0 + 1] = v.y;
+            if (p0 + 2 < n) runs[p0 + 2] = v.z;
+        }
     }
 }
 
