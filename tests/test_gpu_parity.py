@@ -123,6 +123,8 @@ def test_deflate_matches_libz(torch_cuda, native, oracle, synth):
     blobs = [b for b in _corpus() if len(b) > 0]
     for s in (0, 1):
         blobs.append(oracle.encode(synth.synth_ct(s), detail=True)[1]["payload"])
+    from test_oracle import _lz_stress
+    blobs += [_lz_stress(3, 300000), _lz_stress(4, 70001)]
     got = _gpu_deflate(torch_cuda, native, blobs)
     for b, g in zip(blobs, got):
         assert g == zlib.compress(b, 9), len(b)
@@ -155,6 +157,14 @@ def test_inflate_any_conformant_stream(torch_cuda, native):
         got, st = _gpu_inflate(torch_cuda, native, streams, cap)
         assert not st.any()
         for b, g in zip(blobs, got):
+            assert g == b, (level, len(b))
+    # copies from anywhere in the window, byte runs and literal bursts mixed; rows that do not start on 16 bytes
+    from test_oracle import _lz_stress
+    stress = [_lz_stress(3, 300000), _lz_stress(4, 70001), _lz_stress(5, 123457)]
+    for level in (1, 6, 9):
+        got, st = _gpu_inflate(torch_cuda, native, [zlib.compress(b, level) for b in stress], 300003)
+        assert not st.any()
+        for b, g in zip(stress, got):
             assert g == b, (level, len(b))
     # corrupt streams are flagged, not crashed on
     bad = bytearray(zlib.compress(blobs[-1], 9))

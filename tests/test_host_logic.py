@@ -239,6 +239,10 @@ def test_inflate_lane_parallel_core(hostsim, golden_cct):
     assert _hs_inflate_lanes(hostsim, bytes(z), 256 * 40)[0] is None  # corrupt -> error
     assert _hs_inflate_lanes(hostsim, zlib.compress(b"abc" * 100, 9), 10)[0] is None  # output overflow -> error
     assert _hs_inflate_lanes(hostsim, zlib.compress(payload, 9)[:-9], len(payload))[0] is None  # truncated -> error
+    from test_oracle import _lz_stress
+    stress = _lz_stress()
+    for level in (1, 6, 9):
+        assert _hs_inflate_lanes(hostsim, zlib.compress(stress, level), len(stress), level & 3)[0] == stress, level
 
 
 def test_payload_decode_core(hostsim, oracle, synth, golden_cct):
