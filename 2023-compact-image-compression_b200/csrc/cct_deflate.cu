@@ -318,9 +318,10 @@ __global__ void __launch_bounds__(kHsThreads) k_hs_hist(const uint8_t *__restric
 // counts -> absolute offsets inside the stream: thist[tile][bin] = start of the tile's share of the bin;
 // binbase[stream][bin] = start of the bin (binbase[stream][128] = number of chain members)
 __global__ void __launch_bounds__(kHsBins) k_hs_scan(const int32_t *__restrict__ in_len, uint32_t *__restrict__ thist, int max_tiles,
-                                                     uint32_t *__restrict__ binbase) {
+                                                     uint32_t *__restrict__ binbase, uint32_t *__restrict__ tails, int64_t stride) {
     __shared__ uint32_t tot[kHsBins];
     const int stream = blockIdx.x, d = threadIdx.x, n = in_len[stream];
+    if (d == 0) tails[(int64_t)stream * stride] = 0;  // the stream's list of run tails (k_bprobe appends, k_run_tails works it off)
     const int nt = (n + kHsTile - 1) / kHsTile;
     uint32_t *h = thist + (int64_t)stream * max_tiles * kHsBins + d;
     uint32_t run = 0;
@@ -534,11 +535,11 @@ constexpr int kBprobeCtas = CCT_BPROBE_CTAS;  // CTAs per stream (each strides o
 __global__ void __launch_bounds__(kBprobeThreads, 1536 / kBprobeThreads) k_bprobe(const uint8_t *__restrict__ in, int64_t in_stride,
                                                            const int32_t *__restrict__ in_len, const SortEnt *__restrict__ ent_all,
                                                            const uint32_t *__restrict__ runs_all, uint32_t *__restrict__ mlo_all,
-                                                           uint32_t *__restrict__ mhi_all, int64_t stride) {
+                                                           uint32_t *__restrict__ mhi_all, uint32_t *__restrict__ tails_all, int64_t stride) {
     const int stream = blockIdx.y, n = in_len[stream];
     const int members = n >= 4 ? n - 3 : 0;
     const int64_t o = (int64_t)stream * stride;
-    uint32_t *mlo = mlo_all + o, *mhi = mhi_all + o;
+    uint32_t *mlo = mlo_all + o, *mhi = mhi_all + o, *tails = tails_all + o;
     if (blockIdx.x == 0 && threadIdx.x < 3) {  // positions that are in no chain: 0 and the last two
         const int p = threadIdx.x == 0 ? 0 : n - 3 + (int)threadIdx.x;
         if (p >= 0 && p < n && (threadIdx.x == 0 || p >= 1)) mlo[p] = 0;
@@ -548,7 +549,7 @@ __global__ void __launch_bounds__(kBprobeThreads, 1536 / kBprobeThreads) k_bprob
     const uint32_t *runs_s = runs_all + o;
     // opaque to the compiler: it would otherwise re-derive the three bases from the kernel parameters (six instructions)
     // at every use inside the walks instead of keeping them
-    asm volatile("" : "+l"(w_s), "+l"(ent_s), "+l"(runs_s), "+l"(mlo), "+l"(mhi));
+    asm volatile("" : "+l"(w_s), "+l"(ent_s), "+l"(runs_s), "+l"(mlo), "+l"(mhi), "+l"(tails));
     BucketView v{w_s, ent_s, runs_s, n};
     // (the walks are warp-wide: all 32 lanes go round together, lanes past the end idle)
     const int lane = threadIdx.x & 31;
@@ -557,7 +558,7 @@ __global__ void __launch_bounds__(kBprobeThreads, 1536 / kBprobeThreads) k_bprob
         const bool valid = i < members;
         const SortEnt me = valid ? load_ent(v.ent + i) : SortEnt{kEntFirst, 0u};
         uint32_t lo, hi;
-        const bool settled = bucket_probe_quick(v, i, me, valid, &lo);
+        const bool settled = bucket_probe_quick(v, i, me, valid, true, &lo);
         hi = lo;
         if (__any_sync(0xffffffffu, !settled)) {
             uint32_t glo, ghi;
@@ -566,9 +567,74 @@ __global__ void __launch_bounds__(kBprobeThreads, 1536 / kBprobeThreads) k_bprob
         }
         if (valid) {
             const int p = ent_pos(me);
-            if (lo != hi) { mhi[p] = hi; lo |= kProbeHiDiff; }
-            mlo[p] = lo;
+            if (lo >= kProbeTail) {  // a member of a byte run: k_run_tails writes the entries; the start announces the run
+                if (lo == kProbeTailLeader) tails[1u + atomicAdd(tails, 1u)] = (uint32_t)i;
+            } else {
+                if (lo != hi) { mhi[p] = hi; lo |= kProbeHiDiff; }
+                mlo[p] = lo;
+            }
         }
+    }
+}
+
+// ------------------------------------------------------------------ k_run_tails
+// The chain members of byte runs (deflate_core.cuh, "byte runs, settled once per run"): the starts announced by k_bprobe,
+// a lane per run, 32 neighbouring runs per warp.  The lanes walk the run groups below their runs together (run_collect:
+// the start's table entry, the few groups that can give the run's tail a longer match than the run itself); then, run by
+// run, the tail targets -- consecutive entries of the sorted array, consecutive positions -- read their entries off
+// those records, 32 at a time.  A run the walk cannot summarise goes through the general walk.
+constexpr int kTailWarps = 4, kTailCtas = 8;
+__global__ void __launch_bounds__(32 * kTailWarps) k_run_tails(const uint8_t *__restrict__ in, int64_t in_stride,
+                                                              const int32_t *__restrict__ in_len, const SortEnt *__restrict__ ent_all,
+                                                              const uint32_t *__restrict__ runs_all, uint32_t *__restrict__ mlo_all,
+                                                              uint32_t *__restrict__ mhi_all, const uint32_t *__restrict__ tails_all,
+                                                              int64_t stride) {
+    __shared__ TailGroup recs[kTailWarps][kTailRecords][32];
+    const int stream = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t o = (int64_t)stream * stride;
+    const uint32_t *tails = tails_all + o;
+    const int cnt = (int)tails[0];
+    if ((int)blockIdx.x * kTailWarps * 32 >= cnt) return;
+    uint32_t *mlo = mlo_all + o, *mhi = mhi_all + o;
+    BucketView v{in + (int64_t)stream * in_stride, ent_all + o, runs_all + o, in_len[stream]};
+    auto put = [&](int p, uint32_t lo, uint32_t hi) {
+        if (lo != hi) { mhi[p] = hi; lo |= kProbeHiDiff; }
+        mlo[p] = lo;
+    };
+    for (int base = (blockIdx.x * kTailWarps + wid) * 32; base < cnt; base += gridDim.x * kTailWarps * 32) {
+        const bool have = base + lane < cnt;
+        const int i0 = have ? (int)tails[1 + base + lane] : 0;
+        uint32_t slo, shi;
+        const int nrec = run_collect(v, i0, have, &recs[wid][0][lane], 32, &slo, &shi);
+        int s0 = 0, len = 0;
+        if (have) {
+            s0 = ent_pos(load_ent(v.ent + i0));
+            len = (int)(load_u32(v.runs + s0) & 0xFFFFu) + 1;
+            if (nrec >= 0) put(s0, slo, shi);
+        }
+        __syncwarp();
+        const int nruns = min(32, cnt - base);
+        for (int l = 0; l < nruns; l++) {  // (everything below is the same for all lanes: the loops are warp-wide)
+            const int li0 = __shfl_sync(kAll, i0, l), ls0 = __shfl_sync(kAll, s0, l), llen = __shfl_sync(kAll, len, l);
+            const int lnrec = __shfl_sync(kAll, nrec, l);
+            const int jmin = max(1, llen - (kMaxMatch - 1)), jmax = llen - kMinMatch;  // the tail: R = len - j = 257 .. 3
+            uint32_t lo, hi;
+            if (lnrec >= 0) {
+                for (int j = jmin + lane; j <= jmax; j += 32) {
+                    tail_entry(&recs[wid][0][l], 32, lnrec, llen - j, &lo, &hi);
+                    put(ls0 + j, lo, hi);
+                }
+            } else {
+                for (int jb = jmin - 32; jb <= jmax; jb += 32) {  // (the first round is the start's, in lane 0)
+                    const int j = jb < jmin ? 0 : jb + lane;
+                    const bool valid = jb < jmin ? lane == 0 : j <= jmax;
+                    const SortEnt me = valid ? load_ent(v.ent + li0 + j) : SortEnt{kEntFirst, 0u};
+                    bucket_probe(v, li0 + j, me, valid, &lo, &hi);
+                    if (valid) put(ls0 + j, lo, hi);
+                }
+            }
+        }
+        __syncwarp();  // (the records are overwritten by the next 32 runs)
     }
 }
 
@@ -978,7 +1044,7 @@ static void launch_match_tables(const uint8_t *in, int64_t in_stride, const int3
     k_hs_hist<<<gtile, kHsThreads, 0, st>>>(in, in_stride, in_len, ws.thist, ws.max_tiles);
     }
     { CCT_KERNEL(k_hs_scan, st);
-    k_hs_scan<<<B, kHsBins, 0, st>>>(in_len, ws.thist, ws.max_tiles, ws.binbase);
+    k_hs_scan<<<B, kHsBins, 0, st>>>(in_len, ws.thist, ws.max_tiles, ws.binbase, ws.rec, ws.stride);
     }
     { CCT_KERNEL(k_hs_split, st);
     k_hs_split<<<gtile, kHsThreads, 0, st>>>(in, in_stride, in_len, ws.thist, ws.max_tiles, ws.p1, ws.stride);
@@ -996,7 +1062,12 @@ static void launch_match_tables(const uint8_t *in, int64_t in_stride, const int3
     {
         dim3 gp((unsigned)std::min<int64_t>((max_len + kBprobeThreads - 1) / kBprobeThreads, kBprobeCtas), (unsigned)B);
         CCT_KERNEL(k_bprobe, st);
-        k_bprobe<<<gp, kBprobeThreads, 0, st>>>(in, in_stride, in_len, ws.ent, ws.runs, ws.mtab, ws.mhi, ws.stride);
+        k_bprobe<<<gp, kBprobeThreads, 0, st>>>(in, in_stride, in_len, ws.ent, ws.runs, ws.mtab, ws.mhi, ws.rec, ws.stride);
+    }
+    {
+        CCT_KERNEL(k_run_tails, st);
+        k_run_tails<<<dim3(kTailCtas, (unsigned)B), 32 * kTailWarps, 0, st>>>(in, in_stride, in_len, ws.ent, ws.runs, ws.mtab, ws.mhi,
+                                                                              ws.rec, ws.stride);
     }
 }
 

@@ -33,6 +33,7 @@ namespace cct {
 // probe-table entry: bits 0..8 best length (0 = no match), bits 9..23 distance; in the budget-4096 table bit 30 says
 // that the budget-1024 entry differs (and is stored in the second table; otherwise that table holds nothing)
 constexpr uint32_t kProbeHiDiff = 0x40000000u;
+constexpr uint32_t kProbeTail = 0x80000000u, kProbeTailLeader = 0x80000001u;  // (bucket_probe_quick: left to tail_collect / tail_entry)
 CCT_HD uint32_t mtab_pack(int len, int dist) { return (uint32_t)len | ((uint32_t)dist << 9); }
 CCT_HD int mtab_len(uint32_t e) { return (int)(e & 511u); }
 CCT_HD int mtab_dist(uint32_t e) { return (int)((e >> 9) & 32767u); }
@@ -289,6 +290,8 @@ CCT_HD void bucket_probe(const BucketView &v, int i, const SortEnt &me, bool act
     }
 }
 
+CCT_HD uint32_t run_class(int s, int n, uint32_t ri);  // (byte runs, settled once per run: further down)
+
 // The same walk for the common targets, with far fewer instructions.  Returns false when the walk meets anything it
 // does not handle (the caller then runs bucket_probe from the start); true with the table entry, valid for both
 // budgets, otherwise (and for idle lanes).
@@ -298,10 +301,12 @@ CCT_HD void bucket_probe(const BucketView &v, int i, const SortEnt &me, bool act
 //     match four bytes are only noted (a bit per candidate) and measured after every 32 candidates -- inside the loop
 //     the two lanes that need the payload would stall the other thirty.  The result does not depend on that order: it
 //     is the longest candidate, the nearest among equals.
+//   * With `tails` set, the members of a byte run that run_collect settles once per run (run_class) are not walked at
+//     all: the entry returned is the marker kProbeTail, or kProbeTailLeader for the start of the run.
 //   * A position inside a byte run with at least the maximum match length still to go: its predecessor matches that
 //     much, at distance 1, and nothing can beat it.  Likewise one with more than 4096 run members below it: they all
 //     match exactly the rest of the run and use up the chain budget before anything else is seen.
-CCT_HD bool bucket_probe_quick(const BucketView &v, int i, const SortEnt &me, bool active, uint32_t *out) {
+CCT_HD bool bucket_probe_quick(const BucketView &v, int i, const SortEnt &me, bool active, bool tails, uint32_t *out) {
     *out = 0;
     // state of the lane's walk: 0 walking, 1 settled, 2 left to the general walk  (an integer, not two bools: the
     // compiler keeps bools that live across the loop as packed bytes and spends a third of the loop shuffling them)
@@ -315,16 +320,19 @@ CCT_HD bool bucket_probe_quick(const BucketView &v, int i, const SortEnt &me, bo
         quad = me.q;
         limit = s - kMaxDist;
         const int look = v.n - s;
-        if (me.a & kEntFirst) state = 1;  // no chain: no match, whatever the budget
-        else if (me.a & kEntRun) {
+        if (me.a & kEntRun) {
             state = 2;
             const uint32_t ri = load_u32(v.runs + s);
             const int cap = look < kMaxMatch ? look : kMaxMatch, R = (int)(ri & 0xFFFFu) + 1, rb = (int)(ri >> 16);
             // members of the target's own run below it (position 0 is never one): they are visited first, all give R
             const int own = rb < s - 1 ? rb : s - 1;
-            if (own >= 1 && R >= cap) { best = cap; bdist = 1; state = 1; }
+            const uint32_t cls = tails ? run_class(s, v.n, ri) : 0u;
+            if (cls) state = 2u + cls;  // settled once per run (run_collect; the start announces the run even without a chain)
+            else if (me.a & kEntFirst) state = 1;
+            else if (own >= 1 && R >= cap) { best = cap; bdist = 1; state = 1; }
             else if (own > kChainFull) { best = R; bdist = 1; state = 1; }  // ... and exhaust either chain budget
-        } else if (look < 8) state = 2;  // (the loop assumes a length cap >= 8)
+        } else if (me.a & kEntFirst) state = 1;  // no chain: no match, whatever the budget
+        else if (look < 8) state = 2;  // (the loop assumes a length cap >= 8)
         else {
             e = load_ent(--pj);
             state = s - ent_pos(e) > kMaxDist ? 1u : 0u;  // deflate_slow's test on hash_head
@@ -369,7 +377,153 @@ CCT_HD bool bucket_probe_quick(const BucketView &v, int i, const SortEnt &me, bo
         }
     }
     if (state == 1 && best >= kMinMatch) *out = mtab_pack(best, bdist);
-    return state == 1;
+    if (state >= 3) *out = state == 4 ? kProbeTailLeader : kProbeTail;
+    return state == 1 || state >= 3;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Byte runs, settled once per run
+// ------------------------------------------------------------------------------------------------
+// The chain members of a run X of byte c (start s0, `len` bytes, `end` the first position after it) are what the general
+// walk spends most of its steps on -- every one of them steps through every earlier run group of the bucket of (c,c,c)
+// -- and yet they all see the same thing.  A group G of the bucket is entered at its top member (exactly three c's
+// ahead; member i below it has 3 + i); the member with as many leading c's as the target (R) matches R + A bytes, where
+// A = the common prefix of what follows G and what follows X, those with more match R, those with fewer their own count.
+//   * The START of X (R0 = min(len, 258) c's ahead, no member of X below it) is walked group by group like the general
+//     walk does, but only once per run and with every group settled from its run counts.
+//   * The members with 257 .. 3 c's still ahead and part of X below them (the "tail"; those with 258 or more are
+//     settled by the quick walk) get (R, distance 1) from their own run first, so only a group's member with exactly R
+//     leading c's -- end_G - R -- can beat that, and only if A >= 1.  For the target one position further R is one
+//     less and that member lies one position further, too: its distance (end - end_G) and its place in the chain
+//     (a difference of sorted indices) are THE SAME for every target of the tail; what varies is only whether the group
+//     is long enough to hold such a member.  So the walk notes the few groups with A >= 1 that the chain budget and the
+//     distance limit let the tail reach (dropping those a nearer record beats for every R), and each target reads its
+//     entry off the records (tail_entry): the longest R + A, the nearest among equals -- which also reproduces the
+//     early exit at the maximum length.
+// Runs the walk cannot summarise (more records than it may keep, a group not entered at its top) go through the general
+// walk, target by target.
+//
+// run_class: what the quick walk makes of a run member at s (ri = runs[s]): 0 = not settled here, 1 = a tail target,
+// 2 = the start (it announces the run).  All members of a run agree: the run counts must not be capped, the run must
+// not start at position 0 (never in a chain) and must end at least 255 bytes before the input does (the length cap is
+// 258 for every target, and A can be measured without a bound check).
+constexpr int kTailRecords = 8;
+CCT_HD uint32_t run_class(int s, int n, uint32_t ri) {
+    const int rl = (int)(ri & 0xFFFFu), rb = (int)(ri >> 16);
+    if (rl < kMinMatch - 1 || rb + rl + 1 > 65535 || s - rb < 1 || n - (s + rl + 1) < kMaxMatch - kMinMatch) return 0;
+    if (rb == 0) return 2;
+    return rl + 1 < kMaxMatch ? 1u : 0u;
+}
+
+struct TailGroup {  // (8 bytes: the records of 32 runs sit side by side in shared memory)
+    uint32_t a, b;  // a = rank | max_r << 16, b = dist | extra << 16
+};
+// rank: place in every tail target's chain of the group's member with exactly R leading c's (1 = nearest candidate);
+// dist: its distance; max_r: the group holds such a member for R <= max_r; extra: A, 1 .. 255
+CCT_HD TailGroup tail_group(int rank, int dist, int max_r, int extra) {
+    return TailGroup{(uint32_t)rank | ((uint32_t)max_r << 16), (uint32_t)dist | ((uint32_t)extra << 16)};
+}
+
+// One walk over the run groups below the run whose start is entry i0 of the sorted array, warp-wide like the walks above
+// (a lane per run: neighbouring runs of a bucket see the same groups).  Writes the start's table entries (both budgets)
+// and the tail's records out[k * stride]; returns their number, -1 when the run must be left to the general walk.
+CCT_HDN inline int run_collect(const BucketView &v, int i0, bool active, TailGroup *out, int stride, uint32_t *start_lo,
+                               uint32_t *start_hi) {
+    *start_lo = *start_hi = 0;
+    const SortEnt *pj = v.ent + i0;
+    int s0 = 0, len = 0, end = 0, r0 = 0, rank = 0, cnt = 0, limit = 0;
+    uint32_t after = 0, bottom_a = 0;
+    int best[2] = {2, 2}, bdist[2] = {0, 0};  // the start's walk, budget kChainGood / kChainFull
+    bool live[2] = {false, false};
+    if (active) {
+        const SortEnt first = load_ent(pj);
+        s0 = ent_pos(first);
+        len = (int)(load_u32(v.runs + s0) & 0xFFFFu) + 1;
+        end = s0 + len;
+        r0 = len < kMaxMatch ? len : kMaxMatch;
+        after = load_byte(v.w + end);
+        bottom_a = first.a;
+        limit = s0 - kMaxDist;
+        live[0] = live[1] = true;
+    }
+    while (CCT_WARP_ANY(active)) {
+        if (!active) continue;
+        if (bottom_a & kEntFirst) { active = false; continue; }
+        const SortEnt e = load_ent(--pj);
+        rank++;  // e is the rank-th candidate of the start
+        const int cur = ent_pos(e);
+        // the start's loop condition (the first candidate may lie one further than the others); the tail's reach ends earlier
+        if (rank > kChainFull || (rank == 1 ? s0 - cur > kMaxDist : cur <= limit)) { active = false; continue; }
+        if (rank > kChainGood) live[0] = false;
+        bottom_a = e.a;
+        if (!(e.a & kEntRun)) continue;  // shares the hash only: one step of the chain
+        const uint32_t ri = load_u32(v.runs + cur);
+        if ((ri & 0xFFFFu) != (uint32_t)(kMinMatch - 1)) { cnt = -1; active = false; continue; }  // (a group is entered at its top member)
+        int t = (int)(ri >> 16);
+        if (t == 65535) { cnt = -1; active = false; continue; }
+        if (cur - t < 1) t = cur - 1;
+        const int end_g = cur + kMinMatch;
+        const int extra = load_byte(v.w + end_g) == after ? match_extend(v.w + end_g, v.w + end, 1, kMaxMatch - kMinMatch) : 0;
+        // the start: members 0 .. nvis-1 of the group are visited
+        const int count_dist = kMaxDist - (s0 - cur), i_key = r0 - kMinMatch;
+        bool more = false;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int b = 0; b < 2; b++) {
+            if (!live[b]) continue;
+            int nvis = (b ? kChainFull : kChainGood) - rank + 1;
+            if (t + 1 < nvis) nvis = t + 1;
+            if (count_dist < nvis) nvis = count_dist;
+            if (i_key < nvis) {
+                int L = r0 + extra;
+                if (L > kMaxMatch || r0 == kMaxMatch) L = kMaxMatch;
+                if (L > best[b]) { best[b] = L; bdist[b] = s0 - (cur - i_key); if (L >= kMaxMatch) live[b] = false; }
+            } else {
+                const int L = kMinMatch + nvis - 1;
+                if (L > best[b]) { best[b] = L; bdist[b] = s0 - (cur - (nvis - 1)); }
+            }
+            if (nvis < t + 1) live[b] = false;
+            more |= live[b];
+        }
+        // the tail: its targets meet the member with their R at rank + len - 3, end - end_g away
+        const int rank_al = rank + len - kMinMatch, dist = end - end_g;
+        const bool tail_reach = len > kMinMatch && rank_al <= kChainFull && dist < kMaxDist;
+        if (tail_reach && extra > 0) {
+            const int max_r = kMinMatch + t < kMaxMatch ? kMinMatch + t : kMaxMatch;
+            bool beaten = false;  // by a nearer record that is at least as long for every R
+            for (int k = 0; k < cnt; k++) {
+                const TailGroup g = out[k * stride];
+                if ((int)(g.b >> 16) >= extra && (int)(g.a >> 16) >= max_r) beaten = true;
+            }
+            if (!beaten) {
+                if (cnt == kTailRecords) { cnt = -1; active = false; continue; }
+                out[cnt++ * stride] = tail_group(rank_al, dist, max_r, extra);
+            }
+        }
+        if (!more && !tail_reach) { active = false; continue; }
+        if (t) { pj -= t; rank += t; bottom_a = load_ent(pj).a; }
+    }
+    if (cnt >= 0) {
+        *start_hi = best[0] >= kMinMatch ? mtab_pack(best[0], bdist[0]) : 0u;
+        *start_lo = best[1] >= kMinMatch ? mtab_pack(best[1], bdist[1]) : 0u;
+    }
+    return cnt;
+}
+
+// Table entries (both budgets) of the tail target with R leading c's.
+CCT_HD void tail_entry(const TailGroup *g, int stride, int cnt, int R, uint32_t *lo, uint32_t *hi) {
+    int blo = R, dlo = 1, bhi = R, dhi = 1;
+    for (int k = 0; k < cnt; k++) {
+        const TailGroup r = g[k * stride];
+        if (R > (int)(r.a >> 16)) continue;
+        int L = R + (int)(r.b >> 16);
+        if (L > kMaxMatch) L = kMaxMatch;
+        if (L > blo) { blo = L; dlo = (int)(r.b & 0xFFFFu); }  // (every record is within the full budget)
+        if ((int)(r.a & 0xFFFFu) <= kChainGood && L > bhi) { bhi = L; dhi = (int)(r.b & 0xFFFFu); }
+    }
+    *lo = mtab_pack(blo, dlo);
+    *hi = mtab_pack(bhi, dhi);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -4,6 +4,7 @@
 // TEST INFRASTRUCTURE: built and loaded by tests/ only; the product library never contains this file.
 #include <cstdint>
 #include <cstdlib>
+#include <cstdio>
 #include <algorithm>
 #include <cstring>
 #include <vector>
@@ -86,6 +87,43 @@ static void sorted_reference(const uint8_t *w, int n, std::vector<SortEnt> &ent,
     }
 }
 
+// The probe tables of a stream the way the kernels fill them: k_bprobe (quick walk, general walk, the members of byte
+// runs left out and announced by the run's start), then k_run_tails.  Returns the number of entries whose budgets differ;
+// tail_stats[0] = runs announced, [1] = of those left to the general walk, [2] = records collected.
+static int64_t probe_tables(const BucketView &bv, const std::vector<SortEnt> &ent, int n, uint32_t *mlo, uint32_t *mhi,
+                            int64_t *tail_stats = nullptr) {
+    int64_t n_diff = 0;
+    const int members = n >= 4 ? n - 3 : 0;
+    std::vector<int> leaders;
+    auto put = [&](int p, uint32_t lo, uint32_t hi) {
+        if (lo != hi) { mhi[p] = hi; lo |= kProbeHiDiff; n_diff++; }
+        mlo[p] = lo;
+    };
+    for (int i = 0; i < members; i++) {
+        uint32_t lo, hi;
+        if (bucket_probe_quick(bv, i, ent[i], true, true, &lo)) {
+            if (lo >= kProbeTail) { if (lo == kProbeTailLeader) leaders.push_back(i); continue; }
+            hi = lo;
+        } else bucket_probe(bv, i, ent[i], true, &lo, &hi);
+        put(ent_pos(ent[i]), lo, hi);
+    }
+    for (int i0 : leaders) {
+        TailGroup recs[kTailRecords];
+        uint32_t lo, hi;
+        const int nrec = run_collect(bv, i0, true, recs, 1, &lo, &hi), s0 = ent_pos(ent[i0]);
+        const int len = (int)(bv.runs[s0] & 0xFFFFu) + 1;
+        if (tail_stats) { tail_stats[0]++; if (nrec < 0) tail_stats[1]++; else tail_stats[2] += nrec; }
+        if (nrec < 0) bucket_probe(bv, i0, ent[i0], true, &lo, &hi);
+        put(s0, lo, hi);
+        for (int j = std::max(1, len - (kMaxMatch - 1)); j <= len - kMinMatch; j++) {
+            if (nrec >= 0) tail_entry(recs, 1, nrec, len - j, &lo, &hi);
+            else bucket_probe(bv, i0 + j, ent[i0 + j], true, &lo, &hi);
+            put(s0 + j, lo, hi);
+        }
+    }
+    return n_diff;
+}
+
 extern "C" {
 
 // Staged zlib-9 of src[0..n).
@@ -102,16 +140,7 @@ int64_t hs_deflate2(const uint8_t *src, int n, uint8_t *dst, int64_t cap, int pa
     BucketView bv{src, ent.data(), runs.data(), n};
     LzView v{src, n};
     std::vector<uint32_t> mlo((size_t)n + 1, 0), mhi((size_t)n + 1, 0xDEADBEEFu);  // (mhi is read only where flagged)
-    int64_t n_incomplete = 0;
-    const int members = n >= 4 ? n - 3 : 0;
-    for (int i = 0; i < members; i++) {
-        const int p = ent_pos(ent[i]);
-        uint32_t lo, hi;
-        if (bucket_probe_quick(bv, i, ent[i], true, &lo)) hi = lo;
-        else bucket_probe(bv, i, ent[i], true, &lo, &hi);
-        if (lo != hi) { mhi[p] = hi; lo |= kProbeHiDiff; n_incomplete++; }
-        mlo[p] = lo;
-    }
+    const int64_t n_incomplete = probe_tables(bv, ent, n, mlo.data(), mhi.data());
     ProbeTab mtab{mlo.data(), mhi.data()};
     long long c1 = cct_stat[2];
     // speculative windows -> stitch -> compaction (the three parse kernels, sequentially)
@@ -210,11 +239,26 @@ int64_t hs_probe_check(const uint8_t *src, int n, int64_t *steps) {
         const int p = ent_pos(ent[i]);
         bucket_probe(bv, i, ent[i], true, &lo[p], &hi[p]);
         uint32_t q;
-        if (bucket_probe_quick(bv, i, ent[i], true, &q)) { quick++; if (q != lo[p] || q != hi[p]) bad++; }  // the short cut agrees wherever it settles
+        if (bucket_probe_quick(bv, i, ent[i], true, false, &q)) { quick++; if (q != lo[p] || q != hi[p]) bad++; }  // the short cut agrees wherever it settles
     }
     if (steps) { steps[0] = cct_stat[2] - c0; steps[1] = quick; }
     for (int s = 0; s < n; s++)
         if (lm_reference(w.data(), n, dist16.data(), s, kChainFull) != lo[s] || lm_reference(w.data(), n, dist16.data(), s, kChainGood) != hi[s]) bad++;
+    // the tables as the kernels fill them (tails of long runs settled once per run) must be the same
+    std::vector<uint32_t> klo((size_t)n + 1, 0), khi((size_t)n + 1, 0);
+    int64_t ts[3] = {0, 0, 0};
+    probe_tables(bv, ent, n, klo.data(), khi.data(), ts);
+    for (int s = 0; s < n; s++) {
+        const uint32_t want_lo = lo[s] | (lo[s] != hi[s] ? kProbeHiDiff : 0u);
+        if (klo[s] != want_lo || (lo[s] != hi[s] && khi[s] != hi[s])) {
+            bad++;
+            if (getenv("HS_DEBUG") && bad < 12)
+                fprintf(stderr, "pos %d runs rl=%u rb=%u: want lo (%d,%d) hi (%d,%d), kernels lo (%d,%d)%s hi (%d,%d)\n", s, runs[s] & 0xFFFF, runs[s] >> 16,
+                        mtab_len(lo[s]), mtab_dist(lo[s]), mtab_len(hi[s]), mtab_dist(hi[s]), mtab_len(klo[s]), mtab_dist(klo[s]),
+                        (klo[s] & kProbeHiDiff) ? "*" : "", mtab_len(khi[s]), mtab_dist(khi[s]));
+        }
+    }
+    if (steps) { steps[2] = ts[0]; steps[3] = ts[1]; steps[4] = ts[2]; }
     return bad;
 }
 
@@ -229,15 +273,39 @@ void hs_match_tables(const uint8_t *src, int n, uint64_t *ent_out, uint32_t *lo_
     BucketView bv{w.data(), ent.data(), runs.data(), n};
     const int members = n >= 4 ? n - 3 : 0;
     for (int p = 0; p < n; p++) { lo_out[p] = 0; hi_out[p] = 0; }
+    probe_tables(bv, ent, n, lo_out, hi_out);
+    for (int i = 0; i < members; i++) ent_out[i] = (uint64_t)ent[i].a | ((uint64_t)ent[i].q << 32);
+}
+
+// Where the general walk's work comes from (diagnostics): per class of target -- 0 run member with members of its run
+// below it, 1 run start, 2 ordinary position -- out[c] = targets left to the general walk, out[3 + c] = its steps for
+// them, out[6] = warp tasks (32 consecutive entries) with at least one such target, out[7] = the sum over those tasks of
+// the longest walk in them, out[8] = targets deferred to the run tails, out[9] = all targets.
+void hs_general_walk_stats(const uint8_t *src, int n, int64_t *out) {
+    std::vector<uint8_t> w(src, src + n);
+    w.resize((size_t)n + 16, 0);
+    std::vector<SortEnt> ent;
+    std::vector<uint32_t> runs;
+    sorted_reference(w.data(), n, ent, runs);
+    BucketView bv{w.data(), ent.data(), runs.data(), n};
+    const int members = n >= 4 ? n - 3 : 0;
+    for (int k = 0; k < 10; k++) out[k] = 0;
+    long long task_max = 0; bool task_any = false;
     for (int i = 0; i < members; i++) {
-        const int p = ent_pos(ent[i]);
+        if ((i & 31) == 0) { if (task_any) { out[6]++; out[7] += task_max; } task_any = false; task_max = 0; }
         uint32_t lo, hi;
-        if (bucket_probe_quick(bv, i, ent[i], true, &lo)) hi = lo;
-        else bucket_probe(bv, i, ent[i], true, &lo, &hi);
-        if (lo != hi) { hi_out[p] = hi; lo |= kProbeHiDiff; }
-        lo_out[p] = lo;
-        ent_out[i] = (uint64_t)ent[i].a | ((uint64_t)ent[i].q << 32);
+        out[9]++;
+        if (bucket_probe_quick(bv, i, ent[i], true, true, &lo)) { if (lo >= kProbeTail) out[8]++; continue; }
+        const long long c0 = cct_stat[2];
+        bucket_probe(bv, i, ent[i], true, &lo, &hi);
+        const long long st = cct_stat[2] - c0;
+        const int s = ent_pos(ent[i]);
+        int cls = 2;
+        if (ent[i].a & kEntRun) cls = ((runs[s] >> 16) >= 1 && s >= 2) ? 0 : 1;
+        out[cls]++; out[3 + cls] += st;
+        task_any = true; if (st > task_max) task_max = st;
     }
+    if (task_any) { out[6]++; out[7] += task_max; }
 }
 
 void hs_stats(long long *out, int reset) { for (int i = 0; i < 8; i++) { out[i] = cct_stat[i]; if (reset) cct_stat[i] = 0; } }

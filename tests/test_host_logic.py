@@ -141,6 +141,47 @@ def test_sorted_scan_matches_zlib_candidate_loop(hostsim):
         assert hostsim.hs_probe_check(_p(src, C.c_uint8), len(b), None) == 0, len(b)
 
 
+def _runs_blob(rng, nruns, run_bytes, lens, afters, gaps):
+    """Byte runs followed by one of a few continuations (so that what follows two runs often agrees for a while)."""
+    parts = []
+    for _ in range(nruns):
+        parts.append(bytes([int(rng.choice(run_bytes))]) * int(rng.choice(lens)))
+        parts.append(bytes(afters[int(rng.integers(0, len(afters)))]))
+        parts.append(rng.integers(1, 9, size=int(rng.choice(gaps)), dtype=np.uint8).tobytes())
+    return b"".join(parts)
+
+
+def test_run_tails_match_zlib_candidate_loop(hostsim):
+    """The tails of long byte runs (tail_collect / tail_entry: one walk per run, 255 table entries read off its
+    records) against zlib's candidate-by-candidate loop: shared continuations of every length, both chain budgets and
+    the distance limit inside and between runs, runs at either end of the input, capped run counts, hash collisions
+    inside the bucket, groups shorter than the target's run, more records than a run may keep (general-walk fall-back)."""
+    rng = np.random.default_rng(1)
+    afters = [[5, 6, 7, 8, 9, 1, 2, 3], [5, 6, 7, 1], [5, 1], [9], [5, 6, 7, 8, 9, 1, 2, 4], list(range(10, 250)),
+              list(range(10, 250)) + [3], list(range(10, 200))]
+    blobs = [
+        _runs_blob(rng, 60, [0], [258, 259, 260, 300, 515, 516, 517, 1000, 257, 100], afters, [1, 2, 5, 30]),
+        _runs_blob(rng, 80, [0, 0, 0, 7, 200], [258, 270, 400, 3, 5, 40, 258 + 255], afters, [1, 3, 10]),
+        _runs_blob(rng, 30, [0], [2000, 5000, 4096 + 300, 1024 + 258, 1024 + 257, 1024 + 259, 900], afters, [1, 2]),
+        bytes(300) + _runs_blob(rng, 20, [0], [400], afters, [2]),
+        _runs_blob(rng, 12, [0], [9000, 12000, 300], afters, [2, 700]),
+        bytes(70000) + b"\x05\x06" + bytes(66000) + b"\x05\x06\x07" + bytes(400) + b"\x05\x06",
+        b"".join(bytes(300) + bytes([5, 6, 7]) + bytes([32, 0, 0, 1]) * 50 for _ in range(20)),  # (32,0,0) hashes like (0,0,0)
+        b"".join(bytes(300 if i % 25 == 24 else int(rng.integers(3, 60))) + bytes([5, 6, int(rng.integers(1, 4))]) for i in range(600)),
+        b"".join(bytes(300 if i % 10 == 9 else int(rng.integers(100, 280))) + bytes([5, int(rng.integers(1, 3))]) for i in range(300)),
+    ]
+    base = _runs_blob(rng, 20, [0], [400], afters, [2]) + bytes(600)
+    blobs += [base + b"\x05" * k for k in (0, 254, 255, 256)]  # the length cap of the last targets drops below 258
+    announced = fallback = 0
+    for b in blobs:
+        src = np.frombuffer(b, dtype=np.uint8)
+        st = (C.c_int64 * 5)()
+        assert hostsim.hs_probe_check(_p(src, C.c_uint8), len(b), st) == 0, len(b)
+        announced += st[2]
+        fallback += st[3]
+    assert announced > 300 and 0 < fallback < announced  # both ways of settling a tail were exercised
+
+
 def test_staged_deflate_block_boundaries(hostsim):
     rng = np.random.default_rng(11)
     lits = rng.permutation(np.arange(256, dtype=np.uint8).repeat(200))
