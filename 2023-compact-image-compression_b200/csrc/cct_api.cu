@@ -394,13 +394,13 @@ int encode_impl(const uint16_t *d_px, int B, int rows, int cols, uint32_t flags,
         const uint16_t *px = d_px + (int64_t)first * n_px;
         int32_t *stats = d_stats ? d_stats + (int64_t)first * 4 : nullptr;
         if (hooks && hooks->before && (rc = hooks->before(pass, first, b, st)) != CCT_OK) return rc;
-        { CCT_KERNEL(m_zero_jump, st); CK(cudaMemsetAsync(ws.jump, 0, (size_t)b * nb, st)); CK(cudaMemsetAsync(ws.taken, 0, (size_t)b * nb, st)); }
+        { CCT_KERNEL(m_zero_jump, st); launch_zero(ws.jump, (size_t)b * nb, st); launch_zero(ws.taken, (size_t)b * nb, st); }
         launch_gather_stats(px, order, ws.hv, ws.info, b, n_px, st);
         if (flags & CCT_FLAG_SEGMENTATION) launch_mesh(ws.hv, ws.info, ws.jump, ws.taken, stats, b, n_px, st);
         launch_emit(ws.hv, ws.jump, ws.taken, ws.payload, ws.pstride, ws.plen, d_status + first, stats, b, n_px, st);
         const uint8_t *body = ws.payload; int64_t body_stride = ws.pstride; const int32_t *body_len = ws.plen;
         if (flags & CCT_FLAG_DEFLATE) {
-            { CCT_KERNEL(m_zero_zbuf, st); CK(cudaMemsetAsync(ws.zbuf, 0, (size_t)b * ws.zstride, st)); }
+            { CCT_KERNEL(m_zero_zbuf, st); launch_zero(ws.zbuf, (size_t)b * ws.zstride, st); }
             launch_deflate(ws.payload, ws.pstride, ws.plen, b, ws.pstride, ws.zbuf, ws.zstride, ws.zlen, ws.dws, st);
             body = ws.zbuf; body_stride = ws.zstride; body_len = ws.zlen;
         }
@@ -585,16 +585,17 @@ struct HostCtx {
     // CCT_HOST_TRACE=1: device timeline of a host-buffer call (copies and passes), printed to stderr at its end
     std::vector<std::pair<std::string, cudaEvent_t>> marks;
     bool tracing = false;
+    std::vector<cudaEvent_t> mark_pool;  // (created before the call starts: creating an event may synchronise)
     void mark(const char *what, int k, cudaStream_t s) {
-        if (!tracing) return;
-        cudaEvent_t e;
-        cudaEventCreate(&e);
+        if (!tracing || marks.size() >= mark_pool.size()) return;
+        cudaEvent_t e = mark_pool[marks.size()];
         cudaEventRecord(e, s);
         marks.emplace_back(std::string(what) + " " + std::to_string(k), e);
     }
     void trace_begin(cudaStream_t s) {
         const char *e = getenv("CCT_HOST_TRACE");
         tracing = e && atoi(e) > 0;
+        if (tracing) while (mark_pool.size() < 512) { cudaEvent_t ev; cudaEventCreate(&ev); mark_pool.push_back(ev); }
         mark("begin", 0, s);
     }
     void trace_end(const char *call) {
@@ -604,7 +605,6 @@ struct HostCtx {
             cudaEventElapsedTime(&ms, marks[0].second, marks[i].second);
             fprintf(stderr, "[cct trace] %s %-14s %8.3f ms\n", call, marks[i].first.c_str(), ms);
         }
-        for (auto &m : marks) cudaEventDestroy(m.second);
         marks.clear();
         tracing = false;
     }
@@ -688,6 +688,17 @@ int host_schedule(int B, size_t n_px, std::vector<int> &starts, bool decode) {
     }
     starts.clear();
     starts.push_back(0);
+    if (const char *e = getenv(decode ? "CCT_HOST_SIZES_DEC" : "CCT_HOST_SIZES")) {  // explicit pass sizes (experiments): used when they add up to B
+        int at = 0, largest = 0;
+        for (const char *q = e; *q;) {
+            const int v = atoi(q);
+            if (v > 0 && v <= kMaxPass) { at += v; largest = std::max(largest, v); starts.push_back(at); }
+            while (*q && *q != ',') q++;
+            if (*q) q++;
+        }
+        if (at == B) return largest;
+        starts.resize(1);
+    }
     if (B > per) {
         int at = 0, largest = 0;
         for (int d : div) {
@@ -783,9 +794,14 @@ int cct_encode_host(const uint16_t *h_px, int B, int rows, int cols, uint32_t fl
         c->mark("end", k, ps);
         CK(cudaMemcpyAsync(h_offsets + first + 1, d_off + first + 1, (size_t)count * 8, cudaMemcpyDeviceToHost, ps));
         CK(cudaEventRecord(c->event(n_pass + k), ps));
-        return k > 0 ? fetch(k - 1) : CCT_OK;  // pass k is queued: now wait for pass k-1 and start its download
+        // Passes k-1 and k are queued: now wait for pass k-2 and start its download.  (One pass further back than the
+        // data needs: measured, the first kernel of whatever is queued AFTER a download has been issued does not start
+        // before that download is through -- with k-1 here, every pass began 2.6 ms after the one before it on its
+        // lane had ended.)
+        return k > 1 ? fetch(k - 2) : CCT_OK;
     };
     rc = encode_impl(d_px, B, rows, cols, flags, d_out, arena, d_off, d_status, d_stats, c->buf[3], c->cap[3], c->st, &hooks);
+    if (rc == CCT_OK && n_pass > 1) rc = fetch(n_pass - 2);
     if (rc == CCT_OK) rc = fetch(n_pass - 1);
     if (rc != CCT_OK) { c->drain(); return rc; }
     CK(cudaMemcpyAsync(h_status, d_status, (size_t)B * 4, cudaMemcpyDeviceToHost, c->st));

@@ -882,8 +882,8 @@ void launch_decode(const uint8_t *files, const int64_t *offsets, int B, int rows
     if (B == 0) return;
     const int n_px = rows * cols, nb = n_px / kBlock;
     { CCT_KERNEL(m_zero_px, st);
-    cudaMemsetAsync(ws.jflag, 0, (size_t)B * nb, st);
-    cudaMemsetAsync(px, 0, (size_t)B * n_px * sizeof(uint16_t), st);  // np.zeros(size), core.py:436
+    launch_zero(ws.jflag, (size_t)B * nb, st);
+    launch_zero(px, (size_t)B * n_px * sizeof(uint16_t), st);  // np.zeros(size), core.py:436
     }
     { CCT_KERNEL(k_dec_header, st);
     k_dec_header<<<(B + 127) / 128, 128, 0, st>>>(files, offsets, B, rows, cols, status, ws.fl);

@@ -761,7 +761,7 @@ __global__ void __launch_bounds__(kScanThreads) k_symscan(const int32_t *__restr
         // compaction, a word at a time by the whole warp: lane l looks at position 32 j + l of word j, so the symbol
         // loads and the dense stores are coalesced
         const int wbase = base + (wid << 5);
-#pragma unroll 4
+#pragma unroll 8
         for (int j = 0; j < 32; j++) {
             const uint32_t bj = __shfl_sync(0xffffffffu, bits, j);
             const int ij = __shfl_sync(0xffffffffu, idx, j);
@@ -1055,7 +1055,7 @@ static void launch_match_tables(const uint8_t *in, int64_t in_stride, const int3
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
         const int64_t ctas = std::min<int64_t>(total_bins, (int64_t)n_sm * 8);
-        { CCT_KERNEL(m_zero_counters, st); cudaMemsetAsync(ws.counters, 0, 64 * sizeof(uint32_t), st); }
+        { CCT_KERNEL(m_zero_counters, st); launch_zero(ws.counters, 64 * sizeof(uint32_t), st); }
         CCT_KERNEL(k_hs_bins, st);
         k_hs_bins<<<(unsigned)ctas, kBinThreads, 0, st>>>(ws.binbase, ws.p1, ws.ent, ws.stride, (int)total_bins, ws.counters);
     }

@@ -9,9 +9,27 @@
 //   core.py:274-330      JUMP/DELTA/FULL emission + EOF        -> k_emit (per-image scan of unit sizes)
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include "cct_kernels.h"
 
 namespace cct {
+
+// ------------------------------------------------------------------ zero-fill
+__global__ void __launch_bounds__(256) k_zero(uint4 *__restrict__ p16, size_t n16, uint8_t *__restrict__ tail, int ntail) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) p16[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (blockIdx.x == 0 && (int)threadIdx.x < ntail) tail[threadIdx.x] = 0;
+}
+void launch_zero(void *p, size_t bytes, cudaStream_t st) {
+    if (bytes == 0) return;
+    uint8_t *b = (uint8_t *)p;
+    if (reinterpret_cast<uintptr_t>(p) & 15u) { cudaMemsetAsync(p, 0, bytes, st); return; }  // (workspace pieces are 256-byte aligned)
+    const size_t n16 = bytes >> 4;
+    const int ntail = (int)(bytes & 15u);
+    const unsigned grid = (unsigned)std::min<size_t>((n16 + 1023) / 1024 + 1, 148 * 16);
+    k_zero<<<grid, 256, 0, st>>>(reinterpret_cast<uint4 *>(b), n16, b + (n16 << 4), ntail);
+}
 
 // ------------------------------------------------------------------ traversal tables
 __global__ void k_curve_pow2(int32_t *order, uint32_t n) {

@@ -24,6 +24,10 @@ struct ProfScope {
 #define CCT_KERNEL(name, st) ::cct::ProfScope prof_scope_##name(#name, st)
 
 // ---- cct_encode.cu
+// Zero-fill by a kernel.  (cudaMemsetAsync may be carried out by a copy engine: inside the host-buffer entry points it
+// then queues behind whatever upload or download is in flight -- measured: every encode pass started only when the
+// download of the pass two before it had finished.)
+void launch_zero(void *p, size_t bytes, cudaStream_t st);
 void launch_curve_pow2(int32_t *d_order, int n, cudaStream_t st);
 void launch_iota(int32_t *d_order, int64_t n, cudaStream_t st);
 void launch_gather_stats(const uint16_t *px, const int32_t *order, uint16_t *hv, uint8_t *info, int B, int64_t n_px,

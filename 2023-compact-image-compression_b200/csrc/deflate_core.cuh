@@ -435,6 +435,8 @@ CCT_HDN inline int run_collect(const BucketView &v, int i0, bool active, TailGro
     uint32_t after = 0, bottom_a = 0;
     int best[2] = {2, 2}, bdist[2] = {0, 0};  // the start's walk, budget kChainGood / kChainFull
     bool live[2] = {false, false};
+    SortEnt next{0u, 0u};  // the entry below *pj when it has been fetched along with *pj (below a group)
+    bool have_next = false;
     if (active) {
         const SortEnt first = load_ent(pj);
         s0 = ent_pos(first);
@@ -449,7 +451,9 @@ CCT_HDN inline int run_collect(const BucketView &v, int i0, bool active, TailGro
     while (CCT_WARP_ANY(active)) {
         if (!active) continue;
         if (bottom_a & kEntFirst) { active = false; continue; }
-        const SortEnt e = load_ent(--pj);
+        --pj;
+        const SortEnt e = have_next ? next : load_ent(pj);
+        have_next = false;
         rank++;  // e is the rank-th candidate of the start
         const int cur = ent_pos(e);
         // the start's loop condition (the first candidate may lie one further than the others); the tail's reach ends earlier
@@ -502,7 +506,11 @@ CCT_HDN inline int run_collect(const BucketView &v, int i0, bool active, TailGro
             }
         }
         if (!more && !tail_reach) { active = false; continue; }
-        if (t) { pj -= t; rank += t; bottom_a = load_ent(pj).a; }
+        // on to the group's lowest member, and -- in the same round trip -- the entry below it
+        pj -= t; rank += t;
+        have_next = pj > v.ent;
+        if (have_next) next = load_ent(pj - 1);
+        if (t) bottom_a = load_ent(pj).a;
     }
     if (cnt >= 0) {
         *start_hi = best[0] >= kMinMatch ? mtab_pack(best[0], bdist[0]) : 0u;
@@ -729,14 +737,15 @@ struct uint2 { uint32_t x, y; };  // host build of the test harness
 constexpr uint32_t kPqNone = 0xFFFFFFFFu;  // sentinel after the last entry: never "smaller" than a real one
 
 CCT_HDN inline void pq_down(TreeScratch &s, int k, const int heap_len) {  // (heap_len by value: s.pq stores would force a reload)
-    const uint32_t v = s.pq[k], vk = v >> 10;
+    // (a >> 10) <= (b >> 10) is a <= (b | 1023): one OR per comparison instead of two shifts
+    const uint32_t v = s.pq[k];
     int j = k << 1;
     while (j <= heap_len) {
         // children j (even: 8-byte aligned) and j + 1 (the sentinel when j is the last entry)
         const uint2 ch = *reinterpret_cast<const uint2 *>(&s.pq[j]);
         uint32_t c = ch.x;
-        if ((ch.y >> 10) <= (c >> 10)) { j++; c = ch.y; }
-        if (vk <= (c >> 10)) break;
+        if (ch.y <= (c | 1023u)) { j++; c = ch.y; }
+        if (v <= (c | 1023u)) break;
         s.pq[k] = c;
         k = j; j <<= 1;
     }
