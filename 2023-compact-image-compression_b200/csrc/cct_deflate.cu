@@ -724,60 +724,94 @@ __global__ void __launch_bounds__(128) k_walk_stitch(const uint8_t *__restrict__
 }
 
 constexpr int kScanThreads = 256;
+// Symbol starts per tile of kScanThreads mask words (8192 positions): a tile of k_symscan then knows where its symbols
+// go without waiting for the tiles before it.
+__global__ void __launch_bounds__(kScanThreads) k_symcount(const int32_t *__restrict__ in_len, const uint32_t *__restrict__ mask,
+                                                           int64_t mask_stride, int32_t *__restrict__ tile_cnt, int64_t cnt_stride) {
+    const int stream = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
+    const int n_words = (in_len[stream] + 31) >> 5;
+    if (tile * kScanThreads >= n_words) return;
+    const int wi = tile * kScanThreads + tid;
+    int c = wi < n_words ? __popc(mask[(int64_t)stream * mask_stride + wi]) : 0;
+    __shared__ int warp_sum[kScanThreads / 32];
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((tid & 31) == 0) warp_sum[tid >> 5] = c;
+    __syncthreads();
+    if (tid == 0) {
+        int t = 0;
+        for (int w = 0; w < kScanThreads / 32; w++) t += warp_sum[w];
+        tile_cnt[(int64_t)stream * cnt_stride + tile] = t;
+    }
+}
+
+// One CTA per tile: prefix sum over the mask -> the tile's piece of the dense symbol array and the block boundaries in
+// it; the CTA of the stream's last tile also closes the stream (symbol count, flushed blocks).
 __global__ void __launch_bounds__(kScanThreads) k_symscan(const int32_t *__restrict__ in_len, const uint32_t *__restrict__ mask,
                                                           int64_t mask_stride, const uint32_t *__restrict__ rec, uint32_t *__restrict__ syms,
                                                           int64_t stride, int32_t *__restrict__ blk_end, int max_blocks,
-                                                          int32_t *__restrict__ nsym, int32_t *__restrict__ nflush) {
-    const int stream = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+                                                          int32_t *__restrict__ nsym, int32_t *__restrict__ nflush,
+                                                          const int32_t *__restrict__ tile_cnt, int64_t cnt_stride) {
+    const int stream = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n = in_len[stream];
+    const int n_words = (n + 31) >> 5;
+    const int base = tile * kScanThreads;
+    if (base >= n_words) {
+        if (tile == 0 && tid == 0) {  // an empty stream
+            nsym[stream] = 0;
+            nflush[stream] = finish_blocks(0, 0u, n, blk_end + (int64_t)stream * max_blocks);
+        }
+        return;
+    }
     const int64_t o = (int64_t)stream * stride;
     const uint32_t *mk = mask + (int64_t)stream * mask_stride;
     const uint32_t *rc = rec + o;
     uint32_t *out = syms + o;
     int32_t *be = blk_end + (int64_t)stream * max_blocks;
     asm volatile("" : "+l"(mk), "+l"(rc), "+l"(out), "+l"(be));  // (kept in registers instead of re-derived from the parameters)
-    __shared__ int warp_sum[kScanThreads / 32];
-    __shared__ int carry_s;
-    if (tid == 0) carry_s = 0;
-    __syncthreads();
-    const int n_words = (n + 31) >> 5;
-    for (int base = 0; base < n_words; base += kScanThreads) {  // one mask word (32 positions) per thread per tile
-        const int wi = base + tid;
-        uint32_t bits = wi < n_words ? mk[wi] : 0u;
-        const int cnt = __popc(bits);
-        int incl = cnt;
+    __shared__ int warp_sum[kScanThreads / 32], warp_carry[kScanThreads / 32];
+    // symbols before this tile
+    int before = 0;
+    for (int t = tid; t < tile; t += kScanThreads) before += tile_cnt[(int64_t)stream * cnt_stride + t];
+    for (int d = 16; d; d >>= 1) before += __shfl_xor_sync(0xffffffffu, before, d);
+    if (lane == 0) warp_carry[wid] = before;
+    const int wi = base + tid;  // one mask word (32 positions) per thread
+    const uint32_t bits = wi < n_words ? mk[wi] : 0u;
+    const int cnt = __popc(bits);
+    int incl = cnt;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            int t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += t;
-        }
-        if (lane == 31) warp_sum[wid] = incl;
-        __syncthreads();
-        int woff = 0, total = 0;
-        for (int w = 0; w < kScanThreads / 32; w++) { if (w < wid) woff += warp_sum[w]; total += warp_sum[w]; }
-        int idx = carry_s + woff + incl - cnt;
-        __syncthreads();
-        if (tid == 0) carry_s += total;
-        // compaction, a word at a time by the whole warp: lane l looks at position 32 j + l of word j, so the symbol
-        // loads and the dense stores are coalesced
-        const int wbase = base + (wid << 5);
-#pragma unroll 8
-        for (int j = 0; j < 32; j++) {
-            const uint32_t bj = __shfl_sync(0xffffffffu, bits, j);
-            const int ij = __shfl_sync(0xffffffffu, idx, j);
-            if ((bj >> lane) & 1u) {
-                const int p = ((wbase + j) << 5) + lane;
-                const int at = ij + __popc(bj & ((1u << lane) - 1u));
-                if (at > 0 && at % kSymEnd == 0) be[at / kSymEnd - 1] = p;
-                out[at] = rc[p] & ~kSymSlow;
-            }
-        }
-        __syncthreads();
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
     }
-    if (tid == 0) {
-        const int total = carry_s;
-        nsym[stream] = total;
-        nflush[stream] = finish_blocks(total, total ? out[total - 1] : 0u, n, be);
+    if (lane == 31) warp_sum[wid] = incl;
+    __syncthreads();
+    int carry = 0, woff = 0, total = 0;
+    for (int w = 0; w < kScanThreads / 32; w++) { carry += warp_carry[w]; if (w < wid) woff += warp_sum[w]; total += warp_sum[w]; }
+    const int idx = carry + woff + incl - cnt;
+    // compaction, a word at a time by the whole warp: lane l looks at position 32 j + l of word j, so the symbol
+    // loads and the dense stores are coalesced
+    const int wbase = base + (wid << 5);
+#pragma unroll 8
+    for (int j = 0; j < 32; j++) {
+        const uint32_t bj = __shfl_sync(0xffffffffu, bits, j);
+        const int ij = __shfl_sync(0xffffffffu, idx, j);
+        if ((bj >> lane) & 1u) {
+            const int p = ((wbase + j) << 5) + lane;
+            const int at = ij + __popc(bj & ((1u << lane) - 1u));
+            if (at > 0 && at % kSymEnd == 0) be[at / kSymEnd - 1] = p;
+            out[at] = rc[p] & ~kSymSlow;
+        }
+    }
+    if (tid == 0 && base + kScanThreads >= n_words) {  // the last tile: close the stream
+        const int all = carry + total;
+        uint32_t last = 0;
+        if (all) {  // the last symbol of the stream: at the highest position marked (read from rec, not from another CTA's output)
+            int w = n_words - 1;
+            while (mk[w] == 0u) w--;
+            last = rc[(w << 5) + 31 - __clz((int)mk[w])] & ~kSymSlow;
+        }
+        nsym[stream] = all;
+        nflush[stream] = finish_blocks(all, last, n, be);
     }
 }
 
@@ -1095,9 +1129,16 @@ void launch_deflate(const uint8_t *in, int64_t in_stride, const int32_t *in_len,
     k_walk_stitch<<<(B + 3) / 4, 128, 0, st>>>(in, in_stride, in_len, ws.mtab, ws.mhi, ws.mask, ws.mask_stride, ws.rec,
                                                 ws.exits, ws.stride, ws.max_win, B);
     }
-    { CCT_KERNEL(k_symscan, st);
-    k_symscan<<<B, kScanThreads, 0, st>>>(in_len, ws.mask, ws.mask_stride, ws.rec, ws.syms, ws.stride, ws.blk_end, ws.max_blocks,
-                                          ws.nsym, ws.nflush);
+    {   // (the per-tile counts live where the window exits were: the walks are over)
+        int32_t *tile_cnt = reinterpret_cast<int32_t *>(ws.exits);
+        const int64_t cnt_stride = (int64_t)ws.max_win * (int64_t)(sizeof(Walk) / sizeof(int32_t));
+        const dim3 gt((unsigned)((ws.mask_stride + kScanThreads - 1) / kScanThreads), (unsigned)B);
+        { CCT_KERNEL(k_symcount, st);
+        k_symcount<<<gt, kScanThreads, 0, st>>>(in_len, ws.mask, ws.mask_stride, tile_cnt, cnt_stride);
+        }
+        CCT_KERNEL(k_symscan, st);
+        k_symscan<<<gt, kScanThreads, 0, st>>>(in_len, ws.mask, ws.mask_stride, ws.rec, ws.syms, ws.stride, ws.blk_end, ws.max_blocks,
+                                               ws.nsym, ws.nflush, tile_cnt, cnt_stride);
     }
     { CCT_KERNEL(k_adler, st);
     k_adler<<<B, 256, 0, st>>>(in, in_stride, in_len, ws.adler);
