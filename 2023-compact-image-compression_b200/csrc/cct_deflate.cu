@@ -841,8 +841,12 @@ __global__ void __launch_bounds__(256) k_adler(const uint8_t *__restrict__ in, i
 // replaced by a parallel Huffman construction).  That part is a chain of dependent shared-memory accesses, so the
 // kernel's speed is the number of blocks resident per SM: the histogram counters share storage with the priority
 // queue and the block descriptor is assembled where the literal tree's Freq/Dad arrays were (both dead by then).
+#ifndef CCT_BB_PER_WARP
+#define CCT_BB_PER_WARP 2
+#endif
+constexpr int kBBPerWarp = CCT_BB_PER_WARP;  // blocks of one stream per warp: their trees are built side by side, a lane each
 struct BlockBuildSmem {
-    BlockWork wk;
+    BlockWork wk[kBBPerWarp];
 };
 static_assert(sizeof(BlockDesc) <= 2 * kHeapSize * sizeof(uint16_t), "descriptor must fit in lt.freq + lt.dad");
 static_assert((kLCodes + 2 + kDCodes + 2) * sizeof(uint32_t) <= sizeof(TreeScratch::pq), "histogram must fit in the queue");
@@ -853,51 +857,68 @@ __global__ void __launch_bounds__(32) k_block_build(const uint32_t *__restrict__
                                                     const int32_t *__restrict__ in_len, BlockDesc *__restrict__ desc) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BlockBuildSmem &sm = *reinterpret_cast<BlockBuildSmem *>(smem_raw);
-    const int stream = blockIdx.y, blk = blockIdx.x, lane = threadIdx.x;
+    const int stream = blockIdx.y, blk0 = blockIdx.x * kBBPerWarp, lane = threadIdx.x;
     const int nf = nflush[stream];
-    if (blk > nf) return;
+    if (blk0 > nf) return;
+    const int nblk = min(kBBPerWarp, nf + 1 - blk0);  // blocks of this warp
     uint32_t *z = reinterpret_cast<uint32_t *>(&sm);
     for (int i = lane; i < (int)(sizeof(BlockBuildSmem) / 4); i += 32) z[i] = 0;
     __syncwarp();
-    uint32_t *lh = sm.wk.sc.pq, *dh = sm.wk.sc.pq + kLCodes + 2;
     const int32_t *be = blk_end + (int64_t)stream * max_blocks;
-    const uint32_t sym_begin = (uint32_t)blk * kSymEnd;
-    const uint32_t ns = blk < nf ? (uint32_t)kSymEnd : (uint32_t)(nsym[stream] - nf * kSymEnd);
-    const uint32_t pos_begin = blk == 0 ? 0u : (uint32_t)be[blk - 1];
-    const uint32_t pos_end = blk < nf ? (uint32_t)be[blk] : (uint32_t)in_len[stream];
-    const uint32_t *sy = syms + (int64_t)stream * stride + sym_begin;  // stream base is 64-byte aligned
-    auto tally = [&](uint32_t s) {
-        if (sym_dist(s) == 0) atomicAdd(&lh[sym_lc(s)], 1u);
-        else { atomicAdd(&lh[257 + len_code(sym_lc(s))], 1u); atomicAdd(&dh[dist_code(sym_dist(s) - 1)], 1u); }
-    };
-    const uint32_t head = min(ns, (4u - (sym_begin & 3u)) & 3u);  // symbols before the first 16-byte boundary
-    if ((uint32_t)lane < head) tally(sy[lane]);
-    const uint4 *v4 = reinterpret_cast<const uint4 *>(sy + head);
-    const uint32_t nv = (ns - head) >> 2;
+    const int n_in = in_len[stream], n_sym = nsym[stream];
+    // the frequencies of every block, by all lanes
+    for (int k = 0; k < nblk; k++) {
+        BlockWork &wk = sm.wk[k];
+        const int blk = blk0 + k;
+        uint32_t *lh = wk.sc.pq, *dh = wk.sc.pq + kLCodes + 2;
+        const uint32_t sym_begin = (uint32_t)blk * kSymEnd;
+        const uint32_t ns = blk < nf ? (uint32_t)kSymEnd : (uint32_t)(n_sym - nf * kSymEnd);
+        const uint32_t *sy = syms + (int64_t)stream * stride + sym_begin;  // stream base is 64-byte aligned
+        auto tally = [&](uint32_t s) {
+            if (sym_dist(s) == 0) atomicAdd(&lh[sym_lc(s)], 1u);
+            else { atomicAdd(&lh[257 + len_code(sym_lc(s))], 1u); atomicAdd(&dh[dist_code(sym_dist(s) - 1)], 1u); }
+        };
+        const uint32_t head = min(ns, (4u - (sym_begin & 3u)) & 3u);  // symbols before the first 16-byte boundary
+        if ((uint32_t)lane < head) tally(sy[lane]);
+        const uint4 *v4 = reinterpret_cast<const uint4 *>(sy + head);
+        const uint32_t nv = (ns - head) >> 2;
 #pragma unroll 4
-    for (uint32_t i = lane; i < nv; i += 32) {
-        const uint4 q = __ldg(v4 + i);
-        tally(q.x); tally(q.y); tally(q.z); tally(q.w);
+        for (uint32_t i = lane; i < nv; i += 32) {
+            const uint4 q = __ldg(v4 + i);
+            tally(q.x); tally(q.y); tally(q.z); tally(q.w);
+        }
+        for (uint32_t i = head + 4 * nv + lane; i < ns; i += 32) tally(sy[i]);
+        __syncwarp();
+        for (int i = lane; i < kLCodes; i += 32) wk.lt.freq[i] = (uint16_t)lh[i];
+        if (lane < kDCodes) wk.dt.freq[lane] = (uint16_t)dh[lane];
+        __syncwarp();
     }
-    for (uint32_t i = head + 4 * nv + lane; i < ns; i += 32) tally(sy[i]);
-    __syncwarp();
-    for (int i = lane; i < kLCodes; i += 32) sm.wk.lt.freq[i] = (uint16_t)lh[i];
-    if (lane < kDCodes) sm.wk.dt.freq[lane] = (uint16_t)dh[lane];
-    __syncwarp();
-    BlockDesc *d = reinterpret_cast<BlockDesc *>(sm.wk.lt.freq);
-    if (lane == 0) {
-        sm.wk.lt.freq[256] = 1;
+    // the trees: lane k builds block k's
+    if (lane < nblk) {
+        BlockWork &wk = sm.wk[lane];
+        const int blk = blk0 + lane;
+        const uint32_t sym_begin = (uint32_t)blk * kSymEnd;
+        const uint32_t ns = blk < nf ? (uint32_t)kSymEnd : (uint32_t)(n_sym - nf * kSymEnd);
+        const uint32_t pos_begin = blk == 0 ? 0u : (uint32_t)be[blk - 1];
+        const uint32_t pos_end = blk < nf ? (uint32_t)be[blk] : (uint32_t)n_in;
+        const uint32_t *sy = syms + (int64_t)stream * stride + sym_begin;
+        BlockDesc *d = reinterpret_cast<BlockDesc *>(wk.lt.freq);
+        wk.lt.freq[256] = 1;
         // loop top of the iteration that flushes the block: the start of its last symbol + 1, or the end of the input
-        const int64_t top = blk < nf ? (int64_t)pos_end - sym_advance(sy[ns - 1]) + 1 : (int64_t)in_len[stream];
-        build_block(sm.wk, d, pos_end - pos_begin, blk == nf, (int64_t)pos_begin >= window_base_at(top, in_len[stream]));
+        const int64_t top = blk < nf ? (int64_t)pos_end - sym_advance(sy[ns - 1]) + 1 : (int64_t)n_in;
+        build_block(wk, d, pos_end - pos_begin, blk == nf, (int64_t)pos_begin >= window_base_at(top, n_in));
         d->sym_begin = sym_begin; d->nsym = ns; d->pos_begin = pos_begin;
     }
     __syncwarp();
-    fill_block_tables(sm.wk, d, lane, 32);
-    __syncwarp();
-    uint32_t *dst = reinterpret_cast<uint32_t *>(desc + (int64_t)stream * max_blocks + blk);
-    const uint32_t *src = reinterpret_cast<const uint32_t *>(d);
-    for (int i = lane; i < (int)(sizeof(BlockDesc) / 4); i += 32) dst[i] = src[i];
+    for (int k = 0; k < nblk; k++) {
+        BlockWork &wk = sm.wk[k];
+        BlockDesc *d = reinterpret_cast<BlockDesc *>(wk.lt.freq);
+        fill_block_tables(wk, d, lane, 32);
+        __syncwarp();
+        uint32_t *dst = reinterpret_cast<uint32_t *>(desc + (int64_t)stream * max_blocks + blk0 + k);
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(d);
+        for (int i = lane; i < (int)(sizeof(BlockDesc) / 4); i += 32) dst[i] = src[i];
+    }
 }
 
 // ------------------------------------------------------------------ k_layout
@@ -1145,7 +1166,7 @@ void launch_deflate(const uint8_t *in, int64_t in_stride, const int32_t *in_len,
     }
     dim3 gb((unsigned)ws.max_blocks, (unsigned)B);
     { CCT_KERNEL(k_block_build, st);
-    k_block_build<<<gb, 32, sizeof(BlockBuildSmem), st>>>(ws.syms, ws.stride, ws.blk_end, ws.max_blocks, ws.nsym, ws.nflush,
+    k_block_build<<<dim3((unsigned)((ws.max_blocks + kBBPerWarp - 1) / kBBPerWarp), (unsigned)B), 32, sizeof(BlockBuildSmem), st>>>(ws.syms, ws.stride, ws.blk_end, ws.max_blocks, ws.nsym, ws.nflush,
                                                           in_len, ws.desc);
     }
     { CCT_KERNEL(k_layout, st);
