@@ -15,6 +15,8 @@
 //   k_offsets / k_copy   .cct header + stream -> caller's arena at scanned offsets
 #include <cuda_runtime.h>
 
+#include <cstddef>
+
 #include <algorithm>
 #include <mutex>
 
@@ -840,16 +842,18 @@ __global__ void __launch_bounds__(256) k_adler(const uint8_t *__restrict__ in, i
 // lane 0 then runs zlib's tree construction verbatim (its tie-breaking lives in the heap order, so it cannot be
 // replaced by a parallel Huffman construction).  That part is a chain of dependent shared-memory accesses, so the
 // kernel's speed is the number of blocks resident per SM: the histogram counters share storage with the priority
-// queue and the block descriptor is assembled where the literal tree's Freq/Dad arrays were (both dead by then).
+// queue and the order array, and the block descriptor is assembled in their place once the trees are built.
 #ifndef CCT_BB_PER_WARP
-#define CCT_BB_PER_WARP 2
+#define CCT_BB_PER_WARP 3
 #endif
 constexpr int kBBPerWarp = CCT_BB_PER_WARP;  // blocks of one stream per warp: their trees are built side by side, a lane each
 struct BlockBuildSmem {
     BlockWork wk[kBBPerWarp];
 };
-static_assert(sizeof(BlockDesc) <= 2 * kHeapSize * sizeof(uint16_t), "descriptor must fit in lt.freq + lt.dad");
-static_assert((kLCodes + 2 + kDCodes + 2) * sizeof(uint32_t) <= sizeof(TreeScratch::pq), "histogram must fit in the queue");
+static_assert(offsetof(TreeScratch, pq) == 0 && offsetof(TreeScratch, heap) == sizeof(TreeScratch::pq) &&
+              sizeof(BlockDesc) <= sizeof(TreeScratch::pq) + sizeof(TreeScratch::heap), "descriptor must fit in sc.pq + sc.heap");
+static_assert((kLCodes + 2) * sizeof(uint32_t) <= sizeof(TreeScratch::pq) && (kDCodes + 2) * sizeof(uint32_t) <= sizeof(TreeScratch::heap),
+              "histograms must fit in the queue and the order array");
 
 __global__ void __launch_bounds__(32) k_block_build(const uint32_t *__restrict__ syms, int64_t stride,
                                                     const int32_t *__restrict__ blk_end, int max_blocks,
@@ -870,7 +874,7 @@ __global__ void __launch_bounds__(32) k_block_build(const uint32_t *__restrict__
     for (int k = 0; k < nblk; k++) {
         BlockWork &wk = sm.wk[k];
         const int blk = blk0 + k;
-        uint32_t *lh = wk.sc.pq, *dh = wk.sc.pq + kLCodes + 2;
+        uint32_t *lh = wk.sc.pq, *dh = reinterpret_cast<uint32_t *>(wk.sc.heap);
         const uint32_t sym_begin = (uint32_t)blk * kSymEnd;
         const uint32_t ns = blk < nf ? (uint32_t)kSymEnd : (uint32_t)(n_sym - nf * kSymEnd);
         const uint32_t *sy = syms + (int64_t)stream * stride + sym_begin;  // stream base is 64-byte aligned
@@ -902,7 +906,7 @@ __global__ void __launch_bounds__(32) k_block_build(const uint32_t *__restrict__
         const uint32_t pos_begin = blk == 0 ? 0u : (uint32_t)be[blk - 1];
         const uint32_t pos_end = blk < nf ? (uint32_t)be[blk] : (uint32_t)n_in;
         const uint32_t *sy = syms + (int64_t)stream * stride + sym_begin;
-        BlockDesc *d = reinterpret_cast<BlockDesc *>(wk.lt.freq);
+        BlockDesc *d = reinterpret_cast<BlockDesc *>(wk.sc.pq);
         wk.lt.freq[256] = 1;
         // loop top of the iteration that flushes the block: the start of its last symbol + 1, or the end of the input
         const int64_t top = blk < nf ? (int64_t)pos_end - sym_advance(sy[ns - 1]) + 1 : (int64_t)n_in;
@@ -912,7 +916,7 @@ __global__ void __launch_bounds__(32) k_block_build(const uint32_t *__restrict__
     __syncwarp();
     for (int k = 0; k < nblk; k++) {
         BlockWork &wk = sm.wk[k];
-        BlockDesc *d = reinterpret_cast<BlockDesc *>(wk.lt.freq);
+        BlockDesc *d = reinterpret_cast<BlockDesc *>(wk.sc.pq);
         fill_block_tables(wk, d, lane, 32);
         __syncwarp();
         uint32_t *dst = reinterpret_cast<uint32_t *>(desc + (int64_t)stream * max_blocks + blk0 + k);

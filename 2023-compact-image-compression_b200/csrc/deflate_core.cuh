@@ -703,20 +703,25 @@ CCT_HD int finish_blocks(int nsym, uint32_t last_sym, int n, int32_t *blk_end) {
 constexpr int kLCodes = 286, kDCodes = 30, kBLCodes = 19, kHeapSize = 2 * kLCodes + 1, kMaxBits = 15;
 constexpr int kHdrWords = 160;  // dynamic-block header bit string capacity (worst case 4498 bits)
 
-struct Tree {  // one Huffman tree under construction (ct_data with Freq/Dad/Len/Code split out)
-    alignas(8) uint16_t freq[kHeapSize];  // freq + dad: dead once the tree is built; k_block_build assembles
-    uint16_t dad[kHeapSize];              // the block descriptor in their place
-    uint16_t len[kHeapSize];
-    uint16_t code[kLCodes + 2];           // leaves only
+// One Huffman tree under construction (ct_data with Freq/Len/Code split out).  The kernel's speed is the number of
+// blocks resident per SM, so the arrays are as small as they can be: frequencies of the leaves only (an inner node's
+// lives in its queue entry), lengths in bytes, the codes in the place of the frequencies (dead once the lengths and
+// the cost sums are known), and no Dad links at all: inner nodes are numbered in the order they are made, so the
+// k-th pair taken off the queue has the parent elems + k, and the order array says which pair a node was in.
+struct Tree {
+    uint16_t freq[kLCodes + 2];  // leaves only; after gen_bitlen: their codes
+    uint8_t len[kHeapSize + 3];
     int max_code;
+    CCT_HD uint16_t *code() { return freq; }
+    CCT_HD const uint16_t *code() const { return freq; }
 };
 
 struct SmallTree {  // distance (30 symbols) and bit-length (19 symbols) trees
-    uint16_t freq[2 * kDCodes + 1];
-    uint16_t dad[2 * kDCodes + 1];
-    uint16_t len[2 * kDCodes + 1];
-    uint16_t code[kDCodes + 2];
+    uint16_t freq[kDCodes + 2];
+    uint8_t len[2 * kDCodes + 3];
     int max_code;
+    CCT_HD uint16_t *code() { return freq; }
+    CCT_HD const uint16_t *code() const { return freq; }
 };
 
 struct TreeScratch {
@@ -724,7 +729,8 @@ struct TreeScratch {
     // smaller(n, m) = Freq[n] < Freq[m] || (equal && depth[n] <= depth[m]) is exactly (q[n] >> 10) <= (q[m] >> 10);
     // with the node in the same word a sift level is one 8-byte load of both children instead of a chain of
     // heap[] -> Freq[] -> depth[] loads.  (Freq <= 16384 + 2 symbols per block, depth <= 22 < 64, node < 573.)
-    alignas(8) uint32_t pq[kHeapSize + 3];
+    // (At most one entry per leaf is ever queued: a merge takes two out and puts one in.)
+    alignas(8) uint32_t pq[kLCodes + 6];
     int16_t heap[kHeapSize];  // nodes in the order they left the queue (zlib keeps them in the top of its heap array)
     uint16_t bl_count[kMaxBits + 1];
     int heap_len, heap_max;
@@ -788,8 +794,6 @@ CCT_HDN inline void build_tree(TreeScratch &s, T &t, int kind) {
         s.heap[--heap_max] = (int16_t)n; s.heap[--heap_max] = (int16_t)m;
         const uint32_t f = (nq >> 16) + (mq >> 16);
         const uint32_t dn = (nq >> 10) & 63u, dm = (mq >> 10) & 63u;
-        t.freq[node] = (uint16_t)f;
-        t.dad[n] = t.dad[m] = (uint16_t)node;
         s.pq[1] = (f << 16) | ((((dn >= dm ? dn : dm) + 1u) & 63u) << 10) | (uint32_t)node;
         node++;
         pq_down(s, 1, heap_len);
@@ -802,9 +806,9 @@ CCT_HDN inline void build_tree(TreeScratch &s, T &t, int kind) {
     t.len[s.heap[heap_max]] = 0;
     for (h = heap_max + 1; h < heap_size; h++) {
         n = s.heap[h];
-        bits = t.len[t.dad[n]] + 1;
+        bits = t.len[elems + ((heap_size - 1 - h) >> 1)] + 1;  // the parent of the pair n left the queue in
         if (bits > max_length) { bits = max_length; overflow++; }
-        t.len[n] = (uint16_t)bits;
+        t.len[n] = (uint8_t)bits;
         if (n > max_code) continue;  // internal node
         s.bl_count[bits]++;
         int xbits = 0;
@@ -828,7 +832,7 @@ CCT_HDN inline void build_tree(TreeScratch &s, T &t, int kind) {
                 if (m > max_code) continue;
                 if (t.len[m] != (unsigned)bits) {
                     opt_len += ((int64_t)bits - t.len[m]) * t.freq[m];
-                    t.len[m] = (uint16_t)bits;
+                    t.len[m] = (uint8_t)bits;
                 }
                 n--;
             }
@@ -842,7 +846,7 @@ CCT_HDN inline void build_tree(TreeScratch &s, T &t, int kind) {
     for (n = 0; n <= max_code; n++) {
         int len = t.len[n];
         if (len == 0) continue;
-        t.code[n] = (uint16_t)bit_reverse(next_code[len]++, len);
+        t.code()[n] = (uint16_t)bit_reverse(next_code[len]++, len);  // (in place of freq[n])
     }
 }
 
@@ -868,20 +872,20 @@ CCT_HDN inline void tree_rle(const T &t, int max_code, uint16_t *blfreq, const S
         if (++count < max_count && curlen == nextlen) continue;
         else if (count < min_count) {
             if (blfreq) blfreq[curlen] += (uint16_t)count;
-            else do { out->put(bl->code[curlen], bl->len[curlen]); } while (--count != 0);
+            else do { out->put(bl->code()[curlen], bl->len[curlen]); } while (--count != 0);
         } else if (curlen != 0) {
             if (curlen != prevlen) {
                 if (blfreq) blfreq[curlen]++;
-                else { out->put(bl->code[curlen], bl->len[curlen]); count--; }
+                else { out->put(bl->code()[curlen], bl->len[curlen]); count--; }
             }
             if (blfreq) blfreq[16]++;
-            else { out->put(bl->code[16], bl->len[16]); out->put((uint32_t)(count - 3), 2); }
+            else { out->put(bl->code()[16], bl->len[16]); out->put((uint32_t)(count - 3), 2); }
         } else if (count <= 10) {
             if (blfreq) blfreq[17]++;
-            else { out->put(bl->code[17], bl->len[17]); out->put((uint32_t)(count - 3), 3); }
+            else { out->put(bl->code()[17], bl->len[17]); out->put((uint32_t)(count - 3), 3); }
         } else {
             if (blfreq) blfreq[18]++;
-            else { out->put(bl->code[18], bl->len[18]); out->put((uint32_t)(count - 11), 7); }
+            else { out->put(bl->code()[18], bl->len[18]); out->put((uint32_t)(count - 11), 7); }
         }
         count = 0; prevlen = curlen;
         if (nextlen == 0) { max_count = 138; min_count = 3; }
@@ -925,7 +929,7 @@ CCT_HD int64_t window_base_at(int64_t t, int64_t n) {
 // lt.freq / dt.freq must hold the block's symbol frequencies (incl. freq[256] = 1) on entry, every
 // other field zero; can_store = the block's first byte is still inside zlib's window when it is flushed.  Fills
 // desc->type/last/stored_len/hdr/hdr_bits/body_bits and the code tables.  `desc` is
-// written only after the three trees are built, so it may occupy the storage of wk.lt.freq / wk.lt.dad.
+// written only after the three trees are built, so it may occupy the storage of wk.sc.pq / wk.sc.heap.
 CCT_HDN inline void build_block(BlockWork &wk, BlockDesc *desc, uint32_t stored_len, uint32_t last, bool can_store) {
     const uint8_t bl_order[kBLCodes] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
     wk.sc.opt_len = 0; wk.sc.static_len = 0;
@@ -971,8 +975,8 @@ CCT_HD void fill_block_tables(const BlockWork &wk, BlockDesc *desc, int lane, in
         for (int n = lane; n < kLCodes + 2; n += nl) { desc->lcode[n] = (uint16_t)static_lcode(n); desc->llen[n] = (uint8_t)static_llen(n); }
         for (int n = lane; n < kDCodes; n += nl) { desc->dcode[n] = (uint16_t)bit_reverse((uint32_t)n, 5); desc->dlen[n] = 5; }
     } else if (desc->type == 2) {
-        for (int n = lane; n < kLCodes; n += nl) { desc->lcode[n] = wk.lt.code[n]; desc->llen[n] = (uint8_t)(n <= wk.lt.max_code ? wk.lt.len[n] : 0); }
-        for (int n = lane; n < kDCodes; n += nl) { desc->dcode[n] = wk.dt.code[n]; desc->dlen[n] = (uint8_t)(n <= wk.dt.max_code ? wk.dt.len[n] : 0); }
+        for (int n = lane; n < kLCodes; n += nl) { desc->lcode[n] = wk.lt.code()[n]; desc->llen[n] = (uint8_t)(n <= wk.lt.max_code ? wk.lt.len[n] : 0); }
+        for (int n = lane; n < kDCodes; n += nl) { desc->dcode[n] = wk.dt.code()[n]; desc->dlen[n] = (uint8_t)(n <= wk.dt.max_code ? wk.dt.len[n] : 0); }
     }
 }
 
