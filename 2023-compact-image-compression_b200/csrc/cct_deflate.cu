@@ -530,7 +530,7 @@ __global__ void __launch_bounds__(kBinThreads, 5) k_hs_bins(const uint32_t *__re
 #define CCT_BPROBE_THREADS 128
 #endif
 #ifndef CCT_BPROBE_CTAS
-#define CCT_BPROBE_CTAS 32
+#define CCT_BPROBE_CTAS 64
 #endif
 constexpr int kBprobeThreads = CCT_BPROBE_THREADS;
 constexpr int kBprobeCtas = CCT_BPROBE_CTAS;  // CTAs per stream (each strides over the stream's sorted entries)
@@ -585,8 +585,11 @@ __global__ void __launch_bounds__(kBprobeThreads, 1536 / kBprobeThreads) k_bprob
 // the start's table entry, the few groups that can give the run's tail a longer match than the run itself); then, run by
 // run, the tail targets -- consecutive entries of the sorted array, consecutive positions -- read their entries off
 // those records, 32 at a time.  A run the walk cannot summarise goes through the general walk.
+#ifndef CCT_TAIL_CTAS
+#define CCT_TAIL_CTAS 9
+#endif
 constexpr int kTailWarps = 4, kTailCtas = 8;
-__global__ void __launch_bounds__(32 * kTailWarps) k_run_tails(const uint8_t *__restrict__ in, int64_t in_stride,
+__global__ void __launch_bounds__(32 * kTailWarps, CCT_TAIL_CTAS) k_run_tails(const uint8_t *__restrict__ in, int64_t in_stride,
                                                               const int32_t *__restrict__ in_len, const SortEnt *__restrict__ ent_all,
                                                               const uint32_t *__restrict__ runs_all, uint32_t *__restrict__ mlo_all,
                                                               uint32_t *__restrict__ mhi_all, const uint32_t *__restrict__ tails_all,
