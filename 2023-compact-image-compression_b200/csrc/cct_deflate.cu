@@ -1006,8 +1006,19 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(const uint8_t *__restrict
     __shared__ uint16_t lcode[kLCodes + 2], dcode[kDCodes + 2];
     __shared__ uint8_t llen[kLCodes + 2], dlen[kDCodes + 2];
     __shared__ uint32_t warp_sum[kPackThreads / 32];
+    // A match costs two more look-ups than a literal, not a chain of code arithmetic (the lanes of a warp hold both
+    // kinds and run both paths): per length lc the bits of its length code with the extra bits appended and their
+    // number; per distance code the number of bits of code and extra bits together.
+    __shared__ uint32_t mbits[256];
+    __shared__ uint8_t mnb[256], dnb[kDCodes + 2];
     for (int i = tid; i < kLCodes + 2; i += kPackThreads) { lcode[i] = d.lcode[i]; llen[i] = d.llen[i]; }
-    if (tid < kDCodes + 2) { dcode[tid] = d.dcode[tid]; dlen[tid] = d.dlen[tid]; }
+    if (tid < kDCodes + 2) { dcode[tid] = d.dcode[tid]; dlen[tid] = d.dlen[tid]; dnb[tid] = (uint8_t)(d.dlen[tid] + (tid < kDCodes ? dist_extra_bits(tid) : 0)); }
+    static_assert(kPackThreads == 256, "one length per thread");
+    {
+        const int code = len_code(tid), extra = len_extra_bits(code), nb = d.llen[code + 257];
+        mbits[tid] = (uint32_t)d.lcode[code + 257] | (((uint32_t)tid & ((1u << extra) - 1u)) << nb);
+        mnb[tid] = (uint8_t)(nb + extra);
+    }
     __syncthreads();
     const int ns = (int)d.nsym;
     // A thread's symbols are consecutive (its bits are, too), so its loads stride the warp.  The runs are cut on
@@ -1043,7 +1054,10 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(const uint8_t *__restrict
         }
     };
     uint32_t bits = 0;
-    for_each([&](uint32_t sym) { bits += (uint32_t)sym_nbits(sym, llen, dlen); });
+    for_each([&](uint32_t sym) {
+        const int dist = sym_dist(sym), lc = sym_lc(sym);
+        bits += dist ? (uint32_t)mnb[lc] + dnb[dist_code(dist - 1)] : (uint32_t)llen[lc];
+    });
     uint32_t incl = bits;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -1058,10 +1072,13 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(const uint8_t *__restrict
     if (bits) {
         BitSink sink{out32 + (start >> 5), 0ull, (int)(start & 31), true};
         for_each([&](uint32_t sym) {
-            int nb;
-            unsigned long long b = sym_bits(sym, lcode, llen, dcode, dlen, &nb);
-            if (nb > 32) { sink.put((uint32_t)b, 32); sink.put((uint32_t)(b >> 32), nb - 32); }
-            else sink.put((uint32_t)b, nb);
+            const int dist = sym_dist(sym), lc = sym_lc(sym);
+            if (dist == 0) sink.put(lcode[lc], llen[lc]);
+            else {  // length code + extra (at most 20 bits), then distance code + extra (at most 28)
+                sink.put(mbits[lc], mnb[lc]);
+                const int dd = dist - 1, code = dist_code(dd), cl = dlen[code];
+                sink.put((uint32_t)dcode[code] | (((uint32_t)dd & ((1u << dist_extra_bits(code)) - 1u)) << cl), dnb[code]);
+            }
         });
         sink.finish();
     }
