@@ -20,7 +20,7 @@ skip=$(( (n + 1) / 2 ))
 ncu --set full --clock-control none --import-source on --launch-skip $skip -f -o gpurun_out/${tag}_prof \
     python bench.py $A > gpurun_out/${tag}_ncu2.log 2>&1
 ncu -i gpurun_out/${tag}_prof.ncu-rep --page raw --csv > gpurun_out/${tag}_raw.csv 2>/dev/null
-for k in k_bprobe k_hs_bins k_hs_split; do
+for k in k_bprobe k_run_tails k_block_build k_hs_bins; do
   ncu -i gpurun_out/${tag}_prof.ncu-rep --page source --csv --kernel-name regex:$k --print-source cuda,sass \
       > gpurun_out/${tag}_src_$k.csv 2>/dev/null || true
 done
