@@ -125,6 +125,11 @@ def test_deflate_matches_libz(torch_cuda, native, oracle, synth):
         blobs.append(oracle.encode(synth.synth_ct(s), detail=True)[1]["payload"])
     from test_oracle import _lz_stress
     blobs += [_lz_stress(3, 300000), _lz_stress(4, 70001)]
+    from test_host_logic import _runs_blob
+    rng_r = np.random.default_rng(12)
+    afters = [[5, 6, 7, 8, 9, 1, 2, 3], [5, 6, 7, 1], [5, 1], [9], list(range(10, 250))]
+    blobs += [_runs_blob(rng_r, 200, [0, 0, 7], [258, 300, 517, 1000, 40, 5, 3, 2000, 5000], afters, [1, 2, 5, 30, 300]),
+              b"".join(bytes(300 if i % 25 == 24 else int(rng_r.integers(3, 60))) + bytes([5, 6, int(rng_r.integers(1, 4))]) for i in range(600))]
     got = _gpu_deflate(torch_cuda, native, blobs)
     for b, g in zip(blobs, got):
         assert g == zlib.compress(b, 9), len(b)
@@ -492,6 +497,22 @@ def test_stage_match_tables(torch_cuda, native, hostsim, oracle, synth):
     blobs += [bytes(9000) + rng.integers(0, 4, size=3000, dtype=np.uint8).tobytes() + bytes(70000) + b"abc" * 500]
     blobs += [b"", b"a", b"abc", b"aaaa", bytes(4097), bytes(4096) + b"ab"]
     blobs += [oracle.encode(synth.synth_ct(s, 256), detail=True)[1]["payload"] for s in (0, 1)]
+    # byte runs (k_run_tails): shared continuations, both chain budgets, the distance limit, a run at position 0 and at
+    # the end, capped run counts, collisions in the run's bucket, and more records than a run keeps (the general-walk
+    # fall-back inside k_run_tails)
+    from test_host_logic import _runs_blob
+    afters = [[5, 6, 7, 8, 9, 1, 2, 3], [5, 6, 7, 1], [5, 1], [9], list(range(10, 250)), list(range(10, 250)) + [3]]
+    blobs += [
+        _runs_blob(rng, 60, [0], [258, 259, 260, 300, 515, 516, 517, 1000, 257, 100], afters, [1, 2, 5, 30]),
+        _runs_blob(rng, 80, [0, 0, 0, 7, 200], [258, 270, 400, 3, 5, 40, 258 + 255], afters, [1, 3, 10]),
+        _runs_blob(rng, 30, [0], [2000, 5000, 4096 + 300, 1024 + 258, 1024 + 257, 900], afters, [1, 2]),
+        bytes(300) + _runs_blob(rng, 20, [0], [400], afters, [2]) + bytes(600) + b"\x05" * 255,
+        _runs_blob(rng, 12, [0], [9000, 12000, 300], afters, [2, 700]),
+        bytes(70000) + b"\x05\x06" + bytes(66000) + b"\x05\x06\x07" + bytes(400) + b"\x05\x06",
+        b"".join(bytes(300) + bytes([5, 6, 7]) + bytes([32, 0, 0, 1]) * 50 for _ in range(20)),
+        b"".join(bytes(300 if i % 25 == 24 else int(rng.integers(3, 60))) + bytes([5, 6, int(rng.integers(1, 4))]) for i in range(600)),
+        b"".join(bytes(300 if i % 10 == 9 else int(rng.integers(100, 280))) + bytes([5, int(rng.integers(1, 3))]) for i in range(300)),
+    ]
     L = native.lib()
     B = len(blobs)
     max_len = max(len(b) for b in blobs)
