@@ -289,7 +289,12 @@ struct PassHooks {
     // neighbouring passes overlap on the GPU (per-stream kernels of one pass leave SMs idle that the other fills)
     cudaStream_t alt_stream = nullptr;
     void *alt_ws = nullptr;
-    cudaEvent_t ready = nullptr, carry[2] = {nullptr, nullptr};  // set-up done on the main stream; offsets of a pass written
+    // ... and a third (passes 2, 5, 8 ...), used only together with the second
+    cudaStream_t alt_stream2 = nullptr;
+    void *alt_ws2 = nullptr;
+    cudaEvent_t ready = nullptr, carry[3] = {nullptr, nullptr, nullptr};  // set-up done on the main stream; offsets of a pass written
+    int lanes() const { return alt_stream && alt_ws ? (alt_stream2 && alt_ws2 ? 3 : 2) : 1; }
+    cudaStream_t lane_stream(int lane, cudaStream_t main) const { return lane == 0 ? main : (lane == 1 ? alt_stream : alt_stream2); }
 };
 
 // Library-owned second stream of a device for cct_decode_batch (one per device, created on first use).
@@ -376,21 +381,23 @@ int encode_impl(const uint16_t *d_px, int B, int rows, int cols, uint32_t flags,
     rc = get_order(rows, cols, (flags & CCT_FLAG_FRACTAL) != 0, st, &order);
     if (rc != CCT_OK) return rc;
     if (d_stats) CK(cudaMemsetAsync(d_stats, 0, (size_t)B * 4 * sizeof(int32_t), st));
-    EncodeWs wss[2];
+    EncodeWs wss[3];
     encode_ws_carve(&wss[0], d_ws, Bc, n_px, flags);
-    const bool two = hooks && hooks->alt_stream && hooks->alt_ws;
+    const int n_lanes = hooks ? hooks->lanes() : 1;
+    const bool two = n_lanes > 1;
     if (two) {
         encode_ws_carve(&wss[1], hooks->alt_ws, Bc, n_px, flags);
+        if (n_lanes > 2) encode_ws_carve(&wss[2], hooks->alt_ws2, Bc, n_px, flags);
         CK(cudaEventRecord(hooks->ready, st_main));
-        CK(cudaStreamWaitEvent(hooks->alt_stream, hooks->ready, 0));
+        for (int l = 1; l < n_lanes; l++) CK(cudaStreamWaitEvent(hooks->lane_stream(l, st_main), hooks->ready, 0));
     }
     if (hooks && hooks->starts) for (size_t k = 0; k + 1 < hooks->starts->size(); k++) if ((*hooks->starts)[k + 1] - (*hooks->starts)[k] > Bc) return CCT_E_WORKSPACE;
     int pass = 0;
     for (int first = 0, b = 0; first < B; first += b, pass++) {
         b = hooks && hooks->starts ? (*hooks->starts)[pass + 1] - first : std::min(Bc, B - first);
-        const int lane = two ? (pass & 1) : 0;
+        const int lane = pass % n_lanes;
         const EncodeWs &ws = wss[lane];
-        cudaStream_t st = lane ? hooks->alt_stream : st_main;
+        cudaStream_t st = two ? hooks->lane_stream(lane, st_main) : st_main;
         const uint16_t *px = d_px + (int64_t)first * n_px;
         int32_t *stats = d_stats ? d_stats + (int64_t)first * 4 : nullptr;
         if (hooks && hooks->before && (rc = hooks->before(pass, first, b, st)) != CCT_OK) return rc;
@@ -405,14 +412,14 @@ int encode_impl(const uint16_t *d_px, int B, int rows, int cols, uint32_t flags,
             body = ws.zbuf; body_stride = ws.zstride; body_len = ws.zlen;
         }
         // the running offset comes from the previous pass, which ran on the other stream
-        if (two && pass > 0) CK(cudaStreamWaitEvent(st, hooks->carry[(pass - 1) & 1], 0));
+        if (two && pass > 0) CK(cudaStreamWaitEvent(st, hooks->carry[(pass - 1) % n_lanes], 0));
         launch_assemble(body, body_stride, body_len, b, rows, cols, flags, d_out, (int64_t)out_cap, d_offsets, first, d_status, st);
-        if (two) CK(cudaEventRecord(hooks->carry[pass & 1], st));
+        if (two) CK(cudaEventRecord(hooks->carry[pass % n_lanes], st));
         CK(cudaGetLastError());
         if (hooks && hooks->after && (rc = hooks->after(pass, first, b, st)) != CCT_OK) return rc;
     }
-    if (two) {  // the caller's stream ends after everything
-        CK(cudaEventRecord(hooks->ready, hooks->alt_stream));
+    for (int l = 1; l < n_lanes; l++) {  // the caller's stream ends after everything
+        CK(cudaEventRecord(hooks->ready, hooks->lane_stream(l, st_main)));
         CK(cudaStreamWaitEvent(st_main, hooks->ready, 0));
     }
     return CCT_OK;
@@ -432,27 +439,28 @@ int decode_impl(const uint8_t *d_in, const int64_t *d_offsets, int B, int rows, 
     const int32_t *order = nullptr;
     rc = get_order(rows, cols, true, st, &order);
     if (rc != CCT_OK) return rc;
-    DecodeWs wss[2];
+    DecodeWs wss[3];
     decode_ws_carve(&wss[0], d_ws, Bc, n_px);
-    const bool two = hooks && hooks->alt_stream && hooks->alt_ws;
-    if (two) {
+    const int n_lanes = hooks ? hooks->lanes() : 1;
+    if (n_lanes > 1) {
         decode_ws_carve(&wss[1], hooks->alt_ws, Bc, n_px);
+        if (n_lanes > 2) decode_ws_carve(&wss[2], hooks->alt_ws2, Bc, n_px);
         CK(cudaEventRecord(hooks->ready, st));
-        CK(cudaStreamWaitEvent(hooks->alt_stream, hooks->ready, 0));
+        for (int l = 1; l < n_lanes; l++) CK(cudaStreamWaitEvent(hooks->lane_stream(l, st), hooks->ready, 0));
     }
     if (hooks && hooks->starts) for (size_t k = 0; k + 1 < hooks->starts->size(); k++) if ((*hooks->starts)[k + 1] - (*hooks->starts)[k] > Bc) return CCT_E_WORKSPACE;
     int pass = 0;
     for (int first = 0, b = 0; first < B; first += b, pass++) {
         b = hooks && hooks->starts ? (*hooks->starts)[pass + 1] - first : std::min(Bc, B - first);
-        const int lane = two ? (pass & 1) : 0;
-        cudaStream_t ps = lane ? hooks->alt_stream : st;
+        const int lane = pass % n_lanes;
+        cudaStream_t ps = n_lanes > 1 ? hooks->lane_stream(lane, st) : st;
         if (hooks && hooks->before && (rc = hooks->before(pass, first, b, ps)) != CCT_OK) return rc;
         launch_decode(d_in, d_offsets + first, b, rows, cols, order, d_px + (int64_t)first * n_px, d_status + first, wss[lane], ps);
         CK(cudaGetLastError());
         if (hooks && hooks->after && (rc = hooks->after(pass, first, b, ps)) != CCT_OK) return rc;
     }
-    if (two) {
-        CK(cudaEventRecord(hooks->ready, hooks->alt_stream));
+    for (int l = 1; l < n_lanes; l++) {
+        CK(cudaEventRecord(hooks->ready, hooks->lane_stream(l, st)));
         CK(cudaStreamWaitEvent(st, hooks->ready, 0));
     }
     return CCT_OK;
@@ -565,15 +573,15 @@ namespace {
 struct HostCtx {
     std::mutex mu;  // one host-buffer call at a time per device; calls to different devices run side by side
     int dev = -1;
-    cudaStream_t st = nullptr, st2 = nullptr, up = nullptr, down = nullptr;  // kernels (two lanes), host->device copies, device->host copies
-    cudaEvent_t ready = nullptr, carry[2] = {nullptr, nullptr};
+    cudaStream_t st = nullptr, st2 = nullptr, st3 = nullptr, up = nullptr, down = nullptr;  // kernels (up to three lanes), host->device copies, device->host copies
+    cudaEvent_t ready = nullptr, carry[3] = {nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> events;
     cudaEvent_t event(size_t i) {
         while (events.size() <= i) { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); events.push_back(e); }
         return events[i];
     }
-    void *buf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    size_t cap[6] = {0, 0, 0, 0, 0, 0};
+    void *buf[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t cap[7] = {0, 0, 0, 0, 0, 0, 0};
     int ensure(int slot, size_t bytes) {
         if (cap[slot] >= bytes) return CCT_OK;
         if (buf[slot]) { cudaFree(buf[slot]); buf[slot] = nullptr; cap[slot] = 0; }
@@ -608,8 +616,12 @@ struct HostCtx {
         marks.clear();
         tracing = false;
     }
-    void drain() { cudaStreamSynchronize(up); cudaStreamSynchronize(st); cudaStreamSynchronize(st2); cudaStreamSynchronize(down); }
-    void two_lanes(PassHooks &h, int slot) const { h.alt_stream = st2; h.alt_ws = buf[slot]; h.ready = ready; h.carry[0] = carry[0]; h.carry[1] = carry[1]; }
+    void drain() { cudaStreamSynchronize(up); cudaStreamSynchronize(st); cudaStreamSynchronize(st2); cudaStreamSynchronize(st3); cudaStreamSynchronize(down); }
+    void more_lanes(PassHooks &h, int n_lanes) const {  // workspaces of lanes 1 and 2: slots 5 and 6
+        h.alt_stream = st2; h.alt_ws = buf[5]; h.ready = ready;
+        if (n_lanes > 2) { h.alt_stream2 = st3; h.alt_ws2 = buf[6]; }
+        for (int l = 0; l < 3; l++) h.carry[l] = carry[l];
+    }
 };
 
 std::mutex g_ctx_mu;  // guards the map only
@@ -651,9 +663,9 @@ int get_ctx(int device, HostCtx **out) {
         c.dev = device;
         CK(cudaStreamCreateWithFlags(&c.st, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&c.st2, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&c.st3, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&c.ready, cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&c.carry[0], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&c.carry[1], cudaEventDisableTiming));
+        for (int l = 0; l < 3; l++) CK(cudaEventCreateWithFlags(&c.carry[l], cudaEventDisableTiming));
         CK(cudaStreamCreateWithFlags(&c.up, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&c.down, cudaStreamNonBlocking));
     }
@@ -723,10 +735,11 @@ int host_schedule(int B, size_t n_px, std::vector<int> &starts, bool decode) {
     starts.push_back(B);
     return per;
 }
-// Neighbouring passes run on two streams unless CCT_HOST_LANES=1.
-bool host_two_lanes(int n_pass) {
-    if (const char *e = getenv("CCT_HOST_LANES")) return atoi(e) > 1 && n_pass > 1;
-    return n_pass > 1;
+// Neighbouring passes run on two streams (CCT_HOST_LANES = 1, 2 or 3).
+int host_lanes(int n_pass) {
+    int n = 2;
+    if (const char *e = getenv("CCT_HOST_LANES")) n = std::min(std::max(atoi(e), 1), 3);
+    return std::min(n, std::max(n_pass, 1));
 }
 
 }  // namespace
@@ -755,8 +768,8 @@ int cct_encode_host(const uint16_t *h_px, int B, int rows, int cols, uint32_t fl
     if ((rc = c->ensure(1, std::max<size_t>(arena, 16)))) return rc;
     if ((rc = c->ensure(2, (size_t)(B + 1) * 8 + (size_t)B * 4 + (size_t)B * 16))) return rc;
     if ((rc = c->ensure(3, ws_bytes))) return rc;
-    const bool two = host_two_lanes(n_pass);
-    if (two && (rc = c->ensure(5, ws_bytes))) return rc;
+    const int n_lanes = host_lanes(n_pass);
+    for (int l = 1; l < n_lanes; l++) if ((rc = c->ensure(4 + l, ws_bytes))) return rc;
     uint16_t *d_px = (uint16_t *)c->buf[0];
     uint8_t *d_out = (uint8_t *)c->buf[1];
     int64_t *d_off = (int64_t *)c->buf[2];
@@ -784,7 +797,8 @@ int cct_encode_host(const uint16_t *h_px, int B, int rows, int cols, uint32_t fl
     PassHooks hooks;
     hooks.max_pass = per;
     hooks.starts = &starts;
-    if (two) c->two_lanes(hooks, 5);
+    if (n_lanes > 1) c->more_lanes(hooks, n_lanes);
+    const int back = std::max(n_lanes, 2);  // how far the downloads trail the pass being queued
     hooks.before = [&](int k, int, int, cudaStream_t ps) -> int {
         CK(cudaStreamWaitEvent(ps, c->event(k), 0));
         c->mark("start", k, ps);
@@ -794,15 +808,15 @@ int cct_encode_host(const uint16_t *h_px, int B, int rows, int cols, uint32_t fl
         c->mark("end", k, ps);
         CK(cudaMemcpyAsync(h_offsets + first + 1, d_off + first + 1, (size_t)count * 8, cudaMemcpyDeviceToHost, ps));
         CK(cudaEventRecord(c->event(n_pass + k), ps));
-        // Passes k-1 and k are queued: now wait for pass k-2 and start its download.  (One pass further back than the
-        // data needs: measured, the first kernel of whatever is queued AFTER a download has been issued does not start
-        // before that download is through -- with k-1 here, every pass began 2.6 ms after the one before it on its
-        // lane had ended.)
-        return k > 1 ? fetch(k - 2) : CCT_OK;
+        // Passes up to k are queued: now wait for pass k - back and start its download.  (One pass further back than
+        // the data needs: measured, the first kernel of whatever is queued AFTER a download has been issued does not
+        // start before that download is through -- with k-1 here and two lanes, every pass began 2.6 ms after the one
+        // before it on its lane had ended.  With `back` = the number of lanes the next pass is queued while the one
+        // before it on its lane is still running.)
+        return k >= back ? fetch(k - back) : CCT_OK;
     };
     rc = encode_impl(d_px, B, rows, cols, flags, d_out, arena, d_off, d_status, d_stats, c->buf[3], c->cap[3], c->st, &hooks);
-    if (rc == CCT_OK && n_pass > 1) rc = fetch(n_pass - 2);
-    if (rc == CCT_OK) rc = fetch(n_pass - 1);
+    for (int k = std::max(0, n_pass - back); rc == CCT_OK && k < n_pass; k++) rc = fetch(k);
     if (rc != CCT_OK) { c->drain(); return rc; }
     CK(cudaMemcpyAsync(h_status, d_status, (size_t)B * 4, cudaMemcpyDeviceToHost, c->st));
     if (h_stats) CK(cudaMemcpyAsync(h_stats, d_stats, (size_t)B * 16, cudaMemcpyDeviceToHost, c->st));
@@ -835,8 +849,8 @@ int cct_decode_host(const uint8_t *h_in, const int64_t *h_offsets, int B, int ro
     if ((rc = c->ensure(1, std::max<size_t>((size_t)total, 16)))) return rc;
     if ((rc = c->ensure(2, (size_t)(B + 1) * 8 + (size_t)B * 4))) return rc;
     if ((rc = c->ensure(4, ws_bytes))) return rc;
-    const bool two = host_two_lanes(n_pass);
-    if (two && (rc = c->ensure(5, ws_bytes))) return rc;
+    const int n_lanes = host_lanes(n_pass);
+    for (int l = 1; l < n_lanes; l++) if ((rc = c->ensure(4 + l, ws_bytes))) return rc;
     uint16_t *d_px = (uint16_t *)c->buf[0];
     uint8_t *d_in = (uint8_t *)c->buf[1];
     int64_t *d_off = (int64_t *)c->buf[2];
@@ -857,7 +871,7 @@ int cct_decode_host(const uint8_t *h_in, const int64_t *h_offsets, int B, int ro
     PassHooks hooks;
     hooks.max_pass = per;
     hooks.starts = &starts;
-    if (two) c->two_lanes(hooks, 5);
+    if (n_lanes > 1) c->more_lanes(hooks, n_lanes);
     hooks.before = [&](int k, int, int, cudaStream_t ps) -> int {
         CK(cudaStreamWaitEvent(ps, c->event(k), 0));
         c->mark("start", k, ps);
@@ -898,10 +912,11 @@ void cct_release(void) {
         std::lock_guard<std::mutex> lk(g_ctx_mu);
         for (auto &kv : g_ctx) {
             cudaSetDevice(kv.first);
-            for (int i = 0; i < 6; i++) if (kv.second.buf[i]) cudaFree(kv.second.buf[i]);
+            for (int i = 0; i < 7; i++) if (kv.second.buf[i]) cudaFree(kv.second.buf[i]);
             for (cudaEvent_t e : kv.second.events) cudaEventDestroy(e);
             if (kv.second.st) cudaStreamDestroy(kv.second.st);
             if (kv.second.st2) cudaStreamDestroy(kv.second.st2);
+            if (kv.second.st3) cudaStreamDestroy(kv.second.st3);
             if (kv.second.ready) cudaEventDestroy(kv.second.ready);
             for (cudaEvent_t e : kv.second.carry) if (e) cudaEventDestroy(e);
             if (kv.second.up) cudaStreamDestroy(kv.second.up);

@@ -21,20 +21,17 @@ def t(fn, reps=5):
     for _ in range(reps): fn()
     return (time.perf_counter() - t0) / reps * 1e3
 enc(); dec(); assert torch.equal(h_out, h_px)
-enc_cfgs = ["", "256,512,768,768,768,512,256,256", "256,512,896,896,896,384,256", "256,512,1024,1024,768,512",
-            "128,256,512,896,896,768,384,256", "256,512,704,704,704,704,512", "256,384,640,768,768,640,384,256",
-            "192,320,512,768,768,640,512,384", "256,512,832,832,832,416,416", "256,512,1024,1024,640,384,256",
-            "256,512,960,960,704,448,256", "128,384,768,960,960,512,256,128", ""]
-for c in enc_cfgs:
-    os.environ.pop("CCT_HOST_SIZES", None)
-    if c: os.environ["CCT_HOST_SIZES"] = c
-    assert sum(int(x) for x in c.split(",")) == B if c else True
-    print("encode %-40s %.2f ms" % (c or "default", t(enc)), flush=True)
-os.environ.pop("CCT_HOST_SIZES", None)
-dec_cfgs = ["", "64,128,256,512,1024,1024,1088", "128,256,512,1024,1024,1152", "32,96,256,512,1024,1024,1152",
-            "128,128,256,512,768,768,768,768", "64,64,128,256,512,1024,1024,1024", ""]
-for c in dec_cfgs:
-    os.environ.pop("CCT_HOST_SIZES_DEC", None)
-    if c: os.environ["CCT_HOST_SIZES_DEC"] = c
-    assert sum(int(x) for x in c.split(",")) == B if c else True
-    print("decode %-40s %.2f ms" % (c or "default", t(dec)), flush=True)
+def run(kind, fn, cfgs):
+    keys = ("CCT_HOST_SIZES", "CCT_HOST_SIZES_DEC", "CCT_HOST_LANES", "CCT_HOST_PASS", "CCT_HOST_LEADS", "CCT_HOST_TAILS")
+    for env in cfgs:
+        for k in keys: os.environ.pop(k, None)
+        os.environ.update(env)
+        print("%s %-60s %.2f ms" % (kind, " ".join(f"{k[9:]}={v}" for k, v in env.items()) or "default", t(fn)), flush=True)
+    for k in keys: os.environ.pop(k, None)
+L3 = {"CCT_HOST_LANES": "3"}
+run("encode", enc, [{}, L3, {**L3, "CCT_HOST_PASS": "768"}, {**L3, "CCT_HOST_PASS": "640"}, {**L3, "CCT_HOST_PASS": "512"},
+                    {**L3, "CCT_HOST_PASS": "768", "CCT_HOST_LEADS": "4,2,2", "CCT_HOST_TAILS": "2,2,4"},
+                    {**L3, "CCT_HOST_SIZES": "256,384,512,640,640,640,512,320,192"},
+                    {**L3, "CCT_HOST_SIZES": "192,320,448,704,704,704,512,320,192"},
+                    {"CCT_HOST_PASS": "768"}, {}])
+run("decode", dec, [{}, L3, {**L3, "CCT_HOST_PASS": "768"}, {**L3, "CCT_HOST_PASS": "640"}, {"CCT_HOST_LANES": "1"}, {}])

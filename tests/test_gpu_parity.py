@@ -452,6 +452,30 @@ def test_second_device_in_one_process(torch_cuda, pkg, native, synth, oracle):
     assert torch.cuda.current_device() == 0
 
 
+def test_host_entry_points_lanes_and_passes(torch_cuda, native, synth, oracle, monkeypatch):
+    """cct_encode_host / cct_decode_host over several passes on one, two and three lanes (CCT_HOST_LANES), with the
+    downloads trailing the pass being queued: bytes equal the oracle's whatever the schedule, and the pixels come back."""
+    L = native.lib()
+    imgs = np.stack([synth.synth_ct(s, 128) for s in range(23)])
+    want = [oracle.encode(im) for im in imgs]
+    cap = int(L.cct_file_bound(128, 128)) * 23
+    for lanes, sizes in (("1", "5,5,5,8"), ("2", "1,2,4,8,8"), ("3", "3,3,3,3,3,3,3,2"), ("3", "23"), ("3", "11,12"), ("2", "")):
+        monkeypatch.setenv("CCT_HOST_LANES", lanes)
+        if sizes:
+            monkeypatch.setenv("CCT_HOST_SIZES", sizes)
+            monkeypatch.setenv("CCT_HOST_SIZES_DEC", sizes)
+        else:
+            monkeypatch.delenv("CCT_HOST_SIZES", raising=False)
+            monkeypatch.delenv("CCT_HOST_SIZES_DEC", raising=False)
+        arena = np.zeros(cap, np.uint8); off = np.zeros(24, np.int64); st = np.ones(23, np.uint32)
+        native.check(L.cct_encode_host(imgs.ctypes.data, 23, 128, 128, 7, arena.ctypes.data, cap, off.ctypes.data, st.ctypes.data, None, 0))
+        assert not st.any()
+        assert [arena[off[i]:off[i + 1]].tobytes() for i in range(23)] == want, (lanes, sizes)
+        back = np.zeros_like(imgs); dst = np.ones(23, np.uint32)
+        native.check(L.cct_decode_host(arena.ctypes.data, off.ctypes.data, 23, 128, 128, back.ctypes.data, dst.ctypes.data, 0))
+        assert np.array_equal(back, imgs) and not dst.any(), (lanes, sizes)
+
+
 def test_config_batch_roundtrip_4096(torch_cuda, pkg, synth, oracle):
     """BASELINE.json configs[1] at full size through size-independent properties: every bytestream length and a
     checksum of checksums equal the oracle's, and decode(encode(x)) == x for all 4096 slices."""
