@@ -131,6 +131,27 @@ def workload_config(B, n, world, distinct):
             "parallelism": f"batch sharded over {world} GPU(s), no collective on the data path"}
 
 
+def bind_near_gpu(torch, local):
+    """Several ranks on one box: keep this rank (and the pinned buffers it is about to allocate) on the CPUs next to
+    its GPU, as a launcher with NUMA binding would.  Returns what was done, for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        props = torch.cuda.get_device_properties(local)
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(props.uuid)).encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(f"{props.pci_domain_id:08x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0".encode())
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1} & os.sched_getaffinity(0)
+        if not cpus:
+            return "unbound (no CPU affinity reported)"
+        os.sched_setaffinity(0, cpus)
+        return f"rank bound to the {len(cpus)} CPUs next to its GPU"
+    except Exception as e:  # no NVML, no permission ...: run unbound
+        return f"unbound ({type(e).__name__})"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -197,6 +218,7 @@ def main():
     import torch.distributed as dist
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_near_gpu(torch, local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     pkg = importlib.import_module(PKG)
@@ -398,6 +420,8 @@ def main():
             "kernels_ms_per_step": {k: round(v[1] / args.steps, 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
             "kernels_ms_warmup_step": {k: round(v[1], 3) for k, v in sorted(prof_all.items(), key=lambda kv: -kv[1][1])},
             "gen_seconds": round(gen_s, 1)}
+    if numa:
+        line["host_binding"] = numa
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
