@@ -370,6 +370,19 @@ def test_host_pass_schedule(pkg):
             else:
                 assert sizes == ([B] if B else [])
     assert L.cct_debug_host_schedule(4096, 512 * 512, 0, buf, 2) < 0  # too few entries
+    # explicit pass sizes (CCT_HOST_SIZES / CCT_HOST_SIZES_DEC) are taken when they add up to the batch, ignored otherwise
+    import os
+    default = list(buf[:L.cct_debug_host_schedule(4096, 512 * 512, 0, buf, 64) + 1])
+    try:
+        os.environ["CCT_HOST_SIZES"] = "256,512,1024,1024,1024,256"
+        n = L.cct_debug_host_schedule(4096, 512 * 512, 0, buf, 64)
+        assert list(buf[:n + 1]) == [0, 256, 768, 1792, 2816, 3840, 4096]
+        assert list(buf[:L.cct_debug_host_schedule(4096, 512 * 512, 1, buf, 64) + 1]) != [0, 256, 768, 1792, 2816, 3840, 4096]  # (decode has its own)
+        os.environ["CCT_HOST_SIZES"] = "256,512,1024"
+        n = L.cct_debug_host_schedule(4096, 512 * 512, 0, buf, 64)
+        assert list(buf[:n + 1]) == default
+    finally:
+        os.environ.pop("CCT_HOST_SIZES", None)
 
 
 def test_evaluate_host_helpers(pkg, tmp_path):
