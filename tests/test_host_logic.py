@@ -182,6 +182,42 @@ def test_run_tails_match_zlib_candidate_loop(hostsim):
     assert announced > 300 and 0 < fallback < announced  # both ways of settling a tail were exercised
 
 
+def _fuzz_blob(rng):
+    """Runs of a few byte values in every length class (short, around 258, beyond either chain budget, longer than the
+    window), shared continuations, noise, and triples that hash like the run's triple, in random order."""
+    parts, n, total = [], 0, int(rng.integers(2000, 60000))
+    alpha = [int(x) for x in rng.choice(256, size=int(rng.integers(1, 5)), replace=False)]
+    conts = [rng.integers(0, 12, size=int(rng.integers(1, 300)), dtype=np.uint8).tobytes() for _ in range(int(rng.integers(1, 6)))]
+    while n < total:
+        r = rng.random()
+        if r < 0.45:
+            ln = int(rng.choice([1, 2, 3, 4, 5, 8, 16, 40, 100, 257, 258, 259, 300, 516, 1000, 1024 + 258, 4096 + 260, 9000, 33000]))
+            b = bytes([alpha[int(rng.integers(0, len(alpha)))]]) * ln
+        elif r < 0.75:
+            b = conts[int(rng.integers(0, len(conts)))][:int(rng.integers(1, 300))]
+        elif r < 0.9:
+            b = rng.integers(0, int(rng.choice([2, 4, 16, 256])), size=int(rng.integers(1, 400)), dtype=np.uint8).tobytes()
+        else:
+            c = alpha[0]
+            h = ((c << 10) ^ (c << 5) ^ c) & 0x7FFF
+            a_, b_ = int(rng.integers(0, 256)), int(rng.integers(0, 256))
+            c_ = h ^ ((a_ << 10) & 0x7FFF) ^ (b_ << 5)
+            b = bytes([a_, b_, c_]) * int(rng.integers(1, 30)) if c_ < 256 else b"xy"
+        parts.append(b)
+        n += len(b)
+    return b"".join(parts)
+
+
+def test_match_finder_fuzz(hostsim):
+    """A fixed sample of the generator behind a 1500-case campaign (no failures): the probe tables as the kernels fill
+    them against zlib's candidate loop, and the staged encoder against libz."""
+    for seed in range(14):
+        data = _fuzz_blob(np.random.default_rng(9000 + seed))
+        src = np.frombuffer(data, dtype=np.uint8)
+        assert hostsim.hs_probe_check(_p(src, C.c_uint8), len(data), None) == 0, seed
+        assert _hs_deflate(hostsim, data) == zlib.compress(data, 9), seed
+
+
 def test_staged_deflate_block_boundaries(hostsim):
     rng = np.random.default_rng(11)
     lits = rng.permutation(np.arange(256, dtype=np.uint8).repeat(200))
