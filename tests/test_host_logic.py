@@ -218,6 +218,21 @@ def test_match_finder_fuzz(hostsim):
         assert _hs_deflate(hostsim, data) == zlib.compress(data, 9), seed
 
 
+def test_huffman_length_overflow(hostsim):
+    """Fibonacci literal frequencies push the unconstrained code depth past 15 bits (and the bit-length tree past 7):
+    gen_bitlen's overflow repair, with the parents read off the order array instead of Dad links, against libz."""
+    rng = np.random.default_rng(0)
+    for trial in range(12):
+        fib = [1, 1]
+        while len(fib) < 17 + trial % 7:
+            fib.append(fib[-1] + fib[-2])
+        syms = rng.choice(256, size=len(fib), replace=False)
+        arr = np.concatenate([np.full(f, s, dtype=np.uint8) for f, s in zip(fib, syms)] * (1 + trial % 3))
+        rng.shuffle(arr)
+        data = arr.tobytes()
+        assert _hs_deflate(hostsim, data) == zlib.compress(data, 9), (trial, len(data))
+
+
 def test_staged_deflate_block_boundaries(hostsim):
     rng = np.random.default_rng(11)
     lits = rng.permutation(np.arange(256, dtype=np.uint8).repeat(200))
