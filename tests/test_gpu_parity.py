@@ -130,6 +130,13 @@ def test_deflate_matches_libz(torch_cuda, native, oracle, synth):
     afters = [[5, 6, 7, 8, 9, 1, 2, 3], [5, 6, 7, 1], [5, 1], [9], list(range(10, 250))]
     blobs += [_runs_blob(rng_r, 200, [0, 0, 7], [258, 300, 517, 1000, 40, 5, 3, 2000, 5000], afters, [1, 2, 5, 30, 300]),
               b"".join(bytes(300 if i % 25 == 24 else int(rng_r.integers(3, 60))) + bytes([5, 6, int(rng_r.integers(1, 4))]) for i in range(600))]
+    for trial in range(6):  # Fibonacci literal frequencies: code depths beyond 15 bits, gen_bitlen's overflow repair
+        fib = [1, 1]
+        while len(fib) < 17 + trial:
+            fib.append(fib[-1] + fib[-2])
+        arr = np.concatenate([np.full(f, s, dtype=np.uint8) for f, s in zip(fib, rng_r.choice(256, size=len(fib), replace=False))] * (1 + trial % 3))
+        rng_r.shuffle(arr)
+        blobs.append(arr.tobytes())
     got = _gpu_deflate(torch_cuda, native, blobs)
     for b, g in zip(blobs, got):
         assert g == zlib.compress(b, 9), len(b)
